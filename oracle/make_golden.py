@@ -1,0 +1,63 @@
+"""Generate the committed fixtures under tests/golden/ (run once, in the build container).
+
+TEST INFRASTRUCTURE ONLY.  Provenance of every fixture:
+  tpod.npz          decoded from /root/reference/data/tpod.RData (the reference's only bundled data,
+                    man/tpod.Rd) with oracle/rdata.py -- real reference data, bit-exact.
+  perm_kat.json     std::shuffle/std::mt19937 marker orders; the first three (p=10) and the p=376 head
+                    are the known answers recorded in SURVEY.md 8a / BASELINE.md 5 (libstdc++ 13).
+  tpod_em.npz       oracle outputs (float32 recipe and float64 recipe) of the six EM solvers on tpod.
+                    ORACLE-DERIVED, NOT REFERENCE-EXECUTED: R/Rcpp/RcppEigen are absent from this image,
+                    so the reference cannot run here ("parity unpinned").
+  tpod_mrr3.npz     oracle MRR3 (float64) outputs on a fixed synthetic 3-trait Y over tpod genotypes.
+Usage:  python oracle/make_golden.py   (needs /root/reference; tests never do)
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import oracle as O  # noqa: E402
+from rdata import read_rdata  # noqa: E402
+
+OUT = os.path.join(HERE, "..", "tests", "golden")
+
+
+def synth_traits(gen, k=3, seed=20261018):
+    rng = np.random.default_rng(seed)
+    p = gen.shape[1]
+    B = rng.normal(size=(p, k)) * (rng.random((p, k)) < 0.1)
+    G = gen @ B
+    return G / G.std(0) + rng.normal(size=(gen.shape[0], k))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    d = read_rdata("/root/reference/data/tpod.RData")
+    y = np.asarray(d["y"], dtype=np.float64)
+    gen = np.asarray(d["gen"])
+    assert gen.shape == (196, 376) and set(np.unique(gen)) == {0, 1, 2}
+    np.savez_compressed(os.path.join(OUT, "tpod.npz"), y=y, gen=gen.astype(np.int8),
+                        fam=np.asarray(d["fam"]).astype(np.int32), chr=np.asarray(d["chr"]).astype(np.int32))
+    kat = {"p10_iters0_2": O.perm(10, 3).tolist(), "p376_iter0_head8": O.perm(376, 1)[0, :8].tolist(),
+           "p376_iter199_head8": O.perm(376, 200)[199, :8].tolist()}
+    json.dump(kat, open(os.path.join(OUT, "perm_kat.json"), "w"), indent=1)
+    genf = gen.astype(np.float64)
+    em = {}
+    for m in O.EM_MODELS:
+        for dbl in (False, True):
+            r = O.em(m, y, genf, use_double=dbl)
+            tag = m + ("_f64" if dbl else "_f32")
+            for key, v in r.items():
+                em[tag + "__" + key] = np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, "tpod_em.npz"), **em)
+    Y = synth_traits(genf)
+    r = O.mrr3(Y, genf)
+    np.savez_compressed(os.path.join(OUT, "tpod_mrr3.npz"), Y=Y, **{k: np.asarray(v) for k, v in r.items()})
+    print("wrote", sorted(os.listdir(OUT)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,121 @@
+// oracle_capi.cpp -- C entry points over bwgr_oracle.hpp for ctypes (tests, smoke, bench CPU arm).
+// TEST INFRASTRUCTURE ONLY: see the header of bwgr_oracle.hpp.  All matrices are column-major.
+#include "bwgr_oracle.hpp"
+
+#include <cstdio>
+
+namespace {
+template <class R>
+void em_run(int model, const float* y, const float* X, int n, int p, float df, float R2, float Pi, float alpha, int it,
+            double* mu, double* b, double* d, double* hat, double* vbv, double* scal, int* its) {
+  std::vector<R> yy(y, y + n);
+  std::vector<R> XX;
+  const R* Xp;
+  if constexpr (sizeof(R) == sizeof(float)) {
+    Xp = reinterpret_cast<const R*>(X);
+  } else {
+    XX.assign(X, X + (size_t)n * p);
+    Xp = XX.data();
+  }
+  orc::EmPar<R> P;
+  P.df = df; P.R2 = R2; P.Pi = Pi; P.alpha = alpha; P.it = it;
+  orc::EmOut<R> o;
+  orc::em_fit<R>(model, yy.data(), Xp, n, p, P, o);
+  *mu = o.mu;
+  for (int j = 0; j < p; j++) b[j] = o.b[j];
+  for (int j = 0; j < p; j++) d[j] = o.d.empty() ? 0.0 : (double)o.d[j];
+  for (int j = 0; j < p; j++) vbv[j] = o.vbv.empty() ? 0.0 : (double)o.vbv[j];
+  for (int i = 0; i < n; i++) hat[i] = o.hat[i];
+  scal[0] = o.Va; scal[1] = o.Ve; scal[2] = o.h2; scal[3] = o.Vg;
+  *its = o.its;
+}
+}  // namespace
+
+extern "C" {
+
+// Cumulative marker orders of sweeps 0..n_iter-1: out[i*p + jj] (Rcpp20260726ai.cpp:329-331).
+int orc_perm(int p, int n_iter, int32_t* out) {
+  orc::Shuffler sh(p);
+  for (int i = 0; i < n_iter; i++) {
+    sh.next(i);
+    std::memcpy(out + (size_t)i * p, sh.order.data(), sizeof(int) * p);
+  }
+  return 0;
+}
+
+// Univariate EM fit. use_double=0: float32 like the reference; 1: same recipe in float64 (to bound
+// float noise).  it<0: the reference's hard-coded sweep count.  scal = {Va, Ve, h2, Vg}.
+int orc_em(int model, int use_double, const float* y, const float* X, int n, int p, float df, float R2, float Pi,
+           float alpha, int it, double* mu, double* b, double* d, double* hat, double* vbv, double* scal, int* its) {
+  if (model < 0 || model > 5) return -1;
+  if (use_double) em_run<double>(model, y, X, n, p, df, R2, Pi, alpha, it, mu, b, d, hat, vbv, scal, its);
+  else em_run<float>(model, y, X, n, p, df, R2, Pi, alpha, it, mu, b, d, hat, vbv, scal, its);
+  return 0;
+}
+
+// Univariate Gibbs fit (float32 state). scal = {vb, ve, h2, MSx}.
+int orc_gibbs(int model, const float* y, const float* X, int n, int p, float it, float bi, float pi, float df, float R2,
+              uint64_t seed, double* mu, double* b, double* d, double* hat, double* vbv, double* scal) {
+  if (model < 0 || model > 3) return -1;
+  orc::GibbsOut<float> o;
+  orc::gibbs_fit<float>(model, y, X, n, p, it, bi, pi, df, R2, seed, o);
+  *mu = o.mu;
+  for (int j = 0; j < p; j++) { b[j] = o.b[j]; d[j] = o.d[j]; vbv[j] = o.vbv[j]; }
+  for (int i = 0; i < n; i++) hat[i] = o.hat[i];
+  scal[0] = o.vb; scal[1] = o.ve; scal[2] = o.h2; scal[3] = o.MSx;
+  return 0;
+}
+
+int orc_kmup(const float* X, int n, int p, float* b, float* d, const float* xx, float* e, const float* L, float Ve,
+             float pi, uint64_t seed, int ratio_form) {
+  orc::Rng rng(seed);
+  orc::kmup(X, n, p, b, d, xx, e, L, Ve, pi, rng, ratio_form != 0);
+  return 0;
+}
+
+// scal = {mu, Ve, Va, cxx}
+int orc_wgr(const double* y, const double* X, int n, int p, int it, int bi, int th, int iv, int de, double pi, double df,
+            double R2, uint64_t seed, int ratio_form, double* b, double* d, double* Vb, double* hat, double* scal) {
+  orc::WgrOut o;
+  orc::wgr(y, X, n, p, it, bi, th, iv != 0, de != 0, pi, df, R2, seed, ratio_form != 0, o);
+  for (int j = 0; j < p; j++) { b[j] = o.b[j]; d[j] = o.d[j]; Vb[j] = o.Vb[j]; }
+  for (int i = 0; i < n; i++) hat[i] = o.hat[i];
+  scal[0] = o.mu; scal[1] = o.Ve; scal[2] = o.Va; scal[3] = o.cxx;
+  return 0;
+}
+
+// MRR3 (f32_variant=0, float64) / MRR3F (f32_variant=1, float32).  par[] in the order of the R
+// signature after (Y,X): maxit,tol,cores,TH,NLfactor,InnerGS,NoInv,HCS,XFA,ACS,NumXFA,R2,gc0,df0,
+// updateMu,weight_prior_h2,weight_prior_gc,PenCor,MinCor,uncorH2below,roundGCupFrom,roundGCupTo,
+// roundGCdownFrom,roundGCdownTo,bucketGCfrom,bucketGCto,DeflateMax,DeflateBy,OneVarB,OneVarE  (30 values).
+// cnv: 3*maxit doubles (cnvB | cnvH2 | cnvV, each maxit long, first *its valid).
+int orc_mrr3(int f32_variant, const double* Y, const double* X, int n, int k, int p, const double* par, double* mu,
+             double* b, double* hat, double* h2, double* GC, double* vb, double* ve, double* MSx, double* cnv,
+             double* W, int* its) {
+  auto run = [&](auto tag) {
+    using R = decltype(tag);
+    orc::MrrPar<R> P;
+    int q = 0;
+    P.maxit = (int)par[q++]; P.tol = (R)par[q++]; q++; P.TH = par[q++] != 0; P.NLfactor = (R)par[q++];
+    P.InnerGS = par[q++] != 0; P.NoInv = par[q++] != 0; P.HCS = par[q++] != 0; P.XFA = par[q++] != 0; P.ACS = par[q++] != 0;
+    P.NumXFA = (int)par[q++]; P.R2 = (R)par[q++]; P.gc0 = (R)par[q++]; P.df0 = (R)par[q++]; P.updateMu = par[q++] != 0;
+    P.weight_prior_h2 = (R)par[q++]; P.weight_prior_gc = (R)par[q++]; P.PenCor = (R)par[q++]; P.MinCor = (R)par[q++];
+    P.uncorH2below = (R)par[q++]; P.roundGCupFrom = (R)par[q++]; P.roundGCupTo = (R)par[q++];
+    P.roundGCdownFrom = (R)par[q++]; P.roundGCdownTo = (R)par[q++]; P.bucketGCfrom = (R)par[q++];
+    P.bucketGCto = (R)par[q++]; P.DeflateMax = (R)par[q++]; P.DeflateBy = (R)par[q++]; P.OneVarB = par[q++] != 0;
+    P.OneVarE = par[q++] != 0;
+    std::vector<R> Yr(Y, Y + (size_t)n * k), Xr(X, X + (size_t)n * p);
+    orc::MrrOut<R> o;
+    orc::mrr3<R>(Yr.data(), Xr.data(), n, k, p, P, f32_variant != 0, o);
+    for (int t = 0; t < k; t++) { mu[t] = o.mu[t]; h2[t] = o.h2[t]; ve[t] = o.ve[t]; MSx[t] = o.MSx[t]; }
+    for (size_t i = 0; i < (size_t)p * k; i++) { b[i] = o.b[i]; W[i] = o.W[i]; }
+    for (size_t i = 0; i < (size_t)n * k; i++) hat[i] = o.hat[i];
+    for (int i = 0; i < k * k; i++) { GC[i] = o.GC[i]; vb[i] = o.vb[i]; }
+    for (int i = 0; i < o.its; i++) { cnv[i] = o.cnvB[i]; cnv[P.maxit + i] = o.cnvH2[i]; cnv[2 * P.maxit + i] = o.cnvV[i]; }
+    *its = o.its;
+  };
+  if (f32_variant) run(float{}); else run(double{});
+  return 0;
+}
+
+}  // extern "C"
