@@ -1,0 +1,275 @@
+"""Host-side mirror of the reference's R-facing functions for the marker-effect update loop.
+
+Same names, argument names/defaults and returned list keys as the reference's exports
+(R/RcppExports.R:12-65, :180; R/wgr.R:2-8), implemented over the C ABI of include/bwgr_b200.h.
+`gen` / `X` may be a numpy matrix (float or int8, n x p) or an already loaded `Genotypes` store,
+which removes the per-call n x p conversion the reference pays (src/RcppExports.cpp:115-116).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import EmOut, EmParams, GibbsOut, GibbsParams, check
+
+STORE_I8, STORE_2BIT = 0, 1
+PATH_AUTO, PATH_SMALL_N, PATH_BLOCKED = 0, 1, 2
+_EM = {"emRR": 0, "emBA": 1, "emBB": 2, "emBC": 3, "emBL": 4, "emEN": 5}
+_GIBBS = {"BayesRR": 0, "BayesA": 1, "BayesB": 2, "BayesC": 3}
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Genotypes:
+    """Genotype matrix resident in HBM (int8 column-major or 2-bit packed) behind one bwgr_handle."""
+
+    def __init__(self, X=None, storage=STORE_I8, device=0, path=PATH_AUTO, grid=0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        check(self.lib.bwgr_create(device, C.byref(h)))
+        self.h = h
+        self.n = self.p = 0
+        check(self.lib.bwgr_set_tuning(self.h, -1, path, grid))
+        if X is not None:
+            self.load(X, storage)
+
+    def load(self, X, storage=STORE_I8):
+        if hasattr(X, "data_ptr"):  # torch tensor
+            import torch
+            assert X.dtype == torch.int8 and X.dim() == 2
+            # torch is row-major: a (p, n) contiguous tensor is the column-major n x p matrix
+            p, n = X.shape
+            assert X.is_contiguous()
+            fn = self.lib.bwgr_geno_load_i8_device if X.is_cuda else self.lib.bwgr_geno_load_i8
+            check(fn(self.h, C.c_void_p(X.data_ptr()), n, p, n, storage))
+        else:
+            X = np.asarray(X)
+            n, p = X.shape
+            if X.dtype == np.int8:
+                Xf = np.asfortranarray(X)
+                check(self.lib.bwgr_geno_load_i8(self.h, _ptr(Xf), n, p, n, storage))
+            else:
+                Xf = np.asfortranarray(X, dtype=np.float64)
+                check(self.lib.bwgr_geno_load_f64(self.h, _ptr(Xf), n, p, n, storage))
+        self.n, self.p = int(n), int(p)
+        return self
+
+    def set_tuning(self, block=-1, path=-1, grid=-1):
+        check(self.lib.bwgr_set_tuning(self.h, block, path, grid))
+
+    def set_stream(self, stream_ptr):
+        check(self.lib.bwgr_set_stream(self.h, C.c_void_p(stream_ptr)))
+
+    def info(self):
+        n, p, ldb, tot = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        st = C.c_int()
+        check(self.lib.bwgr_geno_info(self.h, C.byref(n), C.byref(p), C.byref(ldb), C.byref(st), C.byref(tot)))
+        return {"n": n.value, "p": p.value, "ld_bytes": ldb.value, "storage": st.value, "total_bytes": tot.value}
+
+    def unpack(self):
+        out = np.empty((self.n, self.p), dtype=np.int8, order="F")
+        check(self.lib.bwgr_geno_unpack_i8(self.h, _ptr(out)))
+        return out
+
+    def raw(self):
+        out = np.empty(self.info()["total_bytes"], dtype=np.uint8)
+        check(self.lib.bwgr_geno_raw(self.h, _ptr(out)))
+        return out
+
+    def stats(self):
+        xx, sx = np.empty(self.p), np.empty(self.p)
+        check(self.lib.bwgr_geno_stats(self.h, _ptr(xx), _ptr(sx)))
+        return xx, sx
+
+    def gram_blocks(self, perm, block=128):
+        perm = np.ascontiguousarray(perm, dtype=np.int32)
+        nb = (self.p + block - 1) // block
+        out = np.empty((nb, block, block), dtype=np.int32)
+        check(self.lib.bwgr_debug_gram(self.h, _ptr(perm), block, _ptr(out)))
+        return out
+
+    def launch_count(self):
+        return int(self.lib.bwgr_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bwgr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def _store(gen, **kw):
+    if isinstance(gen, Genotypes):
+        return gen, False
+    return Genotypes(gen, **kw), True
+
+
+class _EmBuffers:
+    def __init__(self, n, p, nsys):
+        self.mu = np.zeros(nsys)
+        self.b = np.zeros((p, nsys), order="F")
+        self.d = np.zeros((p, nsys), order="F")
+        self.hat = np.zeros((n, nsys), order="F")
+        self.vb = np.zeros((p, nsys), order="F")
+        self.scal = np.zeros((4, nsys), order="F")
+        self.its = np.zeros(nsys, dtype=np.int32)
+        self.c = EmOut(_ptr(self.mu), _ptr(self.b), _ptr(self.d), _ptr(self.hat), _ptr(self.vb), _ptr(self.scal),
+                       _ptr(self.its))
+
+    def result(self, model, squeeze):
+        def v(a):
+            return a[:, 0].copy() if squeeze else a
+
+        def s(a):
+            return float(a[0]) if squeeze else a.copy()
+
+        Va, Ve, h2, Vg = (self.scal[i] for i in range(4))
+        out = {"mu": s(self.mu), "b": v(self.b), "hat": v(self.hat)}
+        if model == "emRR":
+            out.update(Va=s(Va), Ve=s(Ve), h2=s(h2))
+        elif model == "emBA":
+            out.update(Vb=v(self.vb), Ve=s(Ve), h2=s(h2))
+        elif model == "emBB":
+            out.update(d=v(self.d), Vb=v(self.vb), Ve=s(Ve), h2=s(h2))
+        elif model == "emBC":
+            out.update(d=v(self.d), Vg=s(Vg), Va=s(Va), Ve=s(Ve), h2=s(h2))
+        elif model == "emBL":
+            out.update(h2=s(h2))
+        elif model == "emEN":
+            out.update(Va=s(Va), Ve=s(Ve), h2=s(h2))
+        out["its"] = int(self.its[0]) if squeeze else self.its.copy()
+        return out
+
+
+def _em_params(model, y, nsys, it, df, R2, Pi, alpha, row_mask, n):
+    mask = None
+    if row_mask is not None:
+        mask = np.asfortranarray(np.asarray(row_mask).reshape(n, nsys, order="F") != 0, dtype=np.uint8)
+    par = EmParams(_EM[model], nsys, it, df, R2, Pi, alpha, _ptr(mask))
+    return par, mask
+
+
+def em_fit(model, y, gen, df=10.0, R2=0.5, Pi=0.75, alpha=0.02, it=-1, row_mask=None, **store_kw):
+    """Generic entry: y is n (one fit) or n x k (k independent fits sharing gen)."""
+    g, own = _store(gen, **store_kw)
+    try:
+        y = np.asarray(y, dtype=np.float64)
+        squeeze = y.ndim == 1
+        Y = np.asfortranarray(y.reshape(g.n, -1, order="F"))
+        nsys = Y.shape[1]
+        par, mask = _em_params(model, Y, nsys, it, df, R2, Pi, alpha, row_mask, g.n)
+        buf = _EmBuffers(g.n, g.p, nsys)
+        check(g.lib.bwgr_em_fit(g.h, C.byref(par), _ptr(Y), C.byref(buf.c)))
+        del mask
+        return buf.result(model, squeeze)
+    finally:
+        if own:
+            g.close()
+
+
+class EmStepper:
+    """begin / sweeps / end split of one EM fit, for timing sweeps with everything resident."""
+
+    def __init__(self, model, y, gen, df=10.0, R2=0.5, Pi=0.75, alpha=0.02):
+        self.g = gen
+        self.model = model
+        y = np.asarray(y, dtype=np.float64)
+        self.squeeze = y.ndim == 1
+        self.Y = np.asfortranarray(y.reshape(gen.n, -1, order="F"))
+        self.par, self._mask = _em_params(model, self.Y, self.Y.shape[1], -1, df, R2, Pi, alpha, None, gen.n)
+        check(gen.lib.bwgr_em_begin(gen.h, C.byref(self.par), _ptr(self.Y)))
+
+    def sweeps(self, k=1):
+        check(self.g.lib.bwgr_em_sweeps(self.g.h, k))
+
+    def end(self):
+        buf = _EmBuffers(self.g.n, self.g.p, self.Y.shape[1])
+        check(self.g.lib.bwgr_em_end(self.g.h, C.byref(buf.c)))
+        return buf.result(self.model, self.squeeze)
+
+
+def emRR(y, gen, df=10, R2=0.5, **kw):
+    return em_fit("emRR", y, gen, df=df, R2=R2, **kw)
+
+
+def emBA(y, gen, df=10, R2=0.5, **kw):
+    return em_fit("emBA", y, gen, df=df, R2=R2, **kw)
+
+
+def emBB(y, gen, df=10, R2=0.5, Pi=0.75, **kw):
+    return em_fit("emBB", y, gen, df=df, R2=R2, Pi=Pi, **kw)
+
+
+def emBC(y, gen, df=10, R2=0.5, Pi=0.75, **kw):
+    return em_fit("emBC", y, gen, df=df, R2=R2, Pi=Pi, **kw)
+
+
+def emBL(y, gen, R2=0.5, alpha=0.02, **kw):
+    return em_fit("emBL", y, gen, R2=R2, alpha=alpha, **kw)
+
+
+def emEN(y, gen, R2=0.5, alpha=0.02, **kw):
+    return em_fit("emEN", y, gen, R2=R2, alpha=alpha, **kw)
+
+
+def gibbs_fit(model, y, X, it=1500, bi=500, pi=0.95, df=5.0, R2=0.5, seed=1, nchains=1, **store_kw):
+    g, own = _store(X, **store_kw)
+    try:
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        nc = int(nchains)
+        mu = np.zeros(nc)
+        b = np.zeros((g.p, nc), order="F")
+        d = np.zeros((g.p, nc), order="F")
+        hat = np.zeros((g.n, nc), order="F")
+        vb = np.zeros((g.p, nc), order="F")
+        scal = np.zeros((4, nc), order="F")
+        par = GibbsParams(_GIBBS[model], nc, int(it), int(bi), pi, df, R2, seed)
+        out = GibbsOut(_ptr(mu), _ptr(b), _ptr(d), _ptr(hat), _ptr(vb), _ptr(scal))
+        check(g.lib.bwgr_gibbs_fit(g.h, C.byref(par), _ptr(y), C.byref(out)))
+        sq = nc == 1
+
+        def v(a):
+            return a[:, 0].copy() if sq else a
+
+        res = {"mu": float(mu[0]) if sq else mu, "b": v(b), "hat": v(hat),
+               "ve": float(scal[1, 0]) if sq else scal[1].copy(), "h2": float(scal[2, 0]) if sq else scal[2].copy(),
+               "MSx": float(scal[3, 0]) if sq else scal[3].copy()}
+        if model in ("BayesA", "BayesB"):
+            res["vb"] = v(vb)
+        else:
+            res["vb"] = float(scal[0, 0]) if sq else scal[0].copy()
+        if model in ("BayesB", "BayesC"):
+            res["d"] = v(d)
+        return res
+    finally:
+        if own:
+            g.close()
+
+
+def BayesRR(y, X, it=1500, bi=500, df=5, R2=0.5, **kw):
+    return gibbs_fit("BayesRR", y, X, it=it, bi=bi, df=df, R2=R2, **kw)
+
+
+def BayesA(y, X, it=1500, bi=500, df=5, R2=0.5, **kw):
+    return gibbs_fit("BayesA", y, X, it=it, bi=bi, df=df, R2=R2, **kw)
+
+
+def BayesB(y, X, it=1500, bi=500, pi=0.95, df=5, R2=0.5, **kw):
+    return gibbs_fit("BayesB", y, X, it=it, bi=bi, pi=pi, df=df, R2=R2, **kw)
+
+
+def BayesC(y, X, it=1500, bi=500, pi=0.95, df=5, R2=0.5, **kw):
+    return gibbs_fit("BayesC", y, X, it=it, bi=bi, pi=pi, df=df, R2=R2, **kw)

@@ -1,0 +1,844 @@
+// capi.cu -- the thin extern "C" layer of include/bwgr_b200.h: handle, genotype store, and the host
+// orchestration of a fit (what stays C++ behind Rcpp in the drop-in).
+//
+// Host responsibilities, all O(p) or O(n) per sweep and overlapped with the GPU through the stream:
+//   * the marker order of every shuffled solver -- std::shuffle(order, std::mt19937(sweep)), cumulative
+//     (Rcpp20260726ai.cpp:329-331) -- produced with libstdc++ itself and uploaded ahead of use;
+//   * initial hyper-parameters per solver, in float like the reference;
+//   * choosing the kernel family (small-n CTA-per-system vs blocked whole-GPU sweep).
+// There is deliberately no CPU compute path: every sweep runs in the CUDA kernels of this directory.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/bwgr_b200.h"
+#include "kernels.h"
+
+using namespace bwgr;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) return fail(BWGR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (!count) return cudaSuccess;
+    return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+constexpr int kPermRing = 8;
+
+struct Fit {
+  bool active = false;
+  int model = 0;        // device Model id
+  int nsys = 0;
+  int it_target = 0;    // sweeps requested by the reference recipe
+  int sweeps_issued = 0;
+  bool shuffled = true; // EM: shuffled order; Gibbs: natural
+  bool blocked = false;
+  bool masked = false;
+  int rows_per_cta = 0, grid = 0, nblocks = 0;
+  bool gram_cached = false;
+  uint64_t seed = 0;
+  std::vector<SysScalars> sc0;
+  std::vector<float> vy, MSx, cxx;      // per system constants needed for outputs
+  std::vector<int> order;               // host marker order (cumulative shuffles)
+  DevBuf<float> y, e, b, d, vbv, b_prev, B, D, VBv, xx_sys, gram, work;
+  DevBuf<uint8_t> mask;
+  DevBuf<SysScalars> sc;
+  DevBuf<int> perm;                     // [kPermRing][p]
+  DevBuf<long long> gacc;
+  DevBuf<unsigned int> bar;
+  int* h_perm = nullptr;                // pinned [kPermRing][p]
+  cudaEvent_t perm_free[kPermRing] = {};
+  bool perm_ev_valid[kPermRing] = {};
+  void reset() {
+    active = false;
+    if (h_perm) { cudaFreeHost(h_perm); h_perm = nullptr; }
+    for (int i = 0; i < kPermRing; i++)
+      if (perm_free[i]) { cudaEventDestroy(perm_free[i]); perm_free[i] = nullptr; perm_ev_valid[i] = false; }
+  }
+};
+
+}  // namespace
+
+struct bwgr_handle {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  int num_sms = 0;
+  size_t smem_optin = 0;
+  // genotype store
+  DevBuf<int8_t> x8_own;
+  const int8_t* x8 = nullptr;
+  DevBuf<uint8_t> x2;
+  int64_t n = 0, p = 0, ld = 0, ldb = 0;
+  int storage = BWGR_STORE_I8;
+  DevBuf<long long> xx_i, sx_i;
+  DevBuf<float> xx_f;
+  std::vector<double> h_xx, h_sx;
+  DevBuf<int> err;
+  // tuning
+  int path = BWGR_PATH_AUTO, grid = 0;
+  int gram_simt = 0;
+  int64_t launches = 0;
+  Fit fit;
+
+  GenoView view() const {
+    GenoView g;
+    g.x8 = x8; g.x2 = x2.p; g.ld = ld; g.ldb = ldb; g.n = (int)n; g.p = (int)p;
+    g.storage = storage;
+    return g;
+  }
+};
+
+namespace {
+
+int check_err_flag(bwgr_handle* h, const char* where) {
+  int flag = 0;
+  CU(cudaMemcpyAsync(&flag, h->err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (flag) {
+    cudaMemsetAsync(h->err.p, 0, sizeof(int), h->stream);
+    const char* what = flag == 1 ? "non-integer or out-of-range genotype" : flag == 2 ? "tensor-core pipeline watchdog"
+                       : flag == 3 ? "grid barrier watchdog" : flag == 4 ? "fixed-point range of g exceeded" : "device error";
+    return fail(flag == 1 ? BWGR_ERR_ARG : BWGR_ERR_NUMERIC, "%s: %s", where, what);
+  }
+  return 0;
+}
+
+int finish_store(bwgr_handle* h, int storage) {
+  // column statistics from the int8 copy, then optional 2-bit packing
+  GenoView g8 = h->view();
+  g8.storage = 0;
+  if (h->xx_i.alloc(h->p) != cudaSuccess || h->sx_i.alloc(h->p) != cudaSuccess || h->xx_f.alloc(h->p) != cudaSuccess)
+    return fail(BWGR_ERR_CUDA, "cudaMalloc(stats) failed");
+  launch_col_stats(g8, h->xx_i.p, h->sx_i.p, h->stream);
+  h->launches++;
+  std::vector<long long> xx(h->p), sx(h->p);
+  CU(cudaMemcpyAsync(xx.data(), h->xx_i.p, sizeof(long long) * h->p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(sx.data(), h->sx_i.p, sizeof(long long) * h->p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->h_xx.assign(xx.begin(), xx.end());
+  h->h_sx.assign(sx.begin(), sx.end());
+  std::vector<float> xf(h->p);
+  for (int64_t j = 0; j < h->p; j++) xf[j] = (float)xx[j];
+  CU(cudaMemcpyAsync(h->xx_f.p, xf.data(), sizeof(float) * h->p, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->storage = BWGR_STORE_I8;
+  if (storage == BWGR_STORE_2BIT) {
+    h->ldb = h->ld / 4;
+    if (h->x2.alloc((size_t)h->ldb * h->p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(2-bit store) failed");
+    launch_pack_2bit(h->x8, h->ld, (int)h->n, (int)h->p, h->x2.p, h->ldb, h->err.p, h->stream);
+    h->launches++;
+    int rc = check_err_flag(h, "bwgr_geno_load (2-bit needs codes {0,1,2})");
+    if (rc) { h->x2.release(); return rc; }
+    h->storage = BWGR_STORE_2BIT;
+    h->x8_own.release();  // the 2-bit store is the only copy kept in HBM
+    h->x8 = nullptr;
+  }
+  return 0;
+}
+
+int prepare_store(bwgr_handle* h, int64_t n, int64_t p, int storage) {
+  if (!h) return fail(BWGR_ERR_ARG, "null handle");
+  if (n < 2 || p < 1 || n > (int64_t)1 << 30 || p > (int64_t)1 << 30) return fail(BWGR_ERR_ARG, "bad shape n=%lld p=%lld", (long long)n, (long long)p);
+  if (storage != BWGR_STORE_I8 && storage != BWGR_STORE_2BIT) return fail(BWGR_ERR_ARG, "bad storage %d", storage);
+  CU(cudaSetDevice(h->device));
+  h->fit.reset();
+  h->x2.release();
+  h->n = n; h->p = p;
+  h->ld = (n + 127) / 128 * 128;
+  h->ldb = 0;
+  if (h->x8_own.alloc((size_t)h->ld * p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(%lld bytes) for genotypes failed", (long long)(h->ld * p));
+  h->x8 = h->x8_own.p;
+  return 0;
+}
+
+// ---- host-side helpers that mirror the reference's float arithmetic -------------------------------
+float fvar_f(const std::vector<float>& x) {  // fvar, Rcpp20260726ai.cpp:7-9 (sums in double, rounded once)
+  double m = 0;
+  for (float v : x) m += v;
+  const float mean = (float)(m / (double)x.size());
+  double s = 0;
+  for (float v : x) { const float t = v - mean; s += (double)t * t; }
+  return (float)s / (float)(x.size() - 1);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bwgr_last_error(void) { return g_err.c_str(); }
+int bwgr_version(void) { return 100; }
+
+int bwgr_create(int device, bwgr_handle** out) {
+  if (!out) return fail(BWGR_ERR_ARG, "out is NULL");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(BWGR_ERR_CUDA, "no CUDA device: this library has no CPU path");
+  if (device < 0 || device >= count) return fail(BWGR_ERR_ARG, "device %d out of range (%d devices)", device, count);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(BWGR_ERR_UNSUPPORTED, "device %d is sm_%d%d; this build targets sm_100a (B200) only", device, prop.major, prop.minor);
+  bwgr_handle* h = new bwgr_handle();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(BWGR_ERR_CUDA, "cudaStreamCreate failed"); }
+  h->stream = h->own_stream;
+  if (h->err.alloc(1) != cudaSuccess) { delete h; return fail(BWGR_ERR_CUDA, "cudaMalloc failed"); }
+  cudaMemset(h->err.p, 0, sizeof(int));
+  const char* gs = getenv("BWGR_GRAM");
+  h->gram_simt = gs && !strcmp(gs, "simt");
+  *out = h;
+  return 0;
+}
+
+void bwgr_destroy(bwgr_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  h->fit.reset();
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int bwgr_set_stream(bwgr_handle* h, void* s) {
+  if (!h) return fail(BWGR_ERR_ARG, "null handle");
+  CU(cudaStreamSynchronize(h->stream));
+  h->stream = s ? reinterpret_cast<cudaStream_t>(s) : h->own_stream;
+  return 0;
+}
+
+int bwgr_set_tuning(bwgr_handle* h, int block, int path, int grid) {
+  if (!h) return fail(BWGR_ERR_ARG, "null handle");
+  if (block >= 0 && block != kBlk) return fail(BWGR_ERR_UNSUPPORTED, "only block=%d is built", kBlk);
+  if (path >= 0) {
+    if (path > BWGR_PATH_BLOCKED) return fail(BWGR_ERR_ARG, "bad path %d", path);
+    h->path = path;
+  }
+  if (grid >= 0) h->grid = grid;
+  return 0;
+}
+
+int64_t bwgr_launch_count(bwgr_handle* h) { return h ? h->launches : 0; }
+
+// ---- genotype store ---------------------------------------------------------------------------------
+int bwgr_geno_load_f64(bwgr_handle* h, const double* X, int64_t n, int64_t p, int64_t ld, int storage) {
+  if (!X || ld < n) return fail(BWGR_ERR_ARG, "bad X / ld");
+  int rc = prepare_store(h, n, p, storage);
+  if (rc) return rc;
+  // stream the R matrix through a bounded staging buffer (n x p doubles may not fit beside the store)
+  const int64_t chunk_cols = std::max<int64_t>(1, std::min<int64_t>(p, ((int64_t)256 << 20) / (8 * n)));
+  DevBuf<double> stage;
+  if (stage.alloc((size_t)chunk_cols * n) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(staging) failed");
+  const int lo = storage == BWGR_STORE_2BIT ? 0 : -128, hi = storage == BWGR_STORE_2BIT ? 2 : 127;
+  for (int64_t j0 = 0; j0 < p; j0 += chunk_cols) {
+    const int64_t pc = std::min(chunk_cols, p - j0);
+    CU(cudaMemcpy2DAsync(stage.p, n * 8, X + j0 * ld, ld * 8, n * 8, pc, cudaMemcpyHostToDevice, h->stream));
+    launch_pack_f64(stage.p, n, (int)n, (int)pc, h->x8_own.p + j0 * h->ld, h->ld, lo, hi, h->err.p, h->stream);
+    h->launches++;
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  rc = check_err_flag(h, "bwgr_geno_load_f64");
+  if (rc) return rc;
+  return finish_store(h, storage);
+}
+
+static int load_i8_common(bwgr_handle* h, const int8_t* X, int64_t n, int64_t p, int64_t ld, int storage, cudaMemcpyKind kind) {
+  if (!X || ld < n) return fail(BWGR_ERR_ARG, "bad X / ld");
+  int rc = prepare_store(h, n, p, storage);
+  if (rc) return rc;
+  CU(cudaMemcpy2DAsync(h->x8_own.p, h->ld, X, ld, n, p, kind, h->stream));
+  launch_zero_pad(h->x8_own.p, h->ld, (int)n, (int)p, h->stream);
+  h->launches++;
+  return finish_store(h, storage);
+}
+int bwgr_geno_load_i8(bwgr_handle* h, const int8_t* X, int64_t n, int64_t p, int64_t ld, int storage) {
+  return load_i8_common(h, X, n, p, ld, storage, cudaMemcpyHostToDevice);
+}
+int bwgr_geno_load_i8_device(bwgr_handle* h, const int8_t* dX, int64_t n, int64_t p, int64_t ld, int storage) {
+  return load_i8_common(h, dX, n, p, ld, storage, cudaMemcpyDeviceToDevice);
+}
+
+int bwgr_geno_info(bwgr_handle* h, int64_t* n, int64_t* p, int64_t* ld_bytes, int* storage, int64_t* total_bytes) {
+  if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
+  const int64_t ldb = h->storage == BWGR_STORE_2BIT ? h->ldb : h->ld;
+  if (n) *n = h->n;
+  if (p) *p = h->p;
+  if (ld_bytes) *ld_bytes = ldb;
+  if (storage) *storage = h->storage;
+  if (total_bytes) *total_bytes = ldb * h->p;
+  return 0;
+}
+
+int bwgr_geno_raw(bwgr_handle* h, uint8_t* out) {
+  if (!h || !h->p || !out) return fail(BWGR_ERR_STATE, "no genotypes loaded");
+  const void* src = h->storage == BWGR_STORE_2BIT ? (const void*)h->x2.p : (const void*)h->x8;
+  const int64_t ldb = h->storage == BWGR_STORE_2BIT ? h->ldb : h->ld;
+  CU(cudaMemcpyAsync(out, src, (size_t)ldb * h->p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int bwgr_geno_unpack_i8(bwgr_handle* h, int8_t* out) {
+  if (!h || !h->p || !out) return fail(BWGR_ERR_STATE, "no genotypes loaded");
+  if (h->storage == BWGR_STORE_I8) {
+    CU(cudaMemcpy2DAsync(out, h->n, h->x8, h->ld, h->n, h->p, cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    DevBuf<int8_t> tmp;
+    if (tmp.alloc((size_t)h->ld * h->p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+    launch_unpack_2bit(h->x2.p, h->ldb, (int)h->n, (int)h->p, tmp.p, h->ld, h->stream);
+    h->launches++;
+    CU(cudaMemcpy2DAsync(out, h->n, tmp.p, h->ld, h->n, h->p, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int bwgr_geno_stats(bwgr_handle* h, double* xx, double* sx) {
+  if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
+  if (xx) std::copy(h->h_xx.begin(), h->h_xx.end(), xx);
+  if (sx) std::copy(h->h_sx.begin(), h->h_sx.end(), sx);
+  return 0;
+}
+
+}  // extern "C"
+
+// =====================================================================================================
+// Fit orchestration shared by the EM and Gibbs families
+// =====================================================================================================
+namespace {
+
+struct FitSpec {
+  int model;      // device Model
+  int nsys;
+  bool shuffled;
+  const uint8_t* row_mask;  // host, n x nsys or null
+  float df, R2, Pi, alpha, pi;
+  int it, bi;
+  uint64_t seed;
+};
+
+int choose_path(bwgr_handle* h, const FitSpec& s, bool* blocked) {
+  const GenoView g = h->view();
+  const bool small_ok = small_n_fits(g, s.row_mask != nullptr, h->smem_optin);
+  const int grid = h->grid > 0 ? std::min(h->grid, h->num_sms) : h->num_sms;
+  const int64_t rows = ((h->ld + grid - 1) / grid + 15) / 16 * 16;
+  const bool blocked_ok = h->storage == BWGR_STORE_I8 && !s.row_mask && s.nsys <= 32 && rows <= 512 &&
+                          sweep_blocked_smem((int)rows, s.nsys) <= h->smem_optin;
+  if (h->path == BWGR_PATH_SMALL_N) {
+    if (!small_ok) return fail(BWGR_ERR_UNSUPPORTED, "small-n path: residual of n=%lld does not fit one SM", (long long)h->n);
+    *blocked = false;
+  } else if (h->path == BWGR_PATH_BLOCKED) {
+    if (!blocked_ok) return fail(BWGR_ERR_UNSUPPORTED, "blocked path needs the int8 store, no row mask, nsys<=32 and n <= 512 rows x grid");
+    *blocked = true;
+  } else {
+    const bool prefer_small = small_ok && (s.row_mask || s.nsys >= 8 || h->n <= 1024);
+    if (prefer_small) *blocked = false;
+    else if (blocked_ok) *blocked = true;
+    else if (small_ok) *blocked = false;
+    else return fail(BWGR_ERR_UNSUPPORTED, "no kernel family fits n=%lld nsys=%d storage=%d", (long long)h->n, s.nsys, h->storage);
+  }
+  return 0;
+}
+
+int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
+  if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
+  if (!y) return fail(BWGR_ERR_ARG, "y is NULL");
+  if (s.nsys < 1 || s.nsys > 4096) return fail(BWGR_ERR_ARG, "bad nsys %d", s.nsys);
+  CU(cudaSetDevice(h->device));
+  Fit& f = h->fit;
+  f.reset();
+  bool blocked = false;
+  int rc = choose_path(h, s, &blocked);
+  if (rc) return rc;
+  const int64_t n = h->n, p = h->p, ld = h->ld;
+  const int ns = s.nsys;
+  f.model = s.model; f.nsys = ns; f.shuffled = s.shuffled; f.blocked = blocked; f.masked = s.row_mask != nullptr;
+  f.sweeps_issued = 0; f.seed = s.seed; f.gram_cached = false;
+  f.it_target = s.it;
+
+  // ---- per-system row masks and column statistics
+  std::vector<float> n_eff(ns, (float)n);
+  std::vector<std::vector<double>> xx_s, sx_s;  // masked systems only
+  if (f.masked) {
+    std::vector<uint8_t> m((size_t)ns * ld, 0);
+    for (int t = 0; t < ns; t++) {
+      int cnt = 0;
+      for (int64_t i = 0; i < n; i++) { const uint8_t v = s.row_mask[(size_t)t * n + i] ? 1 : 0; m[(size_t)t * ld + i] = v; cnt += v; }
+      if (cnt < 2) return fail(BWGR_ERR_ARG, "row_mask of system %d keeps %d rows", t, cnt);
+      n_eff[t] = (float)cnt;
+    }
+    if (f.mask.alloc(m.size()) != cudaSuccess || f.xx_sys.alloc((size_t)ns * p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+    CU(cudaMemcpyAsync(f.mask.p, m.data(), m.size(), cudaMemcpyHostToDevice, h->stream));
+    DevBuf<long long> txx, tsx;
+    if (txx.alloc(p) != cudaSuccess || tsx.alloc(p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+    xx_s.resize(ns); sx_s.resize(ns);
+    std::vector<long long> hx(p), hs(p);
+    std::vector<float> xf(p);
+    for (int t = 0; t < ns; t++) {
+      launch_col_stats_masked(h->view(), f.mask.p + (size_t)t * ld, txx.p, tsx.p, h->stream);
+      h->launches++;
+      CU(cudaMemcpyAsync(hx.data(), txx.p, sizeof(long long) * p, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaMemcpyAsync(hs.data(), tsx.p, sizeof(long long) * p, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      xx_s[t].assign(hx.begin(), hx.end()); sx_s[t].assign(hs.begin(), hs.end());
+      for (int64_t j = 0; j < p; j++) xf[j] = (float)hx[j];
+      CU(cudaMemcpyAsync(f.xx_sys.p + (size_t)t * p, xf.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+    }
+  }
+
+  // ---- initial state per system, float arithmetic
+  f.sc0.assign(ns, SysScalars());
+  f.vy.assign(ns, 0); f.MSx.assign(ns, 0); f.cxx.assign(ns, 0);
+  std::vector<float> hy((size_t)ns * ld, 0.0f), he((size_t)ns * ld, 0.0f);
+  std::vector<float> hvb;  // initial per-marker variance
+  float vbv_init = 1.0f;
+  for (int t = 0; t < ns; t++) {
+    std::vector<float> yt;
+    yt.reserve(n);
+    for (int64_t i = 0; i < n; i++) {
+      const double v = y[(size_t)t * n + i];
+      if (!(v == v)) return fail(BWGR_ERR_ARG, "y contains NaN (man/em.Rd:38 forbids NA in y)");
+      hy[(size_t)t * ld + i] = (float)v;
+      if (!f.masked || s.row_mask[(size_t)t * n + i]) yt.push_back((float)v);
+    }
+    const float nn = n_eff[t];
+    const std::vector<double>& xx = f.masked ? xx_s[t] : h->h_xx;
+    const std::vector<double>& sx = f.masked ? sx_s[t] : h->h_sx;
+    double svx = 0, sxx = 0, tr = 0;
+    for (int64_t j = 0; j < p; j++) {
+      const double v = (xx[j] - sx[j] * sx[j] / (double)nn) / ((double)nn - 1.0);
+      svx += (double)(float)v;
+      sxx += xx[j];
+    }
+    const float sum_vx = (float)svx;
+    const float vy = fvar_f(yt);
+    double sm = 0;
+    for (float v : yt) sm += v;
+    const float mu = (float)(sm / (double)yt.size());
+    SysScalars c;
+    memset(&c, 0, sizeof c);
+    c.mu = mu; c.df = s.df; c.R2 = s.R2; c.alpha = s.alpha; c.vy = vy; c.n_eff = nn; c.pi_mix = s.pi;
+    c.burn = s.bi; c.sweep = 0;
+    const float df = s.df, R2 = s.R2;
+    float Pi = s.Pi;
+    switch (s.model) {
+      case M_EMRR: {  // Rcpp20260726ai.cpp:317-324
+        const float MSx = sum_vx;
+        c.MSx = MSx; c.lmb = MSx; c.Rho = MSx * (1 - R2) / R2; c.ve = 0.5f * vy; c.vb = c.ve / MSx;
+        c.Se = (1 - R2) * (df + 2) * vy; c.Sb = R2 * (df + 2) * vy / MSx;
+        break;
+      }
+      case M_EMBA: {  // :84-97
+        const float MSx = sum_vx;
+        c.MSx = MSx; c.ve = 1; c.Sb = R2 * (df + 2) * vy / MSx; c.Se = (1 - R2) * (df + 2) * vy;
+        vbv_init = 1.0f;
+        break;
+      }
+      case M_EMBB: {  // :135-154
+        if (Pi > 0.5f) Pi = 1 - Pi;
+        const float MSx = sum_vx * Pi;
+        c.MSx = MSx; c.ve = 1; c.Sb = R2 * (df + 2) * vy / MSx; c.Se = (1 - R2) * (df + 2) * vy;
+        c.Pi = Pi; c.Pi0 = (1 - Pi) / Pi;
+        vbv_init = 1.0f;
+        break;
+      }
+      case M_EMBC: {  // :196-213 (ve = Sa, va = Se: sic)
+        if (Pi > 0.5f) Pi = 1 - Pi;
+        const float MSx = sum_vx * Pi * (1 - Pi);
+        c.MSx = MSx; c.Sa = R2 * (df + 2) * vy / MSx; c.Se = (1 - R2) * (df + 2) * vy;
+        c.ve = c.Sa; c.vb = c.Se; c.lmb = c.ve / c.vb; c.Pi = Pi; c.Pi0 = (1 - Pi) / Pi;
+        break;
+      }
+      case M_EMBL: {  // :359-370
+        const float h2 = R2;
+        const float cxx = (float)(sxx / (double)p);
+        c.cxx = cxx;
+        c.lmb1 = cxx * ((1 - h2) / h2) * s.alpha * 0.5f;
+        c.lmb2 = cxx * ((1 - h2) / h2) * (1 - s.alpha);
+        break;
+      }
+      case M_EMEN: {  // :412-419
+        const float cxx = sum_vx * (1 - R2) / R2;
+        c.cxx = cxx; c.Sy = std::sqrt(vy); c.lmb = cxx;
+        c.lmb1 = 0.5f * cxx * s.alpha * c.Sy; c.lmb2 = cxx * (1 - s.alpha);
+        for (int64_t j = 0; j < p; j++) tr += 1.0 / ((double)(float)xx[j] + (double)cxx);
+        c.trAC22 = (float)tr;
+        break;
+      }
+      case M_BRR: case M_BA: case M_BB: {  // :822-827, :598-609, :649-665
+        const float MSx = sum_vx;
+        c.MSx = MSx; c.Sb = R2 * df * vy / MSx; c.Se = (1 - R2) * df * vy; c.ve = vy; c.vb = c.Sb; c.lmb = c.ve / c.vb;
+        c.Pi0 = s.pi / (1.0f - s.pi);
+        vbv_init = c.Sb;
+        break;
+      }
+      case M_BC: {  // :712-726
+        const float MSx = sum_vx;
+        c.MSx = MSx; c.Sb = df * R2 * vy / MSx / (1 - s.pi); c.Se = df * (1 - R2) * vy; c.ve = vy; c.vb = c.Sb;
+        c.lmb = c.ve / c.vb; c.Pi0 = s.pi / (1.0f - s.pi);
+        break;
+      }
+      default: return fail(BWGR_ERR_ARG, "bad model %d", s.model);
+    }
+    c.C = -0.5f / std::sqrt(c.ve);
+    f.sc0[t] = c;
+    f.vy[t] = vy; f.MSx[t] = c.MSx; f.cxx[t] = c.cxx;
+    for (int64_t i = 0; i < n; i++)
+      if (!f.masked || s.row_mask[(size_t)t * n + i]) he[(size_t)t * ld + i] = hy[(size_t)t * ld + i] - mu;
+    if (model_has_vbj(s.model)) hvb.resize((size_t)ns * p), std::fill(hvb.begin() + (size_t)t * p, hvb.begin() + (size_t)(t + 1) * p, vbv_init);
+  }
+
+  // ---- device state
+  const bool gibbs = model_is_gibbs(s.model);
+  if (f.y.alloc((size_t)ns * ld) != cudaSuccess || f.e.alloc((size_t)ns * ld) != cudaSuccess ||
+      f.b.alloc((size_t)ns * p) != cudaSuccess || f.sc.alloc(ns) != cudaSuccess || f.perm.alloc((size_t)kPermRing * p) != cudaSuccess)
+    return fail(BWGR_ERR_CUDA, "cudaMalloc(fit state) failed");
+  if (model_has_d(s.model) && f.d.alloc((size_t)ns * p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  if (model_has_vbj(s.model) && f.vbv.alloc((size_t)ns * p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  if (s.model == M_EMEN && f.b_prev.alloc((size_t)ns * p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  if (gibbs) {
+    if (f.B.alloc((size_t)ns * p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+    CU(cudaMemsetAsync(f.B.p, 0, sizeof(float) * ns * p, h->stream));
+    if (f.d.p) { if (f.D.alloc((size_t)ns * p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed"); CU(cudaMemsetAsync(f.D.p, 0, sizeof(float) * ns * p, h->stream)); }
+    if (f.vbv.p) { if (f.VBv.alloc((size_t)ns * p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed"); CU(cudaMemsetAsync(f.VBv.p, 0, sizeof(float) * ns * p, h->stream)); }
+  }
+  CU(cudaMemcpyAsync(f.y.p, hy.data(), sizeof(float) * hy.size(), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(f.e.p, he.data(), sizeof(float) * he.size(), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemsetAsync(f.b.p, 0, sizeof(float) * ns * p, h->stream));
+  if (f.d.p) CU(cudaMemsetAsync(f.d.p, 0, sizeof(float) * ns * p, h->stream));
+  if (f.vbv.p) CU(cudaMemcpyAsync(f.vbv.p, hvb.data(), sizeof(float) * hvb.size(), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(f.sc.p, f.sc0.data(), sizeof(SysScalars) * ns, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+
+  CU(cudaMallocHost(reinterpret_cast<void**>(&f.h_perm), sizeof(int) * kPermRing * p));
+  for (int i = 0; i < kPermRing; i++) CU(cudaEventCreateWithFlags(&f.perm_free[i], cudaEventDisableTiming));
+  f.order.resize(p);
+  for (int64_t j = 0; j < p; j++) f.order[j] = (int)j;
+
+  if (blocked) {
+    const int grid0 = h->grid > 0 ? std::min(h->grid, h->num_sms) : h->num_sms;
+    f.rows_per_cta = (int)(((ld + grid0 - 1) / grid0 + 15) / 16 * 16);
+    f.grid = (int)((ld + f.rows_per_cta - 1) / f.rows_per_cta);
+    f.nblocks = (int)((p + kBlk - 1) / kBlk);
+    if (f.gram.alloc((size_t)f.nblocks * kBlk * kBlk) != cudaSuccess || f.gacc.alloc((size_t)3 * ns * kBlk) != cudaSuccess || f.bar.alloc(1) != cudaSuccess)
+      return fail(BWGR_ERR_CUDA, "cudaMalloc(blocked workspace) failed");
+  }
+  f.active = true;
+  return 0;
+}
+
+// Fixed-point quantum of g = x'e: a power of two such that 64 x the Cauchy-Schwarz bound stays below 2^50.
+void g_fixed_point(bwgr_handle* h, const Fit& f, float* quantum, float* limit) {
+  double xxmax = 1;
+  for (double v : h->h_xx) xxmax = std::max(xxmax, v);
+  double yy = 0;
+  for (size_t t = 0; t < f.vy.size(); t++) yy = std::max(yy, (double)f.vy[t] * (double)(h->n - 1));
+  const double bound = 64.0 * std::sqrt(xxmax * std::max(yy, 1e-30));
+  int ex;
+  std::frexp(bound, &ex);
+  *quantum = (float)std::ldexp(1.0, ex - 50);
+  *limit = (float)std::ldexp(1.0, ex);
+}
+
+int fit_sweeps(bwgr_handle* h, int nsweeps) {
+  Fit& f = h->fit;
+  if (!h || !f.active) return fail(BWGR_ERR_STATE, "no fit in progress");
+  CU(cudaSetDevice(h->device));
+  const int64_t p = h->p, ld = h->ld;
+  const GenoView g = h->view();
+  float quantum = 1, limit = 1;
+  if (f.blocked) g_fixed_point(h, f, &quantum, &limit);
+  for (int k = 0; k < nsweeps; k++) {
+    const int sweep = f.sweeps_issued;
+    const int slot = sweep % kPermRing;
+    const int* d_perm = nullptr;
+    if (f.shuffled || (f.blocked && !f.gram_cached)) {
+      if (f.perm_ev_valid[slot]) CU(cudaEventSynchronize(f.perm_free[slot]));
+      int* hp = f.h_perm + (size_t)slot * p;
+      if (f.shuffled) std::shuffle(f.order.begin(), f.order.end(), std::mt19937(sweep));
+      memcpy(hp, f.order.data(), sizeof(int) * p);
+      CU(cudaMemcpyAsync(f.perm.p + (size_t)slot * p, hp, sizeof(int) * p, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (f.shuffled) d_perm = f.perm.p + (size_t)slot * p;
+    else if (f.blocked) d_perm = f.perm.p;  // identity order, uploaded once (slot 0)
+    if (f.model == M_EMEN) CU(cudaMemcpyAsync(f.b_prev.p, f.b.p, sizeof(float) * f.nsys * p, cudaMemcpyDeviceToDevice, h->stream));
+    if (f.blocked) {
+      if (f.shuffled || !f.gram_cached) {
+        if (h->gram_simt) launch_gram_simt(g, d_perm, f.nblocks, f.gram.p, 1, h->stream);
+        else launch_gram_tc(g, d_perm, f.nblocks, f.gram.p, 1, h->err.p, h->num_sms, h->stream);
+        h->launches++;
+        f.gram_cached = true;
+      }
+      CU(cudaMemsetAsync(f.gacc.p, 0, sizeof(long long) * 3 * f.nsys * kBlk, h->stream));
+      CU(cudaMemsetAsync(f.bar.p, 0, sizeof(unsigned int), h->stream));
+      SweepArgs a;
+      memset(&a, 0, sizeof a);
+      a.g = g; a.model = f.model; a.nsys = f.nsys; a.perm = d_perm; a.nblocks = f.nblocks; a.gram = f.gram.p;
+      a.e = f.e.p; a.b = f.b.p; a.d = f.d.p; a.vbv = f.vbv.p; a.xx = h->xx_f.p; a.sc = f.sc.p;
+      a.gacc = f.gacc.p; a.bar = f.bar.p; a.g_quantum = quantum; a.g_limit = limit;
+      a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0;
+      a.rows_per_cta = f.rows_per_cta; a.err = h->err.p;
+      launch_sweep_blocked(a, f.grid, h->stream);
+      h->launches++;
+    } else {
+      SmallNArgs a;
+      memset(&a, 0, sizeof a);
+      a.g = g; a.model = f.model; a.nsys = f.nsys; a.perms = d_perm; a.y = f.y.p; a.e = f.e.p; a.b = f.b.p; a.d = f.d.p;
+      a.vbv = f.vbv.p; a.xx = f.masked ? f.xx_sys.p : h->xx_f.p; a.xx_per_sys = f.masked ? 1 : 0; a.mask = f.mask.p;
+      a.sc = f.sc.p; a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0; a.err = h->err.p;
+      launch_small_n(a, h->smem_optin, h->stream);
+      h->launches++;
+    }
+    if (f.shuffled) { CU(cudaEventRecord(f.perm_free[slot], h->stream)); f.perm_ev_valid[slot] = true; }
+    EpilogueArgs ea;
+    memset(&ea, 0, sizeof ea);
+    ea.model = f.model; ea.nsys = f.nsys; ea.n = (int)h->n; ea.p = (int)p; ea.ld = ld; ea.e = f.e.p; ea.y = f.y.p; ea.b = f.b.p;
+    ea.d = f.d.p; ea.vbv = f.vbv.p; ea.b_prev = f.b_prev.p; ea.mask = f.mask.p; ea.sc = f.sc.p; ea.B = f.B.p; ea.D = f.D.p;
+    ea.VBv = f.VBv.p; ea.seed_lo = (uint32_t)f.seed; ea.seed_hi = (uint32_t)(f.seed >> 32); ea.chain0 = 0;
+    launch_epilogue(ea, h->stream);
+    h->launches++;
+    f.sweeps_issued++;
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return fail(BWGR_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(le));
+  }
+  return 0;
+}
+
+// hat = mu + X b for system t, into a device buffer
+int fit_hat(bwgr_handle* h, const float* b_dev, const float* mu_dev, float* hat_dev) {
+  Fit& f = h->fit;
+  const int splits = 64;
+  if (f.work.n < (size_t)splits * h->ld && f.work.alloc((size_t)splits * h->ld) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  launch_gemv_hat(h->view(), b_dev, mu_dev, hat_dev, f.work.p, splits, h->stream);
+  h->launches += 2;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+static int em_spec(const bwgr_em_params* par, FitSpec* s) {
+  if (!par) return fail(BWGR_ERR_ARG, "params NULL");
+  if (par->model < 0 || par->model > 5) return fail(BWGR_ERR_ARG, "bad EM model %d", par->model);
+  s->model = par->model; s->nsys = par->nsys; s->shuffled = true; s->row_mask = par->row_mask;
+  s->df = (float)par->df; s->R2 = (float)par->R2; s->Pi = (float)par->Pi; s->alpha = (float)par->alpha; s->pi = 0;
+  s->it = par->it < 0 ? (par->model == BWGR_EM_EN ? 300 : 200) : par->it;
+  s->bi = 0; s->seed = 0;
+  return 0;
+}
+
+int bwgr_em_begin(bwgr_handle* h, const bwgr_em_params* par, const double* y) {
+  FitSpec s;
+  int rc = em_spec(par, &s);
+  if (rc) return rc;
+  return fit_begin(h, s, y);
+}
+
+int bwgr_em_sweeps(bwgr_handle* h, int nsweeps) {
+  if (!h) return fail(BWGR_ERR_ARG, "null handle");
+  return fit_sweeps(h, nsweeps);
+}
+
+int bwgr_em_end(bwgr_handle* h, bwgr_em_out* out) {
+  if (!h || !h->fit.active) return fail(BWGR_ERR_STATE, "no fit in progress");
+  if (!out) return fail(BWGR_ERR_ARG, "out NULL");
+  Fit& f = h->fit;
+  const int64_t n = h->n, p = h->p, ld = h->ld;
+  const int ns = f.nsys;
+  int rc = check_err_flag(h, "sweep");
+  if (rc) { f.reset(); return rc; }
+  std::vector<SysScalars> sc(ns);
+  CU(cudaMemcpyAsync(sc.data(), f.sc.p, sizeof(SysScalars) * ns, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<float> hb((size_t)ns * p), hd, hv, hh((size_t)ns * n), he;
+  CU(cudaMemcpyAsync(hb.data(), f.b.p, sizeof(float) * hb.size(), cudaMemcpyDeviceToHost, h->stream));
+  if (f.d.p && out->d) { hd.resize((size_t)ns * p); CU(cudaMemcpyAsync(hd.data(), f.d.p, sizeof(float) * hd.size(), cudaMemcpyDeviceToHost, h->stream)); }
+  if (f.vbv.p && out->vb) { hv.resize((size_t)ns * p); CU(cudaMemcpyAsync(hv.data(), f.vbv.p, sizeof(float) * hv.size(), cudaMemcpyDeviceToHost, h->stream)); }
+  if (f.model == M_EMBL) { he.resize((size_t)ns * ld); CU(cudaMemcpyAsync(he.data(), f.e.p, sizeof(float) * he.size(), cudaMemcpyDeviceToHost, h->stream)); }
+  DevBuf<float> hat;
+  if (hat.alloc((size_t)ld) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  for (int t = 0; t < ns; t++) {
+    rc = fit_hat(h, f.b.p + (size_t)t * p, &f.sc.p[t].mu, hat.p);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(hh.data() + (size_t)t * n, hat.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  for (int t = 0; t < ns; t++) {
+    const SysScalars& c = sc[t];
+    if (out->mu) out->mu[t] = c.mu;
+    if (out->its) out->its[t] = c.its;
+    double Va = 0, Ve = c.ve, h2 = 0, Vg = 0;
+    switch (f.model) {
+      case M_EMRR: Va = c.vb; h2 = 1.0f - c.ve / f.vy[t]; break;
+      case M_EMBA: case M_EMBB: h2 = 1.0f - c.ve / f.vy[t]; break;
+      case M_EMBC: Va = c.vb; Vg = c.vb * f.MSx[t]; h2 = 1.0f - c.ve / f.vy[t]; break;
+      case M_EMBL: {
+        std::vector<float> ev;
+        for (int64_t i = 0; i < n; i++) ev.push_back(he[(size_t)t * ld + i]);
+        h2 = 1.0f - fvar_f(ev) / f.vy[t]; Ve = 0; break;
+      }
+      case M_EMEN: { const float va = c.vb * f.cxx[t]; Va = va; h2 = va / (va + c.ve); break; }
+      default: break;
+    }
+    if (out->scal) { out->scal[4 * t + 0] = Va; out->scal[4 * t + 1] = Ve; out->scal[4 * t + 2] = h2; out->scal[4 * t + 3] = Vg; }
+  }
+  if (out->b) for (size_t i = 0; i < hb.size(); i++) out->b[i] = hb[i];
+  if (out->d && !hd.empty()) for (size_t i = 0; i < hd.size(); i++) out->d[i] = hd[i];
+  if (out->vb && !hv.empty()) for (size_t i = 0; i < hv.size(); i++) out->vb[i] = hv[i];
+  if (out->hat) for (size_t i = 0; i < hh.size(); i++) out->hat[i] = hh[i];
+  f.reset();
+  return 0;
+}
+
+int bwgr_em_fit(bwgr_handle* h, const bwgr_em_params* par, const double* y, bwgr_em_out* out) {
+  int rc = bwgr_em_begin(h, par, y);
+  if (rc) return rc;
+  Fit& f = h->fit;
+  if (f.model == M_EMEN) {
+    // convergence is checked on the device each sweep; poll in batches to keep the host off the path
+    int done_all = 0;
+    std::vector<SysScalars> sc(f.nsys);
+    while (f.sweeps_issued < f.it_target && !done_all) {
+      rc = fit_sweeps(h, std::min(4, f.it_target - f.sweeps_issued));
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(sc.data(), f.sc.p, sizeof(SysScalars) * f.nsys, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      done_all = 1;
+      for (auto& c : sc) done_all &= c.done;
+    }
+  } else {
+    rc = fit_sweeps(h, f.it_target);
+    if (rc) return rc;
+  }
+  return bwgr_em_end(h, out);
+}
+
+// ---- Gibbs -------------------------------------------------------------------------------------------
+int bwgr_gibbs_fit(bwgr_handle* h, const bwgr_gibbs_params* par, const double* y, bwgr_gibbs_out* out) {
+  if (!h || !par || !out) return fail(BWGR_ERR_ARG, "null argument");
+  if (par->model < 0 || par->model > 3) return fail(BWGR_ERR_ARG, "bad Gibbs model %d", par->model);
+  if (par->it < 1 || par->bi < 0 || par->bi >= par->it) return fail(BWGR_ERR_ARG, "need 0 <= bi < it");
+  const int nc = par->nchains < 1 ? 1 : par->nchains;
+  const int64_t n = h->n, p = h->p;
+  std::vector<double> yy((size_t)nc * n);
+  for (int c = 0; c < nc; c++) memcpy(yy.data() + (size_t)c * n, y, sizeof(double) * n);
+  FitSpec s;
+  s.model = M_BRR + par->model; s.nsys = nc; s.shuffled = false; s.row_mask = nullptr;
+  s.df = (float)par->df; s.R2 = (float)par->R2; s.Pi = 0; s.alpha = 0; s.pi = (float)par->pi;
+  s.it = par->it; s.bi = par->bi; s.seed = par->seed;
+  int rc = fit_begin(h, s, yy.data());
+  if (rc) return rc;
+  Fit& f = h->fit;
+  rc = fit_sweeps(h, par->it);
+  if (rc) return rc;
+  rc = check_err_flag(h, "gibbs sweep");
+  if (rc) { f.reset(); return rc; }
+  std::vector<SysScalars> sc(nc);
+  CU(cudaMemcpyAsync(sc.data(), f.sc.p, sizeof(SysScalars) * nc, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<float> B((size_t)nc * p), D, V;
+  CU(cudaMemcpyAsync(B.data(), f.B.p, sizeof(float) * B.size(), cudaMemcpyDeviceToHost, h->stream));
+  if (f.D.p) { D.resize((size_t)nc * p); CU(cudaMemcpyAsync(D.data(), f.D.p, sizeof(float) * D.size(), cudaMemcpyDeviceToHost, h->stream)); }
+  if (f.VBv.p) { V.resize((size_t)nc * p); CU(cudaMemcpyAsync(V.data(), f.VBv.p, sizeof(float) * V.size(), cudaMemcpyDeviceToHost, h->stream)); }
+  CU(cudaStreamSynchronize(h->stream));
+  const float MCMC = (float)par->it - (float)par->bi;  // sic (:626): divisor it-bi although i>bi keeps it-bi-1 draws
+  std::vector<float> Bm(B.size()), hh((size_t)nc * n);
+  for (size_t i = 0; i < B.size(); i++) Bm[i] = B[i] / MCMC;
+  DevBuf<float> bdev, mudev, hat;
+  if (bdev.alloc(p) != cudaSuccess || mudev.alloc(1) != cudaSuccess || hat.alloc(h->ld) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  for (int c = 0; c < nc; c++) {
+    const float MU = (float)(sc[c].MU / MCMC);
+    CU(cudaMemcpyAsync(bdev.p, Bm.data() + (size_t)c * p, sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(mudev.p, &MU, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    rc = fit_hat(h, bdev.p, mudev.p, hat.p);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(hh.data() + (size_t)c * n, hat.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const float VE = (float)(sc[c].VE / MCMC), VBs = (float)(sc[c].VB / MCMC);
+    float vg;
+    if (f.VBv.p) { double sv = 0; for (int64_t j = 0; j < p; j++) sv += V[(size_t)c * p + j] / MCMC; vg = (float)sv; }
+    else vg = VBs * f.MSx[c];
+    if (out->mu) out->mu[c] = MU;
+    if (out->scal) { out->scal[4 * c + 0] = VBs; out->scal[4 * c + 1] = VE; out->scal[4 * c + 2] = vg / (vg + VE); out->scal[4 * c + 3] = f.MSx[c]; }
+    if (out->vb) {
+      if (f.VBv.p) for (int64_t j = 0; j < p; j++) out->vb[(size_t)c * p + j] = V[(size_t)c * p + j] / MCMC;
+      else out->vb[c] = VBs;
+    }
+  }
+  if (out->b) for (size_t i = 0; i < Bm.size(); i++) out->b[i] = Bm[i];
+  if (out->d && !D.empty()) for (size_t i = 0; i < D.size(); i++) out->d[i] = D[i] / MCMC;
+  if (out->hat) for (size_t i = 0; i < hh.size(); i++) out->hat[i] = hh[i];
+  f.reset();
+  return 0;
+}
+
+int bwgr_kmup_sweep(bwgr_handle*, double*, double*, const double*, double*, const double*, double, double, uint64_t) {
+  return fail(BWGR_ERR_UNSUPPORTED, "bwgr_kmup_sweep: not built yet");
+}
+int bwgr_wgr_fit(bwgr_handle*, const double*, int, int, int, int, int, double, double, double, uint64_t, double*, double*,
+                 double*, double*, double*) {
+  return fail(BWGR_ERR_UNSUPPORTED, "bwgr_wgr_fit: not built yet");
+}
+int bwgr_mrr3_fit(bwgr_handle*, int, const double*, int, const double*, double*, double*, double*, double*, double*,
+                  double*, double*, double*, double*, double*, int*) {
+  return fail(BWGR_ERR_UNSUPPORTED, "bwgr_mrr3_fit: not built yet");
+}
+
+int bwgr_debug_gram(bwgr_handle* h, const int32_t* perm, int block, int32_t* gram_out) {
+  if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
+  if (block != kBlk) return fail(BWGR_ERR_UNSUPPORTED, "only block=%d is built", kBlk);
+  if (h->storage != BWGR_STORE_I8) return fail(BWGR_ERR_UNSUPPORTED, "Gram kernel needs the int8 store");
+  CU(cudaSetDevice(h->device));
+  const int64_t p = h->p;
+  const int nblocks = (int)((p + kBlk - 1) / kBlk);
+  DevBuf<int> dperm;
+  DevBuf<int32_t> dg;
+  if (dperm.alloc(p) != cudaSuccess || dg.alloc((size_t)nblocks * kBlk * kBlk) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  CU(cudaMemcpyAsync(dperm.p, perm, sizeof(int) * p, cudaMemcpyHostToDevice, h->stream));
+  if (h->gram_simt) launch_gram_simt(h->view(), dperm.p, nblocks, dg.p, 0, h->stream);
+  else launch_gram_tc(h->view(), dperm.p, nblocks, dg.p, 0, h->err.p, h->num_sms, h->stream);
+  h->launches++;
+  CU(cudaMemcpyAsync(gram_out, dg.p, sizeof(int32_t) * dg.n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return check_err_flag(h, "gram");
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+// epilogue.cu -- per-sweep reductions and hyper-parameter updates (K9 of SURVEY 2c), one CTA per system.
+//
+// Restates, in the reference's float arithmetic, the block that follows the marker loop in every solver:
+//   emRR  Rcpp20260726ai.cpp:338-343   emBA :113-117   emBB :171-175   emBC :229-234
+//   emBL  :389-391                     emEN :440-450
+//   BayesRR :839-844   BayesA :620-624   BayesB :683-687   BayesC :743-748
+// Sums over rows / markers are accumulated in double and rounded once (the reference sums in float
+// packets; both are within float reassociation noise of each other).
+#include "kernels.h"
+
+namespace bwgr {
+
+namespace {
+
+__device__ double block_sum(double v, double* sh) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+  if (threadIdx.x < 32) r = warp_sum(r);
+  __syncthreads();
+  if (threadIdx.x == 0) sh[0] = r;
+  __syncthreads();
+  return sh[0];
+}
+
+__global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
+  __shared__ double sh[32];
+  __shared__ float s_eM;
+  __shared__ int s_acc;
+  const int sys = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  SysScalars* scp = a.sc + sys;
+  if (scp->done) return;
+  float* e = a.e + (size_t)sys * a.ld;
+  const float* y = a.y + (size_t)sys * a.ld;
+  float* b = a.b + (size_t)sys * a.p;
+  const float* d = a.d ? a.d + (size_t)sys * a.p : nullptr;
+  const float* vbv = a.vbv ? a.vbv + (size_t)sys * a.p : nullptr;
+  const uint8_t* mask = a.mask ? a.mask + (size_t)sys * a.ld : nullptr;
+  const int model = a.model;
+
+  double se = 0, see = 0, sey = 0, sy = 0;
+  for (int i = tid; i < a.n; i += T) {
+    if (mask && !mask[i]) continue;
+    const double ev = e[i], yv = y[i];
+    se += ev; see += ev * ev; sey += ev * yv; sy += yv;
+  }
+  double sbb = 0, sd = 0, scnv = 0;
+  for (int j = tid; j < a.p; j += T) {
+    const double bj = b[j];
+    sbb += bj * bj;
+    if (d) sd += d[j];
+    if (a.b_prev) scnv += fabs((double)a.b_prev[(size_t)sys * a.p + j] - bj);
+  }
+  se = block_sum(se, sh); see = block_sum(see, sh); sey = block_sum(sey, sh); sy = block_sum(sy, sh);
+  sbb = block_sum(sbb, sh); sd = block_sum(sd, sh); scnv = block_sum(scnv, sh);
+
+  if (tid == 0) {
+    SysScalars s = *scp;
+    const float n = s.n_eff, p = (float)a.p;
+    const float ee = (float)see, bb = (float)sbb;
+    float eM = (float)(se / (double)n);
+    int accumulate = 0;
+    if (!model_is_gibbs(model)) {
+      switch (model) {
+        case M_EMRR:
+          s.vb = (bb + s.Sb) / (p + s.df);
+          s.ve = (ee + s.Se) / (n + s.df);
+          s.lmb = sqrtf(s.Rho * s.ve / s.vb);
+          break;
+        case M_EMBA:
+        case M_EMBB:
+          s.ve = (ee + s.Se) / (n + s.df);
+          break;
+        case M_EMBC:
+          s.ve = (ee + s.Se) / (n + s.df);
+          s.vb = (bb + s.Sa) / (p + s.df) / ((float)(sd / (double)a.p) - s.Pi);
+          s.lmb = s.ve / s.vb;
+          break;
+        case M_EMEN: {
+          const float ey = (float)(sey - (double)eM * sy);  // e (after mean removal) . y
+          s.ve = ey / (n - 1.0f);
+          s.vb = (bb + s.trAC22 * s.ve) / p;
+          const float L = s.ve / s.vb;
+          s.lmb = L;
+          s.lmb1 = 0.5f * L * s.alpha * s.Sy;
+          s.lmb2 = L * (1.0f - s.alpha);
+          s.cnv = (float)scnv;
+          if (s.cnv < 10e-11f) s.done = 1;
+          break;
+        }
+        default: break;  // emBL, M_MRR: mean removal only (M_MRR: none, see below)
+      }
+      s.C = -0.5f / sqrtf(s.ve);
+      if (model == M_MRR) eM = 0.0f;
+      s.its += 1;
+    } else {
+      // Gibbs: intercept draw, then variances (counter = (0xFFFFFFFF, sweep, chain, purpose))
+      const uint32_t chain = (uint32_t)(a.chain0 + sys), sw = (uint32_t)s.sweep;
+      uint32_t c[4] = {0xFFFFFFFFu, sw, chain, 0u};
+      philox4x32_10(c, a.seed_lo, a.seed_hi);
+      float z, z2;
+      box_muller(c[0], c[1], z, z2);
+      eM = eM + sqrtf(s.ve / n) * z;
+      const float ee2 = (float)(see - 2.0 * (double)eM * se + (double)n * (double)eM * (double)eM);
+      const float chi_e = rchisq_philox(n + s.df, 0xFFFFFFFFu, sw, chain, 1u, a.seed_lo, a.seed_hi);
+      if (model == M_BRR || model == M_BC) {
+        const float chi_b = rchisq_philox(p + s.df, 0xFFFFFFFFu, sw, chain, 2u, a.seed_lo, a.seed_hi);
+        s.ve = (ee2 + s.Se) / chi_e;
+        s.vb = (bb + s.Sb) / chi_b;
+        s.lmb = s.ve / s.vb;
+      } else {
+        s.ve = (ee2 + s.Se) / chi_e;
+      }
+      s.C = -0.5f / sqrtf(s.ve);
+      s.mu += 0.0f;
+      if (s.sweep > s.burn) {  // sic: i > bi, divided later by it-bi (:624-627)
+        accumulate = 1;
+        s.MU += (double)(s.mu + eM); s.VE += (double)s.ve; s.VB += (double)s.vb;
+        s.post_count += 1;
+      }
+    }
+    s.mu += eM;
+    s.sweep += 1;
+    *scp = s;
+    s_eM = eM;
+    s_acc = accumulate;
+  }
+  __syncthreads();
+  const float eM = s_eM;
+  if (eM != 0.0f)
+    for (int i = tid; i < a.n; i += T) {
+      if (mask && !mask[i]) continue;
+      e[i] -= eM;
+    }
+  if (s_acc && a.B) {
+    float* B = a.B + (size_t)sys * a.p;
+    for (int j = tid; j < a.p; j += T) B[j] += b[j];
+    if (a.D && d) { float* D = a.D + (size_t)sys * a.p; for (int j = tid; j < a.p; j += T) D[j] += d[j]; }
+    if (a.VBv && vbv) { float* V = a.VBv + (size_t)sys * a.p; for (int j = tid; j < a.p; j += T) V[j] += vbv[j]; }
+  }
+}
+
+}  // namespace
+
+void launch_epilogue(const EpilogueArgs& a, cudaStream_t st) { epilogue_kernel<<<a.nsys, 1024, 0, st>>>(a); }
+
+}  // namespace bwgr

@@ -1,0 +1,254 @@
+// gram_tc.cu -- Gram blocks X_B' X_B on the 5th-gen tensor cores (K6 of SURVEY 2c; not in the reference,
+// required by the blocked exact Gauss-Seidel reformulation).
+//
+// For every block of 128 markers (in this sweep's order) G = X_B' X_B is a 128 x 128 x n int8 GEMM with
+// exact int32 accumulation: tcgen05.mma kind::i8, M = N = 128, K = 32 per instruction, accumulator in
+// TMEM.  A and B are the SAME shared-memory tile (marker-major, K = rows contiguous), staged as the
+// canonical K-major SWIZZLE_128B layout: row m of the tile holds 128 consecutive genotype rows of marker m,
+// 16-byte chunk c stored at chunk (c ^ (m & 7)); 8-row groups are 1024 B apart (SBO = 1024).
+// Columns of a block are scattered in HBM when the order is shuffled (emRR & co, Rcpp20260726ai.cpp:331),
+// so the tile is gathered with 16-byte cp.async (8 consecutive lanes = one 128-byte line of one column).
+//
+// Warp roles (288 threads): warps 0-3 gather (cp.async producer), warp 4 issues the MMAs (one elected
+// lane) and owns the TMEM allocation, warps 5-8 drain the accumulator (tcgen05.ld -> st.global).
+// Two accumulator stages (2 x 128 TMEM columns) overlap the drain of block i with the MMAs of block i+1.
+// One CTA per SM, persistent over blocks.  HBM traffic: every genotype byte is read exactly once.
+#include "kernels.h"
+
+namespace bwgr {
+
+namespace {
+
+constexpr int kStages = 6;
+constexpr int kTileBytes = 128 * 128;
+constexpr int kLag = 3;  // cp.async groups kept in flight per producer thread
+constexpr uint32_t kSpinLimit = 1u << 22;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug must not hang the GPU (it sets *err and lets the kernel drain).
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0; spin < kSpinLimit; spin++) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return true;
+  }
+  atomicExch(err, 2);
+  return false;
+}
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, 16 B units
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major) = 16 B
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+
+// kind::i8, D = S32, A = B = signed int8, both K-major, M = 128, N = 128.
+constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct GramSmem {
+  uint64_t full[kStages], empty[kStages], tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* __restrict__ perm, int nblocks,
+                                                         int32_t* __restrict__ gram, int out_f32, int* err) {
+  extern __shared__ unsigned char smem_raw[];
+  // tiles first (1024 B aligned for SWIZZLE_128B), bookkeeping after them
+  unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  GramSmem* S = reinterpret_cast<GramSmem*>(tiles + kStages * kTileBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkt = (int)(g.ld >> 7);  // K tiles of 128 rows (ld is a multiple of 128)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; s++) { mbar_init(&S->full[s], 128); mbar_init(&S->empty[s], 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(&S->tmem_full[s], 1); mbar_init(&S->tmem_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&S->tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = S->tmem_base;
+
+  if (warp < 4) {
+    // ===================== producer: gather tiles with cp.async =====================
+    const int t = threadIdx.x;  // 0..127
+    uint32_t it = 0;            // tile counter (runs over blocks and K tiles)
+    bool ok = true;
+    for (int blk = blockIdx.x; blk < nblocks && ok; blk += gridDim.x) {
+      const int8_t* colp[8];
+      uint32_t nbytes[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int m = i * 16 + (t >> 3);
+        const int pos = blk * 128 + m;
+        const bool valid = pos < g.p;
+        const int j = valid ? perm[pos] : 0;
+        colp[i] = g.x8 + (int64_t)j * g.ld + ((t & 7) << 4);
+        nbytes[i] = valid ? 16u : 0u;
+      }
+      for (int kt = 0; kt < nkt && ok; kt++, it++) {
+        const uint32_t stage = it % kStages, phase = (it / kStages) & 1u;
+        ok = mbar_wait(&S->empty[stage], phase ^ 1u, err);
+        const uint32_t tbase = smem_u32(tiles + stage * kTileBytes);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int m = i * 16 + (t >> 3);
+          const uint32_t dst = tbase + m * 128 + ((((uint32_t)t & 7u) ^ ((uint32_t)m & 7u)) << 4);
+          cp_async16_zfill(dst, colp[i] + (int64_t)kt * 128, nbytes[i]);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (it >= kLag) {
+          asm volatile("cp.async.wait_group %0;" ::"n"(kLag) : "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(&S->full[(it - kLag) % kStages]);
+        }
+      }
+    }
+    // drain: signal the last (up to kLag) tiles
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (uint32_t q = (it > kLag ? it - kLag : 0); q < it; q++) mbar_arrive(&S->full[q % kStages]);
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    uint32_t it = 0, bi = 0;
+    bool ok = true;
+    for (int blk = blockIdx.x; blk < nblocks && ok; blk += gridDim.x, bi++) {
+      const uint32_t as = bi & 1u, aphase = (bi >> 1) & 1u;
+      ok = mbar_wait(&S->tmem_empty[as], aphase ^ 1u, err);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + as * 128u;
+      for (int kt = 0; kt < nkt && ok; kt++, it++) {
+        const uint32_t stage = it % kStages, phase = (it / kStages) & 1u;
+        ok = mbar_wait(&S->full[stage], phase, err);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint64_t desc = make_desc_sw128(smem_u32(tiles + stage * kTileBytes));
+#pragma unroll
+          for (int k4 = 0; k4 < 4; k4++)
+            umma_i8(tmem_d, desc + (uint64_t)(k4 * 2), desc + (uint64_t)(k4 * 2), kIdescI8, (kt | k4) != 0 ? 1u : 0u);
+          umma_commit(&S->empty[stage]);  // frees the stage when these MMAs have read it
+        }
+        __syncwarp();
+      }
+      if (lane == 0) umma_commit(&S->tmem_full[as]);
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> HBM =====================
+    const int quarter = warp & 3;  // TMEM lanes this warp may touch
+    const int row = quarter * 32 + lane;
+    uint32_t bi = 0;
+    bool ok = true;
+    for (int blk = blockIdx.x; blk < nblocks && ok; blk += gridDim.x, bi++) {
+      const uint32_t as = bi & 1u, aphase = (bi >> 1) & 1u;
+      ok = mbar_wait(&S->tmem_full[as], aphase, err);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      int32_t* out = gram + ((size_t)blk * 128 + row) * 128;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 128u + (uint32_t)c * 32u;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (out_f32) {
+#pragma unroll
+          for (int q = 0; q < 32; q++) v[q] = __float_as_uint(__int2float_rn((int)v[q]));
+        }
+        if (ok) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 4)
+            *reinterpret_cast<uint4*>(out + c * 32 + q) = make_uint4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S->tmem_empty[as]);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// Debug / test cross-check: the same Gram blocks with dp4a on the CUDA cores.
+__global__ void __launch_bounds__(256) gram_simt_kernel(GenoView g, const int* __restrict__ perm, int32_t* __restrict__ gram, int out_f32) {
+  const int blk = blockIdx.x;
+  const int nw = (int)(g.ld >> 2);
+  for (int idx = threadIdx.x; idx < 128 * 128; idx += blockDim.x) {
+    const int i = idx >> 7, j = idx & 127;
+    const int pi = blk * 128 + i, pj = blk * 128 + j;
+    int acc = 0;
+    if (pi < g.p && pj < g.p) {
+      const int* ci = reinterpret_cast<const int*>(g.x8 + (int64_t)perm[pi] * g.ld);
+      const int* cj = reinterpret_cast<const int*>(g.x8 + (int64_t)perm[pj] * g.ld);
+      for (int w = 0; w < nw; w++) acc = __dp4a(ci[w], cj[w], acc);
+    }
+    gram[(size_t)blk * 128 * 128 + idx] = out_f32 ? __float_as_int(__int2float_rn(acc)) : acc;
+  }
+}
+
+}  // namespace
+
+void launch_gram_tc(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, int* err, int num_sms,
+                    cudaStream_t st) {
+  const size_t smem = (size_t)kStages * kTileBytes + sizeof(GramSmem) + 1024;
+  cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int grid = nblocks < num_sms ? nblocks : num_sms;
+  gram_tc_kernel<<<grid, 288, smem, st>>>(g, perm, nblocks, static_cast<int32_t*>(gram), out_f32, err);
+}
+void launch_gram_simt(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, cudaStream_t st) {
+  gram_simt_kernel<<<nblocks, 256, 0, st>>>(g, perm, static_cast<int32_t*>(gram), out_f32);
+}
+
+}  // namespace bwgr

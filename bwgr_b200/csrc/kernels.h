@@ -1,0 +1,113 @@
+// kernels.h -- internal launch interface between the C-ABI host layer (capi.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace bwgr {
+
+// ---- genotype store -----------------------------------------------------------------------------
+struct GenoView {
+  const int8_t* x8 = nullptr;   // int8 store: column j at x8 + j*ld
+  const uint8_t* x2 = nullptr;  // 2-bit store: column j at x2 + j*ldb, row r in byte r/4, bits 2*(r%4)
+  int64_t ld = 0, ldb = 0;
+  int n = 0, p = 0;
+  int storage = 0;
+};
+
+// f64 (device staging chunk, column-major ld_src) -> int8 store columns [j0, j0+pc); *bad != 0 if a value
+// is not an integer in range.
+void launch_pack_f64(const double* src, int64_t ld_src, int n, int pc, int8_t* dst, int64_t ld, int lo, int hi,
+                     int* bad, cudaStream_t st);
+// int8 store -> 2-bit store (values must be in {0,1,2}; else *bad)
+void launch_pack_2bit(const int8_t* src, int64_t ld, int n, int p, uint8_t* dst, int64_t ldb, int* bad, cudaStream_t st);
+void launch_unpack_2bit(const uint8_t* src, int64_t ldb, int n, int p, int8_t* dst, int64_t ld, cudaStream_t st);
+void launch_check_range_i8(const int8_t* src, int64_t ld, int n, int p, int lo, int hi, int* bad, cudaStream_t st);
+// zero rows [n, ld) of every column
+void launch_zero_pad(int8_t* x, int64_t ld, int n, int p, cudaStream_t st);
+// integer-exact column statistics: xx_j = sum x^2, sx_j = sum x (as int64)
+void launch_col_stats(const GenoView& g, long long* xx, long long* sx, cudaStream_t st);
+// masked variant for a system with a row mask (uint8 n): xx, sx over used rows
+void launch_col_stats_masked(const GenoView& g, const uint8_t* mask, long long* xx, long long* sx, cudaStream_t st);
+// hat = mu + X b (deterministic two-stage reduction). work: [splits][ld] floats.
+void launch_gemv_hat(const GenoView& g, const float* b, const float* mu_dev, float* hat, float* work, int splits,
+                     cudaStream_t st);
+
+// ---- small-n path: one persistent CTA per system -------------------------------------------------
+struct SmallNArgs {
+  GenoView g;
+  int model;
+  int nsys;
+  int sweep0, nsweeps;     // absolute sweep range of this launch
+  const int* perms;        // [nsweeps_total][p] marker order per sweep, or nullptr for natural order
+  int perm_stride_sweeps;  // perms row used = (sweep - perm_base)
+  int perm_base;
+  const float* y;          // [nsys][ld]  (centred later; raw y)
+  float* e;                // [nsys][ld]  residuals (state, persists across launches)
+  float* b;                // [nsys][p]
+  float* d;                // [nsys][p] or nullptr
+  float* vbv;              // [nsys][p] per-marker variance (or KMUP lambda) or nullptr
+  const float* xx;         // [nxx][p]  (nxx = 1 shared or nsys when masked)
+  int xx_per_sys;
+  const uint8_t* mask;     // [nsys][ld] or nullptr
+  SysScalars* sc;          // [nsys]
+  // Gibbs posterior sums
+  float* B; float* D; float* VBv;  // [nsys][p] or nullptr
+  uint32_t seed_lo, seed_hi;
+  int chain0;              // chain id offset for the RNG counter
+  int* err;                // device error flag
+};
+void launch_small_n(const SmallNArgs& a, size_t smem_limit, cudaStream_t st);
+bool small_n_fits(const GenoView& g, bool masked, size_t smem_limit);
+
+// ---- blocked path ---------------------------------------------------------------------------------
+constexpr int kBlk = 128;  // markers per block
+
+// Gram blocks G[blk][i][j] = x_{perm[blk*128+i]}' x_{perm[blk*128+j]} (int32), tcgen05 kind::i8.
+// out_f32: write the (exact) int32 accumulators converted to float, the form the sweep consumes.
+void launch_gram_tc(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, int* err, int num_sms,
+                    cudaStream_t st);
+// SIMT cross-check of the same quantity (debug / tests only; selected with BWGR_GRAM=simt).
+void launch_gram_simt(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, cudaStream_t st);
+
+struct SweepArgs {
+  GenoView g;
+  int model;
+  int nsys;
+  const int* perm;       // this sweep's marker order [p] (device)
+  int nblocks;
+  const float* gram;     // [nblocks][128][128] Gram blocks as float (exact below 2^24)
+  float* e;              // [nsys][ld]
+  float* b; float* d; float* vbv;  // [nsys][p]
+  const float* xx;       // [p]
+  SysScalars* sc;        // [nsys]
+  float* B; float* D; float* VBv;  // Gibbs posterior sums or nullptr
+  long long* gacc;       // [3][nsys][128] fixed-point block accumulators (zeroed before launch)
+  unsigned int* bar;     // grid barrier counter (zeroed before launch)
+  float g_quantum;       // value of one fixed-point unit of g
+  float g_limit;         // |partial g| above this -> err
+  uint32_t seed_lo, seed_hi;
+  int chain0;
+  int rows_per_cta;      // multiple of 16
+  int* err;
+};
+void launch_sweep_blocked(const SweepArgs& a, int grid, cudaStream_t st);
+int sweep_blocked_max_grid(int rows_per_cta, int nsys);
+size_t sweep_blocked_smem(int rows_per_cta, int nsys);
+
+// Sweep epilogue (both paths use the same arithmetic): reductions + hyper-parameter update +
+// e -= mean(e). One CTA per system.
+struct EpilogueArgs {
+  int model, nsys, n, p;
+  int64_t ld;
+  float* e; const float* y; float* b; const float* d; const float* vbv; const float* b_prev;  // b_prev: emEN convergence
+  const uint8_t* mask;
+  SysScalars* sc;
+  float* B; float* D; float* VBv;
+  uint32_t seed_lo, seed_hi;
+  int chain0;
+};
+void launch_epilogue(const EpilogueArgs& a, cudaStream_t st);
+
+}  // namespace bwgr

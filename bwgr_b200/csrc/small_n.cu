@@ -1,0 +1,237 @@
+// small_n.cu -- "small-n batching" path: one persistent CTA per system (trait / fold / chain).
+//
+// The residual vector of a system lives in this SM's shared memory for the whole sweep, so the CTA
+// runs the reference's per-marker step literally (Rcpp20260726ai.cpp:332-337 and siblings):
+//   g = x_j'e  ->  scalar rule  ->  e -= x_j * de
+// Each thread owns fixed 16-row chunks of e (no cross-thread hazard on e), genotype columns are
+// streamed from HBM/L2 through a cp.async ring in marker order (the order is known up front), and
+// the only block-wide synchronisation per marker is the one barrier of the dot-product reduction.
+// Independent systems = independent CTAs: no communication ("replicas").
+#include "kernels.h"
+
+namespace bwgr {
+
+namespace {
+
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Expand 4 packed 2-bit bytes (16 rows) into 16 int8 bytes.
+__device__ __forceinline__ uint4 expand_2bit(uint32_t pk) {
+  uint32_t w[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint32_t byte = (pk >> (8 * q)) & 0xFFu;
+    w[q] = (byte & 3u) | (((byte >> 2) & 3u) << 8) | (((byte >> 4) & 3u) << 16) | (((byte >> 6) & 3u) << 24);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// kRing = genotype columns in flight per CTA (8, 4 or 2 depending on how much shared memory e leaves).
+template <int MODEL, int kRing>
+__global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int sys = blockIdx.x;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  const int ld = (int)a.g.ld, p = a.g.p;
+  const int nchunks = ld >> 4;
+  const bool two_bit = a.g.storage != 0;
+  const int col_bytes = two_bit ? (ld >> 2) : ld;  // bytes of one column slot in the ring
+
+  float* e_s = reinterpret_cast<float*>(smem_raw);                          // [ld]
+  unsigned char* ring = smem_raw + (size_t)ld * 4;                          // [kRing][col_bytes]
+  unsigned char* mask_s = ring + (size_t)kRing * col_bytes;                 // [ld] (only if mask)
+  float* red = reinterpret_cast<float*>(mask_s + (a.mask ? ld : 0));        // [2][32]
+  MarkerDraws* draws = reinterpret_cast<MarkerDraws*>(red + 64);            // [2][T] (Gibbs)
+  __shared__ SysScalars sc;
+
+  if (tid == 0) sc = a.sc[sys];
+  __syncthreads();
+  if (sc.done) return;
+
+  float* e_g = a.e + (size_t)sys * ld;
+  for (int i = tid; i < ld; i += T) e_s[i] = e_g[i];
+  if (a.mask)
+    for (int i = tid; i < ld; i += T) mask_s[i] = a.mask[(size_t)sys * ld + i];
+
+  float* b = a.b + (size_t)sys * p;
+  float* dvec = a.d ? a.d + (size_t)sys * p : nullptr;
+  float* vbv = a.vbv ? a.vbv + (size_t)sys * p : nullptr;
+  const float* xx = a.xx + (a.xx_per_sys ? (size_t)sys * p : 0);
+  const int* order = a.perms;  // nullptr = natural order
+  const int sweep = sc.sweep;
+  const uint32_t chain = (uint32_t)(a.chain0 + sys);
+
+  auto marker_at = [&](int pos) { return order ? order[pos] : pos; };
+  auto issue_col = [&](int pos) {
+    if (pos < p) {
+      const int j = marker_at(pos);
+      unsigned char* slot = ring + (size_t)(pos % kRing) * col_bytes;
+      if (!two_bit) {
+        const int8_t* src = a.g.x8 + (int64_t)j * a.g.ld;
+        for (int c = tid; c < nchunks; c += T) cp_async16(slot + 16 * c, src + 16 * c);
+      } else {
+        const uint8_t* src = a.g.x2 + (int64_t)j * a.g.ldb;
+        for (int c = tid; c < nchunks; c += T) cp_async4(slot + 4 * c, src + 4 * c);
+      }
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll 1
+  for (int q = 0; q < kRing - 1; q++) issue_col(q);
+  __syncthreads();  // e_s, mask_s visible
+
+  // per-marker inputs, prefetched one marker ahead
+  int j_next = marker_at(0);
+  float nb0 = b[j_next], nxx = xx[j_next], nvb = vbv ? vbv[j_next] : 0.0f;
+
+#pragma unroll 1
+  for (int pos = 0; pos < p; pos++) {
+    const int j = j_next;
+    const float b0 = nb0, xxj = nxx, vbj = nvb;
+    if (pos + 1 < p) {
+      j_next = marker_at(pos + 1);
+      nb0 = b[j_next]; nxx = xx[j_next]; nvb = vbv ? vbv[j_next] : 0.0f;
+    }
+    if (model_is_gibbs(MODEL) && (pos % T) == 0) {  // draws of the next T markers, one per thread
+      const int q = pos + tid;
+      if (q < p)
+        draws[((pos / T) & 1) * T + tid] = marker_draws(MODEL, (uint32_t)marker_at(q), (uint32_t)sweep, chain, sc.df, a.seed_lo, a.seed_hi);
+    }
+    issue_col(pos + kRing - 1);
+    cp_async_wait<kRing - 1>();
+
+    // ---- g = x_j' e over this thread's chunks
+    const unsigned char* slot = ring + (size_t)(pos % kRing) * col_bytes;
+    float acc = 0.0f;
+    for (int c = tid; c < nchunks; c += T) {
+      uint4 w = two_bit ? expand_2bit(*reinterpret_cast<const uint32_t*>(slot + 4 * c))
+                        : *reinterpret_cast<const uint4*>(slot + 16 * c);
+      if (a.mask) {
+        const uint4 m = *reinterpret_cast<const uint4*>(mask_s + 16 * c);
+        w.x &= m.x * 0xFFu; w.y &= m.y * 0xFFu; w.z &= m.z * 0xFFu; w.w &= m.w * 0xFFu;
+      }
+      const uint32_t ww[4] = {w.x ^ 0x80808080u, w.y ^ 0x80808080u, w.z ^ 0x80808080u, w.w ^ 0x80808080u};
+      const float4* ev = reinterpret_cast<const float4*>(e_s + 16 * c);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const float4 e4 = ev[q];
+        acc = fmaf(byte_to_float(ww[q], 0), e4.x, acc);
+        acc = fmaf(byte_to_float(ww[q], 1), e4.y, acc);
+        acc = fmaf(byte_to_float(ww[q], 2), e4.z, acc);
+        acc = fmaf(byte_to_float(ww[q], 3), e4.w, acc);
+      }
+    }
+    acc = warp_sum(acc);
+    float* rbuf = red + (pos & 1) * 32;
+    if (lane == 0) rbuf[warp] = acc;
+    __syncthreads();
+    float g = (lane < nwarps) ? rbuf[lane] : 0.0f;
+    g = warp_sum(g);
+
+    // ---- rule (every thread, identical inputs -> identical result)
+    MarkerDraws dr;
+    if (model_is_gibbs(MODEL)) dr = draws[((pos / T) & 1) * T + (pos % T)];
+    else { dr.z1 = dr.z2 = dr.u = 0.0f; dr.chi = 1.0f; }
+    const RuleOut r = marker_rule<MODEL>(g, xxj, b0, vbj, sc, dr);
+    if (tid == 0) {
+      b[j] = r.b;
+      if (model_has_d(MODEL) && dvec) dvec[j] = r.d;
+      if (model_has_vbj(MODEL) && MODEL != M_KMUP && vbv) vbv[j] = r.vbj;
+    }
+
+    // ---- e -= x_j * de on this thread's chunks
+    if (r.de != 0.0f) {
+      for (int c = tid; c < nchunks; c += T) {
+        uint4 w = two_bit ? expand_2bit(*reinterpret_cast<const uint32_t*>(slot + 4 * c))
+                          : *reinterpret_cast<const uint4*>(slot + 16 * c);
+        if (a.mask) {
+          const uint4 m = *reinterpret_cast<const uint4*>(mask_s + 16 * c);
+          w.x &= m.x * 0xFFu; w.y &= m.y * 0xFFu; w.z &= m.z * 0xFFu; w.w &= m.w * 0xFFu;
+        }
+        const uint32_t ww[4] = {w.x ^ 0x80808080u, w.y ^ 0x80808080u, w.z ^ 0x80808080u, w.w ^ 0x80808080u};
+        float4* ev = reinterpret_cast<float4*>(e_s + 16 * c);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          float4 e4 = ev[q];
+          e4.x = fmaf(-byte_to_float(ww[q], 0), r.de, e4.x);
+          e4.y = fmaf(-byte_to_float(ww[q], 1), r.de, e4.y);
+          e4.z = fmaf(-byte_to_float(ww[q], 2), r.de, e4.z);
+          e4.w = fmaf(-byte_to_float(ww[q], 3), r.de, e4.w);
+          ev[q] = e4;
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  for (int i = tid; i < ld; i += T) e_g[i] = e_s[i];
+}
+
+}  // namespace
+
+static size_t small_n_smem(const SmallNArgs& a, int ring, int T) {
+  const size_t ld = (size_t)a.g.ld;
+  const size_t col_bytes = a.g.storage ? (ld >> 2) : ld;
+  return ld * 4 + (size_t)ring * col_bytes + (a.mask ? ld : 0) + 64 * 4 +
+         (model_is_gibbs(a.model) ? 2 * (size_t)T * sizeof(MarkerDraws) : 0) + 16;
+}
+
+// Largest n this path takes: e (4 B/row) + two ring slots must fit the 227 KB of one SM.
+bool small_n_fits(const GenoView& g, bool masked, size_t smem_limit) {
+  SmallNArgs a;
+  a.g = g; a.mask = masked ? reinterpret_cast<const uint8_t*>(1) : nullptr; a.model = M_BB;
+  return small_n_smem(a, 2, 1024) <= smem_limit;
+}
+
+template <int MODEL>
+static void launch_small_model(const SmallNArgs& a, size_t smem_limit, cudaStream_t st) {
+  const int nchunks = (int)(a.g.ld >> 4);
+  int T = ((nchunks + 31) / 32) * 32;
+  if (T > 1024) T = 1024;
+  if (T < 32) T = 32;
+#define BWGR_TRY_RING(RING)                                                                                       \
+  {                                                                                                               \
+    const size_t smem = small_n_smem(a, RING, T);                                                                 \
+    if (smem <= smem_limit) {                                                                                     \
+      cudaFuncSetAttribute(small_n_sweep_kernel<MODEL, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      small_n_sweep_kernel<MODEL, RING><<<a.nsys, T, smem, st>>>(a);                                              \
+      return;                                                                                                     \
+    }                                                                                                             \
+  }
+  BWGR_TRY_RING(8)
+  BWGR_TRY_RING(4)
+  BWGR_TRY_RING(2)
+#undef BWGR_TRY_RING
+}
+
+void launch_small_n(const SmallNArgs& a, size_t smem_limit, cudaStream_t st) {
+  switch (a.model) {
+    case M_EMRR: launch_small_model<M_EMRR>(a, smem_limit, st); break;
+    case M_EMBA: launch_small_model<M_EMBA>(a, smem_limit, st); break;
+    case M_EMBB: launch_small_model<M_EMBB>(a, smem_limit, st); break;
+    case M_EMBC: launch_small_model<M_EMBC>(a, smem_limit, st); break;
+    case M_EMBL: launch_small_model<M_EMBL>(a, smem_limit, st); break;
+    case M_EMEN: launch_small_model<M_EMEN>(a, smem_limit, st); break;
+    case M_BRR: launch_small_model<M_BRR>(a, smem_limit, st); break;
+    case M_BA: launch_small_model<M_BA>(a, smem_limit, st); break;
+    case M_BB: launch_small_model<M_BB>(a, smem_limit, st); break;
+    case M_BC: launch_small_model<M_BC>(a, smem_limit, st); break;
+    case M_KMUP: launch_small_model<M_KMUP>(a, smem_limit, st); break;
+    case M_MRR: launch_small_model<M_MRR>(a, smem_limit, st); break;
+    default: break;
+  }
+}
+
+}  // namespace bwgr

@@ -1,0 +1,169 @@
+/* bwgr_b200.h -- C ABI of the B200-native marker-effect update loop (drop-in for bWGR's hot path).
+ *
+ * Every entry point takes plain pointers and sizes (R's own memory: double, column-major) and
+ * writes into caller-allocated outputs, so the Rcpp shim that replaces the reference's generated
+ * glue (src/RcppExports.cpp:14-1233) is a one-to-one forwarding stub.
+ * All functions return 0 on success or a negative bwgr_status; bwgr_last_error() gives the text.
+ * There is no CPU fallback: without a CUDA device (or with the CUDA library missing) every
+ * compute call fails with BWGR_ERR_CUDA.
+ *
+ * Citations are file:line under the reference tree (alenxav/bWGR).
+ */
+#ifndef BWGR_B200_H
+#define BWGR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define BWGR_API __attribute__((visibility("default")))
+#else
+#define BWGR_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bwgr_handle bwgr_handle; /* one per GPU (= per rank); owns the genotype store */
+
+enum bwgr_status {
+  BWGR_OK = 0,
+  BWGR_ERR_ARG = -1,     /* bad argument (shape, NULL, non-integer genotype ...) */
+  BWGR_ERR_CUDA = -2,    /* CUDA runtime / launch failure, or no device */
+  BWGR_ERR_STATE = -3,   /* call order (no genotypes loaded, no fit in progress ...) */
+  BWGR_ERR_NUMERIC = -4, /* fixed-point range exceeded / kernel watchdog */
+  BWGR_ERR_UNSUPPORTED = -5
+};
+
+/* Genotype storage in HBM: column-major, one marker per column. */
+enum bwgr_storage {
+  BWGR_STORE_I8 = 0,  /* int8, leading dimension padded to 128 rows */
+  BWGR_STORE_2BIT = 1 /* codes {0,1,2} packed 4 per byte (little end first), unpacked on the fly */
+};
+
+/* Univariate EM solvers of src/Rcpp20260726ai.cpp. */
+enum bwgr_em_model {
+  BWGR_EM_RR = 0, /* emRR :308-354 */
+  BWGR_EM_BA = 1, /* emBA :80-128  */
+  BWGR_EM_BB = 2, /* emBB :131-187 */
+  BWGR_EM_BC = 3, /* emBC :190-247 */
+  BWGR_EM_BL = 4, /* emBL :357-397 */
+  BWGR_EM_EN = 5  /* emEN :400-460 */
+};
+
+/* Univariate Gibbs samplers of src/Rcpp20260726ai.cpp. */
+enum bwgr_gibbs_model {
+  BWGR_GIBBS_RR = 0, /* BayesRR :812-855 */
+  BWGR_GIBBS_A = 1,  /* BayesA  :589-635 */
+  BWGR_GIBBS_B = 2,  /* BayesB  :638-699 */
+  BWGR_GIBBS_C = 3   /* BayesC  :702-759 */
+};
+
+/* Which kernel family runs the sweep. AUTO picks SMALL_N when several systems share X and the
+ * residual of one system fits one SM's shared memory, BLOCKED otherwise. */
+enum bwgr_path { BWGR_PATH_AUTO = 0, BWGR_PATH_SMALL_N = 1, BWGR_PATH_BLOCKED = 2 };
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+BWGR_API int bwgr_create(int device, bwgr_handle** out);
+BWGR_API void bwgr_destroy(bwgr_handle* h);
+BWGR_API const char* bwgr_last_error(void);
+BWGR_API int bwgr_version(void);
+/* Use the caller's CUDA stream (cudaStream_t as void*) for all work of this handle; NULL = the
+ * handle's own stream. Lets a host framework time the library with its own events. */
+BWGR_API int bwgr_set_stream(bwgr_handle* h, void* cuda_stream);
+/* Tuning knobs: block = markers per block of the blocked sweep (128); path = bwgr_path;
+ * grid = persistent CTAs (0 = one per SM). Negative values leave a knob unchanged. */
+BWGR_API int bwgr_set_tuning(bwgr_handle* h, int block, int path, int grid);
+
+/* ---- genotype store (replaces the per-call double->float copy of RcppExports.cpp:115-116) -- */
+/* X: host, column-major, n x p, leading dimension ld (>= n). Values must be integers in
+ * [-128,127] (I8) or {0,1,2} (2BIT); anything else -> BWGR_ERR_ARG (no silent rounding). */
+BWGR_API int bwgr_geno_load_f64(bwgr_handle* h, const double* X, int64_t n, int64_t p, int64_t ld, int storage);
+BWGR_API int bwgr_geno_load_i8(bwgr_handle* h, const int8_t* X, int64_t n, int64_t p, int64_t ld, int storage);
+/* Same, X already resident in device memory (int8, column-major). */
+BWGR_API int bwgr_geno_load_i8_device(bwgr_handle* h, const int8_t* dX, int64_t n, int64_t p, int64_t ld, int storage);
+/* Round trip for the bit-exactness tests: unpack the store to host int8 (n x p, ld = n). */
+BWGR_API int bwgr_geno_unpack_i8(bwgr_handle* h, int8_t* X_out);
+/* Raw bytes of the store as laid out in HBM (size from bwgr_geno_info). */
+BWGR_API int bwgr_geno_raw(bwgr_handle* h, uint8_t* bytes_out);
+BWGR_API int bwgr_geno_info(bwgr_handle* h, int64_t* n, int64_t* p, int64_t* ld_bytes, int* storage, int64_t* total_bytes);
+/* Integer-exact column statistics (reference: xx[j]=squaredNorm, :312-316): xx_j = sum x^2, sx_j = sum x. */
+BWGR_API int bwgr_geno_stats(bwgr_handle* h, double* xx, double* sx);
+
+/* ---- univariate EM family ----------------------------------------------------------------- */
+typedef struct {
+  int model;     /* bwgr_em_model */
+  int nsys;      /* systems (traits / folds) sharing the genotypes; y is n x nsys */
+  int it;        /* sweeps; <0 = the reference's hard-coded 200 (emEN: maxit 300 with its tol) */
+  double df, R2, Pi, alpha; /* reference defaults: 10, 0.5, 0.75, 0.02 */
+  const uint8_t* row_mask;  /* optional n x nsys, 1 = row used by the system (CV folds); NULL = all */
+} bwgr_em_params;
+
+typedef struct {
+  double* mu;   /* [nsys] */
+  double* b;    /* [p x nsys] */
+  double* d;    /* [p x nsys] inclusion (emBB, emBC) or NULL */
+  double* hat;  /* [n x nsys] */
+  double* vb;   /* [p x nsys] per-marker Vb (emBA, emBB) or NULL */
+  double* scal; /* [4 x nsys]: Va, Ve, h2, Vg (as each model defines them) */
+  int* its;     /* [nsys] sweeps done */
+} bwgr_em_out;
+
+/* Whole fit, the call the Rcpp shim makes for emRR/emBA/emBB/emBC/emBL/emEN. */
+BWGR_API int bwgr_em_fit(bwgr_handle* h, const bwgr_em_params* par, const double* y, bwgr_em_out* out);
+/* Same fit split in three so that a harness can time sweeps with everything resident in HBM. */
+BWGR_API int bwgr_em_begin(bwgr_handle* h, const bwgr_em_params* par, const double* y);
+BWGR_API int bwgr_em_sweeps(bwgr_handle* h, int nsweeps); /* asynchronous on the handle's stream */
+BWGR_API int bwgr_em_end(bwgr_handle* h, bwgr_em_out* out);
+
+/* ---- univariate Gibbs family --------------------------------------------------------------- */
+typedef struct {
+  int model;    /* bwgr_gibbs_model */
+  int nchains;  /* independent chains of the same model on the same y (seeds seed, seed+1, ...) */
+  int it, bi;   /* reference defaults 1500, 500 */
+  double pi, df, R2; /* 0.95, 5, 0.5 */
+  uint64_t seed;
+} bwgr_gibbs_params;
+
+typedef struct {
+  double* mu;   /* [nchains] */
+  double* b;    /* [p x nchains] posterior means */
+  double* d;    /* [p x nchains] (BayesB/C) or NULL */
+  double* hat;  /* [n x nchains] */
+  double* vb;   /* [p x nchains] (BayesA/B) or [nchains] (BayesRR/C) */
+  double* scal; /* [4 x nchains]: vb (scalar models), ve, h2, MSx */
+} bwgr_gibbs_out;
+
+BWGR_API int bwgr_gibbs_fit(bwgr_handle* h, const bwgr_gibbs_params* par, const double* y, bwgr_gibbs_out* out);
+
+/* One Kuo-Mallick sweep, drop-in for KMUP(X,b,d,xx,e,L,Ve,pi) (:12-38); b,d,e updated in place.
+ * The inclusion probability uses BayesB's ratio form (:673-674), algebraically identical to
+ * :25-27 but free of the exp underflow. */
+BWGR_API int bwgr_kmup_sweep(bwgr_handle* h, double* b, double* d, const double* xx, double* e, const double* L, double Ve,
+                    double pi, uint64_t seed);
+
+/* wgr(y,X,it,bi,th,bag=1,rp,iv,de,pi,df,R2) with the MCMC loop native (R/wgr.R:2-169; eigK=NULL).
+ * scal = {mu, Ve, Va, cxx}; Vb is [p] when iv/de, else scal[2]. */
+BWGR_API int bwgr_wgr_fit(bwgr_handle* h, const double* y, int it, int bi, int th, int iv, int de, double pi, double df,
+                 double R2, uint64_t seed, double* b, double* d, double* Vb, double* hat, double* scal);
+
+/* ---- multivariate ridge -------------------------------------------------------------------- */
+/* MRR3 / MRR3F (src/RcppEigen20230423.cpp:318-701, :704-1079). par[30] = the arguments after
+ * (Y,X) in the order of R/RcppExports.R:180. Y: n x k column-major, NaN = missing.
+ * cnv: 3*maxit doubles (cnvB | cnvH2 | cnvV). */
+BWGR_API int bwgr_mrr3_fit(bwgr_handle* h, int f32_variant, const double* Y, int k, const double* par, double* mu, double* b,
+                  double* hat, double* h2, double* GC, double* vb, double* ve, double* MSx, double* cnv, double* W,
+                  int* its);
+
+/* ---- introspection for tests and the bench -------------------------------------------------- */
+/* Kernels launched by this handle since creation (the bench's gpu_launches claim). */
+BWGR_API int64_t bwgr_launch_count(bwgr_handle* h);
+/* Gram blocks X_B' X_B of one sweep order (perm[p], block markers each), int32, [nblocks][block][block];
+ * the tcgen05 kernel's output, exposed so tests can check it bit-exactly. */
+BWGR_API int bwgr_debug_gram(bwgr_handle* h, const int32_t* perm, int block, int32_t* gram_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BWGR_B200_H */

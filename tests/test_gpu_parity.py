@@ -1,0 +1,191 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Bars (SURVEY 8c / BASELINE.md 5): packing, indexing, column statistics and Gram blocks bit-exact;
+EM solvers rel <= 1e-4 on b (relative to max|b|), hat, variance components and h2 vs the float oracle;
+Gibbs posterior means within Monte-Carlo error across seeds."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import GOLDEN, synth
+
+pytestmark = pytest.mark.gpu
+
+bw = pytest.importorskip("bwgr_b200")
+
+RTOL = 1e-4  # stated tolerance of north_star for EM solvers after convergence
+
+
+def _close_em(out, ref, model):
+    scale = np.abs(ref["b"]).max()
+    assert np.abs(out["b"] - ref["b"]).max() <= RTOL * scale, "b"
+    assert np.abs(out["hat"] - ref["hat"]).max() <= RTOL * np.abs(ref["hat"]).max(), "hat"
+    assert abs(out["mu"] - ref["mu"]) <= RTOL * max(1.0, abs(ref["mu"])), "mu"
+    for key in ("Va", "Ve", "h2", "Vg"):
+        if key in ref:
+            assert abs(out[key] - ref[key]) <= RTOL * max(abs(ref[key]), 1e-3), key
+    if "d" in ref:
+        assert np.abs(out["d"] - ref["d"]).max() <= 1e-3, "d"
+    if "Vb" in ref and model in ("emBA", "emBB"):
+        assert np.abs(out["Vb"] - ref["Vb"]).max() <= RTOL * np.abs(ref["Vb"]).max(), "Vb"
+    assert out["its"] == ref["its"]
+
+
+@pytest.mark.parametrize("storage", [0, 1])
+def test_pack_roundtrip_bit_exact(tpod, storage):
+    _, gen = tpod
+    with bw.Genotypes(gen, storage=storage) as g:
+        assert np.array_equal(g.unpack(), gen)
+        info = g.info()
+        raw = g.raw().reshape(info["p"], info["ld_bytes"])
+        if storage == 0:
+            assert np.array_equal(raw[:, :196].T.view(np.int8), gen) and not raw[:, 196:].any()
+        else:  # byte k holds rows 4k..4k+3, row r in bits 2*(r%4)
+            pad = np.zeros((info["ld_bytes"] * 4, 376), dtype=np.uint8)
+            pad[:196] = gen
+            want = (pad[0::4] | (pad[1::4] << 2) | (pad[2::4] << 4) | (pad[3::4] << 6)).T
+            assert np.array_equal(raw, want)
+        xx, sx = g.stats()
+        assert np.array_equal(xx, (gen.astype(np.int64) ** 2).sum(0)) and np.array_equal(sx, gen.astype(np.int64).sum(0))
+
+
+def test_pack_rejects_non_integer(tpod):
+    _, gen = tpod
+    X = gen.astype(np.float64)
+    X[3, 5] = 0.5
+    with pytest.raises(bw.BwgrError):
+        bw.Genotypes(X)
+    X[3, 5] = 3.0
+    with pytest.raises(bw.BwgrError):
+        bw.Genotypes(X, storage=1)
+    with bw.Genotypes(X, storage=0) as g:  # 3 is fine for int8
+        assert g.unpack()[3, 5] == 3
+
+
+def test_pack_f64_signed_and_ragged():
+    rng = np.random.default_rng(5)
+    for n, p in ((2, 1), (17, 3), (129, 130), (1000, 257)):
+        X = rng.integers(-128, 128, size=(n, p)).astype(np.float64)
+        with bw.Genotypes(X) as g:
+            assert np.array_equal(g.unpack(), X.astype(np.int8))
+            xx, sx = g.stats()
+            assert np.array_equal(xx, (X ** 2).sum(0)) and np.array_equal(sx, X.sum(0))
+
+
+@pytest.mark.parametrize("shape", [(196, 376), (1000, 300), (4100, 129)])
+def test_gram_blocks_bit_exact(tpod, shape):
+    """tcgen05 kind::i8 Gram blocks X_B'X_B == integer numpy, for a shuffled order and ragged last block."""
+    if shape == (196, 376):
+        X = tpod[1]
+    else:
+        X, _ = synth(*shape, seed=7)
+    n, p = X.shape
+    perm = O.perm(p, 3)[2]
+    with bw.Genotypes(X) as g:
+        G = g.gram_blocks(perm)
+    Xi = X.astype(np.int64)
+    for blk in range(G.shape[0]):
+        cols = perm[blk * 128:(blk + 1) * 128]
+        want = np.zeros((128, 128), dtype=np.int64)
+        want[:len(cols), :len(cols)] = Xi[:, cols].T @ Xi[:, cols]
+        assert np.array_equal(G[blk].astype(np.int64), want), blk
+
+
+def test_gram_signed_values():
+    rng = np.random.default_rng(11)
+    X = rng.integers(-128, 128, size=(700, 140)).astype(np.int8)
+    perm = np.arange(140, dtype=np.int32)
+    with bw.Genotypes(X) as g:
+        G = g.gram_blocks(perm)
+    Xi = X.astype(np.int64)
+    want = Xi.T @ Xi
+    assert np.array_equal(G[0].astype(np.int64), want[:128, :128])
+    assert np.array_equal(G[1][:12, :12].astype(np.int64), want[128:, 128:])
+
+
+@pytest.mark.parametrize("path", [1, 2])
+@pytest.mark.parametrize("model", list(O.EM_MODELS))
+def test_em_tpod_matches_golden(tpod, model, path):
+    """config[0]: the six EM solvers on the bundled tpod data, both kernel families."""
+    y, gen = tpod
+    gold = np.load(os.path.join(GOLDEN, "tpod_em.npz"))
+    ref = {k.split("__")[1]: gold[k] for k in gold.files if k.startswith(model + "_f32__")}
+    ref = {k: (v.item() if v.ndim == 0 else v) for k, v in ref.items()}
+    with bw.Genotypes(gen, path=path) as g:
+        out = bw.em_fit(model, y, g)
+    _close_em(out, ref, model)
+
+
+@pytest.mark.parametrize("model", ["emRR", "emBB", "emBC"])
+def test_em_2bit_store_matches_int8(tpod, model):
+    y, gen = tpod
+    with bw.Genotypes(gen, storage=0, path=1) as g:
+        a = bw.em_fit(model, y, g, it=30)
+    with bw.Genotypes(gen, storage=1, path=1) as g:
+        b = bw.em_fit(model, y, g, it=30)
+    assert np.array_equal(a["b"], b["b"]) and np.array_equal(a["hat"], b["hat"])  # same arithmetic, same bits
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_em_synthetic_mid_size(path):
+    """n=3000 x p=2000 synthetic, emRR + emBC, reduced sweeps: both paths vs the float oracle."""
+    X, y = synth(3000, 2000, seed=3)
+    with bw.Genotypes(X, path=path) as g:
+        for model in ("emRR", "emBC"):
+            ref = O.em(model, y, X.astype(np.float32), it=12)
+            out = bw.em_fit(model, y, g, it=12)
+            _close_em(out, ref, model)
+
+
+def test_em_multi_system_and_folds():
+    """Batched fits (config 4 pattern): k traits x folds as independent systems with row masks equal the
+    same fits done one by one on the row subset (what emCV does with gen[-w,], R/cv.R:13-22)."""
+    X, Y = synth(600, 400, k=3, seed=9)
+    rng = np.random.default_rng(1)
+    fold = rng.integers(0, 2, size=600)
+    masks = np.stack([fold != 0, fold != 1, np.ones(600, bool)], axis=1)
+    with bw.Genotypes(X) as g:
+        out = bw.em_fit("emBC", Y, g, it=25, row_mask=masks)
+    for t in range(3):
+        keep = masks[:, t]
+        ref = O.em("emBC", Y[keep, t], X[keep].astype(np.float32), it=25)
+        scale = np.abs(ref["b"]).max()
+        assert np.abs(out["b"][:, t] - ref["b"]).max() <= RTOL * scale
+        assert abs(out["h2"][t] - ref["h2"]) <= RTOL
+        # GEBVs of held-out rows come from the same b (gen[w,] %*% b, R/cv.R:31)
+        hat_all = X.astype(np.float64) @ ref["b"] + ref["mu"]
+        assert np.abs(out["hat"][:, t] - hat_all).max() <= RTOL * np.abs(hat_all).max()
+
+
+def test_blocked_sweep_is_deterministic(tpod):
+    """Fixed-point integer reduction of g across CTAs: repeated fits are bit-identical."""
+    X, y = synth(2500, 700, seed=21)
+    with bw.Genotypes(X, path=2) as g:
+        a = bw.emRR(y, g, it=8)
+        b = bw.emRR(y, g, it=8)
+    assert np.array_equal(a["b"], b["b"]) and a["Ve"] == b["Ve"]
+
+
+@pytest.mark.parametrize("path", [1, 2])
+@pytest.mark.parametrize("model", list(O.GIBBS_MODELS))
+def test_gibbs_posterior_means(tpod, model, path):
+    """Gibbs parity is statistical (R's RNG stream cannot be reproduced): posterior means of b, h2, ve
+    agree with the oracle's within Monte-Carlo error estimated across seeds."""
+    y, gen = tpod
+    X = gen.astype(np.float64)
+    seeds = range(8)
+    ora = [O.gibbs(model, y, X, it=1200, bi=200, seed=100 + s) for s in seeds]
+    with bw.Genotypes(gen, path=path) as g:
+        gpu = [bw.gibbs_fit(model, y, g, it=1200, bi=200, seed=200 + s) for s in seeds]
+    for key in ("h2", "ve", "mu"):
+        a = np.array([r[key] for r in ora]); b = np.array([r[key] for r in gpu])
+        se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+        assert abs(a.mean() - b.mean()) <= 4 * se + 1e-3 * abs(a.mean()), (key, a.mean(), b.mean(), se)
+    A = np.mean([r["hat"] for r in ora], 0); B = np.mean([r["hat"] for r in gpu], 0)
+    assert np.corrcoef(A, B)[0, 1] > 0.995
+    assert np.abs(A - B).max() <= 0.05 * (A.max() - A.min()) + 4 * np.std([r["hat"] for r in ora], 0).max() / np.sqrt(8)
+    if model in ("BayesB", "BayesC"):
+        da = np.mean([r["d"].mean() for r in ora]); db = np.mean([r["d"].mean() for r in gpu])
+        assert abs(da - db) < 0.02
