@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the marker-effect update loop (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (N=1): one emRR Gauss-Seidel sweep (Rcpp20260726ai.cpp:330-344) over synthetic
+n=50,000 x p=50,000 int8 genotypes, k=1 -- the configuration the metric "marker-updates/sec & sweep ms
+at n=50k,p=50k; genotype GB/s vs HBM peak" is quoted on.  A step = one full sweep (p marker updates:
+Gram blocks + blocked sweep + hyper-parameter epilogue).
+  value      marker-updates/s with genotypes, y and all state resident in HBM (CUDA events on the
+             library's stream, max over ranks).
+  e2e        the same metric through the public call a user makes (bwgr_em_fit via bwgr_b200.emRR):
+             host int8 genotypes + y in pinned memory -> H2D -> pack/statistics -> the reference's
+             fixed 200 sweeps -> GEBVs -> D2H, all inside the timed region.
+  roofline   algorithmic bytes = n*p*1 B per sweep / mean duration of the dominant kernel
+             (measured live with CUDA events around each kernel class), against MEASURED_PEAKS.json.
+  cpu_baseline  the oracle (C++ restatement of the reference's single-threaded float32 RcppEigen path;
+             the reference itself needs R/Rcpp and cannot be built) on a bounded sample of the same
+             workload: full n, the first m markers, a few sweeps.
+N>1 (torchrun, one rank per GPU): independent replicas of the same sweep, one per GPU, no collective
+(the row-sharded single fit of config 5 is not built yet); value = total marker-updates/s.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+SEED = 20261018
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=50000)
+    ap.add_argument("--p", type=int, default=50000)
+    ap.add_argument("--model", default="emRR")
+    ap.add_argument("--e2e-fits", type=int, default=1)
+    ap.add_argument("--e2e-sweeps", type=int, default=200)
+    ap.add_argument("--cpu-markers", type=int, default=2048)
+    ap.add_argument("--cpu-sweeps", type=int, default=10)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synth_gpu(n, p, seed, dev):
+    """SURVEY 8d generator on the device: f_j~U(.05,.5), X_ij~Binom(2,f_j), 1% causal, h2=.5.
+    Returns Xt (p x n int8, i.e. the column-major n x p matrix) and y (n float64, host)."""
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    f = torch.empty(p, device=dev).uniform_(0.05, 0.5, generator=g)
+    Xt = torch.empty((p, n), dtype=torch.int8, device=dev)
+    nc = max(1, p // 100)
+    causal = torch.randperm(p, generator=g, device=dev)[:nc]
+    beta = torch.zeros(p, device=dev)
+    beta[causal] = torch.randn(nc, generator=g, device=dev)
+    gv = torch.zeros(n, device=dev)
+    step = 2048
+    for j0 in range(0, p, step):
+        j1 = min(p, j0 + step)
+        fj = f[j0:j1, None]
+        blk = (torch.rand((j1 - j0, n), device=dev, generator=g) < fj).to(torch.int8)
+        blk += (torch.rand((j1 - j0, n), device=dev, generator=g) < fj).to(torch.int8)
+        Xt[j0:j1] = blk
+        gv += beta[j0:j1] @ blk.float()
+    gv = (gv - gv.mean()) / (gv.std() + 1e-12) * (0.5 ** 0.5)
+    y = gv + torch.randn(n, generator=g, device=dev) * (0.5 ** 0.5)
+    return Xt, y.double().cpu().numpy()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(args, Xs, y, native=False):
+    """Oracle emRR on full n x the first m markers: sweeps timed as (it sweeps) - (0 sweeps)."""
+    import oracle as O
+    Xf = np.asfortranarray(Xs, dtype=np.float32)
+    t0 = time.perf_counter()
+    O.em(args.model, y, Xf, it=0, native=native)
+    t1 = time.perf_counter()
+    O.em(args.model, y, Xf, it=args.cpu_sweeps, native=native)
+    t2 = time.perf_counter()
+    sweeps_s = max((t2 - t1) - (t1 - t0), 1e-9)
+    return args.cpu_sweeps * Xf.shape[1] / sweeps_s, sweeps_s
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port; 1 thread, as the reference has no
+    threading: no src/Makevars, no OpenMP pragma) on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    rng = np.random.default_rng(SEED)
+    m = args.cpu_markers
+    f = rng.uniform(0.05, 0.5, size=m)
+    Xs = np.empty((args.n, m), dtype=np.int8, order="F")
+    for j in range(m):
+        Xs[:, j] = rng.binomial(2, f[j], size=args.n)
+    beta = np.zeros(m); beta[rng.choice(m, max(1, m // 100), replace=False)] = rng.normal(size=max(1, m // 100))
+    gv = Xs @ beta
+    y = (gv - gv.mean()) / (gv.std() + 1e-12) * 0.5 ** 0.5 + rng.normal(size=args.n) * 0.5 ** 0.5
+    vals = []
+    for _ in range(max(1, args.warmup > 0)):
+        cpu_sample(args, Xs, y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, _s = cpu_sample(args, Xs, y)
+        vals.append(v)
+    wall = time.perf_counter() - t0
+    val = float(np.median(vals))
+    sample = "oracle %s, full n=%d rows x first %d markers, %d sweeps per step (setup subtracted), g++ -O2, %s" % (
+        args.model, args.n, m, args.cpu_sweeps, cpu_model_name())
+    line = {"impl": "reference", "metric": "marker-updates/sec (emRR Gauss-Seidel sweep, n=50k x p=50k int8)",
+            "value": val, "unit": "marker-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s Gauss-Seidel sweep, synthetic n=%d x p=%d genotypes, k=1" % (args.model, args.n, args.p),
+                       "note": "per-marker cost is independent of p; CPU times a bounded marker sample at full n"},
+            "cpu_baseline": {"value": val, "unit": "marker-updates/s", "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "marker-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+
+    import bwgr_b200 as bw
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, p = args.n, args.p
+    Xt, y = synth_gpu(n, p, SEED + rank, dev)
+    torch.cuda.synchronize()
+
+    g = bw.Genotypes(device=local, path=bw.PATH_BLOCKED)
+    stream = torch.cuda.Stream(device=dev)  # events and the library share this stream
+    g.set_stream(stream.cuda_stream)
+    g.load(Xt)  # device-resident int8 (p x n row-major == n x p column-major)
+    st = bw.EmStepper(args.model, y, g)
+    st.sweeps(args.warmup)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = g.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    st.sweeps(args.steps)
+    e1.record(stream)
+    barrier()
+    launches = g.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # per-kernel durations for the roofline (separate pass: event pairs around every kernel)
+    g.profile(True)
+    st.sweeps(args.steps)
+    prof = g.profile_read()
+    g.profile(False)
+    fit = st.end()
+    assert np.isfinite(fit["b"]).all() and np.isfinite(fit["h2"])
+    hbm_peak, peak_src = peaks()
+    sweep_ms = prof["sweep"]["ms"] / max(1, prof["sweep"]["launches"])
+    gram_ms = prof["gram"]["ms"] / max(1, prof["gram"]["launches"])
+    epi_ms = prof["epilogue"]["ms"] / max(1, prof["epilogue"]["launches"])
+    dom = "sweep_blocked_kernel" if sweep_ms >= gram_ms else "gram_tc_kernel"
+    dom_ms = max(sweep_ms, gram_ms)
+    achieved = n * p / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "kernel": dom, "peak_source": peak_src, "algorithmic_bytes_per_launch": n * p,
+                "kernel_ms": {"sweep_blocked_kernel": sweep_ms, "gram_tc_kernel": gram_ms, "epilogue_kernel": epi_ms},
+                "whole_sweep_frac": (n * p / (ms / args.steps * 1e-3) / 1e9) / hbm_peak}
+    value = world * p * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        Xh = torch.empty((p, n), dtype=torch.int8, pin_memory=True)
+        Xh.copy_(Xt)
+        del Xt
+        torch.cuda.empty_cache()
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_fits):
+            g2 = bw.Genotypes(device=local, path=bw.PATH_BLOCKED)
+            g2.load(Xh)
+            out = bw.emRR(y, g2, it=args.e2e_sweeps)
+            g2.close()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        assert np.isfinite(out["b"]).all()
+        e2e = {"value": world * args.e2e_fits * args.e2e_sweeps * p / dt, "unit": "marker-updates/s",
+               "h2d_bytes_per_step": int(n * p + 8 * n), "d2h_bytes_per_step": int(4 * (p + n) + 64),
+               "step": "one emRR(y, gen) call: %d sweeps incl. H2D of int8 genotypes, packing, column statistics, GEBVs, D2H" % args.e2e_sweeps,
+               "seconds_per_fit": dt / args.e2e_fits}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        m = args.cpu_markers
+        if args.no_e2e:
+            Xs = Xt[:m].cpu().numpy().T
+        else:
+            Xs = Xh[:m].numpy().T
+        v, secs = cpu_sample(args, Xs, y)
+        cpu = {"value": v, "unit": "marker-updates/s", "cores": 1, "kind": "port",
+               "sample": "oracle %s (g++ -O2, float32, 1 thread like the reference), full n=%d x first %d markers, %d sweeps = %.1f s; %s, %d host cores" % (
+                   args.model, n, m, args.cpu_sweeps, secs, cpu_model_name(), os.cpu_count())}
+
+    if rank == 0:
+        line = {"metric": "marker-updates/sec (emRR Gauss-Seidel sweep, n=50k x p=50k int8)", "value": value,
+                "unit": "marker-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "%s Gauss-Seidel sweep, synthetic n=%d x p=%d int8 genotypes, k=1" % (args.model, n, p),
+                           "step": "one full sweep = p marker updates (Gram blocks + blocked sweep + epilogue)",
+                           "l2": "genotypes are %.1f GB per sweep, far larger than the 126 MB L2: no flush needed" % (n * p / 1e9),
+                           "parallelism": "1 GPU" if world == 1 else "%d independent replicas (one fit per GPU, no collective)" % world,
+                           "seed": SEED},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "sweep_ms": ms / args.steps}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

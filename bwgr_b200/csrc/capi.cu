@@ -115,6 +115,32 @@ struct bwgr_handle {
   int gram_simt = 0;
   int64_t launches = 0;
   Fit fit;
+  // optional per-kernel timing (bwgr_profile)
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[3];
+  double prof_ms[3] = {0, 0, 0};
+  int64_t prof_n[3] = {0, 0, 0};
+  cudaEvent_t prof_begin(int cls) {
+    if (!profiling) return nullptr;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    prof_ev[cls].push_back({a, b});
+    cudaEventRecord(a, stream);
+    return b;
+  }
+  void prof_end(cudaEvent_t b) { if (b) cudaEventRecord(b, stream); }
+  void prof_collect() {
+    for (int c = 0; c < 3; c++) {
+      for (auto& pr : prof_ev[c]) {
+        float ms = 0;
+        cudaEventSynchronize(pr.second);
+        cudaEventElapsedTime(&ms, pr.first, pr.second);
+        prof_ms[c] += ms; prof_n[c]++;
+        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+      }
+      prof_ev[c].clear();
+    }
+  }
 
   GenoView view() const {
     GenoView g;
@@ -602,8 +628,10 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
     if (f.model == M_EMEN) CU(cudaMemcpyAsync(f.b_prev.p, f.b.p, sizeof(float) * f.nsys * p, cudaMemcpyDeviceToDevice, h->stream));
     if (f.blocked) {
       if (f.shuffled || !f.gram_cached) {
+        cudaEvent_t pe = h->prof_begin(0);
         if (h->gram_simt) launch_gram_simt(g, d_perm, f.nblocks, f.gram.p, 1, h->stream);
         else launch_gram_tc(g, d_perm, f.nblocks, f.gram.p, 1, h->err.p, h->num_sms, h->stream);
+        h->prof_end(pe);
         h->launches++;
         f.gram_cached = true;
       }
@@ -616,7 +644,9 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
       a.gacc = f.gacc.p; a.bar = f.bar.p; a.g_quantum = quantum; a.g_limit = limit;
       a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0;
       a.rows_per_cta = f.rows_per_cta; a.err = h->err.p;
+      cudaEvent_t pe = h->prof_begin(1);
       launch_sweep_blocked(a, f.grid, h->stream);
+      h->prof_end(pe);
       h->launches++;
     } else {
       SmallNArgs a;
@@ -624,7 +654,9 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
       a.g = g; a.model = f.model; a.nsys = f.nsys; a.perms = d_perm; a.y = f.y.p; a.e = f.e.p; a.b = f.b.p; a.d = f.d.p;
       a.vbv = f.vbv.p; a.xx = f.masked ? f.xx_sys.p : h->xx_f.p; a.xx_per_sys = f.masked ? 1 : 0; a.mask = f.mask.p;
       a.sc = f.sc.p; a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0; a.err = h->err.p;
+      cudaEvent_t pe = h->prof_begin(1);
       launch_small_n(a, h->smem_optin, h->stream);
+      h->prof_end(pe);
       h->launches++;
     }
     if (f.shuffled) { CU(cudaEventRecord(f.perm_free[slot], h->stream)); f.perm_ev_valid[slot] = true; }
@@ -633,7 +665,9 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
     ea.model = f.model; ea.nsys = f.nsys; ea.n = (int)h->n; ea.p = (int)p; ea.ld = ld; ea.e = f.e.p; ea.y = f.y.p; ea.b = f.b.p;
     ea.d = f.d.p; ea.vbv = f.vbv.p; ea.b_prev = f.b_prev.p; ea.mask = f.mask.p; ea.sc = f.sc.p; ea.B = f.B.p; ea.D = f.D.p;
     ea.VBv = f.VBv.p; ea.seed_lo = (uint32_t)f.seed; ea.seed_hi = (uint32_t)(f.seed >> 32); ea.chain0 = 0;
+    cudaEvent_t pe2 = h->prof_begin(2);
     launch_epilogue(ea, h->stream);
+    h->prof_end(pe2);
     h->launches++;
     f.sweeps_issued++;
     cudaError_t le = cudaGetLastError();
@@ -820,6 +854,21 @@ int bwgr_wgr_fit(bwgr_handle*, const double*, int, int, int, int, int, double, d
 int bwgr_mrr3_fit(bwgr_handle*, int, const double*, int, const double*, double*, double*, double*, double*, double*,
                   double*, double*, double*, double*, double*, int*) {
   return fail(BWGR_ERR_UNSUPPORTED, "bwgr_mrr3_fit: not built yet");
+}
+
+int bwgr_profile(bwgr_handle* h, int enable) {
+  if (!h) return fail(BWGR_ERR_ARG, "null handle");
+  h->prof_collect();
+  if (enable) { for (int c = 0; c < 3; c++) { h->prof_ms[c] = 0; h->prof_n[c] = 0; } }
+  h->profiling = enable != 0;
+  return 0;
+}
+int bwgr_profile_read(bwgr_handle* h, double* ms, int64_t* counts) {
+  if (!h) return fail(BWGR_ERR_ARG, "null handle");
+  CU(cudaStreamSynchronize(h->stream));
+  h->prof_collect();
+  for (int c = 0; c < 3; c++) { if (ms) ms[c] = h->prof_ms[c]; if (counts) counts[c] = h->prof_n[c]; }
+  return 0;
 }
 
 int bwgr_debug_gram(bwgr_handle* h, const int32_t* perm, int block, int32_t* gram_out) {

@@ -159,6 +159,11 @@ BWGR_API int bwgr_mrr3_fit(bwgr_handle* h, int f32_variant, const double* Y, int
 /* ---- introspection for tests and the bench -------------------------------------------------- */
 /* Kernels launched by this handle since creation (the bench's gpu_launches claim). */
 BWGR_API int64_t bwgr_launch_count(bwgr_handle* h);
+/* Per-kernel device timing for the roofline report: when enabled, CUDA events bracket every kernel
+ * of the sweep loop on the handle's stream. read: ms[3] / counts[3] = {gram, sweep, epilogue} summed
+ * since enable (synchronises the stream). */
+BWGR_API int bwgr_profile(bwgr_handle* h, int enable);
+BWGR_API int bwgr_profile_read(bwgr_handle* h, double* ms, int64_t* counts);
 /* Gram blocks X_B' X_B of one sweep order (perm[p], block markers each), int32, [nblocks][block][block];
  * the tcgen05 kernel's output, exposed so tests can check it bit-exactly. */
 BWGR_API int bwgr_debug_gram(bwgr_handle* h, const int32_t* perm, int block, int32_t* gram_out);
