@@ -545,6 +545,15 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
       default: return fail(BWGR_ERR_ARG, "bad model %d", s.model);
     }
     c.C = -0.5f / std::sqrt(c.ve);
+    {  // fixed-point scale of the residuals (tensor-core passes): 8x headroom over max|y - mu|
+      float emax = 0;
+      for (float v : yt) emax = std::max(emax, std::fabs(v - mu));
+      int ex = 0;
+      if (emax > 0) std::frexp(emax, &ex);
+      if (ex < -60) ex = -60;
+      c.e_q = std::ldexp(1.0f, ex + 3 - 30);
+      c.e_qinv = std::ldexp(1.0f, 30 - 3 - ex);
+    }
     f.sc0[t] = c;
     f.vy[t] = vy; f.MSx[t] = c.MSx; f.cxx[t] = c.cxx;
     for (int64_t i = 0; i < n; i++)

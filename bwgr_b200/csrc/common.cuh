@@ -18,6 +18,8 @@ struct SysScalars {
   // constants of the fit
   float R2, alpha, vy, MSx, Rho, trAC22, Sy, pi_mix;
   float n_eff;  // rows used by this system (row masks)
+  // fixed-point scale of the residuals for the tensor-core passes: e = q * e_q, |q| <= 2^30 (power of two)
+  float e_q, e_qinv;
   float cnv;    // emEN: sum |b_old - b_new| of the last sweep
   int its;      // sweeps done
   int done;     // emEN convergence reached
@@ -167,6 +169,23 @@ __device__ __forceinline__ RuleOut marker_rule(float g, float xx, float b0, floa
     }
     o.de = o.b - b0;
   }
+  return o;
+}
+
+// Linear rules: the residual step of marker i is  de_i = a_i * g_i + c_i  with a_i, c_i independent of g
+// (g_i = current x_i'e).  emRR :335, emBA :107-111 (de = 2*(b1-b0)), BayesRR :835, BayesA :615, rotated MRR3.
+__host__ __device__ constexpr bool model_is_linear(int m) { return m == M_EMRR || m == M_EMBA || m == M_MRR || m == M_BRR || m == M_BA; }
+struct LinCoef { float a, c, kappa; };
+template <int MODEL>
+__device__ __forceinline__ LinCoef lin_coef(float xx, float b0, float vbj, const SysScalars& s, const MarkerDraws& dr) {
+  const float lmb = (MODEL == M_EMBA || MODEL == M_BA) ? s.ve * (1.0f / vbj) : s.lmb;
+  const float alpha = 1.0f / (xx + lmb);
+  LinCoef o;
+  o.kappa = (MODEL == M_EMBA) ? 2.0f : 1.0f;
+  float c = -lmb * b0 * alpha;                       // (g + xx*b0)*alpha - b0 = g*alpha - lmb*b0*alpha
+  if (MODEL == M_BRR || MODEL == M_BA) c += sqrtf(s.ve * alpha) * dr.z1;
+  o.a = o.kappa * alpha;
+  o.c = o.kappa * c;
   return o;
 }
 

@@ -41,11 +41,20 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
   const int model = a.model;
 
   double se = 0, see = 0, sey = 0, sy = 0;
+  float emax = 0.0f;
   for (int i = tid; i < a.n; i += T) {
     if (mask && !mask[i]) continue;
     const double ev = e[i], yv = y[i];
     se += ev; see += ev * ev; sey += ev * yv; sy += yv;
+    emax = fmaxf(emax, fabsf(e[i]));
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+  __shared__ float sh_max[32];
+  if ((tid & 31) == 0) sh_max[tid >> 5] = emax;
+  __syncthreads();
+  emax = 0.0f;
+  for (int w = 0; w < (T >> 5); w++) emax = fmaxf(emax, sh_max[w]);
   double sbb = 0, sd = 0, scnv = 0;
   for (int j = tid; j < a.p; j += T) {
     const double bj = b[j];
@@ -114,7 +123,6 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
         s.ve = (ee2 + s.Se) / chi_e;
       }
       s.C = -0.5f / sqrtf(s.ve);
-      s.mu += 0.0f;
       if (s.sweep > s.burn) {  // sic: i > bi, divided later by it-bi (:624-627)
         accumulate = 1;
         s.MU += (double)(s.mu + eM); s.VE += (double)s.ve; s.VB += (double)s.vb;
@@ -123,6 +131,14 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
     }
     s.mu += eM;
     s.sweep += 1;
+    {  // fixed-point scale of the residuals for the next sweep: |e| may grow 8x before it saturates 2^30
+      int ex = 0;
+      const float bound = emax + fabsf(eM);
+      if (bound > 0.0f && bound < 3.0e38f) frexpf(bound, &ex);
+      if (ex < -60) ex = -60;
+      s.e_q = ldexpf(1.0f, ex + 3 - 30);
+      s.e_qinv = ldexpf(1.0f, 30 - 3 - ex);
+    }
     *scp = s;
     s_eM = eM;
     s_acc = accumulate;

@@ -1,0 +1,513 @@
+// sweep_tc.cu -- the blocked exact Gauss-Seidel / Gibbs sweep (K1 + K5 + K2 of SURVEY 2c), v2:
+// both streaming contractions on the 5th-gen tensor cores, exact in fixed point.
+//
+// One persistent cooperative kernel per sweep.  CTA c owns the row slab [c*R, (c+1)*R) of every genotype
+// column and the matching slab of the residuals E (float master copy in shared memory).  For each block
+// of 128 markers in this sweep's order (Rcpp20260726ai.cpp:331):
+//   1. the slab of X_B is staged ONCE in shared memory (cp.async gather, double buffered, one block ahead)
+//      in the canonical SWIZZLE_128B layout [128-row atom][marker][128 B];
+//   2. g_B = X_B' E:  E is quantised to 31-bit fixed point (e = q * e_q, e_q a power of two) and split in
+//      four signed int8 limbs, so  g = sum_l 2^(8l) * (X_B' limb_l)  is FOUR columns of one
+//      tcgen05.mma kind::i8 (A = X tile, K-major; B = limb matrix, K-major; exact int32 accumulation in
+//      TMEM).  The per-CTA partial is an integer: it is added to the block accumulator in L2 with 64-bit
+//      integer atomics, so the grid-wide sum is exact and independent of the grid decomposition;
+//   3. one grid barrier; every CTA reads the same g_B and runs the in-block solve on the Gram block
+//      X_B'X_B (gram_tc.cu) held in shared memory.  Linear rules (emRR, emBA, BayesRR, BayesA, rotated
+//      MRR3: de_i = a_i*(g_i - sum_{k<i} G_ik de_k) + c_i) are a unit-lower-triangular system
+//      (I + A L) de = A g + c, solved in 32-marker blocks with 32x32 inverses computed BEFORE the barrier
+//      (they do not depend on E); the other rules walk the scalar chain.  Either way the result is the
+//      reference's Gauss-Seidel order up to float reassociation;
+//   4. E_slab -= X_B_slab * dE_B: dE is quantised to int8 limbs the same way and the SAME staged tile is
+//      read as the MN-major A operand (rows = M) of a second tcgen05.mma; X is read from HBM once per sweep.
+#include "kernels.h"
+
+namespace bwgr {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kAtomBytes = 128 * 128;  // one 128-row atom of the X tile: 128 markers x 128 B
+constexpr uint32_t kSpin = 1u << 22;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0; spin < kSpin; spin++) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return true;
+  }
+  return false;
+}
+// K-major SWIZZLE_128B operand: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t desc_k_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// MN-major SWIZZLE_128B operand: 128 contiguous bytes along M per K index, 8-K groups 1024 B apart
+// (stride byte offset); one 128-byte M block per instruction, so the leading byte offset is unused.
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(kAtomBytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__host__ __device__ constexpr uint32_t idesc_i8(int N, int a_mn) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, int& v0, int& v1, int& v2, int& v3) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ long long combine_limbs(int s0, int s1, int s2, int s3) {
+  return (long long)s0 + ((long long)s1 << 8) + ((long long)s2 << 16) + ((long long)s3 << 24);
+}
+// q (|q| <= 2^30) -> four balanced signed int8 limbs, q = l0 + 2^8 l1 + 2^16 l2 + 2^24 l3
+__device__ __forceinline__ void split_limbs(int q, int& l0, int& l1, int& l2, int& l3) {
+  l0 = (int)(signed char)(q & 0xFF); q = (q - l0) >> 8;
+  l1 = (int)(signed char)(q & 0xFF); q = (q - l1) >> 8;
+  l2 = (int)(signed char)(q & 0xFF); q = (q - l2) >> 8;
+  l3 = q;
+}
+// byte offset of element (row n, K byte kb) inside one K-major SWIZZLE_128B atom stack
+__device__ __forceinline__ uint32_t sw128_off(int n, int kb) {
+  return (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((((kb >> 4) ^ (n & 7)) & 7) << 4) + (kb & 15));
+}
+
+struct MarkerIn { float b0, xx, vbj, a, c, kappa, pad0, pad1; };
+
+struct TcSmem {
+  uint64_t mbar_g, mbar_u;
+  uint32_t tmem_base;
+  int fail;
+};
+
+struct Layout {
+  int R, NA, N, ns;
+  size_t xs, el, dl, gs, es, mt, mk, drw, dlt, total;
+};
+__host__ __device__ inline Layout make_layout(int R, int ns, bool gibbs) {
+  Layout L;
+  L.R = R; L.ns = ns;
+  L.NA = (R + 127) / 128;
+  L.N = ((4 * ns + 15) / 16) * 16;
+  size_t o = 0;
+  L.xs = o; o += (size_t)2 * L.NA * kAtomBytes;            // X tiles (1024-aligned)
+  L.el = o; o += (size_t)L.NA * (L.N / 8) * 1024;          // E limbs  [atom][N/8][8][128]
+  L.dl = o; o += (size_t)(L.N / 8) * 1024;                 // dE limbs [N/8][8][128]
+  L.gs = o; o += (size_t)128 * 128 * 4;                    // Gram block, float
+  L.es = o; o += (size_t)ns * L.NA * 128 * 4;              // E master, float [ns][NA*128]
+  L.mt = o; o += (size_t)ns * 4 * 32 * 33 * 4;             // 32x32 inverses (transposed, padded)
+  L.mk = o; o += (size_t)ns * 128 * sizeof(MarkerIn);
+  L.drw = o; o += gibbs ? (size_t)ns * 128 * sizeof(MarkerDraws) : 0;
+  L.dlt = o; o += (size_t)ns * 128 * 4;
+  L.total = o + 1024;                                      // slack for the 1024 B alignment
+  return L;
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ TcSmem S;
+  __shared__ SysScalars sc[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ns = a.nsys, p = a.g.p, G = gridDim.x;
+  const Layout L = make_layout(a.rows_per_cta, ns, model_is_gibbs(MODEL));
+  const int R = L.R, NA = L.NA, N = L.N, RS = NA * 128;
+  const int row0 = blockIdx.x * R;
+  const int nchunk = R >> 4;
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* Xs = base + L.xs;
+  unsigned char* EL = base + L.el;
+  unsigned char* DL = base + L.dl;
+  float* Gs = reinterpret_cast<float*>(base + L.gs);
+  float* Es = reinterpret_cast<float*>(base + L.es);
+  float* Mt = reinterpret_cast<float*>(base + L.mt);
+  MarkerIn* mk = reinterpret_cast<MarkerIn*>(base + L.mk);
+  MarkerDraws* drw = reinterpret_cast<MarkerDraws*>(base + L.drw);
+  float* dlt = reinterpret_cast<float*>(base + L.dlt);
+
+  // ---- one-time setup
+  if (tid < ns) sc[tid] = a.sc[tid];
+  if (tid == 0) {
+    S.fail = 0;
+    mbar_init(&S.mbar_g, 1);
+    mbar_init(&S.mbar_u, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {  // zero the operand regions (pad rows / chunks stay zero for the whole kernel)
+    uint4* z = reinterpret_cast<uint4*>(base);
+    const int nz = (int)((L.gs) >> 4);
+    for (int i = tid; i < nz; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  for (int s = 0; s < ns; s++)
+    for (int i = tid; i < RS; i += kThreads) {
+      const int r = row0 + i;
+      Es[s * RS + i] = (i < R && r < a.g.ld) ? a.e[(size_t)s * a.g.ld + r] : 0.0f;
+    }
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < (NA + 1) * N) tmem_cols <<= 1;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = S.tmem_base;
+  const uint32_t idesc_g = idesc_i8(N, 0), idesc_u = idesc_i8(N, 1);
+
+  auto issue_tile = [&](int blk) {
+    if (blk < a.nblocks) {
+      unsigned char* dst = Xs + (size_t)(blk & 1) * NA * kAtomBytes;
+      const int total = 128 * nchunk;
+      for (int idx = tid; idx < total; idx += kThreads) {
+        const int m = idx / nchunk, c = idx - m * nchunk;
+        const int pos = blk * 128 + m;
+        const int r = row0 + 16 * c;
+        unsigned char* d = dst + (c >> 3) * kAtomBytes + m * 128 + ((((c & 7) ^ (m & 7)) & 7) << 4);
+        if (pos < p && r < a.g.ld) cp_async16(smem_u32(d), a.g.x8 + (int64_t)a.perm[pos] * a.g.ld + r);
+        else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto issue_gram = [&](int blk) {
+    if (blk < a.nblocks) {
+      const float* src = a.gram + (size_t)blk * 128 * 128;
+      for (int idx = tid; idx < 128 * 128 / 4; idx += kThreads) cp_async16(smem_u32(Gs + 4 * idx), src + 4 * idx);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  issue_tile(0);
+  issue_gram(0);
+  bool fail = false;
+
+#pragma unroll 1
+  for (int blk = 0; blk < a.nblocks; blk++) {
+    const unsigned char* Xt = Xs + (size_t)(blk & 1) * NA * kAtomBytes;
+    const uint32_t par = (uint32_t)blk & 1u;
+    const int nvalid = min(128, p - blk * 128);
+
+    // ---- 1. residual slab -> int8 limbs (B operand of the g pass)
+    for (int task = tid; task < ns * nchunk; task += kThreads) {
+      const int s = task / nchunk, c = task - s * nchunk;
+      const float qinv = sc[s].e_qinv;
+      const float4* ev = reinterpret_cast<const float4*>(Es + s * RS + 16 * c);
+      uint32_t lw[4][4];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; q4++) {
+        const float4 e4 = ev[q4];
+        const float ef[4] = {e4.x, e4.y, e4.z, e4.w};
+        uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const float sv = ef[t] * qinv;
+          if (!(fabsf(sv) <= 1073741824.0f)) fail = true;
+          int l0, l1, l2, l3;
+          split_limbs(__float2int_rn(sv), l0, l1, l2, l3);
+          w0 |= (uint32_t)(l0 & 0xFF) << (8 * t); w1 |= (uint32_t)(l1 & 0xFF) << (8 * t);
+          w2 |= (uint32_t)(l2 & 0xFF) << (8 * t); w3 |= (uint32_t)(l3 & 0xFF) << (8 * t);
+        }
+        lw[0][q4] = w0; lw[1][q4] = w1; lw[2][q4] = w2; lw[3][q4] = w3;
+      }
+      unsigned char* atom = EL + (size_t)(c >> 3) * (N / 8) * 1024;
+#pragma unroll
+      for (int l = 0; l < 4; l++) {
+        const int n = 4 * s + l;
+        *reinterpret_cast<uint4*>(atom + sw128_off(n, (c & 7) * 16)) = make_uint4(lw[l][0], lw[l][1], lw[l][2], lw[l][3]);
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // this block's X tile and Gram block have landed
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    // ---- 2. g pass on the tensor core: D[marker][limb] = sum_rows X[marker][row] * limb[row]
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int at = 0; at < NA; at++) {
+        const uint64_t ad = desc_k_sw128(smem_u32(Xt + (size_t)at * kAtomBytes));
+        const uint64_t bd = desc_k_sw128(smem_u32(EL + (size_t)at * (N / 8) * 1024));
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++) umma_i8(tmem_base, ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), idesc_g, (at | k4) != 0);
+      }
+      umma_commit(&S.mbar_g);
+    }
+    // meanwhile: next X tile (the other buffer is free: its update MMAs were waited for) and the
+    // per-marker inputs of this block
+    issue_tile(blk + 1);
+    for (int idx = tid; idx < ns * 128; idx += kThreads) {
+      const int s = idx >> 7, m = idx & 127, pos = blk * 128 + m;
+      MarkerIn in = {0.0f, 1.0f, 1.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f};
+      if (pos < p && !sc[s].done) {
+        const int j = a.perm[pos];
+        in.b0 = a.b[(size_t)s * p + j];
+        in.xx = a.xx[j];
+        in.vbj = (model_has_vbj(MODEL) && a.vbv) ? a.vbv[(size_t)s * p + j] : 1.0f;
+        MarkerDraws dr;
+        dr.z1 = dr.z2 = dr.u = 0.0f; dr.chi = 1.0f;
+        if (model_is_gibbs(MODEL)) {
+          dr = marker_draws(MODEL, (uint32_t)j, (uint32_t)sc[s].sweep, (uint32_t)(a.chain0 + s), sc[s].df, a.seed_lo, a.seed_hi);
+          drw[idx] = dr;
+        }
+        if (model_is_linear(MODEL)) {
+          const LinCoef lc = lin_coef<MODEL>(in.xx, in.b0, in.vbj, sc[s], dr);
+          in.a = lc.a; in.c = lc.c; in.kappa = lc.kappa;
+        }
+      }
+      mk[idx] = in;
+    }
+    // g epilogue: TMEM -> integer partial -> L2 accumulator (thread = marker)
+    if (warp < 4) {
+      if (!mbar_wait(&S.mbar_g, par)) S.fail = 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int s = 0; s < ns; s++) {
+        int s0, s1, s2, s3;
+        tmem_ld4(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(4 * s), s0, s1, s2, s3);
+        const long long gq = combine_limbs(s0, s1, s2, s3);
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.gacc) + (size_t)(blk % 3) * ns * 128 + s * 128 + tid, (unsigned long long)gq);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(a.bar, 1u);
+    }
+
+    // ---- 3a. (linear rules) invert the four 32x32 diagonal blocks of I + A L while the barrier fills
+    if (model_is_linear(MODEL)) {
+      for (int task = warp; task < ns * 4; task += kThreads / 32) {
+        const int s = task >> 2, d = task & 3;
+        const MarkerIn* mks = mk + s * 128 + 32 * d;
+        float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          float acc = 0.0f;
+          const float* grow = Gs + (32 * d + i) * 128 + 32 * d;
+#pragma unroll
+          for (int k = 0; k < i; k++) acc = fmaf(grow[k], x[k], acc);
+          x[i] = (i == lane) ? 1.0f : -mks[i].a * acc;
+        }
+        float* mt = Mt + (size_t)(s * 4 + d) * 32 * 33 + lane * 33;  // Mt[c][i] = M[i][c], c = lane
+#pragma unroll
+        for (int i = 0; i < 32; i++) mt[i] = x[i];
+      }
+    }
+
+    // ---- 3b. grid barrier (monotonic counter, bounded spin)
+    if (tid == 0) {
+      const unsigned int target = (unsigned int)(blk + 1) * (unsigned int)G;
+      unsigned int spins = 0;
+      while (true) {
+        unsigned int v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.bar) : "memory");
+        if (v >= target) break;
+        if (++spins > (1u << 22)) { S.fail = 1; atomicExch(a.err, 3); break; }
+      }
+    }
+    __syncthreads();
+
+    // ---- 3c. in-block solve, one warp per system, replicated on every CTA
+    for (int s = warp; s < ns; s += kThreads / 32) {
+      const SysScalars Sy = sc[s];
+      const MarkerIn* mks = mk + s * 128;
+      float g[4], de[4];
+      const long long* gq = a.gacc + (size_t)(blk % 3) * ns * 128 + s * 128;
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        long long q;
+        asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(q) : "l"(gq + 32 * t + lane) : "memory");
+        g[t] = (float)((double)q * (double)Sy.e_q);
+        de[t] = 0.0f;
+      }
+      float nb[4] = {0.f, 0.f, 0.f, 0.f}, nd[4] = {1.f, 1.f, 1.f, 1.f}, nv[4] = {1.f, 1.f, 1.f, 1.f};
+      if (Sy.done) {
+        // converged system (emEN): no update
+      } else if (model_is_linear(MODEL)) {
+        float r[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) r[t] = fmaf(mks[32 * t + lane].a, g[t], mks[32 * t + lane].c);
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+          const float* mt = Mt + (size_t)(s * 4 + d) * 32 * 33 + lane;
+          float acc = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 32; k++) acc = fmaf(mt[k * 33], __shfl_sync(0xffffffffu, r[d], k), acc);
+          de[d] = acc;
+          float far[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int k = 0; k < 32; k++) {
+            const float dk = __shfl_sync(0xffffffffu, acc, k);
+            const float* grow = Gs + (32 * d + k) * 128 + lane;  // G[32d+k][32d'+lane] (symmetric)
+#pragma unroll
+            for (int d2 = 0; d2 < 4; d2++)
+              if (d2 > d) far[d2] = fmaf(grow[32 * d2], dk, far[d2]);
+          }
+#pragma unroll
+          for (int d2 = 0; d2 < 4; d2++)
+            if (d2 > d) r[d2] = fmaf(-mks[32 * d2 + lane].a, far[d2], r[d2]);
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+#pragma unroll 8
+          for (int i = 0; i < 32; i++) {
+            const int jj = 32 * t + i;
+            if (jj >= nvalid) break;
+            const float gc = __shfl_sync(0xffffffffu, g[t], i);
+            const MarkerIn in = mks[jj];
+            MarkerDraws dr;
+            if (model_is_gibbs(MODEL)) dr = drw[s * 128 + jj];
+            else { dr.z1 = dr.z2 = dr.u = 0.0f; dr.chi = 1.0f; }
+            const RuleOut ro = marker_rule<MODEL>(gc, in.xx, in.b0, in.vbj, Sy, dr);
+            if (lane == i) { nb[t] = ro.b; nd[t] = ro.d; nv[t] = ro.vbj; de[t] = ro.de; }
+            const float* grow = Gs + jj * 128 + lane;
+#pragma unroll
+            for (int tt = 0; tt < 4; tt++)
+              if (tt >= t) g[tt] = fmaf(-grow[32 * tt], ro.de, g[tt]);
+          }
+        }
+      }
+      // quantise dE to 31-bit fixed point relative to the block maximum (all CTAs compute the same scale)
+      float mx = fmaxf(fmaxf(fabsf(de[0]), fabsf(de[1])), fmaxf(fabsf(de[2]), fabsf(de[3])));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      int ex = 0;
+      if (mx > 0.0f && mx < 3.0e38f) frexpf(mx, &ex);
+      if (ex < -90) ex = -90;
+      const float dq = ldexpf(1.0f, ex - 30), dqinv = ldexpf(1.0f, 30 - ex);
+      if (!(mx < 3.0e38f)) fail = true;
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int jj = 32 * t + lane;
+        const bool valid = jj < nvalid && !Sy.done;
+        const int q = valid ? __float2int_rn(de[t] * dqinv) : 0;
+        const float deq = (float)q * dq;  // the step actually applied to E (exactly representable)
+        int l0, l1, l2, l3;
+        split_limbs(q, l0, l1, l2, l3);
+        DL[sw128_off(4 * s + 0, jj)] = (unsigned char)l0; DL[sw128_off(4 * s + 1, jj)] = (unsigned char)l1;
+        DL[sw128_off(4 * s + 2, jj)] = (unsigned char)l2; DL[sw128_off(4 * s + 3, jj)] = (unsigned char)l3;
+        if (lane == 0 && t == 0) dlt[s * 128] = dq;  // scale for the update epilogue
+        if (valid) {
+          const MarkerIn in = mks[jj];
+          float bnew, dnew = nd[t], vnew = nv[t];
+          if (model_is_linear(MODEL)) {
+            bnew = in.b0 + deq / in.kappa;
+            if (MODEL == M_EMBA) vnew = (Sy.Sb + bnew * bnew) / (Sy.df + 1.0f);
+            if (MODEL == M_BA) vnew = (Sy.Sb + bnew * bnew) / drw[s * 128 + jj].chi;
+          } else {
+            bnew = nb[t];
+          }
+          if (blockIdx.x == 0) {
+            const int j = a.perm[blk * 128 + jj];
+            a.b[(size_t)s * p + j] = bnew;
+            if (model_has_d(MODEL) && a.d) a.d[(size_t)s * p + j] = dnew;
+            if (model_has_vbj(MODEL) && MODEL != M_KMUP && a.vbv) a.vbv[(size_t)s * p + j] = vnew;
+          }
+        }
+      }
+    }
+    if (blockIdx.x == 0 && blk + 2 < a.nblocks)
+      for (int idx = tid; idx < ns * 128; idx += kThreads) a.gacc[(size_t)((blk + 2) % 3) * ns * 128 + idx] = 0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    // ---- 4. update pass on the tensor core: D[row][limb] = sum_markers X[row][marker] * dE_limb[marker]
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint64_t bd = desc_k_sw128(smem_u32(DL));
+      for (int at = 0; at < NA; at++) {
+        const uint64_t ad = desc_mn_sw128(smem_u32(Xt + (size_t)at * kAtomBytes));
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++)
+          umma_i8(tmem_base + (uint32_t)((at + 1) * N), ad + (uint64_t)(k4 * (4096 >> 4)), bd + (uint64_t)(2 * k4), idesc_u, k4 != 0);
+      }
+      umma_commit(&S.mbar_u);
+    }
+    issue_gram(blk + 1);  // Gs is free again (solve done, barrier passed)
+    if (!mbar_wait(&S.mbar_u, par)) S.fail = 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int at = warp >> 2; at < NA; at += 2) {
+      const int ra = (warp & 3) * 32 + lane;  // row inside the atom = TMEM lane
+      const int i = at * 128 + ra;
+      for (int s = 0; s < ns; s++) {
+        int s0, s1, s2, s3;
+        tmem_ld4(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((at + 1) * N + 4 * s), s0, s1, s2, s3);
+        const long long uq = combine_limbs(s0, s1, s2, s3);
+        if (i < R) Es[s * RS + i] -= (float)((double)uq * (double)dlt[s * 128]);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (S.fail) break;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (fail) atomicExch(a.err, 4);
+  if (S.fail && tid == 0) atomicCAS(a.err, 0, 2);
+  for (int s = 0; s < ns; s++)
+    for (int i = tid; i < R; i += kThreads) {
+      const int r = row0 + i;
+      if (r < a.g.ld) a.e[(size_t)s * a.g.ld + r] = Es[s * RS + i];
+    }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+template <int MODEL>
+void launch_model(const SweepArgs& a, int grid, cudaStream_t st) {
+  const Layout L = make_layout(a.rows_per_cta, a.nsys, model_is_gibbs(MODEL));
+  cudaFuncSetAttribute(sweep_tc_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+  SweepArgs args = a;
+  void* params[] = {&args};
+  cudaLaunchCooperativeKernel((void*)sweep_tc_kernel<MODEL>, dim3(grid), dim3(kThreads), params, L.total, st);
+}
+
+}  // namespace
+
+size_t sweep_blocked_smem(int rows_per_cta, int nsys) { return make_layout(rows_per_cta, nsys, true).total + 2048; }
+
+void launch_sweep_blocked(const SweepArgs& a, int grid, cudaStream_t st) {
+  switch (a.model) {
+    case M_EMRR: launch_model<M_EMRR>(a, grid, st); break;
+    case M_EMBA: launch_model<M_EMBA>(a, grid, st); break;
+    case M_EMBB: launch_model<M_EMBB>(a, grid, st); break;
+    case M_EMBC: launch_model<M_EMBC>(a, grid, st); break;
+    case M_EMBL: launch_model<M_EMBL>(a, grid, st); break;
+    case M_EMEN: launch_model<M_EMEN>(a, grid, st); break;
+    case M_BRR: launch_model<M_BRR>(a, grid, st); break;
+    case M_BA: launch_model<M_BA>(a, grid, st); break;
+    case M_BB: launch_model<M_BB>(a, grid, st); break;
+    case M_BC: launch_model<M_BC>(a, grid, st); break;
+    case M_KMUP: launch_model<M_KMUP>(a, grid, st); break;
+    case M_MRR: launch_model<M_MRR>(a, grid, st); break;
+    default: break;
+  }
+}
+
+}  // namespace bwgr
