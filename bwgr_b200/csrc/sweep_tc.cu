@@ -93,7 +93,7 @@ __device__ __forceinline__ uint32_t sw128_off(int n, int kb) {
   return (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((((kb >> 4) ^ (n & 7)) & 7) << 4) + (kb & 15));
 }
 
-struct MarkerIn { float b0, xx, vbj, a, c, kappa, pad0, pad1; };
+struct MarkerIn { float b0, xx, vbj, a, c, kappa; int j; float pad; };
 
 struct TcSmem {
   uint64_t mbar_g, mbar_u;
@@ -103,7 +103,7 @@ struct TcSmem {
 
 struct Layout {
   int R, NA, N, ns;
-  size_t xs, el, dl, gs, es, mt, mk, drw, dlt, total;
+  size_t xs, el, dl, gs, es, mt, mk, drw, dlt, prm, total;
 };
 __host__ __device__ inline Layout make_layout(int R, int ns, bool gibbs) {
   Layout L;
@@ -117,9 +117,10 @@ __host__ __device__ inline Layout make_layout(int R, int ns, bool gibbs) {
   L.gs = o; o += (size_t)128 * 128 * 4;                    // Gram block, float
   L.es = o; o += (size_t)ns * L.NA * 128 * 4;              // E master, float [ns][NA*128]
   L.mt = o; o += (size_t)ns * 4 * 32 * 33 * 4;             // 32x32 inverses (transposed, padded)
-  L.mk = o; o += (size_t)ns * 128 * sizeof(MarkerIn);
-  L.drw = o; o += gibbs ? (size_t)ns * 128 * sizeof(MarkerDraws) : 0;
-  L.dlt = o; o += (size_t)ns * 128 * 4;
+  L.mk = o; o += (size_t)2 * ns * 128 * sizeof(MarkerIn);  // per-marker inputs, double buffered
+  L.drw = o; o += gibbs ? (size_t)2 * ns * 128 * sizeof(MarkerDraws) : 0;
+  L.dlt = o; o += (size_t)ns * 16;                         // dE scale per system
+  L.prm = o; o += (size_t)3 * 128 * 4;                     // marker ids of three consecutive blocks
   L.total = o + 1024;                                      // slack for the 1024 B alignment
   return L;
 }
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
   MarkerIn* mk = reinterpret_cast<MarkerIn*>(base + L.mk);
   MarkerDraws* drw = reinterpret_cast<MarkerDraws*>(base + L.drw);
   float* dlt = reinterpret_cast<float*>(base + L.dlt);
+  int* prm = reinterpret_cast<int*>(base + L.prm);
 
   // ---- one-time setup
   if (tid < ns) sc[tid] = a.sc[tid];
@@ -164,6 +166,15 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
       const int r = row0 + i;
       Es[s * RS + i] = (i < R && r < a.g.ld) ? a.e[(size_t)s * a.g.ld + r] : 0.0f;
     }
+  // marker ids of block blk live in prm[(blk % 3) * 128 ..]; -1 = past the end
+  auto load_perm = [&](int blk) {
+    if (tid < 128) {
+      const int pos = blk * 128 + tid;
+      prm[(blk % 3) * 128 + tid] = (blk < a.nblocks && pos < p) ? a.perm[pos] : -1;
+    }
+  };
+  load_perm(0);
+  load_perm(1);
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < (NA + 1) * N) tmem_cols <<= 1;
   if (warp == 0) {
@@ -176,17 +187,19 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
   const uint32_t tmem_base = S.tmem_base;
   const uint32_t idesc_g = idesc_i8(N, 0), idesc_u = idesc_i8(N, 1);
 
+  // gather the slab of block blk: one warp per marker column, lanes = consecutive 16-byte chunks
   auto issue_tile = [&](int blk) {
     if (blk < a.nblocks) {
       unsigned char* dst = Xs + (size_t)(blk & 1) * NA * kAtomBytes;
-      const int total = 128 * nchunk;
-      for (int idx = tid; idx < total; idx += kThreads) {
-        const int m = idx / nchunk, c = idx - m * nchunk;
-        const int pos = blk * 128 + m;
-        const int r = row0 + 16 * c;
-        unsigned char* d = dst + (c >> 3) * kAtomBytes + m * 128 + ((((c & 7) ^ (m & 7)) & 7) << 4);
-        if (pos < p && r < a.g.ld) cp_async16(smem_u32(d), a.g.x8 + (int64_t)a.perm[pos] * a.g.ld + r);
-        else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+      const int* pm = prm + (blk % 3) * 128;
+      for (int m = warp; m < 128; m += kThreads / 32) {
+        const int j = pm[m];
+        const int8_t* col = a.g.x8 + (int64_t)(j < 0 ? 0 : j) * a.g.ld + row0;
+        for (int c = lane; c < nchunk; c += 32) {
+          unsigned char* d = dst + (c >> 3) * kAtomBytes + m * 128 + ((((c & 7) ^ (m & 7)) & 7) << 4);
+          if (j >= 0 && row0 + 16 * c < a.g.ld) cp_async16(smem_u32(d), col + 16 * c);
+          else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+        }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -198,51 +211,67 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  // per-marker inputs of block blk (b0, xx, per-marker variance, linear coefficients, draws): they do not
+  // depend on the residuals, so they are fetched one block ahead
+  auto load_markers = [&](int blk, int t0, int nt) {
+    if (blk >= a.nblocks) return;
+    MarkerIn* mkb = mk + (size_t)(blk & 1) * ns * 128;
+    MarkerDraws* drb = drw + (size_t)(blk & 1) * ns * 128;
+    const int* pm = prm + (blk % 3) * 128;
+    for (int idx = t0; idx < ns * 128; idx += nt) {
+      const int s = idx >> 7, m = idx & 127;
+      const int j = pm[m];
+      MarkerIn in = {0.0f, 1.0f, 1.0f, 0.0f, 0.0f, 1.0f, j, 0.0f};
+      if (j >= 0 && !sc[s].done) {
+        in.b0 = a.b[(size_t)s * p + j];
+        in.xx = a.xx[j];
+        in.vbj = (model_has_vbj(MODEL) && a.vbv) ? a.vbv[(size_t)s * p + j] : 1.0f;
+        MarkerDraws dr;
+        dr.z1 = dr.z2 = dr.u = 0.0f; dr.chi = 1.0f;
+        if (model_is_gibbs(MODEL)) {
+          dr = marker_draws(MODEL, (uint32_t)j, (uint32_t)sc[s].sweep, (uint32_t)(a.chain0 + s), sc[s].df, a.seed_lo, a.seed_hi);
+          drb[idx] = dr;
+        }
+        if (model_is_linear(MODEL)) {
+          const LinCoef lc = lin_coef<MODEL>(in.xx, in.b0, in.vbj, sc[s], dr);
+          in.a = lc.a; in.c = lc.c; in.kappa = lc.kappa;
+        }
+      }
+      mkb[idx] = in;
+    }
+  };
+  // residual row i of system s -> four int8 limbs in the B operand of the g pass
+  auto store_limbs = [&](int s, int i, float e, float qinv, bool& bad) {
+    const float sv = e * qinv;
+    if (!(fabsf(sv) <= 1073741824.0f)) bad = true;
+    int l0, l1, l2, l3;
+    split_limbs(__float2int_rn(sv), l0, l1, l2, l3);
+    unsigned char* atom = EL + (size_t)(i >> 7) * (N / 8) * 1024;
+    const int kb = i & 127;
+    atom[sw128_off(4 * s + 0, kb)] = (unsigned char)l0; atom[sw128_off(4 * s + 1, kb)] = (unsigned char)l1;
+    atom[sw128_off(4 * s + 2, kb)] = (unsigned char)l2; atom[sw128_off(4 * s + 3, kb)] = (unsigned char)l3;
+  };
 
+  bool fail = false, lfail = false;
   issue_tile(0);
   issue_gram(0);
-  bool fail = false;
+  load_markers(0, tid, kThreads);
+  for (int s = 0; s < ns; s++)
+    for (int i = tid; i < R; i += kThreads) store_limbs(s, i, Es[s * RS + i], sc[s].e_qinv, fail);
 
 #pragma unroll 1
   for (int blk = 0; blk < a.nblocks; blk++) {
     const unsigned char* Xt = Xs + (size_t)(blk & 1) * NA * kAtomBytes;
     const uint32_t par = (uint32_t)blk & 1u;
     const int nvalid = min(128, p - blk * 128);
+    MarkerIn* mkb = mk + (size_t)(blk & 1) * ns * 128;
+    MarkerDraws* drb = drw + (size_t)(blk & 1) * ns * 128;
 
-    // ---- 1. residual slab -> int8 limbs (B operand of the g pass)
-    for (int task = tid; task < ns * nchunk; task += kThreads) {
-      const int s = task / nchunk, c = task - s * nchunk;
-      const float qinv = sc[s].e_qinv;
-      const float4* ev = reinterpret_cast<const float4*>(Es + s * RS + 16 * c);
-      uint32_t lw[4][4];
-#pragma unroll
-      for (int q4 = 0; q4 < 4; q4++) {
-        const float4 e4 = ev[q4];
-        const float ef[4] = {e4.x, e4.y, e4.z, e4.w};
-        uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-          const float sv = ef[t] * qinv;
-          if (!(fabsf(sv) <= 1073741824.0f)) fail = true;
-          int l0, l1, l2, l3;
-          split_limbs(__float2int_rn(sv), l0, l1, l2, l3);
-          w0 |= (uint32_t)(l0 & 0xFF) << (8 * t); w1 |= (uint32_t)(l1 & 0xFF) << (8 * t);
-          w2 |= (uint32_t)(l2 & 0xFF) << (8 * t); w3 |= (uint32_t)(l3 & 0xFF) << (8 * t);
-        }
-        lw[0][q4] = w0; lw[1][q4] = w1; lw[2][q4] = w2; lw[3][q4] = w3;
-      }
-      unsigned char* atom = EL + (size_t)(c >> 3) * (N / 8) * 1024;
-#pragma unroll
-      for (int l = 0; l < 4; l++) {
-        const int n = 4 * s + l;
-        *reinterpret_cast<uint4*>(atom + sw128_off(n, (c & 7) * 16)) = make_uint4(lw[l][0], lw[l][1], lw[l][2], lw[l][3]);
-      }
-    }
     asm volatile("cp.async.wait_group 0;" ::: "memory");   // this block's X tile and Gram block have landed
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // limbs (generic stores) -> tensor core
+    if (__syncthreads_or(lfail ? 1 : 0)) break;  // uniform exit if any wait of the previous block timed out
 
-    // ---- 2. g pass on the tensor core: D[marker][limb] = sum_rows X[marker][row] * limb[row]
+    // ---- 1. g pass on the tensor core: D[marker][limb] = sum_rows X[marker][row] * limb[row]
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int at = 0; at < NA; at++) {
@@ -253,33 +282,13 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
       }
       umma_commit(&S.mbar_g);
     }
-    // meanwhile: next X tile (the other buffer is free: its update MMAs were waited for) and the
-    // per-marker inputs of this block
-    issue_tile(blk + 1);
-    for (int idx = tid; idx < ns * 128; idx += kThreads) {
-      const int s = idx >> 7, m = idx & 127, pos = blk * 128 + m;
-      MarkerIn in = {0.0f, 1.0f, 1.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f};
-      if (pos < p && !sc[s].done) {
-        const int j = a.perm[pos];
-        in.b0 = a.b[(size_t)s * p + j];
-        in.xx = a.xx[j];
-        in.vbj = (model_has_vbj(MODEL) && a.vbv) ? a.vbv[(size_t)s * p + j] : 1.0f;
-        MarkerDraws dr;
-        dr.z1 = dr.z2 = dr.u = 0.0f; dr.chi = 1.0f;
-        if (model_is_gibbs(MODEL)) {
-          dr = marker_draws(MODEL, (uint32_t)j, (uint32_t)sc[s].sweep, (uint32_t)(a.chain0 + s), sc[s].df, a.seed_lo, a.seed_hi);
-          drw[idx] = dr;
-        }
-        if (model_is_linear(MODEL)) {
-          const LinCoef lc = lin_coef<MODEL>(in.xx, in.b0, in.vbj, sc[s], dr);
-          in.a = lc.a; in.c = lc.c; in.kappa = lc.kappa;
-        }
-      }
-      mk[idx] = in;
-    }
-    // g epilogue: TMEM -> integer partial -> L2 accumulator (thread = marker)
-    if (warp < 4) {
-      if (!mbar_wait(&S.mbar_g, par)) S.fail = 1;
+    load_perm(blk + 2);
+    issue_tile(blk + 1);  // the other buffer is free: its update MMAs were waited for
+    if (warp >= 4) {
+      load_markers(blk + 1, tid - 128, 128);
+    } else {
+      // g epilogue: TMEM -> integer partial -> L2 accumulator (thread = marker)
+      if (!mbar_wait(&S.mbar_g, par)) lfail = true;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int s = 0; s < ns; s++) {
         int s0, s1, s2, s3;
@@ -295,19 +304,25 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
       atomicAdd(a.bar, 1u);
     }
 
-    // ---- 3a. (linear rules) invert the four 32x32 diagonal blocks of I + A L while the barrier fills
+    // ---- 2a. (linear rules) invert the four 32x32 diagonal blocks of I + A L while the barrier fills
     if (model_is_linear(MODEL)) {
       for (int task = warp; task < ns * 4; task += kThreads / 32) {
         const int s = task >> 2, d = task & 3;
-        const MarkerIn* mks = mk + s * 128 + 32 * d;
+        const MarkerIn* mks = mkb + s * 128 + 32 * d;
         float x[32];
 #pragma unroll
         for (int i = 0; i < 32; i++) {
-          float acc = 0.0f;
-          const float* grow = Gs + (32 * d + i) * 128 + 32 * d;
+          float acc0 = 0.0f, acc1 = 0.0f;
+          const float4* grow = reinterpret_cast<const float4*>(Gs + (32 * d + i) * 128 + 32 * d);
 #pragma unroll
-          for (int k = 0; k < i; k++) acc = fmaf(grow[k], x[k], acc);
-          x[i] = (i == lane) ? 1.0f : -mks[i].a * acc;
+          for (int k4 = 0; k4 < (i + 3) / 4; k4++) {
+            const float4 gv = grow[k4];
+            if (4 * k4 + 0 < i) acc0 = fmaf(gv.x, x[4 * k4 + 0], acc0);
+            if (4 * k4 + 1 < i) acc1 = fmaf(gv.y, x[4 * k4 + 1], acc1);
+            if (4 * k4 + 2 < i) acc0 = fmaf(gv.z, x[4 * k4 + 2], acc0);
+            if (4 * k4 + 3 < i) acc1 = fmaf(gv.w, x[4 * k4 + 3], acc1);
+          }
+          x[i] = (i == lane) ? 1.0f : -mks[i].a * (acc0 + acc1);
         }
         float* mt = Mt + (size_t)(s * 4 + d) * 32 * 33 + lane * 33;  // Mt[c][i] = M[i][c], c = lane
 #pragma unroll
@@ -315,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
       }
     }
 
-    // ---- 3b. grid barrier (monotonic counter, bounded spin)
+    // ---- 2b. grid barrier (monotonic counter, bounded spin)
     if (tid == 0) {
       const unsigned int target = (unsigned int)(blk + 1) * (unsigned int)G;
       unsigned int spins = 0;
@@ -323,15 +338,15 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
         unsigned int v;
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.bar) : "memory");
         if (v >= target) break;
-        if (++spins > (1u << 22)) { S.fail = 1; atomicExch(a.err, 3); break; }
+        if (++spins > (1u << 22)) { lfail = true; atomicExch(a.err, 3); break; }
       }
     }
     __syncthreads();
 
-    // ---- 3c. in-block solve, one warp per system, replicated on every CTA
+    // ---- 2c. in-block solve, one warp per system, replicated on every CTA
     for (int s = warp; s < ns; s += kThreads / 32) {
       const SysScalars Sy = sc[s];
-      const MarkerIn* mks = mk + s * 128;
+      const MarkerIn* mks = mkb + s * 128;
       float g[4], de[4];
       const long long* gq = a.gacc + (size_t)(blk % 3) * ns * 128 + s * 128;
 #pragma unroll
@@ -351,22 +366,25 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
 #pragma unroll
         for (int d = 0; d < 4; d++) {
           const float* mt = Mt + (size_t)(s * 4 + d) * 32 * 33 + lane;
-          float acc = 0.0f;
+          float ac[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int k = 0; k < 32; k++) acc = fmaf(mt[k * 33], __shfl_sync(0xffffffffu, r[d], k), acc);
+          for (int k = 0; k < 32; k++) ac[k & 3] = fmaf(mt[k * 33], __shfl_sync(0xffffffffu, r[d], k), ac[k & 3]);
+          const float acc = (ac[0] + ac[1]) + (ac[2] + ac[3]);
           de[d] = acc;
-          float far[4] = {0.f, 0.f, 0.f, 0.f};
+          if (d < 3) {
+            float far[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
-          for (int k = 0; k < 32; k++) {
-            const float dk = __shfl_sync(0xffffffffu, acc, k);
-            const float* grow = Gs + (32 * d + k) * 128 + lane;  // G[32d+k][32d'+lane] (symmetric)
+            for (int k = 0; k < 32; k++) {
+              const float dk = __shfl_sync(0xffffffffu, acc, k);
+              const float* grow = Gs + (32 * d + k) * 128 + lane;  // G[32d+k][32d'+lane] (symmetric)
+#pragma unroll
+              for (int d2 = 0; d2 < 4; d2++)
+                if (d2 > d) far[d2][k & 1] = fmaf(grow[32 * d2], dk, far[d2][k & 1]);
+            }
 #pragma unroll
             for (int d2 = 0; d2 < 4; d2++)
-              if (d2 > d) far[d2] = fmaf(grow[32 * d2], dk, far[d2]);
+              if (d2 > d) r[d2] = fmaf(-mks[32 * d2 + lane].a, far[d2][0] + far[d2][1], r[d2]);
           }
-#pragma unroll
-          for (int d2 = 0; d2 < 4; d2++)
-            if (d2 > d) r[d2] = fmaf(-mks[32 * d2 + lane].a, far[d2], r[d2]);
         }
       } else {
 #pragma unroll
@@ -378,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
             const float gc = __shfl_sync(0xffffffffu, g[t], i);
             const MarkerIn in = mks[jj];
             MarkerDraws dr;
-            if (model_is_gibbs(MODEL)) dr = drw[s * 128 + jj];
+            if (model_is_gibbs(MODEL)) dr = drb[s * 128 + jj];
             else { dr.z1 = dr.z2 = dr.u = 0.0f; dr.chi = 1.0f; }
             const RuleOut ro = marker_rule<MODEL>(gc, in.xx, in.b0, in.vbj, Sy, dr);
             if (lane == i) { nb[t] = ro.b; nd[t] = ro.d; nv[t] = ro.vbj; de[t] = ro.de; }
@@ -398,6 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
       if (ex < -90) ex = -90;
       const float dq = ldexpf(1.0f, ex - 30), dqinv = ldexpf(1.0f, 30 - ex);
       if (!(mx < 3.0e38f)) fail = true;
+      if (lane == 0) dlt[s * 4] = dq;  // scale for the update epilogue
 #pragma unroll
       for (int t = 0; t < 4; t++) {
         const int jj = 32 * t + lane;
@@ -408,22 +427,20 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
         split_limbs(q, l0, l1, l2, l3);
         DL[sw128_off(4 * s + 0, jj)] = (unsigned char)l0; DL[sw128_off(4 * s + 1, jj)] = (unsigned char)l1;
         DL[sw128_off(4 * s + 2, jj)] = (unsigned char)l2; DL[sw128_off(4 * s + 3, jj)] = (unsigned char)l3;
-        if (lane == 0 && t == 0) dlt[s * 128] = dq;  // scale for the update epilogue
         if (valid) {
           const MarkerIn in = mks[jj];
           float bnew, dnew = nd[t], vnew = nv[t];
           if (model_is_linear(MODEL)) {
             bnew = in.b0 + deq / in.kappa;
             if (MODEL == M_EMBA) vnew = (Sy.Sb + bnew * bnew) / (Sy.df + 1.0f);
-            if (MODEL == M_BA) vnew = (Sy.Sb + bnew * bnew) / drw[s * 128 + jj].chi;
+            if (MODEL == M_BA) vnew = (Sy.Sb + bnew * bnew) / drb[s * 128 + jj].chi;
           } else {
             bnew = nb[t];
           }
           if (blockIdx.x == 0) {
-            const int j = a.perm[blk * 128 + jj];
-            a.b[(size_t)s * p + j] = bnew;
-            if (model_has_d(MODEL) && a.d) a.d[(size_t)s * p + j] = dnew;
-            if (model_has_vbj(MODEL) && MODEL != M_KMUP && a.vbv) a.vbv[(size_t)s * p + j] = vnew;
+            a.b[(size_t)s * p + in.j] = bnew;
+            if (model_has_d(MODEL) && a.d) a.d[(size_t)s * p + in.j] = dnew;
+            if (model_has_vbj(MODEL) && MODEL != M_KMUP && a.vbv) a.vbv[(size_t)s * p + in.j] = vnew;
           }
         }
       }
@@ -433,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
-    // ---- 4. update pass on the tensor core: D[row][limb] = sum_markers X[row][marker] * dE_limb[marker]
+    // ---- 3. update pass on the tensor core: D[row][limb] = sum_markers X[row][marker] * dE_limb[marker]
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint64_t bd = desc_k_sw128(smem_u32(DL));
@@ -446,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
       umma_commit(&S.mbar_u);
     }
     issue_gram(blk + 1);  // Gs is free again (solve done, barrier passed)
-    if (!mbar_wait(&S.mbar_u, par)) S.fail = 1;
+    if (!mbar_wait(&S.mbar_u, par)) lfail = true;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (int at = warp >> 2; at < NA; at += 2) {
       const int ra = (warp & 3) * 32 + lane;  // row inside the atom = TMEM lane
@@ -455,17 +472,19 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
         int s0, s1, s2, s3;
         tmem_ld4(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((at + 1) * N + 4 * s), s0, s1, s2, s3);
         const long long uq = combine_limbs(s0, s1, s2, s3);
-        if (i < R) Es[s * RS + i] -= (float)((double)uq * (double)dlt[s * 128]);
+        if (i < R) {
+          const float e = Es[s * RS + i] - (float)((double)uq * (double)dlt[s * 4]);
+          Es[s * RS + i] = e;
+          store_limbs(s, i, e, sc[s].e_qinv, fail);  // B operand of the next block's g pass
+        }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (S.fail) break;
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   if (fail) atomicExch(a.err, 4);
-  if (S.fail && tid == 0) atomicCAS(a.err, 0, 2);
+  if (lfail) atomicCAS(a.err, 0, 2);
   for (int s = 0; s < ns; s++)
     for (int i = tid; i < R; i += kThreads) {
       const int r = row0 + i;
