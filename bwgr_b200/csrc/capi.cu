@@ -593,7 +593,7 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
     f.rows_per_cta = (int)(((ld + grid0 - 1) / grid0 + 15) / 16 * 16);
     f.grid = (int)((ld + f.rows_per_cta - 1) / f.rows_per_cta);
     f.nblocks = (int)((p + kBlk - 1) / kBlk);
-    if (f.gram.alloc((size_t)f.nblocks * kBlk * kBlk) != cudaSuccess || f.gacc.alloc((size_t)3 * ns * kBlk) != cudaSuccess || f.bar.alloc(1) != cudaSuccess)
+    if (f.gram.alloc((size_t)f.nblocks * kBlk * kBlk) != cudaSuccess || f.gacc.alloc((size_t)f.nblocks * ns * kBlk) != cudaSuccess || f.bar.alloc(1) != cudaSuccess)
       return fail(BWGR_ERR_CUDA, "cudaMalloc(blocked workspace) failed");
   }
   f.active = true;
@@ -644,7 +644,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
         h->launches++;
         f.gram_cached = true;
       }
-      CU(cudaMemsetAsync(f.gacc.p, 0, sizeof(long long) * 3 * f.nsys * kBlk, h->stream));
+      CU(cudaMemsetAsync(f.gacc.p, 0, sizeof(long long) * (size_t)f.nblocks * f.nsys * kBlk, h->stream));
       CU(cudaMemsetAsync(f.bar.p, 0, sizeof(unsigned int), h->stream));
       SweepArgs a;
       memset(&a, 0, sizeof a);

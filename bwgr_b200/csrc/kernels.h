@@ -83,7 +83,7 @@ struct SweepArgs {
   const float* xx;       // [p]
   SysScalars* sc;        // [nsys]
   float* B; float* D; float* VBv;  // Gibbs posterior sums or nullptr
-  long long* gacc;       // [3][nsys][128] fixed-point block accumulators (zeroed before launch)
+  long long* gacc;       // [nblocks][nsys][128] block accumulators: (sum of integer partials << 8) + arrival count; zeroed before launch
   unsigned int* bar;     // grid barrier counter (zeroed before launch)
   float g_quantum;       // value of one fixed-point unit of g
   float g_limit;         // |partial g| above this -> err

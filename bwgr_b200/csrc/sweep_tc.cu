@@ -11,7 +11,9 @@
 //      tcgen05.mma kind::i8 (A = X tile, K-major; B = limb matrix, K-major; exact int32 accumulation in
 //      TMEM).  The per-CTA partial is an integer: it is added to the block accumulator in L2 with 64-bit
 //      integer atomics, so the grid-wide sum is exact and independent of the grid decomposition;
-//   3. one grid barrier; every CTA reads the same g_B and runs the in-block solve on the Gram block
+//      each CTA adds (partial << 8) + 1, so every 64-bit word carries its own arrival count in the low byte
+//      and readers simply poll the words they need -- no separate grid barrier, no fence;
+//   3. every CTA reads the same g_B and runs the in-block solve on the Gram block
 //      X_B'X_B (gram_tc.cu) held in shared memory.  Linear rules (emRR, emBA, BayesRR, BayesA, rotated
 //      MRR3: de_i = a_i*(g_i - sum_{k<i} G_ik de_k) + c_i) are a unit-lower-triangular system
 //      (I + A L) de = A g + c, solved in 32-marker blocks with 32x32 inverses computed BEFORE the barrier
@@ -28,6 +30,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kAtomBytes = 128 * 128;  // one 128-row atom of the X tile: 128 markers x 128 B
 constexpr uint32_t kSpin = 1u << 22;
+constexpr int kGS = 132;  // row stride (floats) of the Gram block in shared memory: conflict-free LDS.128 down a column
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -93,7 +96,7 @@ __device__ __forceinline__ uint32_t sw128_off(int n, int kb) {
   return (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((((kb >> 4) ^ (n & 7)) & 7) << 4) + (kb & 15));
 }
 
-struct MarkerIn { float b0, xx, vbj, a, c, kappa; int j; float pad; };
+struct MarkerIn { float b0, xx, vbj, a, c, ikappa; int j; float pad; };
 
 struct TcSmem {
   uint64_t mbar_g, mbar_u;
@@ -103,7 +106,7 @@ struct TcSmem {
 
 struct Layout {
   int R, NA, N, ns;
-  size_t xs, el, dl, gs, es, mt, mk, drw, dlt, prm, total;
+  size_t xs, el, dl, gs, es, mt, mk, drw, dlt, prm, rb, total;
 };
 __host__ __device__ inline Layout make_layout(int R, int ns, bool gibbs) {
   Layout L;
@@ -114,13 +117,14 @@ __host__ __device__ inline Layout make_layout(int R, int ns, bool gibbs) {
   L.xs = o; o += (size_t)2 * L.NA * kAtomBytes;            // X tiles (1024-aligned)
   L.el = o; o += (size_t)L.NA * (L.N / 8) * 1024;          // E limbs  [atom][N/8][8][128]
   L.dl = o; o += (size_t)(L.N / 8) * 1024;                 // dE limbs [N/8][8][128]
-  L.gs = o; o += (size_t)128 * 128 * 4;                    // Gram block, float
+  L.gs = o; o += (size_t)128 * kGS * 4;                    // Gram block, float, padded rows
   L.es = o; o += (size_t)ns * L.NA * 128 * 4;              // E master, float [ns][NA*128]
-  L.mt = o; o += (size_t)ns * 4 * 32 * 33 * 4;             // 32x32 inverses (transposed, padded)
+  L.mt = o; o += (size_t)ns * 4 * 8 * kGS * 4;             // 32x32 inverses, [k/4][row][4] with padded k/4 stride
   L.mk = o; o += (size_t)2 * ns * 128 * sizeof(MarkerIn);  // per-marker inputs, double buffered
   L.drw = o; o += gibbs ? (size_t)2 * ns * 128 * sizeof(MarkerDraws) : 0;
   L.dlt = o; o += (size_t)ns * 16;                         // dE scale per system
   L.prm = o; o += (size_t)3 * 128 * 4;                     // marker ids of three consecutive blocks
+  L.rb = o; o += (size_t)ns * 32 * 4;                      // broadcast buffer of the triangular solve
   L.total = o + 1024;                                      // slack for the 1024 B alignment
   return L;
 }
@@ -147,6 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
   MarkerDraws* drw = reinterpret_cast<MarkerDraws*>(base + L.drw);
   float* dlt = reinterpret_cast<float*>(base + L.dlt);
   int* prm = reinterpret_cast<int*>(base + L.prm);
+  float* rb = reinterpret_cast<float*>(base + L.rb);
 
   // ---- one-time setup
   if (tid < ns) sc[tid] = a.sc[tid];
@@ -187,18 +192,28 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
   const uint32_t tmem_base = S.tmem_base;
   const uint32_t idesc_g = idesc_i8(N, 0), idesc_u = idesc_i8(N, 1);
 
-  // gather the slab of block blk: one warp per marker column, lanes = consecutive 16-byte chunks
-  auto issue_tile = [&](int blk) {
-    if (blk < a.nblocks) {
-      unsigned char* dst = Xs + (size_t)(blk & 1) * NA * kAtomBytes;
+  // gather the slab of block blk: one warp per marker column, lanes = consecutive 16-byte chunks.
+  // w0/nw: which warps take part (the prefetch runs beside the solve, on the warps that do not solve)
+  auto issue_tile = [&](int blk, int w0, int nw) {
+    if (blk < a.nblocks && warp >= w0) {
+      const uint32_t dst = smem_u32(Xs + (size_t)(blk & 1) * NA * kAtomBytes);
       const int* pm = prm + (blk % 3) * 128;
-      for (int m = warp; m < 128; m += kThreads / 32) {
+      const bool two = lane + 32 < nchunk;  // slabs longer than 512 rows are not built (NA <= 4)
+      const uint32_t off0 = (uint32_t)((lane >> 3) * kAtomBytes + ((lane & 7) << 4));
+      const uint32_t off1 = (uint32_t)(((lane + 32) >> 3) * kAtomBytes + ((lane & 7) << 4));
+      const bool in0 = lane < nchunk && row0 + 16 * lane < a.g.ld, in1 = two && row0 + 16 * (lane + 32) < a.g.ld;
+      const int8_t* xbase = a.g.x8 + row0 + 16 * lane;
+      for (int m = warp - w0; m < 128; m += nw) {
         const int j = pm[m];
-        const int8_t* col = a.g.x8 + (int64_t)(j < 0 ? 0 : j) * a.g.ld + row0;
-        for (int c = lane; c < nchunk; c += 32) {
-          unsigned char* d = dst + (c >> 3) * kAtomBytes + m * 128 + ((((c & 7) ^ (m & 7)) & 7) << 4);
-          if (j >= 0 && row0 + 16 * c < a.g.ld) cp_async16(smem_u32(d), col + 16 * c);
-          else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+        const uint32_t dm = dst + (uint32_t)(m * 128), sw = (uint32_t)((m & 7) << 4);
+        const int8_t* col = xbase + (int64_t)(j < 0 ? 0 : j) * a.g.ld;
+        if (lane < nchunk) {
+          if (j >= 0 && in0) cp_async16(dm + (off0 ^ sw), col);
+          else asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dm + (off0 ^ sw)), "r"(0) : "memory");
+        }
+        if (two) {
+          if (j >= 0 && in1) cp_async16(dm + (off1 ^ sw), col + 512);
+          else asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dm + (off1 ^ sw)), "r"(0) : "memory");
         }
       }
     }
@@ -207,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
   auto issue_gram = [&](int blk) {
     if (blk < a.nblocks) {
       const float* src = a.gram + (size_t)blk * 128 * 128;
-      for (int idx = tid; idx < 128 * 128 / 4; idx += kThreads) cp_async16(smem_u32(Gs + 4 * idx), src + 4 * idx);
+      for (int idx = tid; idx < 128 * 128 / 4; idx += kThreads) cp_async16(smem_u32(Gs + (idx >> 5) * kGS + 4 * (idx & 31)), src + 4 * idx);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -234,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
         }
         if (model_is_linear(MODEL)) {
           const LinCoef lc = lin_coef<MODEL>(in.xx, in.b0, in.vbj, sc[s], dr);
-          in.a = lc.a; in.c = lc.c; in.kappa = lc.kappa;
+          in.a = lc.a; in.c = lc.c; in.ikappa = 1.0f / lc.kappa;
         }
       }
       mkb[idx] = in;
@@ -253,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
   };
 
   bool fail = false, lfail = false;
-  issue_tile(0);
+  issue_tile(0, 0, kThreads / 32);
   issue_gram(0);
   load_markers(0, tid, kThreads);
   for (int s = 0; s < ns; s++)
@@ -266,6 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
     const int nvalid = min(128, p - blk * 128);
     MarkerIn* mkb = mk + (size_t)(blk & 1) * ns * 128;
     MarkerDraws* drb = drw + (size_t)(blk & 1) * ns * 128;
+    long long* gblk = a.gacc + (size_t)blk * ns * 128;  // this block's accumulators (zeroed by the host)
 
     asm volatile("cp.async.wait_group 0;" ::: "memory");   // this block's X tile and Gram block have landed
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // limbs (generic stores) -> tensor core
@@ -282,38 +298,28 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
       }
       umma_commit(&S.mbar_g);
     }
-    load_perm(blk + 2);
-    issue_tile(blk + 1);  // the other buffer is free: its update MMAs were waited for
-    if (warp >= 4) {
-      load_markers(blk + 1, tid - 128, 128);
-    } else {
-      // g epilogue: TMEM -> integer partial -> L2 accumulator (thread = marker)
+    if (warp < 4) {
+      // g epilogue: TMEM -> integer partial -> L2 accumulator (thread = marker).  The word carries the
+      // partial in bits 8.. and an arrival count in the low byte.
       if (!mbar_wait(&S.mbar_g, par)) lfail = true;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int s = 0; s < ns; s++) {
         int s0, s1, s2, s3;
         tmem_ld4(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(4 * s), s0, s1, s2, s3);
         const long long gq = combine_limbs(s0, s1, s2, s3);
-        atomicAdd(reinterpret_cast<unsigned long long*>(a.gacc) + (size_t)(blk % 3) * ns * 128 + s * 128 + tid, (unsigned long long)gq);
+        atomicAdd(reinterpret_cast<unsigned long long*>(gblk) + s * 128 + tid, (unsigned long long)((gq << 8) + 1));
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      atomicAdd(a.bar, 1u);
-    }
-
-    // ---- 2a. (linear rules) invert the four 32x32 diagonal blocks of I + A L while the barrier fills
-    if (model_is_linear(MODEL)) {
-      for (int task = warp; task < ns * 4; task += kThreads / 32) {
+    } else if (model_is_linear(MODEL)) {
+      // ---- 2a. invert the four 32x32 diagonal blocks of I + A L (E-independent) beside the g pass
+      for (int task = warp - 4; task < ns * 4; task += 4) {
         const int s = task >> 2, d = task & 3;
         const MarkerIn* mks = mkb + s * 128 + 32 * d;
         float x[32];
 #pragma unroll
         for (int i = 0; i < 32; i++) {
           float acc0 = 0.0f, acc1 = 0.0f;
-          const float4* grow = reinterpret_cast<const float4*>(Gs + (32 * d + i) * 128 + 32 * d);
+          const float4* grow = reinterpret_cast<const float4*>(Gs + (32 * d + i) * kGS + 32 * d);
 #pragma unroll
           for (int k4 = 0; k4 < (i + 3) / 4; k4++) {
             const float4 gv = grow[k4];
@@ -324,37 +330,52 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
           }
           x[i] = (i == lane) ? 1.0f : -mks[i].a * (acc0 + acc1);
         }
-        float* mt = Mt + (size_t)(s * 4 + d) * 32 * 33 + lane * 33;  // Mt[c][i] = M[i][c], c = lane
+        // M[i][c] (c = lane) stored as Mt4[c/4][i][c%4] with a padded c/4 stride: conflict-free both ways
+        float* mt = Mt + (size_t)(s * 4 + d) * 8 * kGS + (lane >> 2) * kGS + (lane & 3);
 #pragma unroll
-        for (int i = 0; i < 32; i++) mt[i] = x[i];
-      }
-    }
-
-    // ---- 2b. grid barrier (monotonic counter, bounded spin)
-    if (tid == 0) {
-      const unsigned int target = (unsigned int)(blk + 1) * (unsigned int)G;
-      unsigned int spins = 0;
-      while (true) {
-        unsigned int v;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.bar) : "memory");
-        if (v >= target) break;
-        if (++spins > (1u << 22)) { lfail = true; atomicExch(a.err, 3); break; }
+        for (int i = 0; i < 32; i++) mt[4 * i] = x[i];
       }
     }
     __syncthreads();
 
-    // ---- 2c. in-block solve, one warp per system, replicated on every CTA
+    // ---- 2b. solve warps poll their accumulator words and run the in-block solve; the other warps
+    //          prefetch the next block (marker ids, genotype tile, per-marker inputs) meanwhile
+    const int nsolve = ns < kThreads / 32 ? ns : kThreads / 32;
+    if (warp >= nsolve || ns > kThreads / 32) {
+      if (warp >= nsolve) {
+        const int t0 = (warp - nsolve) * 32 + lane, nt = (kThreads / 32 - nsolve) * 32;
+        if (blk + 2 < a.nblocks + 2)
+          for (int m = t0; m < 128; m += nt) {
+            const int pos = (blk + 2) * 128 + m;
+            prm[((blk + 2) % 3) * 128 + m] = (blk + 2 < a.nblocks && pos < p) ? a.perm[pos] : -1;
+          }
+        issue_tile(blk + 1, nsolve, kThreads / 32 - nsolve);
+        load_markers(blk + 1, t0, nt);
+      }
+    }
     for (int s = warp; s < ns; s += kThreads / 32) {
       const SysScalars Sy = sc[s];
       const MarkerIn* mks = mkb + s * 128;
       float g[4], de[4];
-      const long long* gq = a.gacc + (size_t)(blk % 3) * ns * 128 + s * 128;
+      {
+        const long long* gq = gblk + s * 128;
+        long long q[4];
+        uint32_t spins = 0;
+        while (true) {
+          bool ok = true;
 #pragma unroll
-      for (int t = 0; t < 4; t++) {
-        long long q;
-        asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(q) : "l"(gq + 32 * t + lane) : "memory");
-        g[t] = (float)((double)q * (double)Sy.e_q);
-        de[t] = 0.0f;
+          for (int t = 0; t < 4; t++) {
+            asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(q[t]) : "l"(gq + 32 * t + lane) : "memory");
+            ok = ok && ((int)(q[t] & 0xFF) == G);
+          }
+          if (__all_sync(0xffffffffu, ok)) break;
+          if (++spins > kSpin) { lfail = true; atomicExch(a.err, 3); break; }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          g[t] = (float)((double)(q[t] >> 8) * (double)Sy.e_q);
+          de[t] = 0.0f;
+        }
       }
       float nb[4] = {0.f, 0.f, 0.f, 0.f}, nd[4] = {1.f, 1.f, 1.f, 1.f}, nv[4] = {1.f, 1.f, 1.f, 1.f};
       if (Sy.done) {
@@ -363,27 +384,44 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
         float r[4];
 #pragma unroll
         for (int t = 0; t < 4; t++) r[t] = fmaf(mks[32 * t + lane].a, g[t], mks[32 * t + lane].c);
+        float* rbs = rb + s * 32;
 #pragma unroll
         for (int d = 0; d < 4; d++) {
-          const float* mt = Mt + (size_t)(s * 4 + d) * 32 * 33 + lane;
+          // de_d = M_d r_d : broadcast r_d through shared memory, 128-bit loads down the k axis
+          __syncwarp();
+          rbs[lane] = r[d];
+          __syncwarp();
+          const float* mt = Mt + (size_t)(s * 4 + d) * 8 * kGS + 4 * lane;
           float ac[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int k = 0; k < 32; k++) ac[k & 3] = fmaf(mt[k * 33], __shfl_sync(0xffffffffu, r[d], k), ac[k & 3]);
+          for (int k4 = 0; k4 < 8; k4++) {
+            const float4 mv = *reinterpret_cast<const float4*>(mt + k4 * kGS);
+            const float4 rv = *reinterpret_cast<const float4*>(rbs + 4 * k4);
+            ac[0] = fmaf(mv.x, rv.x, ac[0]); ac[1] = fmaf(mv.y, rv.y, ac[1]);
+            ac[2] = fmaf(mv.z, rv.z, ac[2]); ac[3] = fmaf(mv.w, rv.w, ac[3]);
+          }
           const float acc = (ac[0] + ac[1]) + (ac[2] + ac[3]);
           de[d] = acc;
           if (d < 3) {
-            float far[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+            __syncwarp();
+            rbs[lane] = acc;
+            __syncwarp();
 #pragma unroll
-            for (int k = 0; k < 32; k++) {
-              const float dk = __shfl_sync(0xffffffffu, acc, k);
-              const float* grow = Gs + (32 * d + k) * 128 + lane;  // G[32d+k][32d'+lane] (symmetric)
+            for (int d2 = 0; d2 < 4; d2++) {
+              if (d2 > d) {
+                // r_d2 -= a * sum_k G[32 d2 + lane][32 d + k] * de_d[k]
+                const float* grow = Gs + (32 * d2 + lane) * kGS + 32 * d;
+                float fa[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-              for (int d2 = 0; d2 < 4; d2++)
-                if (d2 > d) far[d2][k & 1] = fmaf(grow[32 * d2], dk, far[d2][k & 1]);
+                for (int k4 = 0; k4 < 8; k4++) {
+                  const float4 gv = *reinterpret_cast<const float4*>(grow + 4 * k4);
+                  const float4 dv = *reinterpret_cast<const float4*>(rbs + 4 * k4);
+                  fa[0] = fmaf(gv.x, dv.x, fa[0]); fa[1] = fmaf(gv.y, dv.y, fa[1]);
+                  fa[2] = fmaf(gv.z, dv.z, fa[2]); fa[3] = fmaf(gv.w, dv.w, fa[3]);
+                }
+                r[d2] = fmaf(-mks[32 * d2 + lane].a, (fa[0] + fa[1]) + (fa[2] + fa[3]), r[d2]);
+              }
             }
-#pragma unroll
-            for (int d2 = 0; d2 < 4; d2++)
-              if (d2 > d) r[d2] = fmaf(-mks[32 * d2 + lane].a, far[d2][0] + far[d2][1], r[d2]);
           }
         }
       } else {
@@ -400,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
             else { dr.z1 = dr.z2 = dr.u = 0.0f; dr.chi = 1.0f; }
             const RuleOut ro = marker_rule<MODEL>(gc, in.xx, in.b0, in.vbj, Sy, dr);
             if (lane == i) { nb[t] = ro.b; nd[t] = ro.d; nv[t] = ro.vbj; de[t] = ro.de; }
-            const float* grow = Gs + jj * 128 + lane;
+            const float* grow = Gs + jj * kGS + lane;
 #pragma unroll
             for (int tt = 0; tt < 4; tt++)
               if (tt >= t) g[tt] = fmaf(-grow[32 * tt], ro.de, g[tt]);
@@ -431,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
           const MarkerIn in = mks[jj];
           float bnew, dnew = nd[t], vnew = nv[t];
           if (model_is_linear(MODEL)) {
-            bnew = in.b0 + deq / in.kappa;
+            bnew = fmaf(deq, in.ikappa, in.b0);
             if (MODEL == M_EMBA) vnew = (Sy.Sb + bnew * bnew) / (Sy.df + 1.0f);
             if (MODEL == M_BA) vnew = (Sy.Sb + bnew * bnew) / drb[s * 128 + jj].chi;
           } else {
@@ -445,8 +483,13 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
         }
       }
     }
-    if (blockIdx.x == 0 && blk + 2 < a.nblocks)
-      for (int idx = tid; idx < ns * 128; idx += kThreads) a.gacc[(size_t)((blk + 2) % 3) * ns * 128 + idx] = 0;
+    if (ns >= kThreads / 32) {  // every warp solved: nobody prefetched beside the solve, do it now
+      __syncthreads();
+      load_perm(blk + 2);
+      issue_tile(blk + 1, 0, kThreads / 32);
+      __syncthreads();
+      load_markers(blk + 1, tid, kThreads);
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
@@ -462,7 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
       }
       umma_commit(&S.mbar_u);
     }
-    issue_gram(blk + 1);  // Gs is free again (solve done, barrier passed)
+    issue_gram(blk + 1);  // Gs is free again (solve done)
     if (!mbar_wait(&S.mbar_u, par)) lfail = true;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (int at = warp >> 2; at < NA; at += 2) {
