@@ -80,7 +80,7 @@ struct Fit {
   DevBuf<uint8_t> mask;
   DevBuf<SysScalars> sc;
   DevBuf<int> perm;                     // [kPermRing][p]
-  DevBuf<long long> gacc;
+  DevBuf<long long> gacc, trace;
   DevBuf<unsigned int> bar;
   int* h_perm = nullptr;                // pinned [kPermRing][p]
   cudaEvent_t perm_free[kPermRing] = {};
@@ -593,7 +593,7 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
     f.rows_per_cta = (int)(((ld + grid0 - 1) / grid0 + 15) / 16 * 16);
     f.grid = (int)((ld + f.rows_per_cta - 1) / f.rows_per_cta);
     f.nblocks = (int)((p + kBlk - 1) / kBlk);
-    if (f.gram.alloc((size_t)f.nblocks * kBlk * kBlk) != cudaSuccess || f.gacc.alloc((size_t)f.nblocks * ns * kBlk) != cudaSuccess || f.bar.alloc(1) != cudaSuccess)
+    if (f.gram.alloc((size_t)f.nblocks * kBlk * kBlk) != cudaSuccess || f.gacc.alloc((size_t)f.nblocks * kNC * ns * kBlk) != cudaSuccess || f.bar.alloc(1) != cudaSuccess)
       return fail(BWGR_ERR_CUDA, "cudaMalloc(blocked workspace) failed");
   }
   f.active = true;
@@ -644,7 +644,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
         h->launches++;
         f.gram_cached = true;
       }
-      CU(cudaMemsetAsync(f.gacc.p, 0, sizeof(long long) * (size_t)f.nblocks * f.nsys * kBlk, h->stream));
+      CU(cudaMemsetAsync(f.gacc.p, 0, sizeof(long long) * (size_t)f.nblocks * kNC * f.nsys * kBlk, h->stream));
       CU(cudaMemsetAsync(f.bar.p, 0, sizeof(unsigned int), h->stream));
       SweepArgs a;
       memset(&a, 0, sizeof a);
@@ -653,6 +653,10 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
       a.gacc = f.gacc.p; a.bar = f.bar.p; a.g_quantum = quantum; a.g_limit = limit;
       a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0;
       a.rows_per_cta = f.rows_per_cta; a.err = h->err.p;
+      if (getenv("BWGR_TRACE")) {
+        if (!f.trace.p) f.trace.alloc((size_t)f.nblocks * 16);
+        a.trace = f.trace.p;
+      }
       cudaEvent_t pe = h->prof_begin(1);
       launch_sweep_blocked(a, f.grid, h->stream);
       h->prof_end(pe);
@@ -729,6 +733,14 @@ int bwgr_em_end(bwgr_handle* h, bwgr_em_out* out) {
   const int ns = f.nsys;
   int rc = check_err_flag(h, "sweep");
   if (rc) { f.reset(); return rc; }
+  if (f.trace.p && getenv("BWGR_TRACE")) {  // debug: per-phase clock stamps of CTA 0, last sweep
+    std::vector<long long> tr((size_t)f.nblocks * 16);
+    cudaMemcpy(tr.data(), f.trace.p, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    if (FILE* fp = fopen(getenv("BWGR_TRACE"), "w")) {
+      for (int b = 0; b < f.nblocks; b++) { for (int k = 0; k < 11; k++) fprintf(fp, "%lld ", tr[(size_t)b * 16 + k]); fprintf(fp, "\n"); }
+      fclose(fp);
+    }
+  }
   std::vector<SysScalars> sc(ns);
   CU(cudaMemcpyAsync(sc.data(), f.sc.p, sizeof(SysScalars) * ns, cudaMemcpyDeviceToHost, h->stream));
   std::vector<float> hb((size_t)ns * p), hd, hv, hh((size_t)ns * n), he;

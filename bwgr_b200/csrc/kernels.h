@@ -63,6 +63,7 @@ bool small_n_fits(const GenoView& g, bool masked, size_t smem_limit);
 
 // ---- blocked path ---------------------------------------------------------------------------------
 constexpr int kBlk = 128;  // markers per block
+constexpr int kNC = 8;     // copies of every block accumulator: spreads the L2 atomic traffic of the grid over 8x more addresses
 
 // Gram blocks G[blk][i][j] = x_{perm[blk*128+i]}' x_{perm[blk*128+j]} (int32), tcgen05 kind::i8.
 // out_f32: write the (exact) int32 accumulators converted to float, the form the sweep consumes.
@@ -83,7 +84,7 @@ struct SweepArgs {
   const float* xx;       // [p]
   SysScalars* sc;        // [nsys]
   float* B; float* D; float* VBv;  // Gibbs posterior sums or nullptr
-  long long* gacc;       // [nblocks][nsys][128] block accumulators: (sum of integer partials << 8) + arrival count; zeroed before launch
+  long long* gacc;       // [nblocks][kNC][nsys][128] block accumulators: (sum of integer partials << 8) + arrival count; zeroed before launch
   unsigned int* bar;     // grid barrier counter (zeroed before launch)
   float g_quantum;       // value of one fixed-point unit of g
   float g_limit;         // |partial g| above this -> err
@@ -91,6 +92,7 @@ struct SweepArgs {
   int chain0;
   int rows_per_cta;      // multiple of 16
   int* err;
+  long long* trace;      // optional [nblocks][16] clock64 stamps of CTA 0 (BWGR_TRACE), else nullptr
 };
 void launch_sweep_blocked(const SweepArgs& a, int grid, cudaStream_t st);
 int sweep_blocked_max_grid(int rows_per_cta, int nsys);

@@ -222,7 +222,13 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
   auto issue_gram = [&](int blk) {
     if (blk < a.nblocks) {
       const float* src = a.gram + (size_t)blk * 128 * 128;
-      for (int idx = tid; idx < 128 * 128 / 4; idx += kThreads) cp_async16(smem_u32(Gs + (idx >> 5) * kGS + 4 * (idx & 31)), src + 4 * idx);
+      // only the triangle the solve reads: linear rules use G[i][k], k <= i (32x32 tiles on and below the
+      // diagonal); the scalar chain reads row jj to the right of the diagonal tile
+      for (int idx = tid; idx < 128 * 128 / 4; idx += kThreads) {
+        const int row = idx >> 5, c4 = idx & 31;
+        const bool keep = model_is_linear(MODEL) ? (c4 >> 3) <= (row >> 5) : (c4 >> 3) >= (row >> 5);
+        if (keep) cp_async16(smem_u32(Gs + row * kGS + 4 * c4), src + 4 * idx);
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -268,6 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
   };
 
   bool fail = false, lfail = false;
+  const bool tracing = a.trace != nullptr && blockIdx.x == 0 && tid == 0;
+#define BWGR_STAMP(k) do { if (tracing) a.trace[(size_t)blk * 16 + (k)] = clock64(); } while (0)
   issue_tile(0, 0, kThreads / 32);
   issue_gram(0);
   load_markers(0, tid, kThreads);
@@ -281,11 +289,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
     const int nvalid = min(128, p - blk * 128);
     MarkerIn* mkb = mk + (size_t)(blk & 1) * ns * 128;
     MarkerDraws* drb = drw + (size_t)(blk & 1) * ns * 128;
-    long long* gblk = a.gacc + (size_t)blk * ns * 128;  // this block's accumulators (zeroed by the host)
+    long long* gblk = a.gacc + (size_t)blk * kNC * ns * 128;  // this block's accumulators [kNC][ns][128] (zeroed by the host)
 
     asm volatile("cp.async.wait_group 0;" ::: "memory");   // this block's X tile and Gram block have landed
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // limbs (generic stores) -> tensor core
     if (__syncthreads_or(lfail ? 1 : 0)) break;  // uniform exit if any wait of the previous block timed out
+    BWGR_STAMP(0);
 
     // ---- 1. g pass on the tensor core: D[marker][limb] = sum_rows X[marker][row] * limb[row]
     if (tid == 0) {
@@ -298,16 +307,18 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
       }
       umma_commit(&S.mbar_g);
     }
+    BWGR_STAMP(1);
     if (warp < 4) {
       // g epilogue: TMEM -> integer partial -> L2 accumulator (thread = marker).  The word carries the
       // partial in bits 8.. and an arrival count in the low byte.
       if (!mbar_wait(&S.mbar_g, par)) lfail = true;
+      BWGR_STAMP(2);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int s = 0; s < ns; s++) {
         int s0, s1, s2, s3;
         tmem_ld4(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(4 * s), s0, s1, s2, s3);
         const long long gq = combine_limbs(s0, s1, s2, s3);
-        atomicAdd(reinterpret_cast<unsigned long long*>(gblk) + s * 128 + tid, (unsigned long long)((gq << 8) + 1));
+        atomicAdd(reinterpret_cast<unsigned long long*>(gblk) + ((size_t)(blockIdx.x % kNC) * ns + s) * 128 + tid, (unsigned long long)((gq << 8) + 1));
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else if (model_is_linear(MODEL)) {
@@ -336,7 +347,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
         for (int i = 0; i < 32; i++) mt[4 * i] = x[i];
       }
     }
+    BWGR_STAMP(3);
     __syncthreads();
+    BWGR_STAMP(4);
 
     // ---- 2b. solve warps poll their accumulator words and run the in-block solve; the other warps
     //          prefetch the next block (marker ids, genotype tile, per-marker inputs) meanwhile
@@ -358,22 +371,31 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
       const MarkerIn* mks = mkb + s * 128;
       float g[4], de[4];
       {
-        const long long* gq = gblk + s * 128;
-        long long q[4];
+        // every word is (sum of partials << 8) + arrivals; copy c collects the CTAs with blockIdx % kNC == c
+        long long q[4] = {0, 0, 0, 0};
         uint32_t spins = 0;
-        while (true) {
-          bool ok = true;
+#pragma unroll 1
+        for (int c = 0; c < kNC; c++) {
+          const long long* gq = gblk + ((size_t)c * ns + s) * 128;
+          const int expect = (G - c + kNC - 1) / kNC;
+          long long w[4];
+          while (true) {
+            bool ok = true;
 #pragma unroll
-          for (int t = 0; t < 4; t++) {
-            asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(q[t]) : "l"(gq + 32 * t + lane) : "memory");
-            ok = ok && ((int)(q[t] & 0xFF) == G);
+            for (int t = 0; t < 4; t++) {
+              asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(w[t]) : "l"(gq + 32 * t + lane) : "memory");
+              ok = ok && ((int)(w[t] & 0xFF) == expect);
+            }
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (++spins > kSpin) { lfail = true; atomicExch(a.err, 3); break; }
           }
-          if (__all_sync(0xffffffffu, ok)) break;
-          if (++spins > kSpin) { lfail = true; atomicExch(a.err, 3); break; }
+#pragma unroll
+          for (int t = 0; t < 4; t++) q[t] += w[t] >> 8;
         }
+        BWGR_STAMP(5);
 #pragma unroll
         for (int t = 0; t < 4; t++) {
-          g[t] = (float)((double)(q[t] >> 8) * (double)Sy.e_q);
+          g[t] = (float)((double)q[t] * (double)Sy.e_q);
           de[t] = 0.0f;
         }
       }
@@ -445,6 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
           }
         }
       }
+      BWGR_STAMP(6);
       // quantise dE to 31-bit fixed point relative to the block maximum (all CTAs compute the same scale)
       float mx = fmaxf(fmaxf(fabsf(de[0]), fabsf(de[1])), fmaxf(fabsf(de[2]), fabsf(de[3])));
 #pragma unroll
@@ -490,8 +513,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
       __syncthreads();
       load_markers(blk + 1, tid, kThreads);
     }
+    BWGR_STAMP(7);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    BWGR_STAMP(8);
 
     // ---- 3. update pass on the tensor core: D[row][limb] = sum_markers X[row][marker] * dE_limb[marker]
     if (tid == 0) {
@@ -507,6 +532,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
     }
     issue_gram(blk + 1);  // Gs is free again (solve done)
     if (!mbar_wait(&S.mbar_u, par)) lfail = true;
+    BWGR_STAMP(9);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (int at = warp >> 2; at < NA; at += 2) {
       const int ra = (warp & 3) * 32 + lane;  // row inside the atom = TMEM lane
@@ -523,7 +549,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    BWGR_STAMP(10);
   }
+#undef BWGR_STAMP
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   if (fail) atomicExch(a.err, 4);
