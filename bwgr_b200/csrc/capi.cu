@@ -82,6 +82,11 @@ struct Fit {
   DevBuf<int> perm;                     // [kPermRing][p]
   DevBuf<long long> gacc, trace;
   DevBuf<unsigned int> bar;
+  // pipelined sweep (sweep_pipe.cu)
+  bool pipe = false;
+  int lookahead = 0, nbuf = 0, sring = 2, nworkers = 0, nc = 1, nband = 1;
+  uint32_t tag = 0;
+  DevBuf<unsigned long long> dew, part;
   int* h_perm = nullptr;                // pinned [kPermRing][p]
   cudaEvent_t perm_free[kPermRing] = {};
   bool perm_ev_valid[kPermRing] = {};
@@ -113,6 +118,7 @@ struct bwgr_handle {
   // tuning
   int path = BWGR_PATH_AUTO, grid = 0;
   int gram_simt = 0;
+  int fp8_codes = 0;  // all genotypes are codes 0..7 (and n small enough): the Gram kernel may use the exact E4M3 path
   int64_t launches = 0;
   Fit fit;
   // optional per-kernel timing (bwgr_profile)
@@ -183,6 +189,21 @@ int finish_store(bwgr_handle* h, int storage) {
   for (int64_t j = 0; j < h->p; j++) xf[j] = (float)xx[j];
   CU(cudaMemcpyAsync(h->xx_f.p, xf.data(), sizeof(float) * h->p, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  {  // codes 0..7 everywhere?  (one more streaming pass at load time)
+    h->fp8_codes = 0;
+    const char* ge = getenv("BWGR_GRAM");
+    double xxmax = 0;  // every Gram entry and every partial sum of non-negative codes is bounded by max_j xx_j (Cauchy-Schwarz)
+    for (double v : h->h_xx) xxmax = std::max(xxmax, v);
+    if (!(ge && !strcmp(ge, "i8")) && xxmax < 16777216.0) {
+      launch_check_range_i8(h->x8, h->ld, (int)h->n, (int)h->p, 0, 7, h->err.p, h->stream);
+      h->launches++;
+      int flag = 0;
+      CU(cudaMemcpyAsync(&flag, h->err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      if (flag) CU(cudaMemsetAsync(h->err.p, 0, sizeof(int), h->stream));
+      h->fp8_codes = flag ? 0 : 1;
+    }
+  }
   h->storage = BWGR_STORE_I8;
   if (storage == BWGR_STORE_2BIT) {
     h->ldb = h->ld / 4;
@@ -380,13 +401,41 @@ struct FitSpec {
   uint64_t seed;
 };
 
+// Geometry of the pipelined sweep: W streaming CTAs (row slabs of R rows, R <= 512) + one solver CTA, look-ahead D,
+// nbuf X tiles per worker.  False if the shape does not fit one SM's shared memory / TMEM.
+struct PipePlan { int R, W, nbuf, D, sring; };
+bool plan_pipe(const bwgr_handle* h, int model, int ns, PipePlan* pl) {
+  const char* sw = getenv("BWGR_SWEEP");
+  if (sw && !strcmp(sw, "v4")) return false;
+  if (h->storage != BWGR_STORE_I8 || ns > 32) return false;
+  const int sms = h->grid > 1 ? std::min(h->grid, h->num_sms) : h->num_sms;
+  if (sms < 2) return false;
+  const int W0 = sms - 1;
+  const int R = (int)(((h->ld + W0 - 1) / W0 + 15) / 16 * 16);
+  if (R > 512) return false;
+  const int W = (int)((h->ld + R - 1) / R);
+  const int NA = (R + 127) / 128, N = ((4 * ns + 15) / 16) * 16;
+  if ((NA + 1) * N > 512) return false;
+  const char* la = getenv("BWGR_LOOKAHEAD");
+  int D = la ? atoi(la) : 1;
+  if (D < 0 || h->gram_simt) D = 0;
+  if (D > 1) D = 1;
+  for (; D >= 0; D--) {
+    for (int sring = 3; sring >= 2; sring--)
+      for (int nbuf = std::min(8, D + 3); nbuf >= D + 1; nbuf--)
+        if (sweep_pipe_smem(R, ns, model, nbuf, sring) <= h->smem_optin - 8192) { pl->R = R; pl->W = W; pl->nbuf = nbuf; pl->D = D; pl->sring = sring; return true; }
+  }
+  return false;
+}
+
 int choose_path(bwgr_handle* h, const FitSpec& s, bool* blocked) {
   const GenoView g = h->view();
   const bool small_ok = small_n_fits(g, s.row_mask != nullptr, h->smem_optin);
   const int grid = h->grid > 0 ? std::min(h->grid, h->num_sms) : h->num_sms;
   const int64_t rows = ((h->ld + grid - 1) / grid + 15) / 16 * 16;
-  const bool blocked_ok = h->storage == BWGR_STORE_I8 && !s.row_mask && s.nsys <= 32 && rows <= 512 &&
-                          sweep_blocked_smem((int)rows, s.nsys) <= h->smem_optin;
+  PipePlan pl;
+  const bool blocked_ok = h->storage == BWGR_STORE_I8 && !s.row_mask && s.nsys <= 32 &&
+                          (plan_pipe(h, s.model, s.nsys, &pl) || (rows <= 512 && sweep_blocked_smem((int)rows, s.nsys) <= h->smem_optin));
   if (h->path == BWGR_PATH_SMALL_N) {
     if (!small_ok) return fail(BWGR_ERR_UNSUPPORTED, "small-n path: residual of n=%lld does not fit one SM", (long long)h->n);
     *blocked = false;
@@ -589,12 +638,25 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
   for (int64_t j = 0; j < p; j++) f.order[j] = (int)j;
 
   if (blocked) {
-    const int grid0 = h->grid > 0 ? std::min(h->grid, h->num_sms) : h->num_sms;
-    f.rows_per_cta = (int)(((ld + grid0 - 1) / grid0 + 15) / 16 * 16);
-    f.grid = (int)((ld + f.rows_per_cta - 1) / f.rows_per_cta);
     f.nblocks = (int)((p + kBlk - 1) / kBlk);
-    if (f.gram.alloc((size_t)f.nblocks * kBlk * kBlk) != cudaSuccess || f.gacc.alloc((size_t)f.nblocks * kNC * ns * kBlk) != cudaSuccess || f.bar.alloc(1) != cudaSuccess)
-      return fail(BWGR_ERR_CUDA, "cudaMalloc(blocked workspace) failed");
+    PipePlan pl;
+    f.pipe = plan_pipe(h, s.model, ns, &pl);
+    if (f.pipe) {
+      f.rows_per_cta = pl.R; f.nworkers = pl.W; f.grid = pl.W + 1; f.nbuf = pl.nbuf; f.sring = pl.sring; f.lookahead = pl.D; f.nband = pl.D + 1;
+      f.nc = std::max(1, 16 / ns);
+      f.tag = 0;
+      if (f.gram.alloc((size_t)f.nblocks * kBlk * kBlk * f.nband) != cudaSuccess ||
+          f.part.alloc((size_t)8 * ns * 128 * 161) != cudaSuccess || f.dew.alloc((size_t)f.nblocks * ns * 136) != cudaSuccess)
+        return fail(BWGR_ERR_CUDA, "cudaMalloc(blocked workspace) failed");
+      CU(cudaMemsetAsync(f.dew.p, 0, sizeof(unsigned long long) * f.dew.n, h->stream));
+    } else {
+      const int grid0 = h->grid > 0 ? std::min(h->grid, h->num_sms) : h->num_sms;
+      f.rows_per_cta = (int)(((ld + grid0 - 1) / grid0 + 15) / 16 * 16);
+      f.grid = (int)((ld + f.rows_per_cta - 1) / f.rows_per_cta);
+      f.nband = 1;
+      if (f.gram.alloc((size_t)f.nblocks * kBlk * kBlk) != cudaSuccess || f.gacc.alloc((size_t)f.nblocks * kNC * ns * kBlk) != cudaSuccess || f.bar.alloc(1) != cudaSuccess)
+        return fail(BWGR_ERR_CUDA, "cudaMalloc(blocked workspace) failed");
+    }
   }
   f.active = true;
   return 0;
@@ -639,28 +701,47 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
       if (f.shuffled || !f.gram_cached) {
         cudaEvent_t pe = h->prof_begin(0);
         if (h->gram_simt) launch_gram_simt(g, d_perm, f.nblocks, f.gram.p, 1, h->stream);
-        else launch_gram_tc(g, d_perm, f.nblocks, f.gram.p, 1, h->err.p, h->num_sms, h->stream);
+        else launch_gram_tc(g, d_perm, f.nblocks, f.gram.p, 1, f.nband, h->fp8_codes, h->err.p, h->num_sms, h->stream);
         h->prof_end(pe);
         h->launches++;
         f.gram_cached = true;
       }
-      CU(cudaMemsetAsync(f.gacc.p, 0, sizeof(long long) * (size_t)f.nblocks * kNC * f.nsys * kBlk, h->stream));
-      CU(cudaMemsetAsync(f.bar.p, 0, sizeof(unsigned int), h->stream));
-      SweepArgs a;
-      memset(&a, 0, sizeof a);
-      a.g = g; a.model = f.model; a.nsys = f.nsys; a.perm = d_perm; a.nblocks = f.nblocks; a.gram = f.gram.p;
-      a.e = f.e.p; a.b = f.b.p; a.d = f.d.p; a.vbv = f.vbv.p; a.xx = h->xx_f.p; a.sc = f.sc.p;
-      a.gacc = f.gacc.p; a.bar = f.bar.p; a.g_quantum = quantum; a.g_limit = limit;
-      a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0;
-      a.rows_per_cta = f.rows_per_cta; a.err = h->err.p;
-      if (getenv("BWGR_TRACE")) {
-        if (!f.trace.p) f.trace.alloc((size_t)f.nblocks * 16);
-        a.trace = f.trace.p;
+      if (f.pipe) {
+        CU(cudaMemsetAsync(f.part.p, 0, sizeof(unsigned long long) * f.part.n, h->stream));
+        PipeArgs a;
+        memset(&a, 0, sizeof a);
+        a.g = g; a.model = f.model; a.nsys = f.nsys; a.perm = d_perm; a.nblocks = f.nblocks; a.gram = f.gram.p; a.nband = f.nband;
+        a.e = f.e.p; a.b = f.b.p; a.d = f.d.p; a.vbv = f.vbv.p; a.xx = h->xx_f.p; a.sc = f.sc.p;
+        a.part = f.part.p; a.hred = f.part.p + (size_t)8 * f.nsys * 128 * 160; a.dew = f.dew.p; a.tag = ++f.tag;
+        a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0;
+        a.rows_per_cta = f.rows_per_cta; a.nworkers = f.nworkers; a.D = f.lookahead; a.nbuf = f.nbuf; a.sring = f.sring; a.err = h->err.p;
+        if (getenv("BWGR_TRACE")) {
+          if (!f.trace.p) { f.trace.alloc((size_t)f.grid * f.nblocks * 32); cudaMemsetAsync(f.trace.p, 0, sizeof(long long) * f.trace.n, h->stream); }
+          a.trace = f.trace.p;
+        }
+        cudaEvent_t pe = h->prof_begin(1);
+        launch_sweep_pipe(a, h->stream);
+        h->prof_end(pe);
+        h->launches++;
+      } else {
+        CU(cudaMemsetAsync(f.gacc.p, 0, sizeof(long long) * (size_t)f.nblocks * kNC * f.nsys * kBlk, h->stream));
+        CU(cudaMemsetAsync(f.bar.p, 0, sizeof(unsigned int), h->stream));
+        SweepArgs a;
+        memset(&a, 0, sizeof a);
+        a.g = g; a.model = f.model; a.nsys = f.nsys; a.perm = d_perm; a.nblocks = f.nblocks; a.gram = f.gram.p;
+        a.e = f.e.p; a.b = f.b.p; a.d = f.d.p; a.vbv = f.vbv.p; a.xx = h->xx_f.p; a.sc = f.sc.p;
+        a.gacc = f.gacc.p; a.bar = f.bar.p; a.g_quantum = quantum; a.g_limit = limit;
+        a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0;
+        a.rows_per_cta = f.rows_per_cta; a.err = h->err.p;
+        if (getenv("BWGR_TRACE")) {
+          if (!f.trace.p) f.trace.alloc((size_t)f.nblocks * 16);
+          a.trace = f.trace.p;
+        }
+        cudaEvent_t pe = h->prof_begin(1);
+        launch_sweep_blocked(a, f.grid, h->stream);
+        h->prof_end(pe);
+        h->launches++;
       }
-      cudaEvent_t pe = h->prof_begin(1);
-      launch_sweep_blocked(a, f.grid, h->stream);
-      h->prof_end(pe);
-      h->launches++;
     } else {
       SmallNArgs a;
       memset(&a, 0, sizeof a);
@@ -733,11 +814,13 @@ int bwgr_em_end(bwgr_handle* h, bwgr_em_out* out) {
   const int ns = f.nsys;
   int rc = check_err_flag(h, "sweep");
   if (rc) { f.reset(); return rc; }
-  if (f.trace.p && getenv("BWGR_TRACE")) {  // debug: per-phase clock stamps of CTA 0, last sweep
-    std::vector<long long> tr((size_t)f.nblocks * 16);
+  if (f.trace.p && getenv("BWGR_TRACE")) {  // debug: raw int64 stamps of the last sweep, [cta][block][16]
+    std::vector<long long> tr(f.trace.n);
     cudaMemcpy(tr.data(), f.trace.p, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-    if (FILE* fp = fopen(getenv("BWGR_TRACE"), "w")) {
-      for (int b = 0; b < f.nblocks; b++) { for (int k = 0; k < 11; k++) fprintf(fp, "%lld ", tr[(size_t)b * 16 + k]); fprintf(fp, "\n"); }
+    if (FILE* fp = fopen(getenv("BWGR_TRACE"), "wb")) {
+      const long long hdr[4] = {f.pipe ? f.grid : 1, f.nblocks, 32, f.lookahead};
+      fwrite(hdr, sizeof(long long), 4, fp);
+      fwrite(tr.data(), sizeof(long long), tr.size(), fp);
       fclose(fp);
     }
   }
@@ -904,7 +987,7 @@ int bwgr_debug_gram(bwgr_handle* h, const int32_t* perm, int block, int32_t* gra
   if (dperm.alloc(p) != cudaSuccess || dg.alloc((size_t)nblocks * kBlk * kBlk) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
   CU(cudaMemcpyAsync(dperm.p, perm, sizeof(int) * p, cudaMemcpyHostToDevice, h->stream));
   if (h->gram_simt) launch_gram_simt(h->view(), dperm.p, nblocks, dg.p, 0, h->stream);
-  else launch_gram_tc(h->view(), dperm.p, nblocks, dg.p, 0, h->err.p, h->num_sms, h->stream);
+  else launch_gram_tc(h->view(), dperm.p, nblocks, dg.p, 0, 1, h->fp8_codes, h->err.p, h->num_sms, h->stream);
   h->launches++;
   CU(cudaMemcpyAsync(gram_out, dg.p, sizeof(int32_t) * dg.n, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));

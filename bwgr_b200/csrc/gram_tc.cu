@@ -19,9 +19,11 @@ namespace bwgr {
 
 namespace {
 
-constexpr int kStages = 6;
 constexpr int kTileBytes = 128 * 128;
-constexpr int kLag = 3;  // cp.async groups kept in flight per producer thread
+// NBAND = 1: diagonal blocks X_b'X_b only.  NBAND = 2: [X_b'X_b | X_{b-1}'X_b] (one-block look-ahead of the
+// pipelined sweep, sweep_pipe.cu): row r of block b holds NBAND*128 entries, x_{b,r}'X_b then x_{b-1,r}'X_b.
+// The gather is latency-bound: keep (almost) the whole 227 KB of shared memory in flight.
+template <int NBAND> struct GramCfg { static constexpr int kStages = NBAND == 1 ? 13 : 6; static constexpr int kLag = kStages - 2; };
 constexpr uint32_t kSpinLimit = 1u << 22;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -67,6 +69,18 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 // kind::i8, D = S32, A = B = signed int8, both K-major, M = 128, N = 128.
 constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
+// kind::f8f6f4 with both operands E4M3 and an F32 accumulator.  Genotype codes 0..7 stored as int8 are, read as E4M3,
+// the subnormals code * 2^-9: the SAME bytes feed this (4x faster) instruction, every product code_i*code_j*2^-18 is
+// exact, and so is the fp32 sum while max_j xx_j < 2^24 -- the epilogue rescales by 2^18 and lands on the exact integer.
+constexpr uint32_t kIdescF8 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -79,17 +93,24 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+template <int NBAND>
 struct GramSmem {
-  uint64_t full[kStages], empty[kStages], tmem_full[2], tmem_empty[2];
+  uint64_t full[GramCfg<NBAND>::kStages], empty[GramCfg<NBAND>::kStages], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
 };
 
+template <int NBAND, bool FP8>
 __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* __restrict__ perm, int nblocks,
                                                          int32_t* __restrict__ gram, int out_f32, int* err) {
+  constexpr int kStages = GramCfg<NBAND>::kStages;
+  constexpr int kLag = GramCfg<NBAND>::kLag;  // cp.async groups kept in flight per producer thread
+  constexpr int kStageBytes = NBAND * kTileBytes;
+  constexpr uint32_t kAccCols = NBAND * 128;  // TMEM columns of one accumulator stage
+  using Sm = GramSmem<NBAND>;
   extern __shared__ unsigned char smem_raw[];
   // tiles first (1024 B aligned for SWIZZLE_128B), bookkeeping after them
   unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  GramSmem* S = reinterpret_cast<GramSmem*>(tiles + kStages * kTileBytes);
+  Sm* S = reinterpret_cast<Sm*>(tiles + kStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkt = (int)(g.ld >> 7);  // K tiles of 128 rows (ld is a multiple of 128)
 
@@ -99,7 +120,7 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&S->tmem_base)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S->tmem_base)), "r"(2u * kAccCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -113,27 +134,31 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
     uint32_t it = 0;            // tile counter (runs over blocks and K tiles)
     bool ok = true;
     for (int blk = blockIdx.x; blk < nblocks && ok; blk += gridDim.x) {
-      const int8_t* colp[8];
-      uint32_t nbytes[8];
+      const int8_t* colp[NBAND][8];
+      uint32_t nbytes[NBAND][8];
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const int m = i * 16 + (t >> 3);
-        const int pos = blk * 128 + m;
-        const bool valid = pos < g.p;
-        const int j = valid ? perm[pos] : 0;
-        colp[i] = g.x8 + (int64_t)j * g.ld + ((t & 7) << 4);
-        nbytes[i] = valid ? 16u : 0u;
-      }
-      for (int kt = 0; kt < nkt && ok; kt++, it++) {
-        const uint32_t stage = it % kStages, phase = (it / kStages) & 1u;
-        ok = mbar_wait(&S->empty[stage], phase ^ 1u, err);
-        const uint32_t tbase = smem_u32(tiles + stage * kTileBytes);
+      for (int d = 0; d < NBAND; d++)
 #pragma unroll
         for (int i = 0; i < 8; i++) {
           const int m = i * 16 + (t >> 3);
-          const uint32_t dst = tbase + m * 128 + ((((uint32_t)t & 7u) ^ ((uint32_t)m & 7u)) << 4);
-          cp_async16_zfill(dst, colp[i] + (int64_t)kt * 128, nbytes[i]);
+          const int pos = (blk - d) * 128 + m;
+          const bool valid = pos >= 0 && pos < g.p;
+          const int j = valid ? perm[pos] : 0;
+          colp[d][i] = g.x8 + (int64_t)j * g.ld + ((t & 7) << 4);
+          nbytes[d][i] = valid ? 16u : 0u;
         }
+      for (int kt = 0; kt < nkt && ok; kt++, it++) {
+        const uint32_t stage = it % kStages, phase = (it / kStages) & 1u;
+        ok = mbar_wait(&S->empty[stage], phase ^ 1u, err);
+        const uint32_t tbase = smem_u32(tiles + stage * kStageBytes);
+#pragma unroll
+        for (int d = 0; d < NBAND; d++)
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int m = i * 16 + (t >> 3);
+            const uint32_t dst = tbase + d * kTileBytes + m * 128 + ((((uint32_t)t & 7u) ^ ((uint32_t)m & 7u)) << 4);
+            cp_async16_zfill(dst, colp[d][i] + (int64_t)kt * 128, nbytes[d][i]);
+          }
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (it >= kLag) {
           asm volatile("cp.async.wait_group %0;" ::"n"(kLag) : "memory");
@@ -154,16 +179,30 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
       const uint32_t as = bi & 1u, aphase = (bi >> 1) & 1u;
       ok = mbar_wait(&S->tmem_empty[as], aphase ^ 1u, err);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tmem_d = tmem_base + as * 128u;
+      const uint32_t tmem_d = tmem_base + as * kAccCols;
       for (int kt = 0; kt < nkt && ok; kt++, it++) {
         const uint32_t stage = it % kStages, phase = (it / kStages) & 1u;
         ok = mbar_wait(&S->full[stage], phase, err);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lane == 0) {
-          const uint64_t desc = make_desc_sw128(smem_u32(tiles + stage * kTileBytes));
+          const uint64_t desc = make_desc_sw128(smem_u32(tiles + stage * kStageBytes));
 #pragma unroll
-          for (int k4 = 0; k4 < 4; k4++)
-            umma_i8(tmem_d, desc + (uint64_t)(k4 * 2), desc + (uint64_t)(k4 * 2), kIdescI8, (kt | k4) != 0 ? 1u : 0u);
+          for (int d = 0; d < NBAND; d++) {
+            const uint64_t bdesc = make_desc_sw128(smem_u32(tiles + stage * kStageBytes + d * kTileBytes));
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++) {
+              // band d >= 1 is stored transposed: row r = marker r of block b-d, columns = markers of block b, so that the
+              // sweep's correction threads (one per marker of block b) read it coalesced
+              const uint32_t acc = (kt | k4) != 0 ? 1u : 0u;
+              if (FP8) {
+                if (d == 0) umma_f8(tmem_d, desc + (uint64_t)(k4 * 2), desc + (uint64_t)(k4 * 2), kIdescF8, acc);
+                else umma_f8(tmem_d + (uint32_t)d * 128u, bdesc + (uint64_t)(k4 * 2), desc + (uint64_t)(k4 * 2), kIdescF8, acc);
+              } else {
+                if (d == 0) umma_i8(tmem_d, desc + (uint64_t)(k4 * 2), desc + (uint64_t)(k4 * 2), kIdescI8, acc);
+                else umma_i8(tmem_d + (uint32_t)d * 128u, bdesc + (uint64_t)(k4 * 2), desc + (uint64_t)(k4 * 2), kIdescI8, acc);
+              }
+            }
+          }
           umma_commit(&S->empty[stage]);  // frees the stage when these MMAs have read it
         }
         __syncwarp();
@@ -181,11 +220,11 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
       const uint32_t as = bi & 1u, aphase = (bi >> 1) & 1u;
       ok = mbar_wait(&S->tmem_full[as], aphase, err);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      int32_t* out = gram + ((size_t)blk * 128 + row) * 128;
+      int32_t* out = gram + ((size_t)blk * 128 + row) * (NBAND * 128);
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
+      for (int c = 0; c < 4 * NBAND; c++) {
         uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 128u + (uint32_t)c * 32u;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kAccCols + (uint32_t)c * 32u;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -197,7 +236,13 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
             : "r"(taddr)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (out_f32) {
+        if (FP8) {  // accumulator = exact integer * 2^-18 in fp32
+#pragma unroll
+          for (int q = 0; q < 32; q++) {
+            const float f = __uint_as_float(v[q]) * 262144.0f;
+            v[q] = out_f32 ? __float_as_uint(f) : (uint32_t)__float2int_rn(f);
+          }
+        } else if (out_f32) {
 #pragma unroll
           for (int q = 0; q < 32; q++) v[q] = __float_as_uint(__int2float_rn((int)v[q]));
         }
@@ -217,7 +262,7 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
   __syncthreads();
   if (warp == 4) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kAccCols) : "memory");
   }
 }
 
@@ -240,12 +285,24 @@ __global__ void __launch_bounds__(256) gram_simt_kernel(GenoView g, const int* _
 
 }  // namespace
 
-void launch_gram_tc(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, int* err, int num_sms,
-                    cudaStream_t st) {
-  const size_t smem = (size_t)kStages * kTileBytes + sizeof(GramSmem) + 1024;
-  cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int NBAND, bool FP8>
+static void launch_gram_band(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, int* err, int num_sms,
+                             cudaStream_t st) {
+  const size_t smem = (size_t)GramCfg<NBAND>::kStages * NBAND * kTileBytes + sizeof(GramSmem<NBAND>) + 1024;
+  cudaFuncSetAttribute(gram_tc_kernel<NBAND, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = nblocks < num_sms ? nblocks : num_sms;
-  gram_tc_kernel<<<grid, 288, smem, st>>>(g, perm, nblocks, static_cast<int32_t*>(gram), out_f32, err);
+  gram_tc_kernel<NBAND, FP8><<<grid, 288, smem, st>>>(g, perm, nblocks, static_cast<int32_t*>(gram), out_f32, err);
+}
+// fp8_codes: every genotype is a code in 0..7 and max_j xx_j < 2^24 (the caller checked) -> the exact E4M3 path
+void launch_gram_tc(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, int nband, int fp8_codes,
+                    int* err, int num_sms, cudaStream_t st) {
+  if (fp8_codes) {
+    if (nband == 2) launch_gram_band<2, true>(g, perm, nblocks, gram, out_f32, err, num_sms, st);
+    else launch_gram_band<1, true>(g, perm, nblocks, gram, out_f32, err, num_sms, st);
+  } else {
+    if (nband == 2) launch_gram_band<2, false>(g, perm, nblocks, gram, out_f32, err, num_sms, st);
+    else launch_gram_band<1, false>(g, perm, nblocks, gram, out_f32, err, num_sms, st);
+  }
 }
 void launch_gram_simt(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, cudaStream_t st) {
   gram_simt_kernel<<<nblocks, 256, 0, st>>>(g, perm, static_cast<int32_t*>(gram), out_f32);

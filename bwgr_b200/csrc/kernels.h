@@ -67,8 +67,11 @@ constexpr int kNC = 8;     // copies of every block accumulator: spreads the L2 
 
 // Gram blocks G[blk][i][j] = x_{perm[blk*128+i]}' x_{perm[blk*128+j]} (int32), tcgen05 kind::i8.
 // out_f32: write the (exact) int32 accumulators converted to float, the form the sweep consumes.
-void launch_gram_tc(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, int* err, int num_sms,
-                    cudaStream_t st);
+// nband = 2: row r of block b holds [x_{b,r}'X_b | x_{b-1,r}'X_b] (256 entries): the cross block (stored transposed) feeds
+// the one-block look-ahead of the pipelined sweep.
+// fp8_codes != 0: all genotypes are codes 0..7 and n*49 < 2^24 -> kind::f8f6f4 on the same bytes (exact, see gram_tc.cu).
+void launch_gram_tc(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, int nband, int fp8_codes,
+                    int* err, int num_sms, cudaStream_t st);
 // SIMT cross-check of the same quantity (debug / tests only; selected with BWGR_GRAM=simt).
 void launch_gram_simt(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, cudaStream_t st);
 
@@ -97,6 +100,36 @@ struct SweepArgs {
 void launch_sweep_blocked(const SweepArgs& a, int grid, cudaStream_t st);
 int sweep_blocked_max_grid(int rows_per_cta, int nsys);
 size_t sweep_blocked_smem(int rows_per_cta, int nsys);
+
+// Pipelined blocked sweep (sweep_pipe.cu): nworkers streaming CTAs + one solver CTA, look-ahead D (0 or 1).
+struct PipeArgs {
+  GenoView g;
+  int model;
+  int nsys;
+  const int* perm;       // this sweep's marker order [p] (device)
+  int nblocks;
+  const float* gram;     // [nblocks][128][nband*128] Gram band as float (exact below 2^24)
+  int nband;
+  float* e;              // [nsys][ld]
+  float* b; float* d; float* vbv;  // [nsys][p]
+  const float* xx;       // [p]
+  SysScalars* sc;        // [nsys]
+  unsigned long long* part;  // [8][nsys][128][160] per-worker integer partials of h: (value << 16) | block tag; zeroed before launch
+  unsigned long long* hred;  // [8][nsys][128] reduced h, same word format; zeroed before launch
+  unsigned long long* dew;  // [nblocks][nsys][136] published steps: (int32 q << 32) | tag, word 128 = (float scale << 32) | tag
+  uint32_t tag;          // unique per launch, never 0
+  uint32_t seed_lo, seed_hi;
+  int chain0;
+  int rows_per_cta;      // multiple of 16, <= 512
+  int nworkers;
+  int D;                 // look-ahead depth
+  int nbuf;              // X tiles in the ring of a worker (>= D + 1)
+  int sring;             // blocks of solve inputs in flight in the solver CTA (2 or 3)
+  int* err;
+  long long* trace;      // optional [nblocks][16] clock64 stamps (BWGR_TRACE), else nullptr
+};
+void launch_sweep_pipe(const PipeArgs& a, cudaStream_t st);
+size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring);
 
 // Sweep epilogue (both paths use the same arithmetic): reductions + hyper-parameter update +
 // e -= mean(e). One CTA per system.

@@ -1,0 +1,923 @@
+// sweep_pipe.cu -- the blocked exact Gauss-Seidel / Gibbs sweep, v5: streaming CTAs + one solver CTA,
+// pipelined with a one-block look-ahead (K1 + K5 + K2 of SURVEY 2c).
+//
+// One persistent cooperative kernel per sweep, grid = W workers + 1 solver.
+//
+//   worker w (one per SM) owns the row slab [w*R, (w+1)*R) of every genotype column and the matching slab
+//   of the residuals E (float master copy + four signed int8 limbs of its 31-bit fixed-point image, both in
+//   shared memory).  Warp roles: 0 = tcgen05 issuer, 1-4 = TMEM epilogue, 5-8 = cp.async gather of the
+//   X tiles (SWIZZLE_128B layout, ring of nbuf tiles, each genotype byte read from HBM once per sweep).
+//   Per block b of 128 markers in this sweep's order (Rcpp20260726ai.cpp:331):
+//     U(b):  E_slab -= X_b dE_b        tcgen05.mma kind::i8, A = tile (MN-major), B = int8 limbs of dE_b
+//     G(c):  h_c partial = X_c' E      c = b+1+D; A = tile (K-major), B = limbs of E; exact int32 in TMEM
+//   The integer partial of h_c goes to an L2 accumulator with one 64-bit red per marker: (value << 8) + 1,
+//   so every word carries its own arrival count and nobody needs a fence or a grid barrier.
+//
+//   solver (the last CTA) polls h_b, forms the up-to-date  g_b = h_b - (X_b'X_{b-1}) dE_{b-1}  (D = 1:
+//   h_b was taken before block b-1 was applied -- this is what takes the worker pipeline and the two L2
+//   round trips off the critical path; the cross Gram block comes from gram_tc.cu, band 2), runs the
+//   in-block sequential solve on the Gram block X_b'X_b and publishes dE_b as 64-bit self-validating words
+//   (int32 fixed-point step | launch tag).  Linear rules (emRR, emBA, BayesRR, BayesA, rotated MRR3) are a
+//   unit-lower-triangular system solved in 32-marker blocks (32x32 inverses computed one block ahead, or an
+//   in-warp substitution when many systems share the SM); the other rules walk the scalar chain.
+//   Either way the result is the reference's Gauss-Seidel order up to float reassociation.
+//
+// Critical path per block with D = 1: cross-Gram correction + in-block solve.  Everything else (gather,
+// both tensor-core passes, quantisation, L2 round trips) runs beside it.
+#include "kernels.h"
+
+namespace bwgr {
+
+namespace {
+
+constexpr int kT = 512;
+constexpr int kAtomBytes = 128 * 128;  // one 128-row atom of an X tile: 128 markers x 128 B
+constexpr uint32_t kSpin = 1u << 21;
+constexpr int kTS = 36;                // row stride (floats) of a 32x32 Gram tile in shared memory
+constexpr int kTileF = 32 * kTS;       // floats per Gram tile
+constexpr int kMS = 132;               // k/4 stride of a 32x32 inverse
+constexpr int kSolveWarps = 8, kInvWarp0 = 4, kCorrWarp0 = 8, kPreWarp0 = 12;
+constexpr int kDewStride = 136;        // 64-bit words per (block, system) of the published step
+constexpr int kLag = 2;
+constexpr int kRing = 8;               // blocks of partial / reduced h kept in flight (ring in L2)
+constexpr int kWPad = 160;             // worker slots per (block, system, marker) row of the partials
+constexpr int kRedWarp = 9;            // worker warp that reduces its share of the partials
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t nbytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+}
+// genotype bytes are streamed once per sweep: L2 evict-first keeps the small hot arrays (Gram band, b, xx, order) resident
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void cp_async16_stream(uint32_t dst, const void* src, uint32_t nbytes, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(nbytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return done != 0;
+}
+// Bounded wait.  A protocol bug or a dead peer must not hang the GPU: on time-out (or when another CTA
+// already raised the error flag) the thread turns `dead` and every later wait returns at once.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, bool& dead, int* err) {
+  if (dead) return;
+  for (uint32_t spin = 0; spin < kSpin; spin++) {
+    if (mbar_try(bar, parity)) return;
+    if ((spin & 1023u) == 1023u && *reinterpret_cast<volatile int*>(err) != 0) break;
+  }
+  dead = true;
+  atomicCAS(err, 0, 2);
+}
+__device__ __forceinline__ uint64_t desc_k_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(kAtomBytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__host__ __device__ constexpr uint32_t idesc_i8(int N, int a_mn) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, int& v0, int& v1, int& v2, int& v3) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ long long combine_limbs(int s0, int s1, int s2, int s3) {
+  return (long long)s0 + ((long long)s1 << 8) + ((long long)s2 << 16) + ((long long)s3 << 24);
+}
+// q (|q| <= 2^30) -> four balanced signed int8 limbs, q = l0 + 2^8 l1 + 2^16 l2 + 2^24 l3
+__device__ __forceinline__ void split_limbs(int q, int& l0, int& l1, int& l2, int& l3) {
+  l0 = (int)(signed char)(q & 0xFF); q = (q - l0) >> 8;
+  l1 = (int)(signed char)(q & 0xFF); q = (q - l1) >> 8;
+  l2 = (int)(signed char)(q & 0xFF); q = (q - l2) >> 8;
+  l3 = q;
+}
+// byte offset of element (row n, K byte kb) inside one K-major SWIZZLE_128B atom stack
+__device__ __forceinline__ uint32_t sw128_off(int n, int kb) {
+  return (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((((kb >> 4) ^ (n & 7)) & 7) << 4) + (kb & 15));
+}
+// one elected lane of a converged warp (the form ptxas recognises: tcgen05.mma is then issued without a per-lane loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// per (system, marker) inputs of the solve; per marker: xx and the marker id
+struct MarkerSys { float b0, vbj, a, c; };
+struct MarkerCol { float xx; int j; };
+
+// index of the 32x32 tile (hi, lo), lo <= hi, in the packed triangle
+__device__ __forceinline__ int tri(int hi, int lo) { return hi * (hi + 1) / 2 + lo; }
+
+struct Sync {
+  // worker
+  uint64_t tile_full[8], tile_empty[8], dl_full[2], u_done, el_full, g_done, g_empty;
+  // solver
+  uint64_t raw_ready[3], in_ready[3], solve_done[3], corr_ready[32], de_ready[32][4];
+  uint32_t tmem_base;
+};
+
+struct WLayout { int NA, N, nbuf; size_t xs, el, dl, es, dq, total; };
+__host__ __device__ inline WLayout worker_layout(int R, int ns, int nbuf) {
+  WLayout L;
+  L.NA = (R + 127) / 128; L.N = ((4 * ns + 15) / 16) * 16; L.nbuf = nbuf;
+  size_t o = 0;
+  L.xs = o; o += (size_t)nbuf * L.NA * kAtomBytes;
+  L.el = o; o += (size_t)L.NA * (L.N / 8) * 1024;
+  L.dl = o; o += (size_t)2 * (L.N / 8) * 1024;
+  L.es = o; o += (size_t)ns * L.NA * 128 * 4;
+  L.dq = o; o += (size_t)2 * 32 * 4;
+  L.total = o;
+  return L;
+}
+struct SLayout { size_t gs, mt, ms, mc, drw, tc, dh, prm, rb, total; };
+// sring = blocks of solve inputs in flight in the solver CTA (2 or 3)
+__host__ __device__ inline SLayout solver_layout(int ns, bool gibbs, bool use_inv, int sring) {
+  SLayout L;
+  size_t o = 0;
+  L.gs = o; o += (size_t)sring * 10 * kTileF * 4;                        // Gram triangle
+  L.mt = o; o += use_inv ? (size_t)sring * ns * 4 * 8 * kMS * 4 : 0;       // 32x32 inverses
+  L.ms = o; o += (size_t)sring * ns * 128 * sizeof(MarkerSys);
+  L.mc = o; o += (size_t)sring * 128 * sizeof(MarkerCol);
+  L.drw = o; o += gibbs ? (size_t)sring * ns * 128 * sizeof(MarkerDraws) : 0;
+  L.tc = o; o += (size_t)ns * 128 * 4;                                   // cross-Gram correction
+  L.dh = o; o += (size_t)ns * 128 * 4;                                   // dE of the block being solved
+  L.prm = o; o += (size_t)2 * 128 * 4;  // unused (kept for alignment)
+  L.rb = o; o += (size_t)kSolveWarps * 32 * 4;
+  L.total = o;
+  return L;
+}
+__host__ __device__ inline bool pipe_use_inv(int model, int ns) { return model_is_linear(model) && ns <= 2; }
+
+template <int MODEL>
+__global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ Sync S;
+  __shared__ SysScalars sc[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ns = a.nsys, p = a.g.p, W = a.nworkers, D = a.D, nblocks = a.nblocks;
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const bool is_solver = (int)blockIdx.x == W;
+  bool dead = false;
+
+  if (tid < ns) sc[tid] = a.sc[tid];
+  if (tid == 0) {
+    for (int i = 0; i < 8; i++) { mbar_init(&S.tile_full[i], 128); mbar_init(&S.tile_empty[i], 1); }
+    mbar_init(&S.dl_full[0], 128); mbar_init(&S.dl_full[1], 128);
+    mbar_init(&S.u_done, 1); mbar_init(&S.el_full, 128); mbar_init(&S.g_done, 1); mbar_init(&S.g_empty, 128);
+    const int nsw = ns < kSolveWarps ? ns : kSolveWarps;
+    for (int i = 0; i < 3; i++) { mbar_init(&S.raw_ready[i], 128); mbar_init(&S.in_ready[i], 128); mbar_init(&S.solve_done[i], nsw); }
+    for (int s = 0; s < 32; s++) {
+      mbar_init(&S.corr_ready[s], 128);
+      for (int d = 0; d < 4; d++) mbar_init(&S.de_ready[s][d], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+
+  if (!is_solver) {
+    // =====================================================================================================
+    // worker
+    // =====================================================================================================
+    const WLayout L = worker_layout(a.rows_per_cta, ns, a.nbuf);
+    const int R = a.rows_per_cta, NA = L.NA, N = L.N, RS = NA * 128, nbuf = L.nbuf;
+    const int row0 = blockIdx.x * R;
+    unsigned char* Xs = base + L.xs;
+    unsigned char* EL = base + L.el;
+    unsigned char* DL = base + L.dl;
+    float* Es = reinterpret_cast<float*>(base + L.es);
+    float* dqs = reinterpret_cast<float*>(base + L.dq);
+    {  // zero tiles and operand regions once: pad rows / chunks / limb columns stay zero for the whole kernel
+      uint4* z = reinterpret_cast<uint4*>(base);
+      const int nz = (int)(L.es >> 4);
+      for (int i = tid; i < nz; i += kT) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    bool bad = false;
+    for (int s = 0; s < ns; s++)
+      for (int i = tid; i < RS; i += kT) {
+        const int r = row0 + i;
+        const float e = (i < R && r < a.g.ld) ? a.e[(size_t)s * a.g.ld + r] : 0.0f;
+        Es[s * RS + i] = e;
+        if (i < R) {
+          const float sv = e * sc[s].e_qinv;
+          if (!(fabsf(sv) <= 1073741824.0f)) bad = true;
+          int l0, l1, l2, l3;
+          split_limbs(__float2int_rn(sv), l0, l1, l2, l3);
+          unsigned char* atom = EL + (size_t)(i >> 7) * (N / 8) * 1024;
+          const int kb = i & 127;
+          atom[sw128_off(4 * s + 0, kb)] = (unsigned char)l0; atom[sw128_off(4 * s + 1, kb)] = (unsigned char)l1;
+          atom[sw128_off(4 * s + 2, kb)] = (unsigned char)l2; atom[sw128_off(4 * s + 3, kb)] = (unsigned char)l3;
+        }
+      }
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < (NA + 1) * N) tmem_cols <<= 1;
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // initial limbs (generic stores) -> tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = S.tmem_base;
+    const uint32_t tmem_g = tmem_base + (uint32_t)(NA * N);
+    const bool tracing = a.trace != nullptr;
+#define WSTAMP(blk, k) do { if (tracing) { long long* tp_ = a.trace + ((size_t)blockIdx.x * nblocks + (blk)) * 32 + (k); tp_[0] = (long long)gtimer(); tp_[16] = clock64(); } } while (0)
+
+    if (warp == 0) {
+      // ------------------------------------------------------------------ tcgen05 issuer
+      const uint32_t idesc_g = idesc_i8(N, 0), idesc_u = idesc_i8(N, 1);
+      auto issue_g = [&](int c) {
+        const unsigned char* Xt = Xs + (size_t)(c % nbuf) * NA * kAtomBytes;
+        mbar_wait(&S.tile_full[c % nbuf], (uint32_t)(c / nbuf) & 1u, dead, a.err);
+        if (c > 0) mbar_wait(&S.g_empty, (uint32_t)(c - 1) & 1u, dead, a.err);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          for (int at = 0; at < NA; at++) {
+            const uint64_t ad = desc_k_sw128(smem_u32(Xt + (size_t)at * kAtomBytes));
+            const uint64_t bd = desc_k_sw128(smem_u32(EL + (size_t)at * (N / 8) * 1024));
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++) umma_i8(tmem_g, ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), idesc_g, (at | k4) != 0);
+          }
+          umma_commit(&S.g_done);
+        }
+        __syncwarp();
+      };
+      const int npro = (D < nblocks - 1 ? D : nblocks - 1);
+      for (int c = 0; c <= npro; c++) issue_g(c);
+      for (int b = 0; b < nblocks; b++) {
+        const unsigned char* Xt = Xs + (size_t)(b % nbuf) * NA * kAtomBytes;
+        mbar_wait(&S.dl_full[b & 1], (uint32_t)(b >> 1) & 1u, dead, a.err);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tracing && lane == 0) WSTAMP(b, 8);
+        if (elect_one()) {
+          const uint64_t bd = desc_k_sw128(smem_u32(DL + (size_t)(b & 1) * (N / 8) * 1024));
+          for (int at = 0; at < NA; at++) {
+            const uint64_t ad = desc_mn_sw128(smem_u32(Xt + (size_t)at * kAtomBytes));
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++)
+              umma_i8(tmem_base + (uint32_t)(at * N), ad + (uint64_t)(k4 * (4096 >> 4)), bd + (uint64_t)(2 * k4), idesc_u, k4 != 0);
+          }
+          umma_commit(&S.u_done);
+          umma_commit(&S.tile_empty[b % nbuf]);
+          if (tracing) WSTAMP(b, 2);
+        }
+        __syncwarp();
+        const int c = b + 1 + D;
+        if (c < nblocks) {
+          mbar_wait(&S.el_full, (uint32_t)b & 1u, dead, a.err);
+          if (tracing && lane == 0) WSTAMP(b, 9);
+          issue_g(c);
+          if (tracing && lane == 0) WSTAMP(b, 5);
+        }
+      }
+    } else if (warp <= 4) {
+      // ------------------------------------------------------------------ TMEM epilogue (thread = TMEM lane)
+      const int quarter = warp & 3;
+      const int q = quarter * 32 + lane;
+      const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
+      const bool t0 = tracing && q == 0;
+      auto g_epilogue = [&](int c) {
+        mbar_wait(&S.g_done, (uint32_t)c & 1u, dead, a.err);
+        if (t0) WSTAMP(c, 6);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // partial of marker q, system s -> part[c % ring][s][this worker][q] (full 32-byte sectors): (value << 16) | block tag
+        unsigned long long* hb = a.part + (((size_t)(c % kRing) * ns) * kWPad + blockIdx.x) * 128 + q;
+        const unsigned long long tagc = (unsigned long long)((c / kRing + 1) & 0xFFFF);
+        for (int s = 0; s < ns; s++) {
+          int s0, s1, s2, s3;
+          tmem_ld4(tmem_g + tlane + (uint32_t)(4 * s), s0, s1, s2, s3);
+          tmem_ld_wait();
+          const long long gq = combine_limbs(s0, s1, s2, s3);
+          st_relaxed_u64(hb + (size_t)s * kWPad * 128, ((unsigned long long)gq << 16) | tagc);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(&S.g_empty);
+        if (t0) WSTAMP(c, 7);
+      };
+      const int npro = (D < nblocks - 1 ? D : nblocks - 1);
+      for (int c = 0; c <= npro; c++) g_epilogue(c);
+      for (int b = 0; b < nblocks; b++) {
+        // ---- the step of block b, published by the solver: (int32 q << 32) | tag per marker, then the scale
+        {
+          const unsigned long long* wv = a.dew + (size_t)b * ns * kDewStride;
+          unsigned char* dl = DL + (size_t)(b & 1) * (N / 8) * 1024;
+          // epilogue warp e receives the systems s = e, e+4, ...: lane l polls step words l, l+32, l+64, l+96 and lane 0 the
+          // scale word as well (one L2 round trip when the step is already there), then writes the limbs of those markers
+          for (int s = quarter; s < ns; s += 4) {
+            const unsigned long long* ws = wv + (size_t)s * kDewStride;
+            unsigned long long v[4] = {0, 0, 0, 0}, vq = 0;
+            uint32_t spin = 0;
+            while (!dead) {
+              bool ok = true;
+#pragma unroll
+              for (int t = 0; t < 4; t++) { v[t] = ld_relaxed_u64(ws + 32 * t + lane); ok = ok && ((uint32_t)v[t] == a.tag); }
+              if (lane == 0) { vq = ld_relaxed_u64(ws + 128); ok = ok && ((uint32_t)vq == a.tag); }
+              if (__all_sync(0xffffffffu, ok)) break;
+              if (++spin > kSpin || ((spin & 255u) == 255u && *reinterpret_cast<volatile int*>(a.err) != 0)) { dead = true; atomicCAS(a.err, 0, 3); }
+            }
+            if (lane == 0) dqs[(b & 1) * 32 + s] = __uint_as_float((uint32_t)(vq >> 32));
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+              const int m = 32 * t + lane;
+              int l0, l1, l2, l3;
+              split_limbs(dead ? 0 : (int)(uint32_t)(v[t] >> 32), l0, l1, l2, l3);
+              dl[sw128_off(4 * s + 0, m)] = (unsigned char)l0; dl[sw128_off(4 * s + 1, m)] = (unsigned char)l1;
+              dl[sw128_off(4 * s + 2, m)] = (unsigned char)l2; dl[sw128_off(4 * s + 3, m)] = (unsigned char)l3;
+            }
+          }
+          if (t0) WSTAMP(b, 0);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(&S.dl_full[b & 1]);
+          named_bar(1, 128);  // the scales (dqs) of all systems visible to the four epilogue warps
+          if (t0) WSTAMP(b, 1);
+        }
+        // ---- E_slab -= X_b dE_b, then the limbs of the new residual (B operand of the next G pass)
+        mbar_wait(&S.u_done, (uint32_t)b & 1u, dead, a.err);
+        if (t0) WSTAMP(b, 3);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int s = 0; s < ns; s++) {
+          // all atoms of this thread's TMEM lane in flight at once: up to four independent dependency chains
+          int acc[4][4];
+#pragma unroll
+          for (int at = 0; at < 4; at++)
+            if (at < NA) tmem_ld4(tmem_base + tlane + (uint32_t)(at * N + 4 * s), acc[at][0], acc[at][1], acc[at][2], acc[at][3]);
+          tmem_ld_wait();
+          const float dqv = dqs[(b & 1) * 32 + s], eqi = sc[s].e_qinv;
+#pragma unroll
+          for (int at = 0; at < 4; at++) {
+            const int i = at * 128 + q;
+            if (at < NA && i < R) {
+              // uq * dq in two exact float pieces (uq = 2^24 hi + lo, |hi| < 2^22, 0 <= lo < 2^24; dq is a power of two)
+              const long long uq = combine_limbs(acc[at][0], acc[at][1], acc[at][2], acc[at][3]);
+              const float hi = (float)(int)(uq >> 24) * 16777216.0f, lo = (float)(int)(uq & 0xFFFFFF);
+              const float e = fmaf(-lo, dqv, fmaf(-hi, dqv, Es[s * RS + i]));
+              Es[s * RS + i] = e;
+              const float sv = e * eqi;
+              if (!(fabsf(sv) <= 1073741824.0f)) bad = true;
+              int l0, l1, l2, l3;
+              split_limbs(__float2int_rn(sv), l0, l1, l2, l3);
+              unsigned char* atom = EL + (size_t)at * (N / 8) * 1024;
+              atom[sw128_off(4 * s + 0, q)] = (unsigned char)l0; atom[sw128_off(4 * s + 1, q)] = (unsigned char)l1;
+              atom[sw128_off(4 * s + 2, q)] = (unsigned char)l2; atom[sw128_off(4 * s + 3, q)] = (unsigned char)l3;
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&S.el_full);
+        if (t0) WSTAMP(b, 4);
+        const int c = b + 1 + D;
+        if (c < nblocks) g_epilogue(c);
+      }
+      // residuals back to HBM
+      named_bar(1, 128);
+      for (int s = 0; s < ns; s++)
+        for (int i = q; i < R; i += 128) {
+          const int r = row0 + i;
+          if (r < a.g.ld) a.e[(size_t)s * a.g.ld + r] = Es[s * RS + i];
+        }
+    } else if ((warp >= 5 && warp <= 8) || (warp >= 10 && warp <= 13)) {
+      // ------------------------------------------------------------------ X tile gather
+      // two groups of four warps take alternate tiles; a group waits for its own tile to land before it signals it,
+      // so a tile is announced the moment it is complete and the other group's tile stays in flight meanwhile
+      const int grp = warp >= 10 ? 1 : 0;
+      const int lw = warp - (grp ? 10 : 5);
+      const int nchunk = R >> 4;
+      const bool act = lane < nchunk && row0 + 16 * lane < a.g.ld;
+      const uint32_t choff = (uint32_t)((lane >> 3) * kAtomBytes + ((lane & 7) << 4));
+      const int8_t* xrow = a.g.x8 + row0 + 16 * lane;
+      const uint64_t pol = policy_evict_first();
+      for (int t = grp; t < nblocks; t += 2) {
+        const int buf = t % nbuf;
+        const int pos = t * 128 + lw + 4 * lane;
+        const int myid = pos < p ? a.perm[pos] : -1;
+        if (t >= nbuf) mbar_wait(&S.tile_empty[buf], (uint32_t)(t / nbuf - 1) & 1u, dead, a.err);
+        const uint32_t dst = smem_u32(Xs + (size_t)buf * NA * kAtomBytes);
+#pragma unroll 8
+        for (int i = 0; i < 32; i++) {
+          const int m = lw + 4 * i;
+          const int j = __shfl_sync(0xffffffffu, myid, i);
+          if (lane < nchunk) {
+            const uint32_t dm = dst + (uint32_t)(m * 128) + (choff ^ (uint32_t)((m & 7) << 4));
+            const bool ok = act && j >= 0;
+            cp_async16_stream(dm, ok ? xrow + (int64_t)j * a.g.ld : a.g.x8, ok ? 16u : 0u, pol);
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (tracing && lw == 0 && lane == 0) WSTAMP(t, 12);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&S.tile_full[buf]);
+        if (tracing && lw == 0 && lane == 0) WSTAMP(t, 13);
+      }
+    } else if (warp == kRedWarp) {
+      // ------------------------------------------------------------------ second hop of the grid reduction
+      // row (block c, system s, marker m) of the partials is summed by worker (s*128 + m) % W; plain loads and one store,
+      // no atomics (143 x 128 L2 atomics per block cost ~7 us; this tree costs two L2 round trips)
+      for (int c = 0; c < nblocks; c++) {
+        const unsigned long long tagc = (unsigned long long)((c / kRing + 1) & 0xFFFF);
+        for (int task = blockIdx.x; task < ns * 128; task += W) {
+          const unsigned long long* row = a.part + ((size_t)(c % kRing) * ns + (task >> 7)) * kWPad * 128 + (task & 127);  // stride 128 words per worker
+          long long sum = 0;
+          uint32_t spin = 0;
+          while (!dead) {  // all W <= 160 words of the row in flight at once; re-read the whole row until every tag matches
+            bool ok = true;
+            sum = 0;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+              const int w = 32 * k + lane;
+              if (w < W) {
+                const unsigned long long v = ld_relaxed_u64(row + (size_t)w * 128);
+                ok = ok && ((v & 0xFFFFull) == tagc);
+                sum += (long long)v >> 16;
+              }
+            }
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (++spin > kSpin || ((spin & 255u) == 255u && *reinterpret_cast<volatile int*>(a.err) != 0)) { dead = true; atomicCAS(a.err, 0, 3); sum = 0; }
+          }
+          if (tracing && lane == 0 && task == (int)blockIdx.x) WSTAMP(c, 14);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (lane == 0) st_relaxed_u64(a.hred + (size_t)(c % kRing) * ns * 128 + task, ((unsigned long long)sum << 16) | tagc);
+          if (tracing && lane == 0 && task == (int)blockIdx.x) WSTAMP(c, 15);
+        }
+      }
+    }
+    if (bad) atomicExch(a.err, 4);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+#undef WSTAMP
+    return;
+  }
+
+  // =======================================================================================================
+  // solver
+  // =======================================================================================================
+  constexpr bool kLinear = model_is_linear(MODEL);
+  constexpr bool kGibbs = model_is_gibbs(MODEL);
+  const bool use_inv = pipe_use_inv(MODEL, ns);
+  const int sring = a.sring;
+  const SLayout L = solver_layout(ns, kGibbs, use_inv, sring);
+  float* Gs = reinterpret_cast<float*>(base + L.gs);
+  float* Mt = reinterpret_cast<float*>(base + L.mt);
+  MarkerSys* msys = reinterpret_cast<MarkerSys*>(base + L.ms);
+  MarkerCol* mcol = reinterpret_cast<MarkerCol*>(base + L.mc);
+  MarkerDraws* drw = reinterpret_cast<MarkerDraws*>(base + L.drw);
+  float* tcor = reinterpret_cast<float*>(base + L.tc);
+  float* dehist = reinterpret_cast<float*>(base + L.dh);
+  float* rb = reinterpret_cast<float*>(base + L.rb);
+  const int gstride = a.nband * 128;  // floats per Gram row in HBM
+  const int nsw = ns < kSolveWarps ? ns : kSolveWarps;
+  __syncthreads();
+  const bool tracing = a.trace != nullptr;
+#define SSTAMP(blk, k) do { if (tracing && warp == 0 && lane == 0) { long long* tp_ = a.trace + ((size_t)blockIdx.x * nblocks + (blk)) * 32 + (k); tp_[0] = (long long)gtimer(); tp_[16] = clock64(); } } while (0)
+
+  if (warp < kSolveWarps) {
+    if (use_inv && warp >= kInvWarp0) {
+      // ------------------------------------------------------------------ inverses of the diagonal blocks (ns <= 2: solve warps 4-7 are free)
+      // invert the four 32x32 diagonal blocks of I + A L (E-independent), one block of markers ahead of the solve
+      for (int nb = 0; nb < nblocks; nb++) {
+        const int slot = nb % sring;
+        mbar_wait(&S.raw_ready[slot], (uint32_t)(nb / sring) & 1u, dead, a.err);
+        const float* Gb = Gs + (size_t)slot * 10 * kTileF;
+        for (int task = warp - kInvWarp0; task < ns * 4; task += 4) {
+          const int s = task >> 2, d = task & 3;
+          const MarkerSys* mk = msys + ((size_t)slot * ns + s) * 128 + 32 * d;
+          const float* gt = Gb + (size_t)tri(d, d) * kTileF;
+          // column `lane` of M = (I + A L)^-1 by right-looking substitution: once x_k is final, every later partial sum
+          // takes its term at once (31-k independent FMAs), so the dependent chain is two FMAs per step
+          float x[32], sacc[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) sacc[i] = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 32; k++) {
+            x[k] = fmaf(-mk[k].a, sacc[k], (k == lane) ? 1.0f : 0.0f);
+            const float4* grow = reinterpret_cast<const float4*>(gt + k * kTS);  // row k = column k (symmetric tile)
+#pragma unroll
+            for (int i4 = (k + 1) / 4; i4 < 8; i4++) {
+              const float4 gv = grow[i4];
+              if (4 * i4 + 0 > k) sacc[4 * i4 + 0] = fmaf(gv.x, x[k], sacc[4 * i4 + 0]);
+              if (4 * i4 + 1 > k) sacc[4 * i4 + 1] = fmaf(gv.y, x[k], sacc[4 * i4 + 1]);
+              if (4 * i4 + 2 > k) sacc[4 * i4 + 2] = fmaf(gv.z, x[k], sacc[4 * i4 + 2]);
+              if (4 * i4 + 3 > k) sacc[4 * i4 + 3] = fmaf(gv.w, x[k], sacc[4 * i4 + 3]);
+            }
+          }
+          // M[i][c] (c = lane) stored as Mt4[c/4][i][c%4] with a padded c/4 stride: conflict-free both ways
+          float* mt = Mt + ((size_t)(slot * ns + s) * 4 + d) * 8 * kMS + (lane >> 2) * kMS + (lane & 3);
+#pragma unroll
+          for (int i = 0; i < 32; i++) mt[4 * i] = x[i];
+        }
+        mbar_arrive(&S.in_ready[slot]);
+        if (tracing && warp == kInvWarp0 && lane == 0) { long long* tp_ = a.trace + ((size_t)blockIdx.x * nblocks + nb) * 32 + 3; tp_[0] = (long long)gtimer(); tp_[16] = clock64(); }
+      }
+    }
+    // -------------------------------------------------------------------- solve warps (one system at a time)
+    if (warp < nsw) {
+      for (int b = 0; b < nblocks; b++) {
+        const int nvalid = min(128, p - b * 128);
+        const int slot = b % sring;
+        const float* Gb = Gs + (size_t)slot * 10 * kTileF;
+        const MarkerCol* mc = mcol + slot * 128;
+        mbar_wait(&S.in_ready[slot], (uint32_t)(b / sring) & 1u, dead, a.err);
+        for (int s = warp; s < ns; s += kSolveWarps) {
+          const SysScalars Sy = sc[s];
+          const MarkerSys* mk = msys + ((size_t)slot * ns + s) * 128;
+          const MarkerDraws* drb = drw + ((size_t)slot * ns + s) * 128;
+          float g[4], de[4];
+          {
+            long long qq[4] = {0, 0, 0, 0};
+            uint32_t spins = 0;
+            const unsigned long long* gq = a.hred + ((size_t)(b % kRing) * ns + s) * 128;
+            const unsigned long long tagb = (unsigned long long)((b / kRing + 1) & 0xFFFF);
+            while (!dead) {
+              bool ok = true;
+#pragma unroll
+              for (int t = 0; t < 4; t++) {
+                const unsigned long long w = ld_relaxed_u64(gq + 32 * t + lane);
+                ok = ok && ((w & 0xFFFFull) == tagb);
+                qq[t] = (long long)w >> 16;
+              }
+              if (__all_sync(0xffffffffu, ok)) break;
+              if (++spins > kSpin || ((spins & 255u) == 255u && *reinterpret_cast<volatile int*>(a.err) != 0)) { dead = true; atomicCAS(a.err, 0, 3); }
+            }
+            if (s == 0) SSTAMP(b, 8);
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+              g[t] = (float)((double)qq[t] * (double)Sy.e_q);
+              de[t] = 0.0f;
+            }
+          }
+          if (D > 0 && b > 0) {
+            mbar_wait(&S.corr_ready[s], (uint32_t)(b - 1) & 1u, dead, a.err);
+#pragma unroll
+            for (int t = 0; t < 4; t++) g[t] -= tcor[s * 128 + 32 * t + lane];
+          }
+          if (s == 0) SSTAMP(b, 9);
+          float nb[4] = {0.f, 0.f, 0.f, 0.f}, nd[4] = {1.f, 1.f, 1.f, 1.f}, nv[4] = {1.f, 1.f, 1.f, 1.f};
+          float* dh = dehist + s * 128;
+          if (Sy.done) {
+            // converged system (emEN): no update
+            if (D > 0) {
+#pragma unroll
+              for (int d = 0; d < 4; d++) dh[32 * d + lane] = 0.0f;
+              __syncwarp();
+              if (lane == 0) for (int d = 0; d < 4; d++) mbar_arrive(&S.de_ready[s][d]);
+            }
+          } else if (kLinear) {
+            float r[4], av[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) { av[t] = mk[32 * t + lane].a; r[t] = fmaf(av[t], g[t], mk[32 * t + lane].c); }
+            float* rbs = rb + warp * 32;
+#pragma unroll
+            for (int d = 0; d < 4; d++) {
+              float acc;
+              if (use_inv) {
+                // de_d = M_d r_d : broadcast r_d through shared memory, 128-bit loads down the k axis
+                __syncwarp();
+                rbs[lane] = r[d];
+                __syncwarp();
+                const float* mt = Mt + ((size_t)(slot * ns + s) * 4 + d) * 8 * kMS + 4 * lane;
+                float ac[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k4 = 0; k4 < 8; k4++) {
+                  const float4 mv = *reinterpret_cast<const float4*>(mt + k4 * kMS);
+                  const float4 rv = *reinterpret_cast<const float4*>(rbs + 4 * k4);
+                  ac[0] = fmaf(mv.x, rv.x, ac[0]); ac[1] = fmaf(mv.y, rv.y, ac[1]);
+                  ac[2] = fmaf(mv.z, rv.z, ac[2]); ac[3] = fmaf(mv.w, rv.w, ac[3]);
+                }
+                acc = (ac[0] + ac[1]) + (ac[2] + ac[3]);
+              } else {
+                // in-warp forward substitution of the 32x32 unit-lower-triangular diagonal block
+                const float* grow = Gb + (size_t)tri(d, d) * kTileF + lane * kTS;
+                float ag[32];
+#pragma unroll
+                for (int k4 = 0; k4 < 8; k4++) {
+                  const float4 gv = *reinterpret_cast<const float4*>(grow + 4 * k4);
+                  ag[4 * k4 + 0] = -av[d] * gv.x; ag[4 * k4 + 1] = -av[d] * gv.y;
+                  ag[4 * k4 + 2] = -av[d] * gv.z; ag[4 * k4 + 3] = -av[d] * gv.w;
+                }
+                float x = r[d];
+#pragma unroll
+                for (int k = 0; k < 31; k++) {
+                  const float xk = __shfl_sync(0xffffffffu, x, k);
+                  if (lane > k) x = fmaf(ag[k], xk, x);
+                }
+                acc = x;
+              }
+              de[d] = acc;
+              __syncwarp();
+              rbs[lane] = acc;
+              if (D > 0) dh[32 * d + lane] = acc;
+              __syncwarp();
+              if (D > 0 && lane == 0) mbar_arrive(&S.de_ready[s][d]);
+              if (d < 3) {
+#pragma unroll
+                for (int d2 = 0; d2 < 4; d2++) {
+                  if (d2 > d) {
+                    // r_d2 -= a * sum_k G[32 d2 + lane][32 d + k] * de_d[k]
+                    const float* grow = Gb + (size_t)tri(d2, d) * kTileF + lane * kTS;
+                    float fa[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; k4++) {
+                      const float4 gv = *reinterpret_cast<const float4*>(grow + 4 * k4);
+                      const float4 dv = *reinterpret_cast<const float4*>(rbs + 4 * k4);
+                      fa[0] = fmaf(gv.x, dv.x, fa[0]); fa[1] = fmaf(gv.y, dv.y, fa[1]);
+                      fa[2] = fmaf(gv.z, dv.z, fa[2]); fa[3] = fmaf(gv.w, dv.w, fa[3]);
+                    }
+                    r[d2] = fmaf(-av[d2], (fa[0] + fa[1]) + (fa[2] + fa[3]), r[d2]);
+                  }
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+#pragma unroll 8
+              for (int i = 0; i < 32; i++) {
+                const int jj = 32 * t + i;
+                if (jj >= nvalid) break;
+                const float gc = __shfl_sync(0xffffffffu, g[t], i);
+                const MarkerSys in = mk[jj];
+                MarkerDraws dr;
+                if (kGibbs) dr = drb[jj];
+                else { dr.z1 = dr.z2 = dr.u = 0.0f; dr.chi = 1.0f; }
+                const RuleOut ro = marker_rule<MODEL>(gc, mc[jj].xx, in.b0, in.vbj, Sy, dr);
+                if (lane == i) { nb[t] = ro.b; nd[t] = ro.d; nv[t] = ro.vbj; de[t] = ro.de; }
+                // row jj of the Gram block to the right of (and inside) its diagonal tile: stored as tile (tt, t)
+#pragma unroll
+                for (int tt = 0; tt < 4; tt++)
+                  if (tt >= t) g[tt] = fmaf(-Gb[(size_t)tri(tt, t) * kTileF + i * kTS + lane], ro.de, g[tt]);
+              }
+              if (D > 0) {
+                dh[32 * t + lane] = de[t];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.de_ready[s][t]);
+              }
+            }
+          }
+          if (s == 0) SSTAMP(b, 10);
+          // quantise dE to 31-bit fixed point relative to the block maximum and publish it
+          float mx = fmaxf(fmaxf(fabsf(de[0]), fabsf(de[1])), fmaxf(fabsf(de[2]), fabsf(de[3])));
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          int ex = 0;
+          if (mx > 0.0f && mx < 3.0e38f) frexpf(mx, &ex);
+          if (ex < -90) ex = -90;
+          const float dq = ldexpf(1.0f, ex - 30), dqinv = ldexpf(1.0f, 30 - ex);
+          if (!(mx < 3.0e38f)) atomicExch(a.err, 4);
+          unsigned long long* wv = a.dew + ((size_t)b * ns + s) * kDewStride;
+          int qv[4];
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            const int jj = 32 * t + lane;
+            const bool valid = jj < nvalid && !Sy.done;
+            qv[t] = valid ? __float2int_rn(de[t] * dqinv) : 0;
+            st_relaxed_u64(wv + jj, ((unsigned long long)(uint32_t)qv[t] << 32) | a.tag);
+          }
+          if (lane == 0) st_relaxed_u64(wv + 128, ((unsigned long long)__float_as_uint(dq) << 32) | a.tag);
+          if (s == 0) SSTAMP(b, 11);
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            const int jj = 32 * t + lane;
+            if (jj < nvalid && !Sy.done) {
+              const float deq = (float)qv[t] * dq;  // the step actually applied to E (exactly representable)
+              const MarkerSys in = mk[jj];
+              float bnew, dnew = nd[t], vnew = nv[t];
+              if (kLinear) {
+                bnew = fmaf(deq, (MODEL == M_EMBA) ? 0.5f : 1.0f, in.b0);
+                if (MODEL == M_EMBA) vnew = (Sy.Sb + bnew * bnew) / (Sy.df + 1.0f);
+                if (MODEL == M_BA) vnew = (Sy.Sb + bnew * bnew) / drb[jj].chi;
+              } else {
+                bnew = nb[t];
+              }
+              const int j = mc[jj].j;
+              a.b[(size_t)s * p + j] = bnew;
+              if (model_has_d(MODEL) && a.d) a.d[(size_t)s * p + j] = dnew;
+              if (model_has_vbj(MODEL) && MODEL != M_KMUP && a.vbv) a.vbv[(size_t)s * p + j] = vnew;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.solve_done[slot]);
+      }
+    }
+  } else if (warp < kPreWarp0) {
+    // -------------------------------------------------------------------- cross-Gram correction (D = 1)
+    // thread = row i of block b+1:  t[s][i] = sum_k (x_{b+1,i}' x_{b,k}) dE_b[s][k], consumed 32 markers at a time
+    if (D > 0) {
+      constexpr int kCS = 256;  // floats per Gram row when the band is 2 (the only band with D = 1): immediate offsets
+      const int i = (warp - kCorrWarp0) * 32 + lane;
+      for (int b = 0; b + 1 < nblocks; b++) {
+        // cross block of block b+1, stored transposed: ct[k * gstride] = x_{b,k}' x_{b+1,i}  (a warp reads 128 B per k)
+        const float* ct = a.gram + (size_t)(b + 1) * 128 * kCS + 128 + i;
+        // two 32-marker chunks of the row in flight at any time (64 registers): chunk d+2 is fetched into the set that
+        // chunk d just released, two solve steps (~1000 cycles) before it is needed -- an L2 hit thanks to the prefetch
+        float c0[32], c1[32];
+#pragma unroll
+        for (int k = 0; k < 32; k++) c0[k] = __ldg(ct + k * kCS);
+#pragma unroll
+        for (int k = 0; k < 32; k++) c1[k] = __ldg(ct + (32 + k) * kCS);
+        if (b + 2 < nblocks) {  // pull the cross block of block b+2 into L2 now: row i of it, 4 lines of 128 B
+          const float* nxt = a.gram + ((size_t)(b + 2) * 128 + i) * kCS + 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; q4++) prefetch_l2(nxt + 32 * q4);
+        }
+        auto chunk = [&](const float (&cv)[32], int d) {
+          for (int s = 0; s < ns; s++) {
+            mbar_wait(&S.de_ready[s][d], (uint32_t)b & 1u, dead, a.err);
+            const float4* dv = reinterpret_cast<const float4*>(dehist + s * 128 + 32 * d);
+            float fa[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k4 = 0; k4 < 8; k4++) {
+              const float4 v = dv[k4];
+              fa[0] = fmaf(cv[4 * k4 + 0], v.x, fa[0]); fa[1] = fmaf(cv[4 * k4 + 1], v.y, fa[1]);
+              fa[2] = fmaf(cv[4 * k4 + 2], v.z, fa[2]); fa[3] = fmaf(cv[4 * k4 + 3], v.w, fa[3]);
+            }
+            const float part = (fa[0] + fa[1]) + (fa[2] + fa[3]);
+            if (d == 0) tcor[s * 128 + i] = part; else tcor[s * 128 + i] += part;
+            if (d == 3) mbar_arrive(&S.corr_ready[s]);
+          }
+        };
+        chunk(c0, 0);
+#pragma unroll
+        for (int k = 0; k < 32; k++) c0[k] = __ldg(ct + (64 + k) * kCS);
+        chunk(c1, 1);
+#pragma unroll
+        for (int k = 0; k < 32; k++) c1[k] = __ldg(ct + (96 + k) * kCS);
+        chunk(c0, 2);
+        chunk(c1, 3);
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- prefetch of the solve inputs (ring of sring blocks)
+    // thread ht = marker ht of the block.  Marker ids are fetched two blocks ahead and the per-marker scalars one block
+    // ahead into registers, so the HBM round trips of these tiny gathers never sit on the per-block path.
+    const int ht = (warp - kPreWarp0) * 32 + lane;  // 0..127
+#define PSTAMP(k) do { if (tracing && ht == 0) { long long* tp_ = a.trace + ((size_t)blockIdx.x * nblocks + nb) * 32 + (k); tp_[0] = (long long)gtimer(); tp_[16] = clock64(); } } while (0)
+    constexpr int kPipeSys = 2;  // systems whose scalars are register-pipelined (more systems: loaded in place)
+    auto perm_at = [&](int blk) { const int pos = blk * 128 + ht; return (blk < nblocks && pos < p) ? a.perm[pos] : -1; };
+    int j_cur = perm_at(0), j_nxt = perm_at(1);
+    float xx_cur = j_cur >= 0 ? a.xx[j_cur] : 1.0f, b_cur[kPipeSys], v_cur[kPipeSys];
+#pragma unroll
+    for (int s = 0; s < kPipeSys; s++) {
+      b_cur[s] = (s < ns && j_cur >= 0) ? a.b[(size_t)s * p + j_cur] : 0.0f;
+      v_cur[s] = (s < ns && j_cur >= 0 && model_has_vbj(MODEL) && a.vbv) ? a.vbv[(size_t)s * p + j_cur] : 1.0f;
+    }
+    const int rr0 = ht >> 3, c4 = ht & 7;
+    for (int nb = 0; nb < nblocks; nb++) {
+      const int slot = nb % sring;
+      if (nb >= sring) mbar_wait(&S.solve_done[slot], (uint32_t)(nb / sring - 1) & 1u, dead, a.err);
+      PSTAMP(0);
+      // Gram triangle of block nb: linear rules read tile (hi, lo) = G[32 hi + r][32 lo + c];
+      // the scalar chain reads the transposed triangle, stored in the same slots
+      {
+        float* Gb = Gs + (size_t)slot * 10 * kTileF;
+        const float* src = a.gram + (size_t)nb * 128 * gstride;
+#pragma unroll
+        for (int it = 0; it < 20; it++) {
+          constexpr int kHi[10] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3}, kLo[10] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3};
+          const int tile = it >> 1, rr = rr0 + 16 * (it & 1);
+          const int hi = kHi[tile], lo = kLo[tile];
+          const int grow_ = kLinear ? 32 * hi + rr : 32 * lo + rr, gcol = kLinear ? 32 * lo + 4 * c4 : 32 * hi + 4 * c4;
+          cp_async16(smem_u32(Gb + (size_t)tile * kTileF + rr * kTS + 4 * c4), src + (size_t)grow_ * gstride + gcol, 16u);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      PSTAMP(1);
+      // issue the gathers of the following blocks now; they are consumed in the next iteration
+      const int j_nn = perm_at(nb + 2);
+      float xx_nxt = 1.0f, b_nxt[kPipeSys], v_nxt[kPipeSys];
+      if (j_nxt >= 0) xx_nxt = a.xx[j_nxt];
+#pragma unroll
+      for (int s = 0; s < kPipeSys; s++) {
+        b_nxt[s] = (s < ns && j_nxt >= 0) ? a.b[(size_t)s * p + j_nxt] : 0.0f;
+        v_nxt[s] = (s < ns && j_nxt >= 0 && model_has_vbj(MODEL) && a.vbv) ? a.vbv[(size_t)s * p + j_nxt] : 1.0f;
+      }
+      {
+        const int j = j_cur;
+        MarkerCol mcv;
+        mcv.xx = xx_cur; mcv.j = j;
+        mcol[slot * 128 + ht] = mcv;
+        for (int s = 0; s < ns; s++) {
+          MarkerSys in = {0.0f, 1.0f, 0.0f, 0.0f};
+          if (j >= 0 && !sc[s].done) {
+            if (s < kPipeSys) { in.b0 = b_cur[s < kPipeSys ? s : 0]; in.vbj = v_cur[s < kPipeSys ? s : 0]; }
+            else {
+              in.b0 = a.b[(size_t)s * p + j];
+              in.vbj = (model_has_vbj(MODEL) && a.vbv) ? a.vbv[(size_t)s * p + j] : 1.0f;
+            }
+            MarkerDraws dr;
+            dr.z1 = dr.z2 = dr.u = 0.0f; dr.chi = 1.0f;
+            if (kGibbs) {
+              dr = marker_draws(MODEL, (uint32_t)j, (uint32_t)sc[s].sweep, (uint32_t)(a.chain0 + s), sc[s].df, a.seed_lo, a.seed_hi);
+              drw[((size_t)slot * ns + s) * 128 + ht] = dr;
+            }
+            if (kLinear) {
+              const LinCoef lc = lin_coef<MODEL>(mcv.xx, in.b0, in.vbj, sc[s], dr);
+              in.a = lc.a; in.c = lc.c;
+            }
+          }
+          msys[((size_t)slot * ns + s) * 128 + ht] = in;
+        }
+      }
+      PSTAMP(2);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (use_inv) mbar_arrive(&S.raw_ready[slot]);
+      else mbar_arrive(&S.in_ready[slot]);
+      PSTAMP(7);
+      j_cur = j_nxt; j_nxt = j_nn; xx_cur = xx_nxt;
+#pragma unroll
+      for (int s = 0; s < kPipeSys; s++) { b_cur[s] = b_nxt[s]; v_cur[s] = v_nxt[s]; }
+    }
+#undef PSTAMP
+  }
+#undef SSTAMP
+}
+
+template <int MODEL>
+void launch_model(const PipeArgs& a, size_t smem, cudaStream_t st) {
+  cudaFuncSetAttribute(sweep_pipe_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  PipeArgs args = a;
+  void* params[] = {&args};
+  cudaLaunchCooperativeKernel((void*)sweep_pipe_kernel<MODEL>, dim3(a.nworkers + 1), dim3(kT), params, smem, st);
+}
+
+}  // namespace
+
+// Shared memory of one CTA (both roles use the same launch) and the largest tile ring that fits.
+size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring) {
+  const size_t w = worker_layout(rows_per_cta, nsys, nbuf).total;
+  const size_t s = solver_layout(nsys, model_is_gibbs(model), pipe_use_inv(model, nsys), sring).total;
+  return (w > s ? w : s) + 1024;
+}
+
+void launch_sweep_pipe(const PipeArgs& a, cudaStream_t st) {
+  const size_t smem = sweep_pipe_smem(a.rows_per_cta, a.nsys, a.model, a.nbuf, a.sring);
+  switch (a.model) {
+    case M_EMRR: launch_model<M_EMRR>(a, smem, st); break;
+    case M_EMBA: launch_model<M_EMBA>(a, smem, st); break;
+    case M_EMBB: launch_model<M_EMBB>(a, smem, st); break;
+    case M_EMBC: launch_model<M_EMBC>(a, smem, st); break;
+    case M_EMBL: launch_model<M_EMBL>(a, smem, st); break;
+    case M_EMEN: launch_model<M_EMEN>(a, smem, st); break;
+    case M_BRR: launch_model<M_BRR>(a, smem, st); break;
+    case M_BA: launch_model<M_BA>(a, smem, st); break;
+    case M_BB: launch_model<M_BB>(a, smem, st); break;
+    case M_BC: launch_model<M_BC>(a, smem, st); break;
+    case M_KMUP: launch_model<M_KMUP>(a, smem, st); break;
+    case M_MRR: launch_model<M_MRR>(a, smem, st); break;
+    default: break;
+  }
+}
+
+}  // namespace bwgr
