@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--e2e-sweeps", type=int, default=200)
     ap.add_argument("--cpu-markers", type=int, default=2048)
     ap.add_argument("--cpu-sweeps", type=int, default=10)
+    ap.add_argument("--cpu-sweeps-main", type=int, default=150, help="sweeps of the cpu_baseline sample of the main arm (~15 s)")
+    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch of the dominant kernel from an ncu capture (profiles/)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -102,7 +104,7 @@ class ClockSampler:
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -138,17 +140,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_sample(args, Xs, y, native=False):
+def ncu_traffic(kernel, n, p):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu capture of the same
+    workload shape (profiles/r1_traffic.json, written by tools/ncu_traffic.py); None if there is no capture for it."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        e = d.get(kernel)
+        if e and e.get("n") == n:
+            return e["bytes_per_launch"] * (p / e["p"])  # captured on a p-slice of the same n; traffic is linear in p
+    except Exception:
+        pass
+    return None
+
+
+def cpu_sample(args, Xs, y, native=False, sweeps=None):
     """Oracle emRR on full n x the first m markers: sweeps timed as (it sweeps) - (0 sweeps)."""
     import oracle as O
     Xf = np.asfortranarray(Xs, dtype=np.float32)
     t0 = time.perf_counter()
     O.em(args.model, y, Xf, it=0, native=native)
     t1 = time.perf_counter()
-    O.em(args.model, y, Xf, it=args.cpu_sweeps, native=native)
+    sweeps = sweeps or args.cpu_sweeps
+    O.em(args.model, y, Xf, it=sweeps, native=native)
     t2 = time.perf_counter()
     sweeps_s = max((t2 - t1) - (t1 - t0), 1e-9)
-    return args.cpu_sweeps * Xf.shape[1] / sweeps_s, sweeps_s
+    return sweeps * Xf.shape[1] / sweeps_s, sweeps_s
 
 
 def cpu_model_name():
@@ -223,6 +239,8 @@ def main():
     g.set_stream(stream.cuda_stream)
     g.load(Xt)  # device-resident int8 (p x n row-major == n x p column-major)
     st = bw.EmStepper(args.model, y, g)
+    sampler = ClockSampler(local)
+    sampler.start()  # started before the warm-up: the timed region can be shorter than nvidia-smi's first sample
     st.sweeps(args.warmup)
     torch.cuda.synchronize()
 
@@ -231,9 +249,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    n_before = len(sampler.rows)
     l0 = g.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -242,7 +259,6 @@ def main():
     barrier()
     launches = g.launch_count() - l0
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -253,18 +269,19 @@ def main():
     st.sweeps(args.steps)
     prof = g.profile_read()
     g.profile(False)
+    clocks = sampler.stop()  # covers warm-up, the timed region and the per-kernel timing pass (all the same sweeps)
     fit = st.end()
     assert np.isfinite(fit["b"]).all() and np.isfinite(fit["h2"])
     hbm_peak, peak_src = peaks()
     sweep_ms = prof["sweep"]["ms"] / max(1, prof["sweep"]["launches"])
     gram_ms = prof["gram"]["ms"] / max(1, prof["gram"]["launches"])
     epi_ms = prof["epilogue"]["ms"] / max(1, prof["epilogue"]["launches"])
-    dom = "sweep_blocked_kernel" if sweep_ms >= gram_ms else "gram_tc_kernel"
+    dom = "sweep_pipe_kernel" if sweep_ms >= gram_ms else "gram_tc_kernel"
     dom_ms = max(sweep_ms, gram_ms)
     achieved = n * p / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "kernel": dom, "peak_source": peak_src, "algorithmic_bytes_per_launch": n * p,
-                "kernel_ms": {"sweep_blocked_kernel": sweep_ms, "gram_tc_kernel": gram_ms, "epilogue_kernel": epi_ms},
+                "traffic": args.traffic if args.traffic is not None else ncu_traffic(dom, n, p), "kernel": dom, "peak_source": peak_src, "algorithmic_bytes_per_launch": n * p,
+                "kernel_ms": {"sweep_pipe_kernel": sweep_ms, "gram_tc_kernel": gram_ms, "epilogue_kernel": epi_ms},
                 "whole_sweep_frac": (n * p / (ms / args.steps * 1e-3) / 1e9) / hbm_peak}
     value = world * p * args.steps / (ms * 1e-3)
 
@@ -302,10 +319,10 @@ def main():
             Xs = Xt[:m].cpu().numpy().T
         else:
             Xs = Xh[:m].numpy().T
-        v, secs = cpu_sample(args, Xs, y)
+        v, secs = cpu_sample(args, Xs, y, sweeps=args.cpu_sweeps_main)
         cpu = {"value": v, "unit": "marker-updates/s", "cores": 1, "kind": "port",
                "sample": "oracle %s (g++ -O2, float32, 1 thread like the reference), full n=%d x first %d markers, %d sweeps = %.1f s; %s, %d host cores" % (
-                   args.model, n, m, args.cpu_sweeps, secs, cpu_model_name(), os.cpu_count())}
+                   args.model, n, m, args.cpu_sweeps_main, secs, cpu_model_name(), os.cpu_count())}
 
     if rank == 0:
         line = {"metric": "marker-updates/sec (emRR Gauss-Seidel sweep, n=50k x p=50k int8)", "value": value,
@@ -313,7 +330,7 @@ def main():
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "%s Gauss-Seidel sweep, synthetic n=%d x p=%d int8 genotypes, k=1" % (args.model, n, p),
-                           "step": "one full sweep = p marker updates (Gram blocks + blocked sweep + epilogue)",
+                           "step": "one full sweep = p marker updates (Gram band + pipelined blocked sweep + epilogue)",
                            "l2": "genotypes are %.1f GB per sweep, far larger than the 126 MB L2: no flush needed" % (n * p / 1e9),
                            "parallelism": "1 GPU" if world == 1 else "%d independent replicas (one fit per GPU, no collective)" % world,
                            "seed": SEED},

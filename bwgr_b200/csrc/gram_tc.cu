@@ -23,11 +23,24 @@ constexpr int kTileBytes = 128 * 128;
 // NBAND = 1: diagonal blocks X_b'X_b only.  NBAND = 2: [X_b'X_b | X_{b-1}'X_b] (one-block look-ahead of the
 // pipelined sweep, sweep_pipe.cu): row r of block b holds NBAND*128 entries, x_{b,r}'X_b then x_{b-1,r}'X_b.
 // The gather is latency-bound: keep (almost) the whole 227 KB of shared memory in flight.
-template <int NBAND> struct GramCfg { static constexpr int kStages = NBAND == 1 ? 13 : 6; static constexpr int kLag = kStages - 2; };
+// A stage holds kSub consecutive 128-row atoms of every column of the band, so one visit to a column reads kSub*128
+// contiguous bytes (DRAM pages are reused instead of re-opened per 128 B).
+template <int NBAND> struct GramCfg {
+  static constexpr int kSub = NBAND == 1 ? 4 : 2;
+  static constexpr int kStages = 3;
+  static constexpr int kLag = 2;
+};
 constexpr uint32_t kSpinLimit = 1u << 22;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one elected lane of a converged warp: the form ptxas turns into back-to-back UTC*MMA issue (a plain `lane == 0`
+// branch makes it wrap every tcgen05.mma in a per-lane loop, ~250 cycles per instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -104,7 +117,8 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
                                                          int32_t* __restrict__ gram, int out_f32, int* err) {
   constexpr int kStages = GramCfg<NBAND>::kStages;
   constexpr int kLag = GramCfg<NBAND>::kLag;  // cp.async groups kept in flight per producer thread
-  constexpr int kStageBytes = NBAND * kTileBytes;
+  constexpr int kSub = GramCfg<NBAND>::kSub;
+  constexpr int kStageBytes = NBAND * kSub * kTileBytes;
   constexpr uint32_t kAccCols = NBAND * 128;  // TMEM columns of one accumulator stage
   using Sm = GramSmem<NBAND>;
   extern __shared__ unsigned char smem_raw[];
@@ -113,6 +127,7 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
   Sm* S = reinterpret_cast<Sm*>(tiles + kStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkt = (int)(g.ld >> 7);  // K tiles of 128 rows (ld is a multiple of 128)
+  const int nkg = (nkt + GramCfg<NBAND>::kSub - 1) / GramCfg<NBAND>::kSub;  // stages per block
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) { mbar_init(&S->full[s], 128); mbar_init(&S->empty[s], 1); }
@@ -147,18 +162,24 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
           colp[d][i] = g.x8 + (int64_t)j * g.ld + ((t & 7) << 4);
           nbytes[d][i] = valid ? 16u : 0u;
         }
-      for (int kt = 0; kt < nkt && ok; kt++, it++) {
+      for (int kg = 0; kg < nkg && ok; kg++, it++) {
         const uint32_t stage = it % kStages, phase = (it / kStages) & 1u;
         ok = mbar_wait(&S->empty[stage], phase ^ 1u, err);
         const uint32_t tbase = smem_u32(tiles + stage * kStageBytes);
 #pragma unroll
-        for (int d = 0; d < NBAND; d++)
+        for (int sub = 0; sub < kSub; sub++) {
+          const int kt = kg * kSub + sub;
+          if (kt < nkt) {
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const int m = i * 16 + (t >> 3);
-            const uint32_t dst = tbase + d * kTileBytes + m * 128 + ((((uint32_t)t & 7u) ^ ((uint32_t)m & 7u)) << 4);
-            cp_async16_zfill(dst, colp[d][i] + (int64_t)kt * 128, nbytes[d][i]);
+            for (int d = 0; d < NBAND; d++)
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                const int m = i * 16 + (t >> 3);
+                const uint32_t dst = tbase + (sub * NBAND + d) * kTileBytes + m * 128 + ((((uint32_t)t & 7u) ^ ((uint32_t)m & 7u)) << 4);
+                cp_async16_zfill(dst, colp[d][i] + (int64_t)kt * 128, nbytes[d][i]);
+              }
           }
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (it >= kLag) {
           asm volatile("cp.async.wait_group %0;" ::"n"(kLag) : "memory");
@@ -180,26 +201,32 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
       ok = mbar_wait(&S->tmem_empty[as], aphase ^ 1u, err);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_base + as * kAccCols;
-      for (int kt = 0; kt < nkt && ok; kt++, it++) {
+      for (int kg = 0; kg < nkg && ok; kg++, it++) {
         const uint32_t stage = it % kStages, phase = (it / kStages) & 1u;
         ok = mbar_wait(&S->full[stage], phase, err);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0) {
-          const uint64_t desc = make_desc_sw128(smem_u32(tiles + stage * kStageBytes));
+        if (elect_one()) {
 #pragma unroll
-          for (int d = 0; d < NBAND; d++) {
-            const uint64_t bdesc = make_desc_sw128(smem_u32(tiles + stage * kStageBytes + d * kTileBytes));
+          for (int sub = 0; sub < kSub; sub++) {
+            const int kt = kg * kSub + sub;
+            if (kt < nkt) {
+              const uint64_t desc = make_desc_sw128(smem_u32(tiles + stage * kStageBytes + sub * NBAND * kTileBytes));
 #pragma unroll
-            for (int k4 = 0; k4 < 4; k4++) {
-              // band d >= 1 is stored transposed: row r = marker r of block b-d, columns = markers of block b, so that the
-              // sweep's correction threads (one per marker of block b) read it coalesced
-              const uint32_t acc = (kt | k4) != 0 ? 1u : 0u;
-              if (FP8) {
-                if (d == 0) umma_f8(tmem_d, desc + (uint64_t)(k4 * 2), desc + (uint64_t)(k4 * 2), kIdescF8, acc);
-                else umma_f8(tmem_d + (uint32_t)d * 128u, bdesc + (uint64_t)(k4 * 2), desc + (uint64_t)(k4 * 2), kIdescF8, acc);
-              } else {
-                if (d == 0) umma_i8(tmem_d, desc + (uint64_t)(k4 * 2), desc + (uint64_t)(k4 * 2), kIdescI8, acc);
-                else umma_i8(tmem_d + (uint32_t)d * 128u, bdesc + (uint64_t)(k4 * 2), desc + (uint64_t)(k4 * 2), kIdescI8, acc);
+              for (int d = 0; d < NBAND; d++) {
+                const uint64_t bdesc = make_desc_sw128(smem_u32(tiles + stage * kStageBytes + (sub * NBAND + d) * kTileBytes));
+#pragma unroll
+                for (int k4 = 0; k4 < 4; k4++) {
+                  // band d >= 1 is stored transposed: row r = marker r of block b-d, columns = markers of block b, so that
+                  // the sweep's correction threads (one per marker of block b) read it coalesced
+                  const uint32_t acc = (kt | k4) != 0 ? 1u : 0u;
+                  if (FP8) {
+                    if (d == 0) umma_f8(tmem_d, desc + (uint64_t)(k4 * 2), desc + (uint64_t)(k4 * 2), kIdescF8, acc);
+                    else umma_f8(tmem_d + (uint32_t)d * 128u, bdesc + (uint64_t)(k4 * 2), desc + (uint64_t)(k4 * 2), kIdescF8, acc);
+                  } else {
+                    if (d == 0) umma_i8(tmem_d, desc + (uint64_t)(k4 * 2), desc + (uint64_t)(k4 * 2), kIdescI8, acc);
+                    else umma_i8(tmem_d + (uint32_t)d * 128u, bdesc + (uint64_t)(k4 * 2), desc + (uint64_t)(k4 * 2), kIdescI8, acc);
+                  }
+                }
               }
             }
           }
@@ -207,7 +234,7 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
         }
         __syncwarp();
       }
-      if (lane == 0) umma_commit(&S->tmem_full[as]);
+      if (elect_one()) umma_commit(&S->tmem_full[as]);
       __syncwarp();
     }
   } else {
@@ -288,7 +315,7 @@ __global__ void __launch_bounds__(256) gram_simt_kernel(GenoView g, const int* _
 template <int NBAND, bool FP8>
 static void launch_gram_band(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, int* err, int num_sms,
                              cudaStream_t st) {
-  const size_t smem = (size_t)GramCfg<NBAND>::kStages * NBAND * kTileBytes + sizeof(GramSmem<NBAND>) + 1024;
+  const size_t smem = (size_t)GramCfg<NBAND>::kStages * GramCfg<NBAND>::kSub * NBAND * kTileBytes + sizeof(GramSmem<NBAND>) + 1024;
   cudaFuncSetAttribute(gram_tc_kernel<NBAND, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = nblocks < num_sms ? nblocks : num_sms;
   gram_tc_kernel<NBAND, FP8><<<grid, 288, smem, st>>>(g, perm, nblocks, static_cast<int32_t*>(gram), out_f32, err);
