@@ -282,3 +282,37 @@ def BayesB(y, X, it=1500, bi=500, pi=0.95, df=5, R2=0.5, **kw):
 
 def BayesC(y, X, it=1500, bi=500, pi=0.95, df=5, R2=0.5, **kw):
     return gibbs_fit("BayesC", y, X, it=it, bi=bi, pi=pi, df=df, R2=R2, **kw)
+
+
+def KMUP(X, b, d, xx, e, L, Ve, pi, seed=1, **store_kw):
+    """One Kuo-Mallick sweep, drop-in for KMUP(X,b,d,xx,e,L,Ve,pi) (Rcpp20260726ai.cpp:12-38): returns (b, d, e)
+    like the reference's list.  X: matrix or Genotypes store."""
+    g, own = _store(X, **store_kw)
+    try:
+        b, d, xx, e, L = (np.array(v, dtype=np.float64) for v in (b, d, xx, e, L))
+        check(g.lib.bwgr_kmup_sweep(g.h, _ptr(b), _ptr(d), _ptr(xx), _ptr(e), _ptr(L), float(Ve), float(pi), int(seed)))
+        return {"b": b, "d": d, "e": e}
+    finally:
+        if own:
+            g.close()
+
+
+def wgr(y, X, it=1500, bi=500, th=1, bag=1, rp=False, iv=False, de=False, pi=0, df=5, R2=0.5, eigK=None, VarK=0.95,
+        verb=False, seed=1, **store_kw):
+    """wgr() of R/wgr.R:2-8 with the MCMC loop native (one C call instead of `it` KMUP round trips).
+    Model map (man/wgr.Rd:185): BRR pi=0,iv=F; BayesA iv=T; BayesB pi>0,iv=T; BayesC pi>0,iv=F; BayesL de=T."""
+    if bag != 1 or rp or eigK is not None:
+        raise _lib.BwgrError(-5, "wgr: bag != 1, rp and eigK are not on the B200 path")
+    g, own = _store(X, **store_kw)
+    try:
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        b, d, Vb = (np.zeros(g.p) for _ in range(3))
+        hat = np.zeros(g.n)
+        scal = np.zeros(4)
+        check(g.lib.bwgr_wgr_fit(g.h, _ptr(y), int(it), int(bi), int(th), int(bool(iv)), int(bool(de)), float(pi), float(df),
+                                 float(R2), int(seed), _ptr(b), _ptr(d), _ptr(Vb), _ptr(hat), _ptr(scal)))
+        return {"mu": float(scal[0]), "b": b, "Vb": Vb if (iv or de) else float(scal[2]), "d": d, "Ve": float(scal[1]),
+                "hat": hat, "cxx": float(scal[3])}
+    finally:
+        if own:
+            g.close()

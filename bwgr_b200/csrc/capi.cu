@@ -87,6 +87,13 @@ struct Fit {
   int lookahead = 0, nbuf = 0, sring = 2, nworkers = 0, nc = 1, nband = 1;
   uint32_t tag = 0;
   DevBuf<unsigned long long> dew, part;
+  float* gram_p = nullptr;              // Gram band in use: f.gram (per fit) or the handle's natural-order cache
+  // single Kuo-Mallick sweep / wgr driver
+  DevBuf<float> xx_over;                // caller's xx (KMUP takes it as an argument, :12)
+  bool skip_epilogue = false;
+  bool wgr_mode = false;
+  DevBuf<WgrState> wst;
+  WgrArgs wgr_args;
   int* h_perm = nullptr;                // pinned [kPermRing][p]
   cudaEvent_t perm_free[kPermRing] = {};
   bool perm_ev_valid[kPermRing] = {};
@@ -118,6 +125,8 @@ struct bwgr_handle {
   // tuning
   int path = BWGR_PATH_AUTO, grid = 0;
   int gram_simt = 0;
+  DevBuf<float> gram_nat;  // Gram band of the natural marker order (Gibbs / KMUP / wgr): depends on the store only
+  int gram_nat_band = 0;
   int fp8_codes = 0;  // all genotypes are codes 0..7 (and n small enough): the Gram kernel may use the exact E4M3 path
   int64_t launches = 0;
   Fit fit;
@@ -226,6 +235,7 @@ int prepare_store(bwgr_handle* h, int64_t n, int64_t p, int storage) {
   CU(cudaSetDevice(h->device));
   h->fit.reset();
   h->x2.release();
+  h->gram_nat.release(); h->gram_nat_band = 0;
   h->n = n; h->p = p;
   h->ld = (n + 127) / 128 * 128;
   h->ldb = 0;
@@ -465,7 +475,8 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
   const int64_t n = h->n, p = h->p, ld = h->ld;
   const int ns = s.nsys;
   f.model = s.model; f.nsys = ns; f.shuffled = s.shuffled; f.blocked = blocked; f.masked = s.row_mask != nullptr;
-  f.sweeps_issued = 0; f.seed = s.seed; f.gram_cached = false;
+  f.sweeps_issued = 0; f.seed = s.seed; f.gram_cached = false; f.skip_epilogue = false; f.wgr_mode = false; f.gram_p = nullptr;
+  f.xx_over.release(); f.wst.release();
   f.it_target = s.it;
 
   // ---- per-system row masks and column statistics
@@ -591,6 +602,10 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
         c.lmb = c.ve / c.vb; c.Pi0 = s.pi / (1.0f - s.pi);
         break;
       }
+      case M_KMUP: {  // state comes from the caller (KMUP :12-38) or from the wgr driver (R/wgr.R:46-59)
+        c.MSx = sum_vx; c.ve = 1; c.vb = 1; c.lmb = 1;
+        break;
+      }
       default: return fail(BWGR_ERR_ARG, "bad model %d", s.model);
     }
     c.C = -0.5f / std::sqrt(c.ve);
@@ -645,7 +660,20 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
       f.rows_per_cta = pl.R; f.nworkers = pl.W; f.grid = pl.W + 1; f.nbuf = pl.nbuf; f.sring = pl.sring; f.lookahead = pl.D; f.nband = pl.D + 1;
       f.nc = std::max(1, 16 / ns);
       f.tag = 0;
-      if (f.gram.alloc((size_t)f.nblocks * kBlk * kBlk * f.nband) != cudaSuccess ||
+      const size_t gram_n = (size_t)f.nblocks * kBlk * kBlk * f.nband;
+      if (!s.shuffled) {  // natural order: one Gram band per genotype store, kept on the handle
+        if (h->gram_nat_band != f.nband || h->gram_nat.n != gram_n) {
+          h->gram_nat_band = 0;
+          if (h->gram_nat.alloc(gram_n) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(Gram band) failed");
+        } else {
+          f.gram_cached = true;
+        }
+        f.gram_p = h->gram_nat.p;
+      } else {
+        if (f.gram.alloc(gram_n) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(Gram band) failed");
+        f.gram_p = f.gram.p;
+      }
+      if (
           f.part.alloc((size_t)8 * ns * 128 * 161) != cudaSuccess || f.dew.alloc((size_t)f.nblocks * ns * 136) != cudaSuccess)
         return fail(BWGR_ERR_CUDA, "cudaMalloc(blocked workspace) failed");
       CU(cudaMemsetAsync(f.dew.p, 0, sizeof(unsigned long long) * f.dew.n, h->stream));
@@ -656,6 +684,7 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
       f.nband = 1;
       if (f.gram.alloc((size_t)f.nblocks * kBlk * kBlk) != cudaSuccess || f.gacc.alloc((size_t)f.nblocks * kNC * ns * kBlk) != cudaSuccess || f.bar.alloc(1) != cudaSuccess)
         return fail(BWGR_ERR_CUDA, "cudaMalloc(blocked workspace) failed");
+      f.gram_p = f.gram.p;
     }
   }
   f.active = true;
@@ -687,7 +716,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
     const int sweep = f.sweeps_issued;
     const int slot = sweep % kPermRing;
     const int* d_perm = nullptr;
-    if (f.shuffled || (f.blocked && !f.gram_cached)) {
+    if (f.shuffled || (f.blocked && f.sweeps_issued == 0)) {  // natural order: the identity is uploaded once (slot 0)
       if (f.perm_ev_valid[slot]) CU(cudaEventSynchronize(f.perm_free[slot]));
       int* hp = f.h_perm + (size_t)slot * p;
       if (f.shuffled) std::shuffle(f.order.begin(), f.order.end(), std::mt19937(sweep));
@@ -700,18 +729,19 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
     if (f.blocked) {
       if (f.shuffled || !f.gram_cached) {
         cudaEvent_t pe = h->prof_begin(0);
-        if (h->gram_simt) launch_gram_simt(g, d_perm, f.nblocks, f.gram.p, 1, h->stream);
-        else launch_gram_tc(g, d_perm, f.nblocks, f.gram.p, 1, f.nband, h->fp8_codes, h->err.p, h->num_sms, h->stream);
+        if (h->gram_simt) launch_gram_simt(g, d_perm, f.nblocks, f.gram_p, 1, h->stream);
+        else launch_gram_tc(g, d_perm, f.nblocks, f.gram_p, 1, f.nband, h->fp8_codes, h->err.p, h->num_sms, h->stream);
         h->prof_end(pe);
         h->launches++;
         f.gram_cached = true;
+        if (!f.shuffled && f.gram_p == h->gram_nat.p) h->gram_nat_band = f.nband;
       }
       if (f.pipe) {
         CU(cudaMemsetAsync(f.part.p, 0, sizeof(unsigned long long) * f.part.n, h->stream));
         PipeArgs a;
         memset(&a, 0, sizeof a);
-        a.g = g; a.model = f.model; a.nsys = f.nsys; a.perm = d_perm; a.nblocks = f.nblocks; a.gram = f.gram.p; a.nband = f.nband;
-        a.e = f.e.p; a.b = f.b.p; a.d = f.d.p; a.vbv = f.vbv.p; a.xx = h->xx_f.p; a.sc = f.sc.p;
+        a.g = g; a.model = f.model; a.nsys = f.nsys; a.perm = d_perm; a.nblocks = f.nblocks; a.gram = f.gram_p; a.nband = f.nband;
+        a.e = f.e.p; a.b = f.b.p; a.d = f.d.p; a.vbv = f.vbv.p; a.xx = f.xx_over.p ? f.xx_over.p : h->xx_f.p; a.sc = f.sc.p;
         a.part = f.part.p; a.hred = f.part.p + (size_t)8 * f.nsys * 128 * 160; a.dew = f.dew.p; a.tag = ++f.tag;
         a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0;
         a.rows_per_cta = f.rows_per_cta; a.nworkers = f.nworkers; a.D = f.lookahead; a.nbuf = f.nbuf; a.sring = f.sring; a.err = h->err.p;
@@ -728,8 +758,8 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
         CU(cudaMemsetAsync(f.bar.p, 0, sizeof(unsigned int), h->stream));
         SweepArgs a;
         memset(&a, 0, sizeof a);
-        a.g = g; a.model = f.model; a.nsys = f.nsys; a.perm = d_perm; a.nblocks = f.nblocks; a.gram = f.gram.p;
-        a.e = f.e.p; a.b = f.b.p; a.d = f.d.p; a.vbv = f.vbv.p; a.xx = h->xx_f.p; a.sc = f.sc.p;
+        a.g = g; a.model = f.model; a.nsys = f.nsys; a.perm = d_perm; a.nblocks = f.nblocks; a.gram = f.gram_p;
+        a.e = f.e.p; a.b = f.b.p; a.d = f.d.p; a.vbv = f.vbv.p; a.xx = f.xx_over.p ? f.xx_over.p : h->xx_f.p; a.sc = f.sc.p;
         a.gacc = f.gacc.p; a.bar = f.bar.p; a.g_quantum = quantum; a.g_limit = limit;
         a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0;
         a.rows_per_cta = f.rows_per_cta; a.err = h->err.p;
@@ -746,7 +776,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
       SmallNArgs a;
       memset(&a, 0, sizeof a);
       a.g = g; a.model = f.model; a.nsys = f.nsys; a.perms = d_perm; a.y = f.y.p; a.e = f.e.p; a.b = f.b.p; a.d = f.d.p;
-      a.vbv = f.vbv.p; a.xx = f.masked ? f.xx_sys.p : h->xx_f.p; a.xx_per_sys = f.masked ? 1 : 0; a.mask = f.mask.p;
+      a.vbv = f.vbv.p; a.xx = f.masked ? f.xx_sys.p : (f.xx_over.p ? f.xx_over.p : h->xx_f.p); a.xx_per_sys = f.masked ? 1 : 0; a.mask = f.mask.p;
       a.sc = f.sc.p; a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0; a.err = h->err.p;
       cudaEvent_t pe = h->prof_begin(1);
       launch_small_n(a, h->smem_optin, h->stream);
@@ -754,15 +784,22 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
       h->launches++;
     }
     if (f.shuffled) { CU(cudaEventRecord(f.perm_free[slot], h->stream)); f.perm_ev_valid[slot] = true; }
-    EpilogueArgs ea;
-    memset(&ea, 0, sizeof ea);
-    ea.model = f.model; ea.nsys = f.nsys; ea.n = (int)h->n; ea.p = (int)p; ea.ld = ld; ea.e = f.e.p; ea.y = f.y.p; ea.b = f.b.p;
-    ea.d = f.d.p; ea.vbv = f.vbv.p; ea.b_prev = f.b_prev.p; ea.mask = f.mask.p; ea.sc = f.sc.p; ea.B = f.B.p; ea.D = f.D.p;
-    ea.VBv = f.VBv.p; ea.seed_lo = (uint32_t)f.seed; ea.seed_hi = (uint32_t)(f.seed >> 32); ea.chain0 = 0;
-    cudaEvent_t pe2 = h->prof_begin(2);
-    launch_epilogue(ea, h->stream);
-    h->prof_end(pe2);
-    h->launches++;
+    if (f.wgr_mode) {
+      cudaEvent_t pe2 = h->prof_begin(2);
+      launch_wgr_step(f.wgr_args, h->num_sms, h->stream);
+      h->prof_end(pe2);
+      h->launches += 2;
+    } else if (!f.skip_epilogue) {
+      EpilogueArgs ea;
+      memset(&ea, 0, sizeof ea);
+      ea.model = f.model; ea.nsys = f.nsys; ea.n = (int)h->n; ea.p = (int)p; ea.ld = ld; ea.e = f.e.p; ea.y = f.y.p; ea.b = f.b.p;
+      ea.d = f.d.p; ea.vbv = f.vbv.p; ea.b_prev = f.b_prev.p; ea.mask = f.mask.p; ea.sc = f.sc.p; ea.B = f.B.p; ea.D = f.D.p;
+      ea.VBv = f.VBv.p; ea.seed_lo = (uint32_t)f.seed; ea.seed_hi = (uint32_t)(f.seed >> 32); ea.chain0 = 0;
+      cudaEvent_t pe2 = h->prof_begin(2);
+      launch_epilogue(ea, h->stream);
+      h->prof_end(pe2);
+      h->launches++;
+    }
     f.sweeps_issued++;
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) return fail(BWGR_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(le));
@@ -948,12 +985,144 @@ int bwgr_gibbs_fit(bwgr_handle* h, const bwgr_gibbs_params* par, const double* y
   return 0;
 }
 
-int bwgr_kmup_sweep(bwgr_handle*, double*, double*, const double*, double*, const double*, double, double, uint64_t) {
-  return fail(BWGR_ERR_UNSUPPORTED, "bwgr_kmup_sweep: not built yet");
+// Common start of KMUP / wgr: a one-system M_KMUP fit whose state (b, d, e, per-marker L, Ve, pi) is set by the caller.
+static int kmup_begin(bwgr_handle* h, const double* b, const double* d, const double* xx, const double* e, const double* L,
+                      double Ve, double pi, uint64_t seed) {
+  if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
+  if (!b || !e || !L) return fail(BWGR_ERR_ARG, "null argument");
+  if (!(Ve > 0)) return fail(BWGR_ERR_ARG, "Ve must be positive");
+  const int64_t n = h->n, p = h->p, ld = h->ld;
+  FitSpec s;
+  s.model = M_KMUP; s.nsys = 1; s.shuffled = false; s.row_mask = nullptr;
+  s.df = 5; s.R2 = 0.5f; s.Pi = 0; s.alpha = 0; s.pi = (float)pi; s.it = 1; s.bi = 0; s.seed = seed;
+  int rc = fit_begin(h, s, e);  // y := e (only its mean/variance feed unused defaults)
+  if (rc) return rc;
+  Fit& f = h->fit;
+  std::vector<float> he(ld, 0.0f), hb(p), hd(p, 1.0f), hl(p);
+  float emax = 0;
+  for (int64_t i = 0; i < n; i++) { he[i] = (float)e[i]; emax = std::max(emax, std::fabs(he[i])); }
+  for (int64_t j = 0; j < p; j++) { hb[j] = (float)b[j]; hl[j] = (float)L[j]; if (d) hd[j] = (float)d[j]; }
+  SysScalars c = f.sc0[0];
+  c.mu = 0; c.ve = (float)Ve; c.pi_mix = (float)pi; c.C = -0.5f / std::sqrt((float)Ve);  // C = -0.5/sqrt(Ve) (:17, sic)
+  c.sweep = 0; c.burn = 0;
+  {
+    int ex = 0;
+    if (emax > 0) std::frexp(emax, &ex);
+    if (ex < -60) ex = -60;
+    c.e_q = std::ldexp(1.0f, ex + 3 - 30);
+    c.e_qinv = std::ldexp(1.0f, 30 - 3 - ex);
+  }
+  f.sc0[0] = c;
+  CU(cudaMemcpyAsync(f.e.p, he.data(), sizeof(float) * ld, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(f.b.p, hb.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(f.d.p, hd.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(f.vbv.p, hl.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(f.sc.p, &c, sizeof(SysScalars), cudaMemcpyHostToDevice, h->stream));
+  if (xx) {
+    std::vector<float> hx(p);
+    for (int64_t j = 0; j < p; j++) hx[j] = (float)xx[j];
+    if (f.xx_over.alloc(p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+    CU(cudaMemcpyAsync(f.xx_over.p, hx.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
 }
-int bwgr_wgr_fit(bwgr_handle*, const double*, int, int, int, int, int, double, double, double, uint64_t, double*, double*,
-                 double*, double*, double*) {
-  return fail(BWGR_ERR_UNSUPPORTED, "bwgr_wgr_fit: not built yet");
+
+// KMUP(X,b,d,xx,e,L,Ve,pi) (:12-38): one sweep, state updated in place.  X = the handle's store.
+int bwgr_kmup_sweep(bwgr_handle* h, double* b, double* d, const double* xx, double* e, const double* L, double Ve, double pi,
+                    uint64_t seed) {
+  int rc = kmup_begin(h, b, d, xx, e, L, Ve, pi, seed);
+  if (rc) return rc;
+  Fit& f = h->fit;
+  f.skip_epilogue = true;
+  rc = fit_sweeps(h, 1);
+  if (rc) return rc;
+  rc = check_err_flag(h, "kmup sweep");
+  if (rc) { f.reset(); return rc; }
+  const int64_t n = h->n, p = h->p;
+  std::vector<float> he(n), hb(p), hd(p);
+  CU(cudaMemcpyAsync(he.data(), f.e.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(hb.data(), f.b.p, sizeof(float) * p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(hd.data(), f.d.p, sizeof(float) * p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int64_t i = 0; i < n; i++) e[i] = he[i];
+  for (int64_t j = 0; j < p; j++) { b[j] = hb[j]; if (d) d[j] = hd[j]; }
+  f.reset();
+  return 0;
+}
+
+// wgr(y, X, it, bi, th, bag = 1, rp = FALSE, iv, de, pi, df, R2, eigK = NULL) (R/wgr.R:2-169) with the MCMC loop on the device.
+int bwgr_wgr_fit(bwgr_handle* h, const double* y, int it, int bi, int th, int iv, int de, double pi, double df, double R2,
+                 uint64_t seed, double* b, double* d, double* Vb, double* hat, double* scal) {
+  if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
+  if (!y) return fail(BWGR_ERR_ARG, "y is NULL");
+  if (it < 1 || bi < 1 || bi > it || th < 1) return fail(BWGR_ERR_ARG, "need 1 <= bi <= it and th >= 1");
+  if (de) iv = 1;  // R/wgr.R:10
+  const int64_t n = h->n, p = h->p;
+  // initial state (R/wgr.R:46-59): b = 0, d = 1, mu = mean(y), e = y - mu, Va = MSx, Vb = Va, Ve = 1, L = Vb/Ve (sic)
+  double mu = 0;
+  for (int64_t i = 0; i < n; i++) { if (!(y[i] == y[i])) return fail(BWGR_ERR_ARG, "y contains NaN"); mu += y[i]; }
+  mu /= (double)n;
+  double vy = 0;
+  for (int64_t i = 0; i < n; i++) vy += (y[i] - mu) * (y[i] - mu);
+  vy /= (double)(n - 1);
+  double MSx = 0, sxx = 0;
+  for (int64_t j = 0; j < p; j++) { MSx += (h->h_xx[j] - h->h_sx[j] * h->h_sx[j] / (double)n) / ((double)n - 1.0); sxx += h->h_xx[j]; }
+  if (!(MSx > 0)) return fail(BWGR_ERR_ARG, "genotypes have no variance");
+  std::vector<double> e0(n), b0(p, 0.0), d0(p, 1.0), L0(p, MSx / 1.0);
+  for (int64_t i = 0; i < n; i++) e0[i] = y[i] - mu;
+  int rc = kmup_begin(h, b0.data(), d0.data(), nullptr, e0.data(), L0.data(), 1.0, pi, seed);
+  if (rc) return rc;
+  Fit& f = h->fit;
+  {
+    SysScalars c = f.sc0[0];
+    c.mu = (float)mu;
+    CU(cudaMemcpyAsync(f.sc.p, &c, sizeof(SysScalars), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  if (f.wst.alloc(1) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  CU(cudaMemsetAsync(f.wst.p, 0, sizeof(WgrState), h->stream));
+  WgrArgs& w = f.wgr_args;
+  memset(&w, 0, sizeof w);
+  w.n = (int)n; w.p = (int)p; w.ld = h->ld; w.e = f.e.p; w.b = f.b.p; w.d = f.d.p; w.L = f.vbv.p;
+  w.B = f.B.p; w.D = f.D.p; w.VB = f.VBv.p; w.sc = f.sc.p; w.st = f.wst.p; w.iv = iv; w.de = de;
+  w.Sb = (float)(R2 * df * vy / MSx); w.Se = (float)((1 - R2) * df * vy); w.df = (float)df; w.MSx = (float)MSx;  // :58-59
+  w.it = it; w.bi = bi; w.th = th; w.seed_lo = (uint32_t)seed; w.seed_hi = (uint32_t)(seed >> 32);
+  f.wgr_mode = true;
+  rc = fit_sweeps(h, it);
+  if (rc) return rc;
+  rc = check_err_flag(h, "wgr sweep");
+  if (rc) { f.reset(); return rc; }
+  WgrState st;
+  CU(cudaMemcpyAsync(&st, f.wst.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<float> B(p), D(p), V(p);
+  CU(cudaMemcpyAsync(B.data(), f.B.p, sizeof(float) * p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(D.data(), f.D.p, sizeof(float) * p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(V.data(), f.VBv.p, sizeof(float) * p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  const double mc = (double)((it - bi) / th + 1);  // length(seq(bi, it, th)) (:41-42)
+  double mD = 0;
+  for (int64_t j = 0; j < p; j++) mD += D[j] / mc;
+  mD /= (double)p;
+  std::vector<float> Bm(p);
+  for (int64_t j = 0; j < p; j++) Bm[j] = (float)(B[j] / mc / mD);  // B = B/mc/mean(D) (:143)
+  const float B0 = (float)(st.B0 / mc);
+  DevBuf<float> bdev, mudev, hatd;
+  if (bdev.alloc(p) != cudaSuccess || mudev.alloc(1) != cudaSuccess || hatd.alloc(h->ld) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  CU(cudaMemcpyAsync(bdev.p, Bm.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(mudev.p, &B0, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  rc = fit_hat(h, bdev.p, mudev.p, hatd.p);  // HAT = B0 + gen0 %*% B (:152)
+  if (rc) return rc;
+  std::vector<float> hh(n);
+  CU(cudaMemcpyAsync(hh.data(), hatd.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (b) for (int64_t j = 0; j < p; j++) b[j] = Bm[j];
+  if (d) for (int64_t j = 0; j < p; j++) d[j] = D[j] / mc;
+  if (Vb && iv) for (int64_t j = 0; j < p; j++) Vb[j] = V[j] / mc;
+  if (hat) for (int64_t i = 0; i < n; i++) hat[i] = hh[i];
+  if (scal) { scal[0] = B0; scal[1] = st.VE / mc; scal[2] = iv ? 0.0 : st.VA / mc; scal[3] = sxx / (double)p; }
+  f.reset();
+  return 0;
 }
 int bwgr_mrr3_fit(bwgr_handle*, int, const double*, int, const double*, double*, double*, double*, double*, double*,
                   double*, double*, double*, double*, double*, int*) {

@@ -158,7 +158,88 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
   }
 }
 
+// ---- wgr(): the R-level MCMC step restated on the device (R/wgr.R:91-136, eigK = NULL, bag = 1) ----------------
+// Kernel A (one CTA): e'e, b'b, mean(e) -> Va (pi/iv dependent), Ve, intercept draw; kernel B (grid): per-marker Vb, L = Ve/Vb,
+// posterior sums, e -= mu0.  The residual the reference rebuilds each iteration (e = y - mu - X b, :124) is the one the sweep
+// maintains, so it is not recomputed.
+__global__ void __launch_bounds__(1024) wgr_scalars_kernel(WgrArgs a) {
+  __shared__ double sh[32];
+  __shared__ float sh_max[32];
+  const int tid = threadIdx.x, T = blockDim.x;
+  double se = 0, see = 0, sbb = 0;
+  float emax = 0.0f;
+  for (int i = tid; i < a.n; i += T) { const double ev = a.e[i]; se += ev; see += ev * ev; emax = fmaxf(emax, fabsf(a.e[i])); }
+  for (int j = tid; j < a.p; j += T) { const double bj = a.b[j]; sbb += bj * bj; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+  if ((tid & 31) == 0) sh_max[tid >> 5] = emax;
+  se = block_sum(se, sh); see = block_sum(see, sh); sbb = block_sum(sbb, sh);
+  if (tid == 0) {
+    emax = 0.0f;
+    for (int w = 0; w < (T >> 5); w++) emax = fmaxf(emax, sh_max[w]);
+    SysScalars s = *a.sc;
+    WgrState w = *a.st;
+    const uint32_t sw = (uint32_t)s.sweep;
+    const int i = s.sweep + 1;  // R's 1-based iteration
+    const float n = (float)a.n, p = (float)a.p;
+    w.Ve_old = s.ve;
+    if (!a.iv) w.Va = ((float)sbb + a.Sb) / rchisq_philox(a.df + p, 0xFFFFFFFEu, sw, 0u, 2u, a.seed_lo, a.seed_hi);  // :113
+    w.Ve = ((float)see + a.Se) / rchisq_philox(n + a.df, 0xFFFFFFFEu, sw, 0u, 1u, a.seed_lo, a.seed_hi);               // :121
+    uint32_t c[4] = {0xFFFFFFFEu, sw, 0u, 0u};
+    philox4x32_10(c, a.seed_lo, a.seed_hi);
+    float z, z2;
+    box_muller(c[0], c[1], z, z2);
+    w.mu0 = (float)(se / (double)n) + (w.Ve / n) * z;  // sic: rnorm(1, mean(e), Ve/n), the sd argument is Ve/n (:125)
+    s.mu += w.mu0;
+    w.post = (i >= a.bi && i <= a.it && ((i - a.bi) % a.th) == 0) ? 1 : 0;
+    if (w.post) { w.B0 += (double)s.mu; w.VE += (double)w.Ve; if (!a.iv) w.VA += (double)w.Va; w.post_count += 1; }
+    s.ve = w.Ve;
+    s.C = -0.5f / sqrtf(s.ve);
+    s.sweep += 1;
+    s.its += 1;
+    {
+      int ex = 0;
+      const float bound = emax + fabsf(w.mu0);
+      if (bound > 0.0f && bound < 3.0e38f) frexpf(bound, &ex);
+      if (ex < -60) ex = -60;
+      s.e_q = ldexpf(1.0f, ex + 3 - 30);
+      s.e_qinv = ldexpf(1.0f, 30 - 3 - ex);
+    }
+    *a.sc = s;
+    *a.st = w;
+  }
+}
+
+__global__ void __launch_bounds__(256) wgr_markers_kernel(WgrArgs a) {
+  const WgrState w = *a.st;
+  const uint32_t sw = (uint32_t)(a.sc->sweep - 1);  // the sweep the scalar kernel just closed
+  const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int j = t0; j < a.p; j += stride) {
+    const float bj = a.b[j];
+    float Vb;
+    if (a.iv) {
+      if (a.de) Vb = sqrtf(bj * bj * w.Ve_old / a.MSx);                                                         // :97, :106
+      else Vb = (a.Sb + bj * bj) / rchisq_philox(a.df + 1.0f, (uint32_t)j, sw, 0u, 3u, a.seed_lo, a.seed_hi);      // :100, :109
+    } else {
+      Vb = w.Va;
+    }
+    a.L[j] = w.Ve / Vb;                                                                                          // :122
+    if (w.post) {
+      a.B[j] += bj;
+      a.D[j] += a.d[j];
+      if (a.iv) a.VB[j] += Vb;
+    }
+  }
+  if (w.mu0 != 0.0f)
+    for (int i = t0; i < a.n; i += stride) a.e[i] -= w.mu0;
+}
+
 }  // namespace
+
+void launch_wgr_step(const WgrArgs& a, int num_sms, cudaStream_t st) {
+  wgr_scalars_kernel<<<1, 1024, 0, st>>>(a);
+  wgr_markers_kernel<<<num_sms, 256, 0, st>>>(a);
+}
 
 void launch_epilogue(const EpilogueArgs& a, cudaStream_t st) { epilogue_kernel<<<a.nsys, 1024, 0, st>>>(a); }
 

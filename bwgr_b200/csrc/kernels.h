@@ -145,4 +145,21 @@ struct EpilogueArgs {
 };
 void launch_epilogue(const EpilogueArgs& a, cudaStream_t st);
 
+// wgr() driver step (R/wgr.R:91-136), after each Kuo-Mallick sweep: variance draws, intercept, posterior sums.
+struct WgrState {      // device resident, one per fit
+  float Ve_old, Ve, Va, mu0;
+  int post;            // this iteration is saved (i %in% seq(bi, it, th))
+  int post_count;
+  double B0, VE, VA;   // posterior sums
+};
+struct WgrArgs {
+  int n, p; int64_t ld;
+  float* e; const float* b; const float* d; float* L;   // L = vbv of the sweep (per-marker lambda)
+  float* B; float* D; float* VB;                        // posterior sums [p]
+  SysScalars* sc; WgrState* st;
+  int iv, de; float Sb, Se, df, MSx; int it, bi, th;
+  uint32_t seed_lo, seed_hi;
+};
+void launch_wgr_step(const WgrArgs& a, int num_sms, cudaStream_t st);
+
 }  // namespace bwgr

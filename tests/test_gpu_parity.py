@@ -199,3 +199,47 @@ def test_gibbs_posterior_means(tpod, model, path):
     if model in ("BayesB", "BayesC"):
         da = np.mean([r["d"].mean() for r in ora]); db = np.mean([r["d"].mean() for r in gpu])
         assert abs(da - db) < 0.02
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_kmup_deterministic_limit(tpod, path):
+    """KMUP(X,b,d,xx,e,L,Ve,pi=0) with a vanishing residual variance draws with sd -> 0: the sweep is then the plain
+    ridge Gauss-Seidel step in natural order, identical in the oracle and on the device whatever the RNG."""
+    y, gen = tpod
+    X = gen.astype(np.float64)
+    p = X.shape[1]
+    xx = (X ** 2).sum(0)
+    e = y - y.mean()
+    L = np.full(p, 37.0)
+    b0 = np.linspace(-0.01, 0.01, p)
+    ref = O.kmup(X, b0, np.ones(p), xx, e, L, 1e-30, 0.0, seed=3)
+    with bw.Genotypes(gen, path=path) as g:
+        out = bw.KMUP(g, b0, np.ones(p), xx, e, L, 1e-30, 0.0, seed=9)
+    assert np.abs(out["b"] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max()
+    assert np.abs(out["e"] - ref["e"]).max() <= RTOL * np.abs(ref["e"]).max()
+    assert np.array_equal(out["d"], np.ones(p))
+
+
+@pytest.mark.parametrize("mode", ["BRR", "BayesA", "BayesB", "BayesC"])
+def test_wgr_posterior_means(tpod, mode):
+    """wgr() with the MCMC loop on the device vs the oracle's restatement of R/wgr.R (ratio form of the inclusion
+    probability on both sides): posterior means agree within Monte-Carlo error across seeds."""
+    y, gen = tpod
+    X = gen.astype(np.float64)
+    kw = {"BRR": dict(pi=0.0, iv=False), "BayesA": dict(pi=0.0, iv=True), "BayesB": dict(pi=0.9, iv=True),
+          "BayesC": dict(pi=0.9, iv=False)}[mode]
+    seeds = range(6)
+    ora = [O.wgr(y, X, it=800, bi=200, seed=50 + s, ratio_form=True, **kw) for s in seeds]
+    with bw.Genotypes(gen) as g:
+        gpu = [bw.wgr(y, g, it=800, bi=200, seed=70 + s, **kw) for s in seeds]
+    for key in ("mu", "Ve"):
+        a = np.array([r[key] for r in ora]); b = np.array([r[key] for r in gpu])
+        se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+        assert abs(a.mean() - b.mean()) <= 4 * se + 2e-2 * abs(a.mean()), (key, a.mean(), b.mean(), se)
+    A = np.mean([r["hat"] for r in ora], 0); B = np.mean([r["hat"] for r in gpu], 0)
+    # yardstick: how well two independent halves of the ORACLE's own seeds agree (half the seeds -> noisier than A vs B)
+    A1 = np.mean([r["hat"] for r in ora[:3]], 0); A2 = np.mean([r["hat"] for r in ora[3:]], 0)
+    assert np.corrcoef(A, B)[0, 1] > min(0.99, np.corrcoef(A1, A2)[0, 1] - 0.005)
+    da = np.mean([r["d"].mean() for r in ora]); db = np.mean([r["d"].mean() for r in gpu])
+    assert abs(da - db) < 0.03
+    assert np.isclose(gpu[0]["cxx"], ora[0]["cxx"])
