@@ -316,3 +316,55 @@ def wgr(y, X, it=1500, bi=500, th=1, bag=1, rp=False, iv=False, de=False, pi=0, 
     finally:
         if own:
             g.close()
+
+
+_MRR3_DEFAULTS = dict(
+    maxit=500, tol=10e-9, cores=1, TH=False, NLfactor=0.0, InnerGS=False, NoInv=False, HCS=False, XFA=False,
+    ACS=False, NumXFA=3, R2=0.5, gc0=0.5, df0=1.0, updateMu=False, weight_prior_h2=0.01, weight_prior_gc=0.01,
+    PenCor=0.0, MinCor=1.0, uncorH2below=0.0, roundGCupFrom=1.0, roundGCupTo=1.0, roundGCdownFrom=1.0,
+    roundGCdownTo=0.0, bucketGCfrom=1.0, bucketGCto=1.0, DeflateMax=0.9, DeflateBy=0.0, OneVarB=False, OneVarE=False)
+
+
+def MRR3(Y, X, f32_variant=False, verbose=False, **kw):
+    """MRR3(Y, X, ...) of R/RcppExports.R:180 (same argument names and defaults, same returned list).
+    The marker loop runs as k rotated ridge systems in the blocked sweep kernel (csrc/mrr.cu)."""
+    par = dict(_MRR3_DEFAULTS)
+    for key, v in kw.items():
+        if key not in par:
+            raise TypeError("unknown MRR3 argument %r" % key)
+        par[key] = v
+    g, own = _store(X)
+    try:
+        Y = np.asfortranarray(Y, dtype=np.float64)
+        n, k = Y.shape
+        p = g.p
+        pv = np.array([float(par[name]) for name in _MRR3_DEFAULTS], dtype=np.float64)
+        maxit = int(par["maxit"])
+        mu, h2, ve, MSx = (np.zeros(k) for _ in range(4))
+        b = np.zeros((p, k), order="F")
+        W = np.zeros((p, k), order="F")
+        hat = np.zeros((n, k), order="F")
+        GC = np.zeros((k, k), order="F")
+        vb = np.zeros((k, k), order="F")
+        cnv = np.zeros(3 * maxit)
+        its = C.c_int()
+        check(g.lib.bwgr_mrr3_fit(g.h, int(bool(f32_variant)), _ptr(Y), k, _ptr(pv), _ptr(mu), _ptr(b), _ptr(hat), _ptr(h2),
+                                  _ptr(GC), _ptr(vb), _ptr(ve), _ptr(MSx), _ptr(cnv), _ptr(W), C.byref(its)))
+        q = its.value
+        return {"mu": mu, "b": b, "hat": hat, "h2": h2, "GC": GC, "vb": vb, "ve": ve, "MSx": MSx, "cnvB": cnv[:q],
+                "cnvH2": cnv[maxit:maxit + q], "cnvV": cnv[2 * maxit:2 * maxit + q], "b_Weights": W, "Its": q}
+    finally:
+        if own:
+            g.close()
+
+
+def MRR3F(Y, X, **kw):
+    return MRR3(Y, X, f32_variant=True, **kw)
+
+
+def mrr(Y, X, **kw):  # R/mix.R:1271
+    return MRR3(Y, X, **kw)
+
+
+def mrr_float(Y, X, **kw):  # R/mix.R:1273
+    return MRR3F(Y, X, **kw)

@@ -89,7 +89,8 @@ struct Fit {
   DevBuf<unsigned long long> dew, part;
   float* gram_p = nullptr;              // Gram band in use: f.gram (per fit) or the handle's natural-order cache
   // single Kuo-Mallick sweep / wgr driver
-  DevBuf<float> xx_over;                // caller's xx (KMUP takes it as an argument, :12)
+  DevBuf<float> xx_over;                // caller's xx (KMUP takes it as an argument, :12) / centred xx (MRR3)
+  DevBuf<float> sx_dev, cshift;         // MRR3: column sums (centred columns) and the per-system mean shift of a sweep
   bool skip_epilogue = false;
   bool wgr_mode = false;
   DevBuf<WgrState> wst;
@@ -476,7 +477,7 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
   const int ns = s.nsys;
   f.model = s.model; f.nsys = ns; f.shuffled = s.shuffled; f.blocked = blocked; f.masked = s.row_mask != nullptr;
   f.sweeps_issued = 0; f.seed = s.seed; f.gram_cached = false; f.skip_epilogue = false; f.wgr_mode = false; f.gram_p = nullptr;
-  f.xx_over.release(); f.wst.release();
+  f.xx_over.release(); f.wst.release(); f.sx_dev.release(); f.cshift.release();
   f.it_target = s.it;
 
   // ---- per-system row masks and column statistics
@@ -600,6 +601,10 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
         const float MSx = sum_vx;
         c.MSx = MSx; c.Sb = df * R2 * vy / MSx / (1 - s.pi); c.Se = df * (1 - R2) * vy; c.ve = vy; c.vb = c.Sb;
         c.lmb = c.ve / c.vb; c.Pi0 = s.pi / (1.0f - s.pi);
+        break;
+      }
+      case M_MRR: {  // rotated MRR3 systems: lambda and scales are set per sweep by the driver
+        c.MSx = sum_vx; c.ve = 1; c.vb = 1; c.lmb = 1;
         break;
       }
       case M_KMUP: {  // state comes from the caller (KMUP :12-38) or from the wgr driver (R/wgr.R:46-59)
@@ -730,7 +735,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
       if (f.shuffled || !f.gram_cached) {
         cudaEvent_t pe = h->prof_begin(0);
         if (h->gram_simt) launch_gram_simt(g, d_perm, f.nblocks, f.gram_p, 1, h->stream);
-        else launch_gram_tc(g, d_perm, f.nblocks, f.gram_p, 1, f.nband, h->fp8_codes, h->err.p, h->num_sms, h->stream);
+        else launch_gram_tc(g, d_perm, f.nblocks, f.gram_p, 1, f.nband, h->fp8_codes, h->err.p, h->num_sms, f.sx_dev.p, h->stream);
         h->prof_end(pe);
         h->launches++;
         f.gram_cached = true;
@@ -741,7 +746,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
         PipeArgs a;
         memset(&a, 0, sizeof a);
         a.g = g; a.model = f.model; a.nsys = f.nsys; a.perm = d_perm; a.nblocks = f.nblocks; a.gram = f.gram_p; a.nband = f.nband;
-        a.e = f.e.p; a.b = f.b.p; a.d = f.d.p; a.vbv = f.vbv.p; a.xx = f.xx_over.p ? f.xx_over.p : h->xx_f.p; a.sc = f.sc.p;
+        a.e = f.e.p; a.b = f.b.p; a.d = f.d.p; a.vbv = f.vbv.p; a.xx = f.xx_over.p ? f.xx_over.p : h->xx_f.p; a.sx = f.sx_dev.p; a.cshift = f.cshift.p; a.sc = f.sc.p;
         a.part = f.part.p; a.hred = f.part.p + (size_t)8 * f.nsys * 128 * 160; a.dew = f.dew.p; a.tag = ++f.tag;
         a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0;
         a.rows_per_cta = f.rows_per_cta; a.nworkers = f.nworkers; a.D = f.lookahead; a.nbuf = f.nbuf; a.sring = f.sring; a.err = h->err.p;
@@ -1124,9 +1129,352 @@ int bwgr_wgr_fit(bwgr_handle* h, const double* y, int it, int bi, int th, int iv
   f.reset();
   return 0;
 }
-int bwgr_mrr3_fit(bwgr_handle*, int, const double*, int, const double*, double*, double*, double*, double*, double*,
-                  double*, double*, double*, double*, double*, int*) {
-  return fail(BWGR_ERR_UNSUPPORTED, "bwgr_mrr3_fit: not built yet");
+}  // extern "C"
+
+namespace {
+// ---- small dense symmetric helpers for the k x k part of MRR3 (column-major, double) ----------------------------------
+using Mat = std::vector<double>;
+// cyclic Jacobi: A = V diag(w) V', eigenvalues ascending (what Eigen's SelfAdjointEigenSolver returns, :639)
+void sym_eig(const Mat& Ain, int k, std::vector<double>& w, Mat& V) {
+  Mat A(Ain);
+  V.assign((size_t)k * k, 0.0);
+  for (int i = 0; i < k; i++) V[i + (size_t)i * k] = 1.0;
+  for (int sweep = 0; sweep < 64; sweep++) {
+    double off = 0;
+    for (int i = 0; i < k; i++) for (int j = 0; j < i; j++) off += A[i + (size_t)j * k] * A[i + (size_t)j * k];
+    if (off < 1e-300) break;
+    for (int pI = 0; pI < k - 1; pI++)
+      for (int q = pI + 1; q < k; q++) {
+        const double apq = A[pI + (size_t)q * k];
+        if (std::fabs(apq) < 1e-300) continue;
+        const double theta = (A[q + (size_t)q * k] - A[pI + (size_t)pI * k]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        for (int r = 0; r < k; r++) {
+          const double arp = A[r + (size_t)pI * k], arq = A[r + (size_t)q * k];
+          A[r + (size_t)pI * k] = c * arp - sn * arq; A[r + (size_t)q * k] = sn * arp + c * arq;
+        }
+        for (int r = 0; r < k; r++) {
+          const double apr = A[pI + (size_t)r * k], aqr = A[q + (size_t)r * k];
+          A[pI + (size_t)r * k] = c * apr - sn * aqr; A[q + (size_t)r * k] = sn * apr + c * aqr;
+        }
+        for (int r = 0; r < k; r++) {
+          const double vrp = V[r + (size_t)pI * k], vrq = V[r + (size_t)q * k];
+          V[r + (size_t)pI * k] = c * vrp - sn * vrq; V[r + (size_t)q * k] = sn * vrp + c * vrq;
+        }
+      }
+  }
+  std::vector<int> idx(k);
+  for (int i = 0; i < k; i++) idx[i] = i;
+  std::sort(idx.begin(), idx.end(), [&](int a, int b) { return A[a + (size_t)a * k] < A[b + (size_t)b * k]; });
+  w.resize(k);
+  Mat Vs((size_t)k * k);
+  for (int c = 0; c < k; c++) { w[c] = A[idx[c] + (size_t)idx[c] * k]; for (int r = 0; r < k; r++) Vs[r + (size_t)c * k] = V[r + (size_t)idx[c] * k]; }
+  V.swap(Vs);
+}
+bool chol_ok(const Mat& Ain, int k) {  // LLT success test (:603-607)
+  Mat A(Ain);
+  for (int j = 0; j < k; j++) {
+    double d = A[j + (size_t)j * k];
+    for (int c = 0; c < j; c++) d -= A[j + (size_t)c * k] * A[j + (size_t)c * k];
+    if (!(d > 0)) return false;
+    d = std::sqrt(d);
+    A[j + (size_t)j * k] = d;
+    for (int i = j + 1; i < k; i++) {
+      double v = A[i + (size_t)j * k];
+      for (int c = 0; c < j; c++) v -= A[i + (size_t)c * k] * A[j + (size_t)c * k];
+      A[i + (size_t)j * k] = v / d;
+    }
+  }
+  return true;
+}
+void sym_pinv(const Mat& A, int k, Mat& out) {  // completeOrthogonalDecomposition().pseudoInverse() of a symmetric matrix (:648)
+  std::vector<double> w; Mat V;
+  sym_eig(A, k, w, V);
+  double wmax = 0;
+  for (double v : w) wmax = std::max(wmax, std::fabs(v));
+  const double tol = wmax * k * 2.220446049250313e-16;
+  out.assign((size_t)k * k, 0.0);
+  for (int c = 0; c < k; c++) {
+    if (std::fabs(w[c]) <= tol) continue;
+    const double iw = 1.0 / w[c];
+    for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) out[i + (size_t)j * k] += iw * V[i + (size_t)c * k] * V[j + (size_t)c * k];
+  }
+}
+}  // namespace
+
+extern "C" {
+
+// MRR3 / MRR3F with the marker loop on the device (see mrr.cu).  Fast path = complete Y and the direct k x k solve:
+// NaN in Y, InnerGS, NLfactor != 0, TH, and MRR3F's NoInv system return BWGR_ERR_UNSUPPORTED (never a CPU fallback).
+int bwgr_mrr3_fit(bwgr_handle* h, int f32_variant, const double* Y, int k, const double* par, double* mu_out, double* b_out,
+                  double* hat_out, double* h2_out, double* GC_out, double* vb_out, double* ve_out, double* MSx_out, double* cnv_out,
+                  double* W_out, int* its_out) {
+  if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
+  if (!Y || !par) return fail(BWGR_ERR_ARG, "null argument");
+  if (k < 1 || k > 32) return fail(BWGR_ERR_UNSUPPORTED, "MRR3 on the B200 path takes 1..32 traits (k=%d)", k);
+  int q = 0;
+  const int maxit = (int)par[q++]; const double tol = par[q++]; q++; const bool TH = par[q++] != 0; const double NLfactor = par[q++];
+  const bool InnerGS = par[q++] != 0, NoInv = par[q++] != 0, HCS = par[q++] != 0, XFA = par[q++] != 0, ACS = par[q++] != 0;
+  const int NumXFA = (int)par[q++]; const double R2 = par[q++], gc0 = par[q++], df0 = par[q++]; const bool updateMu = par[q++] != 0;
+  const double wph2 = par[q++], wpgc = par[q++], PenCor = par[q++], MinCor = par[q++], uncorH2below = par[q++];
+  const double rUpFrom = par[q++], rUpTo = par[q++], rDownFrom = par[q++], rDownTo = par[q++], bkFrom = par[q++], bkTo = par[q++];
+  const double DeflateMax = par[q++], DeflateBy = par[q++]; const bool OneVarB = par[q++] != 0, OneVarE = par[q++] != 0;
+  if (TH || NLfactor != 0 || InnerGS || (f32_variant && NoInv))
+    return fail(BWGR_ERR_UNSUPPORTED, "MRR3: TH, NLfactor, InnerGS and MRR3F's NoInv system are not on the B200 path");
+  if (maxit < 1) return fail(BWGR_ERR_ARG, "maxit < 1");
+  const int64_t n = h->n, p = h->p, ld = h->ld;
+  for (int64_t i = 0; i < n * k; i++)
+    if (!(Y[i] == Y[i])) return fail(BWGR_ERR_UNSUPPORTED, "MRR3: missing phenotypes (NaN) need the per-trait masked solve, not built");
+  auto M = [k](int r, int c) { return (size_t)r + (size_t)c * k; };
+  // ---- setup (:359-432), double on the host
+  std::vector<double> mu(k), vy(k), ve(k), iVe(k), vbInit(k), veInit(k), h2(k), MSx(k), Se(k);
+  std::vector<double> yc((size_t)n * k);
+  for (int t = 0; t < k; t++) {
+    double s = 0;
+    for (int64_t i = 0; i < n; i++) s += Y[(size_t)t * n + i];
+    mu[t] = s / (double)n;
+    double ss = 0;
+    for (int64_t i = 0; i < n; i++) { const double v = Y[(size_t)t * n + i] - mu[t]; yc[(size_t)t * n + i] = v; ss += v * v; }
+    vy[t] = ss / ((double)n - 1.0);
+  }
+  std::vector<float> xxc(p), sxf(p);
+  double msx = 0;
+  for (int64_t j = 0; j < p; j++) {
+    const double c = h->h_xx[j] - h->h_sx[j] * h->h_sx[j] / (double)n;  // XX(J,t) = sum (x - mean)^2, same for every trait (:382-385)
+    xxc[j] = (float)c; sxf[j] = (float)h->h_sx[j];
+    msx += c / (double)n;                                              // XSX (:386-388): the centred column sums to zero
+  }
+  if (!(msx > 0)) return fail(BWGR_ERR_ARG, "genotypes have no variance");
+  const double TrXSX = (double)n * msx, iNp = 1.0 / ((double)n + df0 - 1.0);
+  Mat vb((size_t)k * k, 0.0), iG((size_t)k * k, 0.0), GC((size_t)k * k, 0.0), A, TildeHat((size_t)k * k), Sb;
+  for (int t = 0; t < k; t++) {
+    MSx[t] = msx; ve[t] = vy[t] * (1 - R2); iVe[t] = 1.0 / ve[t]; veInit[t] = ve[t];
+    vbInit[t] = vy[t] * R2 / msx; vb[M(t, t)] = vbInit[t]; iG[M(t, t)] = 1.0 / vbInit[t]; h2[t] = 1 - ve[t] / vy[t];
+  }
+  for (int i = 0; i < k; i++) for (int j = 0; j < i; j++) { const double v = gc0 * std::sqrt(vb[M(i, i)] * vb[M(j, j)]); vb[M(i, j)] = v; vb[M(j, i)] = v; }
+  Sb = vb;
+  for (auto& v : Sb) v *= df0;
+  for (int t = 0; t < k; t++) Se[t] = ve[t] * df0;
+  // ---- device state through the common fit machinery: k systems of the rotated ridge rule
+  FitSpec s;
+  s.model = M_MRR; s.nsys = k; s.shuffled = true; s.row_mask = nullptr;
+  s.df = 0; s.R2 = (float)R2; s.Pi = 0; s.alpha = 0; s.pi = 0; s.it = maxit; s.bi = 0; s.seed = 0;
+  const int saved_path = h->path;
+  h->path = BWGR_PATH_BLOCKED;
+  int rc = fit_begin(h, s, Y);
+  h->path = saved_path;
+  if (rc) return rc;
+  Fit& f = h->fit;
+  if (!f.pipe) { f.reset(); return fail(BWGR_ERR_UNSUPPORTED, "MRR3 needs the pipelined blocked sweep (shape does not fit)"); }
+  f.skip_epilogue = true;
+  DevBuf<float> tilde, e_alt, b_alt, b_old, Tdev, amax;
+  DevBuf<double> red, red2;
+  if (f.xx_over.alloc(p) != cudaSuccess || f.sx_dev.alloc(p) != cudaSuccess || f.cshift.alloc(32) != cudaSuccess ||
+      tilde.alloc((size_t)k * p) != cudaSuccess || e_alt.alloc((size_t)k * ld) != cudaSuccess || b_alt.alloc((size_t)k * p) != cudaSuccess ||
+      b_old.alloc((size_t)k * p) != cudaSuccess || Tdev.alloc(2 * 32 * 32) != cudaSuccess || amax.alloc(32) != cudaSuccess ||
+      red.alloc((size_t)k * k + 3 * k) != cudaSuccess || red2.alloc((size_t)k * k) != cudaSuccess)
+    return fail(BWGR_ERR_CUDA, "cudaMalloc(MRR3 workspace) failed");
+  CU(cudaMemcpyAsync(f.xx_over.p, xxc.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(f.sx_dev.p, sxf.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemsetAsync(e_alt.p, 0, sizeof(float) * k * ld, h->stream));
+  // f.y holds the raw Y, f.e = Y - mu (fit_begin): centre y in place for the e.y reductions (:536)
+  CU(cudaMemcpyAsync(f.y.p, f.e.p, sizeof(float) * k * ld, cudaMemcpyDeviceToDevice, h->stream));
+  launch_xty(h->view(), f.y.p, k, tilde.p, h->stream);  // tilde = X'y (:420)
+  h->launches++;
+  std::vector<double> cnvB, cnvH2, cnvV, hred((size_t)k * k + 3 * k);
+  std::vector<float> Tf(32 * 32), Tif(32 * 32), hmax(32);
+  std::vector<SysScalars> sc(f.sc0);
+  double Deflate = 1, inflate = 0;
+  const double logtol = std::log10(tol), bucketMean = 0.5 * (bkFrom + bkTo);
+  int numit = 0;
+  while (numit < maxit) {
+    const Mat vb0(vb); const std::vector<double> h20(h2);
+    // ---- rotation of this sweep: S^-1 iG S^-1 = U Lambda U', T = S U, T^-1 = U' S^-1
+    Mat Ms((size_t)k * k), U; std::vector<double> lam;
+    for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) Ms[M(i, j)] = iG[M(i, j)] / std::sqrt(iVe[i] * iVe[j]);
+    sym_eig(Ms, k, lam, U);
+    for (int sI = 0; sI < k; sI++) for (int t = 0; t < k; t++) {
+      Tf[sI * k + t] = (float)(std::sqrt(iVe[sI]) * U[M(sI, t)]);       // T[s][t]
+      Tif[sI * k + t] = (float)(U[M(t, sI)] / std::sqrt(iVe[t]));        // Tinv[s][t] = U[t][s] / S_t
+    }
+    CU(cudaMemcpyAsync(Tdev.p, Tf.data(), sizeof(float) * k * k, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(Tdev.p + 1024, Tif.data(), sizeof(float) * k * k, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(b_old.p, f.b.p, sizeof(float) * k * p, cudaMemcpyDeviceToDevice, h->stream));  // beta0 (:475)
+    CU(cudaMemsetAsync(amax.p, 0, sizeof(float) * 32, h->stream));
+    launch_rotate(f.e.p, e_alt.p, ld, (int)n, k, Tdev.p, nullptr, amax.p, h->num_sms, h->stream);
+    launch_rotate(f.b.p, b_alt.p, p, (int)p, k, Tdev.p, nullptr, nullptr, h->num_sms, h->stream);
+    h->launches += 2;
+    std::swap(f.e.p, e_alt.p); std::swap(f.b.p, b_alt.p);
+    CU(cudaMemcpyAsync(hmax.data(), amax.p, sizeof(float) * 32, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int t = 0; t < k; t++) {
+      SysScalars& c = sc[t];
+      c.lmb = (float)std::max(lam[t], 0.0);
+      int ex = 0;
+      if (hmax[t] > 0) std::frexp(hmax[t], &ex);
+      if (ex < -60) ex = -60;
+      c.e_q = std::ldexp(1.0f, ex + 3 - 30); c.e_qinv = std::ldexp(1.0f, 30 - 3 - ex);
+      c.done = 0; c.sweep = numit;
+    }
+    CU(cudaMemcpyAsync(f.sc.p, sc.data(), sizeof(SysScalars) * k, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(f.cshift.p, 0, sizeof(float) * 32, h->stream));
+    rc = fit_sweeps(h, 1);  // marker order shuffle(mt19937(numit)) (:483), centred Gram band, k-system sweep
+    if (rc) { std::swap(f.e.p, e_alt.p); std::swap(f.b.p, b_alt.p); return rc; }
+    // ---- back to trait space: E = (E~ + c) T^-1, b = b~ T^-1
+    launch_rotate(f.e.p, e_alt.p, ld, (int)n, k, Tdev.p + 1024, f.cshift.p, nullptr, h->num_sms, h->stream);
+    launch_rotate(f.b.p, b_alt.p, p, (int)p, k, Tdev.p + 1024, nullptr, nullptr, h->num_sms, h->stream);
+    std::swap(f.e.p, e_alt.p); std::swap(f.b.p, b_alt.p);
+    // ---- reductions of the sweep epilogue: b'tilde (:549), e.y (:536), |beta0 - b|^2 (:662), column sums of e (:652)
+    launch_pair_reduce(f.b.p, tilde.p, p, p, (int)p, k, 0, red.p, h->stream);
+    launch_pair_reduce(f.e.p, f.y.p, ld, ld, (int)n, k, 0, red2.p, h->stream);
+    launch_pair_reduce(b_old.p, f.b.p, p, p, (int)p, k, 1, red.p + (size_t)k * k, h->stream);
+    launch_pair_reduce(f.e.p, nullptr, ld, ld, (int)n, k, 2, red.p + (size_t)k * k + k, h->stream);
+    h->launches += 6;
+    std::vector<double> ey((size_t)k * k), small(2 * k);
+    CU(cudaMemcpyAsync(hred.data(), red.p, sizeof(double) * ((size_t)k * k + 2 * k), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(ey.data(), red2.p, sizeof(double) * k * k, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) TildeHat[M(i, j)] = hred[(size_t)i * k + j];
+    for (int t = 0; t < 2 * k; t++) small[t] = hred[(size_t)k * k + t];
+    rc = check_err_flag(h, "MRR3 sweep");
+    if (rc) { f.reset(); return rc; }
+    // ---- variance components (:536-648), double
+    for (int t = 0; t < k; t++) { ve[t] = (ey[(size_t)t * k + t] + Se[t]) * iNp; h2[t] = 1 - ve[t] / vy[t]; }
+    if (wph2 > 0) for (int t = 0; t < k; t++) ve[t] = ve[t] * (1 - wph2) + wph2 * veInit[t];
+    if (OneVarE) { double m = 0; for (int t = 0; t < k; t++) m += ve[t]; m /= k; for (int t = 0; t < k; t++) ve[t] = m; }
+    for (int t = 0; t < k; t++) iVe[t] = 1.0 / ve[t];
+    for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) {
+      if (i == j) vb[M(i, i)] = (TildeHat[M(i, i)] + Sb[M(i, i)]) / (TrXSX + df0);
+      else vb[M(i, j)] = (TildeHat[M(i, j)] + TildeHat[M(j, i)] + Sb[M(i, j)]) / (TrXSX + TrXSX + df0);
+    }
+    if (wph2 > 0) for (int i = 0; i < k; i++) vb[M(i, i)] = vb[M(i, i)] * (1 - wph2) + wph2 * vbInit[i];
+    if (wpgc > 0) {
+      for (int i = 0; i < k; i++) for (int j = 0; j < k; j++)
+        GC[M(i, j)] = (i != j) ? (1.0 - wpgc) * vb[M(i, j)] / std::sqrt(vb[M(i, i)] * vb[M(j, j)]) + gc0 * wpgc : 1.0;
+      for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) if (i != j) vb[M(i, j)] = GC[M(i, j)] * std::sqrt(vb[M(i, i)] * vb[M(j, j)]);
+    } else {
+      for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) GC[M(i, j)] = vb[M(i, j)] / std::sqrt(vb[M(i, i)] * vb[M(j, j)]);
+    }
+    auto top_factors = [&](double add, double scale) {  // :593-600, :612-617
+      std::vector<double> ew; Mat ev;
+      sym_eig(GC, k, ew, ev);
+      Mat UDU((size_t)k * k, 0.0);
+      for (int fI = 0; fI < NumXFA && fI < k; fI++) {
+        const int c = k - fI - 1;
+        for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) UDU[M(i, j)] += ew[c] * ev[M(i, c)] * ev[M(j, c)];
+      }
+      for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) GC[M(i, j)] = (UDU[M(i, j)] + add) * scale;
+      for (int i = 0; i < k; i++) GC[M(i, i)] = 1;
+    };
+    if (ACS) {
+      double gs = 0;
+      for (double v : GC) gs += v;
+      gs = (gs - k) / ((k * (k - 1))) / 2.0;
+      top_factors(gs, 0.5);
+    } else if (HCS) {
+      double gs = 0;
+      for (int i = 0; i < k; i++) for (int j = 0; j < i; j++) gs += GC[M(i, j)];
+      gs = gs / ((k * (k - 1)) / 2);
+      for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) GC[M(i, j)] = (i != j) ? gs : 1.0;
+    } else if (XFA) {
+      top_factors(0.0, 1.0);
+    }
+    for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) if (i != j) {  // :619-626
+      double& g = GC[M(i, j)];
+      if (MinCor < 1 && g < MinCor) g = 0;
+      if (PenCor > 0) g = std::tanh(PenCor * std::fabs(g)) * g;
+      if (rDownFrom < 1 && g < rDownFrom) g = rDownTo;
+      if (rUpFrom < 1 && g > rUpFrom) g = rUpTo;
+      if (bkFrom < 1 && g > bkFrom && g < bkTo) g = bucketMean;
+      if (uncorH2below > 0 && (h2[i] < uncorH2below || h2[j] < uncorH2below)) g = 0;
+    }
+    {  // bending (:629-644)
+      A = GC;
+      if (DeflateBy > 0) {
+        for (auto& v : A) v *= Deflate;
+        for (int i = 0; i < k; i++) A[M(i, i)] = 1;
+        if (!chol_ok(A, k) && Deflate > DeflateMax) {
+          Deflate -= DeflateBy;
+          A = GC;
+          for (auto& v : A) v *= Deflate;
+          for (int i = 0; i < k; i++) A[M(i, i)] = 1;
+        }
+      }
+      std::vector<double> ew; Mat ev;
+      sym_eig(A, k, ew, ev);
+      if (ew[0] < 0) {
+        inflate = std::fabs(ew[0] * 1.1);
+        for (int i = 0; i < k; i++) A[M(i, i)] += inflate;
+        for (auto& v : A) v /= (1.0 + inflate);
+        GC = A;
+      }
+    }
+    if (OneVarB) {
+      double tmp = 0;
+      for (int i = 0; i < k; i++) tmp += TildeHat[M(i, i)];
+      tmp /= k;
+      for (size_t i = 0; i < vb.size(); i++) vb[i] = GC[i] * tmp;
+    } else {
+      const Mat dv(vb);
+      for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) vb[M(i, j)] = GC[M(i, j)] * std::sqrt(dv[M(i, i)] * dv[M(j, j)]);
+    }
+    sym_pinv(vb, k, iG);
+    if (updateMu) {  // :651-655 (complete Y: Z = 1)
+      std::vector<float> sh(k);
+      for (int t = 0; t < k; t++) { const double m = small[k + t] / ((double)n - 1.0); mu[t] += m; sh[t] = (float)(-m); }
+      // e -= m: a rotation by the identity with a shift
+      std::vector<float> I((size_t)k * k, 0.0f);
+      for (int t = 0; t < k; t++) I[(size_t)t * k + t] = 1.0f;
+      CU(cudaMemcpyAsync(Tdev.p, I.data(), sizeof(float) * k * k, cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemcpyAsync(f.cshift.p, sh.data(), sizeof(float) * k, cudaMemcpyHostToDevice, h->stream));
+      launch_rotate(f.e.p, e_alt.p, ld, (int)n, k, Tdev.p, f.cshift.p, nullptr, h->num_sms, h->stream);
+      std::swap(f.e.p, e_alt.p);
+      CU(cudaStreamSynchronize(h->stream));
+    }
+    double mx = -1e300;
+    for (int t = 0; t < k; t++) mx = std::max(mx, small[t]);
+    const double cnv = std::log10(mx);
+    cnvB.push_back(cnv);
+    if (cnv != cnv) break;  // :663
+    { double sH = 0; for (int t = 0; t < k; t++) sH += (h20[t] - h2[t]) * (h20[t] - h2[t]); cnvH2.push_back(std::log10(sH)); }
+    { double sV = 0; for (size_t i = 0; i < vb.size(); i++) sV += (vb0[i] - vb[i]) * (vb0[i] - vb[i]); cnvV.push_back(std::log10(sV)); }
+    ++numit;
+    if (cnv < logtol) break;
+  }
+  // ---- outputs (:676-700): hat = X_c b + mu = X b + (mu - sum_j mean_j b_j)
+  std::vector<float> hb((size_t)k * p), hh(n);
+  CU(cudaMemcpyAsync(hb.data(), f.b.p, sizeof(float) * k * p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  DevBuf<float> mud, hatd;
+  if (mud.alloc(1) != cudaSuccess || hatd.alloc(ld) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  for (int t = 0; t < k; t++) {
+    double shift = 0;
+    for (int64_t j = 0; j < p; j++) shift += (h->h_sx[j] / (double)n) * (double)hb[(size_t)t * p + j];
+    const float m0 = (float)(mu[t] - shift);
+    CU(cudaMemcpyAsync(mud.p, &m0, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    rc = fit_hat(h, f.b.p + (size_t)t * p, mud.p, hatd.p);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(hh.data(), hatd.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (hat_out) for (int64_t i = 0; i < n; i++) hat_out[(size_t)t * n + i] = hh[i];
+  }
+  for (int t = 0; t < k; t++) {
+    if (mu_out) mu_out[t] = mu[t];
+    if (h2_out) h2_out[t] = h2[t];
+    if (ve_out) ve_out[t] = ve[t];
+    if (MSx_out) MSx_out[t] = MSx[t];
+  }
+  if (b_out) for (size_t i = 0; i < hb.size(); i++) b_out[i] = hb[i];
+  if (W_out) for (size_t i = 0; i < (size_t)k * p; i++) W_out[i] = 1.0;
+  if (GC_out) for (int i = 0; i < k * k; i++) GC_out[i] = GC[i];
+  if (vb_out) for (int i = 0; i < k * k; i++) vb_out[i] = vb[i];
+  if (cnv_out)
+    for (int i = 0; i < numit; i++) { cnv_out[i] = cnvB[i]; cnv_out[maxit + i] = cnvH2[i]; cnv_out[2 * maxit + i] = cnvV[i]; }
+  if (its_out) *its_out = numit;
+  // the swapped buffers go back to their owners before the fit is released
+  f.reset();
+  return 0;
 }
 
 int bwgr_profile(bwgr_handle* h, int enable) {
@@ -1156,7 +1504,7 @@ int bwgr_debug_gram(bwgr_handle* h, const int32_t* perm, int block, int32_t* gra
   if (dperm.alloc(p) != cudaSuccess || dg.alloc((size_t)nblocks * kBlk * kBlk) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
   CU(cudaMemcpyAsync(dperm.p, perm, sizeof(int) * p, cudaMemcpyHostToDevice, h->stream));
   if (h->gram_simt) launch_gram_simt(h->view(), dperm.p, nblocks, dg.p, 0, h->stream);
-  else launch_gram_tc(h->view(), dperm.p, nblocks, dg.p, 0, 1, h->fp8_codes, h->err.p, h->num_sms, h->stream);
+  else launch_gram_tc(h->view(), dperm.p, nblocks, dg.p, 0, 1, h->fp8_codes, h->err.p, h->num_sms, nullptr, h->stream);
   h->launches++;
   CU(cudaMemcpyAsync(gram_out, dg.p, sizeof(int32_t) * dg.n, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));

@@ -110,11 +110,13 @@ template <int NBAND>
 struct GramSmem {
   uint64_t full[GramCfg<NBAND>::kStages], empty[GramCfg<NBAND>::kStages], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
+  float sxc[128];  // column sums of this block's markers (centred Gram)
 };
 
 template <int NBAND, bool FP8>
 __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* __restrict__ perm, int nblocks,
-                                                         int32_t* __restrict__ gram, int out_f32, int* err) {
+                                                         int32_t* __restrict__ gram, int out_f32, int* err,
+                                                         const float* __restrict__ sx, float inv_n) {
   constexpr int kStages = GramCfg<NBAND>::kStages;
   constexpr int kLag = GramCfg<NBAND>::kLag;  // cp.async groups kept in flight per producer thread
   constexpr int kSub = GramCfg<NBAND>::kSub;
@@ -248,6 +250,16 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
       ok = mbar_wait(&S->tmem_full[as], aphase, err);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       int32_t* out = gram + ((size_t)blk * 128 + row) * (NBAND * 128);
+      // centred Gram (MRR3 centres every column, RcppEigen20230423.cpp:378-379): x_ci'x_ck = x_i'x_k - sx_i sx_k / n
+      float sxr0 = 0.0f, sxr1 = 0.0f;
+      if (sx) {
+        const int pos0 = blk * 128 + row, pos1 = (blk - 1) * 128 + row;
+        sxr0 = pos0 < g.p ? sx[perm[pos0]] : 0.0f;
+        sxr1 = (pos1 >= 0 && pos1 < g.p) ? sx[perm[pos1]] : 0.0f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous block's reads of sxc are done
+        S->sxc[row] = sxr0;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
 #pragma unroll
       for (int c = 0; c < 4 * NBAND; c++) {
         uint32_t v[32];
@@ -272,6 +284,11 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
         } else if (out_f32) {
 #pragma unroll
           for (int q = 0; q < 32; q++) v[q] = __float_as_uint(__int2float_rn((int)v[q]));
+        }
+        if (sx && out_f32) {
+          const float sr = (c < 4 ? sxr0 : sxr1) * inv_n;
+#pragma unroll
+          for (int q = 0; q < 32; q++) v[q] = __float_as_uint(fmaf(-sr, S->sxc[(c & 3) * 32 + q], __uint_as_float(v[q])));
         }
         if (ok) {
 #pragma unroll
@@ -314,21 +331,22 @@ __global__ void __launch_bounds__(256) gram_simt_kernel(GenoView g, const int* _
 
 template <int NBAND, bool FP8>
 static void launch_gram_band(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, int* err, int num_sms,
-                             cudaStream_t st) {
+                             const float* sx, cudaStream_t st) {
   const size_t smem = (size_t)GramCfg<NBAND>::kStages * GramCfg<NBAND>::kSub * NBAND * kTileBytes + sizeof(GramSmem<NBAND>) + 1024;
   cudaFuncSetAttribute(gram_tc_kernel<NBAND, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = nblocks < num_sms ? nblocks : num_sms;
-  gram_tc_kernel<NBAND, FP8><<<grid, 288, smem, st>>>(g, perm, nblocks, static_cast<int32_t*>(gram), out_f32, err);
+  gram_tc_kernel<NBAND, FP8><<<grid, 288, smem, st>>>(g, perm, nblocks, static_cast<int32_t*>(gram), out_f32, err, sx, 1.0f / (float)g.n);
 }
 // fp8_codes: every genotype is a code in 0..7 and max_j xx_j < 2^24 (the caller checked) -> the exact E4M3 path
+// sx != nullptr: centred Gram (float output only), sx[j] = column sum of marker j
 void launch_gram_tc(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, int nband, int fp8_codes,
-                    int* err, int num_sms, cudaStream_t st) {
+                    int* err, int num_sms, const float* sx, cudaStream_t st) {
   if (fp8_codes) {
-    if (nband == 2) launch_gram_band<2, true>(g, perm, nblocks, gram, out_f32, err, num_sms, st);
-    else launch_gram_band<1, true>(g, perm, nblocks, gram, out_f32, err, num_sms, st);
+    if (nband == 2) launch_gram_band<2, true>(g, perm, nblocks, gram, out_f32, err, num_sms, sx, st);
+    else launch_gram_band<1, true>(g, perm, nblocks, gram, out_f32, err, num_sms, sx, st);
   } else {
-    if (nband == 2) launch_gram_band<2, false>(g, perm, nblocks, gram, out_f32, err, num_sms, st);
-    else launch_gram_band<1, false>(g, perm, nblocks, gram, out_f32, err, num_sms, st);
+    if (nband == 2) launch_gram_band<2, false>(g, perm, nblocks, gram, out_f32, err, num_sms, sx, st);
+    else launch_gram_band<1, false>(g, perm, nblocks, gram, out_f32, err, num_sms, sx, st);
   }
 }
 void launch_gram_simt(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, cudaStream_t st) {

@@ -70,8 +70,9 @@ constexpr int kNC = 8;     // copies of every block accumulator: spreads the L2 
 // nband = 2: row r of block b holds [x_{b,r}'X_b | x_{b-1,r}'X_b] (256 entries): the cross block (stored transposed) feeds
 // the one-block look-ahead of the pipelined sweep.
 // fp8_codes != 0: all genotypes are codes 0..7 and n*49 < 2^24 -> kind::f8f6f4 on the same bytes (exact, see gram_tc.cu).
+// sx != nullptr (float output): the Gram of the CENTRED columns, x_i'x_k - sx_i sx_k / n (MRR3).
 void launch_gram_tc(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, int nband, int fp8_codes,
-                    int* err, int num_sms, cudaStream_t st);
+                    int* err, int num_sms, const float* sx, cudaStream_t st);
 // SIMT cross-check of the same quantity (debug / tests only; selected with BWGR_GRAM=simt).
 void launch_gram_simt(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, cudaStream_t st);
 
@@ -113,6 +114,9 @@ struct PipeArgs {
   float* e;              // [nsys][ld]
   float* b; float* d; float* vbv;  // [nsys][p]
   const float* xx;       // [p]
+  const float* sx;       // [p] column sums, or nullptr.  Non-null = the columns are centred (MRR3): the Gram band is the
+                         // centred one and g gets the running mean-shift term c * sx_j (the workers stay uncentred)
+  float* cshift;         // [nsys] out: the mean shift c accumulated over the sweep (e_true = e_stored + c)
   SysScalars* sc;        // [nsys]
   unsigned long long* part;  // [8][nsys][128][160] per-worker integer partials of h: (value << 16) | block tag; zeroed before launch
   unsigned long long* hred;  // [8][nsys][128] reduced h, same word format; zeroed before launch
@@ -161,5 +165,15 @@ struct WgrArgs {
   uint32_t seed_lo, seed_hi;
 };
 void launch_wgr_step(const WgrArgs& a, int num_sms, cudaStream_t st);
+
+// ---- multivariate ridge helpers (mrr.cu) ---------------------------------------------------------------------------
+// tilde[t][j] = x_j' Y[t]   (Y: [k][ld] float, out: [k][p])
+void launch_xty(const GenoView& g, const float* Y, int k, float* out, cudaStream_t st);
+// out[t][i] = sum_s (in[s][i] + shift[s]) * T[s*k + t], matrices [k][ld]; amax[t] (zeroed by the caller) = max_i |out[t][i]|
+void launch_rotate(const float* in, float* out, int64_t ld, int len, int k, const float* T, const float* shift, float* amax,
+                   int num_sms, cudaStream_t st);
+// mode 0: out[t1*k+t2] = A[t1].B[t2]; mode 1: out[t] = |A[t]-B[t]|^2; mode 2: out[t] = sum A[t]   (double)
+void launch_pair_reduce(const float* A, const float* B, int64_t lda, int64_t ldb, int len, int k, int mode, double* out,
+                        cudaStream_t st);
 
 }  // namespace bwgr

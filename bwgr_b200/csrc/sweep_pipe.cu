@@ -149,7 +149,7 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long
 
 // per (system, marker) inputs of the solve; per marker: xx and the marker id
 struct MarkerSys { float b0, vbj, a, c; };
-struct MarkerCol { float xx; int j; };
+struct MarkerCol { float xx, sx; int j, pad; };
 
 // index of the 32x32 tile (hi, lo), lo <= hi, in the packed triangle
 __device__ __forceinline__ int tri(int hi, int lo) { return hi * (hi + 1) / 2 + lo; }
@@ -175,7 +175,7 @@ __host__ __device__ inline WLayout worker_layout(int R, int ns, int nbuf) {
   L.total = o;
   return L;
 }
-struct SLayout { size_t gs, mt, ms, mc, drw, tc, dh, prm, rb, total; };
+struct SLayout { size_t gs, mt, ms, mc, drw, tc, dh, prm, rb, cs, total; };
 // sring = blocks of solve inputs in flight in the solver CTA (2 or 3)
 __host__ __device__ inline SLayout solver_layout(int ns, bool gibbs, bool use_inv, int sring) {
   SLayout L;
@@ -189,6 +189,7 @@ __host__ __device__ inline SLayout solver_layout(int ns, bool gibbs, bool use_in
   L.dh = o; o += (size_t)ns * 128 * 4;                                   // dE of the block being solved
   L.prm = o; o += (size_t)2 * 128 * 4;  // unused (kept for alignment)
   L.rb = o; o += (size_t)kSolveWarps * 32 * 4;
+  L.cs = o; o += (size_t)32 * 2 * 4;  // running mean shift per system (centred columns): {current, before the last block}
   L.total = o;
   return L;
 }
@@ -516,6 +517,10 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
   float* tcor = reinterpret_cast<float*>(base + L.tc);
   float* dehist = reinterpret_cast<float*>(base + L.dh);
   float* rb = reinterpret_cast<float*>(base + L.rb);
+  float* cs = reinterpret_cast<float*>(base + L.cs);
+  const bool centred = a.sx != nullptr;
+  const float inv_n = 1.0f / (float)a.g.n;
+  if (tid < 64) cs[tid] = 0.0f;
   const int gstride = a.nband * 128;  // floats per Gram row in HBM
   const int nsw = ns < kSolveWarps ? ns : kSolveWarps;
   __syncthreads();
@@ -601,6 +606,11 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
             mbar_wait(&S.corr_ready[s], (uint32_t)(b - 1) & 1u, dead, a.err);
 #pragma unroll
             for (int t = 0; t < 4; t++) g[t] -= tcor[s * 128 + 32 * t + lane];
+          }
+          if (centred) {  // x_c'e_true = x'e_stored + c * sx with c as of the residual h_b was taken from
+            const float cuse = cs[2 * s + ((D > 0 && b > 0) ? 1 : 0)];
+#pragma unroll
+            for (int t = 0; t < 4; t++) g[t] = fmaf(cuse, mc[32 * t + lane].sx, g[t]);
           }
           if (s == 0) SSTAMP(b, 9);
           float nb[4] = {0.f, 0.f, 0.f, 0.f}, nd[4] = {1.f, 1.f, 1.f, 1.f}, nv[4] = {1.f, 1.f, 1.f, 1.f};
@@ -705,6 +715,15 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
               }
             }
           }
+          if (centred) {  // c += sum_k mean_k dE_k (this block's contribution to the mean of the fitted values)
+            float sm = 0.0f;
+#pragma unroll
+            for (int t = 0; t < 4; t++) sm = fmaf(mc[32 * t + lane].sx, de[t], sm);
+            sm = warp_sum(sm) * inv_n;
+            __syncwarp();
+            if (lane == 0) { const float cc = cs[2 * s]; cs[2 * s + 1] = cc; cs[2 * s] = cc + sm; }
+            __syncwarp();
+          }
           if (s == 0) SSTAMP(b, 10);
           // quantise dE to 31-bit fixed point relative to the block maximum and publish it
           float mx = fmaxf(fmaxf(fabsf(de[0]), fabsf(de[1])), fmaxf(fabsf(de[2]), fabsf(de[3])));
@@ -750,6 +769,8 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.solve_done[slot]);
       }
+      if (centred && a.cshift && lane == 0)
+        for (int s = warp; s < ns; s += kSolveWarps) a.cshift[s] = cs[2 * s];
     }
   } else if (warp < kPreWarp0) {
     // -------------------------------------------------------------------- cross-Gram correction (D = 1)
@@ -807,7 +828,7 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
     constexpr int kPipeSys = 2;  // systems whose scalars are register-pipelined (more systems: loaded in place)
     auto perm_at = [&](int blk) { const int pos = blk * 128 + ht; return (blk < nblocks && pos < p) ? a.perm[pos] : -1; };
     int j_cur = perm_at(0), j_nxt = perm_at(1);
-    float xx_cur = j_cur >= 0 ? a.xx[j_cur] : 1.0f, b_cur[kPipeSys], v_cur[kPipeSys];
+    float xx_cur = j_cur >= 0 ? a.xx[j_cur] : 1.0f, sx_cur = (j_cur >= 0 && a.sx) ? a.sx[j_cur] : 0.0f, b_cur[kPipeSys], v_cur[kPipeSys];
 #pragma unroll
     for (int s = 0; s < kPipeSys; s++) {
       b_cur[s] = (s < ns && j_cur >= 0) ? a.b[(size_t)s * p + j_cur] : 0.0f;
@@ -836,8 +857,8 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
       PSTAMP(1);
       // issue the gathers of the following blocks now; they are consumed in the next iteration
       const int j_nn = perm_at(nb + 2);
-      float xx_nxt = 1.0f, b_nxt[kPipeSys], v_nxt[kPipeSys];
-      if (j_nxt >= 0) xx_nxt = a.xx[j_nxt];
+      float xx_nxt = 1.0f, sx_nxt = 0.0f, b_nxt[kPipeSys], v_nxt[kPipeSys];
+      if (j_nxt >= 0) { xx_nxt = a.xx[j_nxt]; if (a.sx) sx_nxt = a.sx[j_nxt]; }
 #pragma unroll
       for (int s = 0; s < kPipeSys; s++) {
         b_nxt[s] = (s < ns && j_nxt >= 0) ? a.b[(size_t)s * p + j_nxt] : 0.0f;
@@ -846,7 +867,7 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
       {
         const int j = j_cur;
         MarkerCol mcv;
-        mcv.xx = xx_cur; mcv.j = j;
+        mcv.xx = xx_cur; mcv.sx = sx_cur; mcv.j = j; mcv.pad = 0;
         mcol[slot * 128 + ht] = mcv;
         for (int s = 0; s < ns; s++) {
           MarkerSys in = {0.0f, 1.0f, 0.0f, 0.0f};
@@ -875,7 +896,7 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
       if (use_inv) mbar_arrive(&S.raw_ready[slot]);
       else mbar_arrive(&S.in_ready[slot]);
       PSTAMP(7);
-      j_cur = j_nxt; j_nxt = j_nn; xx_cur = xx_nxt;
+      j_cur = j_nxt; j_nxt = j_nn; xx_cur = xx_nxt; sx_cur = sx_nxt;
 #pragma unroll
       for (int s = 0; s < kPipeSys; s++) { b_cur[s] = b_nxt[s]; v_cur[s] = v_nxt[s]; }
     }

@@ -243,3 +243,52 @@ def test_wgr_posterior_means(tpod, mode):
     da = np.mean([r["d"].mean() for r in ora]); db = np.mean([r["d"].mean() for r in gpu])
     assert abs(da - db) < 0.03
     assert np.isclose(gpu[0]["cxx"], ora[0]["cxx"])
+
+
+def _close_mrr(out, ref, rtol):
+    sb = np.abs(ref["b"]).max()
+    assert np.abs(out["b"] - ref["b"]).max() <= rtol * sb, ("b", np.abs(out["b"] - ref["b"]).max() / sb)
+    assert np.abs(out["hat"] - ref["hat"]).max() <= rtol * np.abs(ref["hat"]).max(), "hat"
+    for key in ("mu", "h2", "ve", "MSx"):
+        assert np.abs(out[key] - ref[key]).max() <= rtol * np.abs(ref[key]).max(), key
+    assert np.abs(out["GC"] - ref["GC"]).max() <= 10 * rtol, "GC"
+    assert np.abs(out["vb"] - ref["vb"]).max() <= 10 * rtol * np.abs(ref["vb"]).max(), "vb"
+
+
+def test_mrr3_fixed_sweeps_matches_oracle(tpod):
+    """MRR3 (k = 4 traits on tpod, complete Y): after a fixed number of sweeps the rotated-ridge device path equals the
+    oracle's per-marker k x k LLT solve (float32 state on the device vs the float64 / float32 reference twins)."""
+    _, gen = tpod
+    Y = np.load(os.path.join(GOLDEN, "tpod_mrr3.npz"))["Y"]
+    X = gen.astype(np.float64)
+    for its in (1, 3, 12):
+        ref = O.mrr3(Y, X, maxit=its)
+        with bw.Genotypes(gen) as g:
+            out = bw.MRR3(Y, g, maxit=its)
+        assert out["Its"] == ref["Its"] == its
+        _close_mrr(out, ref, 2e-4)
+        np.testing.assert_allclose(out["cnvB"], ref["cnvB"], atol=2e-3)
+
+
+def test_mrr3_converged_and_options(tpod):
+    _, gen = tpod
+    Y = np.load(os.path.join(GOLDEN, "tpod_mrr3.npz"))["Y"]
+    X = gen.astype(np.float64)
+    with bw.Genotypes(gen) as g:
+        ref = O.mrr3(Y, X, tol=1e-6)
+        out = bw.MRR3(Y, g, tol=1e-6)
+        assert abs(out["Its"] - ref["Its"]) <= 2
+        _close_mrr(out, ref, 1e-3)
+        reff = O.mrr3(Y, X, f32_variant=True, maxit=10)
+        outf = bw.MRR3F(Y, g, maxit=10)
+        _close_mrr(outf, reff, 1e-3)
+        for kw in (dict(HCS=True), dict(XFA=True, NumXFA=2), dict(updateMu=True), dict(OneVarB=True, OneVarE=True)):
+            r = O.mrr3(Y, X, maxit=8, **kw)
+            o = bw.MRR3(Y, g, maxit=8, **kw)
+            _close_mrr(o, r, 1e-3)
+        Yn = Y.copy(); Yn[3, 1] = np.nan
+        with pytest.raises(bw.BwgrError) as ei:
+            bw.MRR3(Yn, g)
+        assert ei.value.code == -5
+        with pytest.raises(bw.BwgrError):
+            bw.MRR3(Y, g, InnerGS=True)
