@@ -630,8 +630,13 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
     if (model_has_vbj(s.model)) hvb.resize((size_t)ns * p), std::fill(hvb.begin() + (size_t)t * p, hvb.begin() + (size_t)(t + 1) * p, vbv_init);
   }
 
-  // ---- device state
+  // ---- device state (buffers a previous fit on this handle left behind must not leak into this one)
   const bool gibbs = model_is_gibbs(s.model);
+  if (!model_has_d(s.model)) f.d.release();
+  if (!model_has_vbj(s.model)) f.vbv.release();
+  if (s.model != M_EMEN) f.b_prev.release();
+  if (!gibbs) { f.B.release(); f.D.release(); f.VBv.release(); }
+  if (!f.masked) { f.mask.release(); f.xx_sys.release(); }
   if (f.y.alloc((size_t)ns * ld) != cudaSuccess || f.e.alloc((size_t)ns * ld) != cudaSuccess ||
       f.b.alloc((size_t)ns * p) != cudaSuccess || f.sc.alloc(ns) != cudaSuccess || f.perm.alloc((size_t)kPermRing * p) != cudaSuccess)
     return fail(BWGR_ERR_CUDA, "cudaMalloc(fit state) failed");
