@@ -128,6 +128,8 @@ struct bwgr_handle {
   int gram_simt = 0;
   DevBuf<float> gram_nat;  // Gram band of the natural marker order (Gibbs / KMUP / wgr): depends on the store only
   int gram_nat_band = 0;
+  alignas(64) unsigned char tmap[128];  // CUtensorMap of the int8 store (TMA tile::gather4)
+  bool tmap_ok = false;
   int fp8_codes = 0;  // all genotypes are codes 0..7 (and n small enough): the Gram kernel may use the exact E4M3 path
   int64_t launches = 0;
   Fit fit;
@@ -199,6 +201,12 @@ int finish_store(bwgr_handle* h, int storage) {
   for (int64_t j = 0; j < h->p; j++) xf[j] = (float)xx[j];
   CU(cudaMemcpyAsync(h->xx_f.p, xf.data(), sizeof(float) * h->p, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  {
+    // TMA tile::gather4 for the Gram tiles is built and bit-exact, but at 128 B per column per visit it is 2x SLOWER than
+    // the cp.async gather (2.43 vs 1.24 ms at 50k x 50k, band 2): opt-in only (BWGR_TMA=1), see profiles/r1_v5_summary.md
+    const char* te = getenv("BWGR_TMA");
+    h->tmap_ok = te && !strcmp(te, "1") && make_geno_tensor_map(h->x8, h->ld, h->p, h->tmap);
+  }
   {  // codes 0..7 everywhere?  (one more streaming pass at load time)
     h->fp8_codes = 0;
     const char* ge = getenv("BWGR_GRAM");
@@ -225,6 +233,7 @@ int finish_store(bwgr_handle* h, int storage) {
     h->storage = BWGR_STORE_2BIT;
     h->x8_own.release();  // the 2-bit store is the only copy kept in HBM
     h->x8 = nullptr;
+    h->tmap_ok = false;
   }
   return 0;
 }
@@ -740,7 +749,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
       if (f.shuffled || !f.gram_cached) {
         cudaEvent_t pe = h->prof_begin(0);
         if (h->gram_simt) launch_gram_simt(g, d_perm, f.nblocks, f.gram_p, 1, h->stream);
-        else launch_gram_tc(g, d_perm, f.nblocks, f.gram_p, 1, f.nband, h->fp8_codes, h->err.p, h->num_sms, f.sx_dev.p, h->stream);
+        else launch_gram_tc(g, d_perm, f.nblocks, f.gram_p, 1, f.nband, h->fp8_codes, h->err.p, h->num_sms, f.sx_dev.p, h->tmap_ok ? h->tmap : nullptr, h->stream);
         h->prof_end(pe);
         h->launches++;
         f.gram_cached = true;
@@ -1509,7 +1518,7 @@ int bwgr_debug_gram(bwgr_handle* h, const int32_t* perm, int block, int32_t* gra
   if (dperm.alloc(p) != cudaSuccess || dg.alloc((size_t)nblocks * kBlk * kBlk) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
   CU(cudaMemcpyAsync(dperm.p, perm, sizeof(int) * p, cudaMemcpyHostToDevice, h->stream));
   if (h->gram_simt) launch_gram_simt(h->view(), dperm.p, nblocks, dg.p, 0, h->stream);
-  else launch_gram_tc(h->view(), dperm.p, nblocks, dg.p, 0, 1, h->fp8_codes, h->err.p, h->num_sms, nullptr, h->stream);
+  else launch_gram_tc(h->view(), dperm.p, nblocks, dg.p, 0, 1, h->fp8_codes, h->err.p, h->num_sms, nullptr, h->tmap_ok ? h->tmap : nullptr, h->stream);
   h->launches++;
   CU(cudaMemcpyAsync(gram_out, dg.p, sizeof(int32_t) * dg.n, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));

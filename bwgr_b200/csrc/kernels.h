@@ -71,8 +71,10 @@ constexpr int kNC = 8;     // copies of every block accumulator: spreads the L2 
 // the one-block look-ahead of the pipelined sweep.
 // fp8_codes != 0: all genotypes are codes 0..7 and n*49 < 2^24 -> kind::f8f6f4 on the same bytes (exact, see gram_tc.cu).
 // sx != nullptr (float output): the Gram of the CENTRED columns, x_i'x_k - sx_i sx_k / n (MRR3).
+// tmap != nullptr: the 128-byte CUtensorMap of make_geno_tensor_map -> the tiles are gathered with TMA tile::gather4.
 void launch_gram_tc(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, int nband, int fp8_codes,
-                    int* err, int num_sms, const float* sx, cudaStream_t st);
+                    int* err, int num_sms, const float* sx, const void* tmap, cudaStream_t st);
+bool make_geno_tensor_map(const int8_t* x8, int64_t ld, int64_t p, void* tmap_out);
 // SIMT cross-check of the same quantity (debug / tests only; selected with BWGR_GRAM=simt).
 void launch_gram_simt(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, cudaStream_t st);
 
