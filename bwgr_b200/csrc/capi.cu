@@ -117,6 +117,7 @@ struct bwgr_handle {
   DevBuf<int8_t> x8_own;
   const int8_t* x8 = nullptr;
   DevBuf<uint8_t> x2;
+  DevBuf<uint8_t> x2g;  // packed 2-bit shadow of an int8 store with codes 0..2: what the Gram kernel gathers (4x fewer bytes)
   int64_t n = 0, p = 0, ld = 0, ldb = 0;
   int storage = BWGR_STORE_I8;
   DevBuf<long long> xx_i, sx_i;
@@ -170,6 +171,13 @@ struct bwgr_handle {
 
 namespace {
 
+// view handed to the Gram kernel: the int8 store plus, when it exists, the packed shadow copy
+GenoView gram_view(const bwgr_handle* h) {
+  GenoView g = h->view();
+  if (h->x2g.p) { g.x2 = h->x2g.p; g.ldb = h->ld / 4; }
+  return g;
+}
+
 int check_err_flag(bwgr_handle* h, const char* where) {
   int flag = 0;
   CU(cudaMemcpyAsync(&flag, h->err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -222,6 +230,18 @@ int finish_store(bwgr_handle* h, int storage) {
       h->fp8_codes = flag ? 0 : 1;
     }
   }
+  h->x2g.release();
+  if (h->fp8_codes && storage == BWGR_STORE_I8) {  // Gram shadow copy (only when every code is 0..2)
+    const char* pe = getenv("BWGR_GRAM_PACKED");
+    if (!(pe && !strcmp(pe, "0")) && h->x2g.alloc((size_t)(h->ld / 4) * h->p) == cudaSuccess) {
+      launch_pack_2bit(h->x8, h->ld, (int)h->n, (int)h->p, h->x2g.p, h->ld / 4, h->err.p, h->stream);
+      h->launches++;
+      int flag = 0;
+      CU(cudaMemcpyAsync(&flag, h->err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      if (flag) { CU(cudaMemsetAsync(h->err.p, 0, sizeof(int), h->stream)); h->x2g.release(); }  // a code 3..7: keep the int8 gather
+    }
+  }
   h->storage = BWGR_STORE_I8;
   if (storage == BWGR_STORE_2BIT) {
     h->ldb = h->ld / 4;
@@ -246,6 +266,7 @@ int prepare_store(bwgr_handle* h, int64_t n, int64_t p, int storage) {
   h->fit.reset();
   h->x2.release();
   h->gram_nat.release(); h->gram_nat_band = 0;
+  h->x2g.release();
   h->n = n; h->p = p;
   h->ld = (n + 127) / 128 * 128;
   h->ldb = 0;
@@ -749,7 +770,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
       if (f.shuffled || !f.gram_cached) {
         cudaEvent_t pe = h->prof_begin(0);
         if (h->gram_simt) launch_gram_simt(g, d_perm, f.nblocks, f.gram_p, 1, h->stream);
-        else launch_gram_tc(g, d_perm, f.nblocks, f.gram_p, 1, f.nband, h->fp8_codes, h->err.p, h->num_sms, f.sx_dev.p, h->tmap_ok ? h->tmap : nullptr, h->stream);
+        else launch_gram_tc(gram_view(h), d_perm, f.nblocks, f.gram_p, 1, f.nband, h->fp8_codes, h->err.p, h->num_sms, f.sx_dev.p, h->tmap_ok ? h->tmap : nullptr, h->stream);
         h->prof_end(pe);
         h->launches++;
         f.gram_cached = true;
@@ -1518,7 +1539,7 @@ int bwgr_debug_gram(bwgr_handle* h, const int32_t* perm, int block, int32_t* gra
   if (dperm.alloc(p) != cudaSuccess || dg.alloc((size_t)nblocks * kBlk * kBlk) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
   CU(cudaMemcpyAsync(dperm.p, perm, sizeof(int) * p, cudaMemcpyHostToDevice, h->stream));
   if (h->gram_simt) launch_gram_simt(h->view(), dperm.p, nblocks, dg.p, 0, h->stream);
-  else launch_gram_tc(h->view(), dperm.p, nblocks, dg.p, 0, 1, h->fp8_codes, h->err.p, h->num_sms, nullptr, h->tmap_ok ? h->tmap : nullptr, h->stream);
+  else launch_gram_tc(gram_view(h), dperm.p, nblocks, dg.p, 0, 1, h->fp8_codes, h->err.p, h->num_sms, nullptr, h->tmap_ok ? h->tmap : nullptr, h->stream);
   h->launches++;
   CU(cudaMemcpyAsync(gram_out, dg.p, sizeof(int32_t) * dg.n, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));

@@ -14,6 +14,7 @@
 // Two accumulator stages (2 x 128 TMEM columns) overlap the drain of block i with the MMAs of block i+1.
 // One CTA per SM, persistent over blocks.  HBM traffic: every genotype byte is read exactly once.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "kernels.h"
@@ -129,10 +130,10 @@ struct GramSmem {
   float sxc[128];  // column sums of this block's markers (centred Gram)
 };
 
-template <int NBAND, bool FP8, bool TMA>
+template <int NBAND, bool FP8, int PROD>
 __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* __restrict__ perm, int nblocks,
                                                          int32_t* __restrict__ gram, int out_f32, int* err,
-                                                         const float* __restrict__ sx, float inv_n,
+                                                         const float* __restrict__ sx, float inv_n, int dbg,
                                                          const __grid_constant__ CUtensorMap tmap) {
   constexpr int kStages = GramCfg<NBAND>::kStages;
   constexpr int kLag = GramCfg<NBAND>::kLag;  // cp.async groups kept in flight per producer thread
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
   const int nkg = (nkt + GramCfg<NBAND>::kSub - 1) / GramCfg<NBAND>::kSub;  // stages per block
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; s++) { mbar_init(&S->full[s], TMA ? 1 : 128); mbar_init(&S->empty[s], 1); }
+    for (int s = 0; s < kStages; s++) { mbar_init(&S->full[s], PROD == 1 ? 1 : 128); mbar_init(&S->empty[s], 1); }
     for (int s = 0; s < 2; s++) { mbar_init(&S->tmem_full[s], 1); mbar_init(&S->tmem_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = S->tmem_base;
 
-  if (TMA && warp < 4) {
+  if (PROD == 1 && warp < 4) {
     // ===================== producer: TMA gather4 (one warp; lane l brings markers 4l..4l+3 of every tile) =====================
     if (warp == 0) {
       uint32_t it = 0;
@@ -193,6 +194,77 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
                             &S->full[stage]);
             }
           }
+        }
+      }
+    }
+  } else if (PROD == 2 && warp < 4) {
+    // ===================== producer: 2-bit packed source (codes 0..3), expanded to bytes in flight =====================
+    // The gather is what bounds this kernel (~4.3 TB/s of cp.async at 50k x 50k whatever the MMA kind); reading the packed
+    // shadow copy moves 4x fewer bytes.  A 16-byte packed chunk = 64 rows of one marker = half a 128-row atom: it is
+    // loaded into registers one stage ahead, expanded with two shift/mask steps per word and stored as four swizzled
+    // 16-byte chunks.  Stage = kSub atoms, i.e. CPC = 2*kSub packed chunks per marker.
+    constexpr int CPC = 2 * kSub;          // packed 16-byte chunks per marker per stage
+    constexpr int NLD = CPC * NBAND;       // loads per thread per stage (128 markers * CPC chunks / 128 threads, per band)
+    const int t = threadIdx.x;
+    const int c = t % CPC, m0 = t / CPC;   // this thread's chunk within the stage and its first marker; markers m0 + (128/CPC)*i
+    uint32_t it = 0;
+    bool ok = true;
+    uint4 cur[NLD], nxt[NLD];
+    auto load_stage = [&](const uint8_t* const (&colp)[NBAND][CPC], const bool (&val)[NBAND][CPC], int kg, uint4 (&dst)[NLD]) {
+#pragma unroll
+      for (int d = 0; d < NBAND; d++)
+#pragma unroll
+        for (int i = 0; i < CPC; i++) {
+          const int64_t off = ((int64_t)kg * CPC + c) * 16;  // byte offset inside the packed column
+          dst[d * CPC + i] = (val[d][i] && off < g.ldb) ? __ldg(reinterpret_cast<const uint4*>(colp[d][i] + off)) : make_uint4(0, 0, 0, 0);
+        }
+    };
+    for (int blk = blockIdx.x; blk < nblocks && ok; blk += gridDim.x) {
+      const uint8_t* colp[NBAND][CPC];
+      bool val[NBAND][CPC];
+#pragma unroll
+      for (int d = 0; d < NBAND; d++)
+#pragma unroll
+        for (int i = 0; i < CPC; i++) {
+          const int m = m0 + (128 / CPC) * i;
+          const int pos = (blk - d) * 128 + m;
+          val[d][i] = pos >= 0 && pos < g.p;
+          colp[d][i] = g.x2 + (int64_t)(val[d][i] ? perm[pos] : 0) * g.ldb;
+        }
+      load_stage(colp, val, 0, cur);
+      for (int kg = 0; kg < nkg && ok; kg++, it++) {
+        if (kg + 1 < nkg) load_stage(colp, val, kg + 1, nxt);
+        const uint32_t stage = it % kStages, phase = (it / kStages) & 1u;
+        ok = mbar_wait(&S->empty[stage], phase ^ 1u, err);
+        const uint32_t tbase = smem_u32(tiles + stage * kStageBytes);
+        const int sub = c >> 1;  // atom of this chunk; rows 64*(c&1) .. +63 inside it -> output chunks 4*(c&1) .. +3
+#pragma unroll
+        for (int d = 0; d < NBAND; d++)
+#pragma unroll
+          for (int i = 0; i < CPC; i++) {
+            const int m = m0 + (128 / CPC) * i;
+            const uint4 pk = cur[d * CPC + i];
+            const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
+            const uint32_t rowb = tbase + (sub * NBAND + d) * kTileBytes + m * 128;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {  // packed word q = rows 16q .. 16q+15 of the half atom = one 16-byte output chunk
+              uint32_t o[4];
+#pragma unroll
+              for (int bq = 0; bq < 4; bq++) {
+                const uint32_t b8 = (w4[q] >> (8 * bq)) & 0xFFu;         // four 2-bit codes
+                uint32_t x = (b8 | (b8 << 12)) & 0x000F000Fu;            // nibbles into the two halfwords
+                x = (x | (x << 6)) & 0x03030303u;                        // each nibble into two bytes
+                o[bq] = x;
+              }
+              const uint32_t oc = (uint32_t)(4 * (c & 1) + q);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((oc ^ ((uint32_t)m & 7u)) << 4)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+            }
+          }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&S->full[stage]);
+        if (kg + 1 < nkg) {
+#pragma unroll
+          for (int q = 0; q < NLD; q++) cur[q] = nxt[q];
         }
       }
     }
@@ -262,7 +334,7 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
 #pragma unroll
           for (int sub = 0; sub < kSub; sub++) {
             const int kt = kg * kSub + sub;
-            if (kt < nkt) {
+            if (kt < nkt && !(dbg & 1)) {  // dbg bit 0 (BWGR_GRAM_DBG=1): gather only, no MMAs -- isolates the gather rate
               const uint64_t desc = make_desc_sw128(smem_u32(tiles + stage * kStageBytes + sub * NBAND * kTileBytes));
 #pragma unroll
               for (int d = 0; d < NBAND; d++) {
@@ -385,20 +457,23 @@ static void launch_gram_band(const GenoView& g, const int* perm, int nblocks, vo
                              const float* sx, const void* tmap, cudaStream_t st) {
   const size_t smem = (size_t)GramCfg<NBAND>::kStages * GramCfg<NBAND>::kSub * NBAND * kTileBytes + sizeof(GramSmem<NBAND>) + 1024;
   const int grid = nblocks < num_sms ? nblocks : num_sms;
-  if (tmap) {
-    cudaFuncSetAttribute(gram_tc_kernel<NBAND, FP8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gram_tc_kernel<NBAND, FP8, true><<<grid, 288, smem, st>>>(g, perm, nblocks, static_cast<int32_t*>(gram), out_f32, err, sx,
-                                                              1.0f / (float)g.n, *static_cast<const CUtensorMap*>(tmap));
-  } else {
-    CUtensorMap dummy;
-    memset(&dummy, 0, sizeof dummy);
-    cudaFuncSetAttribute(gram_tc_kernel<NBAND, FP8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gram_tc_kernel<NBAND, FP8, false><<<grid, 288, smem, st>>>(g, perm, nblocks, static_cast<int32_t*>(gram), out_f32, err, sx,
-                                                               1.0f / (float)g.n, dummy);
-  }
+  const char* de = getenv("BWGR_GRAM_DBG");
+  const int dbg = de ? atoi(de) : 0;
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof tm);
+  if (tmap) memcpy(&tm, tmap, sizeof tm);
+  const float inv_n = 1.0f / (float)g.n;
+  int32_t* out = static_cast<int32_t*>(gram);
+#define BWGR_GRAM_LAUNCH(PROD)                                                                                              \
+  do {                                                                                                                      \
+    cudaFuncSetAttribute(gram_tc_kernel<NBAND, FP8, PROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+    gram_tc_kernel<NBAND, FP8, PROD><<<grid, 288, smem, st>>>(g, perm, nblocks, out, out_f32, err, sx, inv_n, dbg, tm);     \
+  } while (0)
+  if (FP8 && g.x2 && !tmap) BWGR_GRAM_LAUNCH(2);   // packed 2-bit shadow copy: codes 0..2, exact E4M3 products
+  else if (tmap) BWGR_GRAM_LAUNCH(1);
+  else BWGR_GRAM_LAUNCH(0);
+#undef BWGR_GRAM_LAUNCH
 }
-// fp8_codes: every genotype is a code in 0..7 and max_j xx_j < 2^24 (the caller checked) -> the exact E4M3 path
-// sx != nullptr: centred Gram (float output only), sx[j] = column sum of marker j
 void launch_gram_tc(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, int nband, int fp8_codes,
                     int* err, int num_sms, const float* sx, const void* tmap, cudaStream_t st) {
   if (fp8_codes) {
