@@ -506,6 +506,10 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
   // =======================================================================================================
   constexpr bool kLinear = model_is_linear(MODEL);
   constexpr bool kGibbs = model_is_gibbs(MODEL);
+  // Gibbs spike-slab rules (BayesB :670-681, BayesC :731-741, KMUP :19-32): everything that does not depend on g is folded
+  // into four per-marker numbers one block ahead, and the Bernoulli(pj) draw u < 1/(1 + R exp(x)) is taken as
+  // x < log((1/u - 1)/R): the dependent chain per marker is one shuffle, five FMAs and a compare (no exp, no division).
+  constexpr bool kSlabDraw = MODEL == M_BB || MODEL == M_BC || MODEL == M_KMUP;
   const bool use_inv = pipe_use_inv(MODEL, ns);
   const int sring = a.sring;
   const SLayout L = solver_layout(ns, kGibbs, use_inv, sring);
@@ -701,7 +705,19 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
                 MarkerDraws dr;
                 if (kGibbs) dr = drb[jj];
                 else { dr.z1 = dr.z2 = dr.u = 0.0f; dr.chi = 1.0f; }
-                const RuleOut ro = marker_rule<MODEL>(gc, mc[jj].xx, in.b0, in.vbj, Sy, dr);
+                RuleOut ro;
+                if (kSlabDraw) {
+                  const float xxj = mc[jj].xx, b1 = fmaf(gc, in.a, in.c), b2 = dr.z2;
+                  // ||e2||^2 - ||e1||^2 in closed form: KMUP compares the two draws, BayesB/C the draw against b = 0 (:673)
+                  const float q = MODEL == M_KMUP ? (b2 - b1) * fmaf(xxj, (b1 + b2) - 2.0f * in.b0, -2.0f * gc)
+                                                  : b1 * fmaf(xxj, 2.0f * in.b0 - b1, 2.0f * gc);
+                  const bool take = Sy.C * q < dr.u;
+                  ro.b = take ? b1 : b2; ro.d = take ? 1.0f : 0.0f;
+                  ro.de = ro.b - in.b0;
+                  ro.vbj = MODEL == M_BB ? (Sy.Sb + ro.b * ro.b) / dr.chi : in.vbj;
+                } else {
+                  ro = marker_rule<MODEL>(gc, mc[jj].xx, in.b0, in.vbj, Sy, dr);
+                }
                 if (lane == i) { nb[t] = ro.b; nd[t] = ro.d; nv[t] = ro.vbj; de[t] = ro.de; }
                 // row jj of the Gram block to the right of (and inside) its diagonal tile: stored as tile (tt, t)
 #pragma unroll
@@ -886,6 +902,16 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
             if (kLinear) {
               const LinCoef lc = lin_coef<MODEL>(mcv.xx, in.b0, in.vbj, sc[s], dr);
               in.a = lc.a; in.c = lc.c;
+            }
+            if (kSlabDraw) {
+              const float lmb = MODEL == M_BB ? sc[s].ve * (1.0f / in.vbj) : MODEL == M_BC ? sc[s].lmb : in.vbj;  // KMUP: vbj carries L[j]
+              const float ia = 1.0f / (mcv.xx + lmb), sd = sqrtf(sc[s].ve * ia);
+              const float ratio = MODEL == M_KMUP ? sc[s].pi_mix / (1.0f - sc[s].pi_mix) : sc[s].Pi0;
+              in.a = ia;                                   // b1 = g * ia + c
+              in.c = fmaf(mcv.xx * in.b0, ia, sd * dr.z1);
+              dr.z2 = sd * dr.z2;                          // the excluded draw b2
+              dr.u = (MODEL == M_KMUP && !(sc[s].pi_mix > 0.0f)) ? 3.0e38f : logf((1.0f / dr.u - 1.0f) / ratio);  // accept b1 iff C*q < this
+              drw[((size_t)slot * ns + s) * 128 + ht] = dr;
             }
           }
           msys[((size_t)slot * ns + s) * 128 + ht] = in;
