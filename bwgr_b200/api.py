@@ -56,6 +56,28 @@ class Genotypes:
         self.n, self.p = int(n), int(p)
         return self
 
+    def enable_row_sharding(self, group=None):
+        """One large fit sharded by rows over the ranks of a torch.distributed group (one process per GPU of a node):
+        call before load(); every rank then loads ITS rows and passes ITS rows of y to the usual fit functions.
+        The host framework only carries 128 + 64 bytes per rank here (NCCL id, IPC handle of the exchange ring)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        uid = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            check(self.lib.bwgr_dist_unique_id(_ptr(uid)))
+        box = [uid.tobytes()]
+        dist.broadcast_object_list(box, src=0, group=group)
+        uid = np.frombuffer(box[0], dtype=np.uint8).copy()
+        ipc = np.zeros(64, dtype=np.uint8)
+        check(self.lib.bwgr_dist_init(self.h, rank, world, _ptr(uid), _ptr(ipc)))
+        allh = [None] * world
+        dist.all_gather_object(allh, ipc.tobytes(), group=group)
+        blob = np.frombuffer(b"".join(allh), dtype=np.uint8).copy()
+        check(self.lib.bwgr_dist_connect(self.h, _ptr(blob)))
+        self.rank, self.world = rank, world
+        return self
+
     def set_tuning(self, block=-1, path=-1, grid=-1):
         check(self.lib.bwgr_set_tuning(self.h, block, path, grid))
 

@@ -7,6 +7,9 @@
 //   * initial hyper-parameters per solver, in float like the reference;
 //   * choosing the kernel family (small-n CTA-per-system vs blocked whole-GPU sweep).
 // There is deliberately no CPU compute path: every sweep runs in the CUDA kernels of this directory.
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -90,6 +93,7 @@ struct Fit {
   float* gram_p = nullptr;              // Gram band in use: f.gram (per fit) or the handle's natural-order cache
   // single Kuo-Mallick sweep / wgr driver
   DevBuf<float> xx_over;                // caller's xx (KMUP takes it as an argument, :12) / centred xx (MRR3)
+  DevBuf<double> esum; DevBuf<float> emaxv;  // row-sharded fit: all-reduced epilogue sums
   DevBuf<float> sx_dev, cshift;         // MRR3: column sums (centred columns) and the per-system mean shift of a sweep
   bool skip_epilogue = false;
   bool wgr_mode = false;
@@ -106,6 +110,41 @@ struct Fit {
   }
 };
 
+}  // namespace
+
+namespace {
+// NCCL is resolved at run time (dlopen): a single-GPU user of the library never needs it.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (lib) {
+      api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+      api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+      api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+      api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+      api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+      api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy;
+    }
+  }
+  return api;
+}
+#define NC(call)                                                                                                     \
+  do {                                                                                                               \
+    ncclResult_t r_ = (call);                                                                                        \
+    if (r_ != ncclSuccess) return fail(BWGR_ERR_CUDA, "%s failed: %s", #call, nccl().GetErrorString ? nccl().GetErrorString(r_) : "?"); \
+  } while (0)
 }  // namespace
 
 struct bwgr_handle {
@@ -129,6 +168,15 @@ struct bwgr_handle {
   int gram_simt = 0;
   DevBuf<float> gram_nat;  // Gram band of the natural marker order (Gibbs / KMUP / wgr): depends on the store only
   int gram_nat_band = 0;
+  // row-sharded fit over the GPUs of a node (bwgr_dist_*)
+  int world = 1, rank = 0;
+  int64_t n_global = 0;
+  ncclComm_t comm = nullptr;
+  DevBuf<unsigned long long> hx_own;        // this rank's exchange ring [8][world][32][128]
+  unsigned long long* hx[8] = {};           // every rank's ring as seen from this process (peer memory)
+  bool hx_connected = false;
+  unsigned long long dist_gen = 0;          // global block sequence number (same on every rank)
+  DevBuf<double> dscratch;                  // small all-reduce scratch
   alignas(64) unsigned char tmap[128];  // CUtensorMap of the int8 store (TMA tile::gather4)
   bool tmap_ok = false;
   int fp8_codes = 0;  // all genotypes are codes 0..7 (and n small enough): the Gram kernel may use the exact E4M3 path
@@ -191,6 +239,17 @@ int check_err_flag(bwgr_handle* h, const char* where) {
   return 0;
 }
 
+// Row-sharded fit: all-reduce `cnt` host doubles over the ranks (sum or max) through a device scratch buffer.
+int dist_allreduce_host(bwgr_handle* h, double* v, int cnt, bool is_max) {
+  if (h->world <= 1) return 0;
+  if (h->dscratch.n < (size_t)cnt && h->dscratch.alloc(std::max(cnt, 256)) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  CU(cudaMemcpyAsync(h->dscratch.p, v, sizeof(double) * cnt, cudaMemcpyHostToDevice, h->stream));
+  NC(nccl().AllReduce(h->dscratch.p, h->dscratch.p, (size_t)cnt, ncclDouble, is_max ? ncclMax : ncclSum, h->comm, h->stream));
+  CU(cudaMemcpyAsync(v, h->dscratch.p, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int finish_store(bwgr_handle* h, int storage) {
   // column statistics from the int8 copy, then optional 2-bit packing
   GenoView g8 = h->view();
@@ -199,6 +258,16 @@ int finish_store(bwgr_handle* h, int storage) {
     return fail(BWGR_ERR_CUDA, "cudaMalloc(stats) failed");
   launch_col_stats(g8, h->xx_i.p, h->sx_i.p, h->stream);
   h->launches++;
+  h->n_global = h->n;
+  if (h->world > 1) {  // row shards: the column statistics are sums over all individuals
+    if (storage != BWGR_STORE_I8) return fail(BWGR_ERR_UNSUPPORTED, "row-sharded fits take the int8 store");
+    NC(nccl().AllReduce(h->xx_i.p, h->xx_i.p, (size_t)h->p, ncclInt64, ncclSum, h->comm, h->stream));
+    NC(nccl().AllReduce(h->sx_i.p, h->sx_i.p, (size_t)h->p, ncclInt64, ncclSum, h->comm, h->stream));
+    double ng = (double)h->n;
+    int rcn = dist_allreduce_host(h, &ng, 1, false);
+    if (rcn) return rcn;
+    h->n_global = (int64_t)ng;
+  }
   std::vector<long long> xx(h->p), sx(h->p);
   CU(cudaMemcpyAsync(xx.data(), h->xx_i.p, sizeof(long long) * h->p, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(sx.data(), h->sx_i.p, sizeof(long long) * h->p, cudaMemcpyDeviceToHost, h->stream));
@@ -320,6 +389,9 @@ void bwgr_destroy(bwgr_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   h->fit.reset();
+  for (int r = 0; r < h->world; r++)
+    if (r != h->rank && h->hx[r]) cudaIpcCloseMemHandle(h->hx[r]);
+  if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -501,7 +573,16 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
   Fit& f = h->fit;
   f.reset();
   bool blocked = false;
+  const bool dist = h->world > 1;
+  if (dist) {
+    if (!h->hx_connected) return fail(BWGR_ERR_STATE, "row-sharded handle: call bwgr_dist_connect before fitting");
+    if (s.row_mask) return fail(BWGR_ERR_UNSUPPORTED, "row-sharded fits take unmasked systems");
+    if (s.model == M_MRR || s.model == M_KMUP) return fail(BWGR_ERR_UNSUPPORTED, "row sharding covers the univariate EM and Gibbs solvers");
+  }
+  const int saved_path_ = h->path;
+  if (dist) h->path = BWGR_PATH_BLOCKED;
   int rc = choose_path(h, s, &blocked);
+  h->path = saved_path_;
   if (rc) return rc;
   const int64_t n = h->n, p = h->p, ld = h->ld;
   const int ns = s.nsys;
@@ -511,7 +592,7 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
   f.it_target = s.it;
 
   // ---- per-system row masks and column statistics
-  std::vector<float> n_eff(ns, (float)n);
+  std::vector<float> n_eff(ns, (float)(dist ? h->n_global : n));
   std::vector<std::vector<double>> xx_s, sx_s;  // masked systems only
   if (f.masked) {
     std::vector<uint8_t> m((size_t)ns * ld, 0);
@@ -566,10 +647,24 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
       sxx += xx[j];
     }
     const float sum_vx = (float)svx;
-    const float vy = fvar_f(yt);
-    double sm = 0;
-    for (float v : yt) sm += v;
-    const float mu = (float)(sm / (double)yt.size());
+    float vy, mu;
+    if (!dist) {
+      vy = fvar_f(yt);
+      double sm = 0;
+      for (float v : yt) sm += v;
+      mu = (float)(sm / (double)yt.size());
+    } else {  // mean and variance of y over ALL individuals (two small all-reduces)
+      double sm = 0;
+      for (float v : yt) sm += v;
+      rc = dist_allreduce_host(h, &sm, 1, false);
+      if (rc) return rc;
+      mu = (float)(sm / (double)h->n_global);
+      double ss = 0;
+      for (float v : yt) { const float tt = v - mu; ss += (double)tt * tt; }
+      rc = dist_allreduce_host(h, &ss, 1, false);
+      if (rc) return rc;
+      vy = (float)ss / (float)(h->n_global - 1);
+    }
     SysScalars c;
     memset(&c, 0, sizeof c);
     c.mu = mu; c.df = s.df; c.R2 = s.R2; c.alpha = s.alpha; c.vy = vy; c.n_eff = nn; c.pi_mix = s.pi;
@@ -647,6 +742,12 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
     {  // fixed-point scale of the residuals (tensor-core passes): 8x headroom over max|y - mu|
       float emax = 0;
       for (float v : yt) emax = std::max(emax, std::fabs(v - mu));
+      if (dist) {  // the fixed-point scale must be the same on every rank
+        double em = emax;
+        rc = dist_allreduce_host(h, &em, 1, true);
+        if (rc) return rc;
+        emax = (float)em;
+      }
       int ex = 0;
       if (emax > 0) std::frexp(emax, &ex);
       if (ex < -60) ex = -60;
@@ -696,6 +797,15 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
     f.nblocks = (int)((p + kBlk - 1) / kBlk);
     PipePlan pl;
     f.pipe = plan_pipe(h, s.model, ns, &pl);
+    if (dist) {
+      if (!f.pipe) return fail(BWGR_ERR_UNSUPPORTED, "row-sharded fit: the shape does not fit the pipelined blocked sweep");
+      // stale words of a previous fit (another nsys = another ring layout) must not be mistaken for this fit's: zero my ring,
+      // then a collective as the barrier that no peer writes into it before it is clean
+      CU(cudaMemsetAsync(h->hx_own.p, 0, sizeof(unsigned long long) * h->hx_own.n, h->stream));
+      double one = 1;
+      rc = dist_allreduce_host(h, &one, 1, false);
+      if (rc) return rc;
+    }
     if (f.pipe) {
       f.rows_per_cta = pl.R; f.nworkers = pl.W; f.grid = pl.W + 1; f.nbuf = pl.nbuf; f.sring = pl.sring; f.lookahead = pl.D; f.nband = pl.D + 1;
       f.nc = std::max(1, 16 / ns);
@@ -775,6 +885,8 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
         h->launches++;
         f.gram_cached = true;
         if (!f.shuffled && f.gram_p == h->gram_nat.p) h->gram_nat_band = f.nband;
+        if (h->world > 1)  // row shards: the Gram band is a sum over individuals (exact: integers below 2^24 in fp32)
+          NC(nccl().AllReduce(f.gram_p, f.gram_p, (size_t)f.nblocks * kBlk * kBlk * f.nband, ncclFloat, ncclSum, h->comm, h->stream));
       }
       if (f.pipe) {
         CU(cudaMemsetAsync(f.part.p, 0, sizeof(unsigned long long) * f.part.n, h->stream));
@@ -785,6 +897,9 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
         a.part = f.part.p; a.hred = f.part.p + (size_t)8 * f.nsys * 128 * 160; a.dew = f.dew.p; a.tag = ++f.tag;
         a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0;
         a.rows_per_cta = f.rows_per_cta; a.nworkers = f.nworkers; a.D = f.lookahead; a.nbuf = f.nbuf; a.sring = f.sring; a.err = h->err.p;
+        a.world = h->world; a.rank = h->rank; a.gen0 = h->dist_gen;
+        for (int r = 0; r < 8; r++) a.hx[r] = h->hx[r];
+        if (h->world > 1) h->dist_gen += (unsigned long long)f.nblocks;
         if (getenv("BWGR_TRACE")) {
           if (!f.trace.p) { f.trace.alloc((size_t)f.grid * f.nblocks * 32); cudaMemsetAsync(f.trace.p, 0, sizeof(long long) * f.trace.n, h->stream); }
           a.trace = f.trace.p;
@@ -832,10 +947,21 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
     } else if (!f.skip_epilogue) {
       EpilogueArgs ea;
       memset(&ea, 0, sizeof ea);
+      if (h->world > 1) {
+        if (f.esum.n < (size_t)4 * f.nsys && (f.esum.alloc((size_t)4 * f.nsys) != cudaSuccess || f.emaxv.alloc(f.nsys) != cudaSuccess))
+          return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+      }
       ea.model = f.model; ea.nsys = f.nsys; ea.n = (int)h->n; ea.p = (int)p; ea.ld = ld; ea.e = f.e.p; ea.y = f.y.p; ea.b = f.b.p;
       ea.d = f.d.p; ea.vbv = f.vbv.p; ea.b_prev = f.b_prev.p; ea.mask = f.mask.p; ea.sc = f.sc.p; ea.B = f.B.p; ea.D = f.D.p;
       ea.VBv = f.VBv.p; ea.seed_lo = (uint32_t)f.seed; ea.seed_hi = (uint32_t)(f.seed >> 32); ea.chain0 = 0;
       cudaEvent_t pe2 = h->prof_begin(2);
+      if (h->world > 1) {  // sums over individuals: per rank, then all-reduced; everything else is replicated
+        launch_epilogue_partial(ea, f.esum.p, f.emaxv.p, h->stream);
+        NC(nccl().AllReduce(f.esum.p, f.esum.p, (size_t)4 * f.nsys, ncclDouble, ncclSum, h->comm, h->stream));
+        NC(nccl().AllReduce(f.emaxv.p, f.emaxv.p, (size_t)f.nsys, ncclFloat, ncclMax, h->comm, h->stream));
+        ea.esum = f.esum.p; ea.emaxv = f.emaxv.p;
+        h->launches++;
+      }
       launch_epilogue(ea, h->stream);
       h->prof_end(pe2);
       h->launches++;
@@ -929,7 +1055,20 @@ int bwgr_em_end(bwgr_handle* h, bwgr_em_out* out) {
       case M_EMBL: {
         std::vector<float> ev;
         for (int64_t i = 0; i < n; i++) ev.push_back(he[(size_t)t * ld + i]);
-        h2 = 1.0f - fvar_f(ev) / f.vy[t]; Ve = 0; break;
+        if (h->world > 1) {  // var(e) over all individuals (:391)
+          double sums[2] = {0, 0};
+          for (float v : ev) sums[0] += v;
+          rc = dist_allreduce_host(h, sums, 1, false);
+          if (rc) return rc;
+          const float me = (float)(sums[0] / (double)h->n_global);
+          for (float v : ev) { const float tt = v - me; sums[1] += (double)tt * tt; }
+          rc = dist_allreduce_host(h, sums + 1, 1, false);
+          if (rc) return rc;
+          h2 = 1.0f - ((float)sums[1] / (float)(h->n_global - 1)) / f.vy[t];
+        } else {
+          h2 = 1.0f - fvar_f(ev) / f.vy[t];
+        }
+        Ve = 0; break;
       }
       case M_EMEN: { const float va = c.vb * f.cxx[t]; Va = va; h2 = va / (va + c.ve); break; }
       default: break;
@@ -1509,6 +1648,52 @@ int bwgr_mrr3_fit(bwgr_handle* h, int f32_variant, const double* Y, int k, const
   if (its_out) *its_out = numit;
   // the swapped buffers go back to their owners before the fit is released
   f.reset();
+  return 0;
+}
+
+// ---- row sharding over the GPUs of a node ------------------------------------------------------------------------------
+int bwgr_dist_unique_id(void* id128) {
+  if (!id128) return fail(BWGR_ERR_ARG, "null argument");
+  if (!nccl().ok) return fail(BWGR_ERR_UNSUPPORTED, "libnccl.so.2 not found");
+  ncclUniqueId id;
+  NC(nccl().GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128, &id, 128);
+  return 0;
+}
+
+int bwgr_dist_init(bwgr_handle* h, int rank, int world, const void* id128, void* ipc_out) {
+  if (!h || !id128 || !ipc_out) return fail(BWGR_ERR_ARG, "null argument");
+  if (world < 2 || world > 8 || rank < 0 || rank >= world) return fail(BWGR_ERR_ARG, "need 2 <= world <= 8 and 0 <= rank < world");
+  if (!nccl().ok) return fail(BWGR_ERR_UNSUPPORTED, "libnccl.so.2 not found");
+  if (h->p) return fail(BWGR_ERR_STATE, "bwgr_dist_init must precede bwgr_geno_load_*");
+  CU(cudaSetDevice(h->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  NC(nccl().CommInitRank(&h->comm, world, id, rank));
+  if (h->hx_own.alloc((size_t)8 * world * 32 * 128) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(exchange ring) failed");
+  CU(cudaMemset(h->hx_own.p, 0, sizeof(unsigned long long) * h->hx_own.n));
+  cudaIpcMemHandle_t mh;
+  CU(cudaIpcGetMemHandle(&mh, h->hx_own.p));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(ipc_out, &mh, 64);
+  h->world = world; h->rank = rank; h->dist_gen = 0; h->hx_connected = false;
+  return 0;
+}
+
+int bwgr_dist_connect(bwgr_handle* h, const void* ipc_all) {
+  if (!h || !ipc_all) return fail(BWGR_ERR_ARG, "null argument");
+  if (h->world < 2) return fail(BWGR_ERR_STATE, "bwgr_dist_init first");
+  CU(cudaSetDevice(h->device));
+  for (int r = 0; r < h->world; r++) {
+    if (r == h->rank) { h->hx[r] = h->hx_own.p; continue; }
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, static_cast<const unsigned char*>(ipc_all) + 64 * r, 64);
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+    h->hx[r] = static_cast<unsigned long long*>(ptr);
+  }
+  h->hx_connected = true;
   return 0;
 }
 

@@ -42,12 +42,13 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
 
   double se = 0, see = 0, sey = 0, sy = 0;
   float emax = 0.0f;
-  for (int i = tid; i < a.n; i += T) {
-    if (mask && !mask[i]) continue;
-    const double ev = e[i], yv = y[i];
-    se += ev; see += ev * ev; sey += ev * yv; sy += yv;
-    emax = fmaxf(emax, fabsf(e[i]));
-  }
+  if (!a.esum)  // row-sharded fit: the sums over individuals were taken per rank and all-reduced (a.esum)
+    for (int i = tid; i < a.n; i += T) {
+      if (mask && !mask[i]) continue;
+      const double ev = e[i], yv = y[i];
+      se += ev; see += ev * ev; sey += ev * yv; sy += yv;
+      emax = fmaxf(emax, fabsf(e[i]));
+    }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
   __shared__ float sh_max[32];
@@ -64,6 +65,10 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
   }
   se = block_sum(se, sh); see = block_sum(see, sh); sey = block_sum(sey, sh); sy = block_sum(sy, sh);
   sbb = block_sum(sbb, sh); sd = block_sum(sd, sh); scnv = block_sum(scnv, sh);
+  if (a.esum) {
+    se = a.esum[4 * sys + 0]; see = a.esum[4 * sys + 1]; sey = a.esum[4 * sys + 2]; sy = a.esum[4 * sys + 3];
+    emax = a.emaxv[sys];
+  }
 
   if (tid == 0) {
     SysScalars s = *scp;
@@ -234,7 +239,38 @@ __global__ void __launch_bounds__(256) wgr_markers_kernel(WgrArgs a) {
     for (int i = t0; i < a.n; i += stride) a.e[i] -= w.mu0;
 }
 
+// Row-sharded fit: this rank's part of the sums over individuals, [nsys][4] doubles {sum e, sum e^2, sum e y, sum y} and
+// max|e| per system; ncclAllReduce (sum / max) runs between this kernel and epilogue_kernel.
+__global__ void __launch_bounds__(1024) epilogue_partial_kernel(EpilogueArgs a, double* out, float* emax_out) {
+  __shared__ double sh[32];
+  __shared__ float sh_max[32];
+  const int sys = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  const float* e = a.e + (size_t)sys * a.ld;
+  const float* y = a.y + (size_t)sys * a.ld;
+  double se = 0, see = 0, sey = 0, sy = 0;
+  float emax = 0.0f;
+  for (int i = tid; i < a.n; i += T) {
+    const double ev = e[i], yv = y[i];
+    se += ev; see += ev * ev; sey += ev * yv; sy += yv;
+    emax = fmaxf(emax, fabsf(e[i]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+  if ((tid & 31) == 0) sh_max[tid >> 5] = emax;
+  se = block_sum(se, sh); see = block_sum(see, sh); sey = block_sum(sey, sh); sy = block_sum(sy, sh);
+  if (tid == 0) {
+    emax = 0.0f;
+    for (int w = 0; w < (T >> 5); w++) emax = fmaxf(emax, sh_max[w]);
+    out[4 * sys + 0] = se; out[4 * sys + 1] = see; out[4 * sys + 2] = sey; out[4 * sys + 3] = sy;
+    emax_out[sys] = emax;
+  }
+}
+
 }  // namespace
+
+void launch_epilogue_partial(const EpilogueArgs& a, double* out, float* emax_out, cudaStream_t st) {
+  epilogue_partial_kernel<<<a.nsys, 1024, 0, st>>>(a, out, emax_out);
+}
 
 void launch_wgr_step(const WgrArgs& a, int num_sms, cudaStream_t st) {
   wgr_scalars_kernel<<<1, 1024, 0, st>>>(a);

@@ -120,8 +120,13 @@ struct PipeArgs {
                          // centred one and g gets the running mean-shift term c * sx_j (the workers stay uncentred)
   float* cshift;         // [nsys] out: the mean shift c accumulated over the sweep (e_true = e_stored + c)
   SysScalars* sc;        // [nsys]
-  unsigned long long* part;  // [8][nsys][128][160] per-worker integer partials of h: (value << 16) | block tag; zeroed before launch
+  unsigned long long* part;  // [8][nsys][128][160] per-worker integer partials of h: (value << 12) | block tag; zeroed before launch
   unsigned long long* hred;  // [8][nsys][128] reduced h, same word format; zeroed before launch
+  // row-sharded fit over `world` GPUs of a node: hx[r] = rank r's exchange ring [8][world][nsys][128] mapped into this
+  // process (peer memory over NVLink); gen0 = global sequence number of this launch's block 0 (slot / tag of the ring)
+  int world, rank;
+  unsigned long long* hx[8];
+  unsigned long long gen0;
   unsigned long long* dew;  // [nblocks][nsys][136] published steps: (int32 q << 32) | tag, word 128 = (float scale << 32) | tag
   uint32_t tag;          // unique per launch, never 0
   uint32_t seed_lo, seed_hi;
@@ -148,8 +153,11 @@ struct EpilogueArgs {
   float* B; float* D; float* VBv;
   uint32_t seed_lo, seed_hi;
   int chain0;
+  // row-sharded fit: all-reduced sums over individuals [nsys][4] {sum e, sum e^2, sum e.y, sum y} and max|e| [nsys]; else nullptr
+  const double* esum; const float* emaxv;
 };
 void launch_epilogue(const EpilogueArgs& a, cudaStream_t st);
+void launch_epilogue_partial(const EpilogueArgs& a, double* out, float* emax_out, cudaStream_t st);
 
 // wgr() driver step (R/wgr.R:91-136), after each Kuo-Mallick sweep: variance draws, intercept, posterior sums.
 struct WgrState {      // device resident, one per fit

@@ -143,9 +143,27 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// system scope: the exchange ring of a row-sharded fit is written by peer GPUs over NVLink
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+
+// Self-validating 64-bit words of the grid reduction: (signed value << 12) | tag, tag = 1 + (use index of the ring slot) mod 4095
+// (never 0 = freshly zeroed memory; consecutive uses of a slot always differ).  |value| < 2^51: a rank's sum of 143 worker
+// partials of 2^30 * 2 * 512 rows is < 2^48.
+constexpr int kTagBits = 12;
+__device__ __forceinline__ unsigned long long tag_of(unsigned long long use) { return use % 4095ull + 1ull; }
+__device__ __forceinline__ unsigned long long pack_word(long long v, unsigned long long tag) { return ((unsigned long long)v << kTagBits) | tag; }
+__device__ __forceinline__ bool word_ok(unsigned long long w, unsigned long long tag) { return (w & ((1ull << kTagBits) - 1ull)) == tag; }
+__device__ __forceinline__ long long word_val(unsigned long long w) { return (long long)w >> kTagBits; }
 
 // per (system, marker) inputs of the solve; per marker: xx and the marker id
 struct MarkerSys { float b0, vbj, a, c; };
@@ -327,15 +345,15 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
         mbar_wait(&S.g_done, (uint32_t)c & 1u, dead, a.err);
         if (t0) WSTAMP(c, 6);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // partial of marker q, system s -> part[c % ring][s][this worker][q] (full 32-byte sectors): (value << 16) | block tag
+        // partial of marker q, system s -> part[c % ring][s][this worker][q] (full 32-byte sectors): (value << 12) | block tag
         unsigned long long* hb = a.part + (((size_t)(c % kRing) * ns) * kWPad + blockIdx.x) * 128 + q;
-        const unsigned long long tagc = (unsigned long long)((c / kRing + 1) & 0xFFFF);
+        const unsigned long long tagc = tag_of((unsigned long long)(c / kRing));
         for (int s = 0; s < ns; s++) {
           int s0, s1, s2, s3;
           tmem_ld4(tmem_g + tlane + (uint32_t)(4 * s), s0, s1, s2, s3);
           tmem_ld_wait();
           const long long gq = combine_limbs(s0, s1, s2, s3);
-          st_relaxed_u64(hb + (size_t)s * kWPad * 128, ((unsigned long long)gq << 16) | tagc);
+          st_relaxed_u64(hb + (size_t)s * kWPad * 128, pack_word(gq, tagc));
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(&S.g_empty);
@@ -462,7 +480,11 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
       // row (block c, system s, marker m) of the partials is summed by worker (s*128 + m) % W; plain loads and one store,
       // no atomics (143 x 128 L2 atomics per block cost ~7 us; this tree costs two L2 round trips)
       for (int c = 0; c < nblocks; c++) {
-        const unsigned long long tagc = (unsigned long long)((c / kRing + 1) & 0xFFFF);
+        const unsigned long long tagc = tag_of((unsigned long long)(c / kRing));
+        // row-sharded fit: the slot / tag of the exchange ring follow the global block sequence number (never re-zeroed)
+        const unsigned long long gen = a.gen0 + (unsigned long long)c;
+        const unsigned long long tagx = tag_of(gen / kRing);
+        const size_t xslot = (size_t)(gen % kRing);
         for (int task = blockIdx.x; task < ns * 128; task += W) {
           const unsigned long long* row = a.part + ((size_t)(c % kRing) * ns + (task >> 7)) * kWPad * 128 + (task & 127);  // stride 128 words per worker
           long long sum = 0;
@@ -475,8 +497,8 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
               const int w = 32 * k + lane;
               if (w < W) {
                 const unsigned long long v = ld_relaxed_u64(row + (size_t)w * 128);
-                ok = ok && ((v & 0xFFFFull) == tagc);
-                sum += (long long)v >> 16;
+                ok = ok && word_ok(v, tagc);
+                sum += word_val(v);
               }
             }
             if (__all_sync(0xffffffffu, ok)) break;
@@ -485,7 +507,13 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
           if (tracing && lane == 0 && task == (int)blockIdx.x) WSTAMP(c, 14);
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          if (lane == 0) st_relaxed_u64(a.hred + (size_t)(c % kRing) * ns * 128 + task, ((unsigned long long)sum << 16) | tagc);
+          if (a.world > 1) {
+            // third hop over NVLink: this rank's reduced word goes straight into every rank's exchange ring (peer stores);
+            // each solver then sums the `world` words of a marker in rank order -- identical integers on every GPU
+            if (lane < a.world) st_relaxed_sys_u64(a.hx[lane] + ((xslot * a.world + a.rank) * ns) * 128 + task, pack_word(sum, tagx));
+          } else if (lane == 0) {
+            st_relaxed_u64(a.hred + (size_t)(c % kRing) * ns * 128 + task, pack_word(sum, tagc));
+          }
           if (tracing && lane == 0 && task == (int)blockIdx.x) WSTAMP(c, 15);
         }
       }
@@ -586,18 +614,41 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
           {
             long long qq[4] = {0, 0, 0, 0};
             uint32_t spins = 0;
-            const unsigned long long* gq = a.hred + ((size_t)(b % kRing) * ns + s) * 128;
-            const unsigned long long tagb = (unsigned long long)((b / kRing + 1) & 0xFFFF);
-            while (!dead) {
-              bool ok = true;
+            if (a.world > 1) {
+              const unsigned long long gen = a.gen0 + (unsigned long long)b;
+              const unsigned long long tagx = tag_of(gen / kRing);
+              const unsigned long long* gx = a.hx[a.rank] + ((size_t)(gen % kRing) * a.world * ns + s) * 128;
+              for (int src = 0; src < a.world; src++) {
+                const unsigned long long* gq = gx + (size_t)src * ns * 128;
+                long long w4[4] = {0, 0, 0, 0};
+                while (!dead) {
+                  bool ok = true;
 #pragma unroll
-              for (int t = 0; t < 4; t++) {
-                const unsigned long long w = ld_relaxed_u64(gq + 32 * t + lane);
-                ok = ok && ((w & 0xFFFFull) == tagb);
-                qq[t] = (long long)w >> 16;
+                  for (int t = 0; t < 4; t++) {
+                    const unsigned long long w = ld_relaxed_sys_u64(gq + 32 * t + lane);
+                    ok = ok && word_ok(w, tagx);
+                    w4[t] = word_val(w);
+                  }
+                  if (__all_sync(0xffffffffu, ok)) break;
+                  if (++spins > kSpin || ((spins & 255u) == 255u && *reinterpret_cast<volatile int*>(a.err) != 0)) { dead = true; atomicCAS(a.err, 0, 3); }
+                }
+#pragma unroll
+                for (int t = 0; t < 4; t++) qq[t] += w4[t];
               }
-              if (__all_sync(0xffffffffu, ok)) break;
-              if (++spins > kSpin || ((spins & 255u) == 255u && *reinterpret_cast<volatile int*>(a.err) != 0)) { dead = true; atomicCAS(a.err, 0, 3); }
+            } else {
+              const unsigned long long* gq = a.hred + ((size_t)(b % kRing) * ns + s) * 128;
+              const unsigned long long tagb = tag_of((unsigned long long)(b / kRing));
+              while (!dead) {
+                bool ok = true;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                  const unsigned long long w = ld_relaxed_u64(gq + 32 * t + lane);
+                  ok = ok && word_ok(w, tagb);
+                  qq[t] = word_val(w);
+                }
+                if (__all_sync(0xffffffffu, ok)) break;
+                if (++spins > kSpin || ((spins & 255u) == 255u && *reinterpret_cast<volatile int*>(a.err) != 0)) { dead = true; atomicCAS(a.err, 0, 3); }
+              }
             }
             if (s == 0) SSTAMP(b, 8);
 #pragma unroll

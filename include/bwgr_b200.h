@@ -156,6 +156,17 @@ BWGR_API int bwgr_mrr3_fit(bwgr_handle* h, int f32_variant, const double* Y, int
                   double* hat, double* h2, double* GC, double* vb, double* ve, double* MSx, double* cnv, double* W,
                   int* its);
 
+/* ---- one large fit sharded by rows over the GPUs of a node (BASELINE config 5) ---------------------
+ * Not in the reference (single process, single thread).  One process per GPU; every rank loads ITS rows of X and passes
+ * ITS rows of y.  b / variance components come back identical on every rank, hat holds the rank's rows.
+ * Per 128-marker block the reduced partial X_B'E of a rank is stored straight into every peer's exchange ring inside the
+ * sweep kernel (peer memory over NVLink, no host involvement); NCCL all-reduces the per-sweep Gram band and scalars.
+ * Call order on every rank: bwgr_create -> bwgr_dist_init -> (exchange the 64-byte handles) -> bwgr_dist_connect ->
+ * bwgr_geno_load_* -> fits.  Supports the blocked family (unmasked systems, int8 store). */
+BWGR_API int bwgr_dist_unique_id(void* id128);  /* rank 0 creates it, the host framework broadcasts the 128 bytes */
+BWGR_API int bwgr_dist_init(bwgr_handle* h, int rank, int world, const void* id128, void* ipc_handle_out64);
+BWGR_API int bwgr_dist_connect(bwgr_handle* h, const void* ipc_handles_all /* world x 64 bytes, rank order */);
+
 /* ---- introspection for tests and the bench -------------------------------------------------- */
 /* Kernels launched by this handle since creation (the bench's gpu_launches claim). */
 BWGR_API int64_t bwgr_launch_count(bwgr_handle* h);
