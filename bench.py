@@ -324,6 +324,38 @@ def main():
                "sample": "oracle %s (g++ -O2, float32, 1 thread like the reference), full n=%d x first %d markers, %d sweeps = %.1f s; %s, %d host cores" % (
                    args.model, n, m, args.cpu_sweeps_main, secs, cpu_model_name(), os.cpu_count())}
 
+    # ---- N > 1 also measures the OTHER multi-GPU mode of the path: one fit, individuals sharded by rows over the ranks
+    # (BASELINE config 5 pattern; per-block exchange inside the sweep kernel over NVLink peer memory + NCCL per sweep)
+    row_sharded = None
+    if world > 1 and not args.no_e2e:
+        try:
+            Xd = Xh.to(dev)
+            g3 = bw.Genotypes(device=local, path=bw.PATH_BLOCKED)
+            g3.enable_row_sharding()
+            g3.set_stream(stream.cuda_stream)
+            g3.load(Xd)
+            st3 = bw.EmStepper(args.model, y, g3)
+            st3.sweeps(args.warmup)
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            st3.sweeps(args.steps)
+            r1.record(stream)
+            barrier()
+            t = torch.tensor([r0.elapsed_time(r1)], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rs_ms = float(t.item()) / args.steps
+            fit3 = st3.end()
+            g3.close()
+            row_sharded = {"workload": "ONE emRR fit, n=%d individuals sharded by rows over %d GPUs x p=%d" % (n * world, world, p),
+                           "ms_per_sweep": rs_ms, "marker_updates_per_s": p / (rs_ms * 1e-3),
+                           "genotype_GB_per_s_aggregate": n * world * p / (rs_ms * 1e-3) / 1e9,
+                           "frac_of_aggregate_hbm_peak": n * world * p / (rs_ms * 1e-3) / 1e9 / (hbm_peak * world),
+                           "collectives": "per 128-marker block: peer stores of the reduced partial X_B'E into every rank's ring inside the sweep kernel (NVLink); per sweep: ncclAllReduce of the Gram band and of 5 scalars",
+                           "h2": float(fit3["h2"])}
+        except Exception as ex:  # noqa: BLE001
+            row_sharded = {"error": str(ex)[:200]}
+
     if rank == 0:
         line = {"metric": "marker-updates/sec (emRR Gauss-Seidel sweep, n=50k x p=50k int8)", "value": value,
                 "unit": "marker-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -334,7 +366,7 @@ def main():
                            "l2": "genotypes are %.1f GB per sweep, far larger than the 126 MB L2: no flush needed" % (n * p / 1e9),
                            "parallelism": "1 GPU" if world == 1 else "%d independent replicas (one fit per GPU, no collective)" % world,
                            "seed": SEED},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "row_sharded": row_sharded, "gpu_launches": int(launches), "clocks": clocks,
                 "sweep_ms": ms / args.steps}
         print(json.dumps(line), flush=True)
     if world > 1:

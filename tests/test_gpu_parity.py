@@ -292,3 +292,18 @@ def test_mrr3_converged_and_options(tpod):
         assert ei.value.code == -5
         with pytest.raises(bw.BwgrError):
             bw.MRR3(Y, g, InnerGS=True)
+
+
+def test_row_sharded_fit_two_gpus():
+    """One fit sharded by rows over 2 GPUs (torchrun, one process per GPU) equals the single-GPU fit bit for bit: the
+    cross-GPU sums are integer sums.  Needs two visible GPUs (skipped on the single-GPU box)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "dist_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
