@@ -144,6 +144,8 @@ class Genotypes:
 
 def _store(gen, **kw):
     if isinstance(gen, Genotypes):
+        if gen.p == 0:  # same status and text as the C ABI gives for a call before bwgr_geno_load_*
+            raise _lib.BwgrError(-3, "no genotypes loaded")
         return gen, False
     return Genotypes(gen, **kw), True
 

@@ -307,3 +307,48 @@ def test_row_sharded_fit_two_gpus():
                         "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "dist_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DIST CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_error_paths_and_edges(tpod):
+    """Boundary behaviour of the C ABI: bad shapes / NaN / call order are errors with a message, never a silent fallback."""
+    y, gen = tpod
+    with bw.Genotypes(gen) as g:
+        yn = y.copy(); yn[7] = np.nan
+        with pytest.raises(bw.BwgrError) as ei:
+            bw.emRR(yn, g)
+        assert ei.value.code == -1 and "NaN" in str(ei.value)
+        with pytest.raises(bw.BwgrError):
+            bw.gibbs_fit("BayesB", y, g, it=10, bi=10)      # bi must be < it
+        with pytest.raises(bw.BwgrError):
+            bw.wgr(y, g, it=10, bi=0)                       # seq(bi, it, th) needs bi >= 1
+        out = bw.emRR(y, g, it=0)                            # zero sweeps: the initial state comes back
+        assert np.all(out["b"] == 0) and np.allclose(out["hat"], y.mean(), atol=1e-6) and out["its"] == 0
+    g = bw.Genotypes()
+    with pytest.raises(bw.BwgrError) as ei:
+        bw.emRR(y, g)                                        # no genotypes loaded
+    assert ei.value.code == -3
+    g.close()
+    with pytest.raises(bw.BwgrError):
+        bw.Genotypes(np.zeros((1, 5)))                       # n < 2
+    # ragged shapes through the blocked family: p < 128, p = 129, n not a multiple of 16
+    for n, p in ((50, 7), (333, 129), (1001, 260)):
+        X, yy = synth(n, p, seed=n)
+        ref = O.em("emRR", yy, X.astype(np.float32), it=6)
+        with bw.Genotypes(X, path=2) as gg:
+            o = bw.emRR(yy, gg, it=6)
+        assert np.abs(o["b"] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max(), (n, p)
+
+
+def test_signed_genotypes_blocked_path():
+    """General int8 genotypes (centred / negative codes): the kind::i8 Gram path and the limb products stay exact."""
+    rng = np.random.default_rng(4)
+    X = rng.integers(-3, 4, size=(900, 300)).astype(np.int8)
+    beta = np.zeros(300); beta[::17] = rng.normal(size=len(beta[::17]))
+    y = X @ beta + rng.normal(size=900) * 2.0
+    for model in ("emRR", "emBC"):
+        ref = O.em(model, y, X.astype(np.float32), it=10)
+        for path in (1, 2):
+            with bw.Genotypes(X, path=path) as g:
+                out = bw.em_fit(model, y, g, it=10)
+            assert np.abs(out["b"] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max(), (model, path)
+            assert abs(out["h2"] - ref["h2"]) <= RTOL
