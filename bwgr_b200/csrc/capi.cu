@@ -303,7 +303,7 @@ int finish_store(bwgr_handle* h, int storage) {
   if (h->fp8_codes && storage == BWGR_STORE_I8) {  // Gram shadow copy (only when every code is 0..2)
     const char* pe = getenv("BWGR_GRAM_PACKED");
     if (!(pe && !strcmp(pe, "0")) && h->x2g.alloc((size_t)(h->ld / 4) * h->p) == cudaSuccess) {
-      launch_pack_2bit(h->x8, h->ld, (int)h->n, (int)h->p, h->x2g.p, h->ld / 4, h->err.p, h->stream);
+      launch_pack_2bit_gram(h->x8, h->ld, (int)h->p, h->x2g.p, h->err.p, h->stream);
       h->launches++;
       int flag = 0;
       CU(cudaMemcpyAsync(&flag, h->err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));

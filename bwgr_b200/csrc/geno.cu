@@ -72,6 +72,31 @@ void launch_pack_2bit(const int8_t* src, int64_t ld, int n, int p, uint8_t* dst,
   dim3 grid((unsigned)((ldb + 255) / 256 > 64 ? 64 : (ldb + 255) / 256), p);
   pack_2bit_kernel<<<grid, 256, 0, st>>>(src, ld, n, dst, ldb, bad);
 }
+// Gram shadow copy: 16 rows per 32-bit word, interleaved so that the kernel expands it with one shift and one mask per
+// output word: the code of row 16g + 4q + k sits at bits [8k + 2q, 8k + 2q + 1], i.e. (w >> 2q) & 0x03030303 is the four
+// bytes of rows 4q .. 4q+3.  Codes must be 0..3 (else *bad).
+__global__ void pack_2bit_gram_kernel(const int8_t* __restrict__ src, int64_t ld, uint32_t* __restrict__ dst, int64_t ldw,
+                                      int* bad) {
+  const uint4* s = reinterpret_cast<const uint4*>(src + (int64_t)blockIdx.y * ld);
+  uint32_t* d = dst + (int64_t)blockIdx.y * ldw;
+  for (int64_t g = blockIdx.x * blockDim.x + threadIdx.x; g < ldw; g += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = s[g];  // rows 16g .. 16g+15 (pad rows are zero)
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+    uint32_t out = 0, any = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      any |= w4[q] & 0xFCFCFCFCu;
+      out |= (w4[q] & 0x03030303u) << (2 * q);
+    }
+    if (any) atomicExch(bad, 1);
+    d[g] = out;
+  }
+}
+void launch_pack_2bit_gram(const int8_t* src, int64_t ld, int p, uint8_t* dst, int* bad, cudaStream_t st) {
+  const int64_t ldw = ld / 16;
+  dim3 grid((unsigned)((ldw + 255) / 256 > 64 ? 64 : (ldw + 255) / 256), p);
+  pack_2bit_gram_kernel<<<grid, 256, 0, st>>>(src, ld, reinterpret_cast<uint32_t*>(dst), ldw, bad);
+}
 __global__ void unpack_2bit_kernel(const uint8_t* __restrict__ src, int64_t ldb, int n, int8_t* __restrict__ dst,
                                    int64_t ld) {
   const uint8_t* s = src + (int64_t)blockIdx.y * ldb;

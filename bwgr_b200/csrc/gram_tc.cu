@@ -9,8 +9,8 @@
 // Columns of a block are scattered in HBM when the order is shuffled (emRR & co, Rcpp20260726ai.cpp:331),
 // so the tile is gathered with 16-byte cp.async (8 consecutive lanes = one 128-byte line of one column).
 //
-// Warp roles (288 threads): warps 0-3 gather (cp.async producer), warp 4 issues the MMAs (one elected
-// lane) and owns the TMEM allocation, warps 5-8 drain the accumulator (tcgen05.ld -> st.global).
+// Warp roles (416 threads): warps 0-3 gather (cp.async producer; with the packed source warps 9-12 join them), warp 4
+// issues the MMAs (one elected lane) and owns the TMEM allocation, warps 5-8 drain the accumulator (tcgen05.ld -> st.global).
 // Two accumulator stages (2 x 128 TMEM columns) overlap the drain of block i with the MMAs of block i+1.
 // One CTA per SM, persistent over blocks.  HBM traffic: every genotype byte is read exactly once.
 #include <cuda.h>
@@ -131,7 +131,7 @@ struct GramSmem {
 };
 
 template <int NBAND, bool FP8, int PROD>
-__global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* __restrict__ perm, int nblocks,
+__global__ void __launch_bounds__(416, 1) gram_tc_kernel(GenoView g, const int* __restrict__ perm, int nblocks,
                                                          int32_t* __restrict__ gram, int out_f32, int* err,
                                                          const float* __restrict__ sx, float inv_n, int dbg,
                                                          const __grid_constant__ CUtensorMap tmap) {
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
   const int nkg = (nkt + GramCfg<NBAND>::kSub - 1) / GramCfg<NBAND>::kSub;  // stages per block
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; s++) { mbar_init(&S->full[s], PROD == 1 ? 1 : 128); mbar_init(&S->empty[s], 1); }
+    for (int s = 0; s < kStages; s++) { mbar_init(&S->full[s], PROD == 1 ? 1 : PROD == 2 ? 256 : 128); mbar_init(&S->empty[s], 1); }
     for (int s = 0; s < 2; s++) { mbar_init(&S->tmem_full[s], 1); mbar_init(&S->tmem_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -197,36 +197,39 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
         }
       }
     }
-  } else if (PROD == 2 && warp < 4) {
+  } else if (PROD == 2 && (warp < 4 || warp >= 9)) {
     // ===================== producer: 2-bit packed source (codes 0..3), expanded to bytes in flight =====================
     // The gather is what bounds this kernel (~4.3 TB/s of cp.async at 50k x 50k whatever the MMA kind); reading the packed
     // shadow copy moves 4x fewer bytes.  A 16-byte packed chunk = 64 rows of one marker = half a 128-row atom: it is
     // loaded into registers one stage ahead, expanded with two shift/mask steps per word and stored as four swizzled
     // 16-byte chunks.  Stage = kSub atoms, i.e. CPC = 2*kSub packed chunks per marker.
+    // Eight producer warps (0-3 and 9-12): the expansion, not the gather, is what this producer costs.
     constexpr int CPC = 2 * kSub;          // packed 16-byte chunks per marker per stage
-    constexpr int NLD = CPC * NBAND;       // loads per thread per stage (128 markers * CPC chunks / 128 threads, per band)
-    const int t = threadIdx.x;
-    const int c = t % CPC, m0 = t / CPC;   // this thread's chunk within the stage and its first marker; markers m0 + (128/CPC)*i
+    constexpr int NIT = CPC / 2;           // chunks per thread per band per stage (128 markers * CPC chunks / 256 threads)
+    constexpr int NLD = NIT * NBAND;
+    constexpr int MSTEP = 256 / CPC;       // marker stride between a thread's chunks
+    const int t = warp < 4 ? threadIdx.x : threadIdx.x - 160;  // 0..255
+    const int c = t % CPC, m0 = t / CPC;   // this thread's chunk within the stage and its first marker; markers m0 + MSTEP*i
     uint32_t it = 0;
     bool ok = true;
     uint4 cur[NLD], nxt[NLD];
-    auto load_stage = [&](const uint8_t* const (&colp)[NBAND][CPC], const bool (&val)[NBAND][CPC], int kg, uint4 (&dst)[NLD]) {
+    auto load_stage = [&](const uint8_t* const (&colp)[NBAND][NIT], const bool (&val)[NBAND][NIT], int kg, uint4 (&dst)[NLD]) {
 #pragma unroll
       for (int d = 0; d < NBAND; d++)
 #pragma unroll
-        for (int i = 0; i < CPC; i++) {
+        for (int i = 0; i < NIT; i++) {
           const int64_t off = ((int64_t)kg * CPC + c) * 16;  // byte offset inside the packed column
-          dst[d * CPC + i] = (val[d][i] && off < g.ldb) ? __ldg(reinterpret_cast<const uint4*>(colp[d][i] + off)) : make_uint4(0, 0, 0, 0);
+          dst[d * NIT + i] = (val[d][i] && off < g.ldb) ? __ldg(reinterpret_cast<const uint4*>(colp[d][i] + off)) : make_uint4(0, 0, 0, 0);
         }
     };
     for (int blk = blockIdx.x; blk < nblocks && ok; blk += gridDim.x) {
-      const uint8_t* colp[NBAND][CPC];
-      bool val[NBAND][CPC];
+      const uint8_t* colp[NBAND][NIT];
+      bool val[NBAND][NIT];
 #pragma unroll
       for (int d = 0; d < NBAND; d++)
 #pragma unroll
-        for (int i = 0; i < CPC; i++) {
-          const int m = m0 + (128 / CPC) * i;
+        for (int i = 0; i < NIT; i++) {
+          const int m = m0 + MSTEP * i;
           const int pos = (blk - d) * 128 + m;
           val[d][i] = pos >= 0 && pos < g.p;
           colp[d][i] = g.x2 + (int64_t)(val[d][i] ? perm[pos] : 0) * g.ldb;
@@ -241,23 +244,18 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
 #pragma unroll
         for (int d = 0; d < NBAND; d++)
 #pragma unroll
-          for (int i = 0; i < CPC; i++) {
-            const int m = m0 + (128 / CPC) * i;
-            const uint4 pk = cur[d * CPC + i];
+          for (int i = 0; i < NIT; i++) {
+            const int m = m0 + MSTEP * i;
+            const uint4 pk = cur[d * NIT + i];
             const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
             const uint32_t rowb = tbase + (sub * NBAND + d) * kTileBytes + m * 128;
 #pragma unroll
             for (int q = 0; q < 4; q++) {  // packed word q = rows 16q .. 16q+15 of the half atom = one 16-byte output chunk
-              uint32_t o[4];
-#pragma unroll
-              for (int bq = 0; bq < 4; bq++) {
-                const uint32_t b8 = (w4[q] >> (8 * bq)) & 0xFFu;         // four 2-bit codes
-                uint32_t x = (b8 | (b8 << 12)) & 0x000F000Fu;            // nibbles into the two halfwords
-                x = (x | (x << 6)) & 0x03030303u;                        // each nibble into two bytes
-                o[bq] = x;
-              }
+              // interleaved shadow layout (geno.cu): bytes of rows 4r .. 4r+3 = (w >> 2r) & 0x03030303
               const uint32_t oc = (uint32_t)(4 * (c & 1) + q);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((oc ^ ((uint32_t)m & 7u)) << 4)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((oc ^ ((uint32_t)m & 7u)) << 4)),
+                           "r"(w4[q] & 0x03030303u), "r"((w4[q] >> 2) & 0x03030303u), "r"((w4[q] >> 4) & 0x03030303u),
+                           "r"((w4[q] >> 6) & 0x03030303u) : "memory");
             }
           }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -362,7 +360,7 @@ __global__ void __launch_bounds__(288, 1) gram_tc_kernel(GenoView g, const int* 
       if (elect_one()) umma_commit(&S->tmem_full[as]);
       __syncwarp();
     }
-  } else {
+  } else if (warp <= 8) {
     // ===================== epilogue: TMEM -> registers -> HBM =====================
     const int quarter = warp & 3;  // TMEM lanes this warp may touch
     const int row = quarter * 32 + lane;
@@ -467,7 +465,7 @@ static void launch_gram_band(const GenoView& g, const int* perm, int nblocks, vo
 #define BWGR_GRAM_LAUNCH(PROD)                                                                                              \
   do {                                                                                                                      \
     cudaFuncSetAttribute(gram_tc_kernel<NBAND, FP8, PROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-    gram_tc_kernel<NBAND, FP8, PROD><<<grid, 288, smem, st>>>(g, perm, nblocks, out, out_f32, err, sx, inv_n, dbg, tm);     \
+    gram_tc_kernel<NBAND, FP8, PROD><<<grid, 416, smem, st>>>(g, perm, nblocks, out, out_f32, err, sx, inv_n, dbg, tm);     \
   } while (0)
   if (FP8 && g.x2 && !tmap) BWGR_GRAM_LAUNCH(2);   // packed 2-bit shadow copy: codes 0..2, exact E4M3 products
   else if (tmap) BWGR_GRAM_LAUNCH(1);

@@ -22,6 +22,8 @@ void launch_pack_f64(const double* src, int64_t ld_src, int n, int pc, int8_t* d
                      int* bad, cudaStream_t st);
 // int8 store -> 2-bit store (values must be in {0,1,2}; else *bad)
 void launch_pack_2bit(const int8_t* src, int64_t ld, int n, int p, uint8_t* dst, int64_t ldb, int* bad, cudaStream_t st);
+// packed shadow copy for the Gram kernel (interleaved 2-bit layout, see geno.cu); dst: ld/4 bytes per column
+void launch_pack_2bit_gram(const int8_t* src, int64_t ld, int p, uint8_t* dst, int* bad, cudaStream_t st);
 void launch_unpack_2bit(const uint8_t* src, int64_t ldb, int n, int p, int8_t* dst, int64_t ld, cudaStream_t st);
 void launch_check_range_i8(const int8_t* src, int64_t ld, int n, int p, int lo, int hi, int* bad, cudaStream_t st);
 // zero rows [n, ld) of every column
