@@ -134,6 +134,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
   unsigned long long v;
@@ -203,15 +204,17 @@ __host__ __device__ inline SLayout solver_layout(int ns, bool gibbs, bool use_in
   L.ms = o; o += (size_t)sring * ns * 128 * sizeof(MarkerSys);
   L.mc = o; o += (size_t)sring * 128 * sizeof(MarkerCol);
   L.drw = o; o += gibbs ? (size_t)sring * ns * 128 * sizeof(MarkerDraws) : 0;
-  L.tc = o; o += (size_t)ns * 128 * 4;                                   // cross-Gram correction
+  L.tc = o; o += (size_t)2 * ns * 128 * 4;                               // cross-Gram correction, double buffered by block parity
   L.dh = o; o += (size_t)ns * 128 * 4;                                   // dE of the block being solved
   L.prm = o; o += (size_t)2 * 128 * 4;  // unused (kept for alignment)
   L.rb = o; o += (size_t)kSolveWarps * 32 * 4;
-  L.cs = o; o += (size_t)32 * 2 * 4;  // running mean shift per system (centred columns): {current, before the last block}
+  L.cs = o; o += (size_t)32 * 2 * 4 + 2 * 4 * 4;  // running mean shift per system (centred columns): {current, before the last block}
   L.total = o;
   return L;
 }
 __host__ __device__ inline bool pipe_use_inv(int model, int ns) { return model_is_linear(model) && ns <= 2; }
+// one system, linear rule, uncentred columns: the four 32-marker steps of the in-block solve are spread over four warps
+__host__ __device__ inline bool pipe_wps4(int model, int ns, bool centred) { return model_is_linear(model) && ns == 1 && !centred; }
 
 template <int MODEL>
 __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
     mbar_init(&S.dl_full[0], 128); mbar_init(&S.dl_full[1], 128);
     mbar_init(&S.u_done, 1); mbar_init(&S.el_full, 128); mbar_init(&S.g_done, 1); mbar_init(&S.g_empty, 128);
     const int nsw = ns < kSolveWarps ? ns : kSolveWarps;
-    for (int i = 0; i < 3; i++) { mbar_init(&S.raw_ready[i], 128); mbar_init(&S.in_ready[i], 128); mbar_init(&S.solve_done[i], nsw); }
+    for (int i = 0; i < 3; i++) { mbar_init(&S.raw_ready[i], 128); mbar_init(&S.in_ready[i], 128); mbar_init(&S.solve_done[i], pipe_wps4(MODEL, ns, a.sx != nullptr) ? 4 : nsw); }
     for (int s = 0; s < 32; s++) {
       mbar_init(&S.corr_ready[s], 128);
       for (int d = 0; d < 4; d++) mbar_init(&S.de_ready[s][d], 1);
@@ -557,6 +560,7 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
   const int nsw = ns < kSolveWarps ? ns : kSolveWarps;
   __syncthreads();
   const bool tracing = a.trace != nullptr;
+#define SSTAMPW(blk, k) do { if (tracing && lane == 0) { long long* tp_ = a.trace + ((size_t)blockIdx.x * nblocks + (blk)) * 32 + (k); tp_[0] = (long long)gtimer(); tp_[16] = clock64(); } } while (0)
 #define SSTAMP(blk, k) do { if (tracing && warp == 0 && lane == 0) { long long* tp_ = a.trace + ((size_t)blockIdx.x * nblocks + (blk)) * 32 + (k); tp_[0] = (long long)gtimer(); tp_[16] = clock64(); } } while (0)
 
   if (warp < kSolveWarps) {
@@ -598,8 +602,142 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
         if (tracing && warp == kInvWarp0 && lane == 0) { long long* tp_ = a.trace + ((size_t)blockIdx.x * nblocks + nb) * 32 + 3; tp_[0] = (long long)gtimer(); tp_[16] = clock64(); }
       }
     }
+    const bool wps4 = pipe_wps4(MODEL, ns, centred);
+    if (wps4 && warp < 4) {
+      // ------------------------------------------------------------------ one system on four solve warps
+      // warp w owns markers 32w .. 32w+31 of the block (lane = marker).  Step d: warp d applies the inverse of its diagonal
+      // block (one 32x32 mat-vec through shared memory), the later warps subtract its contribution from their right-hand
+      // sides -- the dependent chain is 4 mat-vecs + 3 (hand-over + update) instead of 4 + 6 serial products on one warp.
+      const int w = warp;
+      float* mxs = cs + 64;  // [2][4] block maxima of |dE| per warp, double buffered by block parity
+      float* rbs = rb + w * 32;
+      for (int b = 0; b < nblocks; b++) {
+        const int nvalid = min(128, p - b * 128);
+        const int slot = b % sring;
+        const float* Gb = Gs + (size_t)slot * 10 * kTileF;
+        const MarkerCol* mc = mcol + slot * 128;
+        mbar_wait(&S.in_ready[slot], (uint32_t)(b / sring) & 1u, dead, a.err);
+        const SysScalars Sy = sc[0];
+        const MarkerSys* mk = msys + (size_t)slot * 128;
+        const MarkerDraws* drb = drw + (size_t)slot * 128;
+        const int jj = 32 * w + lane;
+        float g;
+        {
+          long long qq = 0;
+          uint32_t spins = 0;
+          if (a.world > 1) {
+            const unsigned long long gen = a.gen0 + (unsigned long long)b;
+            const unsigned long long tagx = tag_of(gen / kRing);
+            const unsigned long long* gx = a.hx[a.rank] + ((size_t)(gen % kRing) * a.world) * 128 + jj;
+            for (int src = 0; src < a.world; src++) {
+              unsigned long long wv = 0;
+              while (!dead) {
+                wv = ld_relaxed_sys_u64(gx + (size_t)src * 128);
+                if (__all_sync(0xffffffffu, word_ok(wv, tagx))) break;
+                if (++spins > kSpin || ((spins & 255u) == 255u && *reinterpret_cast<volatile int*>(a.err) != 0)) { dead = true; atomicCAS(a.err, 0, 3); }
+              }
+              qq += dead ? 0 : word_val(wv);
+            }
+          } else {
+            const unsigned long long* gq = a.hred + (size_t)(b % kRing) * 128 + jj;
+            const unsigned long long tagb = tag_of((unsigned long long)(b / kRing));
+            unsigned long long wv = 0;
+            while (!dead) {
+              wv = ld_relaxed_u64(gq);
+              if (__all_sync(0xffffffffu, word_ok(wv, tagb))) break;
+              if (++spins > kSpin || ((spins & 255u) == 255u && *reinterpret_cast<volatile int*>(a.err) != 0)) { dead = true; atomicCAS(a.err, 0, 3); }
+            }
+            qq = dead ? 0 : word_val(wv);
+          }
+          if (w == 0) SSTAMPW(b, 8);
+          g = (float)((double)qq * (double)Sy.e_q);
+        }
+        if (D > 0 && b > 0) {
+          mbar_wait(&S.corr_ready[0], (uint32_t)(b - 1) & 1u, dead, a.err);
+          g -= tcor[(b & 1) * ns * 128 + jj];
+        }
+        if (w == 0) SSTAMPW(b, 9);
+        const float av = mk[jj].a;
+        float r = fmaf(av, g, mk[jj].c), de = 0.0f;
+        if (Sy.done) {
+          dehist[jj] = 0.0f;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S.de_ready[0][w]);
+        } else {
+#pragma unroll
+          for (int d = 0; d < 4; d++) {
+            if (w == d) {
+              __syncwarp();
+              rbs[lane] = r;
+              __syncwarp();
+              const float* mt = Mt + ((size_t)slot * 4 + d) * 8 * kMS + 4 * lane;
+              float ac[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int k4 = 0; k4 < 8; k4++) {
+                const float4 mv = *reinterpret_cast<const float4*>(mt + k4 * kMS);
+                const float4 rv = *reinterpret_cast<const float4*>(rbs + 4 * k4);
+                ac[0] = fmaf(mv.x, rv.x, ac[0]); ac[1] = fmaf(mv.y, rv.y, ac[1]);
+                ac[2] = fmaf(mv.z, rv.z, ac[2]); ac[3] = fmaf(mv.w, rv.w, ac[3]);
+              }
+              de = (ac[0] + ac[1]) + (ac[2] + ac[3]);
+              dehist[jj] = de;
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&S.de_ready[0][d]);  // for the cross-Gram correction warps
+              named_bar_arrive(4 + d, 128);                    // hand-over to the later solve warps (hardware barrier: ~30 cycles)
+            } else if (w < d) {
+              named_bar_arrive(4 + d, 128);
+            } else {
+              named_bar(4 + d, 128);
+              const float* grow = Gb + (size_t)tri(w, d) * kTileF + lane * kTS;
+              const float* dv4 = dehist + 32 * d;
+              float fa[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int k4 = 0; k4 < 8; k4++) {
+                const float4 gv = *reinterpret_cast<const float4*>(grow + 4 * k4);
+                const float4 dv = *reinterpret_cast<const float4*>(dv4 + 4 * k4);
+                fa[0] = fmaf(gv.x, dv.x, fa[0]); fa[1] = fmaf(gv.y, dv.y, fa[1]);
+                fa[2] = fmaf(gv.z, dv.z, fa[2]); fa[3] = fmaf(gv.w, dv.w, fa[3]);
+              }
+              r = fmaf(-av, (fa[0] + fa[1]) + (fa[2] + fa[3]), r);
+            }
+          }
+        }
+        if (w == 3) SSTAMPW(b, 10);
+        // block maximum of |dE| over the four warps -> the fixed-point scale of the published step
+        float mx = fabsf(de);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) mxs[(b & 1) * 4 + w] = mx;
+        named_bar(3, 128);
+        mx = fmaxf(fmaxf(mxs[(b & 1) * 4 + 0], mxs[(b & 1) * 4 + 1]), fmaxf(mxs[(b & 1) * 4 + 2], mxs[(b & 1) * 4 + 3]));
+        int ex = 0;
+        if (mx > 0.0f && mx < 3.0e38f) frexpf(mx, &ex);
+        if (ex < -90) ex = -90;
+        const float dq = ldexpf(1.0f, ex - 30), dqinv = ldexpf(1.0f, 30 - ex);
+        if (!(mx < 3.0e38f)) atomicExch(a.err, 4);
+        unsigned long long* wv = a.dew + (size_t)b * kDewStride;
+        const bool valid = jj < nvalid && !Sy.done;
+        const int qv = valid ? __float2int_rn(de * dqinv) : 0;
+        st_relaxed_u64(wv + jj, ((unsigned long long)(uint32_t)qv << 32) | a.tag);
+        if (w == 3 && lane == 0) st_relaxed_u64(wv + 128, ((unsigned long long)__float_as_uint(dq) << 32) | a.tag);
+        if (w == 3) SSTAMPW(b, 11);
+        if (valid) {
+          const float deq = (float)qv * dq;  // the step actually applied to E (exactly representable)
+          const MarkerSys in = mk[jj];
+          const float bnew = fmaf(deq, (MODEL == M_EMBA) ? 0.5f : 1.0f, in.b0);
+          float vnew = in.vbj;
+          if (MODEL == M_EMBA) vnew = (Sy.Sb + bnew * bnew) / (Sy.df + 1.0f);
+          if (MODEL == M_BA) vnew = (Sy.Sb + bnew * bnew) / drb[jj].chi;
+          const int j = mc[jj].j;
+          a.b[j] = bnew;
+          if (model_has_vbj(MODEL) && a.vbv) a.vbv[j] = vnew;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.solve_done[slot]);
+      }
+    }
     // -------------------------------------------------------------------- solve warps (one system at a time)
-    if (warp < nsw) {
+    if (!wps4 && warp < nsw) {
       for (int b = 0; b < nblocks; b++) {
         const int nvalid = min(128, p - b * 128);
         const int slot = b % sring;
@@ -660,7 +798,7 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
           if (D > 0 && b > 0) {
             mbar_wait(&S.corr_ready[s], (uint32_t)(b - 1) & 1u, dead, a.err);
 #pragma unroll
-            for (int t = 0; t < 4; t++) g[t] -= tcor[s * 128 + 32 * t + lane];
+            for (int t = 0; t < 4; t++) g[t] -= tcor[((b & 1) * ns + s) * 128 + 32 * t + lane];
           }
           if (centred) {  // x_c'e_true = x'e_stored + c * sx with c as of the residual h_b was taken from
             const float cuse = cs[2 * s + ((D > 0 && b > 0) ? 1 : 0)];
@@ -872,7 +1010,8 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
               fa[2] = fmaf(cv[4 * k4 + 2], v.z, fa[2]); fa[3] = fmaf(cv[4 * k4 + 3], v.w, fa[3]);
             }
             const float part = (fa[0] + fa[1]) + (fa[2] + fa[3]);
-            if (d == 0) tcor[s * 128 + i] = part; else tcor[s * 128 + i] += part;
+            float* tc = tcor + (((b + 1) & 1) * ns + s) * 128 + i;  // buffer of block b+1 (a late solve warp may still read block b's)
+            if (d == 0) *tc = part; else *tc += part;
             if (d == 3) mbar_arrive(&S.corr_ready[s]);
           }
         };
@@ -980,6 +1119,7 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
 #undef PSTAMP
   }
 #undef SSTAMP
+#undef SSTAMPW
 }
 
 template <int MODEL>
