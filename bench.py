@@ -276,12 +276,13 @@ def main():
     sweep_ms = prof["sweep"]["ms"] / max(1, prof["sweep"]["launches"])
     gram_ms = prof["gram"]["ms"] / max(1, prof["gram"]["launches"])
     epi_ms = prof["epilogue"]["ms"] / max(1, prof["epilogue"]["launches"])
+    inv_ms = prof["block_inverse"]["ms"] / max(1, prof["block_inverse"]["launches"])
     dom = "sweep_pipe_kernel" if sweep_ms >= gram_ms else "gram_tc_kernel"
     dom_ms = max(sweep_ms, gram_ms)
     achieved = n * p / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": args.traffic if args.traffic is not None else ncu_traffic(dom, n, p), "kernel": dom, "peak_source": peak_src, "algorithmic_bytes_per_launch": n * p,
-                "kernel_ms": {"sweep_pipe_kernel": sweep_ms, "gram_tc_kernel": gram_ms, "epilogue_kernel": epi_ms},
+                "kernel_ms": {"sweep_pipe_kernel": sweep_ms, "gram_tc_kernel": gram_ms, "block_inverse_kernel": inv_ms, "epilogue_kernel": epi_ms},
                 "whole_sweep_frac": (n * p / (ms / args.steps * 1e-3) / 1e9) / hbm_peak}
     value = world * p * args.steps / (ms * 1e-3)
 

@@ -116,10 +116,10 @@ class Genotypes:
         check(self.lib.bwgr_profile(self.h, int(enable)))
 
     def profile_read(self):
-        ms = np.zeros(3)
-        cnt = np.zeros(3, dtype=np.int64)
+        ms = np.zeros(4)
+        cnt = np.zeros(4, dtype=np.int64)
         check(self.lib.bwgr_profile_read(self.h, _ptr(ms), _ptr(cnt)))
-        return {k: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, k in enumerate(("gram", "sweep", "epilogue"))}
+        return {k: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, k in enumerate(("gram", "sweep", "epilogue", "block_inverse"))}
 
     def launch_count(self):
         return int(self.lib.bwgr_launch_count(self.h))

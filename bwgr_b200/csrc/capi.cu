@@ -87,7 +87,8 @@ struct Fit {
   DevBuf<unsigned int> bar;
   // pipelined sweep (sweep_pipe.cu)
   bool pipe = false;
-  int lookahead = 0, nbuf = 0, sring = 2, nworkers = 0, nc = 1, nband = 1;
+  int lookahead = 0, nbuf = 0, sring = 2, nworkers = 0, nc = 1, nband = 1, full_inv = 0;
+  DevBuf<float> tinv;                   // (I + A L)^-1 of every block of the current sweep (block_inv.cu)
   uint32_t tag = 0;
   DevBuf<unsigned long long> dew, part;
   float* gram_p = nullptr;              // Gram band in use: f.gram (per fit) or the handle's natural-order cache
@@ -184,9 +185,9 @@ struct bwgr_handle {
   Fit fit;
   // optional per-kernel timing (bwgr_profile)
   bool profiling = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[3];
-  double prof_ms[3] = {0, 0, 0};
-  int64_t prof_n[3] = {0, 0, 0};
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[4];  // gram, sweep, epilogue, block inverses
+  double prof_ms[4] = {0, 0, 0, 0};
+  int64_t prof_n[4] = {0, 0, 0, 0};
   cudaEvent_t prof_begin(int cls) {
     if (!profiling) return nullptr;
     cudaEvent_t a, b;
@@ -197,7 +198,7 @@ struct bwgr_handle {
   }
   void prof_end(cudaEvent_t b) { if (b) cudaEventRecord(b, stream); }
   void prof_collect() {
-    for (int c = 0; c < 3; c++) {
+    for (int c = 0; c < 4; c++) {
       for (auto& pr : prof_ev[c]) {
         float ms = 0;
         cudaEventSynchronize(pr.second);
@@ -516,7 +517,7 @@ struct FitSpec {
 
 // Geometry of the pipelined sweep: W streaming CTAs (row slabs of R rows, R <= 512) + one solver CTA, look-ahead D,
 // nbuf X tiles per worker.  False if the shape does not fit one SM's shared memory / TMEM.
-struct PipePlan { int R, W, nbuf, D, sring; };
+struct PipePlan { int R, W, nbuf, D, sring, full_inv; };
 bool plan_pipe(const bwgr_handle* h, int model, int ns, PipePlan* pl) {
   const char* sw = getenv("BWGR_SWEEP");
   if (sw && !strcmp(sw, "v4")) return false;
@@ -533,10 +534,17 @@ bool plan_pipe(const bwgr_handle* h, int model, int ns, PipePlan* pl) {
   int D = la ? atoi(la) : 1;
   if (D < 0 || h->gram_simt) D = 0;
   if (D > 1) D = 1;
+  // one linear system: the in-block solve applies the precomputed block inverse (block_inv.cu); BWGR_TINV=0 keeps the
+  // four dependent 32-marker steps.  (MRR3's centred systems keep the stepwise solve.)
+  const char* ti = getenv("BWGR_TINV");
+  const int full_inv = model_is_linear(model) && ns == 1 && model != M_MRR && !(ti && !strcmp(ti, "0"));
   for (; D >= 0; D--) {
     for (int sring = 3; sring >= 2; sring--)
       for (int nbuf = std::min(8, D + 3); nbuf >= D + 1; nbuf--)
-        if (sweep_pipe_smem(R, ns, model, nbuf, sring) <= h->smem_optin - 8192) { pl->R = R; pl->W = W; pl->nbuf = nbuf; pl->D = D; pl->sring = sring; return true; }
+        if (sweep_pipe_smem(R, ns, model, nbuf, sring, full_inv) <= h->smem_optin - 8192) {
+          pl->R = R; pl->W = W; pl->nbuf = nbuf; pl->D = D; pl->sring = sring; pl->full_inv = full_inv;
+          return true;
+        }
   }
   return false;
 }
@@ -807,7 +815,7 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
       if (rc) return rc;
     }
     if (f.pipe) {
-      f.rows_per_cta = pl.R; f.nworkers = pl.W; f.grid = pl.W + 1; f.nbuf = pl.nbuf; f.sring = pl.sring; f.lookahead = pl.D; f.nband = pl.D + 1;
+      f.rows_per_cta = pl.R; f.nworkers = pl.W; f.grid = pl.W + 1; f.nbuf = pl.nbuf; f.sring = pl.sring; f.lookahead = pl.D; f.full_inv = pl.full_inv; f.nband = pl.D + 1;
       f.nc = std::max(1, 16 / ns);
       f.tag = 0;
       const size_t gram_n = (size_t)f.nblocks * kBlk * kBlk * f.nband;
@@ -823,6 +831,8 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
         if (f.gram.alloc(gram_n) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(Gram band) failed");
         f.gram_p = f.gram.p;
       }
+      if (f.full_inv && f.tinv.alloc((size_t)f.nblocks * kBlk * kBlk) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(block inverses) failed");
+      if (!f.full_inv) f.tinv.release();
       if (
           f.part.alloc((size_t)8 * ns * 128 * 161) != cudaSuccess || f.dew.alloc((size_t)f.nblocks * ns * 136) != cudaSuccess)
         return fail(BWGR_ERR_CUDA, "cudaMalloc(blocked workspace) failed");
@@ -888,11 +898,18 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
         if (h->world > 1)  // row shards: the Gram band is a sum over individuals (exact: integers below 2^24 in fp32)
           NC(nccl().AllReduce(f.gram_p, f.gram_p, (size_t)f.nblocks * kBlk * kBlk * f.nband, ncclFloat, ncclSum, h->comm, h->stream));
       }
+      if (f.pipe && f.full_inv) {  // the step coefficients change every sweep (lambda), the inverses with them
+        cudaEvent_t pi = h->prof_begin(3);
+        launch_block_inverse(f.model, d_perm, (int)p, f.nblocks, f.gram_p, f.nband, f.xx_over.p ? f.xx_over.p : h->xx_f.p, f.vbv.p, f.sc.p,
+                             f.tinv.p, h->stream);
+        h->prof_end(pi);
+        h->launches++;
+      }
       if (f.pipe) {
         CU(cudaMemsetAsync(f.part.p, 0, sizeof(unsigned long long) * f.part.n, h->stream));
         PipeArgs a;
         memset(&a, 0, sizeof a);
-        a.g = g; a.model = f.model; a.nsys = f.nsys; a.perm = d_perm; a.nblocks = f.nblocks; a.gram = f.gram_p; a.nband = f.nband;
+        a.g = g; a.model = f.model; a.nsys = f.nsys; a.perm = d_perm; a.nblocks = f.nblocks; a.gram = f.gram_p; a.nband = f.nband; a.tinv = f.full_inv ? f.tinv.p : nullptr;
         a.e = f.e.p; a.b = f.b.p; a.d = f.d.p; a.vbv = f.vbv.p; a.xx = f.xx_over.p ? f.xx_over.p : h->xx_f.p; a.sx = f.sx_dev.p; a.cshift = f.cshift.p; a.sc = f.sc.p;
         a.part = f.part.p; a.hred = f.part.p + (size_t)8 * f.nsys * 128 * 160; a.dew = f.dew.p; a.tag = ++f.tag;
         a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0;
@@ -1700,7 +1717,7 @@ int bwgr_dist_connect(bwgr_handle* h, const void* ipc_all) {
 int bwgr_profile(bwgr_handle* h, int enable) {
   if (!h) return fail(BWGR_ERR_ARG, "null handle");
   h->prof_collect();
-  if (enable) { for (int c = 0; c < 3; c++) { h->prof_ms[c] = 0; h->prof_n[c] = 0; } }
+  if (enable) { for (int c = 0; c < 4; c++) { h->prof_ms[c] = 0; h->prof_n[c] = 0; } }
   h->profiling = enable != 0;
   return 0;
 }
@@ -1708,7 +1725,7 @@ int bwgr_profile_read(bwgr_handle* h, double* ms, int64_t* counts) {
   if (!h) return fail(BWGR_ERR_ARG, "null handle");
   CU(cudaStreamSynchronize(h->stream));
   h->prof_collect();
-  for (int c = 0; c < 3; c++) { if (ms) ms[c] = h->prof_ms[c]; if (counts) counts[c] = h->prof_n[c]; }
+  for (int c = 0; c < 4; c++) { if (ms) ms[c] = h->prof_ms[c]; if (counts) counts[c] = h->prof_n[c]; }
   return 0;
 }
 

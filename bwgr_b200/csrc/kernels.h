@@ -115,6 +115,7 @@ struct PipeArgs {
   int nblocks;
   const float* gram;     // [nblocks][128][nband*128] Gram band as float (exact below 2^24)
   int nband;
+  const float* tinv;     // [nblocks][128][128] (I + A L)^-1 of every block (block_inv.cu; one linear system), or nullptr
   float* e;              // [nsys][ld]
   float* b; float* d; float* vbv;  // [nsys][p]
   const float* xx;       // [p]
@@ -142,7 +143,10 @@ struct PipeArgs {
   long long* trace;      // optional [nblocks][16] clock64 stamps (BWGR_TRACE), else nullptr
 };
 void launch_sweep_pipe(const PipeArgs& a, cudaStream_t st);
-size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring);
+size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring, int full_inv);
+// T_b = (I + A_b L_b)^-1 for every 128-marker block of the sweep (linear rules, one system): [nblocks][128][128] float
+void launch_block_inverse(int model, const int* perm, int p, int nblocks, const float* gram, int nband, const float* xx,
+                          const float* vbv, const SysScalars* sc, float* tinv, cudaStream_t st);
 
 // Sweep epilogue (both paths use the same arithmetic): reductions + hyper-parameter update +
 // e -= mean(e). One CTA per system.

@@ -541,7 +541,8 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
   // into four per-marker numbers one block ahead, and the Bernoulli(pj) draw u < 1/(1 + R exp(x)) is taken as
   // x < log((1/u - 1)/R): the dependent chain per marker is one shuffle, five FMAs and a compare (no exp, no division).
   constexpr bool kSlabDraw = MODEL == M_BB || MODEL == M_BC || MODEL == M_KMUP;
-  const bool use_inv = pipe_use_inv(MODEL, ns);
+  const bool full_inv = a.tinv != nullptr;  // T = (I + A L)^-1 of every block precomputed (block_inv.cu)
+  const bool use_inv = !full_inv && pipe_use_inv(MODEL, ns);
   const int sring = a.sring;
   const SLayout L = solver_layout(ns, kGibbs, use_inv, sring);
   float* Gs = reinterpret_cast<float*>(base + L.gs);
@@ -661,6 +662,30 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
         float r = fmaf(av, g, mk[jj].c), de = 0.0f;
         if (Sy.done) {
           dehist[jj] = 0.0f;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S.de_ready[0][w]);
+        } else if (full_inv) {
+          // dE = T r: all right-hand sides through shared memory, then every warp takes its 32 rows of the lower-triangular
+          // product at once -- no dependent 32-marker steps left in the chain
+          rb[jj] = r;
+          named_bar(4, 128);
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            if (t <= w) {
+              const float* trow = Gb + (size_t)tri(w, t) * kTileF + lane * kTS;
+              const float* rv4 = rb + 32 * t;
+              float fa[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int k4 = 0; k4 < 8; k4++) {
+                const float4 tv = *reinterpret_cast<const float4*>(trow + 4 * k4);
+                const float4 rv = *reinterpret_cast<const float4*>(rv4 + 4 * k4);
+                fa[0] = fmaf(tv.x, rv.x, fa[0]); fa[1] = fmaf(tv.y, rv.y, fa[1]);
+                fa[2] = fmaf(tv.z, rv.z, fa[2]); fa[3] = fmaf(tv.w, rv.w, fa[3]);
+              }
+              de += (fa[0] + fa[1]) + (fa[2] + fa[3]);
+            }
+          }
+          dehist[jj] = de;
           __syncwarp();
           if (lane == 0) mbar_arrive(&S.de_ready[0][w]);
         } else {
@@ -1049,14 +1074,16 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
       // the scalar chain reads the transposed triangle, stored in the same slots
       {
         float* Gb = Gs + (size_t)slot * 10 * kTileF;
-        const float* src = a.gram + (size_t)nb * 128 * gstride;
+        // with the precomputed block inverse the solver needs T_b (lower triangle), not the Gram block itself
+        const int tstride = full_inv ? 128 : gstride;
+        const float* src = full_inv ? a.tinv + (size_t)nb * 128 * 128 : a.gram + (size_t)nb * 128 * gstride;
 #pragma unroll
         for (int it = 0; it < 20; it++) {
           constexpr int kHi[10] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3}, kLo[10] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3};
           const int tile = it >> 1, rr = rr0 + 16 * (it & 1);
           const int hi = kHi[tile], lo = kLo[tile];
           const int grow_ = kLinear ? 32 * hi + rr : 32 * lo + rr, gcol = kLinear ? 32 * lo + 4 * c4 : 32 * hi + 4 * c4;
-          cp_async16(smem_u32(Gb + (size_t)tile * kTileF + rr * kTS + 4 * c4), src + (size_t)grow_ * gstride + gcol, 16u);
+          cp_async16(smem_u32(Gb + (size_t)tile * kTileF + rr * kTS + 4 * c4), src + (size_t)grow_ * tstride + gcol, 16u);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
@@ -1133,14 +1160,14 @@ void launch_model(const PipeArgs& a, size_t smem, cudaStream_t st) {
 }  // namespace
 
 // Shared memory of one CTA (both roles use the same launch) and the largest tile ring that fits.
-size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring) {
+size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring, int full_inv) {
   const size_t w = worker_layout(rows_per_cta, nsys, nbuf).total;
-  const size_t s = solver_layout(nsys, model_is_gibbs(model), pipe_use_inv(model, nsys), sring).total;
+  const size_t s = solver_layout(nsys, model_is_gibbs(model), !full_inv && pipe_use_inv(model, nsys), sring).total;
   return (w > s ? w : s) + 1024;
 }
 
 void launch_sweep_pipe(const PipeArgs& a, cudaStream_t st) {
-  const size_t smem = sweep_pipe_smem(a.rows_per_cta, a.nsys, a.model, a.nbuf, a.sring);
+  const size_t smem = sweep_pipe_smem(a.rows_per_cta, a.nsys, a.model, a.nbuf, a.sring, a.tinv != nullptr);
   switch (a.model) {
     case M_EMRR: launch_model<M_EMRR>(a, smem, st); break;
     case M_EMBA: launch_model<M_EMBA>(a, smem, st); break;

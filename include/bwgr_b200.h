@@ -171,7 +171,7 @@ BWGR_API int bwgr_dist_connect(bwgr_handle* h, const void* ipc_handles_all /* wo
 /* Kernels launched by this handle since creation (the bench's gpu_launches claim). */
 BWGR_API int64_t bwgr_launch_count(bwgr_handle* h);
 /* Per-kernel device timing for the roofline report: when enabled, CUDA events bracket every kernel
- * of the sweep loop on the handle's stream. read: ms[3] / counts[3] = {gram, sweep, epilogue} summed
+ * of the sweep loop on the handle's stream. read: ms[4] / counts[4] = {gram, sweep, epilogue, block inverses} summed
  * since enable (synchronises the stream). */
 BWGR_API int bwgr_profile(bwgr_handle* h, int enable);
 BWGR_API int bwgr_profile_read(bwgr_handle* h, double* ms, int64_t* counts);
