@@ -630,15 +630,20 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
             const unsigned long long gen = a.gen0 + (unsigned long long)b;
             const unsigned long long tagx = tag_of(gen / kRing);
             const unsigned long long* gx = a.hx[a.rank] + ((size_t)(gen % kRing) * a.world) * 128 + jj;
-            for (int src = 0; src < a.world; src++) {
-              unsigned long long wv = 0;
-              while (!dead) {
-                wv = ld_relaxed_sys_u64(gx + (size_t)src * 128);
-                if (__all_sync(0xffffffffu, word_ok(wv, tagx))) break;
-                if (++spins > kSpin || ((spins & 255u) == 255u && *reinterpret_cast<volatile int*>(a.err) != 0)) { dead = true; atomicCAS(a.err, 0, 3); }
+            // the words of all ranks in flight at once (one NVLink-written L2 round trip, not `world` of them)
+            unsigned long long wv[8];
+            while (!dead) {
+              bool ok = true;
+#pragma unroll
+              for (int src = 0; src < 8; src++) {
+                wv[src] = src < a.world ? ld_relaxed_sys_u64(gx + (size_t)src * 128) : tagx;
+                ok = ok && word_ok(wv[src], tagx);
               }
-              qq += dead ? 0 : word_val(wv);
+              if (__all_sync(0xffffffffu, ok)) break;
+              if (++spins > kSpin || ((spins & 255u) == 255u && *reinterpret_cast<volatile int*>(a.err) != 0)) { dead = true; atomicCAS(a.err, 0, 3); }
             }
+#pragma unroll
+            for (int src = 0; src < 8; src++) qq += dead ? 0 : word_val(wv[src]);  // tag-only filler words carry value 0
           } else {
             const unsigned long long* gq = a.hred + (size_t)(b % kRing) * 128 + jj;
             const unsigned long long tagb = tag_of((unsigned long long)(b / kRing));
