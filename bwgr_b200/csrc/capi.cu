@@ -312,6 +312,7 @@ int finish_store(bwgr_handle* h, int storage) {
       if (flag) { CU(cudaMemsetAsync(h->err.p, 0, sizeof(int), h->stream)); h->x2g.release(); }  // a code 3..7: keep the int8 gather
     }
   }
+  CU(cudaGetLastError());  // a store kernel that failed to launch must not go unnoticed
   h->storage = BWGR_STORE_I8;
   if (storage == BWGR_STORE_2BIT) {
     h->ldb = h->ld / 4;

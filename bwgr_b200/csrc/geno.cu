@@ -8,10 +8,10 @@ namespace bwgr {
 
 __global__ void pack_f64_kernel(const double* __restrict__ src, int64_t ld_src, int n, int pc, int8_t* __restrict__ dst,
                                 int64_t ld, int lo, int hi, int* bad) {
-  const int j = blockIdx.y;
+  const int j = blockIdx.x;
   const double* s = src + (int64_t)j * ld_src;
   int8_t* d = dst + (int64_t)j * ld;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ld; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < ld; i += gridDim.y * blockDim.x) {
     int8_t v = 0;
     if (i < n) {
       const double x = s[i];
@@ -24,19 +24,19 @@ __global__ void pack_f64_kernel(const double* __restrict__ src, int64_t ld_src, 
 }
 void launch_pack_f64(const double* src, int64_t ld_src, int n, int pc, int8_t* dst, int64_t ld, int lo, int hi, int* bad,
                      cudaStream_t st) {
-  dim3 grid((unsigned)((ld + 1023) / 1024 > 64 ? 64 : (ld + 1023) / 1024), pc);
+  dim3 grid((unsigned)pc, (unsigned)((ld + 1023) / 1024 > 64 ? 64 : (ld + 1023) / 1024));  // columns on x (p can exceed the 65,535 limit of y)
   pack_f64_kernel<<<grid, 256, 0, st>>>(src, ld_src, n, pc, dst, ld, lo, hi, bad);
 }
 
 __global__ void check_range_kernel(const int8_t* __restrict__ src, int64_t ld, int n, int lo, int hi, int* bad) {
-  const int8_t* s = src + (int64_t)blockIdx.y * ld;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  const int8_t* s = src + (int64_t)blockIdx.x * ld;
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
     const int v = s[i];
     if (v < lo || v > hi) atomicExch(bad, 1);
   }
 }
 void launch_check_range_i8(const int8_t* src, int64_t ld, int n, int p, int lo, int hi, int* bad, cudaStream_t st) {
-  dim3 grid((unsigned)((n + 1023) / 1024 > 64 ? 64 : (n + 1023) / 1024), p);
+  dim3 grid((unsigned)p, (unsigned)((n + 1023) / 1024 > 64 ? 64 : (n + 1023) / 1024));  // columns on x (p can exceed the 65,535 limit of y)
   check_range_kernel<<<grid, 256, 0, st>>>(src, ld, n, lo, hi, bad);
 }
 
@@ -51,9 +51,9 @@ void launch_zero_pad(int8_t* x, int64_t ld, int n, int p, cudaStream_t st) {
 // 2-bit packing: byte k of a column holds rows 4k..4k+3, row r in bits 2*(r%4).
 __global__ void pack_2bit_kernel(const int8_t* __restrict__ src, int64_t ld, int n, uint8_t* __restrict__ dst,
                                  int64_t ldb, int* bad) {
-  const int8_t* s = src + (int64_t)blockIdx.y * ld;
-  uint8_t* d = dst + (int64_t)blockIdx.y * ldb;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < ldb; k += gridDim.x * blockDim.x) {
+  const int8_t* s = src + (int64_t)blockIdx.x * ld;
+  uint8_t* d = dst + (int64_t)blockIdx.x * ldb;
+  for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < ldb; k += gridDim.y * blockDim.x) {
     uint32_t byte = 0;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -69,7 +69,7 @@ __global__ void pack_2bit_kernel(const int8_t* __restrict__ src, int64_t ld, int
   }
 }
 void launch_pack_2bit(const int8_t* src, int64_t ld, int n, int p, uint8_t* dst, int64_t ldb, int* bad, cudaStream_t st) {
-  dim3 grid((unsigned)((ldb + 255) / 256 > 64 ? 64 : (ldb + 255) / 256), p);
+  dim3 grid((unsigned)p, (unsigned)((ldb + 255) / 256 > 64 ? 64 : (ldb + 255) / 256));  // columns on x (p can exceed the 65,535 limit of y)
   pack_2bit_kernel<<<grid, 256, 0, st>>>(src, ld, n, dst, ldb, bad);
 }
 // Gram shadow copy: 16 rows per 32-bit word, interleaved so that the kernel expands it with one shift and one mask per
@@ -77,9 +77,9 @@ void launch_pack_2bit(const int8_t* src, int64_t ld, int n, int p, uint8_t* dst,
 // bytes of rows 4q .. 4q+3.  Codes must be 0..3 (else *bad).
 __global__ void pack_2bit_gram_kernel(const int8_t* __restrict__ src, int64_t ld, uint32_t* __restrict__ dst, int64_t ldw,
                                       int* bad) {
-  const uint4* s = reinterpret_cast<const uint4*>(src + (int64_t)blockIdx.y * ld);
-  uint32_t* d = dst + (int64_t)blockIdx.y * ldw;
-  for (int64_t g = blockIdx.x * blockDim.x + threadIdx.x; g < ldw; g += (int64_t)gridDim.x * blockDim.x) {
+  const uint4* s = reinterpret_cast<const uint4*>(src + (int64_t)blockIdx.x * ld);
+  uint32_t* d = dst + (int64_t)blockIdx.x * ldw;
+  for (int64_t g = blockIdx.y * blockDim.x + threadIdx.x; g < ldw; g += (int64_t)gridDim.y * blockDim.x) {
     const uint4 v = s[g];  // rows 16g .. 16g+15 (pad rows are zero)
     const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
     uint32_t out = 0, any = 0;
@@ -94,18 +94,18 @@ __global__ void pack_2bit_gram_kernel(const int8_t* __restrict__ src, int64_t ld
 }
 void launch_pack_2bit_gram(const int8_t* src, int64_t ld, int p, uint8_t* dst, int* bad, cudaStream_t st) {
   const int64_t ldw = ld / 16;
-  dim3 grid((unsigned)((ldw + 255) / 256 > 64 ? 64 : (ldw + 255) / 256), p);
+  dim3 grid((unsigned)p, (unsigned)((ldw + 255) / 256 > 64 ? 64 : (ldw + 255) / 256));  // columns on x (p can exceed the 65,535 limit of y)
   pack_2bit_gram_kernel<<<grid, 256, 0, st>>>(src, ld, reinterpret_cast<uint32_t*>(dst), ldw, bad);
 }
 __global__ void unpack_2bit_kernel(const uint8_t* __restrict__ src, int64_t ldb, int n, int8_t* __restrict__ dst,
                                    int64_t ld) {
-  const uint8_t* s = src + (int64_t)blockIdx.y * ldb;
-  int8_t* d = dst + (int64_t)blockIdx.y * ld;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < ld; r += gridDim.x * blockDim.x)
+  const uint8_t* s = src + (int64_t)blockIdx.x * ldb;
+  int8_t* d = dst + (int64_t)blockIdx.x * ld;
+  for (int r = blockIdx.y * blockDim.x + threadIdx.x; r < ld; r += gridDim.y * blockDim.x)
     d[r] = (r < n) ? (int8_t)((s[r >> 2] >> (2 * (r & 3))) & 3) : (int8_t)0;
 }
 void launch_unpack_2bit(const uint8_t* src, int64_t ldb, int n, int p, int8_t* dst, int64_t ld, cudaStream_t st) {
-  dim3 grid((unsigned)((ld + 1023) / 1024 > 64 ? 64 : (ld + 1023) / 1024), p);
+  dim3 grid((unsigned)p, (unsigned)((ld + 1023) / 1024 > 64 ? 64 : (ld + 1023) / 1024));  // columns on x (p can exceed the 65,535 limit of y)
   unpack_2bit_kernel<<<grid, 256, 0, st>>>(src, ldb, n, dst, ld);
 }
 

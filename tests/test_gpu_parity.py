@@ -352,3 +352,20 @@ def test_signed_genotypes_blocked_path():
                 out = bw.em_fit(model, y, g, it=10)
             assert np.abs(out["b"] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max(), (model, path)
             assert abs(out["h2"] - ref["h2"]) <= RTOL
+
+
+def test_more_markers_than_grid_y_limit():
+    """p > 65,535 (the grid.y limit of CUDA): store kernels index columns on grid.x; pack / statistics / a short fit agree
+    with numpy and the oracle on a wide, short matrix (both stores, both kernel families)."""
+    rng = np.random.default_rng(8)
+    n, p = 64, 70001
+    X = rng.integers(0, 3, size=(n, p)).astype(np.int8)
+    y = rng.normal(size=n)
+    ref = O.em("emRR", y, X.astype(np.float32), it=2)
+    for storage, path in ((0, 2), (0, 1), (1, 1)):
+        with bw.Genotypes(X, storage=storage, path=path) as g:
+            assert np.array_equal(g.unpack(), X)
+            xx, sx = g.stats()
+            assert np.array_equal(xx, (X.astype(np.int64) ** 2).sum(0)) and np.array_equal(sx, X.astype(np.int64).sum(0))
+            out = bw.emRR(y, g, it=2)
+        assert np.abs(out["b"] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max(), (storage, path)
