@@ -369,3 +369,22 @@ def test_more_markers_than_grid_y_limit():
             assert np.array_equal(xx, (X.astype(np.int64) ** 2).sum(0)) and np.array_equal(sx, X.astype(np.int64).sum(0))
             out = bw.emRR(y, g, it=2)
         assert np.abs(out["b"] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max(), (storage, path)
+
+
+@pytest.mark.parametrize("k", [2, 3, 5])
+def test_blocked_family_multi_system(k):
+    """k unmasked systems sharing the genotypes on the pipelined blocked sweep: k = 2 takes the 32x32-inverse solve, k >= 3 the
+    in-warp substitution (linear rules) / one scalar chain per solve warp (spike-slab); each column equals its own fit."""
+    X, Y = synth(900, 500, k=k, seed=31)
+    with bw.Genotypes(X, path=2) as g:
+        for model in ("emRR", "emBC", "emBA"):
+            out = bw.em_fit(model, Y, g, it=8)
+            for t in range(k):
+                ref = O.em(model, Y[:, t], X.astype(np.float32), it=8)
+                assert np.abs(out["b"][:, t] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max(), (model, k, t)
+                assert abs(out["h2"][t] - ref["h2"]) <= RTOL, (model, k, t)
+        chains = bw.gibbs_fit("BayesC", Y[:, 0], g, it=60, bi=10, nchains=k, seed=5)
+        assert chains["b"].shape == (500, k) and np.isfinite(chains["b"]).all()
+        assert np.ptp(chains["h2"]) > 0  # the chains use different Philox streams
+        one = bw.gibbs_fit("BayesC", Y[:, 0], g, it=60, bi=10, nchains=1, seed=5)
+        assert np.allclose(chains["b"][:, 0], one["b"], rtol=0, atol=1e-6 * np.abs(one["b"]).max() + 1e-12)  # chain 0 = the single chain
