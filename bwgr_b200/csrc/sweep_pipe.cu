@@ -18,8 +18,10 @@
 //   round trips off the critical path; the cross Gram block comes from gram_tc.cu, band 2), runs the
 //   in-block sequential solve on the Gram block X_b'X_b and publishes dE_b as 64-bit self-validating words
 //   (int32 fixed-point step | launch tag).  Linear rules (emRR, emBA, BayesRR, BayesA, rotated MRR3) are a
-//   unit-lower-triangular system solved in 32-marker blocks (32x32 inverses computed one block ahead, or an
-//   in-warp substitution when many systems share the SM); the other rules walk the scalar chain.
+//   unit-lower-triangular system: one system applies the block inverse precomputed by block_inv.cu as a single
+//   lower-triangular mat-vec on four warps; two systems step through 32-marker blocks with 32x32 inverses computed
+//   one block ahead; more systems use an in-warp substitution.  The other rules walk the scalar chain.
+//   Row-sharded fits (several GPUs): the reduced partial of a rank is stored into every peer's exchange ring (NVLink).
 //   Either way the result is the reference's Gauss-Seidel order up to float reassociation.
 //
 // Critical path per block with D = 1: cross-Gram correction + in-block solve.  Everything else (gather,
@@ -38,7 +40,6 @@ constexpr int kTileF = 32 * kTS;       // floats per Gram tile
 constexpr int kMS = 132;               // k/4 stride of a 32x32 inverse
 constexpr int kSolveWarps = 8, kInvWarp0 = 4, kCorrWarp0 = 8, kPreWarp0 = 12;
 constexpr int kDewStride = 136;        // 64-bit words per (block, system) of the published step
-constexpr int kLag = 2;
 constexpr int kRing = 8;               // blocks of partial / reduced h kept in flight (ring in L2)
 constexpr int kWPad = 160;             // worker slots per (block, system, marker) row of the partials
 constexpr int kRedWarp = 9;            // worker warp that reduces its share of the partials
@@ -153,9 +154,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
 __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 // Self-validating 64-bit words of the grid reduction: (signed value << 12) | tag, tag = 1 + (use index of the ring slot) mod 4095
 // (never 0 = freshly zeroed memory; consecutive uses of a slot always differ).  |value| < 2^51: a rank's sum of 143 worker
@@ -194,7 +192,7 @@ __host__ __device__ inline WLayout worker_layout(int R, int ns, int nbuf) {
   L.total = o;
   return L;
 }
-struct SLayout { size_t gs, mt, ms, mc, drw, tc, dh, prm, rb, cs, total; };
+struct SLayout { size_t gs, mt, ms, mc, drw, tc, dh, rb, cs, total; };
 // sring = blocks of solve inputs in flight in the solver CTA (2 or 3)
 __host__ __device__ inline SLayout solver_layout(int ns, bool gibbs, bool use_inv, int sring) {
   SLayout L;
@@ -206,7 +204,6 @@ __host__ __device__ inline SLayout solver_layout(int ns, bool gibbs, bool use_in
   L.drw = o; o += gibbs ? (size_t)sring * ns * 128 * sizeof(MarkerDraws) : 0;
   L.tc = o; o += (size_t)2 * ns * 128 * 4;                               // cross-Gram correction, double buffered by block parity
   L.dh = o; o += (size_t)ns * 128 * 4;                                   // dE of the block being solved
-  L.prm = o; o += (size_t)2 * 128 * 4;  // unused (kept for alignment)
   L.rb = o; o += (size_t)kSolveWarps * 32 * 4;
   L.cs = o; o += (size_t)32 * 2 * 4 + 2 * 4 * 4;  // running mean shift per system (centred columns): {current, before the last block}
   L.total = o;
@@ -541,6 +538,9 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
   // into four per-marker numbers one block ahead, and the Bernoulli(pj) draw u < 1/(1 + R exp(x)) is taken as
   // x < log((1/u - 1)/R): the dependent chain per marker is one shuffle, five FMAs and a compare (no exp, no division).
   constexpr bool kSlabDraw = MODEL == M_BB || MODEL == M_BC || MODEL == M_KMUP;
+  // EM spike-slab rules (emBB :162-169, emBC :221-227): the reciprocal 1/(xx + lambda) and xx b0/(xx + lambda) are folded one
+  // block ahead as well; the chain keeps one exp and one reciprocal (the inclusion weight d = 1/(1 + LR) is a value here).
+  constexpr bool kSlabEM = MODEL == M_EMBB || MODEL == M_EMBC;
   const bool full_inv = a.tinv != nullptr;  // T = (I + A L)^-1 of every block precomputed (block_inv.cu)
   const bool use_inv = !full_inv && pipe_use_inv(MODEL, ns);
   const int sring = a.sring;
@@ -934,6 +934,13 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
                   ro.b = take ? b1 : b2; ro.d = take ? 1.0f : 0.0f;
                   ro.de = ro.b - in.b0;
                   ro.vbj = MODEL == M_BB ? (Sy.Sb + ro.b * ro.b) / dr.chi : in.vbj;
+                } else if (kSlabEM) {
+                  const float xxj = mc[jj].xx, b1 = fmaf(gc, in.a, in.c);
+                  const float LR = Sy.Pi0 * expf(Sy.C * (b1 * fmaf(xxj, 2.0f * in.b0 - b1, 2.0f * gc)));
+                  ro.d = __frcp_rn(1.0f + LR);
+                  ro.b = b1 * ro.d;
+                  ro.de = ro.b - in.b0;
+                  ro.vbj = MODEL == M_EMBB ? (Sy.Sb + ro.b * ro.b) / (Sy.df + 1.0f) : in.vbj;
                 } else {
                   ro = marker_rule<MODEL>(gc, mc[jj].xx, in.b0, in.vbj, Sy, dr);
                 }
@@ -1124,6 +1131,12 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
             if (kLinear) {
               const LinCoef lc = lin_coef<MODEL>(mcv.xx, in.b0, in.vbj, sc[s], dr);
               in.a = lc.a; in.c = lc.c;
+            }
+            if (kSlabEM) {
+              const float lmb = MODEL == M_EMBB ? sc[s].ve * (1.0f / in.vbj) : sc[s].lmb;
+              const float ia = 1.0f / (mcv.xx + lmb);
+              in.a = ia;                          // b1 = g * ia + c
+              in.c = mcv.xx * in.b0 * ia;
             }
             if (kSlabDraw) {
               const float lmb = MODEL == M_BB ? sc[s].ve * (1.0f / in.vbj) : MODEL == M_BC ? sc[s].lmb : in.vbj;  // KMUP: vbj carries L[j]
