@@ -66,3 +66,37 @@ def test_fit_sharded_single_process():
     Y = np.arange(12.0).reshape(4, 3)
     out = bd.fit_sharded(_stub_fit, Y)
     assert np.allclose(out["mu"], Y.mean(0)) and out["b"].shape == (5, 3)
+
+
+def test_cv_tasks_cover_every_fit_once():
+    for nf, nt, w in ((5, 20, 8), (5, 20, 1), (3, 2, 4), (5, 20, 7)):
+        per_rank = bd.cv_tasks(nf, nt, w)
+        assert len(per_rank) == w
+        seen = sorted((f, t) for groups in per_rank for f, ts in groups for t in ts)
+        assert seen == [(f, t) for f in range(nf) for t in range(nt)]
+        sizes = [sum(len(ts) for _, ts in groups) for groups in per_rank]
+        assert max(sizes) - min(sizes) <= 1
+        assert max(len(groups) for groups in per_rank) <= 2 or w < nf  # a rank's contiguous chunk spans at most two folds
+
+
+class _FakeStore:
+    def __init__(self, keep):
+        self.keep = keep
+
+    def close(self):
+        pass
+
+
+def test_fit_cv_sharded_single_process():
+    rng = np.random.default_rng(1)
+    n, k = 30, 3
+    Y = rng.normal(size=(n, k))
+    folds = [np.arange(0, 10), np.arange(10, 20), np.arange(20, 30)]
+
+    def fit(Yc, store, scale=1.0):
+        assert Yc.shape[0] == len(store.keep) == 20
+        return {"mu": Yc.mean(0) * scale, "b": np.tile(Yc.mean(0), (4, 1)), "hat": np.zeros((20, Yc.shape[1]))}
+
+    out = bd.fit_cv_sharded(fit, _FakeStore, Y, folds, scale=3.0)
+    want = np.array([Y[np.setdiff1d(np.arange(n), f)][:, t].mean() * 3.0 for f in folds for t in range(k)])
+    assert np.allclose(out["mu"], want) and out["b"].shape == (4, 9) and "hat" not in out
