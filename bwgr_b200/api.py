@@ -14,8 +14,9 @@ from ._lib import EmOut, EmParams, GibbsOut, GibbsParams, check
 
 STORE_I8, STORE_2BIT = 0, 1
 PATH_AUTO, PATH_SMALL_N, PATH_BLOCKED = 0, 1, 2
-_EM = {"emRR": 0, "emBA": 1, "emBB": 2, "emBC": 3, "emBL": 4, "emEN": 5}
-_GIBBS = {"BayesRR": 0, "BayesA": 1, "BayesB": 2, "BayesC": 3}
+_EM = {"emRR": 0, "emBA": 1, "emBB": 2, "emBC": 3, "emBL": 4, "emEN": 5, "emDE": 6, "emML": 7, "emBCpi": 8, "lasso": 9}
+_GIBBS = {"BayesRR": 0, "BayesA": 1, "BayesB": 2, "BayesC": 3, "BayesL": 4, "BayesCpi": 5, "BayesDpi": 6}
+NSCAL = 6  # BWGR_NSCAL of include/bwgr_b200.h
 
 
 def _ptr(a):
@@ -157,7 +158,7 @@ class _EmBuffers:
         self.d = np.zeros((p, nsys), order="F")
         self.hat = np.zeros((n, nsys), order="F")
         self.vb = np.zeros((p, nsys), order="F")
-        self.scal = np.zeros((4, nsys), order="F")
+        self.scal = np.zeros((NSCAL, nsys), order="F")
         self.its = np.zeros(nsys, dtype=np.int32)
         self.c = EmOut(_ptr(self.mu), _ptr(self.b), _ptr(self.d), _ptr(self.hat), _ptr(self.vb), _ptr(self.scal),
                        _ptr(self.its))
@@ -169,7 +170,7 @@ class _EmBuffers:
         def s(a):
             return float(a[0]) if squeeze else a.copy()
 
-        Va, Ve, h2, Vg = (self.scal[i] for i in range(4))
+        Va, Ve, h2, Vg, pi_out, lmb_out = (self.scal[i] for i in range(NSCAL))
         out = {"mu": s(self.mu), "b": v(self.b), "hat": v(self.hat)}
         if model == "emRR":
             out.update(Va=s(Va), Ve=s(Ve), h2=s(h2))
@@ -183,6 +184,14 @@ class _EmBuffers:
             out.update(h2=s(h2))
         elif model == "emEN":
             out.update(Va=s(Va), Ve=s(Ve), h2=s(h2))
+        elif model == "emDE":  # Rcpp20260726ai.cpp:300-305
+            out.update(Vb=v(self.vb), Ve=s(Ve), h2=s(h2))
+        elif model == "emML":  # :513-519
+            out.update(h2=s(h2), Vb=s(Vg), Va=s(Va), Ve=s(Ve))
+        elif model == "emBCpi":  # :1541-1545
+            out.update(d=v(self.d), pi=s(pi_out), Vg=s(Vg), Va=s(Va), Ve=s(Ve), h2=s(h2))
+        elif model == "lasso":  # :1495-1497
+            out.update(h2=s(h2), Lmb=s(lmb_out))
         out["its"] = int(self.its[0]) if squeeze else self.its.copy()
         return out
 
@@ -258,6 +267,24 @@ def emEN(y, gen, R2=0.5, alpha=0.02, **kw):
     return em_fit("emEN", y, gen, R2=R2, alpha=alpha, **kw)
 
 
+def emDE(y, gen, R2=0.5, **kw):
+    return em_fit("emDE", y, gen, R2=R2, **kw)
+
+
+def emML(y, gen, D=None, **kw):
+    if D is not None:  # marker weights (Rcpp20260726ai.cpp:470-476) are not on the B200 path
+        raise _lib.BwgrError(-5, "emML: marker weights D are not on the B200 path")
+    return em_fit("emML", y, gen, **kw)
+
+
+def emBCpi(y, gen, df=10, R2=0.5, Pi=0.75, **kw):
+    return em_fit("emBCpi", y, gen, df=df, R2=R2, Pi=Pi, **kw)
+
+
+def lasso(y, gen, **kw):
+    return em_fit("lasso", y, gen, **kw)
+
+
 def gibbs_fit(model, y, X, it=1500, bi=500, pi=0.95, df=5.0, R2=0.5, seed=1, nchains=1, **store_kw):
     g, own = _store(X, **store_kw)
     try:
@@ -268,7 +295,7 @@ def gibbs_fit(model, y, X, it=1500, bi=500, pi=0.95, df=5.0, R2=0.5, seed=1, nch
         d = np.zeros((g.p, nc), order="F")
         hat = np.zeros((g.n, nc), order="F")
         vb = np.zeros((g.p, nc), order="F")
-        scal = np.zeros((4, nc), order="F")
+        scal = np.zeros((NSCAL, nc), order="F")
         par = GibbsParams(_GIBBS[model], nc, int(it), int(bi), pi, df, R2, seed)
         out = GibbsOut(_ptr(mu), _ptr(b), _ptr(d), _ptr(hat), _ptr(vb), _ptr(scal))
         check(g.lib.bwgr_gibbs_fit(g.h, C.byref(par), _ptr(y), C.byref(out)))
@@ -280,12 +307,17 @@ def gibbs_fit(model, y, X, it=1500, bi=500, pi=0.95, df=5.0, R2=0.5, seed=1, nch
         res = {"mu": float(mu[0]) if sq else mu, "b": v(b), "hat": v(hat),
                "ve": float(scal[1, 0]) if sq else scal[1].copy(), "h2": float(scal[2, 0]) if sq else scal[2].copy(),
                "MSx": float(scal[3, 0]) if sq else scal[3].copy()}
-        if model in ("BayesA", "BayesB"):
+        if model in ("BayesA", "BayesB", "BayesL", "BayesDpi"):
             res["vb"] = v(vb)
         else:
             res["vb"] = float(scal[0, 0]) if sq else scal[0].copy()
-        if model in ("BayesB", "BayesC"):
+        if model in ("BayesB", "BayesC", "BayesCpi", "BayesDpi"):
             res["d"] = v(d)
+        if model in ("BayesCpi", "BayesDpi"):  # these two return pi and PVAL = -log(1 - D) in place of MSx (:914-919, :982-987)
+            del res["MSx"]
+            res["pi"] = float(scal[4, 0]) if sq else scal[4].copy()
+            with np.errstate(divide="ignore"):
+                res["PVAL"] = -np.log(1.0 - res["d"])
         return res
     finally:
         if own:
@@ -306,6 +338,18 @@ def BayesB(y, X, it=1500, bi=500, pi=0.95, df=5, R2=0.5, **kw):
 
 def BayesC(y, X, it=1500, bi=500, pi=0.95, df=5, R2=0.5, **kw):
     return gibbs_fit("BayesC", y, X, it=it, bi=bi, pi=pi, df=df, R2=R2, **kw)
+
+
+def BayesL(y, X, it=1500, bi=500, df=5, R2=0.5, **kw):
+    return gibbs_fit("BayesL", y, X, it=it, bi=bi, df=df, R2=R2, **kw)
+
+
+def BayesCpi(y, X, it=1500, bi=500, df=5, R2=0.5, **kw):
+    return gibbs_fit("BayesCpi", y, X, it=it, bi=bi, df=df, R2=R2, **kw)
+
+
+def BayesDpi(y, X, it=1500, bi=500, df=5, R2=0.5, **kw):
+    return gibbs_fit("BayesDpi", y, X, it=it, bi=bi, df=df, R2=R2, **kw)
 
 
 def KMUP(X, b, d, xx, e, L, Ve, pi, seed=1, **store_kw):
@@ -392,3 +436,71 @@ def mrr(Y, X, **kw):  # R/mix.R:1271
 
 def mrr_float(Y, X, **kw):  # R/mix.R:1273
     return MRR3F(Y, X, **kw)
+
+
+# ---- cross-validation drivers (R/cv.R:2-216): the batched callers of the marker-effect loop --------------------------------
+EMCV_MODELS = ("emRR", "emEN", "emBL", "emDE", "emBA", "emBB", "emBC", "emML", "emBCpi", "lasso")  # R/cv.R:24-26
+MCMCCV_MODELS = ("BayesA", "BayesB", "BayesC", "BayesL", "BayesCpi", "BayesDpi", "BayesRR")          # R/cv.R:132-133
+
+
+def _cv_holdouts(n_rows, k, n, llo, seed):
+    """The held-out row sets: `n` random draws of round(N/k) rows (R/cv.R:6-10 -- random hold-outs, not a partition; the
+    draws come from numpy, not from R's sample()), or one set per level of `llo` (leave-level-out, R/cv.R:45-48)."""
+    if llo is not None:
+        llo = np.asarray(llo)
+        return [np.flatnonzero(llo == lev) for lev in np.unique(llo)]
+    rng = np.random.default_rng(seed)
+    nk = int(round(n_rows / k))
+    return [np.sort(rng.choice(n_rows, nk, replace=False)) for _ in range(n)]
+
+
+def _cv_summary(gebv, models, avg):
+    """sCV of R/cv.R:86-101: predictive ability = correlation of each model's column with OBSERVATION, over the pooled
+    hold-outs (avg, sorted decreasing) or per hold-out; rounded to four digits like the reference."""
+    def pa(M):
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return np.corrcoef(M, rowvar=False)[-1, :-1]
+    if avg:
+        c = pa(np.concatenate(gebv, axis=0))
+        order = np.argsort(-c, kind="stable")
+        return {models[i]: round(float(c[i]), 4) for i in order}
+    return {"CV_%d" % (i + 1): {m: round(float(v), 4) for m, v in zip(models, pa(M))} for i, M in enumerate(gebv)}
+
+
+def _cv_run(models, fit_one, y, gen, holdouts, tbv, avg, ReturnGebv):
+    y = np.asarray(y, dtype=np.float64)
+    X = np.asarray(gen)
+    obs = y if tbv is None else np.asarray(tbv, dtype=np.float64)
+    gebv, B0 = [], []
+    for w in holdouts:
+        keep = np.setdiff1d(np.arange(X.shape[0]), w)
+        with Genotypes(np.asfortranarray(X[keep])) as g:  # gen[-w, ] packed ONCE per fold, shared by every model of the panel
+            B = np.stack([fit_one(m, y[keep], g)["b"] for m in models], axis=1)
+        gebv.append(np.concatenate([X[w].astype(np.float64) @ B, obs[w][:, None]], axis=1))  # gen[w, ] %*% b | OBSERVATION
+        B0.append(B)
+    cv = _cv_summary(gebv, list(models), avg)
+    if not ReturnGebv:
+        return cv
+    beta = np.mean(B0, axis=0)  # R/cv.R:102-106
+    return {"cv": cv, "hat": X.astype(np.float64) @ beta + np.nanmean(y), "beta": beta}
+
+
+def emCV(y, gen, k=5, n=5, Pi=0.75, alpha=0.02, df=10, R2=0.5, avg=True, llo=None, tbv=None, ReturnGebv=False, seed=1):
+    """emCV of R/cv.R:2-108: ten EM solvers per hold-out, predictive correlation of gen[w, ] b with the held-out
+    observations.  Per fold the training rows are packed once into one device store and all ten fits run on it."""
+    def fit_one(m, yk, g):
+        kw = {"emRR": dict(R2=R2, df=df), "emEN": dict(alpha=alpha, R2=R2), "emBL": dict(alpha=alpha, R2=R2), "emDE": dict(R2=R2),
+              "emBA": dict(R2=R2, df=df), "emBB": dict(Pi=Pi, R2=R2, df=df), "emBC": dict(Pi=Pi, R2=R2, df=df), "emML": {},
+              "emBCpi": {}, "lasso": {}}[m]  # R/cv.R:13-22 (emML, emBCpi and lasso run on their defaults)
+        return em_fit(m, yk, g, **kw)
+    return _cv_run(EMCV_MODELS, fit_one, y, gen, _cv_holdouts(np.asarray(gen).shape[0], k, n, llo, seed), tbv, avg, ReturnGebv)
+
+
+def mcmcCV(y, gen, k=5, n=5, it=1500, bi=500, pi=0.95, df=5, R2=0.5, avg=True, llo=None, tbv=None, ReturnGebv=False, seed=1):
+    """mcmcCV of R/cv.R:110-216: the seven Gibbs samplers per hold-out."""
+    def fit_one(m, yk, g):
+        kw = dict(R2=R2, df=df, it=it, bi=bi, seed=seed)
+        if m in ("BayesB", "BayesC"):
+            kw["pi"] = pi
+        return gibbs_fit(m, yk, g, **kw)
+    return _cv_run(MCMCCV_MODELS, fit_one, y, gen, _cv_holdouts(np.asarray(gen).shape[0], k, n, llo, seed), tbv, avg, ReturnGebv)

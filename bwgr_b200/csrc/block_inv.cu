@@ -21,11 +21,12 @@ constexpr int kTileF = 32 * kTS;
 
 __device__ __forceinline__ int tri(int hi, int lo) { return hi * (hi + 1) / 2 + lo; }
 
-// kappa = 2 for emBA (the reference applies the residual update twice), per_marker = lambda_j = ve / vb_j (emBA, BayesA)
+// kappa = 2 for emBA (the reference applies the residual update twice); the penalty of a marker follows marker_lambda<>
+// of common.cuh (same float expressions, so the inverse and the right-hand side of the solve use the same a_i)
 __global__ void __launch_bounds__(128) block_inverse_kernel(const int* __restrict__ perm, int p, const float* __restrict__ gram,
                                                             int gstride, const float* __restrict__ xx,
                                                             const float* __restrict__ vbv, const SysScalars* __restrict__ sc,
-                                                            float kappa, int per_marker, float* __restrict__ tinv) {
+                                                            float kappa, int model, float* __restrict__ tinv) {
   extern __shared__ float sm[];
   float* Gs = sm;                     // 10 lower-triangle tiles (hi, lo): G[32 hi + r][32 lo + q]
   float* av = sm + 10 * kTileF;       // [128]
@@ -36,7 +37,13 @@ __global__ void __launch_bounds__(128) block_inverse_kernel(const int* __restric
     float a = 0.0f;
     if (pos < p) {
       const int m = perm[pos];
-      const float lmb = per_marker ? s.ve * (1.0f / vbv[m]) : s.lmb;
+      float lmb;
+      switch (model) {
+        case M_EMBA: case M_BA: lmb = s.ve * (1.0f / vbv[m]); break;
+        case M_BL: lmb = s.sweep == 0 ? s.ve * (1.0f / vbv[m]) : sqrtf(s.Rho * s.ve / vbv[m]); break;
+        case M_EMDE: lmb = vbv[m]; break;
+        default: lmb = s.lmb; break;
+      }
       a = kappa / (xx[m] + lmb);
     }
     av[tid] = a;
@@ -111,8 +118,7 @@ void launch_block_inverse(int model, const int* perm, int p, int nblocks, const 
     attr_set = true;
   }
   const float kappa = model == M_EMBA ? 2.0f : 1.0f;
-  const int per_marker = (model == M_EMBA || model == M_BA) ? 1 : 0;
-  block_inverse_kernel<<<nblocks, 128, smem, st>>>(perm, p, gram, nband * 128, xx, vbv, sc, kappa, per_marker, tinv);
+  block_inverse_kernel<<<nblocks, 128, smem, st>>>(perm, p, gram, nband * 128, xx, vbv, sc, kappa, rule_model(model), tinv);
 }
 
 }  // namespace bwgr

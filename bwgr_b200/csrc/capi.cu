@@ -724,17 +724,42 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
         c.trAC22 = (float)tr;
         break;
       }
-      case M_BRR: case M_BA: case M_BB: {  // :822-827, :598-609, :649-665
+      case M_EMDE: {  // :262-270 ; the per-marker slot carries Lmb_j
+        const float cxx = sum_vx * (1 - R2) / R2;
+        c.cxx = cxx;
+        vbv_init = (float)p + cxx;
+        break;
+      }
+      case M_EMML: {  // :480-486
+        c.MSx = sum_vx; c.lmb = sum_vx;
+        break;
+      }
+      case M_EMBCPI: {  // :1508-1520 (emBC's start; the prior Pi is kept for the per-sweep update of Pi)
+        if (Pi > 0.5f) Pi = 1 - Pi;
+        const float MSx = sum_vx * Pi * (1 - Pi);
+        c.MSx = MSx; c.Sa = R2 * (df + 2) * vy / MSx; c.Se = (1 - R2) * (df + 2) * vy;
+        c.ve = c.Sa; c.vb = c.Se; c.lmb = c.ve / c.vb; c.Pi = Pi; c.Pi0 = (1 - Pi) / Pi;
+        c.cxx = sum_vx; c.pi_mix = Pi;
+        break;
+      }
+      case M_LASSO: {  // :1470-1472
+        c.lmb = (float)(sxx / (double)p) / (float)p;
+        break;
+      }
+      case M_BRR: case M_BA: case M_BB: case M_BL: case M_BDPI: {  // :822-827, :598-609, :649-665, :771-783, :931-944
         const float MSx = sum_vx;
         c.MSx = MSx; c.Sb = R2 * df * vy / MSx; c.Se = (1 - R2) * df * vy; c.ve = vy; c.vb = c.Sb; c.lmb = c.ve / c.vb;
         c.Pi0 = s.pi / (1.0f - s.pi);
+        c.Rho = MSx * (1 - R2) / R2;  // BayesL's Phi (:773)
+        c.Pi = s.pi;                  // BayesDpi: pi = 0.5 at the start (:934), then the mean inclusion
         vbv_init = c.Sb;
         break;
       }
+      case M_BCPI:  // :866-880 = BayesC started at pi = 0.5
       case M_BC: {  // :712-726
         const float MSx = sum_vx;
         c.MSx = MSx; c.Sb = df * R2 * vy / MSx / (1 - s.pi); c.Se = df * (1 - R2) * vy; c.ve = vy; c.vb = c.Sb;
-        c.lmb = c.ve / c.vb; c.Pi0 = s.pi / (1.0f - s.pi);
+        c.lmb = c.ve / c.vb; c.Pi0 = s.pi / (1.0f - s.pi); c.Pi = s.pi;
         break;
       }
       case M_MRR: {  // rotated MRR3 systems: lambda and scales are set per sweep by the driver
@@ -774,7 +799,7 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
   const bool gibbs = model_is_gibbs(s.model);
   if (!model_has_d(s.model)) f.d.release();
   if (!model_has_vbj(s.model)) f.vbv.release();
-  if (s.model != M_EMEN) f.b_prev.release();
+  if (!model_has_cnv(s.model)) f.b_prev.release();
   if (!gibbs) { f.B.release(); f.D.release(); f.VBv.release(); }
   if (!f.masked) { f.mask.release(); f.xx_sys.release(); }
   if (f.y.alloc((size_t)ns * ld) != cudaSuccess || f.e.alloc((size_t)ns * ld) != cudaSuccess ||
@@ -782,7 +807,7 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
     return fail(BWGR_ERR_CUDA, "cudaMalloc(fit state) failed");
   if (model_has_d(s.model) && f.d.alloc((size_t)ns * p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
   if (model_has_vbj(s.model) && f.vbv.alloc((size_t)ns * p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
-  if (s.model == M_EMEN && f.b_prev.alloc((size_t)ns * p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  if (model_has_cnv(s.model) && f.b_prev.alloc((size_t)ns * p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
   if (gibbs) {
     if (f.B.alloc((size_t)ns * p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
     CU(cudaMemsetAsync(f.B.p, 0, sizeof(float) * ns * p, h->stream));
@@ -886,7 +911,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
     }
     if (f.shuffled) d_perm = f.perm.p + (size_t)slot * p;
     else if (f.blocked) d_perm = f.perm.p;  // identity order, uploaded once (slot 0)
-    if (f.model == M_EMEN) CU(cudaMemcpyAsync(f.b_prev.p, f.b.p, sizeof(float) * f.nsys * p, cudaMemcpyDeviceToDevice, h->stream));
+    if (model_has_cnv(f.model)) CU(cudaMemcpyAsync(f.b_prev.p, f.b.p, sizeof(float) * f.nsys * p, cudaMemcpyDeviceToDevice, h->stream));
     if (f.blocked) {
       if (f.shuffled || !f.gram_cached) {
         cudaEvent_t pe = h->prof_begin(0);
@@ -910,7 +935,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
         CU(cudaMemsetAsync(f.part.p, 0, sizeof(unsigned long long) * f.part.n, h->stream));
         PipeArgs a;
         memset(&a, 0, sizeof a);
-        a.g = g; a.model = f.model; a.nsys = f.nsys; a.perm = d_perm; a.nblocks = f.nblocks; a.gram = f.gram_p; a.nband = f.nband; a.tinv = f.full_inv ? f.tinv.p : nullptr;
+        a.g = g; a.model = rule_model(f.model); a.nsys = f.nsys; a.perm = d_perm; a.nblocks = f.nblocks; a.gram = f.gram_p; a.nband = f.nband; a.tinv = f.full_inv ? f.tinv.p : nullptr;
         a.e = f.e.p; a.b = f.b.p; a.d = f.d.p; a.vbv = f.vbv.p; a.xx = f.xx_over.p ? f.xx_over.p : h->xx_f.p; a.sx = f.sx_dev.p; a.cshift = f.cshift.p; a.sc = f.sc.p;
         a.part = f.part.p; a.hred = f.part.p + (size_t)8 * f.nsys * 128 * 160; a.dew = f.dew.p; a.tag = ++f.tag;
         a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0;
@@ -931,7 +956,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
         CU(cudaMemsetAsync(f.bar.p, 0, sizeof(unsigned int), h->stream));
         SweepArgs a;
         memset(&a, 0, sizeof a);
-        a.g = g; a.model = f.model; a.nsys = f.nsys; a.perm = d_perm; a.nblocks = f.nblocks; a.gram = f.gram_p;
+        a.g = g; a.model = rule_model(f.model); a.nsys = f.nsys; a.perm = d_perm; a.nblocks = f.nblocks; a.gram = f.gram_p;
         a.e = f.e.p; a.b = f.b.p; a.d = f.d.p; a.vbv = f.vbv.p; a.xx = f.xx_over.p ? f.xx_over.p : h->xx_f.p; a.sc = f.sc.p;
         a.gacc = f.gacc.p; a.bar = f.bar.p; a.g_quantum = quantum; a.g_limit = limit;
         a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0;
@@ -948,7 +973,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
     } else {
       SmallNArgs a;
       memset(&a, 0, sizeof a);
-      a.g = g; a.model = f.model; a.nsys = f.nsys; a.perms = d_perm; a.y = f.y.p; a.e = f.e.p; a.b = f.b.p; a.d = f.d.p;
+      a.g = g; a.model = rule_model(f.model); a.nsys = f.nsys; a.perms = d_perm; a.y = f.y.p; a.e = f.e.p; a.b = f.b.p; a.d = f.d.p;
       a.vbv = f.vbv.p; a.xx = f.masked ? f.xx_sys.p : (f.xx_over.p ? f.xx_over.p : h->xx_f.p); a.xx_per_sys = f.masked ? 1 : 0; a.mask = f.mask.p;
       a.sc = f.sc.p; a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0; a.err = h->err.p;
       cudaEvent_t pe = h->prof_begin(1);
@@ -971,6 +996,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
       }
       ea.model = f.model; ea.nsys = f.nsys; ea.n = (int)h->n; ea.p = (int)p; ea.ld = ld; ea.e = f.e.p; ea.y = f.y.p; ea.b = f.b.p;
       ea.d = f.d.p; ea.vbv = f.vbv.p; ea.b_prev = f.b_prev.p; ea.mask = f.mask.p; ea.sc = f.sc.p; ea.B = f.B.p; ea.D = f.D.p;
+      ea.xx = f.masked ? f.xx_sys.p : (f.xx_over.p ? f.xx_over.p : h->xx_f.p); ea.xx_per_sys = f.masked ? 1 : 0;
       ea.VBv = f.VBv.p; ea.seed_lo = (uint32_t)f.seed; ea.seed_hi = (uint32_t)(f.seed >> 32); ea.chain0 = 0;
       cudaEvent_t pe2 = h->prof_begin(2);
       if (h->world > 1) {  // sums over individuals: per rank, then all-reduced; everything else is replicated
@@ -1007,10 +1033,11 @@ extern "C" {
 
 static int em_spec(const bwgr_em_params* par, FitSpec* s) {
   if (!par) return fail(BWGR_ERR_ARG, "params NULL");
-  if (par->model < 0 || par->model > 5) return fail(BWGR_ERR_ARG, "bad EM model %d", par->model);
-  s->model = par->model; s->nsys = par->nsys; s->shuffled = true; s->row_mask = par->row_mask;
+  if (par->model < 0 || par->model > BWGR_EM_LASSO) return fail(BWGR_ERR_ARG, "bad EM model %d", par->model);
+  s->model = par->model; s->nsys = par->nsys; s->row_mask = par->row_mask;
+  s->shuffled = !(par->model == BWGR_EM_BCPI || par->model == BWGR_EM_LASSO);  // these two walk the markers in order (:1523, :1477)
   s->df = (float)par->df; s->R2 = (float)par->R2; s->Pi = (float)par->Pi; s->alpha = (float)par->alpha; s->pi = 0;
-  s->it = par->it < 0 ? (par->model == BWGR_EM_EN ? 300 : 200) : par->it;
+  s->it = par->it < 0 ? (model_has_cnv(par->model) ? 300 : 200) : par->it;  // maxit of the solvers with a stopping rule, else 200 sweeps
   s->bi = 0; s->seed = 0;
   return 0;
 }
@@ -1050,7 +1077,7 @@ int bwgr_em_end(bwgr_handle* h, bwgr_em_out* out) {
   std::vector<float> hb((size_t)ns * p), hd, hv, hh((size_t)ns * n), he;
   CU(cudaMemcpyAsync(hb.data(), f.b.p, sizeof(float) * hb.size(), cudaMemcpyDeviceToHost, h->stream));
   if (f.d.p && out->d) { hd.resize((size_t)ns * p); CU(cudaMemcpyAsync(hd.data(), f.d.p, sizeof(float) * hd.size(), cudaMemcpyDeviceToHost, h->stream)); }
-  if (f.vbv.p && out->vb) { hv.resize((size_t)ns * p); CU(cudaMemcpyAsync(hv.data(), f.vbv.p, sizeof(float) * hv.size(), cudaMemcpyDeviceToHost, h->stream)); }
+  if (f.vbv.p && (out->vb || f.model == M_EMDE)) { hv.resize((size_t)ns * p); CU(cudaMemcpyAsync(hv.data(), f.vbv.p, sizeof(float) * hv.size(), cudaMemcpyDeviceToHost, h->stream)); }
   if (f.model == M_EMBL) { he.resize((size_t)ns * ld); CU(cudaMemcpyAsync(he.data(), f.e.p, sizeof(float) * he.size(), cudaMemcpyDeviceToHost, h->stream)); }
   DevBuf<float> hat;
   if (hat.alloc((size_t)ld) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
@@ -1065,7 +1092,7 @@ int bwgr_em_end(bwgr_handle* h, bwgr_em_out* out) {
     const SysScalars& c = sc[t];
     if (out->mu) out->mu[t] = c.mu;
     if (out->its) out->its[t] = c.its;
-    double Va = 0, Ve = c.ve, h2 = 0, Vg = 0;
+    double Va = 0, Ve = c.ve, h2 = 0, Vg = 0, pi_out = 0, lmb_out = 0;
     switch (f.model) {
       case M_EMRR: Va = c.vb; h2 = 1.0f - c.ve / f.vy[t]; break;
       case M_EMBA: case M_EMBB: h2 = 1.0f - c.ve / f.vy[t]; break;
@@ -1089,9 +1116,28 @@ int bwgr_em_end(bwgr_handle* h, bwgr_em_out* out) {
         Ve = 0; break;
       }
       case M_EMEN: { const float va = c.vb * f.cxx[t]; Va = va; h2 = va / (va + c.ve); break; }
+      case M_EMDE: {  // Vb_j of the last sweep from the penalty it produced: Lmb_j = sqrt(cxx Ve / Vb_j) (:293-296, :305)
+        float sv = 0;
+        if (!hv.empty() || out->vb) {
+          for (int64_t j = 0; j < p; j++) {
+            const float L = hv.empty() ? 0.0f : hv[(size_t)t * p + j];
+            const float vbj = (c.its > 0 && L > 0) ? c.cxx * c.ve / (L * L) : 0.0f;
+            if (!hv.empty()) hv[(size_t)t * p + j] = vbj;
+            sv += vbj;
+          }
+        }
+        h2 = sv / (sv + c.ve);
+        break;
+      }
+      case M_EMML: Vg = c.vb; Va = c.vb * c.MSx; h2 = Va / (Va + c.ve); break;                  // :508-515 (Vg slot = Vb)
+      case M_EMBCPI: Va = c.vb; Vg = c.vb * c.MSx; h2 = 1.0f - c.ve / f.vy[t]; pi_out = c.Pi; break;  // :1539-1545
+      case M_LASSO: h2 = 1.0f - c.ve / f.vy[t]; Ve = 0; lmb_out = c.lmb; break;                       // :1494-1497
       default: break;
     }
-    if (out->scal) { out->scal[4 * t + 0] = Va; out->scal[4 * t + 1] = Ve; out->scal[4 * t + 2] = h2; out->scal[4 * t + 3] = Vg; }
+    if (out->scal) {
+      double* sc_out = out->scal + (size_t)BWGR_NSCAL * t;
+      sc_out[0] = Va; sc_out[1] = Ve; sc_out[2] = h2; sc_out[3] = Vg; sc_out[4] = pi_out; sc_out[5] = lmb_out;
+    }
   }
   if (out->b) for (size_t i = 0; i < hb.size(); i++) out->b[i] = hb[i];
   if (out->d && !hd.empty()) for (size_t i = 0; i < hd.size(); i++) out->d[i] = hd[i];
@@ -1105,7 +1151,7 @@ int bwgr_em_fit(bwgr_handle* h, const bwgr_em_params* par, const double* y, bwgr
   int rc = bwgr_em_begin(h, par, y);
   if (rc) return rc;
   Fit& f = h->fit;
-  if (f.model == M_EMEN) {
+  if (model_has_cnv(f.model)) {
     // convergence is checked on the device each sweep; poll in batches to keep the host off the path
     int done_all = 0;
     std::vector<SysScalars> sc(f.nsys);
@@ -1127,15 +1173,17 @@ int bwgr_em_fit(bwgr_handle* h, const bwgr_em_params* par, const double* y, bwgr
 // ---- Gibbs -------------------------------------------------------------------------------------------
 int bwgr_gibbs_fit(bwgr_handle* h, const bwgr_gibbs_params* par, const double* y, bwgr_gibbs_out* out) {
   if (!h || !par || !out) return fail(BWGR_ERR_ARG, "null argument");
-  if (par->model < 0 || par->model > 3) return fail(BWGR_ERR_ARG, "bad Gibbs model %d", par->model);
+  if (par->model < 0 || par->model > BWGR_GIBBS_DPI) return fail(BWGR_ERR_ARG, "bad Gibbs model %d", par->model);
+  static const int kGibbsModel[] = {M_BRR, M_BA, M_BB, M_BC, M_BL, M_BCPI, M_BDPI};
+  const bool has_pi = par->model == BWGR_GIBBS_CPI || par->model == BWGR_GIBBS_DPI;  // these two start at pi = 0.5 (:870, :934), not an argument
   if (par->it < 1 || par->bi < 0 || par->bi >= par->it) return fail(BWGR_ERR_ARG, "need 0 <= bi < it");
   const int nc = par->nchains < 1 ? 1 : par->nchains;
   const int64_t n = h->n, p = h->p;
   std::vector<double> yy((size_t)nc * n);
   for (int c = 0; c < nc; c++) memcpy(yy.data() + (size_t)c * n, y, sizeof(double) * n);
   FitSpec s;
-  s.model = M_BRR + par->model; s.nsys = nc; s.shuffled = false; s.row_mask = nullptr;
-  s.df = (float)par->df; s.R2 = (float)par->R2; s.Pi = 0; s.alpha = 0; s.pi = (float)par->pi;
+  s.model = kGibbsModel[par->model]; s.nsys = nc; s.shuffled = false; s.row_mask = nullptr;
+  s.df = (float)par->df; s.R2 = (float)par->R2; s.Pi = 0; s.alpha = 0; s.pi = has_pi ? 0.5f : (float)par->pi;
   s.it = par->it; s.bi = par->bi; s.seed = par->seed;
   int rc = fit_begin(h, s, yy.data());
   if (rc) return rc;
@@ -1168,8 +1216,13 @@ int bwgr_gibbs_fit(bwgr_handle* h, const bwgr_gibbs_params* par, const double* y
     float vg;
     if (f.VBv.p) { double sv = 0; for (int64_t j = 0; j < p; j++) sv += V[(size_t)c * p + j] / MCMC; vg = (float)sv; }
     else vg = VBs * f.MSx[c];
+    const float pi_out = has_pi ? 1.0f - (float)(sc[c].PI / MCMC) : 0.0f;  // :911, :975
+    if (f.model == M_BCPI) vg = VBs * f.MSx[c] / pi_out;                   // :913
     if (out->mu) out->mu[c] = MU;
-    if (out->scal) { out->scal[4 * c + 0] = VBs; out->scal[4 * c + 1] = VE; out->scal[4 * c + 2] = vg / (vg + VE); out->scal[4 * c + 3] = f.MSx[c]; }
+    if (out->scal) {
+      double* sc_out = out->scal + (size_t)BWGR_NSCAL * c;
+      sc_out[0] = VBs; sc_out[1] = VE; sc_out[2] = vg / (vg + VE); sc_out[3] = f.MSx[c]; sc_out[4] = pi_out; sc_out[5] = 0;
+    }
     if (out->vb) {
       if (f.VBv.p) for (int64_t j = 0; j < p; j++) out->vb[(size_t)c * p + j] = V[(size_t)c * p + j] / MCMC;
       else out->vb[c] = VBs;

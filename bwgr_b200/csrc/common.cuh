@@ -8,8 +8,14 @@ namespace bwgr {
 // Unified model ids used on the device (EM = bwgr_em_model, Gibbs = 10 + bwgr_gibbs_model).
 enum Model : int {
   M_EMRR = 0, M_EMBA = 1, M_EMBB = 2, M_EMBC = 3, M_EMBL = 4, M_EMEN = 5,
-  M_BRR = 10, M_BA = 11, M_BB = 12, M_BC = 13, M_KMUP = 14, M_MRR = 15 /* rotated MRR3 trait: ridge, per-system lambda */
+  M_EMDE = 6, M_EMML = 7, M_EMBCPI = 8, M_LASSO = 9,  // the rest of emCV's panel (R/cv.R:13-22)
+  M_BRR = 10, M_BA = 11, M_BB = 12, M_BC = 13, M_KMUP = 14, M_MRR = 15 /* rotated MRR3 trait: ridge, per-system lambda */,
+  M_BL = 16, M_BCPI = 17, M_BDPI = 18                  // the rest of mcmcCV's panel (R/cv.R:124-130)
 };
+// Several solvers share one per-marker rule and differ only in the sweep epilogue: the sweep kernels are instantiated per
+// RULE, the epilogue and the host recipes see the full model.  emML :463 steps like emRR, emBCpi :1502 like emBC,
+// BayesCpi :858 like BayesC (its mixing odds Pi0 are never refreshed, only the prior scale Sb follows the inclusion rate).
+__host__ __device__ constexpr int rule_model(int m) { return m == M_EMML ? M_EMRR : m == M_EMBCPI ? M_EMBC : m == M_BCPI ? M_BC : m; }
 
 // Per-system scalar state, device resident, updated by the sweep epilogue.
 struct SysScalars {
@@ -26,7 +32,7 @@ struct SysScalars {
   int sweep;    // absolute sweep index (Gibbs: RNG counter)
   int burn, post_count;
   // posterior accumulators (Gibbs)
-  double MU, VE, VB;
+  double MU, VE, VB, PI;
 };
 
 struct MarkerDraws {  // pre-generated per marker per sweep (Gibbs only)
@@ -89,7 +95,7 @@ __device__ inline MarkerDraws marker_draws(int model, uint32_t marker, uint32_t 
   box_muller(c[0], c[1], m.z1, m.z2);
   m.u = u01(c[2]);
   m.chi = 1.0f;
-  if (model == M_BA || model == M_BB) m.chi = rchisq_philox(df + 1.0f, marker, sweep, chain, 1u, k0, k1);
+  if (model == M_BA || model == M_BB || model == M_BL || model == M_BDPI) m.chi = rchisq_philox(df + 1.0f, marker, sweep, chain, 1u, k0, k1);
   return m;
 }
 
@@ -101,6 +107,16 @@ __device__ inline MarkerDraws marker_draws(int model, uint32_t marker, uint32_t 
 // ---------------------------------------------------------------------------------------------
 struct RuleOut { float b, de, d, vbj; };
 
+// The ridge penalty of marker j as the rule sees it.  vbj is the per-marker slot: a variance (emBA/emBB/BayesA/B/L/Dpi),
+// or the penalty itself (KMUP's L[j], emDE's Lmb[j] :281).  BayesL :790-799: ve/vb_j in the first sweep, sqrt(Phi ve/vb_j) after.
+template <int MODEL>
+__device__ __forceinline__ float marker_lambda(float vbj, const SysScalars& s) {
+  if constexpr (MODEL == M_EMBA || MODEL == M_EMBB || MODEL == M_BA || MODEL == M_BB || MODEL == M_BDPI) return s.ve * (1.0f / vbj);
+  else if constexpr (MODEL == M_BL) return s.sweep == 0 ? s.ve * (1.0f / vbj) : sqrtf(s.Rho * s.ve / vbj);
+  else if constexpr (MODEL == M_EMDE || MODEL == M_KMUP) return vbj;
+  else return s.lmb;
+}
+
 template <int MODEL>
 __device__ __forceinline__ RuleOut marker_rule(float g, float xx, float b0, float vbj, const SysScalars& s,
                                                const MarkerDraws& dr) {
@@ -109,6 +125,17 @@ __device__ __forceinline__ RuleOut marker_rule(float g, float xx, float b0, floa
   if constexpr (MODEL == M_EMRR || MODEL == M_MRR) {  // Rcpp20260726ai.cpp:335 ; MRR3 rotated system
     o.b = (g + xx * b0) / (xx + s.lmb);
     o.de = o.b - b0;
+  } else if constexpr (MODEL == M_EMDE) {  // :281-283 (vbj carries Lmb[j]; the epilogue re-estimates it)
+    o.b = (g + xx * b0) / (vbj + xx);
+    o.de = o.b - b0;
+  } else if constexpr (MODEL == M_LASSO) {  // :1478-1486 ; d carries |x'e~| - |b xx|, which the epilogue sums into the next penalty (:1487-1489)
+    const float yx = g + xx * b0;
+    float b1;
+    if (yx > 0.0f) { b1 = (yx - s.lmb) / xx; if (b1 < 0.0f) b1 = 0.0f; }
+    else           { b1 = (yx + s.lmb) / xx; if (b1 > 0.0f) b1 = 0.0f; }
+    o.b = b1;
+    o.d = fabsf(yx) - fabsf(b1 * xx);
+    o.de = b1 - b0;
   } else if constexpr (MODEL == M_EMBA) {  // :107-111 (e updated twice)
     const float lmb = s.ve * (1.0f / vbj);
     const float b1 = (g + xx * b0) / (xx + lmb);
@@ -141,11 +168,21 @@ __device__ __forceinline__ RuleOut marker_rule(float g, float xx, float b0, floa
     else            { b1 = (OLS + s.lmb1) / (s.lmb2 + xx); if (b1 > 0.0f) b1 = 0.0f; }
     o.b = b1;
     o.de = b1 - b0;
-  } else if constexpr (MODEL == M_BRR || MODEL == M_BA) {  // :835, :615-618
-    const float lmb = (MODEL == M_BA) ? s.ve * (1.0f / vbj) : s.lmb;
+  } else if constexpr (MODEL == M_BRR || MODEL == M_BA || MODEL == M_BL) {  // :835, :615-618, :790-793
+    const float lmb = marker_lambda<MODEL>(vbj, s);
     const float sd = sqrtf(s.ve / (xx + lmb));
     o.b = (g + xx * b0) / (xx + lmb) + sd * dr.z1;
-    if (MODEL == M_BA) o.vbj = (s.Sb + o.b * o.b) / dr.chi;
+    if (MODEL == M_BA || MODEL == M_BL) o.vbj = (s.Sb + o.b * o.b) / dr.chi;
+    o.de = o.b - b0;
+  } else if constexpr (MODEL == M_BDPI) {  // :949-964 ; accept b1 with probability min(1, (1-pi) exp(C(|e1|^2 - |e2|^2))), s.Pi = pi
+    const float lmb = s.ve * (1.0f / vbj);
+    const float sd = sqrtf(s.ve / (xx + lmb));
+    const float b1 = (g + xx * b0) / (xx + lmb) + sd * dr.z1, b2 = sd * dr.z2;
+    const float diff = (b2 - b1) * (-2.0f * g + xx * (b1 + b2 - 2.0f * b0));  // ||e2||^2-||e1||^2, e2 = e - x(b2-b0)
+    float pj = (1.0f - s.Pi) * expf(-s.C * diff);
+    if (pj > 1.0f) pj = 1.0f;
+    if (dr.u < pj) { o.b = b1; o.d = 1.0f; } else { o.b = b2; o.d = 0.0f; }
+    o.vbj = (s.Sb + o.b * o.b) / dr.chi;
     o.de = o.b - b0;
   } else if constexpr (MODEL == M_BB || MODEL == M_BC) {  // :670-681, :731-741
     const float lmb = (MODEL == M_BB) ? s.ve * (1.0f / vbj) : s.lmb;
@@ -173,25 +210,36 @@ __device__ __forceinline__ RuleOut marker_rule(float g, float xx, float b0, floa
 }
 
 // Linear rules: the residual step of marker i is  de_i = a_i * g_i + c_i  with a_i, c_i independent of g
-// (g_i = current x_i'e).  emRR :335, emBA :107-111 (de = 2*(b1-b0)), BayesRR :835, BayesA :615, rotated MRR3.
-__host__ __device__ constexpr bool model_is_linear(int m) { return m == M_EMRR || m == M_EMBA || m == M_MRR || m == M_BRR || m == M_BA; }
+// (g_i = current x_i'e).  emRR :335, emBA :107-111 (de = 2*(b1-b0)), BayesRR :835, BayesA :615, rotated MRR3, emDE :281,
+// emML :492, BayesL :790.
+__host__ __device__ constexpr bool model_is_linear(int m) {
+  return m == M_EMRR || m == M_EMBA || m == M_MRR || m == M_BRR || m == M_BA || m == M_EMDE || m == M_EMML || m == M_BL;
+}
 struct LinCoef { float a, c, kappa; };
 template <int MODEL>
 __device__ __forceinline__ LinCoef lin_coef(float xx, float b0, float vbj, const SysScalars& s, const MarkerDraws& dr) {
-  const float lmb = (MODEL == M_EMBA || MODEL == M_BA) ? s.ve * (1.0f / vbj) : s.lmb;
+  const float lmb = marker_lambda<MODEL>(vbj, s);
   const float alpha = 1.0f / (xx + lmb);
   LinCoef o;
   o.kappa = (MODEL == M_EMBA) ? 2.0f : 1.0f;
   float c = -lmb * b0 * alpha;                       // (g + xx*b0)*alpha - b0 = g*alpha - lmb*b0*alpha
-  if (MODEL == M_BRR || MODEL == M_BA) c += sqrtf(s.ve * alpha) * dr.z1;
+  if (MODEL == M_BRR || MODEL == M_BA || MODEL == M_BL) c += sqrtf(s.ve * alpha) * dr.z1;
   o.a = o.kappa * alpha;
   o.c = o.kappa * c;
   return o;
 }
 
-__host__ __device__ constexpr bool model_is_gibbs(int m) { return m >= M_BRR && m <= M_KMUP; }
-__host__ __device__ constexpr bool model_has_vbj(int m) { return m == M_EMBA || m == M_EMBB || m == M_BA || m == M_BB || m == M_KMUP; }
-__host__ __device__ constexpr bool model_has_d(int m) { return m == M_EMBB || m == M_EMBC || m == M_BB || m == M_BC || m == M_KMUP; }
+__host__ __device__ constexpr bool model_is_gibbs(int m) { return (m >= M_BRR && m <= M_KMUP) || (m >= M_BL && m <= M_BDPI); }
+__host__ __device__ constexpr bool model_has_vbj(int m) {
+  return m == M_EMBA || m == M_EMBB || m == M_BA || m == M_BB || m == M_KMUP || m == M_EMDE || m == M_BL || m == M_BDPI;
+}
+// the rule itself rewrites the per-marker slot (KMUP's L and emDE's Lmb are inputs of the sweep: caller / epilogue own them)
+__host__ __device__ constexpr bool model_rule_writes_vbj(int m) { return model_has_vbj(m) && m != M_KMUP && m != M_EMDE; }
+__host__ __device__ constexpr bool model_has_d(int m) {
+  return m == M_EMBB || m == M_EMBC || m == M_BB || m == M_BC || m == M_KMUP || m == M_EMBCPI || m == M_LASSO || m == M_BCPI || m == M_BDPI;
+}
+// solvers that stop on sum |b_old - b_new| < tol (emEN :449, emDE :297, emML :505, lasso :1492)
+__host__ __device__ constexpr bool model_has_cnv(int m) { return m == M_EMEN || m == M_EMDE || m == M_EMML || m == M_LASSO; }
 
 // int8 genotype byte (two's complement) -> float, on the FMA/ALU pipes (no I2F):
 // place u = (byte ^ 0x80) = x + 128 in the mantissa of 2^23 and subtract 2^23 + 128 (exact).

@@ -3,7 +3,9 @@
 // Restates, in the reference's float arithmetic, the block that follows the marker loop in every solver:
 //   emRR  Rcpp20260726ai.cpp:338-343   emBA :113-117   emBB :171-175   emBC :229-234
 //   emBL  :389-391                     emEN :440-450
+//   emDE  :288-298   emML :498-506   emBCpi :1529-1538   lasso :1487-1492
 //   BayesRR :839-844   BayesA :620-624   BayesB :683-687   BayesC :743-748
+//   BayesL :795-800   BayesCpi :900-908   BayesDpi :966-970
 // Sums over rows / markers are accumulated in double and rounded once (the reference sums in float
 // packets; both are within float reassociation noise of each other).
 #include "kernels.h"
@@ -27,7 +29,7 @@ __device__ double block_sum(double v, double* sh) {
 
 __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
   __shared__ double sh[32];
-  __shared__ float s_eM;
+  __shared__ float s_eM, s_ve, s_cxx;
   __shared__ int s_acc;
   const int sys = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
   SysScalars* scp = a.sc + sys;
@@ -36,7 +38,7 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
   const float* y = a.y + (size_t)sys * a.ld;
   float* b = a.b + (size_t)sys * a.p;
   const float* d = a.d ? a.d + (size_t)sys * a.p : nullptr;
-  const float* vbv = a.vbv ? a.vbv + (size_t)sys * a.p : nullptr;
+  float* vbv = a.vbv ? a.vbv + (size_t)sys * a.p : nullptr;
   const uint8_t* mask = a.mask ? a.mask + (size_t)sys * a.ld : nullptr;
   const int model = a.model;
 
@@ -104,6 +106,44 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
           if (s.cnv < 10e-11f) s.done = 1;
           break;
         }
+        case M_EMDE: {  // :288-298 ; the per-marker penalties follow below, once Ve is known to every thread
+          const float ey = (float)(sey - (double)eM * sy);
+          s.ve = ey / (n - 1.0f);
+          s.cnv = (float)scnv;
+          if (s.cnv < 10e-6f) s.done = 1;
+          break;
+        }
+        case M_EMML: {  // :498-506 ; (y-mu)'e and (y-mu)'(y-mu) with the updated mu and the centred e, from the running sums
+          const double mu1 = (double)s.mu + (double)eM;
+          const double yce = sey - (double)eM * sy;
+          const double syy = ((double)n - 1.0) * (double)s.vy + sy * sy / (double)n;
+          const double ycyc = syy - 2.0 * mu1 * sy + (double)n * mu1 * mu1;
+          s.ve = (float)(yce / (double)n);
+          s.vb = (float)((ycyc - yce) / ((double)n * (double)s.MSx));
+          s.lmb = s.ve / s.vb;
+          s.cnv = (float)scnv;
+          if (s.cnv < 10e-8f) s.done = 1;
+          break;
+        }
+        case M_EMBCPI: {  // :1529-1536 ; pi_mix = the prior Pi, cxx = sum of the marker variances
+          const float dm = (float)(sd / (double)a.p);
+          s.Pi = ((1.0f - dm) * p + s.pi_mix * s.df) / (p + s.df);
+          s.Pi0 = (1.0f - s.Pi) / s.Pi;
+          s.MSx = s.cxx * s.Pi * (1.0f - s.Pi);
+          s.Sa = s.R2 * (s.df + 2.0f) * s.vy / s.MSx;
+          s.ve = (ee + s.Se) / (n + s.df);
+          s.vb = (bb + s.Sa) / (p + s.df) / (dm - s.Pi);
+          s.lmb = s.ve / s.vb;
+          break;
+        }
+        case M_LASSO: {  // :1487-1492 ; d_j = |x_j'e~| - |b_j xx_j| was left by the rule
+          const float tmp = 2.0f * (float)sd / p;
+          s.lmb = 2.0f * sqrtf(fabsf(tmp));
+          s.ve = (float)(sey - (double)eM * sy) / (n - 1.0f);  // for h2 = 1 - (e'y/(n-1))/var(y) (:1494)
+          s.cnv = (float)scnv;
+          if (s.cnv < 10e-8f) s.done = 1;
+          break;
+        }
         default: break;  // emBL, M_MRR: mean removal only (M_MRR: none, see below)
       }
       s.C = -0.5f / sqrtf(s.ve);
@@ -119,18 +159,23 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
       eM = eM + sqrtf(s.ve / n) * z;
       const float ee2 = (float)(see - 2.0 * (double)eM * se + (double)n * (double)eM * (double)eM);
       const float chi_e = rchisq_philox(n + s.df, 0xFFFFFFFFu, sw, chain, 1u, a.seed_lo, a.seed_hi);
-      if (model == M_BRR || model == M_BC) {
+      if (model == M_BRR || model == M_BC || model == M_BCPI) {
         const float chi_b = rchisq_philox(p + s.df, 0xFFFFFFFFu, sw, chain, 2u, a.seed_lo, a.seed_hi);
         s.ve = (ee2 + s.Se) / chi_e;
         s.vb = (bb + s.Sb) / chi_b;
         s.lmb = s.ve / s.vb;
+        if (model == M_BCPI) {  // :906-907 ; the mixing odds Pi0 stay as they were
+          s.Pi = (float)(sd / (double)a.p);
+          s.Sb = s.df * s.R2 * s.vy / s.MSx / (1.0f - s.Pi);
+        }
       } else {
         s.ve = (ee2 + s.Se) / chi_e;
+        if (model == M_BDPI) s.Pi = (float)(sd / (double)a.p);  // :969
       }
       s.C = -0.5f / sqrtf(s.ve);
       if (s.sweep > s.burn) {  // sic: i > bi, divided later by it-bi (:624-627)
         accumulate = 1;
-        s.MU += (double)(s.mu + eM); s.VE += (double)s.ve; s.VB += (double)s.vb;
+        s.MU += (double)(s.mu + eM); s.VE += (double)s.ve; s.VB += (double)s.vb; s.PI += (double)s.Pi;
         s.post_count += 1;
       }
     }
@@ -147,9 +192,20 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
     *scp = s;
     s_eM = eM;
     s_acc = accumulate;
+    s_ve = s.ve; s_cxx = s.cxx;
   }
   __syncthreads();
   const float eM = s_eM;
+  if (model == M_EMDE && vbv) {  // :293-296 ; Vb_j = b_j^2 + Ve/(xx_j + Lmb_j + 1e-4), Lmb_j = sqrt(cxx Ve / Vb_j)
+    const float* xx = a.xx + (a.xx_per_sys ? (size_t)sys * a.p : 0);
+    const float Ve = s_ve, cxx = s_cxx;
+    for (int j = tid; j < a.p; j += T) {
+      float xxj = xx[j];
+      if (xxj == 0.0f) xxj = 0.1f;  // :261
+      const float Vb = b[j] * b[j] + Ve / (xxj + vbv[j] + 0.0001f);
+      vbv[j] = sqrtf(cxx * Ve / Vb);
+    }
+  }
   if (eM != 0.0f)
     for (int i = tid; i < a.n; i += T) {
       if (mask && !mask[i]) continue;

@@ -153,7 +153,8 @@ void launch_block_inverse(int model, const int* perm, int p, int nblocks, const 
 struct EpilogueArgs {
   int model, nsys, n, p;
   int64_t ld;
-  float* e; const float* y; float* b; const float* d; const float* vbv; const float* b_prev;  // b_prev: emEN convergence
+  float* e; const float* y; float* b; const float* d; float* vbv; const float* b_prev;  // b_prev: convergence (model_has_cnv)
+  const float* xx; int xx_per_sys;  // emDE: the per-marker penalty update needs xx_j
   const uint8_t* mask;
   SysScalars* sc;
   float* B; float* D; float* VBv;

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
     if (tid == 0) {
       b[j] = r.b;
       if (model_has_d(MODEL) && dvec) dvec[j] = r.d;
-      if (model_has_vbj(MODEL) && MODEL != M_KMUP && vbv) vbv[j] = r.vbj;
+      if (model_rule_writes_vbj(MODEL) && vbv) vbv[j] = r.vbj;
     }
 
     // ---- e -= x_j * de on this thread's chunks
@@ -217,13 +217,17 @@ static void launch_small_model(const SmallNArgs& a, size_t smem_limit, cudaStrea
 }
 
 void launch_small_n(const SmallNArgs& a, size_t smem_limit, cudaStream_t st) {
-  switch (a.model) {
+  switch (rule_model(a.model)) {
     case M_EMRR: launch_small_model<M_EMRR>(a, smem_limit, st); break;
     case M_EMBA: launch_small_model<M_EMBA>(a, smem_limit, st); break;
     case M_EMBB: launch_small_model<M_EMBB>(a, smem_limit, st); break;
     case M_EMBC: launch_small_model<M_EMBC>(a, smem_limit, st); break;
     case M_EMBL: launch_small_model<M_EMBL>(a, smem_limit, st); break;
     case M_EMEN: launch_small_model<M_EMEN>(a, smem_limit, st); break;
+    case M_EMDE: launch_small_model<M_EMDE>(a, smem_limit, st); break;
+    case M_LASSO: launch_small_model<M_LASSO>(a, smem_limit, st); break;
+    case M_BL: launch_small_model<M_BL>(a, smem_limit, st); break;
+    case M_BDPI: launch_small_model<M_BDPI>(a, smem_limit, st); break;
     case M_BRR: launch_small_model<M_BRR>(a, smem_limit, st); break;
     case M_BA: launch_small_model<M_BA>(a, smem_limit, st); break;
     case M_BB: launch_small_model<M_BB>(a, smem_limit, st); break;

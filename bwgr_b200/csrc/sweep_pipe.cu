@@ -757,10 +757,10 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
           const float bnew = fmaf(deq, (MODEL == M_EMBA) ? 0.5f : 1.0f, in.b0);
           float vnew = in.vbj;
           if (MODEL == M_EMBA) vnew = (Sy.Sb + bnew * bnew) / (Sy.df + 1.0f);
-          if (MODEL == M_BA) vnew = (Sy.Sb + bnew * bnew) / drb[jj].chi;
+          if (MODEL == M_BA || MODEL == M_BL) vnew = (Sy.Sb + bnew * bnew) / drb[jj].chi;
           const int j = mc[jj].j;
           a.b[j] = bnew;
-          if (model_has_vbj(MODEL) && a.vbv) a.vbv[j] = vnew;
+          if (model_rule_writes_vbj(MODEL) && a.vbv) a.vbv[j] = vnew;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.solve_done[slot]);
@@ -997,14 +997,14 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
               if (kLinear) {
                 bnew = fmaf(deq, (MODEL == M_EMBA) ? 0.5f : 1.0f, in.b0);
                 if (MODEL == M_EMBA) vnew = (Sy.Sb + bnew * bnew) / (Sy.df + 1.0f);
-                if (MODEL == M_BA) vnew = (Sy.Sb + bnew * bnew) / drb[jj].chi;
+                if (MODEL == M_BA || MODEL == M_BL) vnew = (Sy.Sb + bnew * bnew) / drb[jj].chi;
               } else {
                 bnew = nb[t];
               }
               const int j = mc[jj].j;
               a.b[(size_t)s * p + j] = bnew;
               if (model_has_d(MODEL) && a.d) a.d[(size_t)s * p + j] = dnew;
-              if (model_has_vbj(MODEL) && MODEL != M_KMUP && a.vbv) a.vbv[(size_t)s * p + j] = vnew;
+              if (model_rule_writes_vbj(MODEL) && a.vbv) a.vbv[(size_t)s * p + j] = vnew;
             }
           }
         }
@@ -1186,7 +1186,7 @@ size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int srin
 
 void launch_sweep_pipe(const PipeArgs& a, cudaStream_t st) {
   const size_t smem = sweep_pipe_smem(a.rows_per_cta, a.nsys, a.model, a.nbuf, a.sring, a.tinv != nullptr);
-  switch (a.model) {
+  switch (rule_model(a.model)) {
     case M_EMRR: launch_model<M_EMRR>(a, smem, st); break;
     case M_EMBA: launch_model<M_EMBA>(a, smem, st); break;
     case M_EMBB: launch_model<M_EMBB>(a, smem, st); break;
@@ -1199,6 +1199,10 @@ void launch_sweep_pipe(const PipeArgs& a, cudaStream_t st) {
     case M_BC: launch_model<M_BC>(a, smem, st); break;
     case M_KMUP: launch_model<M_KMUP>(a, smem, st); break;
     case M_MRR: launch_model<M_MRR>(a, smem, st); break;
+    case M_EMDE: launch_model<M_EMDE>(a, smem, st); break;
+    case M_LASSO: launch_model<M_LASSO>(a, smem, st); break;
+    case M_BL: launch_model<M_BL>(a, smem, st); break;
+    case M_BDPI: launch_model<M_BDPI>(a, smem, st); break;
     default: break;
   }
 }

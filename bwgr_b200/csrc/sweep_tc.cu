@@ -494,14 +494,14 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
           if (model_is_linear(MODEL)) {
             bnew = fmaf(deq, in.ikappa, in.b0);
             if (MODEL == M_EMBA) vnew = (Sy.Sb + bnew * bnew) / (Sy.df + 1.0f);
-            if (MODEL == M_BA) vnew = (Sy.Sb + bnew * bnew) / drb[s * 128 + jj].chi;
+            if (MODEL == M_BA || MODEL == M_BL) vnew = (Sy.Sb + bnew * bnew) / drb[s * 128 + jj].chi;
           } else {
             bnew = nb[t];
           }
           if (blockIdx.x == 0) {
             a.b[(size_t)s * p + in.j] = bnew;
             if (model_has_d(MODEL) && a.d) a.d[(size_t)s * p + in.j] = dnew;
-            if (model_has_vbj(MODEL) && MODEL != M_KMUP && a.vbv) a.vbv[(size_t)s * p + in.j] = vnew;
+            if (model_rule_writes_vbj(MODEL) && a.vbv) a.vbv[(size_t)s * p + in.j] = vnew;
           }
         }
       }
@@ -583,7 +583,7 @@ void launch_model(const SweepArgs& a, int grid, cudaStream_t st) {
 size_t sweep_blocked_smem(int rows_per_cta, int nsys) { return make_layout(rows_per_cta, nsys, true).total + 2048; }
 
 void launch_sweep_blocked(const SweepArgs& a, int grid, cudaStream_t st) {
-  switch (a.model) {
+  switch (rule_model(a.model)) {
     case M_EMRR: launch_model<M_EMRR>(a, grid, st); break;
     case M_EMBA: launch_model<M_EMBA>(a, grid, st); break;
     case M_EMBB: launch_model<M_EMBB>(a, grid, st); break;
@@ -596,6 +596,10 @@ void launch_sweep_blocked(const SweepArgs& a, int grid, cudaStream_t st) {
     case M_BC: launch_model<M_BC>(a, grid, st); break;
     case M_KMUP: launch_model<M_KMUP>(a, grid, st); break;
     case M_MRR: launch_model<M_MRR>(a, grid, st); break;
+    case M_EMDE: launch_model<M_EMDE>(a, grid, st); break;
+    case M_LASSO: launch_model<M_LASSO>(a, grid, st); break;
+    case M_BL: launch_model<M_BL>(a, grid, st); break;
+    case M_BDPI: launch_model<M_BDPI>(a, grid, st); break;
     default: break;
   }
 }

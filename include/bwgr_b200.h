@@ -49,7 +49,12 @@ enum bwgr_em_model {
   BWGR_EM_BB = 2, /* emBB :131-187 */
   BWGR_EM_BC = 3, /* emBC :190-247 */
   BWGR_EM_BL = 4, /* emBL :357-397 */
-  BWGR_EM_EN = 5  /* emEN :400-460 */
+  BWGR_EM_EN = 5, /* emEN :400-460 */
+  /* the rest of emCV's ten-model panel (R/cv.R:13-22) */
+  BWGR_EM_DE = 6,   /* emDE   :250-306   */
+  BWGR_EM_ML = 7,   /* emML   :463-520 (D = NULL) */
+  BWGR_EM_BCPI = 8, /* emBCpi :1502-1546 */
+  BWGR_EM_LASSO = 9 /* lasso  :1463-1500 */
 };
 
 /* Univariate Gibbs samplers of src/Rcpp20260726ai.cpp. */
@@ -57,8 +62,14 @@ enum bwgr_gibbs_model {
   BWGR_GIBBS_RR = 0, /* BayesRR :812-855 */
   BWGR_GIBBS_A = 1,  /* BayesA  :589-635 */
   BWGR_GIBBS_B = 2,  /* BayesB  :638-699 */
-  BWGR_GIBBS_C = 3   /* BayesC  :702-759 */
+  BWGR_GIBBS_C = 3,  /* BayesC  :702-759 */
+  /* the rest of mcmcCV's seven-model panel (R/cv.R:124-130) */
+  BWGR_GIBBS_L = 4,   /* BayesL   :762-809 */
+  BWGR_GIBBS_CPI = 5, /* BayesCpi :858-919 (pi starts at 0.5; params.pi is ignored) */
+  BWGR_GIBBS_DPI = 6  /* BayesDpi :922-987 (same) */
 };
+
+#define BWGR_NSCAL 6 /* scalars per system in bwgr_em_out.scal / bwgr_gibbs_out.scal */
 
 /* Which kernel family runs the sweep. AUTO picks SMALL_N when several systems share X and the
  * residual of one system fits one SM's shared memory, BLOCKED otherwise. */
@@ -95,7 +106,7 @@ BWGR_API int bwgr_geno_stats(bwgr_handle* h, double* xx, double* sx);
 typedef struct {
   int model;     /* bwgr_em_model */
   int nsys;      /* systems (traits / folds) sharing the genotypes; y is n x nsys */
-  int it;        /* sweeps; <0 = the reference's hard-coded 200 (emEN: maxit 300 with its tol) */
+  int it;        /* sweeps; <0 = the reference's hard-coded 200 (emEN, emDE, emML, lasso: maxit 300 with their tol) */
   double df, R2, Pi, alpha; /* reference defaults: 10, 0.5, 0.75, 0.02 */
   const uint8_t* row_mask;  /* optional n x nsys, 1 = row used by the system (CV folds); NULL = all */
 } bwgr_em_params;
@@ -103,10 +114,10 @@ typedef struct {
 typedef struct {
   double* mu;   /* [nsys] */
   double* b;    /* [p x nsys] */
-  double* d;    /* [p x nsys] inclusion (emBB, emBC) or NULL */
+  double* d;    /* [p x nsys] inclusion (emBB, emBC, emBCpi) or NULL */
   double* hat;  /* [n x nsys] */
-  double* vb;   /* [p x nsys] per-marker Vb (emBA, emBB) or NULL */
-  double* scal; /* [4 x nsys]: Va, Ve, h2, Vg (as each model defines them) */
+  double* vb;   /* [p x nsys] per-marker Vb (emBA, emBB, emDE) or NULL */
+  double* scal; /* [BWGR_NSCAL x nsys]: Va, Ve, h2, Vg (as each model defines them; emML: Vg slot = Vb), pi (emBCpi), Lmb (lasso) */
   int* its;     /* [nsys] sweeps done */
 } bwgr_em_out;
 
@@ -129,10 +140,10 @@ typedef struct {
 typedef struct {
   double* mu;   /* [nchains] */
   double* b;    /* [p x nchains] posterior means */
-  double* d;    /* [p x nchains] (BayesB/C) or NULL */
+  double* d;    /* [p x nchains] (BayesB/C/Cpi/Dpi; the reference's PVAL is -log(1 - d)) or NULL */
   double* hat;  /* [n x nchains] */
-  double* vb;   /* [p x nchains] (BayesA/B) or [nchains] (BayesRR/C) */
-  double* scal; /* [4 x nchains]: vb (scalar models), ve, h2, MSx */
+  double* vb;   /* [p x nchains] (BayesA/B/L/Dpi) or [nchains] (BayesRR/C/Cpi) */
+  double* scal; /* [BWGR_NSCAL x nchains]: vb (scalar models), ve, h2, MSx, pi (BayesCpi/Dpi), reserved */
 } bwgr_gibbs_out;
 
 BWGR_API int bwgr_gibbs_fit(bwgr_handle* h, const bwgr_gibbs_params* par, const double* y, bwgr_gibbs_out* out);

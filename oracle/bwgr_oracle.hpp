@@ -95,13 +95,14 @@ struct Shuffler {
 // Univariate EM solvers.  X: n x p column-major, same element type as the arithmetic (the
 // reference casts R doubles to Eigen::MatrixXf, RcppExports.cpp:115).
 // ------------------------------------------------------------------------------------------------
-enum EmModel { EM_RR = 0, EM_BA = 1, EM_BB = 2, EM_BC = 3, EM_BL = 4, EM_EN = 5 };
+enum EmModel { EM_RR = 0, EM_BA = 1, EM_BB = 2, EM_BC = 3, EM_BL = 4, EM_EN = 5, EM_DE = 6, EM_ML = 7, EM_BCPI = 8, EM_LASSO = 9 };
 
 template <class R>
 struct EmOut {
   R mu = 0;
   std::vector<R> b, d, hat, vbv;  // vbv: per-marker Vb (emBA/emBB)
   R Va = 0, Ve = 0, h2 = 0, Vg = 0;
+  R pi = 0, Lmb = 0;  // emBCpi's updated Pi; lasso's final penalty
   int its = 0;
 };
 
@@ -401,6 +402,178 @@ static void emEN(const R* y, const R* X, int n, int p, const EmPar<R>& P, EmOut<
   fitted(X, n, p, b, mu, o.hat);
 }
 
+// emDE: Rcpp20260726ai.cpp:250-306.  Ridge step with a per-marker penalty that the sweep epilogue re-estimates
+// (double-exponential flavour); stops on sum |b_old - b_new| < 1e-5 or after 300 sweeps.
+template <class R>
+static void emDE(const R* y, const R* X, int n, int p, const EmPar<R>& P, EmOut<R>& o) {
+  const int maxit = P.it < 0 ? 300 : P.it;
+  const R tol = R(10e-6f), R2 = P.R2;
+  R mu = vmean(y, n);
+  std::vector<R> e(n);
+  for (int i = 0; i < n; i++) e[i] = y[i] - mu;
+  std::vector<R> xx, vx;
+  xx_vx(X, n, p, xx, &vx);
+  for (int k = 0; k < p; k++) if (xx[k] == 0) xx[k] = R(0.1f);  // :261
+  const R cxx = vsum(vx.data(), p) * (1 - R2) / R2;
+  R Ve = 0;
+  std::vector<R> Vb(p, R(0)), b(p, R(0)), Lmb(p, (R)p + cxx), bc(p);
+  int numit = 0;
+  Shuffler sh(p);
+  while (numit < maxit) {
+    bc = b;
+    sh.next(numit);
+    for (int jj = 0; jj < p; jj++) {
+      const int j = sh.order[jj];
+      const R* x = X + (size_t)j * n;
+      const R b0 = b[j];
+      const R b1 = (vdot(x, e.data(), n) + xx[j] * b0) / (Lmb[j] + xx[j]);
+      b[j] = b1;
+      axpy_sub(e.data(), x, b1 - b0, n);
+    }
+    const R eM = vmean(e.data(), n);
+    mu += eM;
+    for (int r = 0; r < n; r++) e[r] -= eM;
+    Ve = vdot(e.data(), y, n) / (n - 1);
+    for (int j = 0; j < p; j++) Vb[j] = b[j] * b[j] + Ve / (xx[j] + Lmb[j] + R(0.0001f));
+    for (int j = 0; j < p; j++) Lmb[j] = std::sqrt(cxx * Ve / Vb[j]);
+    ++numit;
+    const R cnv = reduce_sum<R>(p, [&](int j) { return std::fabs(bc[j] - b[j]); });
+    if (cnv < tol) break;
+  }
+  const R sVb = vsum(Vb.data(), p);
+  o.its = numit; o.mu = mu; o.b = b; o.vbv = Vb; o.Ve = Ve; o.h2 = sVb / (sVb + Ve);
+  fitted(X, n, p, b, mu, o.hat);
+}
+
+// emML: Rcpp20260726ai.cpp:463-520 with D = NULL (no marker weights).  Ridge step; the variance components come from
+// the moment identities ve = (y-mu)'e/n, vb = (y-mu)'(y-mu-e)/(n MSx); hat is y - e.
+template <class R>
+static void emML(const R* y, const R* X, int n, int p, const EmPar<R>& P, EmOut<R>& o) {
+  const int maxit = P.it < 0 ? 300 : P.it;
+  const R tol = R(10e-8f);
+  R mu = vmean(y, n), ve = 0, vb = 0;
+  std::vector<R> b(p, R(0)), bc(p), e(n), yc(n);
+  for (int i = 0; i < n; i++) e[i] = y[i] - mu;
+  std::vector<R> xx, vx;
+  xx_vx(X, n, p, xx, &vx);
+  const R MSx = vsum(vx.data(), p);
+  R Lmb = MSx;
+  int numit = 0;
+  Shuffler sh(p);
+  while (numit < maxit) {
+    bc = b;
+    sh.next(numit);
+    for (int jj = 0; jj < p; jj++) {
+      const int j = sh.order[jj];
+      const R* x = X + (size_t)j * n;
+      const R b0 = b[j];
+      b[j] = (vdot(x, e.data(), n) + xx[j] * b0) / (xx[j] + Lmb);
+      axpy_sub(e.data(), x, b[j] - b0, n);
+    }
+    const R eM = vmean(e.data(), n);
+    mu += eM;
+    for (int r = 0; r < n; r++) e[r] -= eM;
+    for (int r = 0; r < n; r++) yc[r] = y[r] - mu;
+    ve = vdot(yc.data(), e.data(), n) / (R)n;
+    vb = reduce_sum<R>(n, [&](int r) { return yc[r] * (yc[r] - e[r]); }) / (R)(n * MSx);
+    Lmb = ve / vb;
+    ++numit;
+    const R cnv = reduce_sum<R>(p, [&](int j) { return std::fabs(bc[j] - b[j]); });
+    if (cnv < tol) break;
+  }
+  o.its = numit; o.mu = mu; o.b = b; o.Vg = vb; o.Va = vb * MSx; o.Ve = ve; o.h2 = vb * MSx / (vb * MSx + ve);
+  o.hat.resize(n);
+  for (int r = 0; r < n; r++) o.hat[r] = y[r] - e[r];
+}
+
+// emBCpi: Rcpp20260726ai.cpp:1502-1546.  emBC's step in the natural marker order, with the mixture proportion
+// re-estimated after every sweep from the mean inclusion (and MSx, Sa with it).
+template <class R>
+static void emBCpi(const R* y, const R* X, int n, int p, const EmPar<R>& P, EmOut<R>& o) {
+  const int it = P.it < 0 ? 200 : P.it;
+  const R df = P.df, R2 = P.R2;
+  R Pi = P.Pi;
+  std::vector<R> d(p, R(0)), b(p, R(0));
+  const R vy = fvar(y, n);
+  if (Pi > R(0.5)) Pi = 1 - Pi;
+  std::vector<R> xx, vx;
+  xx_vx(X, n, p, xx, &vx);
+  const R PriorPi = Pi, svx = vsum(vx.data(), p);
+  R MSx = svx * Pi * (1 - Pi);
+  R Sa = R2 * (df + 2) * vy / MSx;
+  const R Se = (1 - R2) * (df + 2) * vy;
+  R mu = vmean(y, n);
+  std::vector<R> e(n), t1(n), t2(n);
+  for (int i = 0; i < n; i++) e[i] = y[i] - mu;
+  R ve = Sa, va = Se, Lmb = ve / va, Pi0 = (1 - Pi) / Pi;
+  for (int i = 0; i < it; i++) {
+    const R C = R(-0.5) / std::sqrt(ve);
+    for (int j = 0; j < p; j++) {
+      const R* x = X + (size_t)j * n;
+      const R b0 = b[j];
+      const R b1 = (vdot(x, e.data(), n) + xx[j] * b0) / (xx[j] + Lmb);
+      const R n1 = sq_after(e.data(), x, b1 - b0, t1.data(), n);
+      const R n2 = sq_after(e.data(), x, R(0) - b0, t2.data(), n);
+      const R LR = Pi0 * std::exp(C * (n2 - n1));
+      d[j] = 1 / (1 + LR);
+      b[j] = b1 * d[j];
+      axpy_sub(e.data(), x, b[j] - b0, n);
+    }
+    const R dm = vmean(d.data(), p);
+    Pi = ((1 - dm) * p + PriorPi * df) / (p + df);
+    Pi0 = (1 - Pi) / Pi;
+    MSx = svx * Pi * (1 - Pi);
+    Sa = R2 * (df + 2) * vy / MSx;
+    ve = (vsq(e.data(), n) + Se) / (n + df);
+    va = (vsq(b.data(), p) + Sa) / (p + df) / (dm - Pi);
+    Lmb = ve / va;
+    const R eM = vmean(e.data(), n);
+    mu += eM;
+    for (int r = 0; r < n; r++) e[r] -= eM;
+  }
+  o.its = it; o.mu = mu; o.b = b; o.d = d; o.pi = Pi; o.Vg = va * MSx; o.Va = va; o.Ve = ve; o.h2 = 1 - ve / vy;
+  fitted(X, n, p, b, mu, o.hat);
+}
+
+// lasso: Rcpp20260726ai.cpp:1463-1500.  Soft-threshold coordinate descent in the natural order; the penalty is
+// re-estimated after every sweep from how much of each marker's x'e the threshold removed.
+template <class R>
+static void lasso(const R* y, const R* X, int n, int p, const EmPar<R>& P, EmOut<R>& o) {
+  const int maxit = P.it < 0 ? 300 : P.it;
+  const R tol = R(10e-8f);
+  R mu = vmean(y, n);
+  std::vector<R> b(p, R(0)), bc(p), yx(p, R(0)), e(n);
+  for (int i = 0; i < n; i++) e[i] = y[i] - mu;
+  std::vector<R> xx;
+  xx_vx<R>(X, n, p, xx, nullptr);
+  R Lmb = vmean(xx.data(), p) / p;
+  int numit = 0;
+  while (numit < maxit) {
+    bc = b;
+    for (int j = 0; j < p; j++) {
+      const R* x = X + (size_t)j * n;
+      axpy_sub(e.data(), x, -b[j], n);  // e += x b_j
+      yx[j] = vdot(e.data(), x, n);
+      if (yx[j] > 0) { b[j] = (yx[j] - Lmb) / xx[j]; if (b[j] < 0) b[j] = 0; }
+      else           { b[j] = (yx[j] + Lmb) / xx[j]; if (b[j] > 0) b[j] = 0; }
+      axpy_sub(e.data(), x, b[j], n);
+    }
+    R tmp = 0;
+    for (int j = 0; j < p; j++) tmp += std::fabs(yx[j]) - std::fabs(b[j] * xx[j]);
+    Lmb = R(2) * tmp / p;
+    Lmb = R(2) * std::sqrt(std::fabs(Lmb));
+    const R eM = vmean(e.data(), n);
+    mu += eM;
+    for (int r = 0; r < n; r++) e[r] -= eM;
+    ++numit;
+    const R cnv = reduce_sum<R>(p, [&](int j) { return std::fabs(bc[j] - b[j]); });
+    if (cnv < tol) break;
+  }
+  o.its = numit; o.mu = mu; o.b = b; o.Lmb = Lmb; o.h2 = 1 - (vdot(e.data(), y, n) / (n - 1)) / fvar(y, n);
+  o.hat.resize(n);
+  for (int r = 0; r < n; r++) o.hat[r] = y[r] - e[r];
+}
+
 template <class R>
 static void em_fit(int model, const R* y, const R* X, int n, int p, const EmPar<R>& P, EmOut<R>& o) {
   switch (model) {
@@ -410,6 +583,10 @@ static void em_fit(int model, const R* y, const R* X, int n, int p, const EmPar<
     case EM_BC: emBC(y, X, n, p, P, o); break;
     case EM_BL: emBL(y, X, n, p, P, o); break;
     case EM_EN: emEN(y, X, n, p, P, o); break;
+    case EM_DE: emDE(y, X, n, p, P, o); break;
+    case EM_ML: emML(y, X, n, p, P, o); break;
+    case EM_BCPI: emBCpi(y, X, n, p, P, o); break;
+    case EM_LASSO: lasso(y, X, n, p, P, o); break;
   }
 }
 
@@ -432,15 +609,18 @@ struct Rng {
 // ------------------------------------------------------------------------------------------------
 // Univariate Gibbs samplers (float32 state; natural marker order).
 // ------------------------------------------------------------------------------------------------
-enum GibbsModel { GB_RR = 0, GB_A = 1, GB_B = 2, GB_C = 3 };
+enum GibbsModel { GB_RR = 0, GB_A = 1, GB_B = 2, GB_C = 3, GB_L = 4, GB_CPI = 5, GB_DPI = 6 };
 
 template <class R>
 struct GibbsOut {
-  R mu = 0, vb = 0, ve = 0, h2 = 0, MSx = 0;
+  R mu = 0, vb = 0, ve = 0, h2 = 0, MSx = 0, pi = 0;  // pi: BayesCpi / BayesDpi (1 - mean inclusion)
   std::vector<R> b, d, hat, vbv;
 };
 
-// BayesRR :812-855, BayesA :589-635, BayesB :638-699, BayesC :702-759 of Rcpp20260726ai.cpp
+// BayesRR :812-855, BayesA :589-635, BayesB :638-699, BayesC :702-759, BayesL :762-809, BayesCpi :858-919,
+// BayesDpi :922-987 of Rcpp20260726ai.cpp.  BayesL = BayesA with Lmb_j = sqrt(Phi ve / vb_j) after the first sweep;
+// BayesCpi = BayesC started at pi = 0.5 whose prior scale Sb follows the mean inclusion (the mixing odds Pi0 stay fixed);
+// BayesDpi = per-marker variances with the Kuo-Mallick style acceptance min(1, (1 - pi) exp(C(|e1|^2 - |e2|^2))), pi = mean(d).
 template <class R>
 static void gibbs_fit(int model, const R* y, const R* X, int n, int p, R it_f, R bi_f, R pi, R df, R R2,
                       uint64_t seed, GibbsOut<R>& o) {
@@ -451,10 +631,14 @@ static void gibbs_fit(int model, const R* y, const R* X, int n, int p, R it_f, R
   xx_vx(X, n, p, xx, &vx);
   const R MSx = vsum(vx.data(), p);
   const R vy = fvar(y, n);
-  R Sb = (model == GB_C) ? df * R2 * vy / MSx / (1 - pi) : R2 * df * vy / MSx;
-  const R Se = (model == GB_C) ? df * (1 - R2) * vy : (1 - R2) * df * vy;
-  const bool per_marker = (model == GB_A || model == GB_B);
-  const bool spike = (model == GB_B || model == GB_C);
+  if (model == GB_CPI || model == GB_DPI) pi = R(0.5f);  // :870, :934 (not an argument of these two)
+  const bool c_like = (model == GB_C || model == GB_CPI);
+  R Sb = c_like ? df * R2 * vy / MSx / (1 - pi) : R2 * df * vy / MSx;
+  const R Se = c_like ? df * (1 - R2) * vy : (1 - R2) * df * vy;
+  const R Phi = MSx * (1 - R2) / R2;  // BayesL :773
+  const bool per_marker = (model == GB_A || model == GB_B || model == GB_L || model == GB_DPI);
+  const bool spike = (model == GB_B || model == GB_C || model == GB_CPI || model == GB_DPI);
+  R PiSum = 0;
   std::vector<R> d(p, R(0)), b(p, R(0)), D(p, R(0)), B(p, R(0)), VBv(p, R(0));
   std::vector<R> vbv(p, Sb), Lmbv(p);
   R ve = vy, vb = Sb, VB = 0, MU = 0, VE = 0;
@@ -472,7 +656,16 @@ static void gibbs_fit(int model, const R* y, const R* X, int n, int p, R it_f, R
       const R b0 = b[j];
       const R sd = std::sqrt(ve / (xx[j] + L));
       const R b1 = (R)rng.rnorm((vdot(x, e.data(), n) + xx[j] * b0) / (xx[j] + L), sd);
-      if (spike) {
+      if (model == GB_CPI || model == GB_DPI) {  // both draw b2 before the test (:886, :951)
+        const R b2 = (R)rng.rnorm(0, sd);
+        const R n1 = sq_after(e.data(), x, b1 - b0, t1.data(), n);
+        const R n2 = sq_after(e.data(), x, (model == GB_DPI ? b2 : R(0)) - b0, t2.data(), n);
+        R pj;
+        if (model == GB_CPI) pj = R(1.0) / (R(1.0) + Pi0 * std::exp(C * (n2 - n1)));
+        else { pj = (1 - pi) * std::exp(C * (n1 - n2)); if (pj > 1) pj = 1; }
+        if (rng.rbinom1(pj) == 1) { b[j] = b1; d[j] = 1; }
+        else { b[j] = b2; d[j] = 0; }
+      } else if (spike) {
         const R n1 = sq_after(e.data(), x, b1 - b0, t1.data(), n);
         const R n2 = sq_after(e.data(), x, R(0) - b0, t2.data(), n);
         const R LR = Pi0 * std::exp(C * (n2 - n1));
@@ -492,13 +685,16 @@ static void gibbs_fit(int model, const R* y, const R* X, int n, int p, R it_f, R
       ve = (vsq(e.data(), n) + Se) / (R)rng.rchisq(n + df);
       vb = (vsq(b.data(), p) + Sb) / (R)rng.rchisq(p + df);
       Lmb = ve / vb;
-    } else if (model == GB_C) {  // :745-747 (vb first, then ve)
+    } else if (c_like) {  // :745-747, :903-907 (vb first, then ve)
       vb = (vsq(b.data(), p) + Sb) / (R)rng.rchisq(df + p);
       ve = (vsq(e.data(), n) + Se) / (R)rng.rchisq(n + df);
       Lmb = ve / vb;
+      if (model == GB_CPI) { pi = vmean(d.data(), p); Sb = df * R2 * vy / MSx / (1 - pi); }  // Pi0 is NOT refreshed (:906-907)
     } else {
       ve = (vsq(e.data(), n) + Se) / (R)rng.rchisq(n + df);
-      for (int j = 0; j < p; j++) Lmbv[j] = ve * (R(1) / vbv[j]);
+      if (model == GB_L) for (int j = 0; j < p; j++) Lmbv[j] = std::sqrt(Phi * ve / vbv[j]);  // :799
+      else for (int j = 0; j < p; j++) Lmbv[j] = ve * (R(1) / vbv[j]);
+      if (model == GB_DPI) pi = vmean(d.data(), p);  // :969
     }
     if (i > ibi) {  // sic: i>ibi yet divided by it-bi (:624-627)
       MU += mu; VE += ve;
@@ -506,12 +702,15 @@ static void gibbs_fit(int model, const R* y, const R* X, int n, int p, R it_f, R
       if (spike) for (int j = 0; j < p; j++) D[j] += d[j];
       if (per_marker) for (int j = 0; j < p; j++) VBv[j] += vbv[j];
       else VB += vb;
+      PiSum += pi;
     }
   }
   MU /= MCMC; VE /= MCMC;
   for (int j = 0; j < p; j++) { B[j] /= MCMC; D[j] /= MCMC; VBv[j] /= MCMC; }
   VB /= MCMC;
   R vg = per_marker ? vsum(VBv.data(), p) : VB * MSx;
+  if (model == GB_CPI || model == GB_DPI) o.pi = 1 - PiSum / MCMC;  // :911, :975
+  if (model == GB_CPI) vg = VB * MSx / o.pi;                         // :913
   o.mu = MU; o.b = B; o.d = D; o.vbv = VBv; o.vb = VB; o.ve = VE; o.h2 = vg / (vg + VE); o.MSx = MSx;
   fitted(X, n, p, B, MU, o.hat);
 }

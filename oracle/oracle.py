@@ -13,8 +13,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBS = {}
 
-EM_MODELS = {"emRR": 0, "emBA": 1, "emBB": 2, "emBC": 3, "emBL": 4, "emEN": 5}
-GIBBS_MODELS = {"BayesRR": 0, "BayesA": 1, "BayesB": 2, "BayesC": 3}
+EM_MODELS = {"emRR": 0, "emBA": 1, "emBB": 2, "emBC": 3, "emBL": 4, "emEN": 5, "emDE": 6, "emML": 7, "emBCpi": 8, "lasso": 9}
+GIBBS_MODELS = {"BayesRR": 0, "BayesA": 1, "BayesB": 2, "BayesC": 3, "BayesL": 4, "BayesCpi": 5, "BayesDpi": 6}
 
 MRR3_DEFAULTS = dict(
     maxit=500, tol=10e-9, cores=1, TH=False, NLfactor=0.0, InnerGS=False, NoInv=False, HCS=False, XFA=False,
@@ -62,13 +62,13 @@ def em(model, y, gen, df=10.0, R2=0.5, Pi=0.75, alpha=0.02, it=-1, use_double=Fa
     its = C.c_int()
     b, d, vbv = (np.zeros(p) for _ in range(3))
     hat = np.zeros(n)
-    scal = np.zeros(4)
+    scal = np.zeros(6)
     rc = lib(native).orc_em(C.c_int(EM_MODELS[model]), C.c_int(int(use_double)), _p(y, C.c_float), _p(X, C.c_float),
                             C.c_int(n), C.c_int(p), C.c_float(df), C.c_float(R2), C.c_float(Pi), C.c_float(alpha),
                             C.c_int(it), C.byref(mu), _p(b, C.c_double), _p(d, C.c_double), _p(hat, C.c_double),
                             _p(vbv, C.c_double), _p(scal, C.c_double), C.byref(its))
     assert rc == 0
-    Va, Ve, h2, Vg = scal
+    Va, Ve, h2, Vg, pi_out, lmb_out = scal
     out = {"mu": mu.value, "b": b, "hat": hat, "its": its.value}
     if model == "emRR":
         out.update(Va=Va, Ve=Ve, h2=h2)
@@ -82,6 +82,14 @@ def em(model, y, gen, df=10.0, R2=0.5, Pi=0.75, alpha=0.02, it=-1, use_double=Fa
         out.update(h2=h2)
     elif model == "emEN":
         out.update(Va=Va, Ve=Ve, h2=h2)
+    elif model == "emDE":
+        out.update(Vb=vbv, Ve=Ve, h2=h2)
+    elif model == "emML":
+        out.update(h2=h2, Vb=Vg, Va=Va, Ve=Ve)
+    elif model == "emBCpi":
+        out.update(d=d, pi=pi_out, Vg=Vg, Va=Va, Ve=Ve, h2=h2)
+    elif model == "lasso":
+        out.update(h2=h2, Lmb=lmb_out)
     return out
 
 
@@ -92,17 +100,22 @@ def gibbs(model, y, X, it=1500, bi=500, pi=0.95, df=5.0, R2=0.5, seed=1):
     mu = C.c_double()
     b, d, vbv = (np.zeros(p) for _ in range(3))
     hat = np.zeros(n)
-    scal = np.zeros(4)
+    scal = np.zeros(5)
     rc = lib().orc_gibbs(C.c_int(GIBBS_MODELS[model]), _p(y, C.c_float), _p(X, C.c_float), C.c_int(n), C.c_int(p),
                          C.c_float(it), C.c_float(bi), C.c_float(pi), C.c_float(df), C.c_float(R2),
                          C.c_uint64(seed), C.byref(mu), _p(b, C.c_double), _p(d, C.c_double), _p(hat, C.c_double),
                          _p(vbv, C.c_double), _p(scal, C.c_double))
     assert rc == 0
-    vb, ve, h2, MSx = scal
+    vb, ve, h2, MSx, pi_out = scal
     out = {"mu": mu.value, "b": b, "hat": hat, "ve": ve, "h2": h2, "MSx": MSx}
-    out["vb"] = vbv if model in ("BayesA", "BayesB") else vb
-    if model in ("BayesB", "BayesC"):
+    out["vb"] = vbv if model in ("BayesA", "BayesB", "BayesL", "BayesDpi") else vb
+    if model in ("BayesB", "BayesC", "BayesCpi", "BayesDpi"):
         out["d"] = d
+    if model in ("BayesCpi", "BayesDpi"):  # these two return pi and PVAL instead of MSx (:914-919, :982-987)
+        del out["MSx"]
+        out["pi"] = pi_out
+        with np.errstate(divide="ignore"):
+            out["PVAL"] = -np.log(1.0 - d)
     return out
 
 

@@ -26,7 +26,7 @@ void em_run(int model, const float* y, const float* X, int n, int p, float df, f
   for (int j = 0; j < p; j++) d[j] = o.d.empty() ? 0.0 : (double)o.d[j];
   for (int j = 0; j < p; j++) vbv[j] = o.vbv.empty() ? 0.0 : (double)o.vbv[j];
   for (int i = 0; i < n; i++) hat[i] = o.hat[i];
-  scal[0] = o.Va; scal[1] = o.Ve; scal[2] = o.h2; scal[3] = o.Vg;
+  scal[0] = o.Va; scal[1] = o.Ve; scal[2] = o.h2; scal[3] = o.Vg; scal[4] = o.pi; scal[5] = o.Lmb;
   *its = o.its;
 }
 }  // namespace
@@ -44,25 +44,25 @@ int orc_perm(int p, int n_iter, int32_t* out) {
 }
 
 // Univariate EM fit. use_double=0: float32 like the reference; 1: same recipe in float64 (to bound
-// float noise).  it<0: the reference's hard-coded sweep count.  scal = {Va, Ve, h2, Vg}.
+// float noise).  it<0: the reference's hard-coded sweep count.  scal = {Va, Ve, h2, Vg, pi, Lmb}.
 int orc_em(int model, int use_double, const float* y, const float* X, int n, int p, float df, float R2, float Pi,
            float alpha, int it, double* mu, double* b, double* d, double* hat, double* vbv, double* scal, int* its) {
-  if (model < 0 || model > 5) return -1;
+  if (model < 0 || model > 9) return -1;
   if (use_double) em_run<double>(model, y, X, n, p, df, R2, Pi, alpha, it, mu, b, d, hat, vbv, scal, its);
   else em_run<float>(model, y, X, n, p, df, R2, Pi, alpha, it, mu, b, d, hat, vbv, scal, its);
   return 0;
 }
 
-// Univariate Gibbs fit (float32 state). scal = {vb, ve, h2, MSx}.
+// Univariate Gibbs fit (float32 state). scal = {vb, ve, h2, MSx, pi}.
 int orc_gibbs(int model, const float* y, const float* X, int n, int p, float it, float bi, float pi, float df, float R2,
               uint64_t seed, double* mu, double* b, double* d, double* hat, double* vbv, double* scal) {
-  if (model < 0 || model > 3) return -1;
+  if (model < 0 || model > 6) return -1;
   orc::GibbsOut<float> o;
   orc::gibbs_fit<float>(model, y, X, n, p, it, bi, pi, df, R2, seed, o);
   *mu = o.mu;
   for (int j = 0; j < p; j++) { b[j] = o.b[j]; d[j] = o.d[j]; vbv[j] = o.vbv[j]; }
   for (int i = 0; i < n; i++) hat[i] = o.hat[i];
-  scal[0] = o.vb; scal[1] = o.ve; scal[2] = o.h2; scal[3] = o.MSx;
+  scal[0] = o.vb; scal[1] = o.ve; scal[2] = o.h2; scal[3] = o.MSx; scal[4] = o.pi;
   return 0;
 }
 

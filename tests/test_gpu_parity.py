@@ -18,7 +18,7 @@ bw = pytest.importorskip("bwgr_b200")
 RTOL = 1e-4  # stated tolerance of north_star for EM solvers after convergence
 
 
-def _close_em(out, ref, model, ref64=None):
+def _close_em(out, ref, model, ref64=None, check_its=True):
     """|gpu - oracle_f32| <= RTOL*scale, widened by the reference's own float noise floor
     |oracle_f32 - oracle_f64| (the float recipe is itself only that close to exact arithmetic)."""
     def noise(key):
@@ -30,14 +30,15 @@ def _close_em(out, ref, model, ref64=None):
     assert np.abs(out["b"] - ref["b"]).max() <= RTOL * scale + noise("b"), "b"
     assert np.abs(out["hat"] - ref["hat"]).max() <= RTOL * np.abs(ref["hat"]).max() + noise("hat"), "hat"
     assert abs(out["mu"] - ref["mu"]) <= RTOL * max(1.0, abs(ref["mu"])) + noise("mu"), "mu"
-    for key in ("Va", "Ve", "h2", "Vg"):
+    for key in ("Va", "Ve", "h2", "Vg", "pi", "Lmb") + (("Vb",) if model == "emML" else ()):
         if key in ref:
             assert abs(out[key] - ref[key]) <= RTOL * max(abs(ref[key]), 1e-3) + noise(key), key
     if "d" in ref:
         assert np.abs(out["d"] - ref["d"]).max() <= 1e-3, "d"
-    if "Vb" in ref and model in ("emBA", "emBB"):
+    if "Vb" in ref and model in ("emBA", "emBB", "emDE"):
         assert np.abs(out["Vb"] - ref["Vb"]).max() <= RTOL * np.abs(ref["Vb"]).max() + noise("Vb"), "Vb"
-    assert out["its"] == ref["its"]
+    if check_its:
+        assert out["its"] == ref["its"]
 
 
 @pytest.mark.parametrize("storage", [0, 1])
@@ -115,7 +116,7 @@ def test_gram_signed_values():
 @pytest.mark.parametrize("path", [1, 2])
 @pytest.mark.parametrize("model", list(O.EM_MODELS))
 def test_em_tpod_matches_golden(tpod, model, path):
-    """config[0]: the six EM solvers on the bundled tpod data, both kernel families."""
+    """config[0]: the ten EM solvers of emCV's panel (R/cv.R:13-22) on the bundled tpod data, both kernel families."""
     y, gen = tpod
     gold = np.load(os.path.join(GOLDEN, "tpod_em.npz"))
     ref = {k.split("__")[1]: gold[k] for k in gold.files if k.startswith(model + "_f32__")}
@@ -124,7 +125,35 @@ def test_em_tpod_matches_golden(tpod, model, path):
     ref64 = {k: (v.item() if v.ndim == 0 else v) for k, v in ref64.items()}
     with bw.Genotypes(gen, path=path) as g:
         out = bw.em_fit(model, y, g)
+    # emML stops on sum|db| < 1e-7, which float noise decides (the oracle's float and double recipes stop 39 sweeps apart):
+    # the converged fit is compared, the sweep count is only bounded
+    _close_em(out, ref, model, ref64, check_its=model != "emML")
+    assert 0 < out["its"] <= 300
+
+
+@pytest.mark.parametrize("path", [1, 2])
+@pytest.mark.parametrize("model", ["emDE", "emML", "emBCpi", "lasso"])
+def test_em_second_panel_fixed_sweeps(model, path):
+    """emDE / emML / emBCpi / lasso after a fixed number of sweeps (before any stopping rule can act), synthetic data with
+    a ragged last block, both kernel families, against the float oracle."""
+    X, y = synth(900, 333, seed=13)
+    ref = O.em(model, y, X.astype(np.float32), it=9)
+    ref64 = O.em(model, y, X.astype(np.float32), it=9, use_double=True)
+    with bw.Genotypes(X, path=path) as g:
+        out = bw.em_fit(model, y, g, it=9)
     _close_em(out, ref, model, ref64)
+
+
+def test_em_second_panel_as_batched_systems():
+    """Three traits as one batched call (nsys = 3) equal three single fits, for the solvers whose sweep epilogue is new."""
+    X, Y = synth(500, 260, k=3, seed=17)
+    with bw.Genotypes(X) as g:
+        for model in ("emDE", "emML", "emBCpi", "lasso"):
+            out = bw.em_fit(model, Y, g, it=7)
+            for t in range(3):
+                ref = O.em(model, Y[:, t], X.astype(np.float32), it=7)
+                assert np.abs(out["b"][:, t] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max() + 1e-7, (model, t)
+                assert abs(out["h2"][t] - ref["h2"]) <= 1e-4, (model, t)
 
 
 @pytest.mark.parametrize("model", ["emRR", "emBB", "emBC"])
@@ -196,9 +225,13 @@ def test_gibbs_posterior_means(tpod, model, path):
     A = np.mean([r["hat"] for r in ora], 0); B = np.mean([r["hat"] for r in gpu], 0)
     assert np.corrcoef(A, B)[0, 1] > 0.995
     assert np.abs(A - B).max() <= 0.05 * (A.max() - A.min()) + 4 * np.std([r["hat"] for r in ora], 0).max() / np.sqrt(8)
-    if model in ("BayesB", "BayesC"):
+    if model in ("BayesB", "BayesC", "BayesCpi", "BayesDpi"):
         da = np.mean([r["d"].mean() for r in ora]); db = np.mean([r["d"].mean() for r in gpu])
         assert abs(da - db) < 0.02
+    if model in ("BayesCpi", "BayesDpi"):  # pi = 1 - mean over saved sweeps of the inclusion rate (:911, :975)
+        pa = np.mean([r["pi"] for r in ora]); pb = np.mean([r["pi"] for r in gpu])
+        assert abs(pa - pb) < 0.02
+        assert np.all(np.isfinite(gpu[0]["PVAL"][gpu[0]["d"] < 1]))
 
 
 @pytest.mark.parametrize("path", [1, 2])
@@ -388,3 +421,26 @@ def test_blocked_family_multi_system(k):
         assert np.ptp(chains["h2"]) > 0  # the chains use different Philox streams
         one = bw.gibbs_fit("BayesC", Y[:, 0], g, it=60, bi=10, nchains=1, seed=5)
         assert np.allclose(chains["b"][:, 0], one["b"], rtol=0, atol=1e-6 * np.abs(one["b"]).max() + 1e-12)  # chain 0 = the single chain
+
+
+def test_emcv_and_mcmccv_drivers(tpod):
+    """emCV / mcmcCV (R/cv.R:2-216): per hold-out the training rows are packed once and the whole panel runs on that store;
+    the predictive abilities are the correlations of gen[w, ] b with the held-out phenotypes."""
+    y, gen = tpod
+    cv = bw.emCV(y, gen, k=5, n=2, avg=False, seed=3)
+    assert list(cv) == ["CV_1", "CV_2"] and list(cv["CV_1"]) == list(bw.api.EMCV_MODELS)
+    # the first hold-out redone by hand for one model, through the oracle
+    rng = np.random.default_rng(3)
+    w = np.sort(rng.choice(196, 39, replace=False))
+    keep = np.setdiff1d(np.arange(196), w)
+    ref = O.em("emRR", y[keep], gen[keep].astype(np.float32))
+    want = np.corrcoef(gen[w].astype(np.float64) @ ref["b"], y[w])[0, 1]
+    assert abs(cv["CV_1"]["emRR"] - want) <= 2e-4
+    assert all(np.isfinite(v) for v in cv["CV_1"].values())
+    full = bw.emCV(y, gen, k=5, n=2, ReturnGebv=True, seed=3)
+    assert full["beta"].shape == (376, 10) and full["hat"].shape == (196, 10)  # gen %*% beta + mean(y), one column per model (R/cv.R:105)
+    assert list(full["cv"].values()) == sorted(full["cv"].values(), reverse=True)
+    mc = bw.mcmcCV(y, gen, k=5, n=1, it=150, bi=50, seed=4)
+    assert set(mc) == set(bw.api.MCMCCV_MODELS) and all(np.isfinite(v) for v in mc.values())
+    llo = bw.emCV(y, gen, llo=np.arange(196) % 2, avg=True)
+    assert set(llo) == set(bw.api.EMCV_MODELS)
