@@ -121,7 +121,7 @@ typedef struct {
   int* its;     /* [nsys] sweeps done */
 } bwgr_em_out;
 
-/* Whole fit, the call the Rcpp shim makes for emRR/emBA/emBB/emBC/emBL/emEN. */
+/* Whole fit, the call the Rcpp shim makes for emRR/emBA/emBB/emBC/emBL/emEN/emDE/emML/emBCpi/lasso. */
 BWGR_API int bwgr_em_fit(bwgr_handle* h, const bwgr_em_params* par, const double* y, bwgr_em_out* out);
 /* Same fit split in three so that a harness can time sweeps with everything resident in HBM. */
 BWGR_API int bwgr_em_begin(bwgr_handle* h, const bwgr_em_params* par, const double* y);
