@@ -31,20 +31,28 @@ n, p = 50000, 50000
 Xt, y = bench.synth_gpu(n, p, bench.SEED, dev)
 g = bw.Genotypes(device=0)
 g.load(Xt)
-bw.emRR(y, g, it=2)  # warm-up (module load, workspaces)
-for m in bw.api.EMCV_MODELS:
-    _, t1 = timed(lambda: bw.em_fit(m, y, g, it=3))
-    r, t2 = timed(lambda: bw.em_fit(m, y, g, it=13))
-    out["em_ms_per_sweep"][m] = round((t2 - t1) / 10 * 1e3, 3)
-for m in bw.api.MCMCCV_MODELS:
-    _, t1 = timed(lambda: bw.gibbs_fit(m, y, g, it=4, bi=1, seed=1))
-    r, t2 = timed(lambda: bw.gibbs_fit(m, y, g, it=14, bi=1, seed=1))
-    out["gibbs_ms_per_sweep"][m] = round((t2 - t1) / 10 * 1e3, 3)
+for m in bw.api.EMCV_MODELS:  # begin / sweeps / end split: 3 untimed sweeps (kernel load, workspaces), then 10 timed ones
+    st = bw.EmStepper(m, y, g)
+    st.sweeps(3)
+    _, t = timed(lambda: st.sweeps(10))
+    st.end()
+    out["em_ms_per_sweep"][m] = round(t / 10 * 1e3, 3)
+for m in bw.api.MCMCCV_MODELS:  # whole fits (the Gibbs entry has no split): device time of the kernel classes from the handle's CUDA events
+    bw.gibbs_fit(m, y, g, it=2, bi=1, seed=1)
+    g.profile(True)
+    bw.gibbs_fit(m, y, g, it=20, bi=1, seed=1)
+    pr = g.profile_read()
+    g.profile(False)
+    out["gibbs_ms_per_sweep"][m] = {k: round(v["ms"] / 20, 3) for k, v in pr.items()}
+    out["gibbs_ms_per_sweep"][m]["total"] = round(sum(v["ms"] for v in pr.values()) / 20, 3)
 print(json.dumps(out), flush=True)
 g.close()
 del Xt
 torch.cuda.empty_cache()
 
+if "noemcv" in sys.argv:
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "panel_bench_sweeps.json"), "w"), indent=1)
+    sys.exit(0)
 # one emCV hold-out, config-4 shape, host matrices in and out (what an R caller hands over)
 n, p = 10000, 50000
 Xt, y = bench.synth_gpu(n, p, bench.SEED, dev)
