@@ -534,10 +534,10 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
   // =======================================================================================================
   constexpr bool kLinear = model_is_linear(MODEL);
   constexpr bool kGibbs = model_is_gibbs(MODEL);
-  // Gibbs spike-slab rules (BayesB :670-681, BayesC :731-741, KMUP :19-32): everything that does not depend on g is folded
+  // Gibbs spike-slab rules (BayesB :670-681, BayesC :731-741, KMUP :19-32, BayesDpi :949-964): everything that does not depend on g is folded
   // into four per-marker numbers one block ahead, and the Bernoulli(pj) draw u < 1/(1 + R exp(x)) is taken as
   // x < log((1/u - 1)/R): the dependent chain per marker is one shuffle, five FMAs and a compare (no exp, no division).
-  constexpr bool kSlabDraw = MODEL == M_BB || MODEL == M_BC || MODEL == M_KMUP;
+  constexpr bool kSlabDraw = MODEL == M_BB || MODEL == M_BC || MODEL == M_KMUP || MODEL == M_BDPI;
   // EM spike-slab rules (emBB :162-169, emBC :221-227): the reciprocal 1/(xx + lambda) and xx b0/(xx + lambda) are folded one
   // block ahead as well; the chain keeps one exp and one reciprocal (the inclusion weight d = 1/(1 + LR) is a value here).
   constexpr bool kSlabEM = MODEL == M_EMBB || MODEL == M_EMBC;
@@ -928,12 +928,13 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
                 if (kSlabDraw) {
                   const float xxj = mc[jj].xx, b1 = fmaf(gc, in.a, in.c), b2 = dr.z2;
                   // ||e2||^2 - ||e1||^2 in closed form: KMUP compares the two draws, BayesB/C the draw against b = 0 (:673)
-                  const float q = MODEL == M_KMUP ? (b2 - b1) * fmaf(xxj, (b1 + b2) - 2.0f * in.b0, -2.0f * gc)
-                                                  : b1 * fmaf(xxj, 2.0f * in.b0 - b1, 2.0f * gc);
+                  // (BayesDpi :953-955 compares the two draws too, with its own acceptance threshold folded into dr.u)
+                  const float q = (MODEL == M_KMUP || MODEL == M_BDPI) ? (b2 - b1) * fmaf(xxj, (b1 + b2) - 2.0f * in.b0, -2.0f * gc)
+                                                                       : b1 * fmaf(xxj, 2.0f * in.b0 - b1, 2.0f * gc);
                   const bool take = Sy.C * q < dr.u;
                   ro.b = take ? b1 : b2; ro.d = take ? 1.0f : 0.0f;
                   ro.de = ro.b - in.b0;
-                  ro.vbj = MODEL == M_BB ? (Sy.Sb + ro.b * ro.b) / dr.chi : in.vbj;
+                  ro.vbj = (MODEL == M_BB || MODEL == M_BDPI) ? (Sy.Sb + ro.b * ro.b) / dr.chi : in.vbj;
                 } else if (kSlabEM) {
                   const float xxj = mc[jj].xx, b1 = fmaf(gc, in.a, in.c);
                   const float LR = Sy.Pi0 * expf(Sy.C * (b1 * fmaf(xxj, 2.0f * in.b0 - b1, 2.0f * gc)));
@@ -1139,13 +1140,15 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
               in.c = mcv.xx * in.b0 * ia;
             }
             if (kSlabDraw) {
-              const float lmb = MODEL == M_BB ? sc[s].ve * (1.0f / in.vbj) : MODEL == M_BC ? sc[s].lmb : in.vbj;  // KMUP: vbj carries L[j]
+              const float lmb = (MODEL == M_BB || MODEL == M_BDPI) ? sc[s].ve * (1.0f / in.vbj) : MODEL == M_BC ? sc[s].lmb : in.vbj;  // KMUP: vbj carries L[j]
               const float ia = 1.0f / (mcv.xx + lmb), sd = sqrtf(sc[s].ve * ia);
               const float ratio = MODEL == M_KMUP ? sc[s].pi_mix / (1.0f - sc[s].pi_mix) : sc[s].Pi0;
               in.a = ia;                                   // b1 = g * ia + c
               in.c = fmaf(mcv.xx * in.b0, ia, sd * dr.z1);
               dr.z2 = sd * dr.z2;                          // the excluded draw b2
-              dr.u = (MODEL == M_KMUP && !(sc[s].pi_mix > 0.0f)) ? 3.0e38f : logf((1.0f / dr.u - 1.0f) / ratio);  // accept b1 iff C*q < this
+              // accept b1 iff C*q < this.  BayesDpi: u < min(1, (1-pi) exp(-C q))  <=>  C q < log((1-pi)/u)
+              if (MODEL == M_BDPI) dr.u = logf((1.0f - sc[s].Pi) / dr.u);
+              else dr.u = (MODEL == M_KMUP && !(sc[s].pi_mix > 0.0f)) ? 3.0e38f : logf((1.0f / dr.u - 1.0f) / ratio);
               drw[((size_t)slot * ns + s) * 128 + ht] = dr;
             }
           }
