@@ -541,6 +541,9 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
   // EM spike-slab rules (emBB :162-169, emBC :221-227): the reciprocal 1/(xx + lambda) and xx b0/(xx + lambda) are folded one
   // block ahead as well; the chain keeps one exp and one reciprocal (the inclusion weight d = 1/(1 + LR) is a value here).
   constexpr bool kSlabEM = MODEL == M_EMBB || MODEL == M_EMBC;
+  // Thresholding rules (emEN :431-436, lasso :1478-1486, emBL :378-386): the reciprocals of their denominators are folded one
+  // block ahead, the chain keeps an FMA, a compare / clip and a multiply (no division).
+  constexpr bool kFoldEM = MODEL == M_EMEN || MODEL == M_LASSO || MODEL == M_EMBL;
   const bool full_inv = a.tinv != nullptr;  // T = (I + A L)^-1 of every block precomputed (block_inv.cu)
   const bool use_inv = !full_inv && pipe_use_inv(MODEL, ns);
   const int sring = a.sring;
@@ -942,6 +945,22 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
                   ro.b = b1 * ro.d;
                   ro.de = ro.b - in.b0;
                   ro.vbj = MODEL == M_EMBB ? (Sy.Sb + ro.b * ro.b) / (Sy.df + 1.0f) : in.vbj;
+                } else if (kFoldEM) {
+                  const float OLS = fmaf(mc[jj].xx, in.b0, gc);
+                  if (MODEL == M_EMBL) {  // in.a = 0.5/(Lmb2 + xx), in.c = 0.5/(xx + cxx)
+                    const float Half = OLS * in.c;
+                    const float G = (OLS > 0.0f ? OLS - Sy.lmb1 : OLS + Sy.lmb1) * in.a;
+                    const bool keep = OLS > 0.0f ? G > 0.0f : G < 0.0f;
+                    ro.b = keep ? G + Half : Half;
+                    ro.d = 1.0f;
+                  } else {                // in.a = 1/(Lmb2 + xx) (emEN) or 1/xx (lasso)
+                    const float l1 = MODEL == M_LASSO ? Sy.lmb : Sy.lmb1;
+                    const float t = OLS > 0.0f ? fmaxf(OLS - l1, 0.0f) : fminf(OLS + l1, 0.0f);
+                    ro.b = t * in.a;
+                    ro.d = MODEL == M_LASSO ? fabsf(OLS) - fabsf(t) : 1.0f;  // lasso: |x'e~| - |b xx| for the next penalty
+                  }
+                  ro.de = ro.b - in.b0;
+                  ro.vbj = in.vbj;
                 } else {
                   ro = marker_rule<MODEL>(gc, mc[jj].xx, in.b0, in.vbj, Sy, dr);
                 }
@@ -1132,6 +1151,10 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
             if (kLinear) {
               const LinCoef lc = lin_coef<MODEL>(mcv.xx, in.b0, in.vbj, sc[s], dr);
               in.a = lc.a; in.c = lc.c;
+            }
+            if (kFoldEM) {
+              if (MODEL == M_EMBL) { in.a = 0.5f / (sc[s].lmb2 + mcv.xx); in.c = 0.5f / (mcv.xx + sc[s].cxx); }
+              else in.a = 1.0f / (MODEL == M_LASSO ? mcv.xx : sc[s].lmb2 + mcv.xx);
             }
             if (kSlabEM) {
               const float lmb = MODEL == M_EMBB ? sc[s].ve * (1.0f / in.vbj) : sc[s].lmb;
