@@ -100,3 +100,53 @@ def test_fit_cv_sharded_single_process():
     out = bd.fit_cv_sharded(fit, _FakeStore, Y, folds, scale=3.0)
     want = np.array([Y[np.setdiff1d(np.arange(n), f)][:, t].mean() * 3.0 for f in folds for t in range(k)])
     assert np.allclose(out["mu"], want) and out["b"].shape == (4, 9) and "hat" not in out
+
+
+def _cv_fit(Yc, store, scale=1.0):
+    return {"mu": Yc.mean(0) * scale, "b": np.tile(Yc.mean(0), (4, 1)), "hat": np.zeros((len(store.keep), Yc.shape[1]))}
+
+
+def _cv_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(1)
+    Y = rng.normal(size=(30, 3))
+    folds = [np.arange(0, 10), np.arange(10, 20), np.arange(20, 30)]
+    loaded = []
+
+    def load(keep):
+        loaded.append(len(keep))
+        return _FakeStore(keep)
+
+    out = bd.fit_cv_sharded(_cv_fit, load, Y, folds, scale=3.0)
+    q.put((rank, {k: v.tolist() for k, v in out.items()}, len(loaded)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_fit_cv_sharded_gloo_world2():
+    """3 folds x 3 traits over two ranks: rank 0 gets tasks 0-4 (folds 0, 1), rank 1 tasks 5-8 (folds 1, 2); both end up with the
+    full fold-major result, and neither builds more row-subset stores than the folds it touches."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cv_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=90) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(1)
+    Y = rng.normal(size=(30, 3))
+    folds = [np.arange(0, 10), np.arange(10, 20), np.arange(20, 30)]
+    want = bd.fit_cv_sharded(_cv_fit, _FakeStore, Y, folds, scale=3.0)  # one rank, same data
+    assert want["mu"].shape == (9,) and "hat" not in want
+    for rank, res, nstores in got:
+        assert nstores == 2, (rank, nstores)
+        for key, v in want.items():
+            assert np.allclose(np.asarray(res[key]), v), (rank, key)
