@@ -444,3 +444,39 @@ def test_emcv_and_mcmccv_drivers(tpod):
     assert set(mc) == set(bw.api.MCMCCV_MODELS) and all(np.isfinite(v) for v in mc.values())
     llo = bw.emCV(y, gen, llo=np.arange(196) % 2, avg=True)
     assert set(llo) == set(bw.api.EMCV_MODELS)
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] shape, n = 50,000 x p = 50,000 int8 (the bench workload; the oracle needs minutes per sweep there):
+    properties that do not depend on the size.  Checksums of the store against torch integer sums; two fits bit-identical
+    (integer grid reductions); a fit of 4 y is 4 x the fit of y (every scale in the solver, fixed point included, is a power of
+    two or scales with y); the variance components returned agree with the returned b and hat (the residual the sweep maintained
+    over 3 x 391 blocks is the residual of the returned effects)."""
+    torch = pytest.importorskip("torch")
+    import bench
+    dev = torch.device("cuda", 0)
+    n = p = 50000
+    Xt, y = bench.synth_gpu(n, p, bench.SEED, dev)
+    with bw.Genotypes(device=0) as g:
+        g.load(Xt)
+        xx, sx = g.stats()
+        sx_t = Xt.sum(1, dtype=torch.int64)
+        xx_t = sx_t + 2 * (Xt == 2).sum(1, dtype=torch.int64)  # codes {0,1,2}: x^2 = x + 2 [x == 2]
+        assert np.array_equal(sx, sx_t.cpu().numpy().astype(np.float64)) and np.array_equal(xx, xx_t.cpu().numpy().astype(np.float64))
+        del Xt, sx_t, xx_t
+        torch.cuda.empty_cache()
+        a = bw.emRR(y, g, it=3)
+        a2 = bw.emRR(y, g, it=3)
+        c = bw.emRR(4.0 * y, g, it=3)
+    assert np.array_equal(a["b"], a2["b"]) and np.array_equal(a["hat"], a2["hat"]) and a["Ve"] == a2["Ve"]
+    sb = np.abs(a["b"]).max()
+    assert sb > 0 and np.abs(c["b"] - 4.0 * a["b"]).max() <= 1e-6 * 4.0 * sb
+    assert abs(c["Ve"] - 16.0 * a["Ve"]) <= 1e-6 * 16.0 * a["Ve"] and abs(c["h2"] - a["h2"]) <= 1e-6
+    df, R2 = 10.0, 0.5
+    vy = y.var(ddof=1)
+    MSx = ((xx - sx * sx / n) / (n - 1)).sum()
+    Va = (a["b"] @ a["b"] + R2 * (df + 2) * vy / MSx) / (p + df)  # Rcpp20260726ai.cpp:338
+    assert abs(a["Va"] - Va) <= 1e-4 * Va
+    Ve = (((y - a["hat"]) ** 2).sum() + (1 - R2) * (df + 2) * vy) / (n + df)  # :339, up to n * mean(e)^2 (removed after Ve is taken)
+    assert abs(a["Ve"] - Ve) <= 1e-3 * Ve
+    assert a["its"] == 3 and np.corrcoef(a["hat"], y)[0, 1] > 0.3
