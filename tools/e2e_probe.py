@@ -1,3 +1,4 @@
+"""Where the time of one end-to-end emRR(y, gen) call goes at 50k x 50k (handle, H2D + pack of pinned int8 genotypes, 200 sweeps, outputs)."""
 import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

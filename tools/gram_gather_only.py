@@ -1,3 +1,4 @@
+"""Gram kernel with its MMAs switched off (BWGR_GRAM_DBG=1) vs on, per look-ahead depth: isolates the gather rate of the producer warps."""
 import os, sys, json
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,3 +1,4 @@
+"""Gram band of the natural marker order with and without the packed 2-bit source (BWGR_GRAM_PACKED), through a BayesRR fit that computes it once."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,3 +1,4 @@
+"""Blocked family beyond three 128-row atoms per worker (n = 52k-70k, NA = 4): parity against the oracle at both look-ahead depths."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,3 +1,4 @@
+"""A few sweeps of one solver of every family on tpod through the blocked path: the workload run under compute-sanitizer."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
