@@ -467,17 +467,44 @@ def _cv_summary(gebv, models, avg):
     return {"CV_%d" % (i + 1): {m: round(float(v), 4) for m, v in zip(models, pa(M))} for i, M in enumerate(gebv)}
 
 
-def _cv_run(models, fit_one, y, gen, holdouts, tbv, avg, ReturnGebv):
+def _cv_world(group):
+    """(rank, world) of the torch.distributed group the hold-outs are dealt over; (0, 1) without an initialised process group."""
+    try:
+        import torch.distributed as dist
+    except ImportError:
+        return 0, 1, None
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group), dist
+    return 0, 1, None
+
+
+def _cv_run(models, fit_one, y, gen, holdouts, tbv, avg, ReturnGebv, group=None, store=None):
+    """The hold-outs are independent fits ("independent folds": no communication): under torch.distributed rank r
+    takes hold-outs r, r + world, ... on its own GPU (LOCAL_RANK) and the per-hold-out results are gathered on the host, so
+    every rank returns the full summary.  `store(X_keep, device)` builds the per-hold-out genotype store (tests inject a stub)."""
+    import os
     y = np.asarray(y, dtype=np.float64)
     X = np.asarray(gen)
     obs = y if tbv is None else np.asarray(tbv, dtype=np.float64)
-    gebv, B0 = [], []
-    for w in holdouts:
+    rank, world, dist = _cv_world(group)
+    device = int(os.environ.get("LOCAL_RANK", rank)) if world > 1 else 0
+    if store is None:
+        def store(Xk, dev):
+            return Genotypes(np.asfortranarray(Xk), device=dev)
+    mine = []
+    for idx in range(rank, len(holdouts), world):
+        w = holdouts[idx]
         keep = np.setdiff1d(np.arange(X.shape[0]), w)
-        with Genotypes(np.asfortranarray(X[keep])) as g:  # gen[-w, ] packed ONCE per fold, shared by every model of the panel
+        with store(X[keep], device) as g:  # gen[-w, ] packed ONCE per hold-out, shared by every model of the panel
             B = np.stack([fit_one(m, y[keep], g)["b"] for m in models], axis=1)
-        gebv.append(np.concatenate([X[w].astype(np.float64) @ B, obs[w][:, None]], axis=1))  # gen[w, ] %*% b | OBSERVATION
-        B0.append(B)
+        M = np.concatenate([X[w].astype(np.float64) @ B, obs[w][:, None]], axis=1)  # gen[w, ] %*% b | OBSERVATION
+        mine.append((idx, M, B))
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine, group=group)
+        mine = sorted((item for per_rank in gathered for item in per_rank), key=lambda item: item[0])
+    gebv = [M for _, M, _ in mine]
+    B0 = [B for _, _, B in mine]
     cv = _cv_summary(gebv, list(models), avg)
     if not ReturnGebv:
         return cv
@@ -485,7 +512,8 @@ def _cv_run(models, fit_one, y, gen, holdouts, tbv, avg, ReturnGebv):
     return {"cv": cv, "hat": X.astype(np.float64) @ beta + np.nanmean(y), "beta": beta}
 
 
-def emCV(y, gen, k=5, n=5, Pi=0.75, alpha=0.02, df=10, R2=0.5, avg=True, llo=None, tbv=None, ReturnGebv=False, seed=1):
+def emCV(y, gen, k=5, n=5, Pi=0.75, alpha=0.02, df=10, R2=0.5, avg=True, llo=None, tbv=None, ReturnGebv=False, seed=1,
+         group=None):
     """emCV of R/cv.R:2-108: ten EM solvers per hold-out, predictive correlation of gen[w, ] b with the held-out
     observations.  Per fold the training rows are packed once into one device store and all ten fits run on it."""
     def fit_one(m, yk, g):
@@ -493,14 +521,17 @@ def emCV(y, gen, k=5, n=5, Pi=0.75, alpha=0.02, df=10, R2=0.5, avg=True, llo=Non
               "emBA": dict(R2=R2, df=df), "emBB": dict(Pi=Pi, R2=R2, df=df), "emBC": dict(Pi=Pi, R2=R2, df=df), "emML": {},
               "emBCpi": {}, "lasso": {}}[m]  # R/cv.R:13-22 (emML, emBCpi and lasso run on their defaults)
         return em_fit(m, yk, g, **kw)
-    return _cv_run(EMCV_MODELS, fit_one, y, gen, _cv_holdouts(np.asarray(gen).shape[0], k, n, llo, seed), tbv, avg, ReturnGebv)
+    return _cv_run(EMCV_MODELS, fit_one, y, gen, _cv_holdouts(np.asarray(gen).shape[0], k, n, llo, seed), tbv, avg, ReturnGebv,
+                   group=group)
 
 
-def mcmcCV(y, gen, k=5, n=5, it=1500, bi=500, pi=0.95, df=5, R2=0.5, avg=True, llo=None, tbv=None, ReturnGebv=False, seed=1):
+def mcmcCV(y, gen, k=5, n=5, it=1500, bi=500, pi=0.95, df=5, R2=0.5, avg=True, llo=None, tbv=None, ReturnGebv=False, seed=1,
+           group=None):
     """mcmcCV of R/cv.R:110-216: the seven Gibbs samplers per hold-out."""
     def fit_one(m, yk, g):
         kw = dict(R2=R2, df=df, it=it, bi=bi, seed=seed)
         if m in ("BayesB", "BayesC"):
             kw["pi"] = pi
         return gibbs_fit(m, yk, g, **kw)
-    return _cv_run(MCMCCV_MODELS, fit_one, y, gen, _cv_holdouts(np.asarray(gen).shape[0], k, n, llo, seed), tbv, avg, ReturnGebv)
+    return _cv_run(MCMCCV_MODELS, fit_one, y, gen, _cv_holdouts(np.asarray(gen).shape[0], k, n, llo, seed), tbv, avg, ReturnGebv,
+                   group=group)

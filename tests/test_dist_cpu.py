@@ -150,3 +150,66 @@ def test_fit_cv_sharded_gloo_world2():
         assert nstores == 2, (rank, nstores)
         for key, v in want.items():
             assert np.allclose(np.asarray(res[key]), v), (rank, key)
+
+
+class _StubStore:
+    def __init__(self, Xk, device):
+        self.X = np.asarray(Xk, dtype=np.float64)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        pass
+
+
+def _stub_panel_fit(model, yk, g):
+    """Stands in for a solver of the panel: a ridge-flavoured closed form whose strength depends on the model name."""
+    lam = {"m_weak": 1e3, "m_strong": 1e1}[model]
+    xc = g.X - g.X.mean(0)
+    return {"b": xc.T @ (yk - yk.mean()) / ((xc * xc).sum(0) + lam)}
+
+
+def _cv_driver_case():
+    rng = np.random.default_rng(2)
+    X = rng.integers(0, 3, size=(40, 12)).astype(np.int8)
+    y = X[:, :3].sum(1) + rng.normal(size=40)
+    from bwgr_b200 import api
+    return X, y, api._cv_holdouts(40, k=5, n=3, llo=None, seed=1)
+
+
+def _cv_driver_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bwgr_b200 import api
+    X, y, hs = _cv_driver_case()
+    out = api._cv_run(("m_weak", "m_strong"), _stub_panel_fit, y, X, hs, None, False, True, store=_StubStore)
+    q.put((rank, out["cv"], out["beta"].tolist(), out["hat"].tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_cv_driver_holdouts_over_two_ranks():
+    """emCV / mcmcCV driver under torch.distributed (gloo, world 2): three hold-outs dealt 2 + 1, every rank returns the same
+    summary as the single-process run."""
+    import torch.multiprocessing as mp
+    from bwgr_b200 import api
+    X, y, hs = _cv_driver_case()
+    want = api._cv_run(("m_weak", "m_strong"), _stub_panel_fit, y, X, hs, None, False, True, store=_StubStore)
+    assert list(want["cv"]) == ["CV_1", "CV_2", "CV_3"] and want["beta"].shape == (12, 2) and want["hat"].shape == (40, 2)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cv_driver_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=90) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for rank, cv, beta, hat in got:
+        assert cv == want["cv"], rank
+        assert np.allclose(beta, want["beta"]) and np.allclose(hat, want["hat"]), rank
