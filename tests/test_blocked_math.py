@@ -1,0 +1,136 @@
+"""The algebra the blocked sweep kernels implement, restated in numpy (float64) and checked against the plain per-marker loop.
+
+Within a block of B markers the Gauss-Seidel steps of a linear rule (emRR Rcpp20260726ai.cpp:335, emBA :107-111, BayesRR :835 ...)
+form the unit-lower-triangular system (I + A L) dE = A g + c  (bwgr_b200/csrc/common.cuh lin_coef, csrc/block_inv.cu), and a
+look-ahead of D blocks takes g from a residual that is D blocks stale, corrected with the cross Gram blocks:
+g_c = X_c' E_(c-D) - sum_d (X_c' X_(c-d)) dE_(c-d)  (csrc/sweep_pipe.cu).  Both are exact reformulations: this file is the
+CPU proof of that (no device involved), for D = 0 .. 3 -- D = 2, 3 are the next step of DESIGN.md section 8."""
+import numpy as np
+import pytest
+
+from conftest import synth
+
+
+def _sequential(X, e, b, lam, kappa, order):
+    e, b = e.copy(), b.copy()
+    xx = (X * X).sum(0)
+    for j in order:
+        b1 = (X[:, j] @ e + xx[j] * b[j]) / (xx[j] + lam[j])
+        e -= kappa * X[:, j] * (b1 - b[j])  # emBA applies the residual update twice (kappa = 2)
+        b[j] = b1
+    return b, e
+
+
+def _blocked(X, e, b, lam, kappa, order, B, D, use_inverse):
+    e, b = e.copy(), b.copy()
+    xx = (X * X).sum(0)
+    blocks = [order[s:s + B] for s in range(0, len(order), B)]
+    steps = []    # dE of every finished block
+    applied = 0   # blocks whose update has reached e
+    for c, cols in enumerate(blocks):
+        while applied < c - D:  # the workers are D blocks behind the solver
+            e -= X[:, blocks[applied]] @ steps[applied]
+            applied += 1
+        Xc = X[:, cols]
+        g = Xc.T @ e
+        for d in range(applied, c):  # stale residual: correct with the cross Gram blocks
+            g -= (Xc.T @ X[:, blocks[d]]) @ steps[d]
+        a = kappa / (xx[cols] + lam[cols])
+        cvec = -kappa * lam[cols] * b[cols] / (xx[cols] + lam[cols])
+        L = np.tril(Xc.T @ Xc, -1)
+        M = np.eye(len(cols)) + a[:, None] * L
+        rhs = a * g + cvec
+        dE = np.linalg.inv(M) @ rhs if use_inverse else np.linalg.solve(M, rhs)
+        b[cols] += dE / kappa
+        steps.append(dE)
+    while applied < len(blocks):
+        e -= X[:, blocks[applied]] @ steps[applied]
+        applied += 1
+    return b, e
+
+
+@pytest.mark.parametrize("D", [0, 1, 2, 3])
+@pytest.mark.parametrize("kappa", [1.0, 2.0])
+def test_blocked_look_ahead_is_exact(D, kappa):
+    X, y = synth(300, 700, seed=4)
+    X = X.astype(np.float64)
+    rng = np.random.default_rng(D)
+    order = rng.permutation(700)
+    lam = rng.uniform(20.0, 400.0, size=700)   # per-marker penalties (emBA / BayesA / emDE); a constant for emRR
+    b0 = rng.normal(size=700) * 0.01
+    e0 = y - y.mean() - X @ b0
+    want_b, want_e = _sequential(X, e0, b0, lam, kappa, order)
+    for use_inverse in (False, True):
+        got_b, got_e = _blocked(X, e0, b0, lam, kappa, order, 128, D, use_inverse)
+        assert np.abs(got_b - want_b).max() <= 1e-10 * np.abs(want_b).max()
+        assert np.abs(got_e - want_e).max() <= 1e-9 * np.abs(want_e).max()
+    if kappa == 1.0:  # with one update per marker the residual stays the residual of b
+        assert np.abs((y - y.mean() - X @ want_b) - want_e).max() <= 1e-9
+
+
+def test_mrr3_rotation_and_analytic_centring_are_exact():
+    """MRR3's per-marker k x k solve (RcppEigen20230423.cpp:504-521, complete Y) against what the device runs:
+    k independent ridge recurrences on residuals rotated by S U (S = diag(iVe)^1/2, S^-1 iG S^-1 = U Lambda U'), genotypes left
+    uncentred, the column centring carried as a running shift c (e_true = e_stored + c, g = x'e_stored + c sx_j)."""
+    rng = np.random.default_rng(8)
+    n, p, k = 120, 60, 4
+    X = rng.integers(0, 3, size=(n, p)).astype(np.float64)
+    m = X.mean(0)
+    Xc = X - m
+    A = rng.normal(size=(k, k))
+    iG = A @ A.T + k * np.eye(k)
+    iVe = rng.uniform(0.5, 3.0, size=k)
+    Y = rng.normal(size=(n, k))
+    E0 = Y - Y.mean(0)
+    b0 = rng.normal(size=(p, k)) * 0.05
+    E0 = E0 - Xc @ b0
+    order = rng.permutation(p)
+    # the reference: one k x k system per marker on the centred column
+    E, b = E0.copy(), b0.copy()
+    for j in order:
+        xx = Xc[:, j] @ Xc[:, j]
+        rhs = (Xc[:, j] @ E + xx * b[j]) * iVe
+        b1 = np.linalg.solve(iG + xx * np.diag(iVe), rhs)
+        E -= np.outer(Xc[:, j], b1 - b[j])
+        b[j] = b1
+    # the device's form
+    S = np.sqrt(iVe)
+    lam, U = np.linalg.eigh(iG / np.outer(S, S))
+    Et = E0 * S @ U                      # E~ = E S U   (n x k)
+    bt = b0 * S @ U                      # b~_j = U' S b_j
+    c = np.zeros(k)
+    sx = X.sum(0)
+    for j in order:
+        xx = X[:, j] @ X[:, j] - sx[j] ** 2 / n          # centred xx_j = xx_j - n m_j^2
+        g = X[:, j] @ Et + c * sx[j]                      # x_c'e_true with sum(e_true) = 0
+        b1 = (g + xx * bt[j]) / (xx + lam)
+        d = b1 - bt[j]
+        Et -= np.outer(X[:, j], d)                        # workers: uncentred update
+        c += m[j] * d                                     # solver: running mean shift
+        bt[j] = b1
+    Et += c                                               # e_true = e_stored + c
+    E_back = (Et @ U.T) / S
+    b_back = (bt @ U.T) / S
+    assert np.abs(b_back - b).max() <= 1e-10 * np.abs(b).max()
+    assert np.abs(E_back - E).max() <= 1e-10 * np.abs(E).max()
+
+
+def test_spike_slab_closed_forms():
+    """|e2|^2 - |e1|^2 without the two n-length temporaries (common.cuh marker_rule): BayesB / emBB compare the
+    new effect with zero, KMUP / BayesDpi compare two draws; and the folded acceptance tests of the fast chain
+    (u < 1/(1 + R e^x)  <=>  x < log((1/u - 1)/R);   u < min(1, q e^-x)  <=>  x < log(q/u))."""
+    rng = np.random.default_rng(3)
+    n = 50
+    x = rng.integers(0, 3, size=n).astype(np.float64)
+    e = rng.normal(size=n)
+    g, xx = x @ e, x @ x
+    b0, b1, b2 = 0.3, -0.2, 0.7
+    n1 = ((e - x * (b1 - b0)) ** 2).sum()
+    assert np.isclose(((e + x * b0) ** 2).sum() - n1, b1 * (2 * g + xx * (2 * b0 - b1)))
+    assert np.isclose(((e - x * (b2 - b0)) ** 2).sum() - n1, (b2 - b1) * (-2 * g + xx * (b1 + b2 - 2 * b0)))
+    for u in (0.01, 0.3, 0.77, 0.999):
+        for xv in (-30.0, -1.0, 0.0, 0.4, 25.0):
+            for R in (0.05, 1.0, 19.0):
+                assert (u < 1 / (1 + R * np.exp(xv))) == (xv < np.log((1 / u - 1) / R))
+            for q in (0.1, 0.5, 0.9):
+                assert (u < min(1.0, q * np.exp(-xv))) == (xv < np.log(q / u))
