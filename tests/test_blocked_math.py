@@ -134,3 +134,61 @@ def test_spike_slab_closed_forms():
                 assert (u < 1 / (1 + R * np.exp(xv))) == (xv < np.log((1 / u - 1) / R))
             for q in (0.1, 0.5, 0.9):
                 assert (u < min(1.0, q * np.exp(-xv))) == (xv < np.log(q / u))
+
+
+def _split_limbs(q):
+    """numpy image of split_limbs() in csrc/sweep_pipe.cu: four balanced signed digits, q = l0 + 2^8 l1 + 2^16 l2 + 2^24 l3."""
+    q = q.astype(np.int64)
+    out = []
+    for _ in range(3):
+        l = ((q & 0xFF) ^ 0x80) - 0x80  # (signed char)(q & 0xFF)
+        out.append(l)
+        q = (q - l) >> 8
+    out.append(q)
+    return out
+
+
+def test_int8_limbs_are_exact():
+    """The tensor-core passes see the residuals as four int8 limbs of a 31-bit fixed-point image: the split is
+    exact and fits int8 for |q| <= 2^30, X'q is recovered exactly from the four int32 limb products, and the per-slab partial sums
+    stay far inside int32 (352 rows x |x| <= 127 x |limb| <= 128)."""
+    rng = np.random.default_rng(6)
+    q = np.concatenate([rng.integers(-2 ** 30, 2 ** 30 + 1, size=5000), [2 ** 30, -2 ** 30, 0, 127, 128, -128, -129, 2 ** 24 - 1]])
+    l0, l1, l2, l3 = _split_limbs(q)
+    for l in (l0, l1, l2, l3):
+        assert l.min() >= -128 and l.max() <= 127
+    assert np.array_equal(l0 + (l1 << 8) + (l2 << 16) + (l3 << 24), q)
+    rows = 352
+    X = rng.integers(-128, 128, size=(rows, 16))
+    qe = rng.integers(-2 ** 30, 2 ** 30 + 1, size=rows)
+    limbs = _split_limbs(qe)
+    parts = [X.T @ l for l in limbs]
+    assert max(np.abs(pt).max() for pt in parts) < 2 ** 31
+    assert np.array_equal(parts[0] + (parts[1] << 8) + (parts[2] << 16) + (parts[3] << 24), X.T @ qe)
+
+
+def test_swizzle_128b_offsets_are_a_bijection():
+    """sw128_off() of csrc/sweep_pipe.cu (K-major SWIZZLE_128B atom stack): every (row, K byte) of a 128 x 128 B tile maps to a
+    distinct byte, 16-byte chunks stay whole, chunk c of row r lands in chunk c ^ (r & 7) of its 128-byte row."""
+    n, kb = np.meshgrid(np.arange(128), np.arange(128), indexing="ij")
+    off = (n >> 3) * 1024 + (n & 7) * 128 + ((((kb >> 4) ^ (n & 7)) & 7) << 4) + (kb & 15)
+    assert sorted(off.ravel().tolist()) == list(range(128 * 128))
+    assert np.array_equal(off // 128, n)                              # a row stays inside its own 128-byte line
+    assert np.array_equal((off % 128) // 16, (kb >> 4) ^ (n & 7))     # XOR swizzle of the 16-byte chunk index
+    assert np.array_equal(off % 16, kb % 16)
+
+
+def test_self_validating_words():
+    """Grid reduction without a barrier: a 64-bit word carries (value << 12) | tag, tag_of(use) = use % 4095 + 1 is
+    never 0 (a zeroed buffer can never look valid) and differs between consecutive uses of a slot; 52 bits hold any partial
+    sum of the sweep (|sum_l 2^(8l) X'limb| <= 2^50 by the Cauchy-Schwarz bound the host checks)."""
+    tags = [(use % 4095) + 1 for use in range(3 * 4095)]
+    assert min(tags) == 1 and max(tags) == 4095 and all(a != b for a, b in zip(tags, tags[1:]))
+    for v in (0, 1, -1, 2 ** 50, -(2 ** 50), 123456789012345):
+        for tag in (1, 77, 4095):
+            w = ((v << 12) | tag) & (2 ** 64 - 1)
+            assert w & 0xFFF == tag
+            back = w >> 12
+            if back >= 2 ** 51:
+                back -= 2 ** 52
+            assert back == v
