@@ -192,3 +192,17 @@ def test_self_validating_words():
             if back >= 2 ** 51:
                 back -= 2 ** 52
             assert back == v
+
+
+def test_genotype_codes_read_as_e4m3_subnormals():
+    """The exact fp8 Gram path (csrc/gram_tc.cu, kIdescF8): the int8 bytes 0..7 ARE the E4M3 subnormals code * 2^-9, every
+    product code_i code_j 2^-18 is exact in fp32, and a column's sum of squares stays an exact fp32 integer while it is below
+    2^24 (n = 50,000 rows of codes {0,1,2}: at most 200,000)."""
+    torch = pytest.importorskip("torch")
+    codes = torch.arange(0, 8, dtype=torch.uint8)
+    assert torch.equal(codes.view(torch.float8_e4m3fn).float() * 512.0, codes.float())
+    rng = np.random.default_rng(9)
+    X = rng.integers(0, 3, size=(50000, 6)).astype(np.uint8)
+    as_f8 = torch.from_numpy(X).view(torch.float8_e4m3fn).float().numpy()     # what the tensor core multiplies
+    G = (as_f8.T.astype(np.float32) @ as_f8.astype(np.float32)) * np.float32(2.0 ** 18)  # fp32 accumulate, epilogue rescale
+    assert np.array_equal(G.astype(np.int64), X.astype(np.int64).T @ X.astype(np.int64))
