@@ -206,3 +206,23 @@ def test_genotype_codes_read_as_e4m3_subnormals():
     as_f8 = torch.from_numpy(X).view(torch.float8_e4m3fn).float().numpy()     # what the tensor core multiplies
     G = (as_f8.T.astype(np.float32) @ as_f8.astype(np.float32)) * np.float32(2.0 ** 18)  # fp32 accumulate, epilogue rescale
     assert np.array_equal(G.astype(np.int64), X.astype(np.int64).T @ X.astype(np.int64))
+
+
+def test_philox_known_answers(tmp_path):
+    """philox4x32_10() of csrc/common.cuh (the counter-based generator behind every Gibbs draw) against the known-answer vectors
+    published with Random123 (Salmon et al. 2011, kat_vectors: zero, all-ones, digits-of-pi counter / key).  Host-only build of
+    the same header with nvcc; no device needed."""
+    import os
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "kat_philox")
+    subprocess.check_call([nvcc, "-std=c++17", "-w", "-I", os.path.join(ROOT, "bwgr_b200", "csrc"), "-o", exe,
+                           os.path.join(ROOT, "tests", "kat_philox.cu")], stderr=subprocess.DEVNULL)
+    out = subprocess.check_output([exe]).decode().split("\n")
+    assert out[0] == "6627e8d5 e169c58d bc57ac4c 9b00dbd8"
+    assert out[1] == "408f276d 41c83b0e a20bc7c6 6d5451fd"
+    assert out[2] == "d16cfe09 94fdcceb 5001e420 24126ea1"
