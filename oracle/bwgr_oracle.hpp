@@ -9,11 +9,15 @@
 //   /root/reference/src/Rcpp20260726ai.cpp      (univariate EM + Gibbs + KMUP, float32)
 //   /root/reference/src/RcppEigen20230423.cpp   (MRR3 float64 :318-701, MRR3F float32 :704-1079)
 //   /root/reference/R/wgr.R                     (wgr MCMC driver :2-169)
-// The reference itself cannot be compiled here (needs R, Rcpp, RcppEigen; none present),
-// and it ships no tests or golden vectors for this path, so:
-//   PARITY UNPINNED -- goldens under tests/golden are oracle-derived, not reference-executed.
-// What *is* pinned: the libstdc++ std::shuffle/std::mt19937 marker order (known answers in
-// SURVEY.md section 8a) and the bundled tpod data set.
+// The reference ships no tests or golden vectors for this path, and R / Rcpp / RcppEigen are absent from this image.
+//   PARITY PINNED (round 2) -- the reference's own sources are compiled UNMODIFIED against stand-in RcppEigen / Rcpp headers
+//   (oracle/shim/RcppEigen.h) into oracle/_ref/libbwgr_ref.so (oracle/Makefile, target `ref`: Rcpp20260726ai.cpp whole,
+//   RcppEigen20230423.cpp:317-1079 = MRR3 + MRR3F).  tests/test_ref_pin.py runs both on the same inputs: the ten EM solvers,
+//   the seven Gibbs samplers (same std::mt19937_64 stream, draw for draw), KMUP, and MRR3 / MRR3F under every flag incl.
+//   missing phenotypes agree to float reassociation (1e-15 for the float64 MRR3); tests/golden/tpod_em.npz (<model>_ref__*) and
+//   tpod_mrr3.npz are REFERENCE-EXECUTED outputs of that library (oracle/make_golden.py).  What the stand-in headers cannot
+//   pin is Eigen's own packet order of float reductions and R's RNG stream (Gibbs parity vs R stays statistical).
+// Also pinned: the libstdc++ std::shuffle/std::mt19937 marker order (known answers in SURVEY.md section 8a) and tpod.
 //
 // Third-party arithmetic restated here (absent from /root/reference):
 //   Eigen (via CRAN RcppEigen, version unpinned by DESCRIPTION:15): dot / squaredNorm / sum are

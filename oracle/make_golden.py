@@ -5,10 +5,12 @@ TEST INFRASTRUCTURE ONLY.  Provenance of every fixture:
                     man/tpod.Rd) with oracle/rdata.py -- real reference data, bit-exact.
   perm_kat.json     std::shuffle/std::mt19937 marker orders; the first three (p=10) and the p=376 head
                     are the known answers recorded in SURVEY.md 8a / BASELINE.md 5 (libstdc++ 13).
-  tpod_em.npz       oracle outputs (float32 recipe and float64 recipe) of the six EM solvers on tpod.
-                    ORACLE-DERIVED, NOT REFERENCE-EXECUTED: R/Rcpp/RcppEigen are absent from this image,
-                    so the reference cannot run here ("parity unpinned").
-  tpod_mrr3.npz     oracle MRR3 (float64) outputs on a fixed synthetic 3-trait Y over tpod genotypes.
+  tpod_em.npz       REFERENCE-EXECUTED (<model>_ref__*): the ten EM solvers of /root/reference/src/Rcpp20260726ai.cpp, compiled
+                    unmodified into oracle/_ref/libbwgr_ref.so against the stand-in RcppEigen headers (oracle/shim/), run on
+                    tpod.  Beside them the oracle's float32 / float64 recipes (<model>_f32__*, <model>_f64__*), kept to bound
+                    float noise.  tests/test_ref_pin.py checks oracle == reference on these and many more inputs.
+  tpod_mrr3.npz     REFERENCE-EXECUTED: MRR3 (float64, RcppEigen20230423.cpp:318-701 compiled the same way) on a fixed
+                    synthetic 3-trait Y over the tpod genotypes.
 Usage:  python oracle/make_golden.py   (needs /root/reference; tests never do)
 """
 import json
@@ -20,6 +22,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import oracle as O  # noqa: E402
+import ref as R  # noqa: E402
 from rdata import read_rdata  # noqa: E402
 
 OUT = os.path.join(HERE, "..", "tests", "golden")
@@ -45,8 +48,10 @@ def main():
            "p376_iter199_head8": O.perm(376, 200)[199, :8].tolist()}
     json.dump(kat, open(os.path.join(OUT, "perm_kat.json"), "w"), indent=1)
     genf = gen.astype(np.float64)
-    em = {}
+    em = {"provenance": np.array("reference-executed")}
     for m in O.EM_MODELS:
+        for key, v in R.em(m, y, genf).items():
+            em[m + "_ref__" + key] = np.asarray(v)
         for dbl in (False, True):
             r = O.em(m, y, genf, use_double=dbl)
             tag = m + ("_f64" if dbl else "_f32")
@@ -54,7 +59,7 @@ def main():
                 em[tag + "__" + key] = np.asarray(v)
     np.savez_compressed(os.path.join(OUT, "tpod_em.npz"), **em)
     Y = synth_traits(genf)
-    r = O.mrr3(Y, genf)
+    r = R.mrr3(Y, genf)
     np.savez_compressed(os.path.join(OUT, "tpod_mrr3.npz"), Y=Y, **{k: np.asarray(v) for k, v in r.items()})
     print("wrote", sorted(os.listdir(OUT)))
 

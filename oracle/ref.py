@@ -1,0 +1,176 @@
+"""ctypes front end of oracle/_ref/libbwgr_ref.so: the reference's OWN solver sources (Rcpp20260726ai.cpp whole, MRR3 / MRR3F of
+RcppEigen20230423.cpp) compiled unmodified against the stand-in headers of oracle/shim/ (see oracle/Makefile, target `ref`).
+
+TEST INFRASTRUCTURE ONLY.  It pins the hand-written oracle (oracle.py / bwgr_oracle.hpp): tests/test_ref_pin.py compares the two,
+and oracle/make_golden.py writes the committed fixtures from THIS library.  The library can only be built where /root/reference
+exists (this container); the built .so is git-ignored and travels to the GPU box with the repo snapshot.  Same function names,
+arguments and returned keys as oracle.py.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oracle import EM_MODELS, GIBBS_MODELS, MRR3_DEFAULTS, _f32, _p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(_HERE, "_ref", "libbwgr_ref.so")
+_REF_SRC = "/root/reference/src/Rcpp20260726ai.cpp"
+_LIB = None
+
+
+def available():
+    """True when the library is built, or can be built here (the reference tree is present)."""
+    return os.path.exists(_PATH) or os.path.exists(_REF_SRC)
+
+
+def build():
+    if os.path.exists(_REF_SRC):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+    return _PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        build()
+        _LIB = C.CDLL(_PATH)
+    return _LIB
+
+
+def em(model, y, gen, df=10.0, R2=0.5, Pi=0.75, alpha=0.02):
+    """The reference's emRR / emBA / ... with its own hard-coded sweep counts (it = 200, or maxit and tol)."""
+    y = _f32(y)
+    X = _f32(gen)
+    n, p = X.shape
+    mu = C.c_double()
+    b, d, vbv = (np.zeros(p) for _ in range(3))
+    hat = np.zeros(n)
+    scal = np.zeros(6)
+    rc = lib().ref_em(C.c_int(EM_MODELS[model]), _p(y, C.c_float), _p(X, C.c_float), C.c_int(n), C.c_int(p), C.c_float(df),
+                      C.c_float(R2), C.c_float(Pi), C.c_float(alpha), C.byref(mu), _p(b, C.c_double), _p(d, C.c_double),
+                      _p(hat, C.c_double), _p(vbv, C.c_double), _p(scal, C.c_double))
+    assert rc == 0
+    Va, Ve, h2, Vg, pi_out, lmb_out = scal
+    out = {"mu": mu.value, "b": b, "hat": hat}
+    if model == "emRR":
+        out.update(Va=Va, Ve=Ve, h2=h2)
+    elif model == "emBA":
+        out.update(Vb=vbv, Ve=Ve, h2=h2)
+    elif model == "emBB":
+        out.update(d=d, Vb=vbv, Ve=Ve, h2=h2)
+    elif model == "emBC":
+        out.update(d=d, Vg=Vg, Va=Va, Ve=Ve, h2=h2)
+    elif model == "emBL":
+        out.update(h2=h2)
+    elif model == "emEN":
+        out.update(Va=Va, Ve=Ve, h2=h2)
+    elif model == "emDE":
+        out.update(Vb=vbv, Ve=Ve, h2=h2)
+    elif model == "emML":
+        out.update(h2=h2, Vb=Vg, Va=Va, Ve=Ve)
+    elif model == "emBCpi":
+        out.update(d=d, pi=pi_out, Vg=Vg, Va=Va, Ve=Ve, h2=h2)
+    elif model == "lasso":
+        out.update(h2=h2, Lmb=lmb_out)
+    return out
+
+
+def gibbs(model, y, X, it=1500, bi=500, pi=0.95, df=5.0, R2=0.5, seed=1):
+    """The reference's BayesRR / BayesA / ... ; R::rnorm / rchisq / rbinom draw from std::mt19937_64(seed) in the shim."""
+    y = _f32(y)
+    X = _f32(X)
+    n, p = X.shape
+    mu = C.c_double()
+    b, d, vbv = (np.zeros(p) for _ in range(3))
+    hat = np.zeros(n)
+    scal = np.zeros(5)
+    rc = lib().ref_gibbs(C.c_int(GIBBS_MODELS[model]), _p(y, C.c_float), _p(X, C.c_float), C.c_int(n), C.c_int(p), C.c_float(it),
+                         C.c_float(bi), C.c_float(pi), C.c_float(df), C.c_float(R2), C.c_uint64(seed), C.byref(mu),
+                         _p(b, C.c_double), _p(d, C.c_double), _p(hat, C.c_double), _p(vbv, C.c_double), _p(scal, C.c_double))
+    assert rc == 0
+    vb, ve, h2, MSx, pi_out = scal
+    out = {"mu": mu.value, "b": b, "hat": hat, "ve": ve, "h2": h2, "MSx": MSx}
+    out["vb"] = vbv if model in ("BayesA", "BayesB", "BayesL", "BayesDpi") else vb
+    if model in ("BayesB", "BayesC", "BayesCpi", "BayesDpi"):
+        out["d"] = d
+    if model in ("BayesCpi", "BayesDpi"):
+        del out["MSx"]
+        out["pi"] = pi_out
+    return out
+
+
+def kmup(X, b, d, xx, e, L, Ve, pi, seed=1):
+    X = _f32(X)
+    n, p = X.shape
+    b, d, xx, e, L = (np.array(v, dtype=np.float32) for v in (b, d, xx, e, L))
+    lib().ref_kmup(_p(X, C.c_float), C.c_int(n), C.c_int(p), _p(b, C.c_float), _p(d, C.c_float), _p(xx, C.c_float), _p(e, C.c_float),
+                   _p(L, C.c_float), C.c_float(Ve), C.c_float(pi), C.c_uint64(seed))
+    return {"b": b, "d": d, "e": e}
+
+
+def kmup2(X, use, b, d, xx, E, L, Ve, pi, seed=1):
+    X = _f32(X)
+    n, p = X.shape
+    use = np.array(use, dtype=np.float32)
+    b, d, xx, E, L = (np.array(v, dtype=np.float32) for v in (b, d, xx, E, L))
+    e_out = np.zeros(use.size, dtype=np.float32)
+    lib().ref_kmup2(_p(X, C.c_float), C.c_int(n), C.c_int(p), _p(use, C.c_float), C.c_int(use.size), _p(b, C.c_float), _p(d, C.c_float),
+                    _p(xx, C.c_float), _p(E, C.c_float), _p(e_out, C.c_float), _p(L, C.c_float), C.c_float(Ve), C.c_float(pi),
+                    C.c_uint64(seed))
+    return {"b": b, "d": d, "e": e_out}
+
+
+def gs(which, y, e, gen, b, Lmb, xx, cxx, maxit=50):
+    """GSRR (which='GSRR') / GSFLM: the warm-start solvers of mm() (Rcpp20260726ai.cpp:1564-1628)."""
+    X = _f32(gen)
+    n, p = X.shape
+    y, e, b, Lmb, xx = (np.array(v, dtype=np.float32) for v in (y, e, b, Lmb, xx))
+    scal = np.zeros(4)
+    lib().ref_gs(C.c_int(0 if which == "GSRR" else 1), _p(y, C.c_float), _p(e, C.c_float), _p(X, C.c_float), C.c_int(n), C.c_int(p),
+                 _p(b, C.c_float), _p(Lmb, C.c_float), _p(xx, C.c_float), C.c_float(cxx), C.c_int(maxit), _p(scal, C.c_double))
+    return {"mu": scal[0], "b": b, "h2": scal[3], "e": e, "Lmb": Lmb}
+
+
+def cnt(X):
+    X = np.array(_f32(X), order="F")
+    lib().ref_cnt_imp(C.c_int(0), _p(X, C.c_float), C.c_int(X.shape[0]), C.c_int(X.shape[1]))
+    return X
+
+
+def imp(X):
+    X = np.array(_f32(X), order="F")
+    lib().ref_cnt_imp(C.c_int(1), _p(X, C.c_float), C.c_int(X.shape[0]), C.c_int(X.shape[1]))
+    return X
+
+
+def mrr3(Y, X, f32_variant=False, **kw):
+    par = dict(MRR3_DEFAULTS)
+    for key, v in kw.items():
+        if key == "NonLinearFactor":
+            key = "NLfactor"
+        if key not in par:
+            raise TypeError("unknown MRR3 argument %r" % key)
+        par[key] = v
+    Y = np.asfortranarray(Y, dtype=np.float64)
+    X = np.asfortranarray(X, dtype=np.float64)
+    n, k = Y.shape
+    p = X.shape[1]
+    pv = np.array([float(par[name]) for name in MRR3_DEFAULTS], dtype=np.float64)
+    maxit = int(par["maxit"])
+    mu, h2, ve, MSx = (np.zeros(k) for _ in range(4))
+    b = np.zeros((p, k), order="F")
+    W = np.zeros((p, k), order="F")
+    hat = np.zeros((n, k), order="F")
+    GC = np.zeros((k, k), order="F")
+    vb = np.zeros((k, k), order="F")
+    cnv = np.zeros(3 * maxit)
+    its = C.c_int()
+    lib().ref_mrr3(C.c_int(int(f32_variant)), _p(Y, C.c_double), _p(X, C.c_double), C.c_int(n), C.c_int(k), C.c_int(p),
+                   _p(pv, C.c_double), _p(mu, C.c_double), _p(b, C.c_double), _p(hat, C.c_double), _p(h2, C.c_double),
+                   _p(GC, C.c_double), _p(vb, C.c_double), _p(ve, C.c_double), _p(MSx, C.c_double), _p(cnv, C.c_double),
+                   _p(W, C.c_double), C.byref(its))
+    q = its.value
+    return {"mu": mu, "b": b, "hat": hat, "h2": h2, "GC": GC, "vb": vb, "ve": ve, "MSx": MSx, "cnvB": cnv[:q],
+            "cnvH2": cnv[maxit:maxit + q], "cnvV": cnv[2 * maxit:2 * maxit + q], "b_Weights": W, "Its": q}

@@ -129,6 +129,11 @@ def test_em_tpod_matches_golden(tpod, model, path):
     # the converged fit is compared, the sweep count is only bounded
     _close_em(out, ref, model, ref64, check_its=model != "emML")
     assert 0 < out["its"] <= 300
+    # ... and against the REFERENCE-EXECUTED golden: the reference's own source compiled into oracle/_ref (oracle/make_golden.py)
+    assert str(gold["provenance"]) == "reference-executed"
+    refx = {k.split("__")[1]: gold[k] for k in gold.files if k.startswith(model + "_ref__")}
+    refx = {k: (v.item() if v.ndim == 0 else v) for k, v in refx.items()}
+    _close_em(out, refx, model, ref64, check_its=False)
 
 
 @pytest.mark.parametrize("path", [1, 2])
