@@ -23,6 +23,13 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def _need(cond, what):
+    """The C ABI takes plain pointers and reads g.n / g.p elements from them: a short vector must be an error here, not a
+    host out-of-bounds read there (BWGR_ERR_ARG, like the C side's own argument checks)."""
+    if not cond:
+        raise _lib.BwgrError(-1, what)
+
+
 class Genotypes:
     """Genotype matrix resident in HBM (int8 column-major or 2-bit packed) behind one bwgr_handle."""
 
@@ -44,6 +51,8 @@ class Genotypes:
             p, n = X.shape
             assert X.is_contiguous()
             fn = self.lib.bwgr_geno_load_i8_device if X.is_cuda else self.lib.bwgr_geno_load_i8
+            if X.is_cuda:  # the handle copies on its own non-blocking stream: the kernels that produced X must have finished
+                torch.cuda.current_stream(X.device).synchronize()
             check(fn(self.h, C.c_void_p(X.data_ptr()), n, p, n, storage))
         else:
             X = np.asarray(X)
@@ -289,6 +298,7 @@ def gibbs_fit(model, y, X, it=1500, bi=500, pi=0.95, df=5.0, R2=0.5, seed=1, nch
     g, own = _store(X, **store_kw)
     try:
         y = np.ascontiguousarray(y, dtype=np.float64)
+        _need(y.size == g.n, "y has %d values, the genotype store %d rows" % (y.size, g.n))
         nc = int(nchains)
         mu = np.zeros(nc)
         b = np.zeros((g.p, nc), order="F")
@@ -358,6 +368,8 @@ def KMUP(X, b, d, xx, e, L, Ve, pi, seed=1, **store_kw):
     g, own = _store(X, **store_kw)
     try:
         b, d, xx, e, L = (np.array(v, dtype=np.float64) for v in (b, d, xx, e, L))
+        _need(b.size == g.p and d.size == g.p and xx.size == g.p and L.size == g.p, "KMUP: b, d, xx, L must have p = %d values" % g.p)
+        _need(e.size == g.n, "KMUP: e must have n = %d values" % g.n)
         check(g.lib.bwgr_kmup_sweep(g.h, _ptr(b), _ptr(d), _ptr(xx), _ptr(e), _ptr(L), float(Ve), float(pi), int(seed)))
         return {"b": b, "d": d, "e": e}
     finally:
@@ -374,6 +386,7 @@ def wgr(y, X, it=1500, bi=500, th=1, bag=1, rp=False, iv=False, de=False, pi=0, 
     g, own = _store(X, **store_kw)
     try:
         y = np.ascontiguousarray(y, dtype=np.float64)
+        _need(y.size == g.n, "y has %d values, the genotype store %d rows" % (y.size, g.n))
         b, d, Vb = (np.zeros(g.p) for _ in range(3))
         hat = np.zeros(g.n)
         scal = np.zeros(4)
@@ -404,6 +417,7 @@ def MRR3(Y, X, f32_variant=False, verbose=False, **kw):
     g, own = _store(X)
     try:
         Y = np.asfortranarray(Y, dtype=np.float64)
+        _need(Y.ndim == 2 and Y.shape[0] == g.n, "Y must be n x k with n = %d rows" % g.n)
         n, k = Y.shape
         p = g.p
         pv = np.array([float(par[name]) for name in _MRR3_DEFAULTS], dtype=np.float64)

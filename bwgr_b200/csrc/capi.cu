@@ -948,8 +948,9 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
           a.trace = f.trace.p;
         }
         cudaEvent_t pe = h->prof_begin(1);
-        launch_sweep_pipe(a, h->stream);
+        const cudaError_t le = launch_sweep_pipe(a, h->stream);
         h->prof_end(pe);
+        if (le != cudaSuccess) return fail(BWGR_ERR_CUDA, "pipelined sweep launch failed: %s", cudaGetErrorString(le));
         h->launches++;
       } else {
         CU(cudaMemsetAsync(f.gacc.p, 0, sizeof(long long) * (size_t)f.nblocks * kNC * f.nsys * kBlk, h->stream));
@@ -1075,6 +1076,7 @@ int bwgr_em_end(bwgr_handle* h, bwgr_em_out* out) {
   std::vector<SysScalars> sc(ns);
   CU(cudaMemcpyAsync(sc.data(), f.sc.p, sizeof(SysScalars) * ns, cudaMemcpyDeviceToHost, h->stream));
   std::vector<float> hb((size_t)ns * p), hd, hv, hh((size_t)ns * n), he;
+  std::vector<uint8_t> hmask;  // row masks of masked systems (emBL's var(e))
   CU(cudaMemcpyAsync(hb.data(), f.b.p, sizeof(float) * hb.size(), cudaMemcpyDeviceToHost, h->stream));
   if (f.d.p && out->d) { hd.resize((size_t)ns * p); CU(cudaMemcpyAsync(hd.data(), f.d.p, sizeof(float) * hd.size(), cudaMemcpyDeviceToHost, h->stream)); }
   if (f.vbv.p && (out->vb || f.model == M_EMDE)) { hv.resize((size_t)ns * p); CU(cudaMemcpyAsync(hv.data(), f.vbv.p, sizeof(float) * hv.size(), cudaMemcpyDeviceToHost, h->stream)); }
@@ -1098,8 +1100,14 @@ int bwgr_em_end(bwgr_handle* h, bwgr_em_out* out) {
       case M_EMBA: case M_EMBB: h2 = 1.0f - c.ve / f.vy[t]; break;
       case M_EMBC: Va = c.vb; Vg = c.vb * f.MSx[t]; h2 = 1.0f - c.ve / f.vy[t]; break;
       case M_EMBL: {
+        // var(e) over the rows the system uses (:391): a masked system's held-out rows never enter e (they stay 0)
         std::vector<float> ev;
-        for (int64_t i = 0; i < n; i++) ev.push_back(he[(size_t)t * ld + i]);
+        if (f.masked && hmask.empty()) {
+          hmask.resize((size_t)ns * ld);
+          CU(cudaMemcpy(hmask.data(), f.mask.p, hmask.size(), cudaMemcpyDeviceToHost));
+        }
+        for (int64_t i = 0; i < n; i++)
+          if (!f.masked || hmask[(size_t)t * ld + i]) ev.push_back(he[(size_t)t * ld + i]);
         if (h->world > 1) {  // var(e) over all individuals (:391)
           double sums[2] = {0, 0};
           for (float v : ev) sums[0] += v;
@@ -1172,7 +1180,8 @@ int bwgr_em_fit(bwgr_handle* h, const bwgr_em_params* par, const double* y, bwgr
 
 // ---- Gibbs -------------------------------------------------------------------------------------------
 int bwgr_gibbs_fit(bwgr_handle* h, const bwgr_gibbs_params* par, const double* y, bwgr_gibbs_out* out) {
-  if (!h || !par || !out) return fail(BWGR_ERR_ARG, "null argument");
+  if (!h || !par || !out || !y) return fail(BWGR_ERR_ARG, "null argument");
+  if (!h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
   if (par->model < 0 || par->model > BWGR_GIBBS_DPI) return fail(BWGR_ERR_ARG, "bad Gibbs model %d", par->model);
   static const int kGibbsModel[] = {M_BRR, M_BA, M_BB, M_BC, M_BL, M_BCPI, M_BDPI};
   const bool has_pi = par->model == BWGR_GIBBS_CPI || par->model == BWGR_GIBBS_DPI;  // these two start at pi = 0.5 (:870, :934), not an argument

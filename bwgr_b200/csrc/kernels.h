@@ -142,7 +142,7 @@ struct PipeArgs {
   int* err;
   long long* trace;      // optional [nblocks][16] clock64 stamps (BWGR_TRACE), else nullptr
 };
-void launch_sweep_pipe(const PipeArgs& a, cudaStream_t st);
+cudaError_t launch_sweep_pipe(const PipeArgs& a, cudaStream_t st);
 size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring, int full_inv);
 // T_b = (I + A_b L_b)^-1 for every 128-marker block of the sweep (linear rules, one system): [nblocks][128][128] float
 void launch_block_inverse(int model, const int* perm, int p, int nblocks, const float* gram, int nband, const float* xx,

@@ -1194,11 +1194,12 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
 }
 
 template <int MODEL>
-void launch_model(const PipeArgs& a, size_t smem, cudaStream_t st) {
-  cudaFuncSetAttribute(sweep_pipe_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t launch_model(const PipeArgs& a, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(sweep_pipe_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
   PipeArgs args = a;
   void* params[] = {&args};
-  cudaLaunchCooperativeKernel((void*)sweep_pipe_kernel<MODEL>, dim3(a.nworkers + 1), dim3(kT), params, smem, st);
+  return cudaLaunchCooperativeKernel((void*)sweep_pipe_kernel<MODEL>, dim3(a.nworkers + 1), dim3(kT), params, smem, st);
 }
 
 }  // namespace
@@ -1210,27 +1211,28 @@ size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int srin
   return (w > s ? w : s) + 1024;
 }
 
-void launch_sweep_pipe(const PipeArgs& a, cudaStream_t st) {
+cudaError_t launch_sweep_pipe(const PipeArgs& a, cudaStream_t st) {
   const size_t smem = sweep_pipe_smem(a.rows_per_cta, a.nsys, a.model, a.nbuf, a.sring, a.tinv != nullptr);
   switch (rule_model(a.model)) {
-    case M_EMRR: launch_model<M_EMRR>(a, smem, st); break;
-    case M_EMBA: launch_model<M_EMBA>(a, smem, st); break;
-    case M_EMBB: launch_model<M_EMBB>(a, smem, st); break;
-    case M_EMBC: launch_model<M_EMBC>(a, smem, st); break;
-    case M_EMBL: launch_model<M_EMBL>(a, smem, st); break;
-    case M_EMEN: launch_model<M_EMEN>(a, smem, st); break;
-    case M_BRR: launch_model<M_BRR>(a, smem, st); break;
-    case M_BA: launch_model<M_BA>(a, smem, st); break;
-    case M_BB: launch_model<M_BB>(a, smem, st); break;
-    case M_BC: launch_model<M_BC>(a, smem, st); break;
-    case M_KMUP: launch_model<M_KMUP>(a, smem, st); break;
-    case M_MRR: launch_model<M_MRR>(a, smem, st); break;
-    case M_EMDE: launch_model<M_EMDE>(a, smem, st); break;
-    case M_LASSO: launch_model<M_LASSO>(a, smem, st); break;
-    case M_BL: launch_model<M_BL>(a, smem, st); break;
-    case M_BDPI: launch_model<M_BDPI>(a, smem, st); break;
+    case M_EMRR: return launch_model<M_EMRR>(a, smem, st);
+    case M_EMBA: return launch_model<M_EMBA>(a, smem, st);
+    case M_EMBB: return launch_model<M_EMBB>(a, smem, st);
+    case M_EMBC: return launch_model<M_EMBC>(a, smem, st);
+    case M_EMBL: return launch_model<M_EMBL>(a, smem, st);
+    case M_EMEN: return launch_model<M_EMEN>(a, smem, st);
+    case M_BRR: return launch_model<M_BRR>(a, smem, st);
+    case M_BA: return launch_model<M_BA>(a, smem, st);
+    case M_BB: return launch_model<M_BB>(a, smem, st);
+    case M_BC: return launch_model<M_BC>(a, smem, st);
+    case M_KMUP: return launch_model<M_KMUP>(a, smem, st);
+    case M_MRR: return launch_model<M_MRR>(a, smem, st);
+    case M_EMDE: return launch_model<M_EMDE>(a, smem, st);
+    case M_LASSO: return launch_model<M_LASSO>(a, smem, st);
+    case M_BL: return launch_model<M_BL>(a, smem, st);
+    case M_BDPI: return launch_model<M_BDPI>(a, smem, st);
     default: break;
   }
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace bwgr

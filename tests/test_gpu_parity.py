@@ -34,7 +34,9 @@ def _close_em(out, ref, model, ref64=None, check_its=True):
         if key in ref:
             assert abs(out[key] - ref[key]) <= RTOL * max(abs(ref[key]), 1e-3) + noise(key), key
     if "d" in ref:
-        assert np.abs(out["d"] - ref["d"]).max() <= 1e-3, "d"
+        # d = 1/(1 + Pi0 exp(C(|e2|^2 - |e1|^2))): the reference subtracts two O(n) float sums (:165, :224), whose cancellation noise
+        # grows with n -- the bar is widened by the float oracle's own distance to its double recipe
+        assert np.abs(out["d"] - ref["d"]).max() <= 1e-3 + noise("d"), "d"
     if "Vb" in ref and model in ("emBA", "emBB", "emDE"):
         assert np.abs(out["Vb"] - ref["Vb"]).max() <= RTOL * np.abs(ref["Vb"]).max() + noise("Vb"), "Vb"
     if check_its:
@@ -485,3 +487,113 @@ def test_full_size_properties():
     Ve = (((y - a["hat"]) ** 2).sum() + (1 - R2) * (df + 2) * vy) / (n + df)  # :339, up to n * mean(e)^2 (removed after Ve is taken)
     assert abs(a["Ve"] - Ve) <= 1e-3 * Ve
     assert a["its"] == 3 and np.corrcoef(a["hat"], y)[0, 1] > 0.3
+
+
+# ======================================================================================================================
+# Parity at the geometry the bench runs: n = 50,000 rows -> 143 workers x 352 rows, 3 row atoms,
+# the same sweep kernel configuration as bench.py; p is cut to 2,048 markers so that the CPU oracle finishes in seconds
+# (its cost per marker does not depend on p).
+# ======================================================================================================================
+@pytest.fixture(scope="module")
+def bench_slice():
+    X, y = synth(50000, 2048, seed=20261018)
+    return X, y
+
+
+@pytest.mark.parametrize("model", ["emRR", "emBA", "emBC"])
+def test_blocked_path_at_bench_geometry(bench_slice, model):
+    X, y = bench_slice
+    it = 8
+    ref = O.em(model, y, X.astype(np.float32), it=it)
+    ref64 = O.em(model, y, X.astype(np.float32), it=it, use_double=True)
+    with bw.Genotypes(X, path=2) as g:
+        out = bw.em_fit(model, y, g, it=it)
+    _close_em(out, ref, model, ref64)
+
+
+def test_bayesb_at_config2_geometry():
+    """BASELINE config 2's shape in n (10,000 rows), 2,048 markers: posterior means across seeds, blocked family."""
+    X, y = synth(10000, 2048, seed=77)
+    Xf = X.astype(np.float64)
+    seeds = range(4)
+    ora = [O.gibbs("BayesB", y, Xf, it=200, bi=50, seed=300 + s) for s in seeds]
+    with bw.Genotypes(X, path=2) as g:
+        gpu = [bw.gibbs_fit("BayesB", y, g, it=200, bi=50, seed=400 + s) for s in seeds]
+    for key in ("h2", "ve", "mu"):
+        a = np.array([r[key] for r in ora]); b = np.array([r[key] for r in gpu])
+        se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+        assert abs(a.mean() - b.mean()) <= 4 * se + 2e-3 * abs(a.mean()), (key, a.mean(), b.mean(), se)
+    A = np.mean([r["hat"] for r in ora], 0); B = np.mean([r["hat"] for r in gpu], 0)
+    assert np.corrcoef(A, B)[0, 1] > 0.99
+    da = np.mean([r["d"].mean() for r in ora]); db = np.mean([r["d"].mean() for r in gpu])
+    assert abs(da - db) < 0.02
+
+
+def test_mrr3_twenty_traits():
+    """BASELINE config 3's trait count: MRR3 at k = 20 (80 limb columns -> N = 96 TMEM columns, three rounds of solve warps) on
+    3000 x 2000 synthetic genotypes with SimY-style correlated traits (GC = 0.5), after 1, 3 and 12 sweeps."""
+    X, _ = synth(3000, 2000, seed=5)
+    rng = np.random.default_rng(8)
+    k, p = 20, X.shape[1]
+    Lc = np.linalg.cholesky(0.5 * np.ones((k, k)) + 0.5 * np.eye(k))
+    B = (rng.normal(size=(p, k)) @ Lc.T) * (rng.random((p, 1)) < 0.05)
+    G = X.astype(np.float64) @ B
+    Y = G / G.std(0) + rng.normal(size=G.shape)
+    Xf = X.astype(np.float64)
+    with bw.Genotypes(X) as g:
+        for its in (1, 3, 12):
+            ref = O.mrr3(Y, Xf, maxit=its)
+            out = bw.MRR3(Y, g, maxit=its)
+            assert out["Its"] == ref["Its"] == its
+            _close_mrr(out, ref, 2e-4)
+
+
+def test_cv_pattern_twenty_traits_five_folds():
+    """BASELINE config 4's pattern at 2000 x 1500: 20 traits x 5 folds = 100 emBC fits, (i) as masked systems of ONE store on the
+    small-n family, (ii) fold by fold on row-subset stores with the traits of a fold as one multi-system fit of the blocked
+    family -- both against per-subset oracle fits (what emCV does with gen[-w,], R/cv.R:13-22)."""
+    n, p, k, nf, it = 2000, 1500, 20, 5, 10
+    X, Y = synth(n, p, k=k, seed=31)
+    perm = np.random.default_rng(1).permutation(n)
+    held = [np.sort(perm[f * n // nf:(f + 1) * n // nf]) for f in range(nf)]
+    refs = {}
+    for f in range(nf):
+        keep = np.ones(n, bool); keep[held[f]] = False
+        for t in range(k):
+            refs[f, t] = O.em("emBC", Y[keep, t], X[keep].astype(np.float32), it=it)
+    # (i) one store, 100 masked systems (system s = fold s // k, trait s % k)
+    masks = np.ones((n, nf * k), bool)
+    Yall = np.empty((n, nf * k))
+    for f in range(nf):
+        masks[held[f], f * k:(f + 1) * k] = False
+        Yall[:, f * k:(f + 1) * k] = Y
+    with bw.Genotypes(X) as g:
+        out = bw.em_fit("emBC", Yall, g, it=it, row_mask=masks)
+    for (f, t), ref in refs.items():
+        s = f * k + t
+        assert np.abs(out["b"][:, s] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max(), (f, t)
+        assert abs(out["h2"][s] - ref["h2"]) <= RTOL, (f, t)
+    # (ii) per fold: row-subset store, 20 traits as one blocked multi-system fit
+    for f in range(nf):
+        keep = np.ones(n, bool); keep[held[f]] = False
+        with bw.Genotypes(np.asfortranarray(X[keep]), path=2) as g:
+            o = bw.em_fit("emBC", np.asfortranarray(Y[keep]), g, it=it)
+        for t in range(k):
+            ref = refs[f, t]
+            assert np.abs(o["b"][:, t] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max(), (f, t)
+            assert abs(o["h2"][t] - ref["h2"]) <= RTOL, (f, t)
+
+
+def test_masked_folds_emBL_emEN():
+    """emBL's h2 = 1 - var(e)/var(y) must take var(e) over the kept rows of a masked system."""
+    X, Y = synth(600, 400, k=2, seed=19)
+    fold = np.random.default_rng(2).integers(0, 3, size=600)
+    masks = np.stack([fold != 0, fold != 1], axis=1)
+    for model in ("emBL", "emEN"):
+        with bw.Genotypes(X) as g:
+            out = bw.em_fit(model, Y, g, it=25, row_mask=masks)
+        for t in range(2):
+            keep = masks[:, t]
+            ref = O.em(model, Y[keep, t], X[keep].astype(np.float32), it=25)
+            assert np.abs(out["b"][:, t] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max(), (model, t)
+            assert abs(out["h2"][t] - ref["h2"]) <= 2 * RTOL, (model, t, out["h2"][t], ref["h2"])
