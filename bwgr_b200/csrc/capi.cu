@@ -18,6 +18,8 @@
 #include <cstring>
 #include <random>
 #include <string>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "../../include/bwgr_b200.h"
@@ -87,10 +89,10 @@ struct Fit {
   DevBuf<unsigned int> bar;
   // pipelined sweep (sweep_pipe.cu)
   bool pipe = false;
-  int lookahead = 0, nbuf = 0, sring = 2, nworkers = 0, nc = 1, nband = 1, full_inv = 0;
+  int lookahead = 0, nbuf = 0, sring = 2, nworkers = 0, nc = 1, nband = 1, full_inv = 0, cl = 0, nclusters = 0;
   DevBuf<float> tinv;                   // (I + A L)^-1 of every block of the current sweep (block_inv.cu)
   uint32_t tag = 0;
-  DevBuf<unsigned long long> dew, part;
+  DevBuf<unsigned long long> dew, part, cx;
   float* gram_p = nullptr;              // Gram band in use: f.gram (per fit) or the handle's natural-order cache
   // single Kuo-Mallick sweep / wgr driver
   DevBuf<float> xx_over;                // caller's xx (KMUP takes it as an argument, :12) / centred xx (MRR3)
@@ -419,24 +421,66 @@ int bwgr_set_tuning(bwgr_handle* h, int block, int path, int grid) {
 int64_t bwgr_launch_count(bwgr_handle* h) { return h ? h->launches : 0; }
 
 // ---- genotype store ---------------------------------------------------------------------------------
+// The boundary conversion of the reference is Rcpp::as<Eigen::MatrixXf> (src/RcppExports.cpp:115-116): a full n x p copy + cast on
+// the CPU, once per call.  Here it happens once per store: a few host threads narrow R's doubles to int8 (exact integers in range
+// only; anything else is an error, never rounded) into two pinned staging buffers laid out like the device store, and the H2D
+// copy of chunk i overlaps the narrowing of chunk i + 1 -- n * p bytes cross PCIe instead of 8 * n * p.
+static void narrow_columns(const double* X, int64_t ld_src, int64_t n, int64_t ld_dst, int64_t j0, int64_t j1, int8_t* dst, int lo, int hi,
+                           std::atomic<int>* bad) {
+  int flag = 0;
+  for (int64_t j = j0; j < j1; j++) {
+    const double* src = X + j * ld_src;
+    int8_t* out = dst + (j - j0) * ld_dst;
+    for (int64_t i = 0; i < n; i++) {
+      const double v = src[i];
+      const int iv = (int)v;
+      flag |= !((double)iv == v) | (iv < lo) | (iv > hi);
+      out[i] = (int8_t)iv;
+    }
+    for (int64_t i = n; i < ld_dst; i++) out[i] = 0;
+  }
+  if (flag) bad->store(1);
+}
+
 int bwgr_geno_load_f64(bwgr_handle* h, const double* X, int64_t n, int64_t p, int64_t ld, int storage) {
   if (!X || ld < n) return fail(BWGR_ERR_ARG, "bad X / ld");
   int rc = prepare_store(h, n, p, storage);
   if (rc) return rc;
-  // stream the R matrix through a bounded staging buffer (n x p doubles may not fit beside the store)
-  const int64_t chunk_cols = std::max<int64_t>(1, std::min<int64_t>(p, ((int64_t)256 << 20) / (8 * n)));
-  DevBuf<double> stage;
-  if (stage.alloc((size_t)chunk_cols * n) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(staging) failed");
   const int lo = storage == BWGR_STORE_2BIT ? 0 : -128, hi = storage == BWGR_STORE_2BIT ? 2 : 127;
-  for (int64_t j0 = 0; j0 < p; j0 += chunk_cols) {
-    const int64_t pc = std::min(chunk_cols, p - j0);
-    CU(cudaMemcpy2DAsync(stage.p, n * 8, X + j0 * ld, ld * 8, n * 8, pc, cudaMemcpyHostToDevice, h->stream));
-    launch_pack_f64(stage.p, n, (int)n, (int)pc, h->x8_own.p + j0 * h->ld, h->ld, lo, hi, h->err.p, h->stream);
-    h->launches++;
-    CU(cudaStreamSynchronize(h->stream));
+  const int64_t ldd = h->ld;
+  const int64_t chunk_cols = std::max<int64_t>(1, std::min<int64_t>(p, ((int64_t)32 << 20) / ldd));
+  const size_t chunk_bytes = (size_t)chunk_cols * ldd;
+  int8_t* stage[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2; i++) {
+    if (cudaMallocHost(reinterpret_cast<void**>(&stage[i]), chunk_bytes) != cudaSuccess || cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) {
+      for (int k = 0; k < 2; k++) { if (stage[k]) cudaFreeHost(stage[k]); if (done[k]) cudaEventDestroy(done[k]); }
+      return fail(BWGR_ERR_CUDA, "cudaMallocHost(staging) failed");
+    }
   }
-  rc = check_err_flag(h, "bwgr_geno_load_f64");
-  if (rc) return rc;
+  unsigned hc = std::thread::hardware_concurrency();
+  const int nthr = (int)std::max(1u, std::min(hc ? hc : 4u, 32u));
+  std::atomic<int> bad(0);
+  cudaError_t ce = cudaSuccess;
+  int64_t nchunk = 0;
+  for (int64_t j0 = 0; j0 < p && ce == cudaSuccess; j0 += chunk_cols, nchunk++) {
+    const int64_t pc = std::min(chunk_cols, p - j0);
+    const int sb = (int)(nchunk & 1);
+    if (nchunk >= 2) ce = cudaEventSynchronize(done[sb]);  // the copy that last read this buffer has finished
+    if (ce != cudaSuccess) break;
+    const int nt = (int)std::min<int64_t>(nthr, pc);
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; t++)
+      pool.emplace_back(narrow_columns, X, ld, n, ldd, j0 + pc * t / nt, j0 + pc * (t + 1) / nt, stage[sb] + (pc * t / nt) * ldd, lo, hi, &bad);
+    narrow_columns(X, ld, n, ldd, j0, j0 + pc / nt, stage[sb], lo, hi, &bad);
+    for (auto& th : pool) th.join();
+    ce = cudaMemcpyAsync(h->x8_own.p + j0 * ldd, stage[sb], (size_t)pc * ldd, cudaMemcpyHostToDevice, h->stream);
+    if (ce == cudaSuccess) ce = cudaEventRecord(done[sb], h->stream);
+  }
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+  for (int i = 0; i < 2; i++) { cudaFreeHost(stage[i]); cudaEventDestroy(done[i]); }
+  if (ce != cudaSuccess) return fail(BWGR_ERR_CUDA, "bwgr_geno_load_f64: %s", cudaGetErrorString(ce));
+  if (bad.load()) return fail(BWGR_ERR_ARG, "bwgr_geno_load_f64: non-integer or out-of-range genotype");
   return finish_store(h, storage);
 }
 
@@ -518,7 +562,7 @@ struct FitSpec {
 
 // Geometry of the pipelined sweep: W streaming CTAs (row slabs of R rows, R <= 512) + one solver CTA, look-ahead D,
 // nbuf X tiles per worker.  False if the shape does not fit one SM's shared memory / TMEM.
-struct PipePlan { int R, W, nbuf, D, sring, full_inv; };
+struct PipePlan { int R, W, nbuf, D, sring, full_inv, cl, nclusters; };
 bool plan_pipe(const bwgr_handle* h, int model, int ns, PipePlan* pl) {
   const char* sw = getenv("BWGR_SWEEP");
   if (sw && !strcmp(sw, "v4")) return false;
@@ -539,10 +583,40 @@ bool plan_pipe(const bwgr_handle* h, int model, int ns, PipePlan* pl) {
   // four dependent 32-marker steps.  (MRR3's centred systems keep the stepwise solve.)
   const char* ti = getenv("BWGR_TINV");
   const int full_inv = model_is_linear(model) && ns == 1 && model != M_MRR && !(ti && !strcmp(ti, "0"));
+  pl->cl = 0; pl->nclusters = 0;
+  // Clustered topology (sweep_pipe.cu): thread-block clusters of one solver + seven workers; partial sums and steps travel
+  // through distributed shared memory, one L2 hop per block is left (the exchange of the cluster sums between the solvers).
+  // Single GPU, at most four systems; BWGR_CLUSTER=0 keeps the flat topology (one solver CTA, two-hop L2 tree).
+  const char* ce = getenv("BWGR_CLUSTER");
+  if (D >= 1 && h->world <= 1 && h->grid <= 1 && !(ce && !strcmp(ce, "0")) && sweep_pipe_cluster_ok(model, ns, full_inv)) {
+    for (int nbuf = D + 2; nbuf >= D + 1; nbuf--) {
+      // rows per worker depend on the number of co-resident clusters, which depends on the shared memory per CTA: iterate
+      int C = 18;
+      for (int iter = 0; iter < 4 && C >= 2; iter++) {
+        const int Wc = 7 * C;
+        const int Rc = (int)(((h->ld + Wc - 1) / Wc + 15) / 16 * 16);
+        if (Rc > 512) { C = 0; break; }
+        const size_t smem = sweep_pipe_smem(Rc, ns, model, nbuf, 3, full_inv, 1);
+        if (smem > h->smem_optin - 4096) { C = 0; break; }
+        const int Cmax = std::min(18, sweep_pipe_max_clusters(model, smem));
+        if (Cmax >= C) break;
+        C = Cmax;
+      }
+      if (C >= 2) {
+        const int Wc = 7 * C;
+        const int Rc = (int)(((h->ld + Wc - 1) / Wc + 15) / 16 * 16);
+        const int NAc = (Rc + 127) / 128;
+        if ((NAc + 1) * N <= 512 && sweep_pipe_smem(Rc, ns, model, nbuf, 3, full_inv, 1) <= h->smem_optin - 4096) {
+          pl->R = Rc; pl->W = Wc; pl->nbuf = nbuf; pl->D = D; pl->sring = 3; pl->full_inv = full_inv; pl->cl = 1; pl->nclusters = C;
+          return true;
+        }
+      }
+    }
+  }
   for (; D >= 0; D--) {
     for (int sring = 3; sring >= 2; sring--)
       for (int nbuf = std::min(8, D + 3); nbuf >= D + 1; nbuf--)
-        if (sweep_pipe_smem(R, ns, model, nbuf, sring, full_inv) <= h->smem_optin - 8192) {
+        if (sweep_pipe_smem(R, ns, model, nbuf, sring, full_inv, 0) <= h->smem_optin - 8192) {
           pl->R = R; pl->W = W; pl->nbuf = nbuf; pl->D = D; pl->sring = sring; pl->full_inv = full_inv;
           return true;
         }
@@ -841,7 +915,8 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
       if (rc) return rc;
     }
     if (f.pipe) {
-      f.rows_per_cta = pl.R; f.nworkers = pl.W; f.grid = pl.W + 1; f.nbuf = pl.nbuf; f.sring = pl.sring; f.lookahead = pl.D; f.full_inv = pl.full_inv; f.nband = pl.D + 1;
+      f.rows_per_cta = pl.R; f.nworkers = pl.W; f.grid = pl.cl ? pl.nclusters * 8 : pl.W + 1; f.nbuf = pl.nbuf; f.sring = pl.sring; f.lookahead = pl.D; f.full_inv = pl.full_inv; f.nband = pl.D + 1;
+      f.cl = pl.cl; f.nclusters = pl.nclusters;
       f.nc = std::max(1, 16 / ns);
       f.tag = 0;
       const size_t gram_n = (size_t)f.nblocks * kBlk * kBlk * f.nband;
@@ -862,6 +937,8 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
       if (
           f.part.alloc((size_t)8 * ns * 128 * 161) != cudaSuccess || f.dew.alloc((size_t)f.nblocks * ns * 136) != cudaSuccess)
         return fail(BWGR_ERR_CUDA, "cudaMalloc(blocked workspace) failed");
+      if (f.cl && f.cx.alloc((size_t)8 * f.nclusters * ns * 128) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(cluster ring) failed");
+      if (!f.cl) f.cx.release();
       CU(cudaMemsetAsync(f.dew.p, 0, sizeof(unsigned long long) * f.dew.n, h->stream));
     } else {
       const int grid0 = h->grid > 0 ? std::min(h->grid, h->num_sms) : h->num_sms;
@@ -932,7 +1009,8 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
         h->launches++;
       }
       if (f.pipe) {
-        CU(cudaMemsetAsync(f.part.p, 0, sizeof(unsigned long long) * f.part.n, h->stream));
+        if (f.cl) CU(cudaMemsetAsync(f.cx.p, 0, sizeof(unsigned long long) * f.cx.n, h->stream));
+        else CU(cudaMemsetAsync(f.part.p, 0, sizeof(unsigned long long) * f.part.n, h->stream));
         PipeArgs a;
         memset(&a, 0, sizeof a);
         a.g = g; a.model = rule_model(f.model); a.nsys = f.nsys; a.perm = d_perm; a.nblocks = f.nblocks; a.gram = f.gram_p; a.nband = f.nband; a.tinv = f.full_inv ? f.tinv.p : nullptr;
@@ -941,6 +1019,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
         a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0;
         a.rows_per_cta = f.rows_per_cta; a.nworkers = f.nworkers; a.D = f.lookahead; a.nbuf = f.nbuf; a.sring = f.sring; a.err = h->err.p;
         a.world = h->world; a.rank = h->rank; a.gen0 = h->dist_gen;
+        a.cl = f.cl; a.nclusters = f.nclusters; a.cx = f.cx.p;
         for (int r = 0; r < 8; r++) a.hx[r] = h->hx[r];
         if (h->world > 1) h->dist_gen += (unsigned long long)f.nblocks;
         if (getenv("BWGR_TRACE")) {

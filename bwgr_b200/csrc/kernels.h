@@ -141,9 +141,15 @@ struct PipeArgs {
   int sring;             // blocks of solve inputs in flight in the solver CTA (2 or 3)
   int* err;
   long long* trace;      // optional [nblocks][16] clock64 stamps (BWGR_TRACE), else nullptr
+  // clustered topology: nclusters thread-block clusters of 8 CTAs = one solver + seven workers each (nworkers = 7 * nclusters);
+  // cx = [8][nclusters][nsys][128] per-cluster sums of h, same word format as hred; zeroed before launch
+  int cl, nclusters;
+  unsigned long long* cx;
 };
 cudaError_t launch_sweep_pipe(const PipeArgs& a, cudaStream_t st);
-size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring, int full_inv);
+size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring, int full_inv, int cl);
+bool sweep_pipe_cluster_ok(int model, int nsys, int full_inv);
+int sweep_pipe_max_clusters(int model, size_t smem);
 // T_b = (I + A_b L_b)^-1 for every 128-marker block of the sweep (linear rules, one system): [nblocks][128][128] float
 void launch_block_inverse(int model, const int* perm, int p, int nblocks, const float* gram, int nband, const float* xx,
                           const float* vbv, const SysScalars* sc, float* tinv, cudaStream_t st);

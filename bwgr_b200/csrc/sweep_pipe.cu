@@ -26,6 +26,8 @@
 //
 // Critical path per block with D = 1: cross-Gram correction + in-block solve.  Everything else (gather,
 // both tensor-core passes, quantisation, L2 round trips) runs beside it.
+#include <string.h>
+
 #include "kernels.h"
 
 namespace bwgr {
@@ -155,6 +157,33 @@ __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsign
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// ---- thread-block clusters (clustered topology: rank 0 of every cluster of 8 is a solver, ranks 1..7 are its workers) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_idx() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// remote shared-memory store that counts its bytes on the destination CTA's mbarrier (no flag, no polling)
+__device__ __forceinline__ void st_async_u64(uint32_t raddr, unsigned long long v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(raddr), "l"(v), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void st_async_u32(uint32_t raddr, uint32_t v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(v), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr int kClSize = 8;             // CTAs per cluster: one solver + seven workers
+constexpr int kClWorkers = kClSize - 1;
+constexpr int kMaxCl = 18;             // clusters whose sums a solver gathers (B200: 15 co-resident clusters of 8 at ~200 KB per CTA)
+constexpr int kDeStride = 132;         // 32-bit words per (parity, system) of a worker's step inbox: 128 steps + the scale (+ pad)
+constexpr int kCommWarp0 = 4;          // clustered solver: warps 4-7 gather the partial sums (they are idle whenever CL is eligible)
+
 // Self-validating 64-bit words of the grid reduction: (signed value << 12) | tag, tag = 1 + (use index of the ring slot) mod 4095
 // (never 0 = freshly zeroed memory; consecutive uses of a slot always differ).  |value| < 2^51: a rank's sum of 143 worker
 // partials of 2^30 * 2 * 512 rows is < 2^48.
@@ -176,11 +205,13 @@ struct Sync {
   uint64_t tile_full[8], tile_empty[8], dl_full[2], u_done, el_full, g_done, g_empty;
   // solver
   uint64_t raw_ready[3], in_ready[3], solve_done[3], corr_ready[32], de_ready[32][4];
+  // clustered topology: step inbox of a worker, partial inbox of a solver, gathered sums ready for the solve warps
+  uint64_t de_in[2], h_in[2], h_ready[2];
   uint32_t tmem_base;
 };
 
-struct WLayout { int NA, N, nbuf; size_t xs, el, dl, es, dq, total; };
-__host__ __device__ inline WLayout worker_layout(int R, int ns, int nbuf) {
+struct WLayout { int NA, N, nbuf; size_t xs, el, dl, es, dq, di, total; };
+__host__ __device__ inline WLayout worker_layout(int R, int ns, int nbuf, bool cl = false) {
   WLayout L;
   L.NA = (R + 127) / 128; L.N = ((4 * ns + 15) / 16) * 16; L.nbuf = nbuf;
   size_t o = 0;
@@ -189,12 +220,13 @@ __host__ __device__ inline WLayout worker_layout(int R, int ns, int nbuf) {
   L.dl = o; o += (size_t)2 * (L.N / 8) * 1024;
   L.es = o; o += (size_t)ns * L.NA * 128 * 4;
   L.dq = o; o += (size_t)2 * 32 * 4;
+  L.di = o; o += cl ? (size_t)2 * ns * kDeStride * 4 : 0;  // step inbox, written by the cluster's solver (st.async)
   L.total = o;
   return L;
 }
-struct SLayout { size_t gs, mt, ms, mc, drw, tc, dh, rb, cs, total; };
+struct SLayout { size_t gs, mt, ms, mc, drw, tc, dh, rb, cs, hi, hs, total; };
 // sring = blocks of solve inputs in flight in the solver CTA (2 or 3)
-__host__ __device__ inline SLayout solver_layout(int ns, bool gibbs, bool use_inv, int sring) {
+__host__ __device__ inline SLayout solver_layout(int ns, bool gibbs, bool use_inv, int sring, bool cl = false) {
   SLayout L;
   size_t o = 0;
   L.gs = o; o += (size_t)sring * 10 * kTileF * 4;                        // Gram triangle
@@ -206,6 +238,9 @@ __host__ __device__ inline SLayout solver_layout(int ns, bool gibbs, bool use_in
   L.dh = o; o += (size_t)ns * 128 * 4;                                   // dE of the block being solved
   L.rb = o; o += (size_t)kSolveWarps * 32 * 4;
   L.cs = o; o += (size_t)32 * 2 * 4 + 2 * 4 * 4;  // running mean shift per system (centred columns): {current, before the last block}
+  o = (o + 15) & ~(size_t)15;
+  L.hi = o; o += cl ? (size_t)2 * kClWorkers * ns * 128 * 8 : 0;  // partial inbox [parity][worker][system][marker], written by the workers
+  L.hs = o; o += cl ? (size_t)2 * ns * 128 * 8 : 0;               // h summed over the whole grid [parity][system][marker]
   L.total = o;
   return L;
 }
@@ -213,7 +248,7 @@ __host__ __device__ inline bool pipe_use_inv(int model, int ns) { return model_i
 // one system, linear rule, uncentred columns: the four 32-marker steps of the in-block solve are spread over four warps
 __host__ __device__ inline bool pipe_wps4(int model, int ns, bool centred) { return model_is_linear(model) && ns == 1 && !centred; }
 
-template <int MODEL>
+template <int MODEL, bool CL>
 __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ Sync S;
@@ -221,7 +256,12 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ns = a.nsys, p = a.g.p, W = a.nworkers, D = a.D, nblocks = a.nblocks;
   unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const bool is_solver = (int)blockIdx.x == W;
+  // clustered topology (CL): rank 0 of every cluster is a solver (all solvers run the identical solve on the identical integer
+  // sums, like the ranks of a row-sharded fit), ranks 1..7 are its workers; worker index = cluster * 7 + rank - 1
+  const int crank = CL ? (int)cluster_ctarank() : 0, cluster = CL ? (int)cluster_idx() : 0;
+  const bool is_solver = CL ? crank == 0 : (int)blockIdx.x == W;
+  const int widx = CL ? cluster * kClWorkers + crank - 1 : (int)blockIdx.x;
+  const bool writer = !CL || cluster == 0;  // the solver that writes b / d / vb back to HBM
   bool dead = false;
 
   if (tid < ns) sc[tid] = a.sc[tid];
@@ -235,16 +275,27 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
       mbar_init(&S.corr_ready[s], 128);
       for (int d = 0; d < 4; d++) mbar_init(&S.de_ready[s][d], 1);
     }
+    for (int i = 0; i < 2; i++) { mbar_init(&S.de_in[i], 1); mbar_init(&S.h_in[i], 1); mbar_init(&S.h_ready[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (CL) {  // expected bytes of the first two blocks (every later phase is armed by the consumer of the phase before)
+      for (int i = 0; i < 2 && i < nblocks; i++) {
+        if (is_solver) mbar_expect_tx(&S.h_in[i], (uint32_t)(kClWorkers * ns * 128 * 8));
+        else mbar_expect_tx(&S.de_in[i], (uint32_t)(ns * 129 * 4));
+      }
+    }
   }
+  if (CL) cluster_sync_all();  // every CTA's barriers exist before the first remote store
 
   if (!is_solver) {
     // =====================================================================================================
     // worker
     // =====================================================================================================
-    const WLayout L = worker_layout(a.rows_per_cta, ns, a.nbuf);
+    const WLayout L = worker_layout(a.rows_per_cta, ns, a.nbuf, CL);
     const int R = a.rows_per_cta, NA = L.NA, N = L.N, RS = NA * 128, nbuf = L.nbuf;
-    const int row0 = blockIdx.x * R;
+    const int row0 = widx * R;
+    const uint32_t* dein = reinterpret_cast<const uint32_t*>(base + L.di);
+    // the solver's partial inbox sits at the same shared-window offset in every CTA of this launch
+    const uint32_t hin_u32 = smem_u32(base) + (uint32_t)solver_layout(ns, model_is_gibbs(MODEL), false, a.sring, CL).hi;
     unsigned char* Xs = base + L.xs;
     unsigned char* EL = base + L.el;
     unsigned char* DL = base + L.dl;
@@ -346,14 +397,18 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
         if (t0) WSTAMP(c, 6);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // partial of marker q, system s -> part[c % ring][s][this worker][q] (full 32-byte sectors): (value << 12) | block tag
-        unsigned long long* hb = a.part + (((size_t)(c % kRing) * ns) * kWPad + blockIdx.x) * 128 + q;
+        unsigned long long* hb = a.part + (((size_t)(c % kRing) * ns) * kWPad + (CL ? 0 : blockIdx.x)) * 128 + q;
         const unsigned long long tagc = tag_of((unsigned long long)(c / kRing));
+        // CL: the partial goes into the cluster solver's shared memory and counts itself on that solver's barrier
+        const uint32_t rdst = CL ? mapa_u32(hin_u32 + (uint32_t)((((c & 1) * kClWorkers + (crank - 1)) * ns) * 128 + q) * 8u, 0u) : 0u;
+        const uint32_t rbar = CL ? mapa_u32(smem_u32(&S.h_in[c & 1]), 0u) : 0u;
         for (int s = 0; s < ns; s++) {
           int s0, s1, s2, s3;
           tmem_ld4(tmem_g + tlane + (uint32_t)(4 * s), s0, s1, s2, s3);
           tmem_ld_wait();
           const long long gq = combine_limbs(s0, s1, s2, s3);
-          st_relaxed_u64(hb + (size_t)s * kWPad * 128, pack_word(gq, tagc));
+          if (CL) st_async_u64(rdst + (uint32_t)s * 1024u, (unsigned long long)gq, rbar);
+          else st_relaxed_u64(hb + (size_t)s * kWPad * 128, pack_word(gq, tagc));
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(&S.g_empty);
@@ -368,11 +423,18 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
           unsigned char* dl = DL + (size_t)(b & 1) * (N / 8) * 1024;
           // epilogue warp e receives the systems s = e, e+4, ...: lane l polls step words l, l+32, l+64, l+96 and lane 0 the
           // scale word as well (one L2 round trip when the step is already there), then writes the limbs of those markers
+          if (CL) mbar_wait(&S.de_in[b & 1], (uint32_t)(b >> 1) & 1u, dead, a.err);
           for (int s = quarter; s < ns; s += 4) {
             const unsigned long long* ws = wv + (size_t)s * kDewStride;
             unsigned long long v[4] = {0, 0, 0, 0}, vq = 0;
             uint32_t spin = 0;
-            while (!dead) {
+            if (CL) {  // the step arrived in this CTA's inbox (st.async from the cluster's solver)
+              const uint32_t* di = dein + (size_t)((b & 1) * ns + s) * kDeStride;
+#pragma unroll
+              for (int t = 0; t < 4; t++) v[t] = (unsigned long long)di[32 * t + lane] << 32;
+              vq = (unsigned long long)di[128] << 32;
+            }
+            while (!CL && !dead) {
               bool ok = true;
 #pragma unroll
               for (int t = 0; t < 4; t++) { v[t] = ld_relaxed_u64(ws + 32 * t + lane); ok = ok && ((uint32_t)v[t] == a.tag); }
@@ -391,6 +453,8 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
             }
           }
           if (t0) WSTAMP(b, 0);
+          // this inbox slot is next used by block b + 2, whose step cannot be sent before this worker's partial of b + 2
+          if (CL && q == 0 && b + 2 < nblocks) mbar_expect_tx(&S.de_in[b & 1], (uint32_t)(ns * 129 * 4));
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           mbar_arrive(&S.dl_full[b & 1]);
           named_bar(1, 128);  // the scales (dqs) of all systems visible to the four epilogue warps
@@ -475,7 +539,7 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
         mbar_arrive(&S.tile_full[buf]);
         if (tracing && lw == 0 && lane == 0) WSTAMP(t, 13);
       }
-    } else if (warp == kRedWarp) {
+    } else if (warp == kRedWarp && !CL) {
       // ------------------------------------------------------------------ second hop of the grid reduction
       // row (block c, system s, marker m) of the partials is summed by worker (s*128 + m) % W; plain loads and one store,
       // no atomics (143 x 128 L2 atomics per block cost ~7 us; this tree costs two L2 round trips)
@@ -526,6 +590,7 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
 #undef WSTAMP
+    if (CL) cluster_sync_all();  // nobody leaves while a peer may still store into its shared memory
     return;
   }
 
@@ -547,7 +612,7 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
   const bool full_inv = a.tinv != nullptr;  // T = (I + A L)^-1 of every block precomputed (block_inv.cu)
   const bool use_inv = !full_inv && pipe_use_inv(MODEL, ns);
   const int sring = a.sring;
-  const SLayout L = solver_layout(ns, kGibbs, use_inv, sring);
+  const SLayout L = solver_layout(ns, kGibbs, use_inv, sring, CL);
   float* Gs = reinterpret_cast<float*>(base + L.gs);
   float* Mt = reinterpret_cast<float*>(base + L.mt);
   MarkerSys* msys = reinterpret_cast<MarkerSys*>(base + L.ms);
@@ -557,6 +622,10 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
   float* dehist = reinterpret_cast<float*>(base + L.dh);
   float* rb = reinterpret_cast<float*>(base + L.rb);
   float* cs = reinterpret_cast<float*>(base + L.cs);
+  const long long* hin = reinterpret_cast<const long long*>(base + L.hi);
+  long long* hsum = reinterpret_cast<long long*>(base + L.hs);
+  // a worker's step inbox sits at the same shared-window offset in every CTA of this launch
+  const uint32_t dein_u32 = smem_u32(base) + (uint32_t)worker_layout(a.rows_per_cta, ns, a.nbuf, CL).di;
   const bool centred = a.sx != nullptr;
   const float inv_n = 1.0f / (float)a.g.n;
   if (tid < 64) cs[tid] = 0.0f;
@@ -606,6 +675,49 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
         if (tracing && warp == kInvWarp0 && lane == 0) { long long* tp_ = a.trace + ((size_t)blockIdx.x * nblocks + nb) * 32 + 3; tp_[0] = (long long)gtimer(); tp_[16] = clock64(); }
       }
     }
+    if (CL && warp >= kCommWarp0) {
+      // ------------------------------------------------------------------ clustered topology: gather h_b
+      // 1. the seven workers of this cluster have stored their partials into this CTA (st.async; the barrier counts the bytes);
+      // 2. their sum goes to the L2 ring as one self-validating word per (system, marker) -- the only L2 hop of a block --
+      //    and the sums of all clusters are polled back, all words of a thread in flight at once;
+      // 3. the grid total (an integer: the same on every solver) is handed to the solve warps through shared memory.
+      const int ct = tid - kCommWarp0 * 32;  // 0..127
+      const int C = a.nclusters;
+      for (int b = 0; b < nblocks; b++) {
+        const int slot = b & 1;
+        mbar_wait(&S.h_in[slot], (uint32_t)(b >> 1) & 1u, dead, a.err);
+        const unsigned long long tagb = tag_of((unsigned long long)(b / kRing));
+        unsigned long long* ring = a.cx + (size_t)(b % kRing) * C * ns * 128;
+        for (int pair = ct; pair < ns * 128; pair += 128) {
+          long long own = 0;
+#pragma unroll
+          for (int wr = 0; wr < kClWorkers; wr++) own += hin[(size_t)((slot * kClWorkers + wr) * ns) * 128 + pair];
+          st_relaxed_u64(ring + (size_t)cluster * ns * 128 + pair, pack_word(dead ? 0 : own, tagb));
+        }
+        // the slot is next used by block b + 2, whose partials cannot be sent before this block's step is published
+        if (ct == 0 && b + 2 < nblocks) mbar_expect_tx(&S.h_in[slot], (uint32_t)(kClWorkers * ns * 128 * 8));
+        for (int pair = ct; pair < ns * 128; pair += 128) {
+          unsigned long long wv[kMaxCl];
+          uint32_t spins = 0;
+          while (!dead) {
+            bool ok = true;
+#pragma unroll
+            for (int cl = 0; cl < kMaxCl; cl++) {
+              wv[cl] = cl < C ? ld_relaxed_u64(ring + (size_t)cl * ns * 128 + pair) : tagb;
+              ok = ok && word_ok(wv[cl], tagb);
+            }
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (++spins > kSpin || ((spins & 255u) == 255u && *reinterpret_cast<volatile int*>(a.err) != 0)) { dead = true; atomicCAS(a.err, 0, 3); }
+          }
+          long long tot = 0;
+#pragma unroll
+          for (int cl = 0; cl < kMaxCl; cl++) tot += dead ? 0 : word_val(wv[cl]);  // tag-only filler words carry value 0
+          hsum[(size_t)slot * ns * 128 + pair] = tot;
+        }
+        mbar_arrive(&S.h_ready[slot]);
+        if (tracing && ct == 0) { long long* tp_ = a.trace + ((size_t)blockIdx.x * nblocks + b) * 32 + 4; tp_[0] = (long long)gtimer(); tp_[16] = clock64(); }
+      }
+    }
     const bool wps4 = pipe_wps4(MODEL, ns, centred);
     if (wps4 && warp < 4) {
       // ------------------------------------------------------------------ one system on four solve warps
@@ -629,7 +741,10 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
         {
           long long qq = 0;
           uint32_t spins = 0;
-          if (a.world > 1) {
+          if (CL) {
+            mbar_wait(&S.h_ready[b & 1], (uint32_t)(b >> 1) & 1u, dead, a.err);
+            qq = dead ? 0 : hsum[(size_t)(b & 1) * 128 + jj];
+          } else if (a.world > 1) {
             const unsigned long long gen = a.gen0 + (unsigned long long)b;
             const unsigned long long tagx = tag_of(gen / kRing);
             const unsigned long long* gx = a.hx[a.rank] + ((size_t)(gen % kRing) * a.world) * 128 + jj;
@@ -751,11 +866,22 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
         unsigned long long* wv = a.dew + (size_t)b * kDewStride;
         const bool valid = jj < nvalid && !Sy.done;
         const int qv = valid ? __float2int_rn(de * dqinv) : 0;
-        st_relaxed_u64(wv + jj, ((unsigned long long)(uint32_t)qv << 32) | a.tag);
-        if (w == 3 && lane == 0) st_relaxed_u64(wv + 128, ((unsigned long long)__float_as_uint(dq) << 32) | a.tag);
+        if (CL) {  // the step goes straight into the inbox of each of this cluster's workers
+          const uint32_t off = dein_u32 + (uint32_t)((b & 1) * kDeStride + jj) * 4u, boff = smem_u32(&S.de_in[b & 1]);
+#pragma unroll
+          for (int wr = 1; wr <= kClWorkers; wr++) st_async_u32(mapa_u32(off, (uint32_t)wr), (uint32_t)qv, mapa_u32(boff, (uint32_t)wr));
+          if (w == 3 && lane == 0) {
+            const uint32_t soff = dein_u32 + (uint32_t)((b & 1) * kDeStride + 128) * 4u;
+#pragma unroll
+            for (int wr = 1; wr <= kClWorkers; wr++) st_async_u32(mapa_u32(soff, (uint32_t)wr), __float_as_uint(dq), mapa_u32(boff, (uint32_t)wr));
+          }
+        } else {
+          st_relaxed_u64(wv + jj, ((unsigned long long)(uint32_t)qv << 32) | a.tag);
+          if (w == 3 && lane == 0) st_relaxed_u64(wv + 128, ((unsigned long long)__float_as_uint(dq) << 32) | a.tag);
+        }
         if (w == 3) SSTAMPW(b, 11);
-        if (valid) {
-          const float deq = (float)qv * dq;  // the step actually applied to E (exactly representable)
+        if (valid && writer) {
+          const float deq = (float)qv * dq;  // the step actually applied to E (a 31-bit integer times a power of two, rounded once)
           const MarkerSys in = mk[jj];
           const float bnew = fmaf(deq, (MODEL == M_EMBA) ? 0.5f : 1.0f, in.b0);
           float vnew = in.vbj;
@@ -785,7 +911,11 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
           {
             long long qq[4] = {0, 0, 0, 0};
             uint32_t spins = 0;
-            if (a.world > 1) {
+            if (CL) {
+              mbar_wait(&S.h_ready[b & 1], (uint32_t)(b >> 1) & 1u, dead, a.err);
+#pragma unroll
+              for (int t = 0; t < 4; t++) qq[t] = dead ? 0 : hsum[(size_t)((b & 1) * ns + s) * 128 + 32 * t + lane];
+            } else if (a.world > 1) {
               const unsigned long long gen = a.gen0 + (unsigned long long)b;
               const unsigned long long tagx = tag_of(gen / kRing);
               const unsigned long long* gx = a.hx[a.rank] + ((size_t)(gen % kRing) * a.world * ns + s) * 128;
@@ -1003,15 +1133,27 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
             const int jj = 32 * t + lane;
             const bool valid = jj < nvalid && !Sy.done;
             qv[t] = valid ? __float2int_rn(de[t] * dqinv) : 0;
-            st_relaxed_u64(wv + jj, ((unsigned long long)(uint32_t)qv[t] << 32) | a.tag);
+            if (CL) {
+              const uint32_t off = dein_u32 + (uint32_t)(((b & 1) * ns + s) * kDeStride + jj) * 4u, boff = smem_u32(&S.de_in[b & 1]);
+#pragma unroll
+              for (int wr = 1; wr <= kClWorkers; wr++) st_async_u32(mapa_u32(off, (uint32_t)wr), (uint32_t)qv[t], mapa_u32(boff, (uint32_t)wr));
+            } else {
+              st_relaxed_u64(wv + jj, ((unsigned long long)(uint32_t)qv[t] << 32) | a.tag);
+            }
           }
-          if (lane == 0) st_relaxed_u64(wv + 128, ((unsigned long long)__float_as_uint(dq) << 32) | a.tag);
+          if (CL) {
+            if (lane == 0) {
+              const uint32_t soff = dein_u32 + (uint32_t)(((b & 1) * ns + s) * kDeStride + 128) * 4u, boff = smem_u32(&S.de_in[b & 1]);
+#pragma unroll
+              for (int wr = 1; wr <= kClWorkers; wr++) st_async_u32(mapa_u32(soff, (uint32_t)wr), __float_as_uint(dq), mapa_u32(boff, (uint32_t)wr));
+            }
+          } else if (lane == 0) st_relaxed_u64(wv + 128, ((unsigned long long)__float_as_uint(dq) << 32) | a.tag);
           if (s == 0) SSTAMP(b, 11);
 #pragma unroll
           for (int t = 0; t < 4; t++) {
             const int jj = 32 * t + lane;
-            if (jj < nvalid && !Sy.done) {
-              const float deq = (float)qv[t] * dq;  // the step actually applied to E (exactly representable)
+            if (jj < nvalid && !Sy.done && writer) {
+              const float deq = (float)qv[t] * dq;  // the step actually applied to E (a 31-bit integer times a power of two, rounded once)
               const MarkerSys in = mk[jj];
               float bnew, dnew = nd[t], vnew = nv[t];
               if (kLinear) {
@@ -1031,7 +1173,7 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.solve_done[slot]);
       }
-      if (centred && a.cshift && lane == 0)
+      if (centred && a.cshift && lane == 0 && writer)
         for (int s = warp; s < ns; s += kSolveWarps) a.cshift[s] = cs[2 * s];
     }
   } else if (warp < kPreWarp0) {
@@ -1191,47 +1333,96 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
   }
 #undef SSTAMP
 #undef SSTAMPW
+  if (CL) {
+    __syncthreads();
+    cluster_sync_all();  // nobody leaves while a peer may still store into its shared memory
+  }
 }
 
 template <int MODEL>
 cudaError_t launch_model(const PipeArgs& a, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(sweep_pipe_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   PipeArgs args = a;
+  if (a.cl) {
+    cudaError_t e = cudaFuncSetAttribute(sweep_pipe_kernel<MODEL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(a.nclusters * kClSize); cfg.blockDim = dim3(kT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kClSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, sweep_pipe_kernel<MODEL, true>, args);
+  }
+  cudaError_t e = cudaFuncSetAttribute(sweep_pipe_kernel<MODEL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
   void* params[] = {&args};
-  return cudaLaunchCooperativeKernel((void*)sweep_pipe_kernel<MODEL>, dim3(a.nworkers + 1), dim3(kT), params, smem, st);
+  return cudaLaunchCooperativeKernel((void*)sweep_pipe_kernel<MODEL, false>, dim3(a.nworkers + 1), dim3(kT), params, smem, st);
+}
+
+// co-resident clusters of kClSize CTAs with `smem` bytes of dynamic shared memory each (0 on error)
+template <int MODEL>
+int max_clusters_model(size_t smem) {
+  if (cudaFuncSetAttribute(sweep_pipe_kernel<MODEL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(kClSize * 32); cfg.blockDim = dim3(kT); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kClSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, sweep_pipe_kernel<MODEL, true>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
 }
 
 }  // namespace
 
 // Shared memory of one CTA (both roles use the same launch) and the largest tile ring that fits.
-size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring, int full_inv) {
-  const size_t w = worker_layout(rows_per_cta, nsys, nbuf).total;
-  const size_t s = solver_layout(nsys, model_is_gibbs(model), !full_inv && pipe_use_inv(model, nsys), sring).total;
+size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring, int full_inv, int cl) {
+  const size_t w = worker_layout(rows_per_cta, nsys, nbuf, cl != 0).total;
+  const size_t s = solver_layout(nsys, model_is_gibbs(model), !full_inv && pipe_use_inv(model, nsys), sring, cl != 0).total;
   return (w > s ? w : s) + 1024;
 }
 
-cudaError_t launch_sweep_pipe(const PipeArgs& a, cudaStream_t st) {
-  const size_t smem = sweep_pipe_smem(a.rows_per_cta, a.nsys, a.model, a.nbuf, a.sring, a.tinv != nullptr);
-  switch (rule_model(a.model)) {
-    case M_EMRR: return launch_model<M_EMRR>(a, smem, st);
-    case M_EMBA: return launch_model<M_EMBA>(a, smem, st);
-    case M_EMBB: return launch_model<M_EMBB>(a, smem, st);
-    case M_EMBC: return launch_model<M_EMBC>(a, smem, st);
-    case M_EMBL: return launch_model<M_EMBL>(a, smem, st);
-    case M_EMEN: return launch_model<M_EMEN>(a, smem, st);
-    case M_BRR: return launch_model<M_BRR>(a, smem, st);
-    case M_BA: return launch_model<M_BA>(a, smem, st);
-    case M_BB: return launch_model<M_BB>(a, smem, st);
-    case M_BC: return launch_model<M_BC>(a, smem, st);
-    case M_KMUP: return launch_model<M_KMUP>(a, smem, st);
-    case M_MRR: return launch_model<M_MRR>(a, smem, st);
-    case M_EMDE: return launch_model<M_EMDE>(a, smem, st);
-    case M_LASSO: return launch_model<M_LASSO>(a, smem, st);
-    case M_BL: return launch_model<M_BL>(a, smem, st);
-    case M_BDPI: return launch_model<M_BDPI>(a, smem, st);
-    default: break;
+#define BWGR_MODEL_SWITCH(CALL)                 \
+  switch (rule_model(model)) {                  \
+    case M_EMRR: return CALL(M_EMRR);           \
+    case M_EMBA: return CALL(M_EMBA);           \
+    case M_EMBB: return CALL(M_EMBB);           \
+    case M_EMBC: return CALL(M_EMBC);           \
+    case M_EMBL: return CALL(M_EMBL);           \
+    case M_EMEN: return CALL(M_EMEN);           \
+    case M_BRR: return CALL(M_BRR);             \
+    case M_BA: return CALL(M_BA);               \
+    case M_BB: return CALL(M_BB);               \
+    case M_BC: return CALL(M_BC);               \
+    case M_KMUP: return CALL(M_KMUP);           \
+    case M_MRR: return CALL(M_MRR);             \
+    case M_EMDE: return CALL(M_EMDE);           \
+    case M_LASSO: return CALL(M_LASSO);         \
+    case M_BL: return CALL(M_BL);               \
+    case M_BDPI: return CALL(M_BDPI);           \
+    default: break;                             \
   }
+
+// The clustered topology needs the solver's warps 4-7 free (comm warps): at most four systems and no in-kernel 32 x 32 inverses.
+bool sweep_pipe_cluster_ok(int model, int nsys, int full_inv) {
+  return nsys <= 4 && !(!full_inv && pipe_use_inv(model, nsys));
+}
+int sweep_pipe_max_clusters(int model, size_t smem) {
+#define BWGR_CALL(M) max_clusters_model<M>(smem)
+  BWGR_MODEL_SWITCH(BWGR_CALL)
+#undef BWGR_CALL
+  return 0;
+}
+
+cudaError_t launch_sweep_pipe(const PipeArgs& a, cudaStream_t st) {
+  const size_t smem = sweep_pipe_smem(a.rows_per_cta, a.nsys, a.model, a.nbuf, a.sring, a.tinv != nullptr, a.cl);
+  const int model = a.model;
+#define BWGR_CALL(M) launch_model<M>(a, smem, st)
+  BWGR_MODEL_SWITCH(BWGR_CALL)
+#undef BWGR_CALL
   return cudaErrorInvalidValue;
 }
 
