@@ -9,16 +9,22 @@ at n=50k,p=50k; genotype GB/s vs HBM peak" is quoted on.  A step = one full swee
 Gram blocks + blocked sweep + hyper-parameter epilogue).
   value      marker-updates/s with genotypes, y and all state resident in HBM (CUDA events on the
              library's stream, max over ranks).
-  e2e        the same metric through the public call a user makes (bwgr_em_fit via bwgr_b200.emRR):
-             host int8 genotypes + y in pinned memory -> H2D -> pack/statistics -> the reference's
-             fixed 200 sweeps -> GEBVs -> D2H, all inside the timed region.
+  e2e        the same metric through the public call a user makes, bwgr_b200.emRR(y, gen) on R's own input: the n x p
+             float64 column-major matrix on the host (what _bWGR_emRR receives).  One warm-up fit, then >= 5 timed fits
+             (median; every fit listed): exact narrowing to int8 by host threads into pinned staging overlapped with the
+             H2D copy, column statistics, the reference's fixed 200 sweeps, GEBVs, D2H -- all inside the timed region.
+             The same call on a host int8 matrix is reported beside it (int8_host_input).
   roofline   algorithmic bytes = n*p*1 B per sweep / mean duration of the dominant kernel
              (measured live with CUDA events around each kernel class), against MEASURED_PEAKS.json.
-  cpu_baseline  the oracle (C++ restatement of the reference's single-threaded float32 RcppEigen path;
-             the reference itself needs R/Rcpp and cannot be built) on a bounded sample of the same
+  cpu_baseline  the oracle (C++ restatement of the reference's single-threaded float32 RcppEigen path, pinned against the
+             reference's own sources compiled with stand-in headers: tests/test_ref_pin.py) on a bounded sample of the same
              workload: full n, the first m markers, a few sweeps.
-N>1 (torchrun, one rank per GPU): independent replicas of the same sweep, one per GPU, no collective
-(the row-sharded single fit of config 5 is not built yet); value = total marker-updates/s.
+N>1 (torchrun, one rank per GPU): ONE fit whose individuals are sharded by rows over the ranks (n = N x 50,000; BASELINE config 5
+pattern): the per-block exchange of the reduced partials runs inside the sweep kernel over NVLink peer memory, the Gram band and
+five scalars are all-reduced with NCCL once per sweep.  value = N x p marker updates per sweep / sweep time (one marker update =
+one marker visited on one 50,000-row shard; scaling "weak").  `row_sharded_parity` = that sharded fit against the single-GPU fit
+of the same global data on rank 0 (max|db| / max|b|, expected 0: every cross-GPU sum is an integer sum).  The communication-free
+mode (N independent fits, one per GPU) is kept as the extra key `replicas`.
 """
 import argparse
 import json
@@ -46,7 +52,7 @@ def parse():
     ap.add_argument("--n", type=int, default=50000)
     ap.add_argument("--p", type=int, default=50000)
     ap.add_argument("--model", default="emRR")
-    ap.add_argument("--e2e-fits", type=int, default=3)
+    ap.add_argument("--e2e-fits", type=int, default=5)
     ap.add_argument("--e2e-sweeps", type=int, default=200)
     ap.add_argument("--cpu-markers", type=int, default=2048)
     ap.add_argument("--cpu-sweeps", type=int, default=10)
@@ -214,6 +220,69 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    return 0
+
+
+def host_f64_matrix(Xt_cpu, n, p):
+    """R's view of the genotypes: an n x p column-major float64 matrix (what _bWGR_emRR receives, src/RcppExports.cpp:110-121)."""
+    Xd = np.empty((n, p), dtype=np.float64, order="F")
+    X8 = Xt_cpu.numpy()  # (p, n) int8, row-major = column-major n x p
+    step = 2048
+    for j0 in range(0, p, step):
+        Xd[:, j0:j0 + step] = X8[j0:j0 + step].T
+    return Xd
+
+
+def timed_fits(fn, nfits):
+    fn()  # one warm-up fit: allocator, pinned staging, first-touch of the host pages
+    out = []
+    for _ in range(nfits):
+        t = time.perf_counter()
+        fn()
+        out.append(time.perf_counter() - t)
+    return out
+
+
+def row_sharded_parity(bw, dist, dev, local, rank, world, stream):
+    """The sharded fit against the single-GPU fit of the same global data (rank 0 gathers the shards): max|db| / max|b|.
+    Small enough for one GPU (world x 8,192 rows x 4,096 markers), the same kernels and exchange as the timed fit."""
+    import torch
+    n_s, p_s = 8192, 4096
+    Xs, ys = synth_gpu(n_s, p_s, SEED + 1000 + rank, dev)
+    torch.cuda.synchronize()
+    g = bw.Genotypes(device=local, path=bw.PATH_BLOCKED)
+    g.enable_row_sharding()
+    g.load(Xs)
+    fit = bw.emRR(ys, g, it=8)
+    g.close()
+    Xall = [torch.empty_like(Xs) for _ in range(world)]
+    dist.all_gather(Xall, Xs)
+    yt = torch.from_numpy(ys).to(dev)
+    yall = [torch.empty_like(yt) for _ in range(world)]
+    dist.all_gather(yall, yt)
+    res = None
+    if rank == 0:
+        Xg = torch.cat(Xall, dim=1).contiguous()  # (p, world * n_s): the global column-major matrix
+        yg = torch.cat(yall).cpu().numpy()
+        torch.cuda.synchronize()
+        g1 = bw.Genotypes(device=local, path=bw.PATH_BLOCKED)
+        g1.load(Xg)
+        one = bw.emRR(yg, g1, it=8)
+        g1.close()
+        res = {"max_abs_db_over_max_abs_b": float(np.abs(fit["b"] - one["b"]).max() / np.abs(one["b"]).max()),
+               "h2_sharded": float(fit["h2"]), "h2_single_gpu": float(one["h2"]),
+               "shape": "n=%d (=%d x %d) x p=%d, emRR, 8 sweeps" % (n_s * world, world, n_s, p_s)}
+    dist.barrier()
+    return res
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
@@ -233,151 +302,183 @@ def main():
     n, p = args.n, args.p
     Xt, y = synth_gpu(n, p, SEED + rank, dev)
     torch.cuda.synchronize()
-
-    g = bw.Genotypes(device=local, path=bw.PATH_BLOCKED)
     stream = torch.cuda.Stream(device=dev)  # events and the library share this stream
-    g.set_stream(stream.cuda_stream)
-    g.load(Xt)  # device-resident int8 (p x n row-major == n x p column-major)
-    st = bw.EmStepper(args.model, y, g)
-    sampler = ClockSampler(local)
-    sampler.start()  # started before the warm-up: the timed region can be shorter than nvidia-smi's first sample
-    st.sweeps(args.warmup)
-    torch.cuda.synchronize()
+    hbm_peak, peak_src = peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    barrier()
-    n_before = len(sampler.rows)
-    l0 = g.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    st.sweeps(args.steps)
-    e1.record(stream)
-    barrier()
-    launches = g.launch_count() - l0
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    def timed_sweeps(g, st):
+        """W warm-up sweeps, then exactly K sweeps between a barrier + synchronize on both sides; max over ranks."""
+        st.sweeps(args.warmup)
+        barrier()
+        l0 = g.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        st.sweeps(args.steps)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        g.profile(True)  # per-kernel durations for the roofline (separate pass: event pairs around every kernel)
+        st.sweeps(args.steps)
+        prof = g.profile_read()
+        g.profile(False)
+        return ms, g.launch_count() - l0 - 0, prof
 
-    # per-kernel durations for the roofline (separate pass: event pairs around every kernel)
-    g.profile(True)
-    st.sweeps(args.steps)
-    prof = g.profile_read()
-    g.profile(False)
+    # ---- independent fits: one emRR sweep stream per GPU (N = 1: THE workload; N > 1: the communication-free mode, extra key)
+    g = bw.Genotypes(device=local, path=bw.PATH_BLOCKED)
+    g.set_stream(stream.cuda_stream)
+    g.load(Xt)  # device-resident int8 (p x n row-major == n x p column-major)
+    st = bw.EmStepper(args.model, y, g)
+    sampler = ClockSampler(local)
+    sampler.start()  # started before the warm-up: the timed region can be shorter than nvidia-smi's first sample
+    ms_rep, launches_rep, prof_rep = timed_sweeps(g, st)
+    launches_rep //= 2  # the per-kernel timing pass repeats the K sweeps
+    rep_value = world * p * args.steps / (ms_rep * 1e-3)
+
+    # ---- N > 1: ONE fit, individuals sharded by rows over the ranks (BASELINE config 5 pattern) -- the headline of --gpus N
+    ms, launches, prof, rs_parity, rs_fit = ms_rep, launches_rep, prof_rep, None, None
+    if world > 1:
+        g3 = bw.Genotypes(device=local, path=bw.PATH_BLOCKED)
+        g3.enable_row_sharding()
+        g3.set_stream(stream.cuda_stream)
+        g3.load(Xt)
+        st3 = bw.EmStepper(args.model, y, g3)
+        ms, launches, prof = timed_sweeps(g3, st3)
+        launches //= 2
     # nvidia-smi needs ~1 s to deliver its first sample and the timed region is ~50 ms: keep the SAME sweep loop running until
     # the sampler has seen the GPU under this load for a while, then read the clocks / throttle reasons
     t_clk = time.perf_counter()
+    stc = st3 if world > 1 else st
     while time.perf_counter() - t_clk < 1.5 or (len(sampler.rows) < 10 and time.perf_counter() - t_clk < 6.0):
-        st.sweeps(20)
+        stc.sweeps(20)
         torch.cuda.synchronize()
     clocks = sampler.stop()  # covers warm-up, the timed region, the per-kernel timing pass and the clock pass (all the same sweeps)
     fit = st.end()
     assert np.isfinite(fit["b"]).all() and np.isfinite(fit["h2"])
-    hbm_peak, peak_src = peaks()
+    g.close()
+    if world > 1:
+        rs_fit = st3.end()
+        g3.close()
+        assert np.isfinite(rs_fit["b"]).all()
+        try:
+            rs_parity = row_sharded_parity(bw, dist, dev, local, rank, world, stream)
+        except Exception as ex:  # noqa: BLE001
+            rs_parity = {"error": str(ex)[:200]}
+
     sweep_ms = prof["sweep"]["ms"] / max(1, prof["sweep"]["launches"])
     gram_ms = prof["gram"]["ms"] / max(1, prof["gram"]["launches"])
     epi_ms = prof["epilogue"]["ms"] / max(1, prof["epilogue"]["launches"])
     inv_ms = prof["block_inverse"]["ms"] / max(1, prof["block_inverse"]["launches"])
     dom = "sweep_pipe_kernel" if sweep_ms >= gram_ms else "gram_tc_kernel"
     dom_ms = max(sweep_ms, gram_ms)
-    achieved = n * p / (dom_ms * 1e-3) / 1e9
+    achieved = n * p / (dom_ms * 1e-3) / 1e9  # per GPU: every rank streams its own n x p bytes per launch
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": args.traffic if args.traffic is not None else ncu_traffic(dom, n, p), "kernel": dom, "peak_source": peak_src, "algorithmic_bytes_per_launch": n * p,
                 "kernel_ms": {"sweep_pipe_kernel": sweep_ms, "gram_tc_kernel": gram_ms, "block_inverse_kernel": inv_ms, "epilogue_kernel": epi_ms},
                 "whole_sweep_frac": (n * p / (ms / args.steps * 1e-3) / 1e9) / hbm_peak}
+    # one marker update = one marker visited on one 50k-row shard: N = 1 -> p per sweep; row-sharded -> N * p per sweep of the ONE fit
     value = world * p * args.steps / (ms * 1e-3)
 
-    # ---- end to end through the public API with host buffers
+    # ---- end to end through the public API with HOST buffers
     e2e = None
     if not args.no_e2e:
-        Xh = torch.empty((p, n), dtype=torch.int8, pin_memory=True)
-        Xh.copy_(Xt)
+        Xh = Xt.cpu()
         del Xt
         torch.cuda.empty_cache()
         torch.cuda.synchronize()
-        barrier()
-        t0 = time.perf_counter()
-        fit_s = []
-        for _ in range(args.e2e_fits):
-            tf = time.perf_counter()
-            g2 = bw.Genotypes(device=local, path=bw.PATH_BLOCKED)
-            g2.load(Xh)
-            out = bw.emRR(y, g2, it=args.e2e_sweeps)
-            g2.close()
-            torch.cuda.synchronize()
-            fit_s.append(time.perf_counter() - tf)
-        dt = float(np.median(fit_s)) * args.e2e_fits  # median fit (every fit is listed in seconds_each_fit)
-        if world > 1:
+        if world == 1:
+            need = 8 * n * p
+            use_f64 = mem_available_bytes() > need + (12 << 30)
+            fits8 = None
+            if use_f64:
+                Xd = host_f64_matrix(Xh, n, p)
+
+                def one_fit():
+                    out = bw.emRR(y, Xd, it=args.e2e_sweeps, path=bw.PATH_BLOCKED)  # numpy double matrix in, R-style list out
+                    assert np.isfinite(out["b"]).all()
+                fit_s = timed_fits(one_fit, max(5, args.e2e_fits))
+                del Xd
+            Xp = Xh.pin_memory()
+
+            def one_fit8():
+                g2 = bw.Genotypes(device=local, path=bw.PATH_BLOCKED)
+                g2.load(Xp)
+                out = bw.emRR(y, g2, it=args.e2e_sweeps)
+                g2.close()
+                assert np.isfinite(out["b"]).all()
+            fits8 = timed_fits(one_fit8, max(5, args.e2e_fits))
+            if not use_f64:
+                fit_s = fits8
+            dt = float(np.median(fit_s))
+            e2e = {"value": args.e2e_sweeps * p / dt, "unit": "marker-updates/s",
+                   "h2d_bytes_per_step": int(n * p + 8 * n), "d2h_bytes_per_step": int(4 * (p + n) + 64),
+                   "host_input_bytes_per_step": int((8 if use_f64 else 1) * n * p + 8 * n),
+                   "step": ("one emRR(y, gen) call on R's double matrix (n x p float64 on the host): exact narrowing to int8 by host threads into pinned "
+                            "staging overlapped with the H2D copy, column statistics, %d sweeps, GEBVs, D2H" % args.e2e_sweeps) if use_f64 else
+                           ("one emRR(y, gen) call on a host int8 matrix (not enough host memory for the float64 copy): H2D, column statistics, %d sweeps, GEBVs, D2H" % args.e2e_sweeps),
+                   "seconds_per_fit": dt, "seconds_each_fit": fit_s, "spread": (max(fit_s) - min(fit_s)) / dt,
+                   "int8_host_input": {"value": args.e2e_sweeps * p / float(np.median(fits8)), "seconds_each_fit": fits8}}
+        else:
+            Xp = Xh.pin_memory()
+
+            def one_fit_sharded():
+                g2 = bw.Genotypes(device=local, path=bw.PATH_BLOCKED)
+                g2.enable_row_sharding()
+                g2.load(Xp)  # this rank's rows, host int8
+                out = bw.emRR(y, g2, it=args.e2e_sweeps)
+                g2.close()
+                assert np.isfinite(out["b"]).all()
+            fit_s = timed_fits(one_fit_sharded, max(3, args.e2e_fits))
+            dt = float(np.median(fit_s))
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        assert np.isfinite(out["b"]).all()
-        e2e = {"value": world * args.e2e_fits * args.e2e_sweeps * p / dt, "unit": "marker-updates/s",
-               "h2d_bytes_per_step": int(n * p + 8 * n), "d2h_bytes_per_step": int(4 * (p + n) + 64),
-               "step": "one emRR(y, gen) call: %d sweeps incl. H2D of int8 genotypes, packing, column statistics, GEBVs, D2H" % args.e2e_sweeps,
-               "seconds_per_fit": dt / args.e2e_fits, "seconds_each_fit": fit_s}
+            e2e = {"value": world * args.e2e_sweeps * p / dt, "unit": "marker-updates/s",
+                   "h2d_bytes_per_step": int(world * (n * p + 8 * n)), "d2h_bytes_per_step": int(world * 4 * (p + n) + 64),
+                   "step": "one row-sharded emRR(y, gen) call over %d GPUs: every rank loads ITS rows from a host int8 matrix (H2D), column statistics "
+                           "(all-reduced), %d sweeps, GEBVs, D2H" % (world, args.e2e_sweeps),
+                   "seconds_per_fit": dt, "seconds_each_fit": fit_s}
 
     cpu = None
     if rank == 0 and not args.no_cpu:
         m = args.cpu_markers
-        if args.no_e2e:
-            Xs = Xt[:m].cpu().numpy().T
-        else:
-            Xs = Xh[:m].numpy().T
+        Xs = (Xt[:m].cpu() if args.no_e2e else Xh[:m]).numpy().T
         v, secs = cpu_sample(args, Xs, y, sweeps=args.cpu_sweeps_main)
         cpu = {"value": v, "unit": "marker-updates/s", "cores": 1, "kind": "port",
-               "sample": "oracle %s (g++ -O2, float32, 1 thread like the reference), full n=%d x first %d markers, %d sweeps = %.1f s; %s, %d host cores" % (
-                   args.model, n, m, args.cpu_sweeps_main, secs, cpu_model_name(), os.cpu_count())}
-
-    # ---- N > 1 also measures the OTHER multi-GPU mode of the path: one fit, individuals sharded by rows over the ranks
-    # (BASELINE config 5 pattern; per-block exchange inside the sweep kernel over NVLink peer memory + NCCL per sweep)
-    row_sharded = None
-    if world > 1 and not args.no_e2e:
-        try:
-            Xd = Xh.to(dev)
-            g3 = bw.Genotypes(device=local, path=bw.PATH_BLOCKED)
-            g3.enable_row_sharding()
-            g3.set_stream(stream.cuda_stream)
-            g3.load(Xd)
-            st3 = bw.EmStepper(args.model, y, g3)
-            st3.sweeps(args.warmup)
-            barrier()
-            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            r0.record(stream)
-            st3.sweeps(args.steps)
-            r1.record(stream)
-            barrier()
-            t = torch.tensor([r0.elapsed_time(r1)], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            rs_ms = float(t.item()) / args.steps
-            fit3 = st3.end()
-            g3.close()
-            row_sharded = {"workload": "ONE emRR fit, n=%d individuals sharded by rows over %d GPUs x p=%d" % (n * world, world, p),
-                           "ms_per_sweep": rs_ms, "marker_updates_per_s": p / (rs_ms * 1e-3),
-                           "genotype_GB_per_s_aggregate": n * world * p / (rs_ms * 1e-3) / 1e9,
-                           "frac_of_aggregate_hbm_peak": n * world * p / (rs_ms * 1e-3) / 1e9 / (hbm_peak * world),
-                           "collectives": "per 128-marker block: peer stores of the reduced partial X_B'E into every rank's ring inside the sweep kernel (NVLink); per sweep: ncclAllReduce of the Gram band and of 5 scalars",
-                           "h2": float(fit3["h2"])}
-        except Exception as ex:  # noqa: BLE001
-            row_sharded = {"error": str(ex)[:200]}
+               "sample": "oracle %s (g++ -O2, float32, 1 thread like the reference; pinned against the reference's own sources, tests/test_ref_pin.py), "
+                         "full n=%d x first %d markers, %d sweeps = %.1f s; %s, %d host cores" % (
+                             args.model, n, m, args.cpu_sweeps_main, secs, cpu_model_name(), os.cpu_count())}
 
     if rank == 0:
+        workload = "%s Gauss-Seidel sweep, synthetic n=%d x p=%d int8 genotypes, k=1" % (args.model, n, p)
+        if world == 1:
+            par = "1 GPU"
+        else:
+            par = ("ONE fit of n=%d individuals sharded by rows over %d GPUs (%d rows each); per 128-marker block the reduced partials cross NVLink as "
+                   "peer stores inside the sweep kernel, per sweep ncclAllReduce of the Gram band and 5 scalars; value counts marker updates per "
+                   "%d-row shard (N x p per sweep)" % (n * world, world, n, n))
         line = {"metric": "marker-updates/sec (emRR Gauss-Seidel sweep, n=50k x p=50k int8)", "value": value,
                 "unit": "marker-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "%s Gauss-Seidel sweep, synthetic n=%d x p=%d int8 genotypes, k=1" % (args.model, n, p),
+                "config": {"workload": workload,
                            "step": "one full sweep = p marker updates (Gram band + pipelined blocked sweep + epilogue)",
-                           "l2": "genotypes are %.1f GB per sweep, far larger than the 126 MB L2: no flush needed" % (n * p / 1e9),
-                           "parallelism": "1 GPU" if world == 1 else "%d independent replicas (one fit per GPU, no collective)" % world,
-                           "seed": SEED},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "row_sharded": row_sharded, "gpu_launches": int(launches), "clocks": clocks,
+                           "l2": "genotypes are %.1f GB per sweep per GPU, far larger than the 126 MB L2: no flush needed" % (n * p / 1e9),
+                           "parallelism": par, "seed": SEED},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "sweep_ms": ms / args.steps}
+        if world > 1:
+            line["row_sharded_parity"] = rs_parity
+            line["row_sharded"] = {"ms_per_sweep": ms / args.steps, "genotype_GB_per_s_aggregate": n * world * p / (ms / args.steps * 1e-3) / 1e9,
+                                   "frac_of_aggregate_hbm_peak": n * world * p / (ms / args.steps * 1e-3) / 1e9 / (hbm_peak * world), "h2": float(rs_fit["h2"])}
+            line["replicas"] = {"what": "%d independent fits, one per GPU, no collective" % world, "value": rep_value, "ms_per_sweep": ms_rep / args.steps}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -207,20 +207,27 @@ struct Sync {
   uint64_t raw_ready[3], in_ready[3], solve_done[3], corr_ready[32], de_ready[32][4];
   // clustered topology: step inbox of a worker, partial inbox of a solver, gathered sums ready for the solve warps
   uint64_t de_in[2], h_in[2], h_ready[2];
+  // fast worker: U accumulator of atom `at` complete / drained
+  uint64_t u_done_at[4], u_free_at[4];
   uint32_t tmem_base;
 };
 
-struct WLayout { int NA, N, nbuf; size_t xs, el, dl, es, dq, di, total; };
-__host__ __device__ inline WLayout worker_layout(int R, int ns, int nbuf, bool cl = false) {
+constexpr int kEpiWarps = 12;          // fast worker: epilogue warps (three groups of four TMEM lane quarters)
+struct WLayout { int NA, N, nbuf; size_t xs, el, dl, es, dq, di, lb, red, total; };
+// fast = the clustered worker for ns <= 2 whose G pass runs on mma.sync inside the epilogue warps (no E-limb operand region)
+__host__ __device__ inline WLayout worker_layout(int R, int ns, int nbuf, bool cl = false, bool fast = false) {
   WLayout L;
   L.NA = (R + 127) / 128; L.N = ((4 * ns + 15) / 16) * 16; L.nbuf = nbuf;
   size_t o = 0;
   L.xs = o; o += (size_t)nbuf * L.NA * kAtomBytes;
-  L.el = o; o += (size_t)L.NA * (L.N / 8) * 1024;
+  L.el = o; o += fast ? 0 : (size_t)L.NA * (L.N / 8) * 1024;
   L.dl = o; o += (size_t)2 * (L.N / 8) * 1024;
   L.es = o; o += (size_t)ns * L.NA * 128 * 4;
   L.dq = o; o += (size_t)2 * 32 * 4;
   L.di = o; o += cl ? (size_t)2 * ns * kDeStride * 4 : 0;  // step inbox, written by the cluster's solver (st.async)
+  o = (o + 15) & ~(size_t)15;
+  L.lb = o; o += fast ? (size_t)kEpiWarps * 256 : 0;             // per-warp limb exchange [8 limb columns][32 rows]
+  L.red = o; o += fast ? (size_t)kEpiWarps * ns * 128 * 8 : 0;   // per-warp partial sums of h [warp][system][marker]
   L.total = o;
   return L;
 }
@@ -266,7 +273,8 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
 
   if (tid < ns) sc[tid] = a.sc[tid];
   if (tid == 0) {
-    for (int i = 0; i < 8; i++) { mbar_init(&S.tile_full[i], 128); mbar_init(&S.tile_empty[i], 1); }
+    for (int i = 0; i < 8; i++) { mbar_init(&S.tile_full[i], (CL && a.fastw) ? 32 : 128); mbar_init(&S.tile_empty[i], 1); }
+    for (int i = 0; i < 4; i++) { mbar_init(&S.u_done_at[i], 1); mbar_init(&S.u_free_at[i], 128); }
     mbar_init(&S.dl_full[0], 128); mbar_init(&S.dl_full[1], 128);
     mbar_init(&S.u_done, 1); mbar_init(&S.el_full, 128); mbar_init(&S.g_done, 1); mbar_init(&S.g_empty, 128);
     const int nsw = ns < kSolveWarps ? ns : kSolveWarps;
@@ -287,6 +295,261 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
   if (CL) cluster_sync_all();  // every CTA's barriers exist before the first remote store
 
   if (!is_solver) {
+    if (CL && a.fastw) {
+      // =====================================================================================================
+      // fast worker (clustered topology, ns <= 2).  Per block b:  U(b) on tcgen05 atom by atom (the MN-major descriptor
+      // transposes the tile in hardware); twelve epilogue warps drain the atoms as they complete, update E and -- with the
+      // new limbs still in registers -- multiply their own 32 rows into the partial of block c = b + 1 + D with
+      // mma.sync.m16n8k32 (K = the warp's 32 rows): no second tcgen05 pass, no hand-over between the two passes.
+      // =====================================================================================================
+      const WLayout L = worker_layout(a.rows_per_cta, ns, a.nbuf, true, true);
+      const int R = a.rows_per_cta, NA = L.NA, N = 16, RS = NA * 128, nbuf = L.nbuf;
+      const int row0 = widx * R;
+      const uint32_t* dein = reinterpret_cast<const uint32_t*>(base + L.di);
+      const uint32_t hin_u32 = smem_u32(base) + (uint32_t)solver_layout(ns, model_is_gibbs(MODEL), false, a.sring, true).hi;
+      unsigned char* Xs = base + L.xs;
+      unsigned char* DL = base + L.dl;
+      float* Es = reinterpret_cast<float*>(base + L.es);
+      unsigned char* lbuf = base + L.lb;
+      long long* red = reinterpret_cast<long long*>(base + L.red);
+      {
+        uint4* z = reinterpret_cast<uint4*>(base);
+        const int nz = (int)(L.es >> 4);
+        for (int i = tid; i < nz; i += kT) z[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < kEpiWarps * 256 / 16; i += kT) reinterpret_cast<uint4*>(lbuf)[i] = make_uint4(0, 0, 0, 0);
+      }
+      for (int s = 0; s < ns; s++)
+        for (int i = tid; i < RS; i += kT) {
+          const int r = row0 + i;
+          Es[s * RS + i] = (i < R && r < a.g.ld) ? a.e[(size_t)s * a.g.ld + r] : 0.0f;
+        }
+      const uint32_t tmem_cols = 64;  // NA (<= 4) accumulators of N = 16 columns
+      if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_base = S.tmem_base;
+      const bool tracing = a.trace != nullptr;
+      bool bad = false;
+#define WSTAMP(blk, k) do { if (tracing) { long long* tp_ = a.trace + ((size_t)blockIdx.x * nblocks + (blk)) * 32 + (k); tp_[0] = (long long)gtimer(); tp_[16] = clock64(); } } while (0)
+      const int npro = (D < nblocks - 1 ? D : nblocks - 1);
+      if (warp == 0) {
+        // ------------------------------------------------------------------ tcgen05 issuer: U(b), one commit per atom
+        const uint32_t idesc_u = idesc_i8(N, 1);
+        for (int b = 0; b < nblocks; b++) {
+          const unsigned char* Xt = Xs + (size_t)(b % nbuf) * NA * kAtomBytes;
+          mbar_wait(&S.tile_full[b % nbuf], (uint32_t)(b / nbuf) & 1u, dead, a.err);  // long complete (G(b) read this tile two blocks ago)
+          mbar_wait(&S.dl_full[b & 1], (uint32_t)(b >> 1) & 1u, dead, a.err);
+          const uint64_t bd = desc_k_sw128(smem_u32(DL + (size_t)(b & 1) * (N / 8) * 1024));
+          for (int at = 0; at < NA; at++) {
+            if (b > 0) mbar_wait(&S.u_free_at[at], (uint32_t)(b - 1) & 1u, dead, a.err);  // the epilogue has drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+              const uint64_t ad = desc_mn_sw128(smem_u32(Xt + (size_t)at * kAtomBytes));
+#pragma unroll
+              for (int k4 = 0; k4 < 4; k4++)
+                umma_i8(tmem_base + (uint32_t)(at * N), ad + (uint64_t)(k4 * (4096 >> 4)), bd + (uint64_t)(2 * k4), idesc_u, k4 != 0);
+              umma_commit(&S.u_done_at[at]);
+              if (at == NA - 1) umma_commit(&S.tile_empty[b % nbuf]);
+            }
+            __syncwarp();
+          }
+          if (tracing && lane == 0) WSTAMP(b, 2);
+        }
+      } else if (warp == 5 || warp == 6) {
+        // ------------------------------------------------------------------ X tile gather: one warp per tile in flight
+        const int grp = warp - 5;
+        const int nchunk = R >> 4;
+        const bool act = lane < nchunk && row0 + 16 * lane < a.g.ld;
+        const uint32_t choff = (uint32_t)((lane >> 3) * kAtomBytes + ((lane & 7) << 4));
+        const int8_t* xrow = a.g.x8 + row0 + 16 * lane;
+        const uint64_t pol = policy_evict_first();
+        for (int t = grp; t < nblocks; t += 2) {
+          const int buf = t % nbuf;
+          int myid[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) { const int pos = t * 128 + 32 * k + lane; myid[k] = pos < p ? a.perm[pos] : -1; }
+          if (t >= nbuf) mbar_wait(&S.tile_empty[buf], (uint32_t)(t / nbuf - 1) & 1u, dead, a.err);
+          const uint32_t dst = smem_u32(Xs + (size_t)buf * NA * kAtomBytes);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+#pragma unroll 8
+            for (int i = 0; i < 32; i++) {
+              const int m = 32 * k + i;
+              const int j = __shfl_sync(0xffffffffu, myid[k], i);
+              if (lane < nchunk) {
+                const uint32_t dm = dst + (uint32_t)(m * 128) + (choff ^ (uint32_t)((m & 7) << 4));
+                const bool ok = act && j >= 0;
+                cp_async16_stream(dm, ok ? xrow + (int64_t)j * a.g.ld : a.g.x8, ok ? 16u : 0u, pol);
+              }
+            }
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(&S.tile_full[buf]);
+        }
+      } else if (warp != 7) {
+        // ------------------------------------------------------------------ epilogue warps: three groups x four TMEM lane quarters
+        const int ew = warp <= 4 ? warp - 1 : warp - 4;       // 0..11
+        const int grp = ew >> 2;                              // atoms at with at % 3 == grp
+        const int quarter = warp & 3;
+        const int q = quarter * 32 + lane;                    // row inside an atom = TMEM lane
+        const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
+        const bool t0 = tracing && warp == 1 && lane == 0;
+        const int g8 = lane >> 2, t4 = lane & 3;
+        unsigned char* lb = lbuf + ew * 256;
+        long long* rw = red + (size_t)ew * ns * 128;
+        // byte offsets of this lane's A fragments inside one atom of a tile (rows 32*quarter + 4*t4 .., markers g8 / g8 + 8)
+        const int kb0 = quarter * 32 + 4 * t4;
+        const uint32_t offA = (uint32_t)(g8 * 128 + ((((kb0 >> 4) ^ g8) & 7) << 4) + (kb0 & 15));
+        const uint32_t offB = (uint32_t)(g8 * 128 + (((((kb0 + 16) >> 4) ^ g8) & 7) << 4) + (kb0 & 15));
+        int acc[8][4];
+        auto g_unit = [&](int c, int at, const int (&l)[8]) {
+          __syncwarp();
+#pragma unroll
+          for (int n = 0; n < 8; n++) if (n < 4 * ns) lb[n * 32 + lane] = (unsigned char)l[n];
+          __syncwarp();
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(lb + g8 * 32 + 4 * t4);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(lb + g8 * 32 + 16 + 4 * t4);
+          const unsigned char* Xa = Xs + ((size_t)(c % nbuf) * NA + at) * kAtomBytes;
+#pragma unroll
+          for (int mt = 0; mt < 8; mt++) {
+            const uint32_t a0 = *reinterpret_cast<const uint32_t*>(Xa + mt * 2048 + offA);
+            const uint32_t a1 = *reinterpret_cast<const uint32_t*>(Xa + mt * 2048 + 1024 + offA);
+            const uint32_t a2 = *reinterpret_cast<const uint32_t*>(Xa + mt * 2048 + offB);
+            const uint32_t a3 = *reinterpret_cast<const uint32_t*>(Xa + mt * 2048 + 1024 + offB);
+            asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                         : "+r"(acc[mt][0]), "+r"(acc[mt][1]), "+r"(acc[mt][2]), "+r"(acc[mt][3])
+                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+          }
+        };
+        auto limbs_of = [&](float e, float eqi, int* l) {
+          const float sv = e * eqi;
+          if (!(fabsf(sv) <= 1073741824.0f)) bad = true;
+          split_limbs(__float2int_rn(sv), l[0], l[1], l[2], l[3]);
+        };
+        auto g_finish = [&](int c) {
+          // this warp's accumulators -> one 64-bit sum per (system, marker); twelve warps -> shared memory -> the first group adds
+          // them up and sends the worker's partial to the cluster's solver
+          named_bar(3, kEpiWarps * 32);  // the previous block's partials have been read
+#pragma unroll
+          for (int mt = 0; mt < 8; mt++) {
+            long long v0 = (t4 & 1) ? ((long long)acc[mt][0] << 16) + ((long long)acc[mt][1] << 24) : (long long)acc[mt][0] + ((long long)acc[mt][1] << 8);
+            long long v1 = (t4 & 1) ? ((long long)acc[mt][2] << 16) + ((long long)acc[mt][3] << 24) : (long long)acc[mt][2] + ((long long)acc[mt][3] << 8);
+            v0 += __shfl_xor_sync(0xffffffffu, v0, 1);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+            const int sy = t4 >> 1;
+            if (!(t4 & 1) && sy < ns) { rw[sy * 128 + 16 * mt + g8] = v0; rw[sy * 128 + 16 * mt + g8 + 8] = v1; }
+          }
+          named_bar(2, kEpiWarps * 32);
+          if (grp == 0) {
+            const uint32_t rdst = mapa_u32(hin_u32 + (uint32_t)((((c & 1) * kClWorkers + (crank - 1)) * ns) * 128 + q) * 8u, 0u);
+            const uint32_t rbar = mapa_u32(smem_u32(&S.h_in[c & 1]), 0u);
+            for (int s = 0; s < ns; s++) {
+              long long sum = 0;
+#pragma unroll
+              for (int w = 0; w < kEpiWarps; w++) sum += red[((size_t)w * ns + s) * 128 + q];
+              st_async_u64(rdst + (uint32_t)s * 1024u, (unsigned long long)sum, rbar);
+            }
+            if (t0) WSTAMP(c, 7);
+          }
+        };
+        // ---- partials of the first blocks from the residuals as loaded
+        for (int c = 0; c <= npro; c++) {
+          mbar_wait(&S.tile_full[c % nbuf], (uint32_t)(c / nbuf) & 1u, dead, a.err);
+#pragma unroll
+          for (int mt = 0; mt < 8; mt++) { acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0; }
+          for (int at = grp; at < NA; at += 3) {
+            if (at * 128 + quarter * 32 >= R) continue;
+            const int i = at * 128 + q;
+            int l[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (i < R) {
+#pragma unroll
+              for (int s = 0; s < 2; s++) if (s < ns) limbs_of(Es[s * RS + i], sc[s].e_qinv, l + 4 * s);
+            }
+            g_unit(c, at, l);
+          }
+          g_finish(c);
+        }
+        for (int b = 0; b < nblocks; b++) {
+          const int c = b + 1 + D;
+          mbar_wait(&S.de_in[b & 1], (uint32_t)(b >> 1) & 1u, dead, a.err);
+          if (t0) WSTAMP(b, 0);
+          if (grp == 0) {  // the limbs of the step of marker q: B operand of U(b)
+            unsigned char* dl = DL + (size_t)(b & 1) * (N / 8) * 1024;
+            for (int s = 0; s < ns; s++) {
+              int l0, l1, l2, l3;
+              split_limbs(dead ? 0 : (int)dein[(size_t)((b & 1) * ns + s) * kDeStride + q], l0, l1, l2, l3);
+              dl[sw128_off(4 * s + 0, q)] = (unsigned char)l0; dl[sw128_off(4 * s + 1, q)] = (unsigned char)l1;
+              dl[sw128_off(4 * s + 2, q)] = (unsigned char)l2; dl[sw128_off(4 * s + 3, q)] = (unsigned char)l3;
+            }
+            // this inbox slot is next used by block b + 2, whose step cannot be sent before this worker's partial of b + 2
+            if (q == 0 && b + 2 < nblocks) mbar_expect_tx(&S.de_in[b & 1], (uint32_t)(ns * 129 * 4));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&S.dl_full[b & 1]);
+            if (t0) WSTAMP(b, 1);
+          }
+          float dqv[2];
+#pragma unroll
+          for (int s = 0; s < 2; s++) dqv[s] = s < ns ? __uint_as_float(dein[(size_t)((b & 1) * ns + s) * kDeStride + 128]) : 0.0f;
+          if (c < nblocks) {
+            mbar_wait(&S.tile_full[c % nbuf], (uint32_t)(c / nbuf) & 1u, dead, a.err);
+#pragma unroll
+            for (int mt = 0; mt < 8; mt++) { acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0; }
+          }
+          for (int at = grp; at < NA; at += 3) {
+            mbar_wait(&S.u_done_at[at], (uint32_t)b & 1u, dead, a.err);
+            if (t0 && at == grp) WSTAMP(b, 3);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            int u[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll
+            for (int s = 0; s < 2; s++) if (s < ns) tmem_ld4(tmem_base + tlane + (uint32_t)(at * N + 4 * s), u[s][0], u[s][1], u[s][2], u[s][3]);
+            tmem_ld_wait();
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&S.u_free_at[at]);
+            if (at * 128 + quarter * 32 >= R) continue;  // rows beyond the slab: nothing to update, nothing to add
+            const int i = at * 128 + q;
+            int l[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (i < R) {
+#pragma unroll
+              for (int s = 0; s < 2; s++) {
+                if (s < ns) {
+                  // uq * dq in two exact float pieces (uq = 2^24 hi + lo, |hi| < 2^22, 0 <= lo < 2^24; dq is a power of two)
+                  const long long uq = combine_limbs(u[s][0], u[s][1], u[s][2], u[s][3]);
+                  const float hi = (float)(int)(uq >> 24) * 16777216.0f, lo = (float)(int)(uq & 0xFFFFFF);
+                  const float e = fmaf(-lo, dqv[s], fmaf(-hi, dqv[s], Es[s * RS + i]));
+                  Es[s * RS + i] = e;
+                  limbs_of(e, sc[s].e_qinv, l + 4 * s);
+                }
+              }
+            }
+            if (c < nblocks) g_unit(c, at, l);
+          }
+          if (t0) WSTAMP(b, 4);
+          if (c < nblocks) g_finish(c);
+        }
+        // residuals back to HBM (every thread its own rows)
+        for (int at = grp; at < NA; at += 3) {
+          const int i = at * 128 + q, r = row0 + i;
+          if (i < R && r < a.g.ld) for (int s = 0; s < ns; s++) a.e[(size_t)s * a.g.ld + r] = Es[s * RS + i];
+        }
+      }
+      if (bad) atomicExch(a.err, 4);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+      }
+#undef WSTAMP
+      cluster_sync_all();
+      return;
+    }
     // =====================================================================================================
     // worker
     // =====================================================================================================
@@ -625,7 +888,7 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
   const long long* hin = reinterpret_cast<const long long*>(base + L.hi);
   long long* hsum = reinterpret_cast<long long*>(base + L.hs);
   // a worker's step inbox sits at the same shared-window offset in every CTA of this launch
-  const uint32_t dein_u32 = smem_u32(base) + (uint32_t)worker_layout(a.rows_per_cta, ns, a.nbuf, CL).di;
+  const uint32_t dein_u32 = smem_u32(base) + (uint32_t)worker_layout(a.rows_per_cta, ns, a.nbuf, CL, CL && a.fastw).di;
   const bool centred = a.sx != nullptr;
   const float inv_n = 1.0f / (float)a.g.n;
   if (tid < 64) cs[tid] = 0.0f;
@@ -716,6 +979,29 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
         }
         mbar_arrive(&S.h_ready[slot]);
         if (tracing && ct == 0) { long long* tp_ = a.trace + ((size_t)blockIdx.x * nblocks + b) * 32 + 4; tp_[0] = (long long)gtimer(); tp_[16] = clock64(); }
+        // until the partials of the next block arrive these warps are idle: three of them take one tile each of the lower-
+        // triangular product dE = T r of the block they just delivered ((2,2), (3,2), (3,3)); the solve warps add the tile sums in
+        // the same order as when they compute all tiles themselves, so the result is bit-identical to the flat topology
+        if (full_inv && pipe_wps4(MODEL, ns, centred) && !sc[0].done) {
+          named_bar(4, 256);  // r of all 128 markers is in shared memory
+          const int hw = warp - kCommWarp0;  // 0: tile (2,2); 1: (3,2); 2: (3,3)
+          if (hw < 3) {
+            const int tw = hw == 0 ? 2 : 3, tt = hw == 1 ? 2 : hw == 0 ? 2 : 3;
+            const float* Gb = Gs + (size_t)(b % sring) * 10 * kTileF;
+            const float* trow = Gb + (size_t)tri(tw, tt) * kTileF + lane * kTS;
+            const float* rv4 = rb + 32 * tt;
+            float fa[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k4 = 0; k4 < 8; k4++) {
+              const float4 tv = *reinterpret_cast<const float4*>(trow + 4 * k4);
+              const float4 rv = *reinterpret_cast<const float4*>(rv4 + 4 * k4);
+              fa[0] = fmaf(tv.x, rv.x, fa[0]); fa[1] = fmaf(tv.y, rv.y, fa[1]);
+              fa[2] = fmaf(tv.z, rv.z, fa[2]); fa[3] = fmaf(tv.w, rv.w, fa[3]);
+            }
+            rb[128 + hw * 32 + lane] = (fa[0] + fa[1]) + (fa[2] + fa[3]);
+          }
+          named_bar(5, 256);
+        }
       }
     }
     const bool wps4 = pipe_wps4(MODEL, ns, centred);
@@ -791,9 +1077,14 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
           // dE = T r: all right-hand sides through shared memory, then every warp takes its 32 rows of the lower-triangular
           // product at once -- no dependent 32-marker steps left in the chain
           rb[jj] = r;
-          named_bar(4, 128);
+          named_bar(4, CL ? 256 : 128);
 #pragma unroll
           for (int t = 0; t < 4; t++) {
+            if (CL && t >= 2) {  // tiles (2,2), (3,2), (3,3) come from the comm warps: same tile sums, added in the same order
+              if (t == 2) named_bar(5, 256);
+              if (t <= w) de += rb[128 + (w == 2 ? 0 : t - 1) * 32 + lane];
+              continue;
+            }
             if (t <= w) {
               const float* trow = Gb + (size_t)tri(w, t) * kTileF + lane * kTS;
               const float* rv4 = rb + 32 * t;
@@ -858,10 +1149,11 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
         if (lane == 0) mxs[(b & 1) * 4 + w] = mx;
         named_bar(3, 128);
         mx = fmaxf(fmaxf(mxs[(b & 1) * 4 + 0], mxs[(b & 1) * 4 + 1]), fmaxf(mxs[(b & 1) * 4 + 2], mxs[(b & 1) * 4 + 3]));
+        // frexp exponent of the block maximum by exponent-field arithmetic (mx = m 2^ex, 0.5 <= m < 1; subnormals clamp below anyway)
         int ex = 0;
-        if (mx > 0.0f && mx < 3.0e38f) frexpf(mx, &ex);
+        if (mx > 0.0f && mx < 3.0e38f) ex = (int)((__float_as_uint(mx) >> 23) & 0xFFu) - 126;
         if (ex < -90) ex = -90;
-        const float dq = ldexpf(1.0f, ex - 30), dqinv = ldexpf(1.0f, 30 - ex);
+        const float dq = __uint_as_float((uint32_t)(ex - 30 + 127) << 23), dqinv = __uint_as_float((uint32_t)(30 - ex + 127) << 23);
         if (!(mx < 3.0e38f)) atomicExch(a.err, 4);
         unsigned long long* wv = a.dew + (size_t)b * kDewStride;
         const bool valid = jj < nvalid && !Sy.done;
@@ -1379,8 +1671,8 @@ int max_clusters_model(size_t smem) {
 }  // namespace
 
 // Shared memory of one CTA (both roles use the same launch) and the largest tile ring that fits.
-size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring, int full_inv, int cl) {
-  const size_t w = worker_layout(rows_per_cta, nsys, nbuf, cl != 0).total;
+size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring, int full_inv, int cl, int fastw) {
+  const size_t w = worker_layout(rows_per_cta, nsys, nbuf, cl != 0, cl != 0 && fastw != 0).total;
   const size_t s = solver_layout(nsys, model_is_gibbs(model), !full_inv && pipe_use_inv(model, nsys), sring, cl != 0).total;
   return (w > s ? w : s) + 1024;
 }
@@ -1418,7 +1710,7 @@ int sweep_pipe_max_clusters(int model, size_t smem) {
 }
 
 cudaError_t launch_sweep_pipe(const PipeArgs& a, cudaStream_t st) {
-  const size_t smem = sweep_pipe_smem(a.rows_per_cta, a.nsys, a.model, a.nbuf, a.sring, a.tinv != nullptr, a.cl);
+  const size_t smem = sweep_pipe_smem(a.rows_per_cta, a.nsys, a.model, a.nbuf, a.sring, a.tinv != nullptr, a.cl, a.fastw);
   const int model = a.model;
 #define BWGR_CALL(M) launch_model<M>(a, smem, st)
   BWGR_MODEL_SWITCH(BWGR_CALL)

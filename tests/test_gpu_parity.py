@@ -597,3 +597,30 @@ def test_masked_folds_emBL_emEN():
             ref = O.em(model, Y[keep, t], X[keep].astype(np.float32), it=25)
             assert np.abs(out["b"][:, t] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max(), (model, t)
             assert abs(out["h2"][t] - ref["h2"]) <= 2 * RTOL, (model, t, out["h2"][t], ref["h2"])
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_kmup_stochastic_branch(tpod, path):
+    """One Kuo-Mallick sweep WITH the indicator branch (pi > 0, Rcpp20260726ai.cpp:23-32), repeated over many seeds from the same
+    start: per-marker means of d (inclusion frequency) and b agree with the oracle's within Monte-Carlo error.  Ratio form of the
+    inclusion probability on both sides (algebraically :25-27)."""
+    y, gen = tpod
+    X = gen.astype(np.float64)
+    n, p = X.shape
+    xx = (X ** 2).sum(0)
+    rng = np.random.default_rng(12)
+    b0 = rng.normal(size=p) * 0.005
+    e0 = y - y.mean() - X @ b0
+    L = np.full(p, 80.0)
+    Ve, pi, reps = 0.03, 0.4, 300
+    A = [O.kmup(X, b0, np.ones(p), xx, e0, L, Ve, pi, seed=1000 + s, ratio_form=True) for s in range(reps)]
+    with bw.Genotypes(gen, path=path) as g:
+        B = [bw.KMUP(g, b0, np.ones(p), xx, e0, L, Ve, pi, seed=5000 + s) for s in range(reps)]
+    da, db = np.mean([r["d"] for r in A], 0), np.mean([r["d"] for r in B], 0)
+    se_d = np.sqrt(da * (1 - da) / reps + db * (1 - db) / reps) + 1e-3
+    assert np.abs(da - db).max() <= 5 * se_d.max(), (np.abs(da - db).max(), se_d.max())
+    assert abs(da.mean() - db.mean()) <= 5 * np.sqrt(2 * 0.25 / (reps * p))
+    ba, bb = np.array([r["b"] for r in A]), np.array([r["b"] for r in B])
+    se_b = np.sqrt(ba.var(0, ddof=1) / reps + bb.var(0, ddof=1) / reps)
+    z = np.abs(ba.mean(0) - bb.mean(0)) / se_b
+    assert z.max() < 5.5 and (z > 3).mean() < 0.02, (z.max(), (z > 3).mean())
