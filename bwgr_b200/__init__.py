@@ -2,5 +2,5 @@
 function names.  The product path is CUDA only: importing works anywhere, calling needs a B200."""
 from .api import (PATH_AUTO, PATH_BLOCKED, PATH_SMALL_N, STORE_2BIT, STORE_I8, BayesA, BayesB, BayesC, BayesRR,  # noqa: F401
                   EmStepper, Genotypes, KMUP, em_fit, emBA, emBB, emBC, emBL, emEN, emRR, gibbs_fit, wgr, MRR3, MRR3F, mrr, mrr_float,
-                  emDE, emML, emBCpi, lasso, BayesL, BayesCpi, BayesDpi, emCV, mcmcCV)
+                  emDE, emML, emBCpi, lasso, BayesL, BayesCpi, BayesDpi, emCV, mcmcCV, GSRR, GSFLM)
 from ._lib import BwgrError, LIB_PATH, SYMBOLS  # noqa: F401

@@ -122,6 +122,16 @@ class Genotypes:
         check(self.lib.bwgr_debug_gram(self.h, _ptr(perm), block, _ptr(out)))
         return out
 
+    def gram_band(self, perm):
+        """The Gram band the pipelined sweep consumes ([nblocks][128][256] floats) from the same dispatch as a fit; returns (band, kind)
+        with kind 4 = FP4 path, 8 = E4M3 / int8 path."""
+        perm = np.ascontiguousarray(perm, dtype=np.int32)
+        nb = (self.p + 127) // 128
+        out = np.empty((nb, 128, 256), dtype=np.float32)
+        kind = C.c_int()
+        check(self.lib.bwgr_debug_gram_band(self.h, _ptr(perm), _ptr(out), C.byref(kind)))
+        return out, kind.value
+
     def profile(self, enable=True):
         check(self.lib.bwgr_profile(self.h, int(enable)))
 
@@ -375,6 +385,31 @@ def KMUP(X, b, d, xx, e, L, Ve, pi, seed=1, **store_kw):
     finally:
         if own:
             g.close()
+
+
+def _gs(which, y, e, gen, b, Lmb, xx, cxx, maxit, **store_kw):
+    g, own = _store(gen, **store_kw)
+    try:
+        y, e, b, Lmb, xx = (np.array(v, dtype=np.float64) for v in (y, e, b, Lmb, xx))
+        _need(y.size == g.n and e.size == g.n, "GSRR / GSFLM: y and e must have n = %d values" % g.n)
+        _need(b.size == g.p and Lmb.size == g.p and xx.size == g.p, "GSRR / GSFLM: b, Lmb, xx must have p = %d values" % g.p)
+        vb = np.zeros(g.p)
+        scal = np.zeros(4)
+        check(g.lib.bwgr_gs_fit(g.h, which, _ptr(y), _ptr(e), _ptr(b), _ptr(Lmb), _ptr(xx), float(cxx), int(maxit), _ptr(vb), _ptr(scal)))
+        return {"mu": float(scal[0]), "b": b, "h2": float(scal[1]), "e": e, "Lmb": Lmb, "vb": vb, "its": int(scal[3])}
+    finally:
+        if own:
+            g.close()
+
+
+def GSRR(y, e, gen, b, Lmb, xx, cxx, maxit=50, **kw):
+    """GSRR(y, e, gen, b, Lmb, xx, cxx, maxit = 50) (Rcpp20260726ai.cpp:1597-1628): same arguments, same list (mu, b, h2, e, Lmb, vb)."""
+    return _gs(0, y, e, gen, b, Lmb, xx, cxx, maxit, **kw)
+
+
+def GSFLM(y, e, gen, b, Lmb, xx, cxx, maxit=50, **kw):
+    """GSFLM(y, e, gen, b, Lmb, xx, cxx, maxit = 50) (Rcpp20260726ai.cpp:1564-1594)."""
+    return _gs(1, y, e, gen, b, Lmb, xx, cxx, maxit, **kw)
 
 
 def wgr(y, X, it=1500, bi=500, th=1, bag=1, rp=False, iv=False, de=False, pi=0, df=5, R2=0.5, eigK=None, VarK=0.95,

@@ -159,6 +159,7 @@ struct bwgr_handle {
   DevBuf<int8_t> x8_own;
   const int8_t* x8 = nullptr;
   DevBuf<uint8_t> x2;
+  DevBuf<uint8_t> x2f;  // packed 2-bit shadow in the layout gram_fp4.cu expands to E2M1 nibbles (codes 0..2 only)
   DevBuf<uint8_t> x2g;  // packed 2-bit shadow of an int8 store with codes 0..2: what the Gram kernel gathers (4x fewer bytes)
   int64_t n = 0, p = 0, ld = 0, ldb = 0;
   int storage = BWGR_STORE_I8;
@@ -302,8 +303,20 @@ int finish_store(bwgr_handle* h, int storage) {
       h->fp8_codes = flag ? 0 : 1;
     }
   }
+  h->x2f.release();
+  if (h->fp8_codes && storage == BWGR_STORE_I8) {  // FP4 Gram shadow copy (gram_fp4.cu): only when every code is 0, 1 or 2
+    const char* fe = getenv("BWGR_GRAM");
+    if (!(fe && !strcmp(fe, "fp8")) && h->x2f.alloc((size_t)(h->ld / 4) * h->p) == cudaSuccess) {
+      launch_pack_2bit_fp4(h->x8, h->ld, (int)h->p, h->x2f.p, h->err.p, h->stream);
+      h->launches++;
+      int flag = 0;
+      CU(cudaMemcpyAsync(&flag, h->err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      if (flag) { CU(cudaMemsetAsync(h->err.p, 0, sizeof(int), h->stream)); h->x2f.release(); }  // a code 3..7: the E4M3 path
+    }
+  }
   h->x2g.release();
-  if (h->fp8_codes && storage == BWGR_STORE_I8) {  // Gram shadow copy (only when every code is 0..2)
+  if (h->fp8_codes && storage == BWGR_STORE_I8 && !h->x2f.p) {  // E4M3 Gram shadow copy (codes 0..3)
     const char* pe = getenv("BWGR_GRAM_PACKED");
     if (!(pe && !strcmp(pe, "0")) && h->x2g.alloc((size_t)(h->ld / 4) * h->p) == cudaSuccess) {
       launch_pack_2bit_gram(h->x8, h->ld, (int)h->p, h->x2g.p, h->err.p, h->stream);
@@ -339,7 +352,7 @@ int prepare_store(bwgr_handle* h, int64_t n, int64_t p, int storage) {
   h->fit.reset();
   h->x2.release();
   h->gram_nat.release(); h->gram_nat_band = 0;
-  h->x2g.release();
+  h->x2g.release(); h->x2f.release();
   h->n = n; h->p = p;
   h->ld = (n + 127) / 128 * 128;
   h->ldb = 0;
@@ -995,7 +1008,10 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
       if (f.shuffled || !f.gram_cached) {
         cudaEvent_t pe = h->prof_begin(0);
         if (h->gram_simt) launch_gram_simt(g, d_perm, f.nblocks, f.gram_p, 1, h->stream);
-        else launch_gram_tc(gram_view(h), d_perm, f.nblocks, f.gram_p, 1, f.nband, h->fp8_codes, h->err.p, h->num_sms, f.sx_dev.p, h->tmap_ok ? h->tmap : nullptr, h->stream);
+        else if (h->x2f.p && f.nband == 2) {
+          const cudaError_t ge = launch_gram_fp4(h->x2f.p, h->ld, (int)h->p, (int)h->n_global, d_perm, f.nblocks, f.gram_p, h->err.p, h->num_sms, f.sx_dev.p, h->stream);
+          if (ge != cudaSuccess) return fail(BWGR_ERR_CUDA, "FP4 Gram launch failed: %s", cudaGetErrorString(ge));
+        } else launch_gram_tc(gram_view(h), d_perm, f.nblocks, f.gram_p, 1, f.nband, h->fp8_codes, h->err.p, h->num_sms, f.sx_dev.p, h->tmap_ok ? h->tmap : nullptr, h->stream);
         h->prof_end(pe);
         h->launches++;
         f.gram_cached = true;
@@ -1257,6 +1273,62 @@ int bwgr_em_fit(bwgr_handle* h, const bwgr_em_params* par, const double* y, bwgr
     if (rc) return rc;
   }
   return bwgr_em_end(h, out);
+}
+
+
+// ---- GSRR / GSFLM: warm-start Gauss-Seidel (Rcpp20260726ai.cpp:1564-1628) ---------------------------------------------
+int bwgr_gs_fit(bwgr_handle* h, int which, const double* y, double* e, double* b, double* Lmb, const double* xx, double cxx, int maxit,
+                double* vb, double* scal) {
+  if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
+  if (!y || !e || !b || !Lmb || !xx) return fail(BWGR_ERR_ARG, "null argument");
+  if (which < 0 || which > 1 || maxit < 1) return fail(BWGR_ERR_ARG, "bad which / maxit");
+  const int64_t n = h->n, p = h->p, ld = h->ld;
+  FitSpec s;
+  s.model = which == 0 ? M_GSRR : M_GSFLM; s.nsys = 1; s.shuffled = false; s.row_mask = nullptr;  // natural marker order (:1581)
+  s.df = 10; s.R2 = 0.5f; s.Pi = 0; s.alpha = 0; s.pi = 0; s.it = maxit; s.bi = 0; s.seed = 0;
+  // fit_begin on the residual as passed in: mu = mean(e), e <- e - mu (:1574), and the y slot keeps e0 for vna = e.e0/n (:1587)
+  int rc = fit_begin(h, s, e);
+  if (rc) return rc;
+  Fit& f = h->fit;
+  std::vector<float> yv(n), hb(p), hl(p), hx(p);
+  for (int64_t i = 0; i < n; i++) { if (!(y[i] == y[i])) return fail(BWGR_ERR_ARG, "y contains NaN"); yv[i] = (float)y[i]; }
+  for (int64_t j = 0; j < p; j++) { hb[j] = (float)b[j]; hl[j] = (float)Lmb[j] + 0.01f; hx[j] = (float)xx[j]; }
+  SysScalars c = f.sc0[0];
+  c.vy = fvar_f(yv);      // float vy = fvar(y) (:1571)
+  c.cxx = (float)cxx;     // phi
+  f.sc0[0] = c; f.vy[0] = c.vy;
+  if (f.xx_over.alloc(p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  CU(cudaMemcpyAsync(f.b.p, hb.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(f.vbv.p, hl.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(f.xx_over.p, hx.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(f.sc.p, &c, sizeof(SysScalars), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  SysScalars sc;
+  int done = 0;
+  while (f.sweeps_issued < maxit && !done) {
+    rc = fit_sweeps(h, std::min(4, maxit - f.sweeps_issued));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(&sc, f.sc.p, sizeof(SysScalars), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    done = sc.done;
+  }
+  rc = check_err_flag(h, "sweep");
+  if (rc) { f.reset(); return rc; }
+  std::vector<float> he(ld);
+  CU(cudaMemcpyAsync(he.data(), f.e.p, sizeof(float) * ld, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(hb.data(), f.b.p, sizeof(float) * p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(hl.data(), f.vbv.p, sizeof(float) * p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int64_t i = 0; i < n; i++) e[i] = he[i];
+  for (int64_t j = 0; j < p; j++) {
+    b[j] = hb[j];
+    const float L = hl[j] - 0.01f;
+    Lmb[j] = L;
+    if (vb) vb[j] = which == 0 ? sc.vb : sc.cxx * sc.ve / (L * L);  // GSFLM: Lmb_j = sqrt(phi vna / Vb_j) (:1589)
+  }
+  if (scal) { scal[0] = sc.mu; scal[1] = 1.0f - sc.ve / c.vy; scal[2] = sc.ve; scal[3] = sc.its; }
+  f.reset();
+  return 0;
 }
 
 // ---- Gibbs -------------------------------------------------------------------------------------------
@@ -1871,6 +1943,31 @@ int bwgr_profile_read(bwgr_handle* h, double* ms, int64_t* counts) {
   h->prof_collect();
   for (int c = 0; c < 4; c++) { if (ms) ms[c] = h->prof_ms[c]; if (counts) counts[c] = h->prof_n[c]; }
   return 0;
+}
+
+// The band the pipelined sweep consumes, produced by the SAME dispatch as in a fit (FP4 shadow when the store has one):
+// out [nblocks][128][256] floats, row r of block b = [x_{b,r}'X_b | x_{b-1,r}'X_b].  *kind_out: 4 = FP4 path, 8 = E4M3 / int8 path.
+int bwgr_debug_gram_band(bwgr_handle* h, const int32_t* perm, float* gram_out, int* kind_out) {
+  if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
+  if (h->storage != BWGR_STORE_I8) return fail(BWGR_ERR_UNSUPPORTED, "Gram kernel needs the int8 store");
+  CU(cudaSetDevice(h->device));
+  const int64_t p = h->p;
+  const int nblocks = (int)((p + kBlk - 1) / kBlk);
+  DevBuf<int> dperm;
+  DevBuf<float> dg;
+  if (dperm.alloc(p) != cudaSuccess || dg.alloc((size_t)nblocks * kBlk * kBlk * 2) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  CU(cudaMemcpyAsync(dperm.p, perm, sizeof(int) * p, cudaMemcpyHostToDevice, h->stream));
+  if (h->x2f.p) {
+    const cudaError_t ge = launch_gram_fp4(h->x2f.p, h->ld, (int)p, (int)h->n, dperm.p, nblocks, dg.p, h->err.p, h->num_sms, nullptr, h->stream);
+    if (ge != cudaSuccess) return fail(BWGR_ERR_CUDA, "FP4 Gram launch failed: %s", cudaGetErrorString(ge));
+  } else {
+    launch_gram_tc(gram_view(h), dperm.p, nblocks, dg.p, 1, 2, h->fp8_codes, h->err.p, h->num_sms, nullptr, h->tmap_ok ? h->tmap : nullptr, h->stream);
+  }
+  if (kind_out) *kind_out = h->x2f.p ? 4 : 8;
+  h->launches++;
+  CU(cudaMemcpyAsync(gram_out, dg.p, sizeof(float) * dg.n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return check_err_flag(h, "gram band");
 }
 
 int bwgr_debug_gram(bwgr_handle* h, const int32_t* perm, int block, int32_t* gram_out) {

@@ -29,7 +29,7 @@ __device__ double block_sum(double v, double* sh) {
 
 __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
   __shared__ double sh[32];
-  __shared__ float s_eM, s_ve, s_cxx;
+  __shared__ float s_eM, s_ve, s_cxx, s_lmb;
   __shared__ int s_acc;
   const int sys = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
   SysScalars* scp = a.sc + sys;
@@ -144,6 +144,14 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
           if (s.cnv < 10e-8f) s.done = 1;
           break;
         }
+        case M_GSRR:
+        case M_GSFLM: {  // :1586-1590, :1618-1624 ; the y slot holds e0 (the residual as passed in); cxx = phi
+          s.ve = (float)(sey - (double)eM * sy) / n;  // vna = e . e0 / n, e after the mean removal
+          if (model == M_GSRR) { s.vb = (s.vy - s.ve) / s.cxx; s.lmb = s.ve / s.vb; }
+          s.cnv = (float)scnv;
+          if (s.cnv < 10e-8f) s.done = 1;
+          break;
+        }
         default: break;  // emBL, M_MRR: mean removal only (M_MRR: none, see below)
       }
       s.C = -0.5f / sqrtf(s.ve);
@@ -192,7 +200,7 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
     *scp = s;
     s_eM = eM;
     s_acc = accumulate;
-    s_ve = s.ve; s_cxx = s.cxx;
+    s_ve = s.ve; s_cxx = s.cxx; s_lmb = s.lmb;
   }
   __syncthreads();
   const float eM = s_eM;
@@ -204,6 +212,17 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
       if (xxj == 0.0f) xxj = 0.1f;  // :261
       const float Vb = b[j] * b[j] + Ve / (xxj + vbv[j] + 0.0001f);
       vbv[j] = sqrtf(cxx * Ve / Vb);
+    }
+  }
+  if ((model == M_GSRR || model == M_GSFLM) && vbv) {  // the per-marker slot carries Lmb_j + 0.01 (the rule's denominator)
+    const float* xx = a.xx + (a.xx_per_sys ? (size_t)sys * a.p : 0);
+    const float vna = s_ve, phi = s_cxx;
+    for (int j = tid; j < a.p; j += T) {
+      if (model == M_GSRR) vbv[j] = s_lmb + 0.01f;  // :1621-1623
+      else {                                        // :1588-1589 ; Vb_j = b_j^2 + vna/(xx_j + Lmb_j), Lmb_j = sqrt(phi vna / Vb_j)
+        const float Vb = b[j] * b[j] + vna / (xx[j] + (vbv[j] - 0.01f));
+        vbv[j] = sqrtf(phi * vna / Vb) + 0.01f;
+      }
     }
   }
   if (eM != 0.0f)

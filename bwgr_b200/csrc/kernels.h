@@ -76,6 +76,11 @@ constexpr int kNC = 8;     // copies of every block accumulator: spreads the L2 
 // tmap != nullptr: the 128-byte CUtensorMap of make_geno_tensor_map -> the tiles are gathered with TMA tile::gather4.
 void launch_gram_tc(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, int nband, int fp8_codes,
                     int* err, int num_sms, const float* sx, const void* tmap, cudaStream_t st);
+// FP4 path (gram_fp4.cu): band-2 Gram of a store whose codes are all 0..2, from the packed shadow of launch_pack_2bit_fp4
+// (ld / 4 bytes per column); exact, twice the E4M3 rate.  gram: [nblocks][128][256] floats.
+void launch_pack_2bit_fp4(const int8_t* src, int64_t ld, int p, uint8_t* dst, int* bad, cudaStream_t st);
+cudaError_t launch_gram_fp4(const uint8_t* x2f, int64_t ld, int p, int n, const int* perm, int nblocks, float* gram, int* err,
+                            int num_sms, const float* sx, cudaStream_t st);
 bool make_geno_tensor_map(const int8_t* x8, int64_t ld, int64_t p, void* tmap_out);
 // SIMT cross-check of the same quantity (debug / tests only; selected with BWGR_GRAM=simt).
 void launch_gram_simt(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, cudaStream_t st);

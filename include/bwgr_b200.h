@@ -154,6 +154,12 @@ BWGR_API int bwgr_gibbs_fit(bwgr_handle* h, const bwgr_gibbs_params* par, const 
 BWGR_API int bwgr_kmup_sweep(bwgr_handle* h, double* b, double* d, const double* xx, double* e, const double* L, double Ve,
                     double pi, uint64_t seed);
 
+/* GSRR / GSFLM(y, e, gen, b, Lmb, xx, cxx, maxit = 50) (:1564-1628): the warm-start Gauss-Seidel solvers mm() calls inside its
+ * back-fitting loop (R/mix.R:890-892).  which = 0 GSRR, 1 GSFLM.  In / out: e [n], b [p], Lmb [p] (the state the caller carries from
+ * one outer iteration to the next); out: vb [p]; scal = {mu, h2, vna (the residual variance e.e0/n), sweeps done}. */
+BWGR_API int bwgr_gs_fit(bwgr_handle* h, int which, const double* y, double* e, double* b, double* Lmb, const double* xx, double cxx,
+                int maxit, double* vb, double* scal);
+
 /* wgr(y,X,it,bi,th,bag=1,rp,iv,de,pi,df,R2) with the MCMC loop native (R/wgr.R:2-169; eigK=NULL).
  * scal = {mu, Ve, Va, cxx}; Vb is [p] when iv/de, else scal[2]. */
 BWGR_API int bwgr_wgr_fit(bwgr_handle* h, const double* y, int it, int bi, int th, int iv, int de, double pi, double df,
@@ -188,6 +194,7 @@ BWGR_API int bwgr_profile(bwgr_handle* h, int enable);
 BWGR_API int bwgr_profile_read(bwgr_handle* h, double* ms, int64_t* counts);
 /* Gram blocks X_B' X_B of one sweep order (perm[p], block markers each), int32, [nblocks][block][block];
  * the tcgen05 kernel's output, exposed so tests can check it bit-exactly. */
+BWGR_API int bwgr_debug_gram_band(bwgr_handle* h, const int32_t* perm, float* gram_out /* [nblocks][128][256] */, int* kind_out);
 BWGR_API int bwgr_debug_gram(bwgr_handle* h, const int32_t* perm, int block, int32_t* gram_out);
 
 #ifdef __cplusplus

@@ -752,6 +752,100 @@ static inline void kmup(const float* X, int n, int p, float* b, float* d, const 
   }
 }
 
+
+// KMUP2: Rcpp20260726ai.cpp:41-77.  The bagged sweep of wgr(bag != 1): only the rows `use` enter; note (H.e0 + b0) without the xx
+// factor (:59, sic) and xx scaled by bg = n0 / n.  e_out has length nuse.
+static inline void kmup2(const float* X, int n0, int p, const float* use, int nuse, float* b, float* d, const float* xx, const float* E,
+                         float* e_out, const float* L, float Ve, float pi, Rng& rng, bool ratio_form) {
+  const int n = nuse;
+  const float C = -0.5f / std::sqrt(Ve);
+  const float bg = (float)n0 / (float)n;
+  std::vector<float> e0(n), H(n), e1(n), e2(n);
+  for (int k = 0; k < n; k++) e0[k] = E[(int)use[k]];
+  for (int j = 0; j < p; j++) {
+    for (int x = 0; x < n; x++) H[x] = X[(size_t)j * n0 + (int)use[x]];
+    const float b0 = b[j];
+    const float sd = std::sqrt(Ve / (xx[j] * bg + L[j]));
+    const float b1 = (float)rng.rnorm((vdot(H.data(), e0.data(), n) + b0) / (xx[j] * bg + L[j]), sd);
+    const float b2 = (float)rng.rnorm(0, sd);
+    for (int i = 0; i < n; i++) e1[i] = e0[i] - H[i] * (b1 - b0);
+    if (pi > 0) {
+      for (int i = 0; i < n; i++) e2[i] = e0[i] - H[i] * (b2 - b0);
+      float pj;
+      if (ratio_form) pj = 1.0f / (1.0f + (pi / (1 - pi)) * std::exp(C * (vsq(e2.data(), n) - vsq(e1.data(), n))));
+      else {
+        const float cj = (1 - pi) * std::exp(C * vsq(e1.data(), n));
+        const float dj = (pi)*std::exp(C * vsq(e2.data(), n));
+        pj = cj / (cj + dj);
+      }
+      if (rng.rbinom1(pj) == 1) { b[j] = b1; d[j] = 1; e0 = e1; }
+      else { b[j] = b2; d[j] = 0; e0 = e2; }
+    } else {
+      d[j] = 1; b[j] = b1; e0 = e1;
+    }
+  }
+  std::memcpy(e_out, e0.data(), sizeof(float) * n);
+}
+
+// GSRR :1597-1628 / GSFLM :1564-1594: the warm-start Gauss-Seidel solvers of mm() (R/mix.R:890-892); natural marker order, the
+// state (b, e, Lmb) is the caller's.  flm = false: GSRR (one variance), true: GSFLM (per-marker variances).  Returns sweeps done.
+struct GsOut { float mu = 0, h2 = 0, vna = 0; int its = 0; };
+static inline GsOut gs_solver(bool flm, const float* y, float* e, const float* X, int n, int p, float* b, float* Lmb, const float* xx,
+                              float cxx, int maxit, float* Vb) {
+  const float tol = 10e-8f, phi = cxx;
+  std::vector<float> e0(e, e + n), bc(p);
+  const float vy = fvar(y, n);
+  float vna = vdot(y, e, n) / (n - 1);
+  float mu = vmean(e, n);
+  for (int i = 0; i < n; i++) e[i] -= mu;
+  int numit = 0;
+  while (numit < maxit) {
+    std::copy(b, b + p, bc.begin());
+    for (int j = 0; j < p; j++) {
+      const float* x = X + (size_t)j * n;
+      const float b0 = b[j];
+      const float b1 = (vdot(x, e, n) + xx[j] * b0) / (Lmb[j] + xx[j] + 0.01f);
+      b[j] = b1;
+      axpy_sub(e, x, b1 - b0, n);
+    }
+    const float eM = vmean(e, n);
+    mu += eM;
+    for (int i = 0; i < n; i++) e[i] -= eM;
+    vna = vdot(e, e0.data(), n) / n;
+    if (flm) {
+      for (int j = 0; j < p; j++) Vb[j] = b[j] * b[j] + vna / (xx[j] + Lmb[j]);
+      for (int j = 0; j < p; j++) Lmb[j] = std::sqrt(phi * vna / Vb[j]);
+    } else {
+      const float vg = (vy - vna) / phi, LmbTmp = vna / vg;
+      for (int j = 0; j < p; j++) { Vb[j] = vg; Lmb[j] = LmbTmp; }
+    }
+    ++numit;
+    float cnv = 0;
+    for (int j = 0; j < p; j++) cnv += std::fabs(bc[j] - b[j]);
+    if (cnv < tol) break;
+  }
+  GsOut o;
+  o.mu = mu; o.h2 = 1.0f - vna / vy; o.vna = vna; o.its = numit;
+  return o;
+}
+
+// CNT :1308-1313 (column centring) and IMP :1316-1335 (NaN -> column mean of the observed values), in place
+static inline void cnt_columns(float* X, int n, int p) {
+  for (int j = 0; j < p; j++) { float* x = X + (size_t)j * n; const float m = vmean(x, n); for (int i = 0; i < n; i++) x[i] -= m; }
+}
+static inline void imp_columns(float* X, int n, int p) {
+  for (int j = 0; j < p; j++) {
+    float* x = X + (size_t)j * n;
+    bool hasna = false;
+    for (int i = 0; i < n; i++) if (std::isnan(x[i])) { hasna = true; break; }
+    if (!hasna) continue;
+    float sum = 0; int cnt = 0;
+    for (int i = 0; i < n; i++) if (!std::isnan(x[i])) { sum += x[i]; cnt++; }
+    const float EXP = sum / cnt;
+    for (int i = 0; i < n; i++) if (std::isnan(x[i])) x[i] = EXP;
+  }
+}
+
 // wgr(): R/wgr.R:2-169 with eigK=NULL, bag=1, no NA.  The driver arithmetic is R's (double);
 // every KMUP call crosses the Rcpp boundary, i.e. casts X,b,d,xx,e,L to float and back
 // (RcppExports.cpp:16-31).

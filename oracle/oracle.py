@@ -129,6 +129,42 @@ def kmup(X, b, d, xx, e, L, Ve, pi, seed=1, ratio_form=False):
     return {"b": b, "d": d, "e": e}
 
 
+def kmup2(X, use, b, d, xx, E, L, Ve, pi, seed=1, ratio_form=False):
+    X = _f32(X)
+    n, p = X.shape
+    use = np.array(use, dtype=np.float32)
+    b, d, xx, E, L = (np.array(v, dtype=np.float32) for v in (b, d, xx, E, L))
+    e_out = np.zeros(use.size, dtype=np.float32)
+    lib().orc_kmup2(_p(X, C.c_float), C.c_int(n), C.c_int(p), _p(use, C.c_float), C.c_int(use.size), _p(b, C.c_float), _p(d, C.c_float),
+                    _p(xx, C.c_float), _p(E, C.c_float), _p(e_out, C.c_float), _p(L, C.c_float), C.c_float(Ve), C.c_float(pi),
+                    C.c_uint64(seed), C.c_int(int(ratio_form)))
+    return {"b": b, "d": d, "e": e_out}
+
+
+def gs(which, y, e, gen, b, Lmb, xx, cxx, maxit=50):
+    """GSRR / GSFLM (Rcpp20260726ai.cpp:1564-1628)."""
+    X = _f32(gen)
+    n, p = X.shape
+    y, e, b, Lmb, xx = (np.array(v, dtype=np.float32) for v in (y, e, b, Lmb, xx))
+    vb = np.zeros(p, dtype=np.float32)
+    scal = np.zeros(4)
+    lib().orc_gs(C.c_int(0 if which == "GSRR" else 1), _p(y, C.c_float), _p(e, C.c_float), _p(X, C.c_float), C.c_int(n), C.c_int(p),
+                 _p(b, C.c_float), _p(Lmb, C.c_float), _p(xx, C.c_float), C.c_float(cxx), C.c_int(maxit), _p(vb, C.c_float), _p(scal, C.c_double))
+    return {"mu": scal[0], "b": b, "h2": scal[1], "e": e, "Lmb": Lmb, "vb": vb, "its": int(scal[3])}
+
+
+def cnt(X):
+    X = np.array(_f32(X), order="F")
+    lib().orc_cnt_imp(C.c_int(0), _p(X, C.c_float), C.c_int(X.shape[0]), C.c_int(X.shape[1]))
+    return X
+
+
+def imp(X):
+    X = np.array(_f32(X), order="F")
+    lib().orc_cnt_imp(C.c_int(1), _p(X, C.c_float), C.c_int(X.shape[0]), C.c_int(X.shape[1]))
+    return X
+
+
 def wgr(y, X, it=1500, bi=500, th=1, iv=False, de=False, pi=0.0, df=5.0, R2=0.5, seed=1, ratio_form=False):
     y = np.ascontiguousarray(y, dtype=np.float64)
     X = np.asfortranarray(X, dtype=np.float64)

@@ -73,6 +73,26 @@ int orc_kmup(const float* X, int n, int p, float* b, float* d, const float* xx, 
   return 0;
 }
 
+int orc_kmup2(const float* X, int n, int p, const float* use, int nuse, float* b, float* d, const float* xx, const float* E, float* e_out,
+              const float* L, float Ve, float pi, uint64_t seed, int ratio_form) {
+  orc::Rng rng(seed);
+  orc::kmup2(X, n, p, use, nuse, b, d, xx, E, e_out, L, Ve, pi, rng, ratio_form != 0);
+  return 0;
+}
+
+// which = 0 GSRR, 1 GSFLM; scal = {mu, h2, vna, its}
+int orc_gs(int which, const float* y, float* e, const float* X, int n, int p, float* b, float* Lmb, const float* xx, float cxx, int maxit,
+           float* vb, double* scal) {
+  const orc::GsOut o = orc::gs_solver(which != 0, y, e, X, n, p, b, Lmb, xx, cxx, maxit, vb);
+  scal[0] = o.mu; scal[1] = o.h2; scal[2] = o.vna; scal[3] = o.its;
+  return 0;
+}
+
+int orc_cnt_imp(int which, float* X, int n, int p) {
+  if (which == 0) orc::cnt_columns(X, n, p); else orc::imp_columns(X, n, p);
+  return 0;
+}
+
 // scal = {mu, Ve, Va, cxx}
 int orc_wgr(const double* y, const double* X, int n, int p, int it, int bi, int th, int iv, int de, double pi, double df,
             double R2, uint64_t seed, int ratio_form, double* b, double* d, double* Vb, double* hat, double* scal) {

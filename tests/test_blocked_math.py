@@ -226,3 +226,24 @@ def test_philox_known_answers(tmp_path):
     assert out[0] == "6627e8d5 e169c58d bc57ac4c 9b00dbd8"
     assert out[1] == "408f276d 41c83b0e a20bc7c6 6d5451fd"
     assert out[2] == "d16cfe09 94fdcceb 5001e420 24126ea1"
+
+
+def test_fp4_shadow_layout_expands_to_e2m1_nibbles():
+    """gram_fp4.cu: the packed 2-bit shadow (word k = rows 16k..16k+15, nibble i = {row 16k+i, row 16k+8+i}) expands with
+    (w & 0x33333333) << 1 and (w >> 1) & 0x66666666 into E2M1 nibbles code << 1 (0 -> 0.0, 1 -> 1.0, 2 -> 2.0), element 2i in
+    the low nibble of byte i -- and E2M1 decodes those nibbles back to the codes."""
+    rng = np.random.default_rng(3)
+    codes = rng.integers(0, 3, size=(64, 16)).astype(np.uint32)   # 64 words x 16 rows
+    w = np.zeros(64, dtype=np.uint32)
+    for r in range(16):
+        w |= codes[:, r] << np.uint32(4 * (r & 7) + 2 * (r >> 3))
+    lo = (w & np.uint32(0x33333333)) << np.uint32(1)
+    hi = (w >> np.uint32(1)) & np.uint32(0x66666666)
+    e2m1 = {0: 0.0, 1: 0.5, 2: 1.0, 3: 1.5, 4: 2.0, 5: 3.0, 6: 4.0, 7: 6.0}
+    for i in range(8):
+        nib_lo = (lo >> np.uint32(4 * i)) & np.uint32(15)
+        nib_hi = (hi >> np.uint32(4 * i)) & np.uint32(15)
+        assert np.array_equal(nib_lo, codes[:, i] << 1) and np.array_equal(nib_hi, codes[:, 8 + i] << 1)
+        assert all(e2m1[int(v)] == float(c) for v, c in zip(nib_lo, codes[:, i]))
+    # a code 3 is caught by the pack kernel's test (both bits of a field set)
+    assert (np.uint32(3 << 6) & (np.uint32(3 << 6) >> np.uint32(1)) & np.uint32(0x55555555)) != 0

@@ -624,3 +624,69 @@ def test_kmup_stochastic_branch(tpod, path):
     se_b = np.sqrt(ba.var(0, ddof=1) / reps + bb.var(0, ddof=1) / reps)
     z = np.abs(ba.mean(0) - bb.mean(0)) / se_b
     assert z.max() < 5.5 and (z > 3).mean() < 0.02, (z.max(), (z > 3).mean())
+
+
+@pytest.mark.parametrize("path", [1, 2])
+@pytest.mark.parametrize("which", ["GSRR", "GSFLM"])
+def test_gs_warm_start_solvers(tpod, which, path):
+    """GSRR / GSFLM (Rcpp20260726ai.cpp:1564-1628): the warm-start Gauss-Seidel solvers of mm(), natural marker order, state (b, e, Lmb)
+    carried by the caller from one call to the next -- a cold start and a warm restart, both kernel families, vs the oracle."""
+    y, gen = tpod
+    X = gen.astype(np.float64)
+    n, p = X.shape
+    xx = (X * X).sum(0)
+    cxx = float(X.var(0, ddof=1).sum())
+    fn = bw.GSRR if which == "GSRR" else bw.GSFLM
+    e0 = y - 0.05
+    with bw.Genotypes(gen, path=path) as g:
+        ref = O.gs(which, y, e0, X, np.zeros(p), np.full(p, cxx), xx, cxx, maxit=7)
+        out = fn(y, e0, g, np.zeros(p), np.full(p, cxx), xx, cxx, maxit=7)
+        assert out["its"] == ref["its"]
+        for key in ("b", "e", "Lmb", "vb"):
+            assert np.abs(out[key] - ref[key]).max() <= RTOL * np.abs(ref[key]).max(), (which, key)
+        assert abs(out["mu"] - ref["mu"]) <= RTOL and abs(out["h2"] - ref["h2"]) <= RTOL
+        ref2 = O.gs(which, y, ref["e"] + ref["mu"], X, ref["b"], ref["Lmb"], xx, cxx, maxit=50)
+        out2 = fn(y, out["e"] + out["mu"], g, out["b"], out["Lmb"], xx, cxx, maxit=50)
+        assert np.abs(out2["b"] - ref2["b"]).max() <= 3 * RTOL * np.abs(ref2["b"]).max()
+        assert abs(out2["h2"] - ref2["h2"]) <= 3 * RTOL
+
+
+@pytest.mark.parametrize("shape", [(196, 376), (1000, 300), (4100, 129), (50000, 512)])
+def test_gram_band_bit_exact(tpod, shape):
+    """The band the sweep consumes, [X_b'X_b | X_{b-1}'X_b], from the production dispatch (block-scaled FP4 tcgen05.mma for stores whose
+    codes are all 0..2): every entry equals the integer numpy product bit for bit -- shuffled order, ragged last block, up to the
+    bench's row count."""
+    if shape == (196, 376):
+        X = tpod[1]
+    else:
+        X, _ = synth(*shape, seed=13)
+    n, p = X.shape
+    perm = O.perm(p, 2)[1]
+    with bw.Genotypes(X) as g:
+        G, kind = g.gram_band(perm)
+    assert kind == 4  # codes 0..2 -> the FP4 path
+    Xi = X.astype(np.int64)
+    nb = G.shape[0]
+    for blk in range(nb):
+        cols = perm[blk * 128:(blk + 1) * 128]
+        want = np.zeros((128, 128), dtype=np.int64)
+        want[:len(cols), :len(cols)] = Xi[:, cols].T @ Xi[:, cols]
+        assert np.array_equal(G[blk][:, :128].astype(np.int64), want), ("diag", blk)
+        if blk > 0:
+            prev = perm[(blk - 1) * 128:blk * 128]
+            wc = np.zeros((128, 128), dtype=np.int64)
+            wc[:len(prev), :len(cols)] = Xi[:, prev].T @ Xi[:, cols]
+            assert np.array_equal(G[blk][:, 128:].astype(np.int64), wc), ("cross", blk)
+
+
+def test_gram_band_general_int8_takes_the_exact_integer_path():
+    rng = np.random.default_rng(17)
+    X = rng.integers(-3, 9, size=(900, 260)).astype(np.int8)
+    perm = np.arange(260, dtype=np.int32)
+    with bw.Genotypes(X) as g:
+        G, kind = g.gram_band(perm)
+    assert kind == 8
+    Xi = X.astype(np.int64)
+    want = Xi.T @ Xi
+    assert np.array_equal(G[1][:, :128].astype(np.int64), want[128:256, 128:256])
+    assert np.array_equal(G[1][:, 128:].astype(np.int64), want[0:128, 128:256])

@@ -122,3 +122,47 @@ def test_goldens_are_reference_output(tpod):
         r = R.em(model, y, X)
         for key, v in r.items():
             assert np.allclose(g[model + "_ref__" + key], v, rtol=0, atol=0), (model, key)
+
+
+def _gs_inputs(tpod):
+    y, X = tpod
+    n, p = X.shape
+    xx = (X * X).sum(0)
+    cxx = float(X.var(0, ddof=1).sum())
+    return y, X, n, p, xx, cxx
+
+
+@pytest.mark.parametrize("which", ["GSRR", "GSFLM"])
+def test_gs_warm_start_solvers_match_reference_text(tpod, which):
+    """GSRR / GSFLM (Rcpp20260726ai.cpp:1564-1628), including a second call warm-started from the first one's state."""
+    y, X, n, p, xx, cxx = _gs_inputs(tpod)
+    e = y - 0.05
+    b = np.zeros(p)
+    L = np.full(p, cxx)
+    a = O.gs(which, y, e, X, b, L, xx, cxx, maxit=7)
+    r = R.gs(which, y, e, X, b, L, xx, cxx, maxit=7)
+    for key in ("b", "e", "Lmb"):
+        assert rel(a[key], r[key]) < 5e-5, (which, key, rel(a[key], r[key]))
+    assert abs(a["mu"] - r["mu"]) < 1e-6 and abs(a["h2"] - r["h2"]) < 1e-5
+    a2 = O.gs(which, y, a["e"] + a["mu"], X, a["b"], a["Lmb"], xx, cxx, maxit=50)
+    r2 = R.gs(which, y, r["e"] + r["mu"], X, r["b"], r["Lmb"], xx, cxx, maxit=50)
+    assert rel(a2["b"], r2["b"]) < 2e-4 and abs(a2["h2"] - r2["h2"]) < 1e-4
+
+
+def test_kmup2_and_preprocessing_match_reference_text(tpod):
+    y, X = tpod
+    n, p = X.shape
+    rng = np.random.default_rng(4)
+    use = np.sort(rng.choice(n, size=n // 2, replace=False)).astype(np.float64)
+    xx = (X * X).sum(0)
+    b0 = rng.normal(size=p) * 0.01
+    E = y - y.mean() - X @ b0
+    L = np.full(p, 40.0)
+    for pi in (0.0, 0.3):
+        a = O.kmup2(X, use, b0, np.ones(p), xx, E, L, 0.03, pi, seed=8)
+        r = R.kmup2(X, use, b0, np.ones(p), xx, E, L, 0.03, pi, seed=8)
+        assert np.array_equal(a["d"], r["d"]) and rel(a["b"], r["b"]) < 1e-4 and rel(a["e"], r["e"]) < 1e-4
+    Xn = X.copy()
+    Xn[rng.random(X.shape) < 0.03] = np.nan
+    assert np.allclose(O.imp(Xn), R.imp(Xn), rtol=0, atol=1e-6) and not np.isnan(O.imp(Xn)).any()
+    assert np.allclose(O.cnt(X), R.cnt(X), rtol=0, atol=1e-6)
