@@ -33,7 +33,7 @@ def _need(cond, what):
 class Genotypes:
     """Genotype matrix resident in HBM (int8 column-major or 2-bit packed) behind one bwgr_handle."""
 
-    def __init__(self, X=None, storage=STORE_I8, device=0, path=PATH_AUTO, grid=0):
+    def __init__(self, X=None, storage=STORE_I8, device=0, path=PATH_AUTO, grid=0, centred_ok=False):
         self.lib = _lib.load()
         h = C.c_void_p()
         check(self.lib.bwgr_create(device, C.byref(h)))
@@ -41,9 +41,9 @@ class Genotypes:
         self.n = self.p = 0
         check(self.lib.bwgr_set_tuning(self.h, -1, path, grid))
         if X is not None:
-            self.load(X, storage)
+            self.load(X, storage, centred_ok=centred_ok)
 
-    def load(self, X, storage=STORE_I8):
+    def load(self, X, storage=STORE_I8, centred_ok=False):
         if hasattr(X, "data_ptr"):  # torch tensor
             import torch
             assert X.dtype == torch.int8 and X.dim() == 2
@@ -62,7 +62,8 @@ class Genotypes:
                 check(self.lib.bwgr_geno_load_i8(self.h, _ptr(Xf), n, p, n, storage))
             else:
                 Xf = np.asfortranarray(X, dtype=np.float64)
-                check(self.lib.bwgr_geno_load_f64(self.h, _ptr(Xf), n, p, n, storage))
+                fn = self.lib.bwgr_geno_load_f64_centred if centred_ok else self.lib.bwgr_geno_load_f64
+                check(fn(self.h, _ptr(Xf), n, p, n, storage))
         self.n, self.p = int(n), int(p)
         return self
 
@@ -449,7 +450,7 @@ def MRR3(Y, X, f32_variant=False, verbose=False, **kw):
         if key not in par:
             raise TypeError("unknown MRR3 argument %r" % key)
         par[key] = v
-    g, own = _store(X)
+    g, own = _store(X, centred_ok=True)  # MRR3 centres every column itself (:378-379): X and CNT(X) are the same model
     try:
         Y = np.asfortranarray(Y, dtype=np.float64)
         _need(Y.ndim == 2 and Y.shape[0] == g.n, "Y must be n x k with n = %d rows" % g.n)

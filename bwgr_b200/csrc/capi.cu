@@ -166,6 +166,8 @@ struct bwgr_handle {
   DevBuf<long long> xx_i, sx_i;
   DevBuf<float> xx_f;
   std::vector<double> h_xx, h_sx;
+  std::vector<double> col_offset;  // bwgr_geno_load_f64_centred: x = code + col_offset[j]
+  bool has_offset = false;
   DevBuf<int> err;
   // tuning
   int path = BWGR_PATH_AUTO, grid = 0;
@@ -438,12 +440,37 @@ int64_t bwgr_launch_count(bwgr_handle* h) { return h ? h->launches : 0; }
 // the CPU, once per call.  Here it happens once per store: a few host threads narrow R's doubles to int8 (exact integers in range
 // only; anything else is an error, never rounded) into two pinned staging buffers laid out like the device store, and the H2D
 // copy of chunk i overlaps the narrowing of chunk i + 1 -- n * p bytes cross PCIe instead of 8 * n * p.
+//
+// offsets != nullptr (bwgr_geno_load_f64_centred): a column may be "integer codes + one constant", e.g. CNT(gen) (Rcpp20260726ai.cpp:1308,
+// the reference's own mrr(Y, CNT(gen)) example, man/mvr.Rd:144-153).  The constant (fractional part of the first entry plus the
+// column minimum, so that the stored codes start at 0) goes to offsets[j]; the codes must still be exact integers (1e-4, the
+// resolution of a float32 column mean).
 static void narrow_columns(const double* X, int64_t ld_src, int64_t n, int64_t ld_dst, int64_t j0, int64_t j1, int8_t* dst, int lo, int hi,
-                           std::atomic<int>* bad) {
+                           std::atomic<int>* bad, double* offsets) {
   int flag = 0;
   for (int64_t j = j0; j < j1; j++) {
     const double* src = X + j * ld_src;
     int8_t* out = dst + (j - j0) * ld_dst;
+    if (offsets) {
+      const double v0 = src[0];
+      double frac = v0 - std::floor(v0);
+      if (!(frac == frac) || frac < 1e-4 || frac > 1.0 - 1e-4) frac = 0.0;
+      offsets[j] = 0.0;
+      if (frac != 0.0) {
+        double mn = 1e300;
+        for (int64_t i = 0; i < n; i++) mn = std::min(mn, src[i] - frac);
+        const double base = std::nearbyint(mn);
+        for (int64_t i = 0; i < n; i++) {
+          const double t = src[i] - frac - base;
+          const double r = std::nearbyint(t);
+          flag |= !(std::fabs(t - r) <= 1e-4) | (r < lo) | (r > hi);
+          out[i] = (int8_t)(int)r;
+        }
+        for (int64_t i = n; i < ld_dst; i++) out[i] = 0;
+        offsets[j] = frac + base;
+        continue;
+      }
+    }
     for (int64_t i = 0; i < n; i++) {
       const double v = src[i];
       const int iv = (int)v;
@@ -455,10 +482,13 @@ static void narrow_columns(const double* X, int64_t ld_src, int64_t n, int64_t l
   if (flag) bad->store(1);
 }
 
-int bwgr_geno_load_f64(bwgr_handle* h, const double* X, int64_t n, int64_t p, int64_t ld, int storage) {
+static int load_f64_common(bwgr_handle* h, const double* X, int64_t n, int64_t p, int64_t ld, int storage, bool allow_offset) {
   if (!X || ld < n) return fail(BWGR_ERR_ARG, "bad X / ld");
   int rc = prepare_store(h, n, p, storage);
   if (rc) return rc;
+  h->col_offset.clear(); h->has_offset = false;
+  if (allow_offset) h->col_offset.assign((size_t)p, 0.0);
+  double* offs = allow_offset ? h->col_offset.data() : nullptr;
   const int lo = storage == BWGR_STORE_2BIT ? 0 : -128, hi = storage == BWGR_STORE_2BIT ? 2 : 127;
   const int64_t ldd = h->ld;
   const int64_t chunk_cols = std::max<int64_t>(1, std::min<int64_t>(p, ((int64_t)32 << 20) / ldd));
@@ -484,8 +514,8 @@ int bwgr_geno_load_f64(bwgr_handle* h, const double* X, int64_t n, int64_t p, in
     const int nt = (int)std::min<int64_t>(nthr, pc);
     std::vector<std::thread> pool;
     for (int t = 1; t < nt; t++)
-      pool.emplace_back(narrow_columns, X, ld, n, ldd, j0 + pc * t / nt, j0 + pc * (t + 1) / nt, stage[sb] + (pc * t / nt) * ldd, lo, hi, &bad);
-    narrow_columns(X, ld, n, ldd, j0, j0 + pc / nt, stage[sb], lo, hi, &bad);
+      pool.emplace_back(narrow_columns, X, ld, n, ldd, j0 + pc * t / nt, j0 + pc * (t + 1) / nt, stage[sb] + (pc * t / nt) * ldd, lo, hi, &bad, offs);
+    narrow_columns(X, ld, n, ldd, j0, j0 + pc / nt, stage[sb], lo, hi, &bad, offs);
     for (auto& th : pool) th.join();
     ce = cudaMemcpyAsync(h->x8_own.p + j0 * ldd, stage[sb], (size_t)pc * ldd, cudaMemcpyHostToDevice, h->stream);
     if (ce == cudaSuccess) ce = cudaEventRecord(done[sb], h->stream);
@@ -494,7 +524,14 @@ int bwgr_geno_load_f64(bwgr_handle* h, const double* X, int64_t n, int64_t p, in
   for (int i = 0; i < 2; i++) { cudaFreeHost(stage[i]); cudaEventDestroy(done[i]); }
   if (ce != cudaSuccess) return fail(BWGR_ERR_CUDA, "bwgr_geno_load_f64: %s", cudaGetErrorString(ce));
   if (bad.load()) return fail(BWGR_ERR_ARG, "bwgr_geno_load_f64: non-integer or out-of-range genotype");
+  if (allow_offset) for (double v : h->col_offset) if (v != 0.0) { h->has_offset = true; break; }
   return finish_store(h, storage);
+}
+int bwgr_geno_load_f64(bwgr_handle* h, const double* X, int64_t n, int64_t p, int64_t ld, int storage) {
+  return load_f64_common(h, X, n, p, ld, storage, false);
+}
+int bwgr_geno_load_f64_centred(bwgr_handle* h, const double* X, int64_t n, int64_t p, int64_t ld, int storage) {
+  return load_f64_common(h, X, n, p, ld, storage, true);
 }
 
 static int load_i8_common(bwgr_handle* h, const int8_t* X, int64_t n, int64_t p, int64_t ld, int storage, cudaMemcpyKind kind) {
@@ -667,6 +704,9 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
   if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
   if (!y) return fail(BWGR_ERR_ARG, "y is NULL");
   if (s.nsys < 1 || s.nsys > 4096) return fail(BWGR_ERR_ARG, "bad nsys %d", s.nsys);
+  if (h->has_offset && s.model != M_MRR)
+    return fail(BWGR_ERR_UNSUPPORTED, "this store holds integer codes + a constant per column (bwgr_geno_load_f64_centred): only the solvers that "
+                                      "centre the columns themselves (MRR3 / MRR3F) can use it");
   CU(cudaSetDevice(h->device));
   Fit& f = h->fit;
   f.reset();

@@ -91,6 +91,10 @@ BWGR_API int bwgr_set_tuning(bwgr_handle* h, int block, int path, int grid);
 /* X: host, column-major, n x p, leading dimension ld (>= n). Values must be integers in
  * [-128,127] (I8) or {0,1,2} (2BIT); anything else -> BWGR_ERR_ARG (no silent rounding). */
 BWGR_API int bwgr_geno_load_f64(bwgr_handle* h, const double* X, int64_t n, int64_t p, int64_t ld, int storage);
+/* The same for a caller whose solver centres the columns itself (MRR3 / MRR3F, RcppEigen20230423.cpp:378-379): a column may be
+ * "integer codes + one constant", e.g. CNT(gen) (Rcpp20260726ai.cpp:1308; the reference's own example mrr(Y, CNT(gen)), man/mvr.Rd:144-153).
+ * The codes are stored, the constants dropped; the other solvers refuse such a store (BWGR_ERR_UNSUPPORTED). */
+BWGR_API int bwgr_geno_load_f64_centred(bwgr_handle* h, const double* X, int64_t n, int64_t p, int64_t ld, int storage);
 BWGR_API int bwgr_geno_load_i8(bwgr_handle* h, const int8_t* X, int64_t n, int64_t p, int64_t ld, int storage);
 /* Same, X already resident in device memory (int8, column-major). */
 BWGR_API int bwgr_geno_load_i8_device(bwgr_handle* h, const int8_t* dX, int64_t n, int64_t p, int64_t ld, int storage);

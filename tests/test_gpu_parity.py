@@ -690,3 +690,22 @@ def test_gram_band_general_int8_takes_the_exact_integer_path():
     want = Xi.T @ Xi
     assert np.array_equal(G[1][:, :128].astype(np.int64), want[128:256, 128:256])
     assert np.array_equal(G[1][:, 128:].astype(np.int64), want[0:128, 128:256])
+
+
+def test_mrr_on_centred_genotypes(tpod):
+    """The reference's own multivariate example is mrr(Y, CNT(gen)) (man/mvr.Rd:144-153; CNT = column centring, Rcpp20260726ai.cpp:1308).
+    MRR3 centres X itself, so the centred matrix is the same model: the loader stores the integer codes, drops the column constants, and
+    the fit equals the oracle's on the centred float matrix.  The univariate solvers refuse such a store."""
+    _, gen = tpod
+    Y = np.load(os.path.join(GOLDEN, "tpod_mrr3.npz"))["Y"]
+    Xc = O.cnt(gen.astype(np.float64)).astype(np.float64)  # float32 column means, like the reference's CNT
+    ref = O.mrr3(Y, Xc, maxit=6)
+    out = bw.mrr(Y, Xc, maxit=6)
+    _close_mrr(out, ref, 2e-4)
+    with bw.Genotypes(Xc, centred_ok=True) as g:
+        assert np.array_equal(g.unpack(), gen)  # codes - min = the 0/1/2 genotypes
+        with pytest.raises(bw.BwgrError) as ei:
+            bw.emRR(Y[:, 0], g, it=2)
+        assert ei.value.code == -5
+    with pytest.raises(bw.BwgrError):
+        bw.Genotypes(Xc)  # the strict loader still rejects non-integers
