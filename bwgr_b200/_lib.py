@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libbwgr_b200.so")
 # every symbol include/bwgr_b200.h declares (tests check the shared object exports all of them)
 SYMBOLS = [
     "bwgr_create", "bwgr_destroy", "bwgr_last_error", "bwgr_version", "bwgr_set_stream", "bwgr_set_tuning",
-    "bwgr_geno_load_f64", "bwgr_geno_load_f64_centred", "bwgr_geno_load_i8", "bwgr_geno_load_i8_device", "bwgr_geno_unpack_i8", "bwgr_geno_raw",
+    "bwgr_geno_load_f64", "bwgr_geno_load_f64_centred", "bwgr_geno_load_bed", "bwgr_geno_load_i8", "bwgr_geno_load_i8_device", "bwgr_geno_unpack_i8", "bwgr_geno_raw",
     "bwgr_geno_info", "bwgr_geno_stats", "bwgr_em_fit", "bwgr_em_begin", "bwgr_em_sweeps", "bwgr_em_end",
     "bwgr_gibbs_fit", "bwgr_kmup_sweep", "bwgr_gs_fit", "bwgr_wgr_fit", "bwgr_mrr3_fit", "bwgr_dist_unique_id", "bwgr_dist_init", "bwgr_dist_connect", "bwgr_launch_count", "bwgr_debug_gram", "bwgr_debug_gram_band", "bwgr_profile", "bwgr_profile_read",
 ]
@@ -63,6 +63,7 @@ def load():
         lib.bwgr_set_tuning.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         for name in ("bwgr_geno_load_f64", "bwgr_geno_load_f64_centred", "bwgr_geno_load_i8", "bwgr_geno_load_i8_device"):
             getattr(lib, name).argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int]
+        lib.bwgr_geno_load_bed.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p]
         lib.bwgr_geno_unpack_i8.argtypes = [C.c_void_p, C.c_void_p]
         lib.bwgr_geno_raw.argtypes = [C.c_void_p, C.c_void_p]
         lib.bwgr_geno_info.argtypes = [C.c_void_p] + [C.c_void_p] * 5

@@ -67,6 +67,18 @@ class Genotypes:
         self.n, self.p = int(n), int(p)
         return self
 
+    def load_bed(self, prefix, storage=STORE_I8, missing=-1):
+        """PLINK binary fileset `prefix`.bed / .bim / .fam -> store (additive count of allele A1).  missing: see bwgr_geno_load_bed.
+        Returns the number of missing calls met."""
+        def lines(path):
+            with open(path, "rb") as f:
+                return sum(1 for _ in f)
+        n, p = lines(prefix + ".fam"), lines(prefix + ".bim")
+        nm = C.c_int64()
+        check(self.lib.bwgr_geno_load_bed(self.h, (prefix + ".bed").encode(), n, p, storage, int(missing), C.byref(nm)))
+        self.n, self.p = int(n), int(p)
+        return int(nm.value)
+
     def enable_row_sharding(self, group=None):
         """One large fit sharded by rows over the ranks of a torch.distributed group (one process per GPU of a node):
         call before load(); every rank then loads ITS rows and passes ITS rows of y to the usual fit functions.

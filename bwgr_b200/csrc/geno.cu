@@ -28,6 +28,48 @@ void launch_pack_f64(const double* src, int64_t ld_src, int n, int pc, int8_t* d
   pack_f64_kernel<<<grid, 256, 0, st>>>(src, ld_src, n, pc, dst, ld, lo, hi, bad);
 }
 
+// PLINK .bed (variant-major): column j = ceil(n/4) bytes, sample i in bits 2*(i%4) of byte i/4: 00 = two copies of allele A1, 10 = one,
+// 11 = none, 01 = missing.  Decoded to the additive count of A1 (what `plink --recode A` writes).  missing: 0..2 = that code,
+// -2 = the rounded mean of the column's observed codes (integer stand-in for IMP, Rcpp20260726ai.cpp:1316-1335), -1 = an error (*bad).
+// nmiss += the number of missing calls.
+__global__ void __launch_bounds__(256) decode_bed_kernel(const uint8_t* __restrict__ bed, int64_t bpc, int n, int8_t* __restrict__ dst, int64_t ld,
+                                                         int missing, int* bad, unsigned long long* nmiss) {
+  __shared__ int s_sum, s_cnt, s_fill;
+  const uint8_t* col = bed + (int64_t)blockIdx.x * bpc;
+  int8_t* d = dst + (int64_t)blockIdx.x * ld;
+  if (threadIdx.x == 0) { s_sum = 0; s_cnt = 0; s_fill = missing >= 0 ? missing : 0; }
+  __syncthreads();
+  int sum = 0, cnt = 0, miss = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = (col[i >> 2] >> (2 * (i & 3))) & 3;
+    if (c == 1) miss++;
+    else { sum += c == 0 ? 2 : c == 2 ? 1 : 0; cnt++; }
+  }
+  if (miss) {
+    atomicAdd(nmiss, (unsigned long long)miss);
+    if (missing == -1) atomicExch(bad, 1);
+  }
+  if (missing == -2) {
+    atomicAdd(&s_sum, sum); atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) s_fill = s_cnt > 0 ? (int)rintf((float)s_sum / (float)s_cnt) : 0;
+    __syncthreads();
+  }
+  const int fill = s_fill;
+  for (int i = threadIdx.x; i < ld; i += blockDim.x) {
+    int v = 0;
+    if (i < n) {
+      const int c = (col[i >> 2] >> (2 * (i & 3))) & 3;
+      v = c == 0 ? 2 : c == 2 ? 1 : c == 3 ? 0 : fill;
+    }
+    d[i] = (int8_t)v;
+  }
+}
+void launch_decode_bed(const uint8_t* bed, int64_t bytes_per_col, int n, int p, int8_t* dst, int64_t ld, int missing, int* bad,
+                       unsigned long long* nmiss, cudaStream_t st) {
+  decode_bed_kernel<<<(unsigned)p, 256, 0, st>>>(bed, bytes_per_col, n, dst, ld, missing, bad, nmiss);
+}
+
 __global__ void check_range_kernel(const int8_t* __restrict__ src, int64_t ld, int n, int lo, int hi, int* bad) {
   const int8_t* s = src + (int64_t)blockIdx.x * ld;
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {

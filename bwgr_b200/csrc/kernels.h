@@ -26,6 +26,9 @@ void launch_pack_2bit(const int8_t* src, int64_t ld, int n, int p, uint8_t* dst,
 void launch_pack_2bit_gram(const int8_t* src, int64_t ld, int p, uint8_t* dst, int* bad, cudaStream_t st);
 void launch_unpack_2bit(const uint8_t* src, int64_t ldb, int n, int p, int8_t* dst, int64_t ld, cudaStream_t st);
 void launch_check_range_i8(const int8_t* src, int64_t ld, int n, int p, int lo, int hi, int* bad, cudaStream_t st);
+// PLINK .bed payload (variant-major, after the 3 magic bytes) -> int8 store, additive count of allele A1; see geno.cu
+void launch_decode_bed(const uint8_t* bed, int64_t bytes_per_col, int n, int p, int8_t* dst, int64_t ld, int missing, int* bad,
+                       unsigned long long* nmiss, cudaStream_t st);
 // zero rows [n, ld) of every column
 void launch_zero_pad(int8_t* x, int64_t ld, int n, int p, cudaStream_t st);
 // integer-exact column statistics: xx_j = sum x^2, sx_j = sum x (as int64)

@@ -95,6 +95,11 @@ BWGR_API int bwgr_geno_load_f64(bwgr_handle* h, const double* X, int64_t n, int6
  * "integer codes + one constant", e.g. CNT(gen) (Rcpp20260726ai.cpp:1308; the reference's own example mrr(Y, CNT(gen)), man/mvr.Rd:144-153).
  * The codes are stored, the constants dropped; the other solvers refuse such a store (BWGR_ERR_UNSUPPORTED). */
 BWGR_API int bwgr_geno_load_f64_centred(bwgr_handle* h, const double* X, int64_t n, int64_t p, int64_t ld, int storage);
+/* On-disk ingestion: a PLINK .bed file (variant-major; n = lines of the .fam file, p = lines of the .bim file) decoded on the device
+ * to the additive count of allele A1 (0/1/2, like `plink --recode A`).  missing: 0..2 = code given to missing calls, -2 = the rounded
+ * mean of the marker's observed codes (an integer stand-in for IMP, Rcpp20260726ai.cpp:1316-1335), -1 = missing calls are an error.
+ * *nmissing_out (optional) = the number of missing calls met. */
+BWGR_API int bwgr_geno_load_bed(bwgr_handle* h, const char* path, int64_t n, int64_t p, int storage, int missing, int64_t* nmissing_out);
 BWGR_API int bwgr_geno_load_i8(bwgr_handle* h, const int8_t* X, int64_t n, int64_t p, int64_t ld, int storage);
 /* Same, X already resident in device memory (int8, column-major). */
 BWGR_API int bwgr_geno_load_i8_device(bwgr_handle* h, const int8_t* dX, int64_t n, int64_t p, int64_t ld, int storage);

@@ -709,3 +709,57 @@ def test_mrr_on_centred_genotypes(tpod):
         assert ei.value.code == -5
     with pytest.raises(bw.BwgrError):
         bw.Genotypes(Xc)  # the strict loader still rejects non-integers
+
+
+def _write_plink(prefix, G, miss):
+    """Minimal PLINK fileset of genotypes G (n x p, A1 counts 0/1/2) with missing calls where `miss` is True."""
+    n, p = G.shape
+    code = np.where(miss, 1, np.where(G == 2, 0, np.where(G == 1, 2, 3))).astype(np.uint8)  # 00 A1A1, 10 het, 11 A2A2, 01 missing
+    pad = np.zeros(((n + 3) // 4 * 4, p), dtype=np.uint8)
+    pad[:n] = code
+    by = (pad[0::4] | (pad[1::4] << 2) | (pad[2::4] << 4) | (pad[3::4] << 6)).T  # variant-major
+    with open(prefix + ".bed", "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 0x01])); f.write(np.ascontiguousarray(by).tobytes())
+    with open(prefix + ".fam", "w") as f:
+        for i in range(n):
+            f.write("f%d i%d 0 0 0 -9\n" % (i, i))
+    with open(prefix + ".bim", "w") as f:
+        for j in range(p):
+            f.write("1 snp%d 0 %d A C\n" % (j, j + 1))
+
+
+def test_plink_bed_ingestion(tmp_path, tpod):
+    """a PLINK .bed file goes straight to the store (2 bits per genotype over PCIe, decoded on the device)."""
+    y, gen = tpod
+    rng = np.random.default_rng(6)
+    n, p = 1003, 517   # n not a multiple of 4, ragged last block
+    G = rng.integers(0, 3, size=(n, p)).astype(np.int8)
+    prefix = str(tmp_path / "toy")
+    _write_plink(prefix, G, np.zeros_like(G, bool))
+    for storage in (0, 1):
+        g = bw.Genotypes()
+        assert g.load_bed(prefix, storage=storage) == 0
+        assert np.array_equal(g.unpack(), G)
+        xx, sx = g.stats()
+        assert np.array_equal(xx, (G.astype(np.int64) ** 2).sum(0))
+        g.close()
+    miss = rng.random(G.shape) < 0.02
+    _write_plink(prefix, G, miss)
+    g = bw.Genotypes()
+    with pytest.raises(bw.BwgrError):
+        g.load_bed(prefix)                      # missing calls are an error unless a policy is given
+    assert g.load_bed(prefix, missing=1) == int(miss.sum())
+    assert np.array_equal(g.unpack(), np.where(miss, 1, G))
+    assert g.load_bed(prefix, missing=-2) == int(miss.sum())
+    want = G.copy()
+    for j in range(p):
+        obs = G[~miss[:, j], j]
+        want[miss[:, j], j] = int(np.rint(np.float32(obs.sum()) / np.float32(obs.size)))
+    assert np.array_equal(g.unpack(), want)
+    # the tpod genotypes through a .bed file give the same fit as through R's double matrix
+    _write_plink(prefix, gen, np.zeros_like(gen, bool))
+    g.load_bed(prefix)
+    a = bw.emRR(y, g, it=10)
+    g.close()
+    b = bw.emRR(y, gen.astype(np.float64), it=10)
+    assert np.array_equal(a["b"], b["b"])
