@@ -25,7 +25,7 @@ class BwgrError(RuntimeError):
 
 class EmParams(C.Structure):
     _fields_ = [("model", C.c_int), ("nsys", C.c_int), ("it", C.c_int), ("df", C.c_double), ("R2", C.c_double),
-                ("Pi", C.c_double), ("alpha", C.c_double), ("row_mask", C.c_void_p)]
+                ("Pi", C.c_double), ("alpha", C.c_double), ("row_mask", C.c_void_p), ("weights", C.c_void_p)]
 
 
 class EmOut(C.Structure):

@@ -228,15 +228,15 @@ class _EmBuffers:
         return out
 
 
-def _em_params(model, y, nsys, it, df, R2, Pi, alpha, row_mask, n):
+def _em_params(model, y, nsys, it, df, R2, Pi, alpha, row_mask, n, weights=None):
     mask = None
     if row_mask is not None:
         mask = np.asfortranarray(np.asarray(row_mask).reshape(n, nsys, order="F") != 0, dtype=np.uint8)
-    par = EmParams(_EM[model], nsys, it, df, R2, Pi, alpha, _ptr(mask))
-    return par, mask
+    par = EmParams(_EM[model], nsys, it, df, R2, Pi, alpha, _ptr(mask), _ptr(weights))
+    return par, (mask, weights)
 
 
-def em_fit(model, y, gen, df=10.0, R2=0.5, Pi=0.75, alpha=0.02, it=-1, row_mask=None, **store_kw):
+def em_fit(model, y, gen, df=10.0, R2=0.5, Pi=0.75, alpha=0.02, it=-1, row_mask=None, weights=None, **store_kw):
     """Generic entry: y is n (one fit) or n x k (k independent fits sharing gen)."""
     g, own = _store(gen, **store_kw)
     try:
@@ -244,7 +244,10 @@ def em_fit(model, y, gen, df=10.0, R2=0.5, Pi=0.75, alpha=0.02, it=-1, row_mask=
         squeeze = y.ndim == 1
         Y = np.asfortranarray(y.reshape(g.n, -1, order="F"))
         nsys = Y.shape[1]
-        par, mask = _em_params(model, Y, nsys, it, df, R2, Pi, alpha, row_mask, g.n)
+        if weights is not None:
+            weights = np.ascontiguousarray(weights, dtype=np.float64)
+            _need(weights.size == g.p, "marker weights must have p = %d values" % g.p)
+        par, mask = _em_params(model, Y, nsys, it, df, R2, Pi, alpha, row_mask, g.n, weights)
         buf = _EmBuffers(g.n, g.p, nsys)
         check(g.lib.bwgr_em_fit(g.h, C.byref(par), _ptr(Y), C.byref(buf.c)))
         del mask
@@ -304,9 +307,8 @@ def emDE(y, gen, R2=0.5, **kw):
 
 
 def emML(y, gen, D=None, **kw):
-    if D is not None:  # marker weights (Rcpp20260726ai.cpp:470-476) are not on the B200 path
-        raise _lib.BwgrError(-5, "emML: marker weights D are not on the B200 path")
-    return em_fit("emML", y, gen, **kw)
+    """emML(y, gen, D = NULL) (Rcpp20260726ai.cpp:463-521); D = optional marker weights: the penalty of marker j is Lmb / D[j] (:495)."""
+    return em_fit("emML", y, gen, weights=D, **kw)
 
 
 def emBCpi(y, gen, df=10, R2=0.5, Pi=0.75, **kw):

@@ -93,6 +93,7 @@ struct Fit {
   DevBuf<float> tinv;                   // (I + A L)^-1 of every block of the current sweep (block_inv.cu)
   uint32_t tag = 0;
   DevBuf<unsigned long long> dew, part, cx;
+  DevBuf<float> wts;  // emML: marker weights d_j
   float* gram_p = nullptr;              // Gram band in use: f.gram (per fit) or the handle's natural-order cache
   // single Kuo-Mallick sweep / wgr driver
   DevBuf<float> xx_over;                // caller's xx (KMUP takes it as an argument, :12) / centred xx (MRR3)
@@ -774,7 +775,7 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
   const int ns = s.nsys;
   f.model = s.model; f.nsys = ns; f.shuffled = s.shuffled; f.blocked = blocked; f.masked = s.row_mask != nullptr;
   f.sweeps_issued = 0; f.seed = s.seed; f.gram_cached = false; f.skip_epilogue = false; f.wgr_mode = false; f.gram_p = nullptr;
-  f.xx_over.release(); f.wst.release(); f.sx_dev.release(); f.cshift.release();
+  f.xx_over.release(); f.wst.release(); f.sx_dev.release(); f.cshift.release(); f.wts.release();
   f.it_target = s.it;
 
   // ---- per-system row masks and column statistics
@@ -907,6 +908,7 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
         vbv_init = (float)p + cxx;
         break;
       }
+      case M_EMMLD:
       case M_EMML: {  // :480-486
         c.MSx = sum_vx; c.lmb = sum_vx;
         break;
@@ -1183,6 +1185,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
       ea.model = f.model; ea.nsys = f.nsys; ea.n = (int)h->n; ea.p = (int)p; ea.ld = ld; ea.e = f.e.p; ea.y = f.y.p; ea.b = f.b.p;
       ea.d = f.d.p; ea.vbv = f.vbv.p; ea.b_prev = f.b_prev.p; ea.mask = f.mask.p; ea.sc = f.sc.p; ea.B = f.B.p; ea.D = f.D.p;
       ea.xx = f.masked ? f.xx_sys.p : (f.xx_over.p ? f.xx_over.p : h->xx_f.p); ea.xx_per_sys = f.masked ? 1 : 0;
+      ea.wts = f.wts.p;
       ea.VBv = f.VBv.p; ea.seed_lo = (uint32_t)f.seed; ea.seed_hi = (uint32_t)(f.seed >> 32); ea.chain0 = 0;
       cudaEvent_t pe2 = h->prof_begin(2);
       if (h->world > 1) {  // sums over individuals: per rank, then all-reduced; everything else is replicated
@@ -1232,7 +1235,26 @@ int bwgr_em_begin(bwgr_handle* h, const bwgr_em_params* par, const double* y) {
   FitSpec s;
   int rc = em_spec(par, &s);
   if (rc) return rc;
-  return fit_begin(h, s, y);
+  if (par->weights) {  // emML(y, gen, D): the weighted penalty Lmb / d_j (:495-496) travels in the per-marker slot
+    if (par->model != BWGR_EM_ML) return fail(BWGR_ERR_ARG, "marker weights belong to emML");
+    if (par->nsys != 1 || par->row_mask) return fail(BWGR_ERR_UNSUPPORTED, "emML with marker weights: one unmasked system");
+    s.model = M_EMMLD;
+  }
+  rc = fit_begin(h, s, y);
+  if (rc || !par->weights) return rc;
+  Fit& f = h->fit;
+  const int64_t p = h->p;
+  std::vector<float> w(p), l0(p);
+  for (int64_t j = 0; j < p; j++) {
+    w[j] = (float)par->weights[j];
+    if (!(w[j] > 0.0f)) { f.reset(); return fail(BWGR_ERR_ARG, "marker weights must be positive"); }
+    l0[j] = f.sc0[0].lmb / w[j];
+  }
+  if (f.wts.alloc(p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  CU(cudaMemcpyAsync(f.wts.p, w.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(f.vbv.p, l0.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
 }
 
 int bwgr_em_sweeps(bwgr_handle* h, int nsweeps) {
@@ -1322,6 +1344,7 @@ int bwgr_em_end(bwgr_handle* h, bwgr_em_out* out) {
         h2 = sv / (sv + c.ve);
         break;
       }
+      case M_EMMLD:
       case M_EMML: Vg = c.vb; Va = c.vb * c.MSx; h2 = Va / (Va + c.ve); break;                  // :508-515 (Vg slot = Vb)
       case M_EMBCPI: Va = c.vb; Vg = c.vb * c.MSx; h2 = 1.0f - c.ve / f.vy[t]; pi_out = c.Pi; break;  // :1539-1545
       case M_LASSO: h2 = 1.0f - c.ve / f.vy[t]; Ve = 0; lmb_out = c.lmb; break;                       // :1494-1497

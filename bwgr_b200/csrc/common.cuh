@@ -11,14 +11,16 @@ enum Model : int {
   M_EMDE = 6, M_EMML = 7, M_EMBCPI = 8, M_LASSO = 9,  // the rest of emCV's panel (R/cv.R:13-22)
   M_BRR = 10, M_BA = 11, M_BB = 12, M_BC = 13, M_KMUP = 14, M_MRR = 15 /* rotated MRR3 trait: ridge, per-system lambda */,
   M_BL = 16, M_BCPI = 17, M_BDPI = 18,                 // the rest of mcmcCV's panel (R/cv.R:124-130)
-  M_GSRR = 19, M_GSFLM = 20                            // warm-start Gauss-Seidel solvers of mm() (Rcpp20260726ai.cpp:1564-1628)
+  M_GSRR = 19, M_GSFLM = 20,                           // warm-start Gauss-Seidel solvers of mm() (Rcpp20260726ai.cpp:1564-1628)
+  M_EMMLD = 21                                         // emML with marker weights D: penalty Lmb / d_j (:495-496)
 };
 // Several solvers share one per-marker rule and differ only in the sweep epilogue: the sweep kernels are instantiated per
 // RULE, the epilogue and the host recipes see the full model.  emML :463 steps like emRR, emBCpi :1502 like emBC,
 // BayesCpi :858 like BayesC (its mixing odds Pi0 are never refreshed, only the prior scale Sb follows the inclusion rate).
 // GSRR / GSFLM :1583, :1615 step like emDE with the per-marker slot carrying Lmb_j + 0.01 (their denominator is Lmb_j + xx_j + 0.01).
 __host__ __device__ constexpr int rule_model(int m) {
-  return m == M_EMML ? M_EMRR : m == M_EMBCPI ? M_EMBC : m == M_BCPI ? M_BC : (m == M_GSRR || m == M_GSFLM) ? M_EMDE : m;
+  // emML with weights steps like emDE too: the per-marker slot carries Lmb / d_j, refreshed by the epilogue after every sweep
+  return m == M_EMML ? M_EMRR : m == M_EMBCPI ? M_EMBC : m == M_BCPI ? M_BC : (m == M_GSRR || m == M_GSFLM || m == M_EMMLD) ? M_EMDE : m;
 }
 
 // Per-system scalar state, device resident, updated by the sweep epilogue.
@@ -218,7 +220,7 @@ __device__ __forceinline__ RuleOut marker_rule(float g, float xx, float b0, floa
 // emML :492, BayesL :790.
 __host__ __device__ constexpr bool model_is_linear(int m) {
   return m == M_EMRR || m == M_EMBA || m == M_MRR || m == M_BRR || m == M_BA || m == M_EMDE || m == M_EMML || m == M_BL || m == M_GSRR ||
-         m == M_GSFLM;
+         m == M_GSFLM || m == M_EMMLD;
 }
 struct LinCoef { float a, c, kappa; };
 template <int MODEL>
@@ -237,15 +239,15 @@ __device__ __forceinline__ LinCoef lin_coef(float xx, float b0, float vbj, const
 __host__ __device__ constexpr bool model_is_gibbs(int m) { return (m >= M_BRR && m <= M_KMUP) || (m >= M_BL && m <= M_BDPI); }
 __host__ __device__ constexpr bool model_has_vbj(int m) {
   return m == M_EMBA || m == M_EMBB || m == M_BA || m == M_BB || m == M_KMUP || m == M_EMDE || m == M_BL || m == M_BDPI || m == M_GSRR ||
-         m == M_GSFLM;
+         m == M_GSFLM || m == M_EMMLD;
 }
 // the rule itself rewrites the per-marker slot (KMUP's L and emDE's Lmb are inputs of the sweep: caller / epilogue own them)
-__host__ __device__ constexpr bool model_rule_writes_vbj(int m) { return model_has_vbj(m) && m != M_KMUP && m != M_EMDE && m != M_GSRR && m != M_GSFLM; }
+__host__ __device__ constexpr bool model_rule_writes_vbj(int m) { return model_has_vbj(m) && m != M_KMUP && m != M_EMDE && m != M_GSRR && m != M_GSFLM && m != M_EMMLD; }
 __host__ __device__ constexpr bool model_has_d(int m) {
   return m == M_EMBB || m == M_EMBC || m == M_BB || m == M_BC || m == M_KMUP || m == M_EMBCPI || m == M_LASSO || m == M_BCPI || m == M_BDPI;
 }
 // solvers that stop on sum |b_old - b_new| < tol (emEN :449, emDE :297, emML :505, lasso :1492)
-__host__ __device__ constexpr bool model_has_cnv(int m) { return m == M_EMEN || m == M_EMDE || m == M_EMML || m == M_LASSO || m == M_GSRR || m == M_GSFLM; }
+__host__ __device__ constexpr bool model_has_cnv(int m) { return m == M_EMEN || m == M_EMDE || m == M_EMML || m == M_LASSO || m == M_GSRR || m == M_GSFLM || m == M_EMMLD; }
 
 // int8 genotype byte (two's complement) -> float, on the FMA/ALU pipes (no I2F):
 // place u = (byte ^ 0x80) = x + 128 in the mantissa of 2^23 and subtract 2^23 + 128 (exact).

@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
           if (s.cnv < 10e-6f) s.done = 1;
           break;
         }
+        case M_EMMLD:
         case M_EMML: {  // :498-506 ; (y-mu)'e and (y-mu)'(y-mu) with the updated mu and the centred e, from the running sums
           const double mu1 = (double)s.mu + (double)eM;
           const double yce = sey - (double)eM * sy;
@@ -213,6 +214,9 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
       const float Vb = b[j] * b[j] + Ve / (xxj + vbv[j] + 0.0001f);
       vbv[j] = sqrtf(cxx * Ve / Vb);
     }
+  }
+  if (model == M_EMMLD && vbv && a.wts) {  // :495 ; the penalty of marker j is Lmb / d_j
+    for (int j = tid; j < a.p; j += T) vbv[j] = s_lmb / a.wts[j];
   }
   if ((model == M_GSRR || model == M_GSFLM) && vbv) {  // the per-marker slot carries Lmb_j + 0.01 (the rule's denominator)
     const float* xx = a.xx + (a.xx_per_sys ? (size_t)sys * a.p : 0);

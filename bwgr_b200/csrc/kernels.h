@@ -170,6 +170,7 @@ struct EpilogueArgs {
   int64_t ld;
   float* e; const float* y; float* b; const float* d; float* vbv; const float* b_prev;  // b_prev: convergence (model_has_cnv)
   const float* xx; int xx_per_sys;  // emDE: the per-marker penalty update needs xx_j
+  const float* wts;                 // emML with marker weights: d_j (one system)
   const uint8_t* mask;
   SysScalars* sc;
   float* B; float* D; float* VBv;

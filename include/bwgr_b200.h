@@ -118,6 +118,7 @@ typedef struct {
   int it;        /* sweeps; <0 = the reference's hard-coded 200 (emEN, emDE, emML, lasso: maxit 300 with their tol) */
   double df, R2, Pi, alpha; /* reference defaults: 10, 0.5, 0.75, 0.02 */
   const uint8_t* row_mask;  /* optional n x nsys, 1 = row used by the system (CV folds); NULL = all */
+  const double* weights;    /* emML only: optional marker weights D [p] (Rcpp20260726ai.cpp:471-475; one system, no row mask); NULL = none */
 } bwgr_em_params;
 
 typedef struct {

@@ -114,6 +114,7 @@ template <class R>
 struct EmPar {
   R df = 10, R2 = 0.5, Pi = 0.75, alpha = 0.02;
   int it = -1;  // <0: the reference's hard-coded count (200; emEN maxit 300)
+  const double* D = nullptr;  // emML: optional marker weights (:471-475), p values, cast to float like the reference does
 };
 
 template <class R>
@@ -471,7 +472,8 @@ static void emML(const R* y, const R* X, int n, int p, const EmPar<R>& P, EmOut<
       const int j = sh.order[jj];
       const R* x = X + (size_t)j * n;
       const R b0 = b[j];
-      b[j] = (vdot(x, e.data(), n) + xx[j] * b0) / (xx[j] + Lmb);
+      if (P.D) b[j] = (vdot(x, e.data(), n) + xx[j] * b0) / (xx[j] + Lmb / (R)(float)P.D[j]);  // :495-496
+      else b[j] = (vdot(x, e.data(), n) + xx[j] * b0) / (xx[j] + Lmb);
       axpy_sub(e.data(), x, b[j] - b0, n);
     }
     const R eM = vmean(e.data(), n);

@@ -93,6 +93,22 @@ def em(model, y, gen, df=10.0, R2=0.5, Pi=0.75, alpha=0.02, it=-1, use_double=Fa
     return out
 
 
+def emML_weighted(y, gen, D, it=-1, use_double=False):
+    """emML(y, gen, D) with marker weights (Rcpp20260726ai.cpp:463-521, P_WEIGHTS)."""
+    y = _f32(y)
+    X = _f32(gen)
+    n, p = X.shape
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    mu = C.c_double()
+    its = C.c_int()
+    b = np.zeros(p)
+    hat = np.zeros(n)
+    scal = np.zeros(6)
+    lib().orc_emml_weighted(C.c_int(int(use_double)), _p(y, C.c_float), _p(X, C.c_float), C.c_int(n), C.c_int(p), _p(D, C.c_double), C.c_int(it),
+                            C.byref(mu), _p(b, C.c_double), _p(hat, C.c_double), _p(scal, C.c_double), C.byref(its))
+    return {"mu": mu.value, "b": b, "hat": hat, "h2": scal[2], "Vb": scal[3], "Va": scal[0], "Ve": scal[1], "its": its.value}
+
+
 def gibbs(model, y, X, it=1500, bi=500, pi=0.95, df=5.0, R2=0.5, seed=1):
     y = _f32(y)
     X = _f32(X)

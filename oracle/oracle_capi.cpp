@@ -7,7 +7,7 @@
 namespace {
 template <class R>
 void em_run(int model, const float* y, const float* X, int n, int p, float df, float R2, float Pi, float alpha, int it,
-            double* mu, double* b, double* d, double* hat, double* vbv, double* scal, int* its) {
+            double* mu, double* b, double* d, double* hat, double* vbv, double* scal, int* its, const double* D = nullptr) {
   std::vector<R> yy(y, y + n);
   std::vector<R> XX;
   const R* Xp;
@@ -18,7 +18,7 @@ void em_run(int model, const float* y, const float* X, int n, int p, float df, f
     Xp = XX.data();
   }
   orc::EmPar<R> P;
-  P.df = df; P.R2 = R2; P.Pi = Pi; P.alpha = alpha; P.it = it;
+  P.df = df; P.R2 = R2; P.Pi = Pi; P.alpha = alpha; P.it = it; P.D = D;
   orc::EmOut<R> o;
   orc::em_fit<R>(model, yy.data(), Xp, n, p, P, o);
   *mu = o.mu;
@@ -50,6 +50,15 @@ int orc_em(int model, int use_double, const float* y, const float* X, int n, int
   if (model < 0 || model > 9) return -1;
   if (use_double) em_run<double>(model, y, X, n, p, df, R2, Pi, alpha, it, mu, b, d, hat, vbv, scal, its);
   else em_run<float>(model, y, X, n, p, df, R2, Pi, alpha, it, mu, b, d, hat, vbv, scal, its);
+  return 0;
+}
+
+// emML with marker weights D (Rcpp20260726ai.cpp:463-521, P_WEIGHTS branch)
+int orc_emml_weighted(int use_double, const float* y, const float* X, int n, int p, const double* D, int it, double* mu, double* b,
+                      double* hat, double* scal, int* its) {
+  std::vector<double> d(p), vbv(p);
+  if (use_double) em_run<double>(7, y, X, n, p, 10, 0.5f, 0.75f, 0.02f, it, mu, b, d.data(), hat, vbv.data(), scal, its, D);
+  else em_run<float>(7, y, X, n, p, 10, 0.5f, 0.75f, 0.02f, it, mu, b, d.data(), hat, vbv.data(), scal, its, D);
   return 0;
 }
 

@@ -60,6 +60,18 @@ int ref_em(int model, const float* y, const float* X, int n, int p, float df, fl
   return 0;
 }
 
+// emML(y, gen, D) with marker weights; scal as ref_em
+int ref_emml_weighted(const float* y, const float* X, int n, int p, const double* D, double* mu, double* b, double* hat, double* scal_out) {
+  Rcpp::Nullable<Rcpp::NumericVector> Dn(Rcpp::NumericVector(D, (size_t)p));
+  List* l = (List*)emML(vec_f(y, n), mat_f(X, n, p), Dn);
+  *mu = scal(l, "mu");
+  put(l, "b", b); put(l, "hat", hat);
+  for (int i = 0; i < 6; i++) scal_out[i] = 0;
+  scal_out[0] = scal(l, "Va"); scal_out[1] = scal(l, "Ve"); scal_out[2] = scal(l, "h2"); scal_out[3] = scal(l, "Vb");
+  delete l;
+  return 0;
+}
+
 // model ids as in oracle.py GIBBS_MODELS.  scal = {vb, ve, h2, MSx, pi}
 int ref_gibbs(int model, const float* y, const float* X, int n, int p, float it, float bi, float pi, float df, float R2, uint64_t seed,
               double* mu, double* b, double* d, double* hat, double* vbv, double* scal_out) {

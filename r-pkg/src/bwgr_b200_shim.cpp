@@ -24,15 +24,17 @@ bwgr_handle* handle() {  // one handle (= one GPU) per R session
 void check(int rc) { if (rc != BWGR_OK) Rcpp::stop(bwgr_last_error()); }
 
 // the store persists on the handle: the same matrix object (pointer, shape) fitted again is not packed again
-bwgr_handle* load(SEXP genSEXP, int64_t* n, int64_t* p) {
+bwgr_handle* load(SEXP genSEXP, int64_t* n, int64_t* p, bool centred_ok = false) {
   static const double* last = nullptr;
   static int64_t ln = 0, lp = 0;
+  static bool lc = false;
   NumericMatrix gen(genSEXP);  // R's own memory, no copy
   *n = gen.nrow(); *p = gen.ncol();
   bwgr_handle* h = handle();
-  if (gen.begin() != last || *n != ln || *p != lp) {
-    check(bwgr_geno_load_f64(h, gen.begin(), *n, *p, *n, BWGR_STORE_I8));  // exact integer codes only; anything else is an R error
-    last = gen.begin(); ln = *n; lp = *p;
+  if (gen.begin() != last || *n != ln || *p != lp || lc != centred_ok) {
+    // exact integer codes only (plus one constant per column for the solvers that centre the columns); anything else is an R error
+    check(centred_ok ? bwgr_geno_load_f64_centred(h, gen.begin(), *n, *p, *n, BWGR_STORE_I8) : bwgr_geno_load_f64(h, gen.begin(), *n, *p, *n, BWGR_STORE_I8));
+    last = gen.begin(); ln = *n; lp = *p; lc = centred_ok;
   }
   return h;
 }
@@ -46,14 +48,14 @@ struct EmFit {
   double mu = 0, scal[BWGR_NSCAL] = {0, 0, 0, 0, 0, 0};
   int its = 0;
 };
-EmFit em(int model, SEXP ySEXP, SEXP genSEXP, double df, double R2, double Pi, double alpha) {
+EmFit em(int model, SEXP ySEXP, SEXP genSEXP, double df, double R2, double Pi, double alpha, const double* weights = nullptr) {
   int64_t n, p;
   bwgr_handle* h = load(genSEXP, &n, &p);
   NumericVector y(ySEXP);
   if (y.size() != n) Rcpp::stop("y and gen disagree on the number of individuals");
   EmFit f;
   f.b = NumericVector(p); f.d = NumericVector(p); f.hat = NumericVector(n); f.vb = NumericVector(p);
-  bwgr_em_params par = {model, 1, -1, df, R2, Pi, alpha, nullptr};
+  bwgr_em_params par = {model, 1, -1, df, R2, Pi, alpha, nullptr, weights};
   bwgr_em_out out = {&f.mu, f.b.begin(), f.d.begin(), f.hat.begin(), f.vb.begin(), f.scal, &f.its};
   check(bwgr_em_fit(h, &par, y.begin(), &out));
   return f;
@@ -129,8 +131,9 @@ END_RCPP
 }
 RcppExport SEXP _bWGR_emML(SEXP ySEXP, SEXP genSEXP, SEXP DSEXP) {
 BEGIN_RCPP
-  if (!Rf_isNull(DSEXP)) Rcpp::stop("emML: marker weights D are not on the B200 path");  // :471-475
-  EmFit f = em(BWGR_EM_ML, ySEXP, genSEXP, 10, 0.5, 0.75, 0.02);
+  NumericVector D;  // optional marker weights (:471-475): the penalty of marker j becomes Lmb / D[j]
+  if (!Rf_isNull(DSEXP)) D = NumericVector(DSEXP);
+  EmFit f = em(BWGR_EM_ML, ySEXP, genSEXP, 10, 0.5, 0.75, 0.02, Rf_isNull(DSEXP) ? nullptr : D.begin());
   return List::create(Named("mu") = f.mu, Named("b") = f.b, Named("hat") = f.hat, Named("h2") = f.scal[2], Named("Vb") = f.scal[3],
                       Named("Va") = f.scal[0], Named("Ve") = f.scal[1]);  // :514-520
 END_RCPP
@@ -221,11 +224,35 @@ BEGIN_RCPP
 END_RCPP
 }
 
+// ---- GSRR / GSFLM: the warm-start solvers of mm() (glue :493-527; lists Rcpp20260726ai.cpp:1591-1593, :1625-1627) ----
+static SEXP gs_call(int which, SEXP ySEXP, SEXP eSEXP, SEXP genSEXP, SEXP bSEXP, SEXP LmbSEXP, SEXP xxSEXP, SEXP cxxSEXP, SEXP maxitSEXP) {
+  int64_t n, p;
+  bwgr_handle* h = load(genSEXP, &n, &p);
+  NumericVector y(ySEXP), xx(xxSEXP);
+  NumericVector e = Rcpp::clone(NumericVector(eSEXP)), b = Rcpp::clone(NumericVector(bSEXP)), Lmb = Rcpp::clone(NumericVector(LmbSEXP));
+  if (y.size() != n || e.size() != n || b.size() != p || Lmb.size() != p || xx.size() != p) Rcpp::stop("GSRR / GSFLM: argument lengths disagree with gen");
+  NumericVector vb(p);
+  double scal[4] = {0, 0, 0, 0};
+  check(bwgr_gs_fit(h, which, y.begin(), e.begin(), b.begin(), Lmb.begin(), xx.begin(), Rcpp::as<double>(cxxSEXP), Rcpp::as<int>(maxitSEXP),
+                    vb.begin(), scal));
+  return List::create(Named("mu") = scal[0], Named("b") = b, Named("h2") = scal[1], Named("e") = e, Named("Lmb") = Lmb, Named("vb") = vb);
+}
+RcppExport SEXP _bWGR_GSRR(SEXP ySEXP, SEXP eSEXP, SEXP genSEXP, SEXP bSEXP, SEXP LmbSEXP, SEXP xxSEXP, SEXP cxxSEXP, SEXP maxitSEXP) {
+BEGIN_RCPP
+  return gs_call(0, ySEXP, eSEXP, genSEXP, bSEXP, LmbSEXP, xxSEXP, cxxSEXP, maxitSEXP);
+END_RCPP
+}
+RcppExport SEXP _bWGR_GSFLM(SEXP ySEXP, SEXP eSEXP, SEXP genSEXP, SEXP bSEXP, SEXP LmbSEXP, SEXP xxSEXP, SEXP cxxSEXP, SEXP maxitSEXP) {
+BEGIN_RCPP
+  return gs_call(1, ySEXP, eSEXP, genSEXP, bSEXP, LmbSEXP, xxSEXP, cxxSEXP, maxitSEXP);
+END_RCPP
+}
+
 // ---- MRR3 / MRR3F (glue :755-840; list RcppEigen20230423.cpp:687-700).  The 31 arguments after (Y, X) travel as one double array in
 // the order of R/RcppExports.R:180; `verbose` stays on the R side ----
 static SEXP mrr3_call(int f32_variant, SEXP YSEXP, SEXP XSEXP, const double* par) {
   int64_t n, p;
-  bwgr_handle* h = load(XSEXP, &n, &p);
+  bwgr_handle* h = load(XSEXP, &n, &p, /*centred_ok=*/true);  // MRR3 centres every column itself: mrr(Y, CNT(gen)) is accepted
   NumericMatrix Y(YSEXP);
   if (Y.nrow() != n) Rcpp::stop("Y and X disagree on the number of individuals");
   const int k = Y.ncol(), maxit = (int)par[0];

@@ -763,3 +763,16 @@ def test_plink_bed_ingestion(tmp_path, tpod):
     g.close()
     b = bw.emRR(y, gen.astype(np.float64), it=10)
     assert np.array_equal(a["b"], b["b"])
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_emml_marker_weights(tpod, path):
+    """emML(y, gen, D): the weighted penalty Lmb / D[j] (Rcpp20260726ai.cpp:471-475, :495-496)."""
+    y, gen = tpod
+    D = np.random.default_rng(9).uniform(0.5, 2.0, size=gen.shape[1])
+    ref = O.emML_weighted(y, gen.astype(np.float64), D, it=40)
+    ref64 = O.emML_weighted(y, gen.astype(np.float64), D, it=40, use_double=True)
+    with bw.Genotypes(gen, path=path) as g:
+        out = bw.emML(y, g, D=D, it=40)
+    _close_em(out, ref, "emML", ref64, check_its=False)
+    assert np.abs(out["b"] - bw.emML(y, gen, it=40)["b"]).max() > 1e-2 * np.abs(ref["b"]).max()  # the weights matter

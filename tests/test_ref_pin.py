@@ -166,3 +166,12 @@ def test_kmup2_and_preprocessing_match_reference_text(tpod):
     Xn[rng.random(X.shape) < 0.03] = np.nan
     assert np.allclose(O.imp(Xn), R.imp(Xn), rtol=0, atol=1e-6) and not np.isnan(O.imp(Xn)).any()
     assert np.allclose(O.cnt(X), R.cnt(X), rtol=0, atol=1e-6)
+
+
+def test_emml_marker_weights_match_reference_text(tpod):
+    y, X = tpod
+    D = np.random.default_rng(9).uniform(0.5, 2.0, size=X.shape[1])
+    a, r = O.emML_weighted(y, X, D), R.emML_weighted(y, X, D)
+    for key in r:
+        assert rel(a[key], r[key]) < 5e-5, (key, rel(a[key], r[key]))
+    assert rel(a["b"], O.em("emML", y, X)["b"]) > 1e-2  # the weights matter
