@@ -457,7 +457,7 @@ static void narrow_columns(const double* X, int64_t ld_src, int64_t n, int64_t l
       double frac = v0 - std::floor(v0);
       if (!(frac == frac) || frac < 1e-4 || frac > 1.0 - 1e-4) frac = 0.0;
       offsets[j] = 0.0;
-      if (frac != 0.0) {
+      {  // also for an integer-valued column: the solver centres anyway, and codes starting at 0 keep the store on the FP4 / E4M3 Gram paths
         double mn = 1e300;
         for (int64_t i = 0; i < n; i++) mn = std::min(mn, src[i] - frac);
         const double base = std::nearbyint(mn);
@@ -690,7 +690,7 @@ bool plan_pipe(const bwgr_handle* h, int model, int ns, PipePlan* pl) {
   if (D >= 1 && h->world <= 1 && h->grid <= 1 && !(ce && !strcmp(ce, "0")) && sweep_pipe_cluster_ok(model, ns, full_inv)) {
     const char* fe = getenv("BWGR_FASTW");
     for (int fastw = (ns <= 2 && !(fe && !strcmp(fe, "0"))) ? 1 : 0; fastw >= 0; fastw--)
-      for (int nbuf = D + 2; nbuf >= D + 1; nbuf--) {
+      for (int nbuf = D + 2; nbuf >= D + 1 + fastw; nbuf--) {  // the fast worker refills a tile buffer one block before its next use
         // rows per worker depend on the number of co-resident clusters, which depends on the shared memory per CTA: iterate
         int C = 18;
         for (int iter = 0; iter < 4 && C >= 2; iter++) {
@@ -913,6 +913,7 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
         c.MSx = sum_vx; c.lmb = sum_vx;
         break;
       }
+      case M_GSRR: case M_GSFLM: break;  // warm start: the caller's state is uploaded by bwgr_gs_fit
       case M_EMBCPI: {  // :1508-1520 (emBC's start; the prior Pi is kept for the per-sweep update of Pi)
         if (Pi > 0.5f) Pi = 1 - Pi;
         const float MSx = sum_vx * Pi * (1 - Pi);

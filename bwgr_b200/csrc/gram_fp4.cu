@@ -130,34 +130,40 @@ __global__ void __launch_bounds__(416, 1) gram_fp4_kernel(const uint8_t* __restr
         val[i] = pos < p;
         colp[i] = x2f + (int64_t)(val[i] ? perm[pos] : 0) * ldb;
       }
-      uint4 cur[4], nxt[4];
+      // kPf stages of packed chunks in flight per thread (16 bytes x 4 markers each): the gather is latency-bound, L2 serves the second
+      // reader of every tile (block b's tile 1 is block b + 1's tile 0, fetched by a neighbouring CTA at about the same time)
+      constexpr int kPf = 4;
+      uint4 q[kPf][4];
       auto load_stage = [&](int kg, uint4 (&dst)[4]) {
         const int64_t off = (int64_t)kg * 64 + c * 16;  // byte offset inside the packed column
 #pragma unroll
-        for (int i = 0; i < 4; i++) dst[i] = (val[i] && off < ldb) ? __ldg(reinterpret_cast<const uint4*>(colp[i] + off)) : make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < 4; i++) dst[i] = (val[i] && kg < nkg && off < ldb) ? __ldg(reinterpret_cast<const uint4*>(colp[i] + off)) : make_uint4(0, 0, 0, 0);
       };
-      load_stage(0, cur);
-      for (int kg = 0; kg < nkg && ok; kg++, it++) {
-        if (kg + 1 < nkg) load_stage(kg + 1, nxt);
-        const uint32_t stage = it % kStages, phase = (it / kStages) & 1u;
-        ok = mbar_wait(&S->empty[stage], phase ^ 1u, err);
-        const uint32_t tbase = smem_u32(tiles + stage * kStageBytes);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int m = m0 + 64 * (i & 1);
-          const uint32_t rowb = tbase + (uint32_t)((i >> 1) * 16384 + (m >> 3) * 1024 + (m & 7) * 128);
-          const uint4 pk = cur[i];
-          const uint32_t sw = (uint32_t)m & 7u;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((((uint32_t)(2 * c)) ^ sw) << 4)),
-                       "r"((pk.x & 0x33333333u) << 1), "r"((pk.x >> 1) & 0x66666666u), "r"((pk.y & 0x33333333u) << 1), "r"((pk.y >> 1) & 0x66666666u) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((((uint32_t)(2 * c + 1)) ^ sw) << 4)),
-                       "r"((pk.z & 0x33333333u) << 1), "r"((pk.z >> 1) & 0x66666666u), "r"((pk.w & 0x33333333u) << 1), "r"((pk.w >> 1) & 0x66666666u) : "memory");
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(&S->full[stage]);
-        if (kg + 1 < nkg) {
+      for (int s = 0; s < kPf - 1; s++) load_stage(s, q[s]);
+      for (int kg0 = 0; kg0 < nkg && ok; kg0 += kPf) {
 #pragma unroll
-          for (int i = 0; i < 4; i++) cur[i] = nxt[i];
+        for (int u = 0; u < kPf; u++) {
+          const int kg = kg0 + u;
+          if (kg >= nkg || !ok) break;
+          load_stage(kg + kPf - 1, q[(u + kPf - 1) % kPf]);
+          const uint32_t stage = it % kStages, phase = (it / kStages) & 1u;
+          ok = mbar_wait(&S->empty[stage], phase ^ 1u, err);
+          const uint32_t tbase = smem_u32(tiles + stage * kStageBytes);
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int m = m0 + 64 * (i & 1);
+            const uint32_t rowb = tbase + (uint32_t)((i >> 1) * 16384 + (m >> 3) * 1024 + (m & 7) * 128);
+            const uint4 pk = q[u][i];
+            const uint32_t sw = (uint32_t)m & 7u;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((((uint32_t)(2 * c)) ^ sw) << 4)),
+                         "r"((pk.x & 0x33333333u) << 1), "r"((pk.x >> 1) & 0x66666666u), "r"((pk.y & 0x33333333u) << 1), "r"((pk.y >> 1) & 0x66666666u) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((((uint32_t)(2 * c + 1)) ^ sw) << 4)),
+                         "r"((pk.z & 0x33333333u) << 1), "r"((pk.z >> 1) & 0x66666666u), "r"((pk.w & 0x33333333u) << 1), "r"((pk.w >> 1) & 0x66666666u) : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(&S->full[stage]);
+          it++;
         }
       }
     }

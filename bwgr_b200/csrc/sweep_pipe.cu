@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
 
   if (tid < ns) sc[tid] = a.sc[tid];
   if (tid == 0) {
-    for (int i = 0; i < 8; i++) { mbar_init(&S.tile_full[i], (CL && a.fastw) ? 32 : 128); mbar_init(&S.tile_empty[i], 1); }
+    for (int i = 0; i < 8; i++) { mbar_init(&S.tile_full[i], (CL && a.fastw) ? kEpiWarps * 32 : 128); mbar_init(&S.tile_empty[i], 1); }
     for (int i = 0; i < 4; i++) { mbar_init(&S.u_done_at[i], 1); mbar_init(&S.u_free_at[i], 128); }
     mbar_init(&S.dl_full[0], 128); mbar_init(&S.dl_full[1], 128);
     mbar_init(&S.u_done, 1); mbar_init(&S.el_full, 128); mbar_init(&S.g_done, 1); mbar_init(&S.g_empty, 128);
@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
           const unsigned char* Xt = Xs + (size_t)(b % nbuf) * NA * kAtomBytes;
           mbar_wait(&S.tile_full[b % nbuf], (uint32_t)(b / nbuf) & 1u, dead, a.err);  // long complete (G(b) read this tile two blocks ago)
           mbar_wait(&S.dl_full[b & 1], (uint32_t)(b >> 1) & 1u, dead, a.err);
+          if (tracing && lane == 0) WSTAMP(b, 9);
           const uint64_t bd = desc_k_sw128(smem_u32(DL + (size_t)(b & 1) * (N / 8) * 1024));
           for (int at = 0; at < NA; at++) {
             if (b > 0) mbar_wait(&S.u_free_at[at], (uint32_t)(b - 1) & 1u, dead, a.err);  // the epilogue has drained this accumulator
@@ -360,40 +361,7 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
           }
           if (tracing && lane == 0) WSTAMP(b, 2);
         }
-      } else if (warp == 5 || warp == 6) {
-        // ------------------------------------------------------------------ X tile gather: one warp per tile in flight
-        const int grp = warp - 5;
-        const int nchunk = R >> 4;
-        const bool act = lane < nchunk && row0 + 16 * lane < a.g.ld;
-        const uint32_t choff = (uint32_t)((lane >> 3) * kAtomBytes + ((lane & 7) << 4));
-        const int8_t* xrow = a.g.x8 + row0 + 16 * lane;
-        const uint64_t pol = policy_evict_first();
-        for (int t = grp; t < nblocks; t += 2) {
-          const int buf = t % nbuf;
-          int myid[4];
-#pragma unroll
-          for (int k = 0; k < 4; k++) { const int pos = t * 128 + 32 * k + lane; myid[k] = pos < p ? a.perm[pos] : -1; }
-          if (t >= nbuf) mbar_wait(&S.tile_empty[buf], (uint32_t)(t / nbuf - 1) & 1u, dead, a.err);
-          const uint32_t dst = smem_u32(Xs + (size_t)buf * NA * kAtomBytes);
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-#pragma unroll 8
-            for (int i = 0; i < 32; i++) {
-              const int m = 32 * k + i;
-              const int j = __shfl_sync(0xffffffffu, myid[k], i);
-              if (lane < nchunk) {
-                const uint32_t dm = dst + (uint32_t)(m * 128) + (choff ^ (uint32_t)((m & 7) << 4));
-                const bool ok = act && j >= 0;
-                cp_async16_stream(dm, ok ? xrow + (int64_t)j * a.g.ld : a.g.x8, ok ? 16u : 0u, pol);
-              }
-            }
-          }
-          asm volatile("cp.async.commit_group;" ::: "memory");
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(&S.tile_full[buf]);
-        }
-      } else if (warp != 7) {
+      } else if (warp < 5 || warp > 7) {
         // ------------------------------------------------------------------ epilogue warps: three groups x four TMEM lane quarters
         const int ew = warp <= 4 ? warp - 1 : warp - 4;       // 0..11
         const int grp = ew >> 2;                              // atoms at with at % 3 == grp
@@ -408,6 +376,34 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
         const int kb0 = quarter * 32 + 4 * t4;
         const uint32_t offA = (uint32_t)(g8 * 128 + ((((kb0 >> 4) ^ g8) & 7) << 4) + (kb0 & 15));
         const uint32_t offB = (uint32_t)(g8 * 128 + (((((kb0 + 16) >> 4) ^ g8) & 7) << 4) + (kb0 & 15));
+        // ---- X tile gather, spread over the twelve epilogue warps (a single warp issues cp.async far too slowly: 128 per tile).
+        // Warp ew brings markers ew, ew + 12, ... of a tile: 16-byte chunk `lane` of the row slab of each (SWIZZLE_128B layout the
+        // U pass reads through its MN-major descriptor).  Tile t + nbuf goes into tile t's buffer as soon as U(t) has read it.
+        const int nchunk = R >> 4;
+        const bool gact = lane < nchunk && row0 + 16 * lane < a.g.ld;
+        const uint32_t choff = (uint32_t)((lane >> 3) * kAtomBytes + ((lane & 7) << 4));
+        const int8_t* xrow = a.g.x8 + row0 + 16 * lane;
+        const uint64_t pol = policy_evict_first();
+        auto marker_of = [&](int t) { const int pos = t * 128 + ew + kEpiWarps * lane; return (t < nblocks && lane < 11 && ew + kEpiWarps * lane < 128 && pos < p) ? a.perm[pos] : -1; };
+        auto gather_issue = [&](int t, int ids) {  // ids: lane i holds the marker id of tile row ew + 12 i
+          const uint32_t dst = smem_u32(Xs + (size_t)(t % nbuf) * NA * kAtomBytes);
+#pragma unroll
+          for (int i = 0; i < 11; i++) {
+            const int m = ew + kEpiWarps * i;
+            const int j = __shfl_sync(0xffffffffu, ids, i);
+            if (m < 128 && lane < nchunk) {
+              const uint32_t dm = dst + (uint32_t)(m * 128) + (choff ^ (uint32_t)((m & 7) << 4));
+              const bool ok = gact && j >= 0;
+              cp_async16_stream(dm, ok ? xrow + (int64_t)j * a.g.ld : a.g.x8, ok ? 16u : 0u, pol);
+            }
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto gather_land = [&](int t) {  // this warp's share of tile t has landed -> visible to the tensor core -> count it on the tile's barrier
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(&S.tile_full[t % nbuf]);
+        };
         int acc[8][4];
         auto g_unit = [&](int c, int at, const int (&l)[8]) {
           __syncwarp();
@@ -459,7 +455,12 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
             if (t0) WSTAMP(c, 7);
           }
         };
-        // ---- partials of the first blocks from the residuals as loaded
+        // ---- the first nbuf tiles, then the partials of the first blocks from the residuals as loaded
+        for (int t = 0; t < nbuf && t < nblocks; t++) gather_issue(t, marker_of(t));
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int t = 0; t < nbuf && t < nblocks; t++) mbar_arrive(&S.tile_full[t]);
+        int ids_next = marker_of(nbuf);  // marker ids of the next tile to fetch, one block ahead of their use
         for (int c = 0; c <= npro; c++) {
           mbar_wait(&S.tile_full[c % nbuf], (uint32_t)(c / nbuf) & 1u, dead, a.err);
 #pragma unroll
@@ -498,7 +499,9 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
 #pragma unroll
           for (int s = 0; s < 2; s++) dqv[s] = s < ns ? __uint_as_float(dein[(size_t)((b & 1) * ns + s) * kDeStride + 128]) : 0.0f;
           if (c < nblocks) {
+            if (c >= nbuf) gather_land(c);  // issued one block ago (the first nbuf tiles were counted in the prologue)
             mbar_wait(&S.tile_full[c % nbuf], (uint32_t)(c / nbuf) & 1u, dead, a.err);
+            if (t0) WSTAMP(b, 5);
 #pragma unroll
             for (int mt = 0; mt < 8; mt++) { acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0; }
           }
@@ -529,8 +532,15 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
               }
             }
             if (c < nblocks) g_unit(c, at, l);
+            if (t0 && at == grp) WSTAMP(b, 6);
           }
           if (t0) WSTAMP(b, 4);
+          if (b + nbuf < nblocks) {  // U(b) has read tile b (all atoms committed): its buffer takes tile b + nbuf, needed one block from now
+            mbar_wait(&S.tile_empty[b % nbuf], (uint32_t)(b / nbuf) & 1u, dead, a.err);
+            gather_issue(b + nbuf, ids_next);
+            ids_next = marker_of(b + nbuf + 1);
+            if (t0) WSTAMP(b, 8);
+          }
           if (c < nblocks) g_finish(c);
         }
         // residuals back to HBM (every thread its own rows)
