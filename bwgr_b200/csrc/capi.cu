@@ -89,7 +89,7 @@ struct Fit {
   DevBuf<unsigned int> bar;
   // pipelined sweep (sweep_pipe.cu)
   bool pipe = false;
-  int lookahead = 0, nbuf = 0, sring = 2, nworkers = 0, nc = 1, nband = 1, full_inv = 0, cl = 0, nclusters = 0, fastw = 0;
+  int lookahead = 0, nbuf = 0, sring = 2, nworkers = 0, nc = 1, nband = 1, full_inv = 0, cl = 0, nclusters = 0;
   DevBuf<float> tinv;                   // (I + A L)^-1 of every block of the current sweep (block_inv.cu)
   uint32_t tag = 0;
   DevBuf<unsigned long long> dew, part, cx;
@@ -661,7 +661,7 @@ struct FitSpec {
 
 // Geometry of the pipelined sweep: W streaming CTAs (row slabs of R rows, R <= 512) + one solver CTA, look-ahead D,
 // nbuf X tiles per worker.  False if the shape does not fit one SM's shared memory / TMEM.
-struct PipePlan { int R, W, nbuf, D, sring, full_inv, cl, nclusters, fastw; };
+struct PipePlan { int R, W, nbuf, D, sring, full_inv, cl, nclusters; };
 bool plan_pipe(const bwgr_handle* h, int model, int ns, PipePlan* pl) {
   const char* sw = getenv("BWGR_SWEEP");
   if (sw && !strcmp(sw, "v4")) return false;
@@ -682,22 +682,21 @@ bool plan_pipe(const bwgr_handle* h, int model, int ns, PipePlan* pl) {
   // four dependent 32-marker steps.  (MRR3's centred systems keep the stepwise solve.)
   const char* ti = getenv("BWGR_TINV");
   const int full_inv = model_is_linear(model) && ns == 1 && model != M_MRR && !(ti && !strcmp(ti, "0"));
-  pl->cl = 0; pl->nclusters = 0; pl->fastw = 0;
+  pl->cl = 0; pl->nclusters = 0;
   // Clustered topology (sweep_pipe.cu): thread-block clusters of one solver + seven workers; partial sums and steps travel
   // through distributed shared memory, one L2 hop per block is left (the exchange of the cluster sums between the solvers).
   // Single GPU, at most four systems; BWGR_CLUSTER=0 keeps the flat topology (one solver CTA, two-hop L2 tree).
   const char* ce = getenv("BWGR_CLUSTER");
   if (D >= 1 && h->world <= 1 && h->grid <= 1 && !(ce && !strcmp(ce, "0")) && sweep_pipe_cluster_ok(model, ns, full_inv)) {
-    const char* fe = getenv("BWGR_FASTW");
-    for (int fastw = (ns <= 2 && !(fe && !strcmp(fe, "0"))) ? 1 : 0; fastw >= 0; fastw--)
-      for (int nbuf = D + 2; nbuf >= D + 1 + fastw; nbuf--) {  // the fast worker refills a tile buffer one block before its next use
+    {
+      for (int nbuf = D + 2; nbuf >= D + 1; nbuf--) {
         // rows per worker depend on the number of co-resident clusters, which depends on the shared memory per CTA: iterate
         int C = 18;
         for (int iter = 0; iter < 4 && C >= 2; iter++) {
           const int Wc = 7 * C;
           const int Rc = (int)(((h->ld + Wc - 1) / Wc + 15) / 16 * 16);
           if (Rc > 512) { C = 0; break; }
-          const size_t smem = sweep_pipe_smem(Rc, ns, model, nbuf, 3, full_inv, 1, fastw);
+          const size_t smem = sweep_pipe_smem(Rc, ns, model, nbuf, 3, full_inv, 1);
           if (smem > h->smem_optin - 9216) { C = 0; break; }  // the kernel's static shared memory (barriers, system scalars) is ~9 KB
           const int Cmax = std::min(18, sweep_pipe_max_clusters(model, smem));
           if (Cmax >= C) break;
@@ -707,17 +706,18 @@ bool plan_pipe(const bwgr_handle* h, int model, int ns, PipePlan* pl) {
           const int Wc = 7 * C;
           const int Rc = (int)(((h->ld + Wc - 1) / Wc + 15) / 16 * 16);
           const int NAc = (Rc + 127) / 128;
-          if ((NAc + 1) * N <= 512 && sweep_pipe_smem(Rc, ns, model, nbuf, 3, full_inv, 1, fastw) <= h->smem_optin - 9216) {
-            pl->R = Rc; pl->W = Wc; pl->nbuf = nbuf; pl->D = D; pl->sring = 3; pl->full_inv = full_inv; pl->cl = 1; pl->nclusters = C; pl->fastw = fastw;
+          if ((NAc + 1) * N <= 512 && sweep_pipe_smem(Rc, ns, model, nbuf, 3, full_inv, 1) <= h->smem_optin - 9216) {
+            pl->R = Rc; pl->W = Wc; pl->nbuf = nbuf; pl->D = D; pl->sring = 3; pl->full_inv = full_inv; pl->cl = 1; pl->nclusters = C;
             return true;
           }
         }
       }
+    }
   }
   for (; D >= 0; D--) {
     for (int sring = 3; sring >= 2; sring--)
       for (int nbuf = std::min(8, D + 3); nbuf >= D + 1; nbuf--)
-        if (sweep_pipe_smem(R, ns, model, nbuf, sring, full_inv, 0, 0) <= h->smem_optin - 8192) {
+        if (sweep_pipe_smem(R, ns, model, nbuf, sring, full_inv, 0) <= h->smem_optin - 8192) {
           pl->R = R; pl->W = W; pl->nbuf = nbuf; pl->D = D; pl->sring = sring; pl->full_inv = full_inv;
           return true;
         }
@@ -1022,7 +1022,7 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
     }
     if (f.pipe) {
       f.rows_per_cta = pl.R; f.nworkers = pl.W; f.grid = pl.cl ? pl.nclusters * 8 : pl.W + 1; f.nbuf = pl.nbuf; f.sring = pl.sring; f.lookahead = pl.D; f.full_inv = pl.full_inv; f.nband = pl.D + 1;
-      f.cl = pl.cl; f.nclusters = pl.nclusters; f.fastw = pl.fastw;
+      f.cl = pl.cl; f.nclusters = pl.nclusters;
       f.nc = std::max(1, 16 / ns);
       f.tag = 0;
       const size_t gram_n = (size_t)f.nblocks * kBlk * kBlk * f.nband;
@@ -1128,7 +1128,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
         a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0;
         a.rows_per_cta = f.rows_per_cta; a.nworkers = f.nworkers; a.D = f.lookahead; a.nbuf = f.nbuf; a.sring = f.sring; a.err = h->err.p;
         a.world = h->world; a.rank = h->rank; a.gen0 = h->dist_gen;
-        a.cl = f.cl; a.nclusters = f.nclusters; a.cx = f.cx.p; a.fastw = f.fastw;
+        a.cl = f.cl; a.nclusters = f.nclusters; a.cx = f.cx.p;
         for (int r = 0; r < 8; r++) a.hx[r] = h->hx[r];
         if (h->world > 1) h->dist_gen += (unsigned long long)f.nblocks;
         if (getenv("BWGR_TRACE")) {

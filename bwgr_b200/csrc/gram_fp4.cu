@@ -139,14 +139,15 @@ __global__ void __launch_bounds__(416, 1) gram_fp4_kernel(const uint8_t* __restr
 #pragma unroll
         for (int i = 0; i < 4; i++) dst[i] = (val[i] && kg < nkg && off < ldb) ? __ldg(reinterpret_cast<const uint4*>(colp[i] + off)) : make_uint4(0, 0, 0, 0);
       };
-#pragma unroll
-      for (int s = 0; s < kPf - 1; s++) load_stage(s, q[s]);
+      // loads go out two stages at a time: the four threads of a marker then ask for one whole 128-byte line of its packed column
+      // (two 64-byte visits to the same DRAM page at different times cost two activations)
+      load_stage(0, q[0]); load_stage(1, q[1]);
       for (int kg0 = 0; kg0 < nkg && ok; kg0 += kPf) {
 #pragma unroll
         for (int u = 0; u < kPf; u++) {
           const int kg = kg0 + u;
           if (kg >= nkg || !ok) break;
-          load_stage(kg + kPf - 1, q[(u + kPf - 1) % kPf]);
+          if ((u & 1) == 0) { load_stage(kg + 2, q[(u + 2) % kPf]); load_stage(kg + 3, q[(u + 3) % kPf]); }
           const uint32_t stage = it % kStages, phase = (it / kStages) & 1u;
           ok = mbar_wait(&S->empty[stage], phase ^ 1u, err);
           const uint32_t tbase = smem_u32(tiles + stage * kStageBytes);

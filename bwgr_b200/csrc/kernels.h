@@ -153,10 +153,9 @@ struct PipeArgs {
   // cx = [8][nclusters][nsys][128] per-cluster sums of h, same word format as hred; zeroed before launch
   int cl, nclusters;
   unsigned long long* cx;
-  int fastw;             // clustered topology, nsys <= 2: the worker whose G pass runs on mma.sync inside the epilogue warps
 };
 cudaError_t launch_sweep_pipe(const PipeArgs& a, cudaStream_t st);
-size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring, int full_inv, int cl, int fastw);
+size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring, int full_inv, int cl);
 bool sweep_pipe_cluster_ok(int model, int nsys, int full_inv);
 int sweep_pipe_max_clusters(int model, size_t smem);
 // T_b = (I + A_b L_b)^-1 for every 128-marker block of the sweep (linear rules, one system): [nblocks][128][128] float

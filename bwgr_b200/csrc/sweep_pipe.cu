@@ -182,6 +182,7 @@ constexpr int kClSize = 8;             // CTAs per cluster: one solver + seven w
 constexpr int kClWorkers = kClSize - 1;
 constexpr int kMaxCl = 18;             // clusters whose sums a solver gathers (B200: 15 co-resident clusters of 8 at ~200 KB per CTA)
 constexpr int kDeStride = 132;         // 32-bit words per (parity, system) of a worker's step inbox: 128 steps + the scale (+ pad)
+constexpr int kAtomsPerGroup = 2;      // row atoms whose U epilogue / G issue are handled together (see the worker)
 constexpr int kCommWarp0 = 4;          // clustered solver: warps 4-7 gather the partial sums (they are idle whenever CL is eligible)
 
 // Self-validating 64-bit words of the grid reduction: (signed value << 12) | tag, tag = 1 + (use index of the ring slot) mod 4095
@@ -207,27 +208,22 @@ struct Sync {
   uint64_t raw_ready[3], in_ready[3], solve_done[3], corr_ready[32], de_ready[32][4];
   // clustered topology: step inbox of a worker, partial inbox of a solver, gathered sums ready for the solve warps
   uint64_t de_in[2], h_in[2], h_ready[2];
-  // fast worker: U accumulator of atom `at` complete / drained
-  uint64_t u_done_at[4], u_free_at[4];
+  // per 128-row atom: U accumulator complete (tcgen05.commit) / new residual limbs of the atom written (128 epilogue threads)
+  uint64_t u_done_at[4], el_full_at[4];
   uint32_t tmem_base;
 };
 
-constexpr int kEpiWarps = 12;          // fast worker: epilogue warps (three groups of four TMEM lane quarters)
-struct WLayout { int NA, N, nbuf; size_t xs, el, dl, es, dq, di, lb, red, total; };
-// fast = the clustered worker for ns <= 2 whose G pass runs on mma.sync inside the epilogue warps (no E-limb operand region)
-__host__ __device__ inline WLayout worker_layout(int R, int ns, int nbuf, bool cl = false, bool fast = false) {
+struct WLayout { int NA, N, nbuf; size_t xs, el, dl, es, dq, di, total; };
+__host__ __device__ inline WLayout worker_layout(int R, int ns, int nbuf, bool cl = false) {
   WLayout L;
   L.NA = (R + 127) / 128; L.N = ((4 * ns + 15) / 16) * 16; L.nbuf = nbuf;
   size_t o = 0;
   L.xs = o; o += (size_t)nbuf * L.NA * kAtomBytes;
-  L.el = o; o += fast ? 0 : (size_t)L.NA * (L.N / 8) * 1024;
+  L.el = o; o += (size_t)L.NA * (L.N / 8) * 1024;
   L.dl = o; o += (size_t)2 * (L.N / 8) * 1024;
   L.es = o; o += (size_t)ns * L.NA * 128 * 4;
   L.dq = o; o += (size_t)2 * 32 * 4;
   L.di = o; o += cl ? (size_t)2 * ns * kDeStride * 4 : 0;  // step inbox, written by the cluster's solver (st.async)
-  o = (o + 15) & ~(size_t)15;
-  L.lb = o; o += fast ? (size_t)kEpiWarps * 256 : 0;             // per-warp limb exchange [8 limb columns][32 rows]
-  L.red = o; o += fast ? (size_t)kEpiWarps * ns * 128 * 8 : 0;   // per-warp partial sums of h [warp][system][marker]
   L.total = o;
   return L;
 }
@@ -273,8 +269,8 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
 
   if (tid < ns) sc[tid] = a.sc[tid];
   if (tid == 0) {
-    for (int i = 0; i < 8; i++) { mbar_init(&S.tile_full[i], (CL && a.fastw) ? kEpiWarps * 32 : 128); mbar_init(&S.tile_empty[i], 1); }
-    for (int i = 0; i < 4; i++) { mbar_init(&S.u_done_at[i], 1); mbar_init(&S.u_free_at[i], 128); }
+    for (int i = 0; i < 8; i++) { mbar_init(&S.tile_full[i], 128); mbar_init(&S.tile_empty[i], 1); }
+    for (int i = 0; i < 4; i++) { mbar_init(&S.u_done_at[i], 1); mbar_init(&S.el_full_at[i], 128); }
     mbar_init(&S.dl_full[0], 128); mbar_init(&S.dl_full[1], 128);
     mbar_init(&S.u_done, 1); mbar_init(&S.el_full, 128); mbar_init(&S.g_done, 1); mbar_init(&S.g_empty, 128);
     const int nsw = ns < kSolveWarps ? ns : kSolveWarps;
@@ -295,271 +291,6 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
   if (CL) cluster_sync_all();  // every CTA's barriers exist before the first remote store
 
   if (!is_solver) {
-    if (CL && a.fastw) {
-      // =====================================================================================================
-      // fast worker (clustered topology, ns <= 2).  Per block b:  U(b) on tcgen05 atom by atom (the MN-major descriptor
-      // transposes the tile in hardware); twelve epilogue warps drain the atoms as they complete, update E and -- with the
-      // new limbs still in registers -- multiply their own 32 rows into the partial of block c = b + 1 + D with
-      // mma.sync.m16n8k32 (K = the warp's 32 rows): no second tcgen05 pass, no hand-over between the two passes.
-      // =====================================================================================================
-      const WLayout L = worker_layout(a.rows_per_cta, ns, a.nbuf, true, true);
-      const int R = a.rows_per_cta, NA = L.NA, N = 16, RS = NA * 128, nbuf = L.nbuf;
-      const int row0 = widx * R;
-      const uint32_t* dein = reinterpret_cast<const uint32_t*>(base + L.di);
-      const uint32_t hin_u32 = smem_u32(base) + (uint32_t)solver_layout(ns, model_is_gibbs(MODEL), false, a.sring, true).hi;
-      unsigned char* Xs = base + L.xs;
-      unsigned char* DL = base + L.dl;
-      float* Es = reinterpret_cast<float*>(base + L.es);
-      unsigned char* lbuf = base + L.lb;
-      long long* red = reinterpret_cast<long long*>(base + L.red);
-      {
-        uint4* z = reinterpret_cast<uint4*>(base);
-        const int nz = (int)(L.es >> 4);
-        for (int i = tid; i < nz; i += kT) z[i] = make_uint4(0, 0, 0, 0);
-        for (int i = tid; i < kEpiWarps * 256 / 16; i += kT) reinterpret_cast<uint4*>(lbuf)[i] = make_uint4(0, 0, 0, 0);
-      }
-      for (int s = 0; s < ns; s++)
-        for (int i = tid; i < RS; i += kT) {
-          const int r = row0 + i;
-          Es[s * RS + i] = (i < R && r < a.g.ld) ? a.e[(size_t)s * a.g.ld + r] : 0.0f;
-        }
-      const uint32_t tmem_cols = 64;  // NA (<= 4) accumulators of N = 16 columns
-      if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tmem_base = S.tmem_base;
-      const bool tracing = a.trace != nullptr;
-      bool bad = false;
-#define WSTAMP(blk, k) do { if (tracing) { long long* tp_ = a.trace + ((size_t)blockIdx.x * nblocks + (blk)) * 32 + (k); tp_[0] = (long long)gtimer(); tp_[16] = clock64(); } } while (0)
-      const int npro = (D < nblocks - 1 ? D : nblocks - 1);
-      if (warp == 0) {
-        // ------------------------------------------------------------------ tcgen05 issuer: U(b), one commit per atom
-        const uint32_t idesc_u = idesc_i8(N, 1);
-        for (int b = 0; b < nblocks; b++) {
-          const unsigned char* Xt = Xs + (size_t)(b % nbuf) * NA * kAtomBytes;
-          mbar_wait(&S.tile_full[b % nbuf], (uint32_t)(b / nbuf) & 1u, dead, a.err);  // long complete (G(b) read this tile two blocks ago)
-          mbar_wait(&S.dl_full[b & 1], (uint32_t)(b >> 1) & 1u, dead, a.err);
-          if (tracing && lane == 0) WSTAMP(b, 9);
-          const uint64_t bd = desc_k_sw128(smem_u32(DL + (size_t)(b & 1) * (N / 8) * 1024));
-          for (int at = 0; at < NA; at++) {
-            if (b > 0) mbar_wait(&S.u_free_at[at], (uint32_t)(b - 1) & 1u, dead, a.err);  // the epilogue has drained this accumulator
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
-              const uint64_t ad = desc_mn_sw128(smem_u32(Xt + (size_t)at * kAtomBytes));
-#pragma unroll
-              for (int k4 = 0; k4 < 4; k4++)
-                umma_i8(tmem_base + (uint32_t)(at * N), ad + (uint64_t)(k4 * (4096 >> 4)), bd + (uint64_t)(2 * k4), idesc_u, k4 != 0);
-              umma_commit(&S.u_done_at[at]);
-              if (at == NA - 1) umma_commit(&S.tile_empty[b % nbuf]);
-            }
-            __syncwarp();
-          }
-          if (tracing && lane == 0) WSTAMP(b, 2);
-        }
-      } else if (warp < 5 || warp > 7) {
-        // ------------------------------------------------------------------ epilogue warps: three groups x four TMEM lane quarters
-        const int ew = warp <= 4 ? warp - 1 : warp - 4;       // 0..11
-        const int grp = ew >> 2;                              // atoms at with at % 3 == grp
-        const int quarter = warp & 3;
-        const int q = quarter * 32 + lane;                    // row inside an atom = TMEM lane
-        const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
-        const bool t0 = tracing && warp == 1 && lane == 0;
-        const int g8 = lane >> 2, t4 = lane & 3;
-        unsigned char* lb = lbuf + ew * 256;
-        long long* rw = red + (size_t)ew * ns * 128;
-        // byte offsets of this lane's A fragments inside one atom of a tile (rows 32*quarter + 4*t4 .., markers g8 / g8 + 8)
-        const int kb0 = quarter * 32 + 4 * t4;
-        const uint32_t offA = (uint32_t)(g8 * 128 + ((((kb0 >> 4) ^ g8) & 7) << 4) + (kb0 & 15));
-        const uint32_t offB = (uint32_t)(g8 * 128 + (((((kb0 + 16) >> 4) ^ g8) & 7) << 4) + (kb0 & 15));
-        // ---- X tile gather, spread over the twelve epilogue warps (a single warp issues cp.async far too slowly: 128 per tile).
-        // Warp ew brings markers ew, ew + 12, ... of a tile: 16-byte chunk `lane` of the row slab of each (SWIZZLE_128B layout the
-        // U pass reads through its MN-major descriptor).  Tile t + nbuf goes into tile t's buffer as soon as U(t) has read it.
-        const int nchunk = R >> 4;
-        const bool gact = lane < nchunk && row0 + 16 * lane < a.g.ld;
-        const uint32_t choff = (uint32_t)((lane >> 3) * kAtomBytes + ((lane & 7) << 4));
-        const int8_t* xrow = a.g.x8 + row0 + 16 * lane;
-        const uint64_t pol = policy_evict_first();
-        auto marker_of = [&](int t) { const int pos = t * 128 + ew + kEpiWarps * lane; return (t < nblocks && lane < 11 && ew + kEpiWarps * lane < 128 && pos < p) ? a.perm[pos] : -1; };
-        auto gather_issue = [&](int t, int ids) {  // ids: lane i holds the marker id of tile row ew + 12 i
-          const uint32_t dst = smem_u32(Xs + (size_t)(t % nbuf) * NA * kAtomBytes);
-#pragma unroll
-          for (int i = 0; i < 11; i++) {
-            const int m = ew + kEpiWarps * i;
-            const int j = __shfl_sync(0xffffffffu, ids, i);
-            if (m < 128 && lane < nchunk) {
-              const uint32_t dm = dst + (uint32_t)(m * 128) + (choff ^ (uint32_t)((m & 7) << 4));
-              const bool ok = gact && j >= 0;
-              cp_async16_stream(dm, ok ? xrow + (int64_t)j * a.g.ld : a.g.x8, ok ? 16u : 0u, pol);
-            }
-          }
-          asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        auto gather_land = [&](int t) {  // this warp's share of tile t has landed -> visible to the tensor core -> count it on the tile's barrier
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(&S.tile_full[t % nbuf]);
-        };
-        int acc[8][4];
-        auto g_unit = [&](int c, int at, const int (&l)[8]) {
-          __syncwarp();
-#pragma unroll
-          for (int n = 0; n < 8; n++) if (n < 4 * ns) lb[n * 32 + lane] = (unsigned char)l[n];
-          __syncwarp();
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(lb + g8 * 32 + 4 * t4);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(lb + g8 * 32 + 16 + 4 * t4);
-          const unsigned char* Xa = Xs + ((size_t)(c % nbuf) * NA + at) * kAtomBytes;
-#pragma unroll
-          for (int mt = 0; mt < 8; mt++) {
-            const uint32_t a0 = *reinterpret_cast<const uint32_t*>(Xa + mt * 2048 + offA);
-            const uint32_t a1 = *reinterpret_cast<const uint32_t*>(Xa + mt * 2048 + 1024 + offA);
-            const uint32_t a2 = *reinterpret_cast<const uint32_t*>(Xa + mt * 2048 + offB);
-            const uint32_t a3 = *reinterpret_cast<const uint32_t*>(Xa + mt * 2048 + 1024 + offB);
-            asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                         : "+r"(acc[mt][0]), "+r"(acc[mt][1]), "+r"(acc[mt][2]), "+r"(acc[mt][3])
-                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-          }
-        };
-        auto limbs_of = [&](float e, float eqi, int* l) {
-          const float sv = e * eqi;
-          if (!(fabsf(sv) <= 1073741824.0f)) bad = true;
-          split_limbs(__float2int_rn(sv), l[0], l[1], l[2], l[3]);
-        };
-        auto g_finish = [&](int c) {
-          // this warp's accumulators -> one 64-bit sum per (system, marker); twelve warps -> shared memory -> the first group adds
-          // them up and sends the worker's partial to the cluster's solver
-          named_bar(3, kEpiWarps * 32);  // the previous block's partials have been read
-#pragma unroll
-          for (int mt = 0; mt < 8; mt++) {
-            long long v0 = (t4 & 1) ? ((long long)acc[mt][0] << 16) + ((long long)acc[mt][1] << 24) : (long long)acc[mt][0] + ((long long)acc[mt][1] << 8);
-            long long v1 = (t4 & 1) ? ((long long)acc[mt][2] << 16) + ((long long)acc[mt][3] << 24) : (long long)acc[mt][2] + ((long long)acc[mt][3] << 8);
-            v0 += __shfl_xor_sync(0xffffffffu, v0, 1);
-            v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
-            const int sy = t4 >> 1;
-            if (!(t4 & 1) && sy < ns) { rw[sy * 128 + 16 * mt + g8] = v0; rw[sy * 128 + 16 * mt + g8 + 8] = v1; }
-          }
-          named_bar(2, kEpiWarps * 32);
-          if (grp == 0) {
-            const uint32_t rdst = mapa_u32(hin_u32 + (uint32_t)((((c & 1) * kClWorkers + (crank - 1)) * ns) * 128 + q) * 8u, 0u);
-            const uint32_t rbar = mapa_u32(smem_u32(&S.h_in[c & 1]), 0u);
-            for (int s = 0; s < ns; s++) {
-              long long sum = 0;
-#pragma unroll
-              for (int w = 0; w < kEpiWarps; w++) sum += red[((size_t)w * ns + s) * 128 + q];
-              st_async_u64(rdst + (uint32_t)s * 1024u, (unsigned long long)sum, rbar);
-            }
-            if (t0) WSTAMP(c, 7);
-          }
-        };
-        // ---- the first nbuf tiles, then the partials of the first blocks from the residuals as loaded
-        for (int t = 0; t < nbuf && t < nblocks; t++) gather_issue(t, marker_of(t));
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int t = 0; t < nbuf && t < nblocks; t++) mbar_arrive(&S.tile_full[t]);
-        int ids_next = marker_of(nbuf);  // marker ids of the next tile to fetch, one block ahead of their use
-        for (int c = 0; c <= npro; c++) {
-          mbar_wait(&S.tile_full[c % nbuf], (uint32_t)(c / nbuf) & 1u, dead, a.err);
-#pragma unroll
-          for (int mt = 0; mt < 8; mt++) { acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0; }
-          for (int at = grp; at < NA; at += 3) {
-            if (at * 128 + quarter * 32 >= R) continue;
-            const int i = at * 128 + q;
-            int l[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (i < R) {
-#pragma unroll
-              for (int s = 0; s < 2; s++) if (s < ns) limbs_of(Es[s * RS + i], sc[s].e_qinv, l + 4 * s);
-            }
-            g_unit(c, at, l);
-          }
-          g_finish(c);
-        }
-        for (int b = 0; b < nblocks; b++) {
-          const int c = b + 1 + D;
-          mbar_wait(&S.de_in[b & 1], (uint32_t)(b >> 1) & 1u, dead, a.err);
-          if (t0) WSTAMP(b, 0);
-          if (grp == 0) {  // the limbs of the step of marker q: B operand of U(b)
-            unsigned char* dl = DL + (size_t)(b & 1) * (N / 8) * 1024;
-            for (int s = 0; s < ns; s++) {
-              int l0, l1, l2, l3;
-              split_limbs(dead ? 0 : (int)dein[(size_t)((b & 1) * ns + s) * kDeStride + q], l0, l1, l2, l3);
-              dl[sw128_off(4 * s + 0, q)] = (unsigned char)l0; dl[sw128_off(4 * s + 1, q)] = (unsigned char)l1;
-              dl[sw128_off(4 * s + 2, q)] = (unsigned char)l2; dl[sw128_off(4 * s + 3, q)] = (unsigned char)l3;
-            }
-            // this inbox slot is next used by block b + 2, whose step cannot be sent before this worker's partial of b + 2
-            if (q == 0 && b + 2 < nblocks) mbar_expect_tx(&S.de_in[b & 1], (uint32_t)(ns * 129 * 4));
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&S.dl_full[b & 1]);
-            if (t0) WSTAMP(b, 1);
-          }
-          float dqv[2];
-#pragma unroll
-          for (int s = 0; s < 2; s++) dqv[s] = s < ns ? __uint_as_float(dein[(size_t)((b & 1) * ns + s) * kDeStride + 128]) : 0.0f;
-          if (c < nblocks) {
-            if (c >= nbuf) gather_land(c);  // issued one block ago (the first nbuf tiles were counted in the prologue)
-            mbar_wait(&S.tile_full[c % nbuf], (uint32_t)(c / nbuf) & 1u, dead, a.err);
-            if (t0) WSTAMP(b, 5);
-#pragma unroll
-            for (int mt = 0; mt < 8; mt++) { acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0; }
-          }
-          for (int at = grp; at < NA; at += 3) {
-            mbar_wait(&S.u_done_at[at], (uint32_t)b & 1u, dead, a.err);
-            if (t0 && at == grp) WSTAMP(b, 3);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            int u[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-#pragma unroll
-            for (int s = 0; s < 2; s++) if (s < ns) tmem_ld4(tmem_base + tlane + (uint32_t)(at * N + 4 * s), u[s][0], u[s][1], u[s][2], u[s][3]);
-            tmem_ld_wait();
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&S.u_free_at[at]);
-            if (at * 128 + quarter * 32 >= R) continue;  // rows beyond the slab: nothing to update, nothing to add
-            const int i = at * 128 + q;
-            int l[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (i < R) {
-#pragma unroll
-              for (int s = 0; s < 2; s++) {
-                if (s < ns) {
-                  // uq * dq in two exact float pieces (uq = 2^24 hi + lo, |hi| < 2^22, 0 <= lo < 2^24; dq is a power of two)
-                  const long long uq = combine_limbs(u[s][0], u[s][1], u[s][2], u[s][3]);
-                  const float hi = (float)(int)(uq >> 24) * 16777216.0f, lo = (float)(int)(uq & 0xFFFFFF);
-                  const float e = fmaf(-lo, dqv[s], fmaf(-hi, dqv[s], Es[s * RS + i]));
-                  Es[s * RS + i] = e;
-                  limbs_of(e, sc[s].e_qinv, l + 4 * s);
-                }
-              }
-            }
-            if (c < nblocks) g_unit(c, at, l);
-            if (t0 && at == grp) WSTAMP(b, 6);
-          }
-          if (t0) WSTAMP(b, 4);
-          if (b + nbuf < nblocks) {  // U(b) has read tile b (all atoms committed): its buffer takes tile b + nbuf, needed one block from now
-            mbar_wait(&S.tile_empty[b % nbuf], (uint32_t)(b / nbuf) & 1u, dead, a.err);
-            gather_issue(b + nbuf, ids_next);
-            ids_next = marker_of(b + nbuf + 1);
-            if (t0) WSTAMP(b, 8);
-          }
-          if (c < nblocks) g_finish(c);
-        }
-        // residuals back to HBM (every thread its own rows)
-        for (int at = grp; at < NA; at += 3) {
-          const int i = at * 128 + q, r = row0 + i;
-          if (i < R && r < a.g.ld) for (int s = 0; s < ns; s++) a.e[(size_t)s * a.g.ld + r] = Es[s * RS + i];
-        }
-      }
-      if (bad) atomicExch(a.err, 4);
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
-      if (warp == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
-      }
-#undef WSTAMP
-      cluster_sync_all();
-      return;
-    }
     // =====================================================================================================
     // worker
     // =====================================================================================================
@@ -615,24 +346,31 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
     if (warp == 0) {
       // ------------------------------------------------------------------ tcgen05 issuer
       const uint32_t idesc_g = idesc_i8(N, 0), idesc_u = idesc_i8(N, 1);
-      auto issue_g = [&](int c) {
+      // The row atoms of the slab are handled in groups of two (kAtomsPerGroup): the U pass commits group by group, the epilogue
+      // updates E and writes the new limbs group by group (both atoms of a group in flight at once: the epilogue is latency-bound),
+      // and the MMAs of G(c) over a group are issued as soon as that group's limbs are in shared memory (el_full_at[g]; `use` = use
+      // number of those barriers, < 0 = the limbs written at start-up).  The two tensor-core passes and the epilogue overlap by halves.
+      auto issue_g = [&](int c, int use) {
         const unsigned char* Xt = Xs + (size_t)(c % nbuf) * NA * kAtomBytes;
         mbar_wait(&S.tile_full[c % nbuf], (uint32_t)(c / nbuf) & 1u, dead, a.err);
         if (c > 0) mbar_wait(&S.g_empty, (uint32_t)(c - 1) & 1u, dead, a.err);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (elect_one()) {
-          for (int at = 0; at < NA; at++) {
-            const uint64_t ad = desc_k_sw128(smem_u32(Xt + (size_t)at * kAtomBytes));
-            const uint64_t bd = desc_k_sw128(smem_u32(EL + (size_t)at * (N / 8) * 1024));
+        for (int g = 0; g * kAtomsPerGroup < NA; g++) {
+          if (use >= 0) mbar_wait(&S.el_full_at[g], (uint32_t)use & 1u, dead, a.err);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
+            for (int at = g * kAtomsPerGroup; at < NA && at < (g + 1) * kAtomsPerGroup; at++) {
+              const uint64_t ad = desc_k_sw128(smem_u32(Xt + (size_t)at * kAtomBytes));
+              const uint64_t bd = desc_k_sw128(smem_u32(EL + (size_t)at * (N / 8) * 1024));
 #pragma unroll
-            for (int k4 = 0; k4 < 4; k4++) umma_i8(tmem_g, ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), idesc_g, (at | k4) != 0);
+              for (int k4 = 0; k4 < 4; k4++) umma_i8(tmem_g, ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), idesc_g, (at | k4) != 0);
+            }
+            if ((g + 1) * kAtomsPerGroup >= NA) umma_commit(&S.g_done);
           }
-          umma_commit(&S.g_done);
+          __syncwarp();
         }
-        __syncwarp();
       };
       const int npro = (D < nblocks - 1 ? D : nblocks - 1);
-      for (int c = 0; c <= npro; c++) issue_g(c);
+      for (int c = 0; c <= npro; c++) issue_g(c, -1);
       for (int b = 0; b < nblocks; b++) {
         const unsigned char* Xt = Xs + (size_t)(b % nbuf) * NA * kAtomBytes;
         mbar_wait(&S.dl_full[b & 1], (uint32_t)(b >> 1) & 1u, dead, a.err);
@@ -645,17 +383,15 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
 #pragma unroll
             for (int k4 = 0; k4 < 4; k4++)
               umma_i8(tmem_base + (uint32_t)(at * N), ad + (uint64_t)(k4 * (4096 >> 4)), bd + (uint64_t)(2 * k4), idesc_u, k4 != 0);
+            if ((at % kAtomsPerGroup) == kAtomsPerGroup - 1 || at == NA - 1) umma_commit(&S.u_done_at[at / kAtomsPerGroup]);  // the epilogue starts on this group while the next one is multiplied
           }
-          umma_commit(&S.u_done);
           umma_commit(&S.tile_empty[b % nbuf]);
           if (tracing) WSTAMP(b, 2);
         }
         __syncwarp();
         const int c = b + 1 + D;
         if (c < nblocks) {
-          mbar_wait(&S.el_full, (uint32_t)b & 1u, dead, a.err);
-          if (tracing && lane == 0) WSTAMP(b, 9);
-          issue_g(c);
+          issue_g(c, b);
           if (tracing && lane == 0) WSTAMP(b, 5);
         }
       }
@@ -734,39 +470,42 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
           if (t0) WSTAMP(b, 1);
         }
         // ---- E_slab -= X_b dE_b, then the limbs of the new residual (B operand of the next G pass)
-        mbar_wait(&S.u_done, (uint32_t)b & 1u, dead, a.err);
-        if (t0) WSTAMP(b, 3);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int s = 0; s < ns; s++) {
-          // all atoms of this thread's TMEM lane in flight at once: up to four independent dependency chains
-          int acc[4][4];
+        // group by group (two row atoms each), as the issuer commits them
+        for (int g = 0; g * kAtomsPerGroup < NA; g++) {
+          mbar_wait(&S.u_done_at[g], (uint32_t)b & 1u, dead, a.err);
+          if (t0 && g == 0) WSTAMP(b, 3);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int at0 = g * kAtomsPerGroup;
+          for (int s = 0; s < ns; s++) {
+            int acc[kAtomsPerGroup][4];
 #pragma unroll
-          for (int at = 0; at < 4; at++)
-            if (at < NA) tmem_ld4(tmem_base + tlane + (uint32_t)(at * N + 4 * s), acc[at][0], acc[at][1], acc[at][2], acc[at][3]);
-          tmem_ld_wait();
-          const float dqv = dqs[(b & 1) * 32 + s], eqi = sc[s].e_qinv;
+            for (int u = 0; u < kAtomsPerGroup; u++)
+              if (at0 + u < NA) tmem_ld4(tmem_base + tlane + (uint32_t)((at0 + u) * N + 4 * s), acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+            tmem_ld_wait();
+            const float dqv = dqs[(b & 1) * 32 + s], eqi = sc[s].e_qinv;
 #pragma unroll
-          for (int at = 0; at < 4; at++) {
-            const int i = at * 128 + q;
-            if (at < NA && i < R) {
-              // uq * dq in two exact float pieces (uq = 2^24 hi + lo, |hi| < 2^22, 0 <= lo < 2^24; dq is a power of two)
-              const long long uq = combine_limbs(acc[at][0], acc[at][1], acc[at][2], acc[at][3]);
-              const float hi = (float)(int)(uq >> 24) * 16777216.0f, lo = (float)(int)(uq & 0xFFFFFF);
-              const float e = fmaf(-lo, dqv, fmaf(-hi, dqv, Es[s * RS + i]));
-              Es[s * RS + i] = e;
-              const float sv = e * eqi;
-              if (!(fabsf(sv) <= 1073741824.0f)) bad = true;
-              int l0, l1, l2, l3;
-              split_limbs(__float2int_rn(sv), l0, l1, l2, l3);
-              unsigned char* atom = EL + (size_t)at * (N / 8) * 1024;
-              atom[sw128_off(4 * s + 0, q)] = (unsigned char)l0; atom[sw128_off(4 * s + 1, q)] = (unsigned char)l1;
-              atom[sw128_off(4 * s + 2, q)] = (unsigned char)l2; atom[sw128_off(4 * s + 3, q)] = (unsigned char)l3;
+            for (int u = 0; u < kAtomsPerGroup; u++) {
+              const int at = at0 + u, i = at * 128 + q;
+              if (at < NA && i < R) {
+                // uq * dq in two exact float pieces (uq = 2^24 hi + lo, |hi| < 2^22, 0 <= lo < 2^24; dq is a power of two)
+                const long long uq = combine_limbs(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+                const float hi = (float)(int)(uq >> 24) * 16777216.0f, lo = (float)(int)(uq & 0xFFFFFF);
+                const float e = fmaf(-lo, dqv, fmaf(-hi, dqv, Es[s * RS + i]));
+                Es[s * RS + i] = e;
+                const float sv = e * eqi;
+                if (!(fabsf(sv) <= 1073741824.0f)) bad = true;
+                int l0, l1, l2, l3;
+                split_limbs(__float2int_rn(sv), l0, l1, l2, l3);
+                unsigned char* atom = EL + (size_t)at * (N / 8) * 1024;
+                atom[sw128_off(4 * s + 0, q)] = (unsigned char)l0; atom[sw128_off(4 * s + 1, q)] = (unsigned char)l1;
+                atom[sw128_off(4 * s + 2, q)] = (unsigned char)l2; atom[sw128_off(4 * s + 3, q)] = (unsigned char)l3;
+              }
             }
           }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(&S.el_full_at[g]);
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(&S.el_full);
         if (t0) WSTAMP(b, 4);
         const int c = b + 1 + D;
         if (c < nblocks) g_epilogue(c);
@@ -898,7 +637,7 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
   const long long* hin = reinterpret_cast<const long long*>(base + L.hi);
   long long* hsum = reinterpret_cast<long long*>(base + L.hs);
   // a worker's step inbox sits at the same shared-window offset in every CTA of this launch
-  const uint32_t dein_u32 = smem_u32(base) + (uint32_t)worker_layout(a.rows_per_cta, ns, a.nbuf, CL, CL && a.fastw).di;
+  const uint32_t dein_u32 = smem_u32(base) + (uint32_t)worker_layout(a.rows_per_cta, ns, a.nbuf, CL).di;
   const bool centred = a.sx != nullptr;
   const float inv_n = 1.0f / (float)a.g.n;
   if (tid < 64) cs[tid] = 0.0f;
@@ -1681,8 +1420,8 @@ int max_clusters_model(size_t smem) {
 }  // namespace
 
 // Shared memory of one CTA (both roles use the same launch) and the largest tile ring that fits.
-size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring, int full_inv, int cl, int fastw) {
-  const size_t w = worker_layout(rows_per_cta, nsys, nbuf, cl != 0, cl != 0 && fastw != 0).total;
+size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring, int full_inv, int cl) {
+  const size_t w = worker_layout(rows_per_cta, nsys, nbuf, cl != 0).total;
   const size_t s = solver_layout(nsys, model_is_gibbs(model), !full_inv && pipe_use_inv(model, nsys), sring, cl != 0).total;
   return (w > s ? w : s) + 1024;
 }
@@ -1720,7 +1459,7 @@ int sweep_pipe_max_clusters(int model, size_t smem) {
 }
 
 cudaError_t launch_sweep_pipe(const PipeArgs& a, cudaStream_t st) {
-  const size_t smem = sweep_pipe_smem(a.rows_per_cta, a.nsys, a.model, a.nbuf, a.sring, a.tinv != nullptr, a.cl, a.fastw);
+  const size_t smem = sweep_pipe_smem(a.rows_per_cta, a.nsys, a.model, a.nbuf, a.sring, a.tinv != nullptr, a.cl);
   const int model = a.model;
 #define BWGR_CALL(M) launch_model<M>(a, smem, st)
   BWGR_MODEL_SWITCH(BWGR_CALL)

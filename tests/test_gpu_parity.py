@@ -776,3 +776,22 @@ def test_emml_marker_weights(tpod, path):
         out = bw.emML(y, g, D=D, it=40)
     _close_em(out, ref, "emML", ref64, check_its=False)
     assert np.abs(out["b"] - bw.emML(y, gen, it=40)["b"]).max() > 1e-2 * np.abs(ref["b"]).max()  # the weights matter
+
+
+@pytest.mark.parametrize("env", [{"BWGR_CLUSTER": "0"}, {"BWGR_CLUSTER": "0", "BWGR_LOOKAHEAD": "0"}, {"BWGR_TINV": "0"}, {"BWGR_SWEEP": "v4"},
+                                 {"BWGR_GRAM": "fp8"}, {"BWGR_GRAM": "i8"}, {"BWGR_GRAM": "simt"}, {"BWGR_TMA": "1", "BWGR_GRAM": "fp8"},
+                                 {"BWGR_GRAM_PACKED": "0", "BWGR_GRAM": "fp8"}])
+def test_every_kernel_variant_behind_a_switch(monkeypatch, env):
+    """Every alternative kernel the library can select (flat topology, no look-ahead, stepwise in-block solve, the v4 sweep, the
+    E4M3 / int8 / SIMT Gram kernels, the TMA gather4 and unpacked producers) fits the same data to the same parity bar as the default."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    X, y = synth(3000, 2000, seed=3)
+    ref = O.em("emRR", y, X.astype(np.float32), it=6)
+    ref64 = O.em("emRR", y, X.astype(np.float32), it=6, use_double=True)
+    with bw.Genotypes(X, path=2) as g:
+        out = bw.emRR(y, g, it=6)
+        outc = bw.em_fit("emBC", y, g, it=6)
+    _close_em(out, ref, "emRR", ref64)
+    refc = O.em("emBC", y, X.astype(np.float32), it=6)
+    _close_em(outc, refc, "emBC", O.em("emBC", y, X.astype(np.float32), it=6, use_double=True))
