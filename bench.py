@@ -148,9 +148,9 @@ class ClockSampler:
 
 def ncu_traffic(kernel, n, p):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu capture of the same
-    workload shape (profiles/r1_traffic.json, written by tools/ncu_traffic.py); None if there is no capture for it."""
+    workload shape (profiles/r2_traffic.json, written by tools/ncu_traffic.py); None if there is no capture for it."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         e = d.get(kernel)
         if e and e.get("n") == n:
             return e["bytes_per_launch"] * (p / e["p"])  # captured on a p-slice of the same n; traffic is linear in p
@@ -376,12 +376,12 @@ def main():
     gram_ms = prof["gram"]["ms"] / max(1, prof["gram"]["launches"])
     epi_ms = prof["epilogue"]["ms"] / max(1, prof["epilogue"]["launches"])
     inv_ms = prof["block_inverse"]["ms"] / max(1, prof["block_inverse"]["launches"])
-    dom = "sweep_pipe_kernel" if sweep_ms >= gram_ms else "gram_tc_kernel"
+    dom = "sweep_pipe_kernel" if sweep_ms >= gram_ms else "gram_fp4_kernel"
     dom_ms = max(sweep_ms, gram_ms)
     achieved = n * p / (dom_ms * 1e-3) / 1e9  # per GPU: every rank streams its own n x p bytes per launch
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": args.traffic if args.traffic is not None else ncu_traffic(dom, n, p), "kernel": dom, "peak_source": peak_src, "algorithmic_bytes_per_launch": n * p,
-                "kernel_ms": {"sweep_pipe_kernel": sweep_ms, "gram_tc_kernel": gram_ms, "block_inverse_kernel": inv_ms, "epilogue_kernel": epi_ms},
+                "kernel_ms": {"sweep_pipe_kernel": sweep_ms, "gram_fp4_kernel": gram_ms, "block_inverse_kernel": inv_ms, "epilogue_kernel": epi_ms},
                 "whole_sweep_frac": (n * p / (ms / args.steps * 1e-3) / 1e9) / hbm_peak}
     # one marker update = one marker visited on one 50k-row shard: N = 1 -> p per sweep; row-sharded -> N * p per sweep of the ONE fit
     value = world * p * args.steps / (ms * 1e-3)

@@ -494,14 +494,23 @@ static int load_f64_common(bwgr_handle* h, const double* X, int64_t n, int64_t p
   const int64_t ldd = h->ld;
   const int64_t chunk_cols = std::max<int64_t>(1, std::min<int64_t>(p, ((int64_t)32 << 20) / ldd));
   const size_t chunk_bytes = (size_t)chunk_cols * ldd;
-  int8_t* stage[2] = {nullptr, nullptr};
-  cudaEvent_t done[2] = {nullptr, nullptr};
-  for (int i = 0; i < 2; i++) {
-    if (cudaMallocHost(reinterpret_cast<void**>(&stage[i]), chunk_bytes) != cudaSuccess || cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) {
-      for (int k = 0; k < 2; k++) { if (stage[k]) cudaFreeHost(stage[k]); if (done[k]) cudaEventDestroy(done[k]); }
+  // the two pinned staging buffers are kept for the life of the process (cudaMallocHost / cudaFreeHost cost tens of milliseconds
+  // each and would otherwise be paid by every emRR(y, gen) call of the drop-in, which creates and destroys its store)
+  static int8_t* s_stage[2] = {nullptr, nullptr};
+  static size_t s_stage_bytes = 0;
+  if (s_stage_bytes < chunk_bytes) {
+    for (int i = 0; i < 2; i++) { if (s_stage[i]) cudaFreeHost(s_stage[i]); s_stage[i] = nullptr; }
+    s_stage_bytes = 0;
+    if (cudaMallocHost(reinterpret_cast<void**>(&s_stage[0]), chunk_bytes) != cudaSuccess || cudaMallocHost(reinterpret_cast<void**>(&s_stage[1]), chunk_bytes) != cudaSuccess) {
+      for (int i = 0; i < 2; i++) { if (s_stage[i]) cudaFreeHost(s_stage[i]); s_stage[i] = nullptr; }
       return fail(BWGR_ERR_CUDA, "cudaMallocHost(staging) failed");
     }
+    s_stage_bytes = chunk_bytes;
   }
+  int8_t* stage[2] = {s_stage[0], s_stage[1]};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2; i++)
+    if (cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaEventCreate failed");
   unsigned hc = std::thread::hardware_concurrency();
   const int nthr = (int)std::max(1u, std::min(hc ? hc : 4u, 32u));
   std::atomic<int> bad(0);
@@ -522,7 +531,7 @@ static int load_f64_common(bwgr_handle* h, const double* X, int64_t n, int64_t p
     if (ce == cudaSuccess) ce = cudaEventRecord(done[sb], h->stream);
   }
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
-  for (int i = 0; i < 2; i++) { cudaFreeHost(stage[i]); cudaEventDestroy(done[i]); }
+  for (int i = 0; i < 2; i++) cudaEventDestroy(done[i]);
   if (ce != cudaSuccess) return fail(BWGR_ERR_CUDA, "bwgr_geno_load_f64: %s", cudaGetErrorString(ce));
   if (bad.load()) return fail(BWGR_ERR_ARG, "bwgr_geno_load_f64: non-integer or out-of-range genotype");
   if (allow_offset) for (double v : h->col_offset) if (v != 0.0) { h->has_offset = true; break; }

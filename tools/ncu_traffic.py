@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Extract per-launch DRAM traffic and duration of the kernels of an ncu --set full capture into profiles/r1_traffic.json.
+"""Extract per-launch DRAM traffic and duration of the kernels of an ncu --set full capture into profiles/r2_traffic.json.
 
 usage: python tools/ncu_traffic.py report.ncu-rep n p   (n, p = the workload shape the capture was taken on)"""
 import csv
@@ -18,7 +18,7 @@ for r in rows[2:]:
     d = dict(zip(hdr, r))
     u = dict(zip(hdr, units))
     name = d["Kernel Name"]
-    key = "sweep_pipe_kernel" if "sweep_pipe" in name else "gram_tc_kernel" if "gram_tc" in name else "epilogue_kernel" if "epilogue" in name else None
+    key = "sweep_pipe_kernel" if "sweep_pipe" in name else "gram_fp4_kernel" if "gram_fp4" in name else "gram_tc_kernel" if "gram_tc" in name else "epilogue_kernel" if "epilogue" in name else None
     if key is None or key in res:
         continue
 
@@ -30,6 +30,6 @@ for r in rows[2:]:
     res[key] = {"n": n, "p": p, "bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
                 "dram_read": val("dram__bytes_read.sum"), "dram_write": val("dram__bytes_write.sum"),
                 "duration_ns_under_ncu": val("gpu__time_duration.sum"), "kernel": name[:80]}
-path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "r1_traffic.json")
+path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "r2_traffic.json")
 json.dump(res, open(path, "w"), indent=1)
 print(json.dumps(res, indent=1))
