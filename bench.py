@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--cpu-sweeps", type=int, default=10)
     ap.add_argument("--cpu-sweeps-main", type=int, default=150, help="sweeps of the cpu_baseline sample of the main arm (~15 s)")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch of the dominant kernel from an ncu capture (profiles/)")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE.json configs[k-1]... 1 (default) = the metric's configuration (emRR 50k x 50k); 2 wgr BayesB 10k x 50k; "
+                         "3 MRR3 50k x 50k x 20 traits; 4 5-fold x 20-trait emBC fits; 5 row shards of 62500 x 100k per GPU (500k x 100k over 8)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -283,13 +286,153 @@ def row_sharded_parity(bw, dist, dev, local, rank, world, stream):
     return res
 
 
+def run_config(args, rank, world, local):
+    """One JSON line for BASELINE.json configs 2-4 (`--config K`): the chain / multi-trait / batched-fold callers of the marker loop
+    at their named shapes.  A step is one pass over all p markers (one Gibbs iteration, one MRR3 sweep, one sweep of every fit);
+    K steps are timed as call(W + K) - call(W) with CUDA events on the library's stream, so set-up and read-back cancel."""
+    import torch
+    import torch.distributed as dist
+
+    import bwgr_b200 as bw
+    from oracle import oracle as O
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg, K, W = args.config, args.steps, max(3, args.warmup)
+    n, p = (50000, 50000) if cfg == 3 else (10000, 50000)
+    Xt, y = synth_gpu(n, p, SEED, dev)
+    stream = torch.cuda.Stream(device=dev)
+    g = bw.Genotypes(device=local)
+    g.set_stream(stream.cuda_stream)
+    g.load(Xt)
+    hbm_peak, peak_src = peaks()
+    rng = np.random.default_rng(2)
+    ktr = 20
+    Y = np.stack([y * np.sqrt(0.5) + rng.normal(size=n) * np.sqrt(0.5) for _ in range(ktr)], axis=1)
+    units = 1  # independent fits sharing one pass over the genotypes
+    if cfg == 2:
+        name = "wgr BayesB (pi=0.95, iv=TRUE) Gibbs, synthetic n=10000 x p=50000 int8 genotypes; step = one MCMC iteration over all markers"
+        call = lambda it: bw.wgr(y, g, it=it, bi=max(1, it // 4), pi=0.95, iv=True, seed=1)  # noqa: E731
+        kernel = "sweep_pipe_kernel (Kuo-Mallick rule) + wgr step"
+    elif cfg == 3:
+        name = "MRR3 multivariate ridge, synthetic n=50000 x p=50000 int8 genotypes, k=20 traits; step = one sweep (p marker updates of 20 traits each)"
+        call = lambda it: bw.MRR3(Y, g, maxit=it, tol=0.0)  # noqa: E731
+        kernel = "sweep_pipe_kernel (20 rotated systems)"
+    else:
+        folds = 5
+        perm = rng.permutation(n)
+        mine = [i for i in range(folds * ktr) if i % world == rank]  # fits sharded round-robin, no communication
+        Yall = np.repeat(Y, folds, axis=1)[:, mine]
+        mask = np.ones((n, folds * ktr), dtype=bool)
+        for t in range(ktr):
+            for f in range(folds):
+                mask[perm[f * n // folds:(f + 1) * n // folds], folds * t + f] = False
+        mask = np.ascontiguousarray(mask[:, mine])
+        units = folds * ktr
+        name = ("emCV pattern: 5 folds x 20 traits = 100 emBC fits on synthetic n=10000 x p=50000 int8 genotypes (row masks), %d fits per GPU; "
+                "step = one sweep of every fit" % len(mine))
+        call = lambda it: bw.em_fit("emBC", Yall, g, it=it, row_mask=mask)  # noqa: E731
+        kernel = "masked batched sweep (sweep_pipe_kernel / small_n_kernel per plan)"
+
+    def timed_call(it):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = g.launch_count()
+        e0.record(stream)
+        r = call(it)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return r, e0.elapsed_time(e1), g.launch_count() - l0
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    call(W)  # warm-up (>= 3 steps)
+    _, t_w, l_w = timed_call(W)
+    res, t_wk, l_wk = timed_call(W + K)
+    ms = t_wk - t_w
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    t_clk = time.perf_counter()
+    while time.perf_counter() - t_clk < 1.5 or (len(sampler.rows) < 10 and time.perf_counter() - t_clk < 6.0):
+        call(W)
+    clocks = sampler.stop()
+    value = units * p * K / (ms * 1e-3)
+    fits_here = units // world if cfg == 4 else 1
+    achieved = n * p / (ms / K * 1e-3) / 1e9  # the genotypes are streamed once per step per GPU whatever the number of fits on it
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "kernel": kernel, "peak_source": peak_src, "algorithmic_bytes_per_launch": n * p,
+                "note": "whole step (all launches of one pass) against one pass over the int8 genotypes; these chains are latency-bound, not HBM-bound"}
+    e2e = None
+    if not args.no_e2e and rank == 0:
+        Xh = Xt.cpu().numpy().T  # n x p int8, host (column-major view)
+        it_e = W + K
+        t0 = time.perf_counter()
+        if cfg == 2:
+            bw.wgr(y, Xh, it=it_e, bi=max(1, it_e // 4), pi=0.95, iv=True, seed=1)
+        elif cfg == 3:
+            bw.MRR3(Y, Xh, maxit=it_e, tol=0.0)
+        else:
+            bw.em_fit("emBC", Yall, Xh, it=it_e, row_mask=mask)
+        dt = time.perf_counter() - t0
+        e2e = {"value": units // (world if cfg == 4 else 1) * p * it_e / dt, "unit": "marker-updates/s", "h2d_bytes_per_step": int(n * p), "d2h_bytes_per_step": int(8 * (n + p) * (ktr if cfg != 2 else 1)),
+               "step": "one public call on a HOST int8 matrix with %d steps: H2D, column statistics, the steps, read-back; rank 0 only" % it_e, "seconds": dt}
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        ns_, m = (2000, 1024) if cfg == 3 else (n, 512)
+        Xs = Xt[:m, :ns_].cpu().numpy().T.astype(np.float64)
+        t0 = time.perf_counter()
+        if cfg == 2:
+            its = 40
+            O.wgr(y[:ns_], Xs, it=its, bi=10, pi=0.95, iv=True, seed=1)
+            upd = its * m
+        elif cfg == 3:
+            its = 6
+            O.mrr3(Y[:ns_], Xs, maxit=its, tol=0.0)
+            upd = its * m
+        else:
+            its = 10
+            for f in range(4):
+                O.em("emBC", Yall[:, f], Xs.astype(np.float32), it=its)
+            upd = 4 * its * m
+        secs = time.perf_counter() - t0
+        cpu = {"value": upd / secs * (ns_ / n), "unit": "marker-updates/s", "cores": 1, "kind": "port",
+               "sample": "oracle on %d rows x first %d markers, %d steps = %.1f s, scaled by rows to n=%d (cost is linear in n); %s" % (
+                   ns_, m, its, secs, n, cpu_model_name())}
+    if rank == 0:
+        line = {"metric": "marker-updates/sec (BASELINE config %d)" % cfg, "value": value, "unit": "marker-updates/s", "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if cfg == 4 else "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": name, "seed": SEED, "fits_on_this_gpu": fits_here,
+                                                "l2": "genotypes are %.1f GB per step, larger than the 126 MB L2" % (n * p / 1e9)},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(l_wk), "clocks": clocks}
+        if cfg == 2:
+            line["check"] = {"mean_inclusion": float(np.mean(res["d"])), "Ve": res["Ve"], "cor_hat_y": float(np.corrcoef(res["hat"], y)[0, 1])}
+        elif cfg == 3:
+            line["check"] = {"h2_mean": float(np.mean(res["h2"])), "marker_trait_updates_per_s": value * ktr}
+        else:
+            line["check"] = {"h2_mean": float(np.mean(res["h2"]))}
+        print(json.dumps(line), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.config == 5:  # one GPU's share of the 500k x 100k row-sharded fit: the main flow below at that shard shape
+        args.n, args.p = 62500, 100000
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.config in (2, 3, 4):
+        run_config(args, rank, world, local)
         return
     import torch
     import torch.distributed as dist
@@ -464,7 +607,9 @@ def main():
             par = ("ONE fit of n=%d individuals sharded by rows over %d GPUs (%d rows each); per 128-marker block the reduced partials cross NVLink as "
                    "peer stores inside the sweep kernel, per sweep ncclAllReduce of the Gram band and 5 scalars; value counts marker updates per "
                    "%d-row shard (N x p per sweep)" % (n * world, world, n, n))
-        line = {"metric": "marker-updates/sec (emRR Gauss-Seidel sweep, n=50k x p=50k int8)", "value": value,
+        metric = "marker-updates/sec (emRR Gauss-Seidel sweep, n=50k x p=50k int8)" if args.config == 1 else \
+            "marker-updates/sec (BASELINE config 5: emRR Gauss-Seidel, row shards of %d x %d int8 per GPU)" % (n, p)
+        line = {"metric": metric, "value": value,
                 "unit": "marker-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",

@@ -7,6 +7,7 @@
 //   * initial hyper-parameters per solver, in float like the reference;
 //   * choosing the kernel family (small-n CTA-per-system vs blocked whole-GPU sweep).
 // There is deliberately no CPU compute path: every sweep runs in the CUDA kernels of this directory.
+#include <cuda.h>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -95,6 +96,10 @@ struct Fit {
   DevBuf<unsigned long long> dew, part, cx;
   DevBuf<float> wts;  // emML: marker weights d_j
   float* gram_p = nullptr;              // Gram band in use: f.gram (per fit) or the handle's natural-order cache
+  // Gram band of sweep s + 1 computed on the handle's side stream while sweep s runs (the clustered sweep leaves SMs idle)
+  bool overlap = false;
+  DevBuf<float> gram2;                  // band buffer of the odd sweeps (f.gram: even sweeps)
+  int gram_ahead = -1;                  // sweep whose band has been issued on the side stream (-1: none)
   // single Kuo-Mallick sweep / wgr driver
   DevBuf<float> xx_over;                // caller's xx (KMUP takes it as an argument, :12) / centred xx (MRR3)
   DevBuf<double> esum; DevBuf<float> emaxv;  // row-sharded fit: all-reduced epilogue sums
@@ -186,6 +191,13 @@ struct bwgr_handle {
   DevBuf<double> dscratch;                  // small all-reduce scratch
   alignas(64) unsigned char tmap[128];  // CUtensorMap of the int8 store (TMA tile::gather4)
   bool tmap_ok = false;
+  // side stream for work that overlaps the clustered sweep, gated by a flag word the sweep kernel stores (stream memory operations)
+  cudaStream_t side = nullptr;
+  cudaEvent_t side_done[2] = {nullptr, nullptr};
+  DevBuf<unsigned int> started;
+  unsigned int started_seq = 0;
+  CUresult (*wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+  CUresult (*write32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
   int fp8_codes = 0;  // all genotypes are codes 0..7 (and n small enough): the Gram kernel may use the exact E4M3 path
   int64_t launches = 0;
   Fit fit;
@@ -396,6 +408,22 @@ int bwgr_create(int device, bwgr_handle** out) {
   h->smem_optin = prop.sharedMemPerBlockOptin;
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(BWGR_ERR_CUDA, "cudaStreamCreate failed"); }
   h->stream = h->own_stream;
+  {  // side stream + stream memory operations (driver entry points through the runtime: no link against libcuda)
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    void *fw = nullptr, *fs = nullptr;
+    cudaDriverEntryPointQueryResult q1, q2;
+    if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, lo) == cudaSuccess &&
+        cudaEventCreateWithFlags(&h->side_done[0], cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&h->side_done[1], cudaEventDisableTiming) == cudaSuccess && h->started.alloc(1) == cudaSuccess &&
+        cudaGetDriverEntryPoint("cuStreamWaitValue32", &fw, cudaEnableDefault, &q1) == cudaSuccess && q1 == cudaDriverEntryPointSuccess &&
+        cudaGetDriverEntryPoint("cuStreamWriteValue32", &fs, cudaEnableDefault, &q2) == cudaSuccess && q2 == cudaDriverEntryPointSuccess) {
+      h->wait32 = reinterpret_cast<decltype(h->wait32)>(fw);
+      h->write32 = reinterpret_cast<decltype(h->write32)>(fs);
+      cudaMemset(h->started.p, 0, sizeof(unsigned int));
+    }
+    cudaGetLastError();
+  }
   if (h->err.alloc(1) != cudaSuccess) { delete h; return fail(BWGR_ERR_CUDA, "cudaMalloc failed"); }
   cudaMemset(h->err.p, 0, sizeof(int));
   const char* gs = getenv("BWGR_GRAM");
@@ -413,6 +441,8 @@ void bwgr_destroy(bwgr_handle* h) {
     if (r != h->rank && h->hx[r]) cudaIpcCloseMemHandle(h->hx[r]);
   if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->side) cudaStreamDestroy(h->side);
+  for (int i = 0; i < 2; i++) if (h->side_done[i]) cudaEventDestroy(h->side_done[i]);
   delete h;
 }
 
@@ -784,6 +814,8 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
   const int ns = s.nsys;
   f.model = s.model; f.nsys = ns; f.shuffled = s.shuffled; f.blocked = blocked; f.masked = s.row_mask != nullptr;
   f.sweeps_issued = 0; f.seed = s.seed; f.gram_cached = false; f.skip_epilogue = false; f.wgr_mode = false; f.gram_p = nullptr;
+  f.overlap = false; f.gram_ahead = -1;
+  if (h->side) CU(cudaStreamSynchronize(h->side));  // a band computed ahead for a sweep the previous fit never ran
   f.xx_over.release(); f.wst.release(); f.sx_dev.release(); f.cshift.release(); f.wts.release();
   f.it_target = s.it;
 
@@ -1046,7 +1078,15 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
       } else {
         if (f.gram.alloc(gram_n) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(Gram band) failed");
         f.gram_p = f.gram.p;
+        // the clustered sweep occupies 8 x nclusters of the SMs: the next sweep's Gram band (a function of the marker order only)
+        // is computed on the others meanwhile.  BWGR_OVERLAP=0 keeps everything on one stream.
+        const char* ov = getenv("BWGR_OVERLAP");
+        f.overlap = f.cl && h->world <= 1 && h->wait32 && h->x2f.p && f.nband == 2 && !h->gram_simt && !(ov && !strcmp(ov, "0")) &&
+                    f.nclusters * 8 < h->num_sms;
+        if (f.overlap && f.gram2.alloc(gram_n) != cudaSuccess) { cudaGetLastError(); f.overlap = false; }
       }
+      if (!f.overlap) f.gram2.release();
+      f.gram_ahead = -1;
       if (f.full_inv && f.tinv.alloc((size_t)f.nblocks * kBlk * kBlk) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(block inverses) failed");
       if (!f.full_inv) f.tinv.release();
       if (
@@ -1094,18 +1134,26 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
     const int sweep = f.sweeps_issued;
     const int slot = sweep % kPermRing;
     const int* d_perm = nullptr;
-    if (f.shuffled || (f.blocked && f.sweeps_issued == 0)) {  // natural order: the identity is uploaded once (slot 0)
-      if (f.perm_ev_valid[slot]) CU(cudaEventSynchronize(f.perm_free[slot]));
-      int* hp = f.h_perm + (size_t)slot * p;
-      if (f.shuffled) std::shuffle(f.order.begin(), f.order.end(), std::mt19937(sweep));
+    // the marker order of sweep `sw` (cumulative shuffles, Rcpp20260726ai.cpp:329-331) goes up on stream `st`
+    auto upload_order = [&](int sw, cudaStream_t st) -> cudaError_t {
+      const int sl = sw % kPermRing;
+      if (f.perm_ev_valid[sl]) { cudaError_t e = cudaEventSynchronize(f.perm_free[sl]); if (e != cudaSuccess) return e; }
+      int* hp = f.h_perm + (size_t)sl * p;
+      if (f.shuffled) std::shuffle(f.order.begin(), f.order.end(), std::mt19937(sw));
       memcpy(hp, f.order.data(), sizeof(int) * p);
-      CU(cudaMemcpyAsync(f.perm.p + (size_t)slot * p, hp, sizeof(int) * p, cudaMemcpyHostToDevice, h->stream));
-    }
+      return cudaMemcpyAsync(f.perm.p + (size_t)sl * p, hp, sizeof(int) * p, cudaMemcpyHostToDevice, st);
+    };
+    const bool ahead = f.overlap && f.gram_ahead == sweep;  // order and Gram band of this sweep were issued on the side stream
+    if (f.overlap) f.gram_p = (sweep & 1) ? f.gram2.p : f.gram.p;
+    if (!ahead && (f.shuffled || (f.blocked && f.sweeps_issued == 0)))  // natural order: the identity is uploaded once (slot 0)
+      CU(upload_order(sweep, h->stream));
     if (f.shuffled) d_perm = f.perm.p + (size_t)slot * p;
     else if (f.blocked) d_perm = f.perm.p;  // identity order, uploaded once (slot 0)
     if (model_has_cnv(f.model)) CU(cudaMemcpyAsync(f.b_prev.p, f.b.p, sizeof(float) * f.nsys * p, cudaMemcpyDeviceToDevice, h->stream));
     if (f.blocked) {
-      if (f.shuffled || !f.gram_cached) {
+      if (ahead) {
+        CU(cudaStreamWaitEvent(h->stream, h->side_done[sweep & 1], 0));
+      } else if (f.shuffled || !f.gram_cached) {
         cudaEvent_t pe = h->prof_begin(0);
         if (h->gram_simt) launch_gram_simt(g, d_perm, f.nblocks, f.gram_p, 1, h->stream);
         else if (h->x2f.p && f.nband == 2) {
@@ -1144,11 +1192,29 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
           if (!f.trace.p) { f.trace.alloc((size_t)f.grid * f.nblocks * 32); cudaMemsetAsync(f.trace.p, 0, sizeof(long long) * f.trace.n, h->stream); }
           a.trace = f.trace.p;
         }
+        if (f.overlap) { a.started = h->started.p; a.started_val = ++h->started_seq; }
         cudaEvent_t pe = h->prof_begin(1);
         const cudaError_t le = launch_sweep_pipe(a, h->stream);
         h->prof_end(pe);
         if (le != cudaSuccess) return fail(BWGR_ERR_CUDA, "pipelined sweep launch failed: %s", cudaGetErrorString(le));
         h->launches++;
+        if (f.overlap) {
+          // the flag is also set when the sweep has drained, whatever happened inside it: the side stream never waits forever
+          const CUdeviceptr flag = reinterpret_cast<CUdeviceptr>(h->started.p);
+          if (h->write32(h->stream, flag, a.started_val, 0) != CUDA_SUCCESS) return fail(BWGR_ERR_CUDA, "cuStreamWriteValue32 failed");
+          const bool more = k + 1 < nsweeps || sweep + 1 < f.it_target;
+          if (more && !h->profiling) {  // sweep + 1: order + Gram band on the SMs this sweep leaves idle, as soon as it is resident
+            if (h->wait32(h->side, flag, a.started_val, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) return fail(BWGR_ERR_CUDA, "cuStreamWaitValue32 failed");
+            CU(upload_order(sweep + 1, h->side));
+            const int* np_ = f.perm.p + (size_t)((sweep + 1) % kPermRing) * p;
+            const cudaError_t ge = launch_gram_fp4(h->x2f.p, h->ld, (int)h->p, (int)h->n_global, np_, f.nblocks, ((sweep + 1) & 1) ? f.gram2.p : f.gram.p,
+                                                   h->err.p, h->num_sms, f.sx_dev.p, h->side, true);
+            if (ge != cudaSuccess) return fail(BWGR_ERR_CUDA, "FP4 Gram launch failed: %s", cudaGetErrorString(ge));
+            CU(cudaEventRecord(h->side_done[(sweep + 1) & 1], h->side));
+            f.gram_ahead = sweep + 1;
+            h->launches++;
+          }
+        }
       } else {
         CU(cudaMemsetAsync(f.gacc.p, 0, sizeof(long long) * (size_t)f.nblocks * kNC * f.nsys * kBlk, h->stream));
         CU(cudaMemsetAsync(f.bar.p, 0, sizeof(unsigned int), h->stream));

@@ -290,11 +290,13 @@ void launch_pack_2bit_fp4(const int8_t* src, int64_t ld, int p, uint8_t* dst, in
 
 // gram: [nblocks][128][256] floats (band 2).  x2f: the packed shadow, ld / 4 bytes per column.
 cudaError_t launch_gram_fp4(const uint8_t* x2f, int64_t ld, int p, int n, const int* perm, int nblocks, float* gram, int* err,
-                            int num_sms, const float* sx, cudaStream_t st) {
+                            int num_sms, const float* sx, cudaStream_t st, bool block_per_cta) {
   const size_t smem = (size_t)kStages * kStageBytes + sizeof(Fp4Smem) + 1024;
   cudaError_t e = cudaFuncSetAttribute(gram_fp4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int grid = nblocks < num_sms ? nblocks : num_sms;
+  // block_per_cta: one short CTA per marker block instead of a persistent grid -- the hardware hands blocks to whichever SMs are
+  // free, which is what a launch that shares the GPU with the clustered sweep needs
+  const int grid = block_per_cta || nblocks < num_sms ? nblocks : num_sms;
   gram_fp4_kernel<<<grid, 416, smem, st>>>(x2f, ld / 4, ld, p, n, perm, nblocks, gram, err, sx, 1.0f / (float)n);
   return cudaGetLastError();
 }

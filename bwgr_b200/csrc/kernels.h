@@ -83,7 +83,7 @@ void launch_gram_tc(const GenoView& g, const int* perm, int nblocks, void* gram,
 // (ld / 4 bytes per column); exact, twice the E4M3 rate.  gram: [nblocks][128][256] floats.
 void launch_pack_2bit_fp4(const int8_t* src, int64_t ld, int p, uint8_t* dst, int* bad, cudaStream_t st);
 cudaError_t launch_gram_fp4(const uint8_t* x2f, int64_t ld, int p, int n, const int* perm, int nblocks, float* gram, int* err,
-                            int num_sms, const float* sx, cudaStream_t st);
+                            int num_sms, const float* sx, cudaStream_t st, bool block_per_cta = false);
 bool make_geno_tensor_map(const int8_t* x8, int64_t ld, int64_t p, void* tmap_out);
 // SIMT cross-check of the same quantity (debug / tests only; selected with BWGR_GRAM=simt).
 void launch_gram_simt(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, cudaStream_t st);
@@ -153,6 +153,10 @@ struct PipeArgs {
   // cx = [8][nclusters][nsys][128] per-cluster sums of h, same word format as hred; zeroed before launch
   int cl, nclusters;
   unsigned long long* cx;
+  // optional: cluster 0 stores started_val here once the first grid sum has gone round, i.e. when every CTA of the launch is
+  // resident -- a side stream waits on it (cuStreamWaitValue32) before it fills the SMs this launch leaves idle
+  unsigned int* started;
+  unsigned int started_val;
 };
 cudaError_t launch_sweep_pipe(const PipeArgs& a, cudaStream_t st);
 size_t sweep_pipe_smem(int rows_per_cta, int nsys, int model, int nbuf, int sring, int full_inv, int cl);

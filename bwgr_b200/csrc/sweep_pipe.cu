@@ -727,6 +727,10 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
           hsum[(size_t)slot * ns * 128 + pair] = tot;
         }
         mbar_arrive(&S.h_ready[slot]);
+        if (b == 0 && ct == 0 && cluster == 0 && a.started) {  // every cluster has delivered a sum: the whole grid is resident
+          *reinterpret_cast<volatile unsigned int*>(a.started) = a.started_val;
+          __threadfence_system();
+        }
         if (tracing && ct == 0) { long long* tp_ = a.trace + ((size_t)blockIdx.x * nblocks + b) * 32 + 4; tp_[0] = (long long)gtimer(); tp_[16] = clock64(); }
         // until the partials of the next block arrive these warps are idle: three of them take one tile each of the lower-
         // triangular product dE = T r of the block they just delivered ((2,2), (3,2), (3,3)); the solve warps add the tile sums in

@@ -214,6 +214,25 @@ def test_blocked_sweep_is_deterministic(tpod):
     assert np.array_equal(a["b"], b["b"]) and a["Ve"] == b["Ve"]
 
 
+def test_gram_band_computed_ahead_changes_nothing(monkeypatch):
+    """The next sweep's Gram band is computed on a side stream while the clustered sweep runs (capi.cu fit_sweeps): the fit is
+    bit-identical to the one-stream schedule, for straight fits, stepped fits and back-to-back fits on one store."""
+    X, y = synth(20000, 4000, seed=33)
+    with bw.Genotypes(X, path=2) as g:
+        a = bw.emRR(y, g, it=14)
+        st = bw.EmStepper("emRR", y, g)
+        for k in (1, 3, 2, 8):
+            st.sweeps(k)
+        s = st.end()
+        c = bw.em_fit("emBA", y, g, it=9)
+        monkeypatch.setenv("BWGR_OVERLAP", "0")
+        b = bw.emRR(y, g, it=14)
+        d = bw.em_fit("emBA", y, g, it=9)
+    assert np.array_equal(a["b"], b["b"]) and a["Ve"] == b["Ve"] and np.array_equal(a["hat"], b["hat"])
+    assert np.array_equal(a["b"], s["b"])
+    assert np.array_equal(c["b"], d["b"]) and c["h2"] == d["h2"]
+
+
 @pytest.mark.parametrize("path", [1, 2])
 @pytest.mark.parametrize("model", list(O.GIBBS_MODELS))
 def test_gibbs_posterior_means(tpod, model, path):
@@ -780,7 +799,7 @@ def test_emml_marker_weights(tpod, path):
 
 @pytest.mark.parametrize("env", [{"BWGR_CLUSTER": "0"}, {"BWGR_CLUSTER": "0", "BWGR_LOOKAHEAD": "0"}, {"BWGR_TINV": "0"}, {"BWGR_SWEEP": "v4"},
                                  {"BWGR_GRAM": "fp8"}, {"BWGR_GRAM": "i8"}, {"BWGR_GRAM": "simt"}, {"BWGR_TMA": "1", "BWGR_GRAM": "fp8"},
-                                 {"BWGR_GRAM_PACKED": "0", "BWGR_GRAM": "fp8"}])
+                                 {"BWGR_GRAM_PACKED": "0", "BWGR_GRAM": "fp8"}, {"BWGR_OVERLAP": "0"}])
 def test_every_kernel_variant_behind_a_switch(monkeypatch, env):
     """Every alternative kernel the library can select (flat topology, no look-ahead, stepwise in-block solve, the v4 sweep, the
     E4M3 / int8 / SIMT Gram kernels, the TMA gather4 and unpacked producers) fits the same data to the same parity bar as the default."""
