@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--n", type=int, default=50000)
     ap.add_argument("--p", type=int, default=50000)
     ap.add_argument("--model", default="emRR")
-    ap.add_argument("--e2e-fits", type=int, default=5)
+    ap.add_argument("--e2e-fits", type=int, default=7)
     ap.add_argument("--e2e-sweeps", type=int, default=200)
     ap.add_argument("--cpu-markers", type=int, default=2048)
     ap.add_argument("--cpu-sweeps", type=int, default=10)
@@ -294,7 +294,7 @@ def run_config(args, rank, world, local):
     import torch.distributed as dist
 
     import bwgr_b200 as bw
-    from oracle import oracle as O
+    import oracle as O
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -383,19 +383,19 @@ def run_config(args, rank, world, local):
                "step": "one public call on a HOST int8 matrix with %d steps: H2D, column statistics, the steps, read-back; rank 0 only" % it_e, "seconds": dt}
     cpu = None
     if rank == 0 and not args.no_cpu:
-        ns_, m = (2000, 1024) if cfg == 3 else (n, 512)
+        ns_, m = (10000, 2048) if cfg == 3 else (n, 1024)
         Xs = Xt[:m, :ns_].cpu().numpy().T.astype(np.float64)
         t0 = time.perf_counter()
         if cfg == 2:
-            its = 40
+            its = 400
             O.wgr(y[:ns_], Xs, it=its, bi=10, pi=0.95, iv=True, seed=1)
             upd = its * m
         elif cfg == 3:
-            its = 6
+            its = 12
             O.mrr3(Y[:ns_], Xs, maxit=its, tol=0.0)
             upd = its * m
         else:
-            its = 10
+            its = 60
             for f in range(4):
                 O.em("emBC", Yall[:, f], Xs.astype(np.float32), it=its)
             upd = 4 * its * m
@@ -567,6 +567,7 @@ def main():
                             "staging overlapped with the H2D copy, column statistics, %d sweeps, GEBVs, D2H" % args.e2e_sweeps) if use_f64 else
                            ("one emRR(y, gen) call on a host int8 matrix (not enough host memory for the float64 copy): H2D, column statistics, %d sweeps, GEBVs, D2H" % args.e2e_sweeps),
                    "seconds_per_fit": dt, "seconds_each_fit": fit_s, "spread": (max(fit_s) - min(fit_s)) / dt,
+                   "iqr_over_median": float(np.subtract(*np.percentile(fit_s, [75, 25])) / dt),
                    "int8_host_input": {"value": args.e2e_sweeps * p / float(np.median(fits8)), "seconds_each_fit": fits8}}
         else:
             Xp = Xh.pin_memory()

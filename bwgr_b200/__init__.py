@@ -4,3 +4,4 @@ from .api import (PATH_AUTO, PATH_BLOCKED, PATH_SMALL_N, STORE_2BIT, STORE_I8, B
                   EmStepper, Genotypes, KMUP, em_fit, emBA, emBB, emBC, emBL, emEN, emRR, gibbs_fit, wgr, MRR3, MRR3F, mrr, mrr_float,
                   emDE, emML, emBCpi, lasso, BayesL, BayesCpi, BayesDpi, emCV, mcmcCV, GSRR, GSFLM)
 from ._lib import BwgrError, LIB_PATH, SYMBOLS  # noqa: F401
+from .api import trim  # noqa: F401

@@ -175,6 +175,11 @@ class Genotypes:
         self.close()
 
 
+def trim():
+    """Return the device / pinned blocks kept from closed stores and fits to the driver (bwgr_trim)."""
+    _lib.load().bwgr_trim()
+
+
 def _store(gen, **kw):
     if isinstance(gen, Genotypes):
         if gen.p == 0:  # same status and text as the C ABI gives for a call before bwgr_geno_load_*

@@ -20,6 +20,8 @@
 #include <random>
 #include <string>
 #include <atomic>
+#include <mutex>
+#include <sched.h>
 #include <thread>
 #include <vector>
 
@@ -48,22 +50,98 @@ int fail(int code, const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail(BWGR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+// Device and pinned-host blocks released by a handle are kept for the next one: the drop-in creates and destroys a store and a
+// fit per emRR(y, gen) call, and cudaFree / cudaFreeHost of gigabyte blocks cost anything from 3 to 200 ms each on a busy
+// driver (measured: tools/load_probe.py).  Exact-size reuse, bounded (BWGR_CACHE_GB, default 24; 0 = off), emptied by bwgr_trim().
+struct BlockCache {
+  struct Blk { void* p; size_t bytes; int dev; bool host; };
+  std::mutex mu;
+  std::vector<Blk> blocks;
+  size_t held = 0;
+  static size_t limit() {
+    static const size_t lim = [] { const char* e = getenv("BWGR_CACHE_GB"); return (size_t)((e ? atof(e) : 24.0) * 1073741824.0); }();
+    return lim;
+  }
+  void* take(size_t bytes, int dev, bool host) {
+    std::lock_guard<std::mutex> l(mu);
+    for (size_t i = 0; i < blocks.size(); i++)
+      if (blocks[i].bytes == bytes && blocks[i].dev == dev && blocks[i].host == host) {
+        void* p = blocks[i].p;
+        held -= bytes;
+        blocks.erase(blocks.begin() + (long)i);
+        return p;
+      }
+    return nullptr;
+  }
+  static void drop(const Blk& b) { if (b.host) cudaFreeHost(b.p); else { int cur = 0; cudaGetDevice(&cur); cudaSetDevice(b.dev); cudaFree(b.p); cudaSetDevice(cur); } }
+  void give(void* p, size_t bytes, int dev, bool host) {
+    if (bytes > limit() || bytes < 4096) { drop({p, bytes, dev, host}); return; }
+    std::lock_guard<std::mutex> l(mu);
+    blocks.push_back({p, bytes, dev, host});
+    held += bytes;
+    while (held > limit() && !blocks.empty()) { held -= blocks.front().bytes; drop(blocks.front()); blocks.erase(blocks.begin()); }
+  }
+  void trim() {
+    std::lock_guard<std::mutex> l(mu);
+    for (auto& b : blocks) drop(b);
+    blocks.clear(); held = 0;
+  }
+};
+BlockCache& block_cache() { static BlockCache* c = new BlockCache; return *c; }  // never destroyed: no CUDA calls at process exit
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  int dev = 0;
+  bool cacheable = true;  // false: memory other processes have mapped (cudaIpc)
   cudaError_t alloc(size_t count) {
     release();
     n = count;
     if (!count) return cudaSuccess;
-    return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+    const size_t bytes = count * sizeof(T);
+    cudaGetDevice(&dev);
+    if (cacheable) {
+      if (void* q = block_cache().take(bytes, dev, false)) {
+        p = static_cast<T*>(q);
+        // a fresh cudaMalloc block usually reads as zeros; keep that for the small state buffers (the big ones are stores and
+        // bands their producers overwrite in full)
+        if (bytes <= ((size_t)256 << 20)) { cudaError_t e = cudaMemset(p, 0, bytes); if (e != cudaSuccess) return e; return cudaDeviceSynchronize(); }
+        return cudaSuccess;
+      }
+    }
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), bytes);
+    if (e != cudaSuccess && cacheable) {  // the cache may be what fills the device
+      cudaGetLastError();
+      block_cache().trim();
+      e = cudaMalloc(reinterpret_cast<void**>(&p), bytes);
+    }
+    if (e != cudaSuccess) { p = nullptr; n = 0; }
+    return e;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (cacheable) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != dev) cudaSetDevice(dev);
+        cudaDeviceSynchronize();  // what cudaFree would have implied: nothing in flight still uses the block
+        if (cur != dev) cudaSetDevice(cur);
+        block_cache().give(p, n * sizeof(T), dev, false);
+      } else {
+        cudaFree(p);
+      }
+    }
     p = nullptr; n = 0;
   }
   ~DevBuf() { release(); }
 };
+
+inline cudaError_t pinned_alloc(void** p, size_t bytes) {
+  if ((*p = block_cache().take(bytes, -1, true))) return cudaSuccess;
+  return cudaMallocHost(p, bytes);
+}
+inline void pinned_free(void* p, size_t bytes) { if (p) block_cache().give(p, bytes, -1, true); }
 
 constexpr int kPermRing = 8;
 
@@ -109,11 +187,12 @@ struct Fit {
   DevBuf<WgrState> wst;
   WgrArgs wgr_args;
   int* h_perm = nullptr;                // pinned [kPermRing][p]
+  size_t h_perm_bytes = 0;
   cudaEvent_t perm_free[kPermRing] = {};
   bool perm_ev_valid[kPermRing] = {};
   void reset() {
     active = false;
-    if (h_perm) { cudaFreeHost(h_perm); h_perm = nullptr; }
+    if (h_perm) { pinned_free(h_perm, h_perm_bytes); h_perm = nullptr; }
     for (int i = 0; i < kPermRing; i++)
       if (perm_free[i]) { cudaEventDestroy(perm_free[i]); perm_free[i] = nullptr; perm_ev_valid[i] = false; }
   }
@@ -392,6 +471,7 @@ extern "C" {
 
 const char* bwgr_last_error(void) { return g_err.c_str(); }
 int bwgr_version(void) { return 100; }
+void bwgr_trim(void) { block_cache().trim(); }
 
 int bwgr_create(int device, bwgr_handle** out) {
   if (!out) return fail(BWGR_ERR_ARG, "out is NULL");
@@ -466,18 +546,12 @@ int bwgr_set_tuning(bwgr_handle* h, int block, int path, int grid) {
 
 int64_t bwgr_launch_count(bwgr_handle* h) { return h ? h->launches : 0; }
 
-// ---- genotype store ---------------------------------------------------------------------------------
-// The boundary conversion of the reference is Rcpp::as<Eigen::MatrixXf> (src/RcppExports.cpp:115-116): a full n x p copy + cast on
-// the CPU, once per call.  Here it happens once per store: a few host threads narrow R's doubles to int8 (exact integers in range
-// only; anything else is an error, never rounded) into two pinned staging buffers laid out like the device store, and the H2D
-// copy of chunk i overlaps the narrowing of chunk i + 1 -- n * p bytes cross PCIe instead of 8 * n * p.
-//
-// offsets != nullptr (bwgr_geno_load_f64_centred): a column may be "integer codes + one constant", e.g. CNT(gen) (Rcpp20260726ai.cpp:1308,
-// the reference's own mrr(Y, CNT(gen)) example, man/mvr.Rd:144-153).  The constant (fractional part of the first entry plus the
-// column minimum, so that the stored codes start at 0) goes to offsets[j]; the codes must still be exact integers (1e-4, the
-// resolution of a float32 column mean).
-static void narrow_columns(const double* X, int64_t ld_src, int64_t n, int64_t ld_dst, int64_t j0, int64_t j1, int8_t* dst, int lo, int hi,
-                           std::atomic<int>* bad, double* offsets) {
+// Host side of emRR(y, gen) on R's double matrix: exact narrowing to int8 codes (host_narrow.cpp) by a pool of host threads into
+// pinned staging buffers, each chunk of columns copied to the device while the next ones are narrowed.
+// offsets != nullptr (the centred loader): a column may be "integer codes + one constant" (CNT(gen), or any integer-valued
+// column): the constant -- the fractional part of the first value plus the column minimum, so that the stored codes start at 0 --
+// goes to offsets[j]; the codes must still be integers to 1e-4, the resolution of a float32 column mean.
+static int narrow_columns(const double* X, int64_t ld_src, int64_t n, int64_t ld_dst, int64_t j0, int64_t j1, int8_t* dst, int lo, int hi, double* offsets) {
   int flag = 0;
   for (int64_t j = j0; j < j1; j++) {
     const double* src = X + j * ld_src;
@@ -486,31 +560,31 @@ static void narrow_columns(const double* X, int64_t ld_src, int64_t n, int64_t l
       const double v0 = src[0];
       double frac = v0 - std::floor(v0);
       if (!(frac == frac) || frac < 1e-4 || frac > 1.0 - 1e-4) frac = 0.0;
-      offsets[j] = 0.0;
-      {  // also for an integer-valued column: the solver centres anyway, and codes starting at 0 keep the store on the FP4 / E4M3 Gram paths
-        double mn = 1e300;
-        for (int64_t i = 0; i < n; i++) mn = std::min(mn, src[i] - frac);
-        const double base = std::nearbyint(mn);
-        for (int64_t i = 0; i < n; i++) {
-          const double t = src[i] - frac - base;
-          const double r = std::nearbyint(t);
-          flag |= !(std::fabs(t - r) <= 1e-4) | (r < lo) | (r > hi);
-          out[i] = (int8_t)(int)r;
-        }
-        for (int64_t i = n; i < ld_dst; i++) out[i] = 0;
-        offsets[j] = frac + base;
-        continue;
-      }
-    }
-    for (int64_t i = 0; i < n; i++) {
-      const double v = src[i];
-      const int iv = (int)v;
-      flag |= !((double)iv == v) | (iv < lo) | (iv > hi);
-      out[i] = (int8_t)iv;
+      // also for an integer-valued column: the solver centres anyway, and codes starting at 0 keep the store on the FP4 / E4M3 Gram paths
+      const double base = std::nearbyint(bwgr::column_min(src, n) - frac);
+      flag |= bwgr::narrow_column_shifted(src, n, out, frac + base, lo, hi);
+      offsets[j] = frac + base;
+    } else {
+      flag |= bwgr::narrow_column(src, n, out, lo, hi);
     }
     for (int64_t i = n; i < ld_dst; i++) out[i] = 0;
   }
-  if (flag) bad->store(1);
+  return flag;
+}
+
+// host threads the loader may keep busy: the cores this process may run on, capped by the cgroup CPU quota (a container that
+// over-subscribes its quota is throttled for the rest of every scheduling period -- stalls of tens of milliseconds)
+static int loader_threads() {
+  if (const char* e = getenv("BWGR_LOAD_THREADS")) { const int v = atoi(e); if (v > 0) return std::min(v, 256); }
+  int nt = (int)std::thread::hardware_concurrency();
+  cpu_set_t cs;
+  if (sched_getaffinity(0, sizeof cs, &cs) == 0) nt = std::min(nt > 0 ? nt : 1 << 20, CPU_COUNT(&cs));
+  if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+    long long quota = 0, period = 0;
+    if (fscanf(f, "%lld %lld", &quota, &period) == 2 && quota > 0 && period > 0) nt = std::min<long long>(nt, std::max<long long>(1, quota / period));
+    fclose(f);
+  }
+  return std::max(1, std::min(nt, 64));
 }
 
 static int load_f64_common(bwgr_handle* h, const double* X, int64_t n, int64_t p, int64_t ld, int storage, bool allow_offset) {
@@ -522,46 +596,73 @@ static int load_f64_common(bwgr_handle* h, const double* X, int64_t n, int64_t p
   double* offs = allow_offset ? h->col_offset.data() : nullptr;
   const int lo = storage == BWGR_STORE_2BIT ? 0 : -128, hi = storage == BWGR_STORE_2BIT ? 2 : 127;
   const int64_t ldd = h->ld;
+  constexpr int kStage = 4;
   const int64_t chunk_cols = std::max<int64_t>(1, std::min<int64_t>(p, ((int64_t)32 << 20) / ldd));
   const size_t chunk_bytes = (size_t)chunk_cols * ldd;
-  // the two pinned staging buffers are kept for the life of the process (cudaMallocHost / cudaFreeHost cost tens of milliseconds
+  // the pinned staging buffers are kept for the life of the process (cudaMallocHost / cudaFreeHost cost tens of milliseconds
   // each and would otherwise be paid by every emRR(y, gen) call of the drop-in, which creates and destroys its store)
-  static int8_t* s_stage[2] = {nullptr, nullptr};
+  static int8_t* s_stage[kStage] = {};
   static size_t s_stage_bytes = 0;
+  static std::mutex s_mu;
+  std::lock_guard<std::mutex> lock(s_mu);
   if (s_stage_bytes < chunk_bytes) {
-    for (int i = 0; i < 2; i++) { if (s_stage[i]) cudaFreeHost(s_stage[i]); s_stage[i] = nullptr; }
+    bool ok = true;
+    for (int i = 0; i < kStage; i++) { if (s_stage[i]) cudaFreeHost(s_stage[i]); s_stage[i] = nullptr; }
     s_stage_bytes = 0;
-    if (cudaMallocHost(reinterpret_cast<void**>(&s_stage[0]), chunk_bytes) != cudaSuccess || cudaMallocHost(reinterpret_cast<void**>(&s_stage[1]), chunk_bytes) != cudaSuccess) {
-      for (int i = 0; i < 2; i++) { if (s_stage[i]) cudaFreeHost(s_stage[i]); s_stage[i] = nullptr; }
+    for (int i = 0; i < kStage && ok; i++) ok = cudaMallocHost(reinterpret_cast<void**>(&s_stage[i]), chunk_bytes) == cudaSuccess;
+    if (!ok) {
+      for (int i = 0; i < kStage; i++) { if (s_stage[i]) cudaFreeHost(s_stage[i]); s_stage[i] = nullptr; }
       return fail(BWGR_ERR_CUDA, "cudaMallocHost(staging) failed");
     }
     s_stage_bytes = chunk_bytes;
   }
-  int8_t* stage[2] = {s_stage[0], s_stage[1]};
-  cudaEvent_t done[2] = {nullptr, nullptr};
-  for (int i = 0; i < 2; i++)
+  cudaEvent_t done[kStage] = {};
+  for (int i = 0; i < kStage; i++)
     if (cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaEventCreate failed");
-  unsigned hc = std::thread::hardware_concurrency();
-  const int nthr = (int)std::max(1u, std::min(hc ? hc : 4u, 32u));
-  std::atomic<int> bad(0);
+  const int64_t nchunk = (p + chunk_cols - 1) / chunk_cols;
+  const int nthr = (int)std::min<int64_t>(loader_threads(), p);
+  const int nslice = (int)std::min<int64_t>(chunk_cols, 2 * nthr);  // tasks per chunk
+  // task t = (chunk t / nslice, slice t % nslice), handed out in order; a chunk may be written once the copy that last read its
+  // staging buffer has finished (`released`, advanced by this thread), and is copied once all its slices are in (`left`)
+  std::atomic<int64_t> next_task(0), released(kStage);
+  std::vector<std::atomic<int>> left((size_t)nchunk);
+  for (auto& l : left) l.store(nslice);
+  std::atomic<int> bad(0), stop(0);
+  auto worker = [&]() {
+    for (;;) {
+      const int64_t t = next_task.fetch_add(1);
+      const int64_t c = t / nslice;
+      if (c >= nchunk) return;
+      while (c >= released.load(std::memory_order_acquire)) { if (stop.load()) return; std::this_thread::yield(); }
+      const int sl = (int)(t % nslice);
+      const int64_t j0 = c * chunk_cols, pc = std::min(chunk_cols, p - j0);
+      const int64_t a = pc * sl / nslice, b = pc * (sl + 1) / nslice;
+      if (b > a && narrow_columns(X, ld, n, ldd, j0 + a, j0 + b, s_stage[c % kStage] + a * ldd, lo, hi, offs)) bad.store(1);
+      left[(size_t)c].fetch_sub(1, std::memory_order_release);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthr; t++) pool.emplace_back(worker);
   cudaError_t ce = cudaSuccess;
-  int64_t nchunk = 0;
-  for (int64_t j0 = 0; j0 < p && ce == cudaSuccess; j0 += chunk_cols, nchunk++) {
-    const int64_t pc = std::min(chunk_cols, p - j0);
-    const int sb = (int)(nchunk & 1);
-    if (nchunk >= 2) ce = cudaEventSynchronize(done[sb]);  // the copy that last read this buffer has finished
-    if (ce != cudaSuccess) break;
-    const int nt = (int)std::min<int64_t>(nthr, pc);
-    std::vector<std::thread> pool;
-    for (int t = 1; t < nt; t++)
-      pool.emplace_back(narrow_columns, X, ld, n, ldd, j0 + pc * t / nt, j0 + pc * (t + 1) / nt, stage[sb] + (pc * t / nt) * ldd, lo, hi, &bad, offs);
-    narrow_columns(X, ld, n, ldd, j0, j0 + pc / nt, stage[sb], lo, hi, &bad, offs);
-    for (auto& th : pool) th.join();
-    ce = cudaMemcpyAsync(h->x8_own.p + j0 * ldd, stage[sb], (size_t)pc * ldd, cudaMemcpyHostToDevice, h->stream);
-    if (ce == cudaSuccess) ce = cudaEventRecord(done[sb], h->stream);
+  int64_t synced = 0;  // copies known to have finished
+  for (int64_t c = 0; c < nchunk && ce == cudaSuccess; c++) {
+    while (left[(size_t)c].load(std::memory_order_acquire) > 0) {
+      if (synced < c && cudaEventQuery(done[synced % kStage]) == cudaSuccess) released.store(++synced + kStage, std::memory_order_release);
+      else std::this_thread::yield();
+    }
+    const int64_t j0 = c * chunk_cols, pc = std::min(chunk_cols, p - j0);
+    ce = cudaMemcpyAsync(h->x8_own.p + j0 * ldd, s_stage[c % kStage], (size_t)pc * ldd, cudaMemcpyHostToDevice, h->stream);
+    if (ce == cudaSuccess) ce = cudaEventRecord(done[c % kStage], h->stream);
+    while (ce == cudaSuccess && synced <= c && c + 1 < nchunk && c + 1 >= synced + kStage) {  // the next chunk cannot start before an older copy ends
+      ce = cudaEventSynchronize(done[synced % kStage]);
+      released.store(++synced + kStage, std::memory_order_release);
+    }
   }
+  stop.store(1);
+  for (auto& th : pool) th.join();
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
-  for (int i = 0; i < 2; i++) cudaEventDestroy(done[i]);
+  for (int i = 0; i < kStage; i++) cudaEventDestroy(done[i]);
+  cudaGetLastError();
   if (ce != cudaSuccess) return fail(BWGR_ERR_CUDA, "bwgr_geno_load_f64: %s", cudaGetErrorString(ce));
   if (bad.load()) return fail(BWGR_ERR_ARG, "bwgr_geno_load_f64: non-integer or out-of-range genotype");
   if (allow_offset) for (double v : h->col_offset) if (v != 0.0) { h->has_offset = true; break; }
@@ -1043,7 +1144,8 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
   CU(cudaMemcpyAsync(f.sc.p, f.sc0.data(), sizeof(SysScalars) * ns, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
 
-  CU(cudaMallocHost(reinterpret_cast<void**>(&f.h_perm), sizeof(int) * kPermRing * p));
+  f.h_perm_bytes = sizeof(int) * kPermRing * p;
+  CU(pinned_alloc(reinterpret_cast<void**>(&f.h_perm), f.h_perm_bytes));
   for (int i = 0; i < kPermRing; i++) CU(cudaEventCreateWithFlags(&f.perm_free[i], cudaEventDisableTiming));
   f.order.resize(p);
   for (int64_t j = 0; j < p; j++) f.order[j] = (int)j;
@@ -2091,6 +2193,7 @@ int bwgr_dist_init(bwgr_handle* h, int rank, int world, const void* id128, void*
   ncclUniqueId id;
   memcpy(&id, id128, 128);
   NC(nccl().CommInitRank(&h->comm, world, id, rank));
+  h->hx_own.cacheable = false;  // peers map it (cudaIpc): never handed to another owner
   if (h->hx_own.alloc((size_t)8 * world * 32 * 128) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(exchange ring) failed");
   CU(cudaMemset(h->hx_own.p, 0, sizeof(unsigned long long) * h->hx_own.n));
   cudaIpcMemHandle_t mh;

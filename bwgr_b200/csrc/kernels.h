@@ -84,6 +84,10 @@ void launch_gram_tc(const GenoView& g, const int* perm, int nblocks, void* gram,
 void launch_pack_2bit_fp4(const int8_t* src, int64_t ld, int p, uint8_t* dst, int* bad, cudaStream_t st);
 cudaError_t launch_gram_fp4(const uint8_t* x2f, int64_t ld, int p, int n, const int* perm, int nblocks, float* gram, int* err,
                             int num_sms, const float* sx, cudaStream_t st, bool block_per_cta = false);
+// host_narrow.cpp: one column of R's double matrix -> int8 codes, exactly (nonzero = not an integer code in [lo, hi])
+int narrow_column(const double* src, int64_t n, int8_t* out, int lo, int hi);
+int narrow_column_shifted(const double* src, int64_t n, int8_t* out, double shift, int lo, int hi);
+double column_min(const double* src, int64_t n);
 bool make_geno_tensor_map(const int8_t* x8, int64_t ld, int64_t p, void* tmap_out);
 // SIMT cross-check of the same quantity (debug / tests only; selected with BWGR_GRAM=simt).
 void launch_gram_simt(const GenoView& g, const int* perm, int nblocks, void* gram, int out_f32, cudaStream_t st);

@@ -80,6 +80,10 @@ BWGR_API int bwgr_create(int device, bwgr_handle** out);
 BWGR_API void bwgr_destroy(bwgr_handle* h);
 BWGR_API const char* bwgr_last_error(void);
 BWGR_API int bwgr_version(void);
+/* Device and pinned-host blocks released by destroyed handles are kept for reuse by the next handle of the process (an R session
+ * calls emRR(y, gen) repeatedly on the same shapes; cudaFree of gigabyte blocks is slow and erratic).  Bound: BWGR_CACHE_GB
+ * (default 24, 0 = keep nothing).  bwgr_trim() returns everything held to the driver. */
+BWGR_API void bwgr_trim(void);
 /* Use the caller's CUDA stream (cudaStream_t as void*) for all work of this handle; NULL = the
  * handle's own stream. Lets a host framework time the library with its own events. */
 BWGR_API int bwgr_set_stream(bwgr_handle* h, void* cuda_stream);
@@ -204,6 +208,11 @@ BWGR_API int bwgr_profile(bwgr_handle* h, int enable);
 BWGR_API int bwgr_profile_read(bwgr_handle* h, double* ms, int64_t* counts);
 /* Gram blocks X_B' X_B of one sweep order (perm[p], block markers each), int32, [nblocks][block][block];
  * the tcgen05 kernel's output, exposed so tests can check it bit-exactly. */
+/* Host-side test hook of the float64 loader's narrowing paths (csrc/host_narrow.cpp); needs no GPU.  level: -1 = the path the
+ * loader uses on this CPU, 0 plain, 1 AVX2, 2 AVX-512 (-1 returned if the CPU lacks it).  Returns 1 if any value is not an
+ * integer code in [lo, hi] (to 1e-4 after subtracting `shift` when use_shift), else 0. */
+BWGR_API int bwgr_debug_narrow(const double* src, int64_t n, int8_t* out, int use_shift, double shift, int lo, int hi, int level,
+                               double* min_out);
 BWGR_API int bwgr_debug_gram_band(bwgr_handle* h, const int32_t* perm, float* gram_out /* [nblocks][128][256] */, int* kind_out);
 BWGR_API int bwgr_debug_gram(bwgr_handle* h, const int32_t* perm, int block, int32_t* gram_out);
 

@@ -64,3 +64,48 @@ def test_cv_host_logic():
     assert pooled["m2"] == round(float(np.corrcoef(M[:, 1], obs)[0, 1]), 4)
     per = api._cv_summary([M[:25], M[25:]], ["m1", "m2", "m3"], avg=False)
     assert list(per) == ["CV_1", "CV_2"] and per["CV_2"]["m3"] == round(float(np.corrcoef(M[25:, 2], obs[25:])[0, 1]), 4)
+
+
+@pytest.mark.parametrize("level", [0, 1, 2, -1])
+def test_float64_loader_narrowing_paths(level):
+    """The loader of R's double matrix (capi.cu load_f64_common -> csrc/host_narrow.cpp): every code path (plain, AVX2, AVX-512)
+    narrows exact integer codes bit for bit and flags anything else -- fractions, NaN, infinities, out-of-range codes -- wherever in
+    the column it sits (vector body or scalar tail)."""
+    import ctypes as C
+
+    import numpy as np
+    cdll = _lib().load()
+    rng = np.random.default_rng(level + 5)
+
+    def run(col, use_shift=0, shift=0.0, lo=-128, hi=127):
+        col = np.ascontiguousarray(col, dtype=np.float64)
+        out = np.full(col.size, 77, dtype=np.int8)
+        mn = C.c_double()
+        rc = cdll.bwgr_debug_narrow(col.ctypes.data, col.size, out.ctypes.data, use_shift, float(shift), lo, hi, level, C.byref(mn))
+        return rc, out, mn.value
+
+    if run(np.zeros(4))[0] == -1:
+        pytest.skip("this CPU lacks the instruction set of level %d" % level)
+    for n in (1, 3, 15, 16, 17, 31, 64, 1000, 1003):
+        col = rng.integers(-128, 128, size=n).astype(np.float64)
+        rc, out, mn = run(col)
+        assert rc == 0 and np.array_equal(out, col.astype(np.int8)) and mn == col.min()
+        codes = rng.integers(0, 3, size=n)
+        rc, out, _ = run(codes, lo=0, hi=2)
+        assert rc == 0 and np.array_equal(out, codes.astype(np.int8))
+        # centred column: codes + a constant, float32-resolution noise allowed
+        shift = -0.73125
+        rc, out, _ = run(codes + shift + rng.uniform(-5e-5, 5e-5, size=n), use_shift=1, shift=shift, lo=0, hi=2)
+        assert rc == 0 and np.array_equal(out, codes.astype(np.int8))
+        for bad in (0.5, np.nan, np.inf, -np.inf, 128.0, -129.0, 3e9, 1e300, 1.0000001):
+            for pos in {0, n // 2, n - 1}:
+                c2 = col.copy()
+                c2[pos] = bad
+                assert run(c2)[0] == 1, (n, bad, pos)
+                if bad != 1.0000001:
+                    c3 = codes.astype(np.float64) + shift
+                    c3[pos] = bad
+                    assert run(c3, use_shift=1, shift=shift, lo=0, hi=2)[0] == 1, (n, bad, pos, "shifted")
+        c2 = codes.astype(np.float64)
+        c2[n // 2] = 3.0
+        assert run(c2, lo=0, hi=2)[0] == 1
