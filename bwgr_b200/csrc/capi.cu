@@ -207,6 +207,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;  // optional (NCCL >= 2.18)
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
 };
@@ -222,6 +223,7 @@ NcclApi& nccl() {
       api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
       api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(lib, "ncclAllReduce"));
       api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+      api.CommSplit = reinterpret_cast<decltype(api.CommSplit)>(dlsym(lib, "ncclCommSplit"));
       api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
       api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy;
     }
@@ -263,6 +265,7 @@ struct bwgr_handle {
   int world = 1, rank = 0;
   int64_t n_global = 0;
   ncclComm_t comm = nullptr;
+  ncclComm_t comm_side = nullptr;  // second communicator over the same ranks: collectives of the side stream (Gram band computed ahead)
   DevBuf<unsigned long long> hx_own;        // this rank's exchange ring [8][world][32][128]
   unsigned long long* hx[8] = {};           // every rank's ring as seen from this process (peer memory)
   bool hx_connected = false;
@@ -519,6 +522,7 @@ void bwgr_destroy(bwgr_handle* h) {
   h->fit.reset();
   for (int r = 0; r < h->world; r++)
     if (r != h->rank && h->hx[r]) cudaIpcCloseMemHandle(h->hx[r]);
+  if (h->comm_side && nccl().ok) nccl().CommDestroy(h->comm_side);
   if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->side) cudaStreamDestroy(h->side);
@@ -806,7 +810,14 @@ bool plan_pipe(const bwgr_handle* h, int model, int ns, PipePlan* pl) {
   const char* sw = getenv("BWGR_SWEEP");
   if (sw && !strcmp(sw, "v4")) return false;
   if (h->storage != BWGR_STORE_I8 || ns > 32) return false;
-  const int sms = h->grid > 1 ? std::min(h->grid, h->num_sms) : h->num_sms;
+  int sms = h->grid > 1 ? std::min(h->grid, h->num_sms) : h->num_sms;
+  if (const char* ge = getenv("BWGR_GRID")) { const int v = atoi(ge); if (v > 1) sms = std::min(v, h->num_sms); }  // CTAs of the flat topology
+  else if (h->world > 1 && h->grid <= 1 && h->x2f.p && h->comm_side && h->num_sms > 64) {
+    // row-sharded fit, flat topology: the per-block chain is latency-bound, so ~104 CTAs sweep as fast as 148 and the SMs left idle
+    // compute the next sweep's Gram band meanwhile (measured at 50k x 50k: 104 CTAs 1.54 ms per sweep, 120: 1.68, 148: 1.84)
+    const int want = h->num_sms - 44;
+    if ((h->ld + want - 2) / (want - 1) <= 496) sms = want;
+  }
   if (sms < 2) return false;
   const int W0 = sms - 1;
   const int R = (int)(((h->ld + W0 - 1) / W0 + 15) / 16 * 16);
@@ -825,7 +836,8 @@ bool plan_pipe(const bwgr_handle* h, int model, int ns, PipePlan* pl) {
   pl->cl = 0; pl->nclusters = 0;
   // Clustered topology (sweep_pipe.cu): thread-block clusters of one solver + seven workers; partial sums and steps travel
   // through distributed shared memory, one L2 hop per block is left (the exchange of the cluster sums between the solvers).
-  // Single GPU, at most four systems; BWGR_CLUSTER=0 keeps the flat topology (one solver CTA, two-hop L2 tree).
+  // Single GPU, at most four systems; BWGR_CLUSTER=0 keeps the flat topology (one solver CTA, two-hop L2 tree).  Row-sharded fits use
+  // the flat one: a clustered variant with a third (NVLink) hop after the cluster exchange measured 1.79 ms against 1.43 ms per sweep.
   const char* ce = getenv("BWGR_CLUSTER");
   if (D >= 1 && h->world <= 1 && h->grid <= 1 && !(ce && !strcmp(ce, "0")) && sweep_pipe_cluster_ok(model, ns, full_inv)) {
     {
@@ -1183,8 +1195,8 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
         // the clustered sweep occupies 8 x nclusters of the SMs: the next sweep's Gram band (a function of the marker order only)
         // is computed on the others meanwhile.  BWGR_OVERLAP=0 keeps everything on one stream.
         const char* ov = getenv("BWGR_OVERLAP");
-        f.overlap = f.cl && h->world <= 1 && h->wait32 && h->x2f.p && f.nband == 2 && !h->gram_simt && !(ov && !strcmp(ov, "0")) &&
-                    f.nclusters * 8 < h->num_sms;
+        f.overlap = (h->world <= 1 || h->comm_side) && h->wait32 && h->x2f.p && f.nband == 2 && !h->gram_simt && !(ov && !strcmp(ov, "0")) &&
+                    f.grid + 8 <= h->num_sms;  // at least a few SMs are left idle by the sweep
         if (f.overlap && f.gram2.alloc(gram_n) != cudaSuccess) { cudaGetLastError(); f.overlap = false; }
       }
       if (!f.overlap) f.gram2.release();
@@ -1312,6 +1324,10 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
             const cudaError_t ge = launch_gram_fp4(h->x2f.p, h->ld, (int)h->p, (int)h->n_global, np_, f.nblocks, ((sweep + 1) & 1) ? f.gram2.p : f.gram.p,
                                                    h->err.p, h->num_sms, f.sx_dev.p, h->side, true);
             if (ge != cudaSuccess) return fail(BWGR_ERR_CUDA, "FP4 Gram launch failed: %s", cudaGetErrorString(ge));
+            if (h->world > 1) {  // row shards: the band is a sum over individuals; its own communicator, so it never queues behind (or ahead of) the main stream's
+              float* gn = ((sweep + 1) & 1) ? f.gram2.p : f.gram.p;
+              NC(nccl().AllReduce(gn, gn, (size_t)f.nblocks * kBlk * kBlk * f.nband, ncclFloat, ncclSum, h->comm_side, h->side));
+            }
             CU(cudaEventRecord(h->side_done[(sweep + 1) & 1], h->side));
             f.gram_ahead = sweep + 1;
             h->launches++;
@@ -2193,6 +2209,7 @@ int bwgr_dist_init(bwgr_handle* h, int rank, int world, const void* id128, void*
   ncclUniqueId id;
   memcpy(&id, id128, 128);
   NC(nccl().CommInitRank(&h->comm, world, id, rank));
+  if (nccl().CommSplit && nccl().CommSplit(h->comm, 0, rank, &h->comm_side, nullptr) != ncclSuccess) h->comm_side = nullptr;
   h->hx_own.cacheable = false;  // peers map it (cudaIpc): never handed to another owner
   if (h->hx_own.alloc((size_t)8 * world * 32 * 128) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(exchange ring) failed");
   CU(cudaMemset(h->hx_own.p, 0, sizeof(unsigned long long) * h->hx_own.n));

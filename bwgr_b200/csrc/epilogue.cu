@@ -8,6 +8,8 @@
 //   BayesL :795-800   BayesCpi :900-908   BayesDpi :966-970
 // Sums over rows / markers are accumulated in double and rounded once (the reference sums in float
 // packets; both are within float reassociation noise of each other).
+#include <cooperative_groups.h>
+
 #include "kernels.h"
 
 namespace bwgr {
@@ -27,11 +29,19 @@ __device__ double block_sum(double v, double* sh) {
   return sh[0];
 }
 
-__global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
+// A cluster of kEpiCl CTAs per system: one CTA alone spends ~100 k cycles on the double-precision sums over n rows and p markers
+// (ncu: a single SM busy for 52 us at 50k x 50k); the partial sums meet in CTA 0 through distributed shared memory, in rank order.
+constexpr int kEpiCl = 8;
+
+__global__ void __cluster_dims__(kEpiCl, 1, 1) __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ double sh[32];
+  __shared__ double part[kEpiCl][8];
   __shared__ float s_eM, s_ve, s_cxx, s_lmb;
   __shared__ int s_acc;
-  const int sys = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  const int cr = (int)cluster.block_rank();
+  const int sys = blockIdx.x / kEpiCl, tid = threadIdx.x, T = blockDim.x * kEpiCl, gt = cr * (int)blockDim.x + tid;
   SysScalars* scp = a.sc + sys;
   if (scp->done) return;
   float* e = a.e + (size_t)sys * a.ld;
@@ -45,11 +55,21 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
   double se = 0, see = 0, sey = 0, sy = 0;
   float emax = 0.0f;
   if (!a.esum)  // row-sharded fit: the sums over individuals were taken per rank and all-reduced (a.esum)
-    for (int i = tid; i < a.n; i += T) {
-      if (mask && !mask[i]) continue;
-      const double ev = e[i], yv = y[i];
-      se += ev; see += ev * ev; sey += ev * yv; sy += yv;
-      emax = fmaxf(emax, fabsf(e[i]));
+    for (int i0 = gt; i0 < a.n; i0 += 8 * T) {  // one CTA walks the vector: eight loads in flight per thread, or latency is all there is
+      float ev[8], yv[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int i = i0 + u * T;
+        const bool ok = i < a.n && (!mask || mask[i]);
+        ev[u] = ok ? e[i] : 0.0f;
+        yv[u] = ok ? y[i] : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const double ed = ev[u], yd = yv[u];
+        se += ed; see += ed * ed; sey += ed * yd; sy += yd;
+        emax = fmaxf(emax, fabsf(ev[u]));
+      }
     }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
@@ -57,22 +77,46 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
   if ((tid & 31) == 0) sh_max[tid >> 5] = emax;
   __syncthreads();
   emax = 0.0f;
-  for (int w = 0; w < (T >> 5); w++) emax = fmaxf(emax, sh_max[w]);
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) emax = fmaxf(emax, sh_max[w]);
   double sbb = 0, sd = 0, scnv = 0;
-  for (int j = tid; j < a.p; j += T) {
-    const double bj = b[j];
-    sbb += bj * bj;
-    if (d) sd += d[j];
-    if (a.b_prev) scnv += fabs((double)a.b_prev[(size_t)sys * a.p + j] - bj);
+  for (int j0 = gt; j0 < a.p; j0 += 8 * T) {
+    float bv[8], dv[8], pv[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int j = j0 + u * T;
+      const bool ok = j < a.p;
+      bv[u] = ok ? b[j] : 0.0f;
+      dv[u] = (ok && d) ? d[j] : 0.0f;
+      pv[u] = (ok && a.b_prev) ? a.b_prev[(size_t)sys * a.p + j] : bv[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const double bj = bv[u];
+      sbb += bj * bj;
+      sd += (double)dv[u];
+      scnv += fabs((double)pv[u] - bj);
+    }
   }
   se = block_sum(se, sh); see = block_sum(see, sh); sey = block_sum(sey, sh); sy = block_sum(sy, sh);
   sbb = block_sum(sbb, sh); sd = block_sum(sd, sh); scnv = block_sum(scnv, sh);
+  if (tid == 0) {  // this CTA's sums into CTA 0's table
+    double* dst = cluster.map_shared_rank(&part[0][0], 0) + cr * 8;
+    dst[0] = se; dst[1] = see; dst[2] = sey; dst[3] = sy; dst[4] = sbb; dst[5] = sd; dst[6] = scnv; dst[7] = (double)emax;
+  }
+  cluster.sync();
+  if (cr == 0 && tid == 0) {
+    se = see = sey = sy = sbb = sd = scnv = 0.0; emax = 0.0f;
+    for (int c = 0; c < kEpiCl; c++) {
+      se += part[c][0]; see += part[c][1]; sey += part[c][2]; sy += part[c][3]; sbb += part[c][4]; sd += part[c][5]; scnv += part[c][6];
+      emax = fmaxf(emax, (float)part[c][7]);
+    }
+  }
   if (a.esum) {
     se = a.esum[4 * sys + 0]; see = a.esum[4 * sys + 1]; sey = a.esum[4 * sys + 2]; sy = a.esum[4 * sys + 3];
     emax = a.emaxv[sys];
   }
 
-  if (tid == 0) {
+  if (cr == 0 && tid == 0) {
     SysScalars s = *scp;
     const float n = s.n_eff, p = (float)a.p;
     const float ee = (float)see, bb = (float)sbb;
@@ -203,12 +247,17 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
     s_acc = accumulate;
     s_ve = s.ve; s_cxx = s.cxx; s_lmb = s.lmb;
   }
-  __syncthreads();
+  cluster.sync();
+  if (cr != 0 && tid == 0) {  // the scalars every CTA needs for its share of the element-wise passes
+    s_eM = *cluster.map_shared_rank(&s_eM, 0); s_acc = *cluster.map_shared_rank(&s_acc, 0);
+    s_ve = *cluster.map_shared_rank(&s_ve, 0); s_cxx = *cluster.map_shared_rank(&s_cxx, 0); s_lmb = *cluster.map_shared_rank(&s_lmb, 0);
+  }
+  cluster.sync();  // CTA 0 stays until its shared memory has been read
   const float eM = s_eM;
   if (model == M_EMDE && vbv) {  // :293-296 ; Vb_j = b_j^2 + Ve/(xx_j + Lmb_j + 1e-4), Lmb_j = sqrt(cxx Ve / Vb_j)
     const float* xx = a.xx + (a.xx_per_sys ? (size_t)sys * a.p : 0);
     const float Ve = s_ve, cxx = s_cxx;
-    for (int j = tid; j < a.p; j += T) {
+    for (int j = gt; j < a.p; j += T) {
       float xxj = xx[j];
       if (xxj == 0.0f) xxj = 0.1f;  // :261
       const float Vb = b[j] * b[j] + Ve / (xxj + vbv[j] + 0.0001f);
@@ -216,12 +265,12 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
     }
   }
   if (model == M_EMMLD && vbv && a.wts) {  // :495 ; the penalty of marker j is Lmb / d_j
-    for (int j = tid; j < a.p; j += T) vbv[j] = s_lmb / a.wts[j];
+    for (int j = gt; j < a.p; j += T) vbv[j] = s_lmb / a.wts[j];
   }
   if ((model == M_GSRR || model == M_GSFLM) && vbv) {  // the per-marker slot carries Lmb_j + 0.01 (the rule's denominator)
     const float* xx = a.xx + (a.xx_per_sys ? (size_t)sys * a.p : 0);
     const float vna = s_ve, phi = s_cxx;
-    for (int j = tid; j < a.p; j += T) {
+    for (int j = gt; j < a.p; j += T) {
       if (model == M_GSRR) vbv[j] = s_lmb + 0.01f;  // :1621-1623
       else {                                        // :1588-1589 ; Vb_j = b_j^2 + vna/(xx_j + Lmb_j), Lmb_j = sqrt(phi vna / Vb_j)
         const float Vb = b[j] * b[j] + vna / (xx[j] + (vbv[j] - 0.01f));
@@ -230,15 +279,18 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(EpilogueArgs a) {
     }
   }
   if (eM != 0.0f)
-    for (int i = tid; i < a.n; i += T) {
-      if (mask && !mask[i]) continue;
-      e[i] -= eM;
+    for (int i0 = gt; i0 < a.n; i0 += 8 * T) {
+      float ev[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) { const int i = i0 + u * T; ev[u] = i < a.n ? e[i] : 0.0f; }
+#pragma unroll
+      for (int u = 0; u < 8; u++) { const int i = i0 + u * T; if (i < a.n && (!mask || mask[i])) e[i] = ev[u] - eM; }
     }
   if (s_acc && a.B) {
     float* B = a.B + (size_t)sys * a.p;
-    for (int j = tid; j < a.p; j += T) B[j] += b[j];
-    if (a.D && d) { float* D = a.D + (size_t)sys * a.p; for (int j = tid; j < a.p; j += T) D[j] += d[j]; }
-    if (a.VBv && vbv) { float* V = a.VBv + (size_t)sys * a.p; for (int j = tid; j < a.p; j += T) V[j] += vbv[j]; }
+    for (int j = gt; j < a.p; j += T) B[j] += b[j];
+    if (a.D && d) { float* D = a.D + (size_t)sys * a.p; for (int j = gt; j < a.p; j += T) D[j] += d[j]; }
+    if (a.VBv && vbv) { float* V = a.VBv + (size_t)sys * a.p; for (int j = gt; j < a.p; j += T) V[j] += vbv[j]; }
   }
 }
 
@@ -356,6 +408,6 @@ void launch_wgr_step(const WgrArgs& a, int num_sms, cudaStream_t st) {
   wgr_markers_kernel<<<num_sms, 256, 0, st>>>(a);
 }
 
-void launch_epilogue(const EpilogueArgs& a, cudaStream_t st) { epilogue_kernel<<<a.nsys, 1024, 0, st>>>(a); }
+void launch_epilogue(const EpilogueArgs& a, cudaStream_t st) { epilogue_kernel<<<a.nsys * kEpiCl, 1024, 0, st>>>(a); }
 
 }  // namespace bwgr

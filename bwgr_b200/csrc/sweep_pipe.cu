@@ -813,6 +813,10 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
             qq = dead ? 0 : word_val(wv);
           }
           if (w == 0) SSTAMPW(b, 8);
+          if (!CL && b == 0 && w == 0 && lane == 0 && a.started) {  // flat topology: the first reduced h means every worker is resident
+            *reinterpret_cast<volatile unsigned int*>(a.started) = a.started_val;
+            __threadfence_system();
+          }
           g = (float)((double)qq * (double)Sy.e_q);
         }
         if (D > 0 && b > 0) {
@@ -997,6 +1001,10 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
               }
             }
             if (s == 0) SSTAMP(b, 8);
+            if (!CL && b == 0 && s == 0 && lane == 0 && a.started) {
+              *reinterpret_cast<volatile unsigned int*>(a.started) = a.started_val;
+              __threadfence_system();
+            }
 #pragma unroll
             for (int t = 0; t < 4; t++) {
               g[t] = (float)((double)qq[t] * (double)Sy.e_q);
