@@ -841,9 +841,15 @@ bool plan_pipe(const bwgr_handle* h, int model, int ns, PipePlan* pl) {
   const char* ce = getenv("BWGR_CLUSTER");
   if (D >= 1 && h->world <= 1 && h->grid <= 1 && !(ce && !strcmp(ce, "0")) && sweep_pipe_cluster_ok(model, ns, full_inv)) {
     {
-      for (int nbuf = D + 2; nbuf >= D + 1; nbuf--) {
+      // The sweep is latency-bound: 14 clusters sweep as fast as 15 (measured 1.226 against 1.235 ms at 50k x 50k), and every SM left
+      // idle works on the next sweep's Gram band meanwhile (capi.cu fit_sweeps).  First choice: leave at least 36 SMs; if the rows per
+      // worker then exceed the tile (512), take every cluster that fits.  BWGR_MAXCL=k overrides.
+      const int cap_side = std::max(2, (h->num_sms - 36) / 8);
+      for (int nbuf = D + 2; nbuf >= D + 1; nbuf--)
+      for (int pass = 0; pass < 2; pass++) {
         // rows per worker depend on the number of co-resident clusters, which depends on the shared memory per CTA: iterate
-        int C = 18;
+        int C = pass == 0 ? std::min(18, cap_side) : 18;
+        if (const char* mc = getenv("BWGR_MAXCL")) { const int v = atoi(mc); if (v >= 2) C = std::min(v, 18); }
         for (int iter = 0; iter < 4 && C >= 2; iter++) {
           const int Wc = 7 * C;
           const int Rc = (int)(((h->ld + Wc - 1) / Wc + 15) / 16 * 16);
@@ -1456,6 +1462,21 @@ int bwgr_em_sweeps(bwgr_handle* h, int nsweeps) {
   return fit_sweeps(h, nsweeps);
 }
 
+// debug (BWGR_TRACE=file): raw int64 stamps of the last sweep, [cta][block][32]
+static void dump_trace(bwgr_handle* h) {
+  Fit& f = h->fit;
+  if (!f.trace.p || !getenv("BWGR_TRACE")) return;
+  cudaStreamSynchronize(h->stream);
+  std::vector<long long> tr(f.trace.n);
+  cudaMemcpy(tr.data(), f.trace.p, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+  if (FILE* fp = fopen(getenv("BWGR_TRACE"), "wb")) {
+    const long long hdr[4] = {f.pipe ? f.grid : 1, f.nblocks, 32, f.lookahead};
+    fwrite(hdr, sizeof(long long), 4, fp);
+    fwrite(tr.data(), sizeof(long long), tr.size(), fp);
+    fclose(fp);
+  }
+}
+
 int bwgr_em_end(bwgr_handle* h, bwgr_em_out* out) {
   if (!h || !h->fit.active) return fail(BWGR_ERR_STATE, "no fit in progress");
   if (!out) return fail(BWGR_ERR_ARG, "out NULL");
@@ -1464,16 +1485,7 @@ int bwgr_em_end(bwgr_handle* h, bwgr_em_out* out) {
   const int ns = f.nsys;
   int rc = check_err_flag(h, "sweep");
   if (rc) { f.reset(); return rc; }
-  if (f.trace.p && getenv("BWGR_TRACE")) {  // debug: raw int64 stamps of the last sweep, [cta][block][16]
-    std::vector<long long> tr(f.trace.n);
-    cudaMemcpy(tr.data(), f.trace.p, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-    if (FILE* fp = fopen(getenv("BWGR_TRACE"), "wb")) {
-      const long long hdr[4] = {f.pipe ? f.grid : 1, f.nblocks, 32, f.lookahead};
-      fwrite(hdr, sizeof(long long), 4, fp);
-      fwrite(tr.data(), sizeof(long long), tr.size(), fp);
-      fclose(fp);
-    }
-  }
+  dump_trace(h);
   std::vector<SysScalars> sc(ns);
   CU(cudaMemcpyAsync(sc.data(), f.sc.p, sizeof(SysScalars) * ns, cudaMemcpyDeviceToHost, h->stream));
   std::vector<float> hb((size_t)ns * p), hd, hv, hh((size_t)ns * n), he;
@@ -1810,6 +1822,7 @@ int bwgr_wgr_fit(bwgr_handle* h, const double* y, int it, int bi, int th, int iv
   if (rc) return rc;
   rc = check_err_flag(h, "wgr sweep");
   if (rc) { f.reset(); return rc; }
+  dump_trace(h);
   WgrState st;
   CU(cudaMemcpyAsync(&st, f.wst.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
   std::vector<float> B(p), D(p), V(p);
@@ -2185,6 +2198,7 @@ int bwgr_mrr3_fit(bwgr_handle* h, int f32_variant, const double* Y, int k, const
     for (int i = 0; i < numit; i++) { cnv_out[i] = cnvB[i]; cnv_out[maxit + i] = cnvH2[i]; cnv_out[2 * maxit + i] = cnvV[i]; }
   if (its_out) *its_out = numit;
   // the swapped buffers go back to their owners before the fit is released
+  dump_trace(h);
   f.reset();
   return 0;
 }

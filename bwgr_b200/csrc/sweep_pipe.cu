@@ -1065,11 +1065,17 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
                   ag[4 * k4 + 0] = -av[d] * gv.x; ag[4 * k4 + 1] = -av[d] * gv.y;
                   ag[4 * k4 + 2] = -av[d] * gv.z; ag[4 * k4 + 3] = -av[d] * gv.w;
                 }
+                // x_k (final) -> x_{k+1} is the chain.  The broadcast of lane k+1 is taken off it: its value BEFORE step k is shuffled
+                // out ahead, and every lane applies step k to it with the owner's own coefficient and FMA (same bits).
                 float x = r[d];
+                float xk = __shfl_sync(0xffffffffu, x, 0);
+                const float* gcol = Gb + (size_t)tri(d, d) * kTileF;
 #pragma unroll
                 for (int k = 0; k < 31; k++) {
-                  const float xk = __shfl_sync(0xffffffffu, x, k);
+                  const float pre = __shfl_sync(0xffffffffu, x, k + 1);
+                  const float cn = -mk[32 * d + k + 1].a * gcol[(k + 1) * kTS + k];
                   if (lane > k) x = fmaf(ag[k], xk, x);
+                  xk = fmaf(cn, xk, pre);
                 }
                 acc = x;
               }
@@ -1099,20 +1105,39 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
               }
             }
           } else {
+            // The chain: g of marker jj -> rule -> step -> g of marker jj + 1.  Lane jj + 1 owns that g, but its broadcast does not
+            // have to sit on the chain: its value BEFORE step jj is shuffled out while the rule of jj is evaluated, and every lane
+            // applies step jj to it with the same fused multiply-add the owner uses (same bits).  Chain per marker = rule + one FMA.
+            // The marker's own inputs (coefficients, draws, xx) are read one marker ahead: their shared-memory latency would otherwise
+            // open every link of the chain (the loop has no early exit for the same reason: markers past the end of the last block
+            // are walked with a zero step).
+            float gc = __shfl_sync(0xffffffffu, g[0], 0);
+            MarkerSys in_n = mk[0];
+            MarkerDraws dr_n;
+            if (kGibbs) dr_n = drb[0];
+            else { dr_n.z1 = dr_n.z2 = dr_n.u = 0.0f; dr_n.chi = 1.0f; }
+            float xx_n = mc[0].xx;
 #pragma unroll
             for (int t = 0; t < 4; t++) {
 #pragma unroll 8
               for (int i = 0; i < 32; i++) {
                 const int jj = 32 * t + i;
-                if (jj >= nvalid) break;
-                const float gc = __shfl_sync(0xffffffffu, g[t], i);
-                const MarkerSys in = mk[jj];
-                MarkerDraws dr;
-                if (kGibbs) dr = drb[jj];
-                else { dr.z1 = dr.z2 = dr.u = 0.0f; dr.chi = 1.0f; }
+                const bool valid = jj < nvalid;
+                const MarkerSys in = in_n;
+                const MarkerDraws dr = dr_n;
+                const float xxj_ = xx_n;
+                {
+                  const int jn = jj < 127 ? jj + 1 : 127;
+                  in_n = mk[jn];
+                  if (kGibbs) dr_n = drb[jn];
+                  xx_n = mc[jn].xx;
+                }
+                // marker jj + 1 as its owner has it now (steps 0 .. jj-1 applied), and the Gram element that couples it to marker jj
+                const float gnext = i < 31 ? __shfl_sync(0xffffffffu, g[t], i + 1) : __shfl_sync(0xffffffffu, g[t < 3 ? t + 1 : 3], 0);
+                const float Gnext = i < 31 ? Gb[(size_t)tri(t, t) * kTileF + i * kTS + i + 1] : Gb[(size_t)tri(t < 3 ? t + 1 : 3, t) * kTileF + i * kTS];
                 RuleOut ro;
                 if (kSlabDraw) {
-                  const float xxj = mc[jj].xx, b1 = fmaf(gc, in.a, in.c), b2 = dr.z2;
+                  const float xxj = xxj_, b1 = fmaf(gc, in.a, in.c), b2 = dr.z2;
                   // ||e2||^2 - ||e1||^2 in closed form: KMUP compares the two draws, BayesB/C the draw against b = 0 (:673)
                   // (BayesDpi :953-955 compares the two draws too, with its own acceptance threshold folded into dr.u)
                   const float q = (MODEL == M_KMUP || MODEL == M_BDPI) ? (b2 - b1) * fmaf(xxj, (b1 + b2) - 2.0f * in.b0, -2.0f * gc)
@@ -1122,14 +1147,14 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
                   ro.de = ro.b - in.b0;
                   ro.vbj = (MODEL == M_BB || MODEL == M_BDPI) ? (Sy.Sb + ro.b * ro.b) / dr.chi : in.vbj;
                 } else if (kSlabEM) {
-                  const float xxj = mc[jj].xx, b1 = fmaf(gc, in.a, in.c);
+                  const float xxj = xxj_, b1 = fmaf(gc, in.a, in.c);
                   const float LR = Sy.Pi0 * expf(Sy.C * (b1 * fmaf(xxj, 2.0f * in.b0 - b1, 2.0f * gc)));
                   ro.d = __frcp_rn(1.0f + LR);
                   ro.b = b1 * ro.d;
                   ro.de = ro.b - in.b0;
                   ro.vbj = MODEL == M_EMBB ? (Sy.Sb + ro.b * ro.b) / (Sy.df + 1.0f) : in.vbj;
                 } else if (kFoldEM) {
-                  const float OLS = fmaf(mc[jj].xx, in.b0, gc);
+                  const float OLS = fmaf(xxj_, in.b0, gc);
                   if (MODEL == M_EMBL) {  // in.a = 0.5/(Lmb2 + xx), in.c = 0.5/(xx + cxx)
                     const float Half = OLS * in.c;
                     const float G = (OLS > 0.0f ? OLS - Sy.lmb1 : OLS + Sy.lmb1) * in.a;
@@ -1145,13 +1170,15 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
                   ro.de = ro.b - in.b0;
                   ro.vbj = in.vbj;
                 } else {
-                  ro = marker_rule<MODEL>(gc, mc[jj].xx, in.b0, in.vbj, Sy, dr);
+                  ro = marker_rule<MODEL>(gc, xxj_, in.b0, in.vbj, Sy, dr);
                 }
-                if (lane == i) { nb[t] = ro.b; nd[t] = ro.d; nv[t] = ro.vbj; de[t] = ro.de; }
+                if (!valid) ro.de = 0.0f;
+                if (lane == i && valid) { nb[t] = ro.b; nd[t] = ro.d; nv[t] = ro.vbj; de[t] = ro.de; }
                 // row jj of the Gram block to the right of (and inside) its diagonal tile: stored as tile (tt, t)
 #pragma unroll
                 for (int tt = 0; tt < 4; tt++)
                   if (tt >= t) g[tt] = fmaf(-Gb[(size_t)tri(tt, t) * kTileF + i * kTS + lane], ro.de, g[tt]);
+                gc = fmaf(-Gnext, ro.de, gnext);
               }
               if (D > 0) {
                 dh[32 * t + lane] = de[t];
