@@ -12,3 +12,4 @@ echo "launch list rc=$?"
 timeout 300 $CMD > gpurun_out/plain2_${TAG}.log 2>&1 &&
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"sweep_pipe|gram_fp4" -s 4 -c 2 -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
 echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full_${TAG}.log
+timeout 600 python tools/cfg4_probe.py > gpurun_out/cfg4_probe_${TAG}.log 2>&1; echo "cfg4 probe rc=$?"; tail -3 gpurun_out/cfg4_probe_${TAG}.log
