@@ -517,7 +517,8 @@ def _cv_holdouts(n_rows, k, n, llo, seed):
     draws come from numpy, not from R's sample()), or one set per level of `llo` (leave-level-out, R/cv.R:45-48)."""
     if llo is not None:
         llo = np.asarray(llo)
-        return [np.flatnonzero(llo == lev) for lev in np.unique(llo)]
+        lev, first = np.unique(llo, return_index=True)
+        return [np.flatnonzero(llo == v) for v in lev[np.argsort(first)]]  # unique(as.character(llo)): order of first appearance
     rng = np.random.default_rng(seed)
     nk = int(round(n_rows / k))
     return [np.sort(rng.choice(n_rows, nk, replace=False)) for _ in range(n)]
@@ -526,9 +527,15 @@ def _cv_holdouts(n_rows, k, n, llo, seed):
 def _cv_summary(gebv, models, avg):
     """sCV of R/cv.R:86-101: predictive ability = correlation of each model's column with OBSERVATION, over the pooled
     hold-outs (avg, sorted decreasing) or per hold-out; rounded to four digits like the reference."""
-    def pa(M):
+    def pa(M):  # cor(..., use = 'p') of R/cv.R:88 / :97: pairwise-complete rows for every (model, OBSERVATION) pair
+        obs = M[:, -1]
+        out = np.full(M.shape[1] - 1, np.nan)
         with np.errstate(invalid="ignore", divide="ignore"):
-            return np.corrcoef(M, rowvar=False)[-1, :-1]
+            for j in range(M.shape[1] - 1):
+                ok = np.isfinite(M[:, j]) & np.isfinite(obs)
+                if ok.sum() > 1:
+                    out[j] = np.corrcoef(M[ok, j], obs[ok])[0, 1]
+        return out
     if avg:
         c = pa(np.concatenate(gebv, axis=0))
         order = np.argsort(-c, kind="stable")
@@ -596,7 +603,9 @@ def emCV(y, gen, k=5, n=5, Pi=0.75, alpha=0.02, df=10, R2=0.5, avg=True, llo=Non
 
 def mcmcCV(y, gen, k=5, n=5, it=1500, bi=500, pi=0.95, df=5, R2=0.5, avg=True, llo=None, tbv=None, ReturnGebv=False, seed=1,
            group=None):
-    """mcmcCV of R/cv.R:110-216: the seven Gibbs samplers per hold-out."""
+    """mcmcCV of R/cv.R:110-216: the seven Gibbs samplers per hold-out.  Deliberate deviation: every column is labelled with the
+    model that produced it; the reference fits BayesRR, BayesCpi, BayesDpi as f5..f7 (cv.R:128-130) but names those columns BayesCpi,
+    BayesDpi, BayesRR (:132-133), i.e. its last three labels are rotated."""
     def fit_one(m, yk, g):
         kw = dict(R2=R2, df=df, it=it, bi=bi, seed=seed)
         if m in ("BayesB", "BayesC"):

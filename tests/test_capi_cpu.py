@@ -56,6 +56,7 @@ def test_cv_host_logic():
     assert [w.tolist() for w in hs] == [w.tolist() for w in api._cv_holdouts(196, 5, 3, None, 7)]            # seed-reproducible
     lev = np.array(list("aabbbcc"))
     assert [w.tolist() for w in api._cv_holdouts(7, 5, 5, lev, 1)] == [[0, 1], [2, 3, 4], [5, 6]]             # leave-level-out
+    assert [w.tolist() for w in api._cv_holdouts(5, 5, 5, np.array(list("zzaaz")), 1)] == [[0, 1, 4], [2, 3]]  # levels in order of appearance
     rng = np.random.default_rng(0)
     obs = rng.normal(size=50)
     M = np.stack([obs + rng.normal(size=50) * s for s in (2.0, 0.1, 0.7)] + [obs], axis=1)

@@ -799,7 +799,8 @@ def test_emml_marker_weights(tpod, path):
 
 @pytest.mark.parametrize("env", [{"BWGR_CLUSTER": "0"}, {"BWGR_CLUSTER": "0", "BWGR_LOOKAHEAD": "0"}, {"BWGR_TINV": "0"}, {"BWGR_SWEEP": "v4"},
                                  {"BWGR_GRAM": "fp8"}, {"BWGR_GRAM": "i8"}, {"BWGR_GRAM": "simt"}, {"BWGR_TMA": "1", "BWGR_GRAM": "fp8"},
-                                 {"BWGR_GRAM_PACKED": "0", "BWGR_GRAM": "fp8"}, {"BWGR_OVERLAP": "0"}])
+                                 {"BWGR_GRAM_PACKED": "0", "BWGR_GRAM": "fp8"}, {"BWGR_OVERLAP": "0"}, {"BWGR_MAXCL": "18"},
+                                 {"BWGR_CLUSTER": "0", "BWGR_GRID": "100"}, {"BWGR_LOAD_THREADS": "3", "BWGR_CACHE_GB": "0"}])
 def test_every_kernel_variant_behind_a_switch(monkeypatch, env):
     """Every alternative kernel the library can select (flat topology, no look-ahead, stepwise in-block solve, the v4 sweep, the
     E4M3 / int8 / SIMT Gram kernels, the TMA gather4 and unpacked producers) fits the same data to the same parity bar as the default."""
