@@ -283,6 +283,16 @@ struct bwgr_handle {
   int fp8_codes = 0;  // all genotypes are codes 0..7 (and n small enough): the Gram kernel may use the exact E4M3 path
   int64_t launches = 0;
   Fit fit;
+  // debug (BWGR_GAPS=1): events at the kernel boundaries of every sweep on the main stream, printed by bwgr_em_end
+  std::vector<cudaEvent_t> gap_ev;
+  void gap_mark() {
+    static const bool on = getenv("BWGR_GAPS") != nullptr;
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, stream);
+    gap_ev.push_back(e);
+  }
   // optional per-kernel timing (bwgr_profile)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[4];  // gram, sweep, epilogue, block inverses
@@ -1174,6 +1184,13 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
     f.pipe = plan_pipe(h, s.model, ns, &pl);
     if (dist) {
       if (!f.pipe) return fail(BWGR_ERR_UNSUPPORTED, "row-sharded fit: the shape does not fit the pipelined blocked sweep");
+      {  // the per-rank Gram bands are summed in float by ncclAllReduce: exact (= independent of the sharding) only below 2^24.
+         // |G_jk| <= max_j xx_j (Cauchy-Schwarz) over ALL individuals; h_xx holds the all-reduced column statistics.
+        double xxmax = 0;
+        for (double v : h->h_xx) xxmax = std::max(xxmax, v);
+        if (!(xxmax < 16777216.0))
+          return fail(BWGR_ERR_UNSUPPORTED, "row-sharded fit: max_j sum_i x_ij^2 = %.0f >= 2^24, the float sum of the per-GPU Gram bands would depend on the sharding", xxmax);
+      }
       // stale words of a previous fit (another nsys = another ring layout) must not be mistaken for this fit's: zero my ring,
       // then a collective as the barrier that no peer writes into it before it is clean
       CU(cudaMemsetAsync(h->hx_own.p, 0, sizeof(unsigned long long) * h->hx_own.n, h->stream));
@@ -1287,6 +1304,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
         if (h->world > 1)  // row shards: the Gram band is a sum over individuals (exact: integers below 2^24 in fp32)
           NC(nccl().AllReduce(f.gram_p, f.gram_p, (size_t)f.nblocks * kBlk * kBlk * f.nband, ncclFloat, ncclSum, h->comm, h->stream));
       }
+      h->gap_mark();  // 0: band of this sweep available
       if (f.pipe && f.full_inv) {  // the step coefficients change every sweep (lambda), the inverses with them
         cudaEvent_t pi = h->prof_begin(3);
         launch_block_inverse(f.model, d_perm, (int)p, f.nblocks, f.gram_p, f.nband, f.xx_over.p ? f.xx_over.p : h->xx_f.p, f.vbv.p, f.sc.p,
@@ -1313,9 +1331,11 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
           a.trace = f.trace.p;
         }
         if (f.overlap) { a.started = h->started.p; a.started_val = ++h->started_seq; }
+        h->gap_mark();  // 1: inverses done, rings zeroed
         cudaEvent_t pe = h->prof_begin(1);
         const cudaError_t le = launch_sweep_pipe(a, h->stream);
         h->prof_end(pe);
+        h->gap_mark();  // 2: sweep done
         if (le != cudaSuccess) return fail(BWGR_ERR_CUDA, "pipelined sweep launch failed: %s", cudaGetErrorString(le));
         h->launches++;
         if (f.overlap) {
@@ -1398,6 +1418,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
       launch_epilogue(ea, h->stream);
       h->prof_end(pe2);
       h->launches++;
+      h->gap_mark();  // 3: epilogue done
     }
     f.sweeps_issued++;
     cudaError_t le = cudaGetLastError();
@@ -1465,6 +1486,25 @@ int bwgr_em_sweeps(bwgr_handle* h, int nsweeps) {
 // debug (BWGR_TRACE=file): raw int64 stamps of the last sweep, [cta][block][32]
 static void dump_trace(bwgr_handle* h) {
   Fit& f = h->fit;
+  if (!h->gap_ev.empty()) {  // BWGR_GAPS: median time between consecutive marks of the main stream (4 marks per sweep)
+    cudaStreamSynchronize(h->stream);
+    const size_t ns = h->gap_ev.size() / 4;
+    if (ns > 12) {
+      const char* names[4] = {"band ready -> inverses + ring memset done", "-> sweep done", "-> epilogue done", "-> next band ready (wait for the side stream)"};
+      for (int k = 0; k < 4; k++) {
+        std::vector<float> v;
+        for (size_t s = 8; s + 1 < ns; s++) {
+          float ms = 0;
+          cudaEventElapsedTime(&ms, h->gap_ev[4 * s + k], h->gap_ev[4 * s + k + 1]);
+          v.push_back(ms);
+        }
+        std::sort(v.begin(), v.end());
+        fprintf(stderr, "[bwgr gaps] %-52s median %.1f us  (min %.1f, max %.1f)\n", names[k], 1e3 * v[v.size() / 2], 1e3 * v.front(), 1e3 * v.back());
+      }
+    }
+    for (cudaEvent_t e : h->gap_ev) cudaEventDestroy(e);
+    h->gap_ev.clear();
+  }
   if (!f.trace.p || !getenv("BWGR_TRACE")) return;
   cudaStreamSynchronize(h->stream);
   std::vector<long long> tr(f.trace.n);

@@ -14,9 +14,12 @@
 // 16k + i (low two bits) and 16k + 8 + i (high two bits), so the E2M1 nibbles of rows 16k..16k+7 are (w & 0x33333333) << 1 and
 // those of rows 16k+8..16k+15 are (w >> 1) & 0x66666666: two ALU operations per eight rows, 0.25 bytes per genotype from HBM.
 //
-// Warp roles (416 threads): warps 0-3 and 9-12 expand packed chunks into the K-major SWIZZLE_128B tiles (a 128-byte tile row =
-// 256 genotype rows of one marker), warp 4 issues the MMAs and owns TMEM (256 accumulator columns + a region of scale bytes
-// 0x7F = 2^0), warps 5-8 drain the accumulator.  One CTA per SM, persistent over blocks.
+// Warp roles (672 threads): warps 0-3 and 9-20 (512 producers) expand packed chunks into the K-major SWIZZLE_128B tiles (a 128-byte
+// tile row = 256 genotype rows of one marker), six stages of loads in flight per thread (the gather is DRAM-latency-bound: with 256
+// producers and four stages the kernel took 0.41 ms and, next to the sweep on the side stream, finished 92 us late every sweep; with
+// 512 and six it takes 0.39 ms and is never waited for); warp 4 issues the MMAs and owns TMEM (256 accumulator columns + a region of
+// scale bytes 0x7F = 2^0), warps 5-8 drain the accumulator.  One CTA per SM; persistent over blocks, or one CTA per block when the
+// launch shares the GPU with the sweep.
 #include <stdint.h>
 #include <string.h>
 
@@ -27,6 +30,8 @@ namespace bwgr {
 namespace {
 
 constexpr int kStages = 6;
+constexpr int kProducers = 512;             // warps 0-3 and 9-20: one packed 16-byte chunk of one marker of each tile per thread and stage
+constexpr int kThreads = kProducers + 160;  // + MMA warp (4) + four epilogue warps (5-8)
 constexpr int kStageBytes = 2 * 128 * 128;  // two tiles (block b, block b + 1) x 128 markers x 128 bytes (256 rows as FP4)
 constexpr uint32_t kSpinLimit = 1u << 22;
 constexpr uint32_t kAccCols = 256, kSfCol = 256, kSfCols = 64, kTmemCols = 512;
@@ -77,7 +82,7 @@ struct Fp4Smem {
   float sxc[256];  // column sums of the markers of block b | block b + 1 (centred Gram)
 };
 
-__global__ void __launch_bounds__(416, 1) gram_fp4_kernel(const uint8_t* __restrict__ x2f, int64_t ldb, int64_t ld, int p, int n,
+__global__ void __launch_bounds__(kThreads, 1) gram_fp4_kernel(const uint8_t* __restrict__ x2f, int64_t ldb, int64_t ld, int p, int n,
                                                           const int* __restrict__ perm, int nblocks, float* __restrict__ gram,
                                                           int* err, const float* __restrict__ sx, float inv_n) {
   extern __shared__ unsigned char smem_raw[];
@@ -87,7 +92,7 @@ __global__ void __launch_bounds__(416, 1) gram_fp4_kernel(const uint8_t* __restr
   const int nkg = (int)((ld + 255) >> 8);  // stages of 256 genotype rows per block
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; s++) { mbar_init(&S->full[s], 256); mbar_init(&S->empty[s], 1); }
+    for (int s = 0; s < kStages; s++) { mbar_init(&S->full[s], kProducers); mbar_init(&S->empty[s], 1); }
     mbar_init(&S->tmem_full, 1); mbar_init(&S->tmem_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -115,46 +120,48 @@ __global__ void __launch_bounds__(416, 1) gram_fp4_kernel(const uint8_t* __restr
 
   if (warp < 4 || warp >= 9) {
     // ===================== producer: packed 2-bit chunks -> E2M1 nibbles, SWIZZLE_128B K-major tiles =====================
-    // thread t: packed chunk c = t & 3 (64 rows = 32 bytes of FP4 = one K step of one marker) of the markers m0 and m0 + 64 of
-    // both tiles; four consecutive threads read 64 contiguous bytes of one packed column
-    const int t = warp < 4 ? threadIdx.x : threadIdx.x - 160;  // 0..255
+    // thread t: packed chunk c = t & 3 (64 rows = 32 bytes of FP4 = one K step of one marker) of marker m0 of both tiles; four
+    // consecutive threads read 64 contiguous bytes of one packed column
+    const int t = warp < 4 ? threadIdx.x : threadIdx.x - 160;  // 0..511
     const int c = t & 3, m0 = t >> 2;
     uint32_t it = 0;
     bool ok = true;
     for (int blk = blockIdx.x; blk < nblocks && ok; blk += gridDim.x) {
-      const uint8_t* colp[4];
-      bool val[4];
+      const uint8_t* colp[2];
+      bool val[2];
 #pragma unroll
-      for (int i = 0; i < 4; i++) {  // i = 2 * tile + half
-        const int pos = (blk + (i >> 1)) * 128 + m0 + 64 * (i & 1);
+      for (int i = 0; i < 2; i++) {  // i = tile
+        const int pos = (blk + i) * 128 + m0;
         val[i] = pos < p;
         colp[i] = x2f + (int64_t)(val[i] ? perm[pos] : 0) * ldb;
       }
-      // kPf stages of packed chunks in flight per thread (16 bytes x 4 markers each): the gather is latency-bound, L2 serves the second
-      // reader of every tile (block b's tile 1 is block b + 1's tile 0, fetched by a neighbouring CTA at about the same time)
-      constexpr int kPf = 4;
-      uint4 q[kPf][4];
-      auto load_stage = [&](int kg, uint4 (&dst)[4]) {
+      // kPf stages of packed chunks in flight per thread (16 bytes x 2 markers each): the gather is latency-bound (DRAM latency under
+      // load is about two stage times), L2 serves the second reader of every tile (block b's tile 1 is block b + 1's tile 0, fetched
+      // by a neighbouring CTA at about the same time)
+      constexpr int kPf = 6;
+      uint4 q[kPf][2];
+      auto load_stage = [&](int kg, uint4 (&dst)[2]) {
         const int64_t off = (int64_t)kg * 64 + c * 16;  // byte offset inside the packed column
 #pragma unroll
-        for (int i = 0; i < 4; i++) dst[i] = (val[i] && kg < nkg && off < ldb) ? __ldg(reinterpret_cast<const uint4*>(colp[i] + off)) : make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < 2; i++) dst[i] = (val[i] && kg < nkg && off < ldb) ? __ldg(reinterpret_cast<const uint4*>(colp[i] + off)) : make_uint4(0, 0, 0, 0);
       };
       // loads go out two stages at a time: the four threads of a marker then ask for one whole 128-byte line of its packed column
       // (two 64-byte visits to the same DRAM page at different times cost two activations)
-      load_stage(0, q[0]); load_stage(1, q[1]);
+#pragma unroll
+      for (int s0 = 0; s0 < kPf - 2; s0++) load_stage(s0, q[s0]);
       for (int kg0 = 0; kg0 < nkg && ok; kg0 += kPf) {
 #pragma unroll
         for (int u = 0; u < kPf; u++) {
           const int kg = kg0 + u;
           if (kg >= nkg || !ok) break;
-          if ((u & 1) == 0) { load_stage(kg + 2, q[(u + 2) % kPf]); load_stage(kg + 3, q[(u + 3) % kPf]); }
+          if ((u & 1) == 0) { load_stage(kg + kPf - 2, q[(u + kPf - 2) % kPf]); load_stage(kg + kPf - 1, q[(u + kPf - 1) % kPf]); }
           const uint32_t stage = it % kStages, phase = (it / kStages) & 1u;
           ok = mbar_wait(&S->empty[stage], phase ^ 1u, err);
           const uint32_t tbase = smem_u32(tiles + stage * kStageBytes);
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const int m = m0 + 64 * (i & 1);
-            const uint32_t rowb = tbase + (uint32_t)((i >> 1) * 16384 + (m >> 3) * 1024 + (m & 7) * 128);
+          for (int i = 0; i < 2; i++) {
+            const int m = m0;
+            const uint32_t rowb = tbase + (uint32_t)(i * 16384 + (m >> 3) * 1024 + (m & 7) * 128);
             const uint4 pk = q[u][i];
             const uint32_t sw = (uint32_t)m & 7u;
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((((uint32_t)(2 * c)) ^ sw) << 4)),
@@ -297,7 +304,7 @@ cudaError_t launch_gram_fp4(const uint8_t* x2f, int64_t ld, int p, int n, const 
   // block_per_cta: one short CTA per marker block instead of a persistent grid -- the hardware hands blocks to whichever SMs are
   // free, which is what a launch that shares the GPU with the clustered sweep needs
   const int grid = block_per_cta || nblocks < num_sms ? nblocks : num_sms;
-  gram_fp4_kernel<<<grid, 416, smem, st>>>(x2f, ld / 4, ld, p, n, perm, nblocks, gram, err, sx, 1.0f / (float)n);
+  gram_fp4_kernel<<<grid, kThreads, smem, st>>>(x2f, ld / 4, ld, p, n, perm, nblocks, gram, err, sx, 1.0f / (float)n);
   return cudaGetLastError();
 }
 

@@ -181,8 +181,12 @@ BWGR_API int bwgr_wgr_fit(bwgr_handle* h, const double* y, int it, int bi, int t
 
 /* ---- multivariate ridge -------------------------------------------------------------------- */
 /* MRR3 / MRR3F (src/RcppEigen20230423.cpp:318-701, :704-1079). par[30] = the arguments after
- * (Y,X) in the order of R/RcppExports.R:180. Y: n x k column-major, NaN = missing.
- * cnv: 3*maxit doubles (cnvB | cnvH2 | cnvV). */
+ * (Y,X) in the order of R/RcppExports.R:180. Y: n x k column-major.
+ * cnv: 3*maxit doubles (cnvB | cnvH2 | cnvV).
+ * On the device: complete phenotypes and the direct k x k solve, with HCS / XFA / ACS / updateMu / OneVarB / OneVarE / the GC and h2
+ * shaping arguments (PenCor, MinCor, uncorH2below, roundGC*, bucketGC*, Deflate*, weight_prior_*).
+ * NOT built -- BWGR_ERR_UNSUPPORTED, never a CPU fallback: NaN in Y (missing phenotypes), InnerGS = TRUE, TH = TRUE, NLfactor != 0,
+ * MRR3F with NoInv = TRUE, row-sharded stores. */
 BWGR_API int bwgr_mrr3_fit(bwgr_handle* h, int f32_variant, const double* Y, int k, const double* par, double* mu, double* b,
                   double* hat, double* h2, double* GC, double* vb, double* ve, double* MSx, double* cnv, double* W,
                   int* its);

@@ -84,6 +84,31 @@ def test_pack_f64_signed_and_ragged():
             assert np.array_equal(xx, (X ** 2).sum(0)) and np.array_equal(sx, X.sum(0))
 
 
+def test_float64_loader_many_chunks_and_block_reuse():
+    """The float64 loader's thread pool over several staging chunks (a chunk is 32 MB of int8: 2,500 columns at n = 13,000), a ragged
+    last chunk, and device / pinned blocks handed from a closed store to the next one (BlockCache) and given back (bw.trim)."""
+    rng = np.random.default_rng(12)
+    n, p = 13001, 6001
+    X8 = rng.integers(0, 3, size=(n, p), dtype=np.int8)
+    Xd = np.asfortranarray(X8, dtype=np.float64)
+    y = rng.normal(size=n)
+    fits = []
+    for rep in range(3):
+        with bw.Genotypes(Xd, path=2) as g:
+            assert np.array_equal(g.unpack(), X8)
+            xx, sx = g.stats()
+            assert np.array_equal(sx, X8.astype(np.int64).sum(0))
+            fits.append(bw.emRR(y, g, it=5))
+        if rep == 1:
+            bw.trim()
+    assert all(np.array_equal(fits[0]["b"], f["b"]) and fits[0]["Ve"] == f["Ve"] for f in fits[1:])
+    with bw.Genotypes(X8, path=2) as g:  # the int8 loader sees the same store
+        assert np.array_equal(bw.emRR(y, g, it=5)["b"], fits[0]["b"])
+    Xd[n // 2, p - 3] = 1.5
+    with pytest.raises(bw.BwgrError):
+        bw.Genotypes(Xd)
+
+
 @pytest.mark.parametrize("shape", [(196, 376), (1000, 300), (4100, 129)])
 def test_gram_blocks_bit_exact(tpod, shape):
     """tcgen05 kind::i8 Gram blocks X_B'X_B == integer numpy, for a shuffled order and ragged last block."""
