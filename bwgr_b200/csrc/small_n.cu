@@ -48,11 +48,17 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
   const bool two_bit = a.g.storage != 0;
   const int col_bytes = two_bit ? (ld >> 2) : ld;  // bytes of one column slot in the ring
 
+  // e in shared memory, quarter-chunk major: rows 16c + 4q .. 16c + 4q + 3 of chunk c sit at float4 index q * nchunks + c, so that the
+  // threads of a warp (consecutive chunks) read consecutive 16-byte words.  (Row-major, thread c's four float4 are 64 bytes apart from
+  // thread c + 1's: a 4-way bank conflict on every one of the twelve accesses per marker -- ncu: 1.8e9 conflict cycles, short-scoreboard
+  // stall 7.5 per issue at the config-4 shape.)
   float* e_s = reinterpret_cast<float*>(smem_raw);                          // [ld]
+  auto e_idx = [&](int i) { return ((((i >> 2) & 3) * nchunks + (i >> 4)) << 2) + (i & 3); };
   unsigned char* ring = smem_raw + (size_t)ld * 4;                          // [kRing][col_bytes]
   unsigned char* mask_s = ring + (size_t)kRing * col_bytes;                 // [ld] (only if mask)
   float* red = reinterpret_cast<float*>(mask_s + (a.mask ? ld : 0));        // [2][32]
   MarkerDraws* draws = reinterpret_cast<MarkerDraws*>(red + 64);            // [2][T] (Gibbs)
+  int* ord_s = reinterpret_cast<int*>(draws + (model_is_gibbs(MODEL) ? 2 * T : 0));  // [2][T]: the marker order, two chunks of T positions
   __shared__ SysScalars sc;
 
   if (tid == 0) sc = a.sc[sys];
@@ -60,7 +66,7 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
   if (sc.done) return;
 
   float* e_g = a.e + (size_t)sys * ld;
-  for (int i = tid; i < ld; i += T) e_s[i] = e_g[i];
+  for (int i = tid; i < ld; i += T) e_s[e_idx(i)] = e_g[i];
   if (a.mask)
     for (int i = tid; i < ld; i += T) mask_s[i] = a.mask[(size_t)sys * ld + i];
 
@@ -72,7 +78,12 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
   const int sweep = sc.sweep;
   const uint32_t chain = (uint32_t)(a.chain0 + sys);
 
-  auto marker_at = [&](int pos) { return order ? order[pos] : pos; };
+  // the order is read through shared memory: straight from global memory the index load sat in front of every column address and
+  // every per-marker input (a dependent L2 round trip per marker in every thread)
+  auto marker_at = [&](int pos) { return order ? ord_s[((pos / T) & 1) * T + (pos % T)] : pos; };
+  if (order)
+    for (int k = 0; k < 2; k++) { const int q = k * T + tid; if (q < p) ord_s[k * T + tid] = order[q]; }
+  __syncthreads();
   auto issue_col = [&](int pos) {
     if (pos < p) {
       const int j = marker_at(pos);
@@ -92,17 +103,23 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
   for (int q = 0; q < kRing - 1; q++) issue_col(q);
   __syncthreads();  // e_s, mask_s visible
 
-  // per-marker inputs, prefetched one marker ahead
-  int j_next = marker_at(0);
-  float nb0 = b[j_next], nxx = xx[j_next], nvb = vbv ? vbv[j_next] : 0.0f;
+  // per-marker inputs, prefetched two markers ahead (a permutation visits a marker once per sweep: nothing read early is stale)
+  int jA = marker_at(0), jB = p > 1 ? marker_at(1) : 0;
+  float bA = b[jA], xA = xx[jA], vA = vbv ? vbv[jA] : 0.0f;
+  float bB = b[jB], xB = xx[jB], vB = vbv ? vbv[jB] : 0.0f;
 
 #pragma unroll 1
   for (int pos = 0; pos < p; pos++) {
-    const int j = j_next;
-    const float b0 = nb0, xxj = nxx, vbj = nvb;
-    if (pos + 1 < p) {
-      j_next = marker_at(pos + 1);
-      nb0 = b[j_next]; nxx = xx[j_next]; nvb = vbv ? vbv[j_next] : 0.0f;
+    const int j = jA;
+    const float b0 = bA, xxj = xA, vbj = vA;
+    jA = jB; bA = bB; xA = xB; vA = vB;
+    if (order && pos > 0 && (pos % T) == 0) {  // chunk pos / T + 1 of the order replaces chunk pos / T - 1 (nobody reads that any more)
+      const int q = pos + T + tid;
+      if (q < p) ord_s[(((pos / T) + 1) & 1) * T + tid] = order[q];
+    }
+    if (pos + 2 < p) {
+      jB = marker_at(pos + 2);
+      bB = b[jB]; xB = xx[jB]; vB = vbv ? vbv[jB] : 0.0f;
     }
     if (model_is_gibbs(MODEL) && (pos % T) == 0) {  // draws of the next T markers, one per thread
       const int q = pos + tid;
@@ -123,10 +140,10 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
         w.x &= m.x * 0xFFu; w.y &= m.y * 0xFFu; w.z &= m.z * 0xFFu; w.w &= m.w * 0xFFu;
       }
       const uint32_t ww[4] = {w.x ^ 0x80808080u, w.y ^ 0x80808080u, w.z ^ 0x80808080u, w.w ^ 0x80808080u};
-      const float4* ev = reinterpret_cast<const float4*>(e_s + 16 * c);
+      const float4* ev = reinterpret_cast<const float4*>(e_s) + c;
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        const float4 e4 = ev[q];
+        const float4 e4 = ev[(size_t)q * nchunks];
         acc = fmaf(byte_to_float(ww[q], 0), e4.x, acc);
         acc = fmaf(byte_to_float(ww[q], 1), e4.y, acc);
         acc = fmaf(byte_to_float(ww[q], 2), e4.z, acc);
@@ -161,22 +178,22 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
           w.x &= m.x * 0xFFu; w.y &= m.y * 0xFFu; w.z &= m.z * 0xFFu; w.w &= m.w * 0xFFu;
         }
         const uint32_t ww[4] = {w.x ^ 0x80808080u, w.y ^ 0x80808080u, w.z ^ 0x80808080u, w.w ^ 0x80808080u};
-        float4* ev = reinterpret_cast<float4*>(e_s + 16 * c);
+        float4* ev = reinterpret_cast<float4*>(e_s) + c;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-          float4 e4 = ev[q];
+          float4 e4 = ev[(size_t)q * nchunks];
           e4.x = fmaf(-byte_to_float(ww[q], 0), r.de, e4.x);
           e4.y = fmaf(-byte_to_float(ww[q], 1), r.de, e4.y);
           e4.z = fmaf(-byte_to_float(ww[q], 2), r.de, e4.z);
           e4.w = fmaf(-byte_to_float(ww[q], 3), r.de, e4.w);
-          ev[q] = e4;
+          ev[(size_t)q * nchunks] = e4;
         }
       }
     }
   }
   cp_async_wait<0>();
   __syncthreads();
-  for (int i = tid; i < ld; i += T) e_g[i] = e_s[i];
+  for (int i = tid; i < ld; i += T) e_g[i] = e_s[e_idx(i)];
 }
 
 }  // namespace
@@ -185,7 +202,7 @@ static size_t small_n_smem(const SmallNArgs& a, int ring, int T) {
   const size_t ld = (size_t)a.g.ld;
   const size_t col_bytes = a.g.storage ? (ld >> 2) : ld;
   return ld * 4 + (size_t)ring * col_bytes + (a.mask ? ld : 0) + 64 * 4 +
-         (model_is_gibbs(a.model) ? 2 * (size_t)T * sizeof(MarkerDraws) : 0) + 16;
+         (model_is_gibbs(a.model) ? 2 * (size_t)T * sizeof(MarkerDraws) : 0) + 2 * (size_t)T * sizeof(int) + 16;
 }
 
 // Largest n this path takes: e (4 B/row) + two ring slots must fit the 227 KB of one SM.

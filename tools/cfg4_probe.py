@@ -4,7 +4,7 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, bwgr_b200 as bw
 dev = torch.device("cuda", 0)
-n, p, ktr, folds = 10000, 50000, 20, 5
+n, p, ktr, folds = 10000, int(os.environ.get('CFG4_P', 50000)), 20, 5
 Xt, y = bench.synth_gpu(n, p, bench.SEED, dev)
 rng = np.random.default_rng(2)
 Y = np.stack([y * np.sqrt(0.5) + rng.normal(size=n) * np.sqrt(0.5) for _ in range(ktr)], axis=1)
@@ -17,7 +17,7 @@ for t in range(ktr):
 g = bw.Genotypes(device=0)
 g.load(Xt)
 bw.em_fit("emBC", Yall, g, it=2, row_mask=mask)
-for it in (3, 9):
+for it in ((3,) if 'CFG4_P' in os.environ else (3, 9)):
     g.profile(True)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     bw.em_fit("emBC", Yall, g, it=it, row_mask=mask)
