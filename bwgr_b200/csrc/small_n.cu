@@ -80,13 +80,20 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
 
   // the order is read through shared memory: straight from global memory the index load sat in front of every column address and
   // every per-marker input (a dependent L2 round trip per marker in every thread)
-  auto marker_at = [&](int pos) { return order ? ord_s[((pos / T) & 1) * T + (pos % T)] : pos; };
+  // (pm, pb) = (pos % T, (pos / T) & 1), kept incrementally: T is a run-time value and an integer division costs ~20 instructions,
+  // three of them per marker were a third of the instruction stream of a kernel that is issue-bound
+  int pm = 0, pb = 0;
+  const bool single = nchunks <= T;
+  auto marker_ahead = [&](int pos, int d) {  // marker at position pos + d, 0 <= d < T
+    int m = pm + d, bsel = pb;
+    if (m >= T) { m -= T; bsel ^= 1; }
+    return order ? ord_s[bsel * T + m] : pos + d;
+  };
   if (order)
     for (int k = 0; k < 2; k++) { const int q = k * T + tid; if (q < p) ord_s[k * T + tid] = order[q]; }
   __syncthreads();
-  auto issue_col = [&](int pos) {
+  auto issue_col = [&](int pos, int j) {
     if (pos < p) {
-      const int j = marker_at(pos);
       unsigned char* slot = ring + (size_t)(pos % kRing) * col_bytes;
       if (!two_bit) {
         const int8_t* src = a.g.x8 + (int64_t)j * a.g.ld;
@@ -100,11 +107,11 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
   };
 
 #pragma unroll 1
-  for (int q = 0; q < kRing - 1; q++) issue_col(q);
+  for (int q = 0; q < kRing - 1; q++) issue_col(q, marker_ahead(0, q));
   __syncthreads();  // e_s, mask_s visible
 
   // per-marker inputs, prefetched two markers ahead (a permutation visits a marker once per sweep: nothing read early is stale)
-  int jA = marker_at(0), jB = p > 1 ? marker_at(1) : 0;
+  int jA = marker_ahead(0, 0), jB = p > 1 ? marker_ahead(0, 1) : 0;
   float bA = b[jA], xA = xx[jA], vA = vbv ? vbv[jA] : 0.0f;
   float bB = b[jB], xB = xx[jB], vB = vbv ? vbv[jB] : 0.0f;
 
@@ -113,25 +120,51 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
     const int j = jA;
     const float b0 = bA, xxj = xA, vbj = vA;
     jA = jB; bA = bB; xA = xB; vA = vB;
-    if (order && pos > 0 && (pos % T) == 0) {  // chunk pos / T + 1 of the order replaces chunk pos / T - 1 (nobody reads that any more)
+    if (order && pos > 0 && pm == 0) {  // chunk pos / T + 1 of the order replaces chunk pos / T - 1 (nobody reads that any more)
       const int q = pos + T + tid;
-      if (q < p) ord_s[(((pos / T) + 1) & 1) * T + tid] = order[q];
+      if (q < p) ord_s[(pb ^ 1) * T + tid] = order[q];
     }
     if (pos + 2 < p) {
-      jB = marker_at(pos + 2);
+      jB = marker_ahead(pos, 2);
       bB = b[jB]; xB = xx[jB]; vB = vbv ? vbv[jB] : 0.0f;
     }
-    if (model_is_gibbs(MODEL) && (pos % T) == 0) {  // draws of the next T markers, one per thread
+    if (model_is_gibbs(MODEL) && pm == 0) {  // draws of the next T markers, one per thread
       const int q = pos + tid;
       if (q < p)
-        draws[((pos / T) & 1) * T + tid] = marker_draws(MODEL, (uint32_t)marker_at(q), (uint32_t)sweep, chain, sc.df, a.seed_lo, a.seed_hi);
+        draws[pb * T + tid] = marker_draws(MODEL, (uint32_t)marker_ahead(pos, tid), (uint32_t)sweep, chain, sc.df, a.seed_lo, a.seed_hi);
     }
-    issue_col(pos + kRing - 1);
+    issue_col(pos + kRing - 1, pos + kRing - 1 < p ? marker_ahead(pos, kRing - 1) : 0);
     cp_async_wait<kRing - 1>();
 
     // ---- g = x_j' e over this thread's chunks
     const unsigned char* slot = ring + (size_t)(pos % kRing) * col_bytes;
     float acc = 0.0f;
+    // one chunk per thread (n <= 16 T rows, the usual case): the sixteen genotypes of the thread are converted once and stay in
+    // registers for the residual update
+    float xf[16];
+    if (single) {
+      if (tid < nchunks) {
+        const int c = tid;
+        uint4 w = two_bit ? expand_2bit(*reinterpret_cast<const uint32_t*>(slot + 4 * c))
+                          : *reinterpret_cast<const uint4*>(slot + 16 * c);
+        if (a.mask) {
+          const uint4 m = *reinterpret_cast<const uint4*>(mask_s + 16 * c);
+          w.x &= m.x * 0xFFu; w.y &= m.y * 0xFFu; w.z &= m.z * 0xFFu; w.w &= m.w * 0xFFu;
+        }
+        const uint32_t ww[4] = {w.x ^ 0x80808080u, w.y ^ 0x80808080u, w.z ^ 0x80808080u, w.w ^ 0x80808080u};
+        const float4* ev = reinterpret_cast<const float4*>(e_s) + c;
+        float a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const float4 e4 = ev[(size_t)q * nchunks];
+#pragma unroll
+          for (int k = 0; k < 4; k++) xf[4 * q + k] = byte_to_float(ww[q], k);
+          a4[q] = fmaf(xf[4 * q + 0], e4.x, a4[q]); a4[q] = fmaf(xf[4 * q + 1], e4.y, a4[q]);
+          a4[q] = fmaf(xf[4 * q + 2], e4.z, a4[q]); a4[q] = fmaf(xf[4 * q + 3], e4.w, a4[q]);
+        }
+        acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+      }
+    } else
     for (int c = tid; c < nchunks; c += T) {
       uint4 w = two_bit ? expand_2bit(*reinterpret_cast<const uint32_t*>(slot + 4 * c))
                         : *reinterpret_cast<const uint4*>(slot + 16 * c);
@@ -159,7 +192,7 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
 
     // ---- rule (every thread, identical inputs -> identical result)
     MarkerDraws dr;
-    if (model_is_gibbs(MODEL)) dr = draws[((pos / T) & 1) * T + (pos % T)];
+    if (model_is_gibbs(MODEL)) dr = draws[pb * T + pm];
     else { dr.z1 = dr.z2 = dr.u = 0.0f; dr.chi = 1.0f; }
     const RuleOut r = marker_rule<MODEL>(g, xxj, b0, vbj, sc, dr);
     if (tid == 0) {
@@ -169,7 +202,18 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
     }
 
     // ---- e -= x_j * de on this thread's chunks
-    if (r.de != 0.0f) {
+    if (r.de != 0.0f && single) {
+      if (tid < nchunks) {
+        float4* ev = reinterpret_cast<float4*>(e_s) + tid;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          float4 e4 = ev[(size_t)q * nchunks];
+          e4.x = fmaf(-xf[4 * q + 0], r.de, e4.x); e4.y = fmaf(-xf[4 * q + 1], r.de, e4.y);
+          e4.z = fmaf(-xf[4 * q + 2], r.de, e4.z); e4.w = fmaf(-xf[4 * q + 3], r.de, e4.w);
+          ev[(size_t)q * nchunks] = e4;
+        }
+      }
+    } else if (r.de != 0.0f) {
       for (int c = tid; c < nchunks; c += T) {
         uint4 w = two_bit ? expand_2bit(*reinterpret_cast<const uint32_t*>(slot + 4 * c))
                           : *reinterpret_cast<const uint4*>(slot + 16 * c);
@@ -190,6 +234,7 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
         }
       }
     }
+    if (++pm == T) { pm = 0; pb ^= 1; }
   }
   cp_async_wait<0>();
   __syncthreads();
