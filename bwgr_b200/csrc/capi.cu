@@ -1966,6 +1966,352 @@ void sym_pinv(const Mat& A, int k, Mat& out) {  // completeOrthogonalDecompositi
     for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) out[i + (size_t)j * k] += iw * V[i + (size_t)c * k] * V[j + (size_t)c * k];
   }
 }
+
+// MRR3's argument list after (Y, X), in the order of R/RcppExports.R:180
+struct MrrFlags {
+  int maxit; double tol; bool TH; double NLfactor; bool InnerGS, NoInv, HCS, XFA, ACS; int NumXFA; double R2, gc0, df0; bool updateMu;
+  double wph2, wpgc, PenCor, MinCor, uncorH2below, rUpFrom, rUpTo, rDownFrom, rDownTo, bkFrom, bkTo, DeflateMax, DeflateBy;
+  bool OneVarB, OneVarE;
+  explicit MrrFlags(const double* par) {
+    int q = 0;
+    maxit = (int)par[q++]; tol = par[q++]; q++; TH = par[q++] != 0; NLfactor = par[q++];
+    InnerGS = par[q++] != 0; NoInv = par[q++] != 0; HCS = par[q++] != 0; XFA = par[q++] != 0; ACS = par[q++] != 0;
+    NumXFA = (int)par[q++]; R2 = par[q++]; gc0 = par[q++]; df0 = par[q++]; updateMu = par[q++] != 0;
+    wph2 = par[q++]; wpgc = par[q++]; PenCor = par[q++]; MinCor = par[q++]; uncorH2below = par[q++];
+    rUpFrom = par[q++]; rUpTo = par[q++]; rDownFrom = par[q++]; rDownTo = par[q++]; bkFrom = par[q++]; bkTo = par[q++];
+    DeflateMax = par[q++]; DeflateBy = par[q++]; OneVarB = par[q++] != 0; OneVarE = par[q++] != 0;
+  }
+};
+// The k x k state of the variance components that survives from sweep to sweep.
+struct MrrVar {
+  Mat vb, iG, GC, Sb;
+  std::vector<double> vbInit;
+  double Deflate = 1, inflate = 0;
+};
+// Genetic (co)variances of one sweep (:559-648): TildeHat and the traces Tr (TrXSX, or TrDinvXSX under TH) in, vb / GC / iG out.
+// Shared by the rotated fast path and the general path; double, on the host (k <= 32).
+void mrr_varcomp(const MrrFlags& F, int k, const Mat& TildeHat, const std::vector<double>& Tr, const std::vector<double>& h2, MrrVar& V) {
+  auto M = [k](int r, int c) { return (size_t)r + (size_t)c * k; };
+  Mat &vb = V.vb, &iG = V.iG, &GC = V.GC, A;
+  const Mat& Sb = V.Sb;
+  const std::vector<double>& vbInit = V.vbInit;
+  double &Deflate = V.Deflate, &inflate = V.inflate;
+  const double df0 = F.df0, wph2 = F.wph2, wpgc = F.wpgc, gc0 = F.gc0, PenCor = F.PenCor, MinCor = F.MinCor, uncorH2below = F.uncorH2below;
+  const double rUpFrom = F.rUpFrom, rUpTo = F.rUpTo, rDownFrom = F.rDownFrom, rDownTo = F.rDownTo, bkFrom = F.bkFrom, bkTo = F.bkTo;
+  const double DeflateMax = F.DeflateMax, DeflateBy = F.DeflateBy, bucketMean = 0.5 * (F.bkFrom + F.bkTo);
+  const bool ACS = F.ACS, HCS = F.HCS, XFA = F.XFA, OneVarB = F.OneVarB;
+  const int NumXFA = F.NumXFA;
+  const bool rebuild = !F.NoInv || F.TH;  // :628, :647: with NoInv (and no TH) the correlations are not bent and iG keeps its start value
+  for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) {
+    if (i == j) vb[M(i, i)] = (TildeHat[M(i, i)] + Sb[M(i, i)]) / (Tr[i] + df0);
+    else vb[M(i, j)] = (TildeHat[M(i, j)] + TildeHat[M(j, i)] + Sb[M(i, j)]) / (Tr[i] + Tr[j] + df0);
+  }
+  if (wph2 > 0) for (int i = 0; i < k; i++) vb[M(i, i)] = vb[M(i, i)] * (1 - wph2) + wph2 * vbInit[i];
+  if (wpgc > 0) {
+    for (int i = 0; i < k; i++) for (int j = 0; j < k; j++)
+      GC[M(i, j)] = (i != j) ? (1.0 - wpgc) * vb[M(i, j)] / std::sqrt(vb[M(i, i)] * vb[M(j, j)]) + gc0 * wpgc : 1.0;
+    for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) if (i != j) vb[M(i, j)] = GC[M(i, j)] * std::sqrt(vb[M(i, i)] * vb[M(j, j)]);
+  } else {
+    for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) GC[M(i, j)] = vb[M(i, j)] / std::sqrt(vb[M(i, i)] * vb[M(j, j)]);
+  }
+  auto top_factors = [&](double add, double scale) {  // :593-600, :612-617
+    std::vector<double> ew; Mat ev;
+    sym_eig(GC, k, ew, ev);
+    Mat UDU((size_t)k * k, 0.0);
+    for (int fI = 0; fI < NumXFA && fI < k; fI++) {
+      const int c = k - fI - 1;
+      for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) UDU[M(i, j)] += ew[c] * ev[M(i, c)] * ev[M(j, c)];
+    }
+    for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) GC[M(i, j)] = (UDU[M(i, j)] + add) * scale;
+    for (int i = 0; i < k; i++) GC[M(i, i)] = 1;
+  };
+  if (ACS) {
+    double gs = 0;
+    for (double v : GC) gs += v;
+    gs = (gs - k) / ((k * (k - 1))) / 2.0;
+    top_factors(gs, 0.5);
+  } else if (HCS) {
+    double gs = 0;
+    for (int i = 0; i < k; i++) for (int j = 0; j < i; j++) gs += GC[M(i, j)];
+    gs = gs / ((k * (k - 1)) / 2);
+    for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) GC[M(i, j)] = (i != j) ? gs : 1.0;
+  } else if (XFA) {
+    top_factors(0.0, 1.0);
+  }
+  for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) if (i != j) {  // :619-626
+    double& g = GC[M(i, j)];
+    if (MinCor < 1 && g < MinCor) g = 0;
+    if (PenCor > 0) g = std::tanh(PenCor * std::fabs(g)) * g;
+    if (rDownFrom < 1 && g < rDownFrom) g = rDownTo;
+    if (rUpFrom < 1 && g > rUpFrom) g = rUpTo;
+    if (bkFrom < 1 && g > bkFrom && g < bkTo) g = bucketMean;
+    if (uncorH2below > 0 && (h2[i] < uncorH2below || h2[j] < uncorH2below)) g = 0;
+  }
+  if (rebuild) {  // bending (:629-644)
+    A = GC;
+    if (DeflateBy > 0) {
+      for (auto& v : A) v *= Deflate;
+      for (int i = 0; i < k; i++) A[M(i, i)] = 1;
+      if (!chol_ok(A, k) && Deflate > DeflateMax) {
+        Deflate -= DeflateBy;
+        A = GC;
+        for (auto& v : A) v *= Deflate;
+        for (int i = 0; i < k; i++) A[M(i, i)] = 1;
+      }
+    }
+    std::vector<double> ew; Mat ev;
+    sym_eig(A, k, ew, ev);
+    if (ew[0] < 0) {
+      inflate = std::fabs(ew[0] * 1.1);
+      for (int i = 0; i < k; i++) A[M(i, i)] += inflate;
+      for (auto& v : A) v /= (1.0 + inflate);
+      GC = A;
+    }
+  }
+  if (OneVarB) {
+    double tmp = 0;
+    for (int i = 0; i < k; i++) tmp += TildeHat[M(i, i)];
+    tmp /= k;
+    for (size_t i = 0; i < vb.size(); i++) vb[i] = GC[i] * tmp;
+  } else {
+    const Mat dv(vb);
+    for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) vb[M(i, j)] = GC[M(i, j)] * std::sqrt(dv[M(i, i)] * dv[M(j, j)]);
+  }
+  if (rebuild) sym_pinv(vb, k, iG);
+}
+
+// MRR3 / MRR3F on the general device path (mrr_gen.cu): per-trait observation masks, InnerGS, NLfactor, TH, MRR3F's NoInv system.
+// Host side = the reference's set-up (:359-432) and the k x k variance block; everything O(n), O(p) or O(n p) is a kernel.
+int mrr3_general(bwgr_handle* h, int f32_variant, const double* Y, int k, const MrrFlags& F, double* mu_out, double* b_out,
+                 double* hat_out, double* h2_out, double* GC_out, double* vb_out, double* ve_out, double* MSx_out, double* cnv_out,
+                 double* W_out, int* its_out) {
+  if (h->storage != BWGR_STORE_I8 || !h->x8) return fail(BWGR_ERR_UNSUPPORTED, "MRR3 (general path) reads the int8 store");
+  if (h->world > 1) return fail(BWGR_ERR_UNSUPPORTED, "MRR3 does not run on a row-sharded store");
+  const int64_t n = h->n, p = h->p, ld = h->ld;
+  const int maxit = F.maxit, kk = k * k;
+  const bool innergs = F.InnerGS, noinv_system = f32_variant && F.NoInv, NonLinear = F.NLfactor != 0;
+  const int nmat = innergs ? 2 : 1;
+  auto M = [k](int r, int c) { return (size_t)r + (size_t)c * k; };
+  CU(cudaSetDevice(h->device));
+  // ---- incidence, counts, centred phenotypes (:359-376)
+  std::vector<uint32_t> zb((size_t)ld, 0u);
+  std::vector<double> nn(k), mu(k), ysum(k), vy(k), yh((size_t)k * ld, 0.0);
+  for (int t = 0; t < k; t++) {
+    double sum = 0; int64_t cnt = 0;
+    for (int64_t i = 0; i < n; i++) { const double v = Y[(size_t)t * n + i]; if (v == v) { zb[i] |= 1u << t; sum += v; cnt++; } }
+    if (cnt < 2) return fail(BWGR_ERR_ARG, "MRR3: trait %d has fewer than two observations", t + 1);
+    nn[t] = (double)cnt; mu[t] = sum / (double)cnt;
+    double s1 = 0, s2 = 0;
+    for (int64_t i = 0; i < n; i++) {
+      const double v = Y[(size_t)t * n + i];
+      if (v == v) { const double c = v - mu[t]; yh[(size_t)t * ld + i] = c; s1 += c; s2 += c * c; }
+    }
+    ysum[t] = s1; vy[t] = s2 / (nn[t] - 1.0);
+    if (!(vy[t] > 0)) return fail(BWGR_ERR_ARG, "MRR3: trait %d has no variance", t + 1);
+  }
+  // ---- launch geometry: one CTA per row slab, all co-resident
+  int rp = (int)((ld + h->num_sms - 1) / h->num_sms);
+  rp = std::max(64, (rp + 15) / 16 * 16);
+  const int grid = (int)((ld + rp - 1) / rp);
+  const size_t smem = mrr_gen_smem(k, rp, innergs);
+  if (smem > h->smem_optin || grid > h->num_sms)
+    return fail(BWGR_ERR_UNSUPPORTED, "MRR3 (general path): %lld rows x %d traits do not fit the shared memory of %d SMs", (long long)n, k, h->num_sms);
+  DevBuf<uint32_t> zbits; DevBuf<double> yd, ed, bd, bold, fixd, meand, tilded, sold, Wd, xsxd, dinvd, small, partd;
+  DevBuf<unsigned int> bar; DevBuf<int> permd;
+  const size_t nsmall = (size_t)2 * kk + 8 * 32;  // iG | vb | iVe | se | ey | cnv | trd | par(2 x 32) | shift
+  if (zbits.alloc(ld) != cudaSuccess || yd.alloc((size_t)k * ld) != cudaSuccess || ed.alloc((size_t)k * ld) != cudaSuccess ||
+      bd.alloc((size_t)p * k) != cudaSuccess || bold.alloc((size_t)p * k) != cudaSuccess || fixd.alloc((size_t)p * 2 * k) != cudaSuccess ||
+      meand.alloc(p) != cudaSuccess || tilded.alloc((size_t)p * k) != cudaSuccess || sold.alloc((size_t)p * nmat * kk) != cudaSuccess ||
+      (NonLinear && Wd.alloc((size_t)p * k) != cudaSuccess) || (F.TH && (xsxd.alloc((size_t)p * k) != cudaSuccess || dinvd.alloc((size_t)p * k) != cudaSuccess)) ||
+      small.alloc(nsmall + kk) != cudaSuccess || partd.alloc((size_t)2 * grid * 32) != cudaSuccess || bar.alloc(1) != cudaSuccess ||
+      permd.alloc(p + 32) != cudaSuccess)
+    return fail(BWGR_ERR_CUDA, "cudaMalloc(MRR3 general workspace) failed");
+  double *d_iG = small.p, *d_vb = small.p + kk, *d_iVe = d_vb + kk, *d_se = d_iVe + 32, *d_ey = d_se + 32, *d_cnv = d_ey + 32,
+         *d_trd = d_cnv + 32, *d_par = d_trd + 32, *d_shift = d_par + 64, *d_th = small.p + nsmall;
+  cudaStream_t st = h->stream;
+  CU(cudaMemcpyAsync(zbits.p, zb.data(), sizeof(uint32_t) * ld, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(yd.p, yh.data(), sizeof(double) * k * ld, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ed.p, yd.p, sizeof(double) * k * ld, cudaMemcpyDeviceToDevice, st));  // e = y (:435)
+  CU(cudaMemsetAsync(bd.p, 0, sizeof(double) * p * k, st));
+  // ---- masked column statistics (:381-392) and tilde = X_c'y (:420) from one pass over the store
+  std::vector<double> sxz((size_t)p * k), sxxz((size_t)p * k), tilde((size_t)p * k), fixed((size_t)p * 2 * k), meanv(p), xsx;
+  {
+    DevBuf<double> a1, a2;
+    if (a1.alloc((size_t)p * k) != cudaSuccess || a2.alloc((size_t)p * k) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+    launch_mrr_gen_colstats(h->view(), zbits.p, yd.p, k, a1.p, a2.p, tilded.p, st);
+    h->launches++;
+    CU(cudaMemcpyAsync(sxz.data(), a1.p, sizeof(double) * p * k, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(sxxz.data(), a2.p, sizeof(double) * p * k, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(tilde.data(), tilded.p, sizeof(double) * p * k, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  std::vector<double> MSx(k, 0.0), TrXSX(k);
+  if (F.TH) xsx.resize((size_t)p * k);
+  for (int64_t j = 0; j < p; j++) {
+    const double m = h->h_sx[j] / (double)n;  // X.colwise().mean() over all n0 rows (:378)
+    meanv[j] = m;
+    for (int t = 0; t < k; t++) {
+      const size_t q = (size_t)j * k + t;
+      const double XX = sxxz[q] - 2.0 * m * sxz[q] + m * m * nn[t];  // sum_i (x - m)^2 z_it
+      const double sc = sxz[q] - m * nn[t];                           // sum_i (x - m) z_it
+      const double qq = sc / nn[t], v = XX / nn[t] - qq * qq;         // XSX (:386-388)
+      fixed[(size_t)j * 2 * k + t] = XX; fixed[(size_t)j * 2 * k + k + t] = sc;
+      MSx[t] += v;
+      if (F.TH) xsx[q] = v * nn[t];                                   // :423
+      tilde[q] -= m * ysum[t];
+    }
+  }
+  for (int t = 0; t < k; t++) {
+    if (!(MSx[t] > 0)) return fail(BWGR_ERR_ARG, "genotypes have no variance");
+    TrXSX[t] = nn[t] * MSx[t];
+  }
+  CU(cudaMemcpyAsync(fixd.p, fixed.data(), sizeof(double) * p * 2 * k, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(meand.p, meanv.data(), sizeof(double) * p, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(tilded.p, tilde.data(), sizeof(double) * p * k, cudaMemcpyHostToDevice, st));
+  if (F.TH) CU(cudaMemcpyAsync(xsxd.p, xsx.data(), sizeof(double) * p * k, cudaMemcpyHostToDevice, st));
+  // ---- starting values (:394-432)
+  std::vector<double> ve(k), iVe(k), veInit(k), h2(k), Se(k), iNp(k);
+  MrrVar V;
+  Mat &vb = V.vb, &iG = V.iG, &GC = V.GC, TildeHat((size_t)kk);
+  vb.assign((size_t)kk, 0.0); iG.assign((size_t)kk, 0.0); GC.assign((size_t)kk, 0.0);
+  V.vbInit.resize(k);
+  for (int t = 0; t < k; t++) {
+    ve[t] = vy[t] * (1 - F.R2); iVe[t] = 1.0 / ve[t]; veInit[t] = ve[t];
+    V.vbInit[t] = vy[t] * F.R2 / MSx[t]; vb[M(t, t)] = V.vbInit[t]; iG[M(t, t)] = 1.0 / V.vbInit[t]; h2[t] = 1 - ve[t] / vy[t];
+    Se[t] = ve[t] * F.df0; iNp[t] = 1.0 / (nn[t] + F.df0 - 1.0);
+  }
+  for (int i = 0; i < k; i++) for (int j = 0; j < i; j++) { const double v = F.gc0 * std::sqrt(vb[M(i, i)] * vb[M(j, j)]); vb[M(i, j)] = v; vb[M(j, i)] = v; }
+  V.Sb = vb;
+  for (auto& v : V.Sb) v *= F.df0;
+  std::vector<int> order(p), irgs(32);
+  for (int64_t j = 0; j < p; j++) order[j] = (int)j;
+  for (int j = 0; j < 32; j++) irgs[j] = j;
+  std::vector<double> W, bh, cnvB, cnvH2, cnvV, hsmall(32 * 4 + kk), trd(k);
+  if (NonLinear) { W.assign((size_t)p * k, 1.0); CU(cudaMemcpyAsync(Wd.p, W.data(), sizeof(double) * p * k, cudaMemcpyHostToDevice, st)); }
+  const double logtol = std::log10(F.tol);
+  int numit = 0, rc = 0;
+  MrrGenArgs a;
+  a.g = h->view(); a.k = k; a.rows_per_cta = rp; a.innergs = innergs ? 1 : 0; a.perm = permd.p; a.irgs = permd.p + p; a.zbits = zbits.p;
+  a.e = ed.p; a.b = bd.p; a.fixed = fixd.p; a.mean = meand.p; a.sol = sold.p; a.se0 = d_se; a.part = partd.p; a.bar = bar.p; a.err = h->err.p;
+  while (numit < maxit) {
+    const Mat vb0(vb); const std::vector<double> h20(h2);
+    CU(cudaMemcpyAsync(bold.p, bd.p, sizeof(double) * p * k, cudaMemcpyDeviceToDevice, st));  // beta0 (:475)
+    std::shuffle(order.begin(), order.end(), std::mt19937(numit));                           // :483-484, cumulative
+    std::shuffle(irgs.begin(), irgs.begin() + k, std::mt19937(numit));
+    CU(cudaMemcpyAsync(permd.p, order.data(), sizeof(int) * p, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(permd.p + p, irgs.data(), sizeof(int) * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_iG, iG.data(), sizeof(double) * kk, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_vb, vb.data(), sizeof(double) * kk, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_iVe, iVe.data(), sizeof(double) * k, cudaMemcpyHostToDevice, st));
+    // MRR3 applies the marker weights in the solve (:504); MRR3F never does (its weights are an output only)
+    launch_mrr_gen_systems((int)p, k, fixd.p, (NonLinear && !f32_variant) ? Wd.p : nullptr, d_iG, d_vb, d_iVe, noinv_system ? 1 : 0,
+                           innergs ? 1 : 0, sold.p, st);
+    launch_mrr_gen_colred(ed.p, nullptr, ld, (int)n, k, d_se, st);
+    CU(cudaMemsetAsync(bar.p, 0, sizeof(unsigned int), st));
+    {
+      const cudaError_t le = launch_mrr_gen_sweep(a, grid, st);
+      if (le != cudaSuccess) return fail(BWGR_ERR_CUDA, "MRR3 general sweep launch failed: %s", cudaGetErrorString(le));
+    }
+    launch_mrr_gen_colred(ed.p, yd.p, ld, (int)n, k, d_ey, st);  // e.y (:536)
+    h->launches += 4;
+    CU(cudaMemcpyAsync(hsmall.data(), d_ey, sizeof(double) * k, cudaMemcpyDeviceToHost, st));
+    if (NonLinear) { bh.resize((size_t)p * k); CU(cudaMemcpyAsync(bh.data(), bd.p, sizeof(double) * p * k, cudaMemcpyDeviceToHost, st)); }
+    CU(cudaStreamSynchronize(st));
+    rc = check_err_flag(h, "MRR3 general sweep");
+    if (rc) return rc;
+    if (NonLinear) {  // :524-533
+      std::vector<double> tmpW(p);
+      for (int t = 0; t < k; t++) {
+        double maxW = -INFINITY, minW = INFINITY;
+        for (int64_t j = 0; j < p; j++) { const double v = std::fabs(bh[(size_t)j * k + t]); maxW = std::max(maxW, v); minW = std::min(minW, v); }
+        double sw = 0;
+        for (int64_t j = 0; j < p; j++) { tmpW[j] = F.NLfactor * (std::fabs(bh[(size_t)j * k + t]) - minW) / (maxW - minW) + (1.0 - F.NLfactor); sw += tmpW[j]; }
+        const double mw = sw / (double)p;
+        for (int64_t j = 0; j < p; j++) W[(size_t)j * k + t] = tmpW[j] + (1.0 - mw);
+      }
+      CU(cudaMemcpyAsync(Wd.p, W.data(), sizeof(double) * p * k, cudaMemcpyHostToDevice, st));
+    }
+    // ---- residual variances (:536-543)
+    for (int t = 0; t < k; t++) { ve[t] = (hsmall[t] + Se[t]) * iNp[t]; h2[t] = 1 - ve[t] / vy[t]; }
+    if (F.wph2 > 0) for (int t = 0; t < k; t++) ve[t] = ve[t] * (1 - F.wph2) + F.wph2 * veInit[t];
+    if (F.OneVarE) { double m = 0; for (int t = 0; t < k; t++) m += ve[t]; m /= k; for (int t = 0; t < k; t++) ve[t] = m; }
+    for (int t = 0; t < k; t++) iVe[t] = 1.0 / ve[t];
+    // ---- tilde-hat (:546-556) and the convergence sums (:662)
+    if (F.TH) {
+      std::vector<double> par(64, 0.0);
+      for (int t = 0; t < k; t++) { par[t] = ve[t]; par[k + t] = iG[M(t, t)]; }
+      CU(cudaMemcpyAsync(d_par, par.data(), sizeof(double) * 2 * k, cudaMemcpyHostToDevice, st));
+      launch_mrr_gen_pk(2, xsxd.p, nullptr, dinvd.p, d_par, (int)p, k, d_trd, st);
+      launch_mrr_gen_pk(0, bd.p, tilded.p, dinvd.p, nullptr, (int)p, k, d_th, st);
+      h->launches++;
+    } else {
+      launch_mrr_gen_pk(0, bd.p, tilded.p, nullptr, nullptr, (int)p, k, d_th, st);
+    }
+    launch_mrr_gen_pk(1, bold.p, bd.p, nullptr, nullptr, (int)p, k, d_cnv, st);
+    h->launches += 2;
+    CU(cudaMemcpyAsync(hsmall.data(), d_cnv, sizeof(double) * 64, cudaMemcpyDeviceToHost, st));  // cnv | trd
+    CU(cudaMemcpyAsync(hsmall.data() + 128, d_th, sizeof(double) * kk, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) TildeHat[M(i, j)] = hsmall[128 + (size_t)i * k + j];
+    for (int t = 0; t < k; t++) trd[t] = hsmall[32 + t];
+    mrr_varcomp(F, k, TildeHat, F.TH ? trd : TrXSX, h2, V);
+    if (F.updateMu) {  // :651-655; iN is 1 / (n_t - 1) by now (:395)
+      launch_mrr_gen_colred(ed.p, nullptr, ld, (int)n, k, d_se, st);
+      std::vector<double> sh(k);
+      CU(cudaMemcpyAsync(sh.data(), d_se, sizeof(double) * k, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      for (int t = 0; t < k; t++) { sh[t] /= (nn[t] - 1.0); mu[t] += sh[t]; }
+      CU(cudaMemcpyAsync(d_shift, sh.data(), sizeof(double) * k, cudaMemcpyHostToDevice, st));
+      launch_mrr_gen_shift(ed.p, zbits.p, ld, (int)n, k, d_shift, st);
+      CU(cudaStreamSynchronize(st));
+      h->launches += 2;
+    }
+    double mx = -1e300;
+    for (int t = 0; t < k; t++) mx = std::max(mx, hsmall[t]);
+    const double cnv = std::log10(mx);
+    cnvB.push_back(cnv);
+    if (cnv != cnv) break;  // :663
+    { double sH = 0; for (int t = 0; t < k; t++) sH += (h20[t] - h2[t]) * (h20[t] - h2[t]); cnvH2.push_back(std::log10(sH)); }
+    { double sV = 0; for (size_t i = 0; i < vb.size(); i++) sV += (vb0[i] - vb[i]) * (vb0[i] - vb[i]); cnvV.push_back(std::log10(sV)); }
+    ++numit;
+    if (cnv < logtol) break;
+  }
+  // ---- outputs (:676-700): hat = X_c b + mu = X b + (mu - sum_j mean_j b_j)
+  bh.resize((size_t)p * k);
+  CU(cudaMemcpyAsync(bh.data(), bd.p, sizeof(double) * p * k, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  {
+    DevBuf<float> bf, mud, hatd;
+    std::vector<float> bt(p), hh(n);
+    if (bf.alloc(p) != cudaSuccess || mud.alloc(1) != cudaSuccess || hatd.alloc(ld) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+    for (int t = 0; t < k && hat_out; t++) {
+      double shift = 0;
+      for (int64_t j = 0; j < p; j++) { const double v = bh[(size_t)j * k + t]; shift += meanv[j] * v; bt[j] = (float)v; }
+      const float m0 = (float)(mu[t] - shift);
+      CU(cudaMemcpyAsync(bf.p, bt.data(), sizeof(float) * p, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(mud.p, &m0, sizeof(float), cudaMemcpyHostToDevice, st));
+      rc = fit_hat(h, bf.p, mud.p, hatd.p);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(hh.data(), hatd.p, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      for (int64_t i = 0; i < n; i++) hat_out[(size_t)t * n + i] = hh[i];
+    }
+  }
+  for (int t = 0; t < k; t++) {
+    if (mu_out) mu_out[t] = mu[t];
+    if (h2_out) h2_out[t] = h2[t];
+    if (ve_out) ve_out[t] = ve[t];
+    if (MSx_out) MSx_out[t] = MSx[t];
+  }
+  if (b_out) for (int t = 0; t < k; t++) for (int64_t j = 0; j < p; j++) b_out[(size_t)t * p + j] = bh[(size_t)j * k + t];
+  if (W_out) for (int t = 0; t < k; t++) for (int64_t j = 0; j < p; j++) W_out[(size_t)t * p + j] = NonLinear ? W[(size_t)j * k + t] : 1.0;
+  if (GC_out) for (int i = 0; i < kk; i++) GC_out[i] = GC[i];
+  if (vb_out) for (int i = 0; i < kk; i++) vb_out[i] = vb[i];
+  if (cnv_out)
+    for (int i = 0; i < numit; i++) { cnv_out[i] = cnvB[i]; cnv_out[maxit + i] = cnvH2[i]; cnv_out[2 * maxit + i] = cnvV[i]; }
+  if (its_out) *its_out = numit;
+  return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -1978,19 +2324,18 @@ int bwgr_mrr3_fit(bwgr_handle* h, int f32_variant, const double* Y, int k, const
   if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
   if (!Y || !par) return fail(BWGR_ERR_ARG, "null argument");
   if (k < 1 || k > 32) return fail(BWGR_ERR_UNSUPPORTED, "MRR3 on the B200 path takes 1..32 traits (k=%d)", k);
-  int q = 0;
-  const int maxit = (int)par[q++]; const double tol = par[q++]; q++; const bool TH = par[q++] != 0; const double NLfactor = par[q++];
-  const bool InnerGS = par[q++] != 0, NoInv = par[q++] != 0, HCS = par[q++] != 0, XFA = par[q++] != 0, ACS = par[q++] != 0;
-  const int NumXFA = (int)par[q++]; const double R2 = par[q++], gc0 = par[q++], df0 = par[q++]; const bool updateMu = par[q++] != 0;
-  const double wph2 = par[q++], wpgc = par[q++], PenCor = par[q++], MinCor = par[q++], uncorH2below = par[q++];
-  const double rUpFrom = par[q++], rUpTo = par[q++], rDownFrom = par[q++], rDownTo = par[q++], bkFrom = par[q++], bkTo = par[q++];
-  const double DeflateMax = par[q++], DeflateBy = par[q++]; const bool OneVarB = par[q++] != 0, OneVarE = par[q++] != 0;
-  if (TH || NLfactor != 0 || InnerGS || (f32_variant && NoInv))
-    return fail(BWGR_ERR_UNSUPPORTED, "MRR3: TH, NLfactor, InnerGS and MRR3F's NoInv system are not on the B200 path");
+  const MrrFlags F(par);
+  const int maxit = F.maxit; const double tol = F.tol, R2 = F.R2, gc0 = F.gc0, df0 = F.df0, wph2 = F.wph2;
+  const bool updateMu = F.updateMu, OneVarE = F.OneVarE;
   if (maxit < 1) return fail(BWGR_ERR_ARG, "maxit < 1");
   const int64_t n = h->n, p = h->p, ld = h->ld;
-  for (int64_t i = 0; i < n * k; i++)
-    if (!(Y[i] == Y[i])) return fail(BWGR_ERR_UNSUPPORTED, "MRR3: missing phenotypes (NaN) need the per-trait masked solve, not built");
+  bool missing = false;
+  for (int64_t i = 0; i < n * k && !missing; i++) missing = !(Y[i] == Y[i]);
+  // Everything the rotation cannot express -- missing phenotypes (per-trait XX), the inner Gauss-Seidel solve, marker weights,
+  // MRR3F's NoInv system, the tilde-hat estimator -- runs on the general device path (mrr_gen.cu); BWGR_MRR=general forces it.
+  const char* force = getenv("BWGR_MRR");
+  if (missing || F.TH || F.NLfactor != 0 || F.InnerGS || (f32_variant && F.NoInv) || (force && !strcmp(force, "general")))
+    return mrr3_general(h, f32_variant, Y, k, F, mu_out, b_out, hat_out, h2_out, GC_out, vb_out, ve_out, MSx_out, cnv_out, W_out, its_out);
   auto M = [k](int r, int c) { return (size_t)r + (size_t)c * k; };
   // ---- setup (:359-432), double on the host
   std::vector<double> mu(k), vy(k), ve(k), iVe(k), vbInit(k), veInit(k), h2(k), MSx(k), Se(k);
@@ -2012,7 +2357,9 @@ int bwgr_mrr3_fit(bwgr_handle* h, int f32_variant, const double* Y, int k, const
   }
   if (!(msx > 0)) return fail(BWGR_ERR_ARG, "genotypes have no variance");
   const double TrXSX = (double)n * msx, iNp = 1.0 / ((double)n + df0 - 1.0);
-  Mat vb((size_t)k * k, 0.0), iG((size_t)k * k, 0.0), GC((size_t)k * k, 0.0), A, TildeHat((size_t)k * k), Sb;
+  MrrVar V;
+  Mat &vb = V.vb, &iG = V.iG, &GC = V.GC, &Sb = V.Sb, TildeHat((size_t)k * k);
+  vb.assign((size_t)k * k, 0.0); iG.assign((size_t)k * k, 0.0); GC.assign((size_t)k * k, 0.0);
   for (int t = 0; t < k; t++) {
     MSx[t] = msx; ve[t] = vy[t] * (1 - R2); iVe[t] = 1.0 / ve[t]; veInit[t] = ve[t];
     vbInit[t] = vy[t] * R2 / msx; vb[M(t, t)] = vbInit[t]; iG[M(t, t)] = 1.0 / vbInit[t]; h2[t] = 1 - ve[t] / vy[t];
@@ -2020,6 +2367,7 @@ int bwgr_mrr3_fit(bwgr_handle* h, int f32_variant, const double* Y, int k, const
   for (int i = 0; i < k; i++) for (int j = 0; j < i; j++) { const double v = gc0 * std::sqrt(vb[M(i, i)] * vb[M(j, j)]); vb[M(i, j)] = v; vb[M(j, i)] = v; }
   Sb = vb;
   for (auto& v : Sb) v *= df0;
+  V.vbInit = vbInit;
   for (int t = 0; t < k; t++) Se[t] = ve[t] * df0;
   // ---- device state through the common fit machinery: k systems of the rotated ridge rule
   FitSpec s;
@@ -2050,8 +2398,7 @@ int bwgr_mrr3_fit(bwgr_handle* h, int f32_variant, const double* Y, int k, const
   std::vector<double> cnvB, cnvH2, cnvV, hred((size_t)k * k + 3 * k);
   std::vector<float> Tf(32 * 32), Tif(32 * 32), hmax(32);
   std::vector<SysScalars> sc(f.sc0);
-  double Deflate = 1, inflate = 0;
-  const double logtol = std::log10(tol), bucketMean = 0.5 * (bkFrom + bkTo);
+  const double logtol = std::log10(tol);
   int numit = 0;
   while (numit < maxit) {
     const Mat vb0(vb); const std::vector<double> h20(h2);
@@ -2109,82 +2456,7 @@ int bwgr_mrr3_fit(bwgr_handle* h, int f32_variant, const double* Y, int k, const
     if (wph2 > 0) for (int t = 0; t < k; t++) ve[t] = ve[t] * (1 - wph2) + wph2 * veInit[t];
     if (OneVarE) { double m = 0; for (int t = 0; t < k; t++) m += ve[t]; m /= k; for (int t = 0; t < k; t++) ve[t] = m; }
     for (int t = 0; t < k; t++) iVe[t] = 1.0 / ve[t];
-    for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) {
-      if (i == j) vb[M(i, i)] = (TildeHat[M(i, i)] + Sb[M(i, i)]) / (TrXSX + df0);
-      else vb[M(i, j)] = (TildeHat[M(i, j)] + TildeHat[M(j, i)] + Sb[M(i, j)]) / (TrXSX + TrXSX + df0);
-    }
-    if (wph2 > 0) for (int i = 0; i < k; i++) vb[M(i, i)] = vb[M(i, i)] * (1 - wph2) + wph2 * vbInit[i];
-    if (wpgc > 0) {
-      for (int i = 0; i < k; i++) for (int j = 0; j < k; j++)
-        GC[M(i, j)] = (i != j) ? (1.0 - wpgc) * vb[M(i, j)] / std::sqrt(vb[M(i, i)] * vb[M(j, j)]) + gc0 * wpgc : 1.0;
-      for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) if (i != j) vb[M(i, j)] = GC[M(i, j)] * std::sqrt(vb[M(i, i)] * vb[M(j, j)]);
-    } else {
-      for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) GC[M(i, j)] = vb[M(i, j)] / std::sqrt(vb[M(i, i)] * vb[M(j, j)]);
-    }
-    auto top_factors = [&](double add, double scale) {  // :593-600, :612-617
-      std::vector<double> ew; Mat ev;
-      sym_eig(GC, k, ew, ev);
-      Mat UDU((size_t)k * k, 0.0);
-      for (int fI = 0; fI < NumXFA && fI < k; fI++) {
-        const int c = k - fI - 1;
-        for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) UDU[M(i, j)] += ew[c] * ev[M(i, c)] * ev[M(j, c)];
-      }
-      for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) GC[M(i, j)] = (UDU[M(i, j)] + add) * scale;
-      for (int i = 0; i < k; i++) GC[M(i, i)] = 1;
-    };
-    if (ACS) {
-      double gs = 0;
-      for (double v : GC) gs += v;
-      gs = (gs - k) / ((k * (k - 1))) / 2.0;
-      top_factors(gs, 0.5);
-    } else if (HCS) {
-      double gs = 0;
-      for (int i = 0; i < k; i++) for (int j = 0; j < i; j++) gs += GC[M(i, j)];
-      gs = gs / ((k * (k - 1)) / 2);
-      for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) GC[M(i, j)] = (i != j) ? gs : 1.0;
-    } else if (XFA) {
-      top_factors(0.0, 1.0);
-    }
-    for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) if (i != j) {  // :619-626
-      double& g = GC[M(i, j)];
-      if (MinCor < 1 && g < MinCor) g = 0;
-      if (PenCor > 0) g = std::tanh(PenCor * std::fabs(g)) * g;
-      if (rDownFrom < 1 && g < rDownFrom) g = rDownTo;
-      if (rUpFrom < 1 && g > rUpFrom) g = rUpTo;
-      if (bkFrom < 1 && g > bkFrom && g < bkTo) g = bucketMean;
-      if (uncorH2below > 0 && (h2[i] < uncorH2below || h2[j] < uncorH2below)) g = 0;
-    }
-    {  // bending (:629-644)
-      A = GC;
-      if (DeflateBy > 0) {
-        for (auto& v : A) v *= Deflate;
-        for (int i = 0; i < k; i++) A[M(i, i)] = 1;
-        if (!chol_ok(A, k) && Deflate > DeflateMax) {
-          Deflate -= DeflateBy;
-          A = GC;
-          for (auto& v : A) v *= Deflate;
-          for (int i = 0; i < k; i++) A[M(i, i)] = 1;
-        }
-      }
-      std::vector<double> ew; Mat ev;
-      sym_eig(A, k, ew, ev);
-      if (ew[0] < 0) {
-        inflate = std::fabs(ew[0] * 1.1);
-        for (int i = 0; i < k; i++) A[M(i, i)] += inflate;
-        for (auto& v : A) v /= (1.0 + inflate);
-        GC = A;
-      }
-    }
-    if (OneVarB) {
-      double tmp = 0;
-      for (int i = 0; i < k; i++) tmp += TildeHat[M(i, i)];
-      tmp /= k;
-      for (size_t i = 0; i < vb.size(); i++) vb[i] = GC[i] * tmp;
-    } else {
-      const Mat dv(vb);
-      for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) vb[M(i, j)] = GC[M(i, j)] * std::sqrt(dv[M(i, i)] * dv[M(j, j)]);
-    }
-    sym_pinv(vb, k, iG);
+    { const std::vector<double> Tr((size_t)k, TrXSX); mrr_varcomp(F, k, TildeHat, Tr, h2, V); }
     if (updateMu) {  // :651-655 (complete Y: Z = 1)
       std::vector<float> sh(k);
       for (int t = 0; t < k; t++) { const double m = small[k + t] / ((double)n - 1.0); mu[t] += m; sh[t] = (float)(-m); }

@@ -216,4 +216,35 @@ void launch_rotate(const float* in, float* out, int64_t ld, int len, int k, cons
 void launch_pair_reduce(const float* A, const float* B, int64_t lda, int64_t ldb, int len, int k, int mode, double* out,
                         cudaStream_t st);
 
+// ---- general multivariate ridge sweep (mrr_gen.cu): missing phenotypes, InnerGS, marker weights, NoInv, TH --------------
+struct MrrGenArgs {
+  GenoView g;
+  int k;
+  int rows_per_cta;       // multiple of 16; grid * rows_per_cta >= ld
+  int innergs;            // sol holds [LHS | PRE] per marker and the chain walks the inner Gauss-Seidel order
+  const int* perm;        // marker order of this sweep [p]
+  const int* irgs;        // inner order [k] (InnerGS) or nullptr
+  const uint32_t* zbits;  // [ld] bit t = trait t observed in row i
+  double* e;              // [k][ld] residuals (zero where unobserved)
+  double* b;              // [p][k] effects, marker-major
+  const double* fixed;    // [p][2k]: XX(j, 0..k) | sum_i (x_ij - mean_j) z_it
+  const double* mean;     // [p] column means
+  const double* sol;      // [p][nmat * k * k] from launch_mrr_gen_systems
+  const double* se0;      // [k] column sums of e at launch
+  double* part;           // [2][grid][32] per-CTA partial dot products
+  unsigned int* bar;      // arrival counter, zeroed before launch
+  int* err;
+};
+size_t mrr_gen_smem(int k, int rows_per_cta, int innergs);
+// masked integer column sums and X'y in one pass: sxz, sxxz, xty are [p][k] (y: [k][ld] float64, zero where unobserved)
+void launch_mrr_gen_colstats(const GenoView& g, const uint32_t* zbits, const double* y, int k, double* sxz, double* sxxz,
+                             double* xty, cudaStream_t st);
+void launch_mrr_gen_systems(int p, int k, const double* fixed, const double* W, const double* iG, const double* vb,
+                            const double* iVe, int noinv_system, int innergs, double* sol, cudaStream_t st);
+cudaError_t launch_mrr_gen_sweep(const MrrGenArgs& a, int grid, cudaStream_t st);
+void launch_mrr_gen_colred(const double* A, const double* B, int64_t ld, int n, int k, double* out, cudaStream_t st);
+void launch_mrr_gen_pk(int mode, const double* A, const double* B, double* C, const double* par, int p, int k, double* out,
+                       cudaStream_t st);
+void launch_mrr_gen_shift(double* e, const uint32_t* zbits, int64_t ld, int n, int k, const double* shift, cudaStream_t st);
+
 }  // namespace bwgr
