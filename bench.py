@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--cpu-sweeps", type=int, default=10)
     ap.add_argument("--cpu-sweeps-main", type=int, default=150, help="sweeps of the cpu_baseline sample of the main arm (~15 s)")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch of the dominant kernel from an ncu capture (profiles/)")
+    ap.add_argument("--missing", type=float, default=0.0,
+                    help="--config 3 only: fraction of the phenotypes set to NaN at random (unbalanced traits: MRR3's general device path)")
     ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4, 5],
                     help="BASELINE.json configs[k-1]... 1 (default) = the metric's configuration (emRR 50k x 50k); 2 wgr BayesB 10k x 50k; "
                          "3 MRR3 50k x 50k x 20 traits; 4 5-fold x 20-trait emBC fits; 5 row shards of 62500 x 100k per GPU (500k x 100k over 8)")
@@ -319,6 +321,11 @@ def run_config(args, rank, world, local):
         name = "MRR3 multivariate ridge, synthetic n=50000 x p=50000 int8 genotypes, k=20 traits; step = one sweep (p marker updates of 20 traits each)"
         call = lambda it: bw.MRR3(Y, g, maxit=it, tol=0.0)  # noqa: E731
         kernel = "sweep_pipe_kernel (20 rotated systems)"
+        if args.missing > 0:
+            Y = Y.copy()
+            Y[rng.random(Y.shape) < args.missing] = np.nan
+            name += "; %.0f %% of the phenotypes missing at random (per-trait masked k x k systems, float64)" % (100 * args.missing)
+            kernel = "mrr_gen_sweep_kernel (one k x k system per marker, per-marker grid sum)"
     else:
         folds = 5
         perm = rng.permutation(n)

@@ -407,6 +407,25 @@ def KMUP(X, b, d, xx, e, L, Ve, pi, seed=1, **store_kw):
             g.close()
 
 
+def KMUP2(X, Use, b, d, xx, E, L, Ve, pi, seed=1, **store_kw):
+    """The bagged Kuo-Mallick sweep, drop-in for KMUP2(X,Use,b,d,xx,E,L,Ve,pi) (Rcpp20260726ai.cpp:41-77): Use = 0-based rows (distinct);
+    returns (b, d, e) with e the residuals of the rows in use, like the reference's list."""
+    g, own = _store(X, **store_kw)
+    try:
+        Use = np.array(Use, dtype=np.float64).ravel()
+        b, d, xx, E, L = (np.array(v, dtype=np.float64) for v in (b, d, xx, E, L))
+        _need(b.size == g.p and d.size == g.p and xx.size == g.p and L.size == g.p, "KMUP2: b, d, xx, L must have p = %d values" % g.p)
+        _need(E.size == g.n, "KMUP2: E must have n = %d values" % g.n)
+        _need(2 <= Use.size <= g.n, "KMUP2: Use must name between 2 and n rows")
+        e = np.zeros(Use.size)
+        check(g.lib.bwgr_kmup2_sweep(g.h, _ptr(Use), int(Use.size), _ptr(b), _ptr(d), _ptr(xx), _ptr(E), _ptr(e), _ptr(L), float(Ve),
+                                     float(pi), int(seed)))
+        return {"b": b, "d": d, "e": e}
+    finally:
+        if own:
+            g.close()
+
+
 def _gs(which, y, e, gen, b, Lmb, xx, cxx, maxit, **store_kw):
     g, own = _store(gen, **store_kw)
     try:
@@ -436,8 +455,8 @@ def wgr(y, X, it=1500, bi=500, th=1, bag=1, rp=False, iv=False, de=False, pi=0, 
         verb=False, seed=1, **store_kw):
     """wgr() of R/wgr.R:2-8 with the MCMC loop native (one C call instead of `it` KMUP round trips).
     Model map (man/wgr.Rd:185): BRR pi=0,iv=F; BayesA iv=T; BayesB pi>0,iv=T; BayesC pi>0,iv=F; BayesL de=T."""
-    if bag != 1 or rp or eigK is not None:
-        raise _lib.BwgrError(-5, "wgr: bag != 1, rp and eigK are not on the B200 path")
+    if eigK is not None:
+        raise _lib.BwgrError(-5, "wgr: the polygenic term (eigK: Kuo-Mallick sweeps over real-valued eigenvectors) is not on the B200 path")
     g, own = _store(X, **store_kw)
     try:
         y = np.ascontiguousarray(y, dtype=np.float64)
@@ -445,8 +464,12 @@ def wgr(y, X, it=1500, bi=500, th=1, bag=1, rp=False, iv=False, de=False, pi=0, 
         b, d, Vb = (np.zeros(g.p) for _ in range(3))
         hat = np.zeros(g.n)
         scal = np.zeros(4)
-        check(g.lib.bwgr_wgr_fit(g.h, _ptr(y), int(it), int(bi), int(th), int(bool(iv)), int(bool(de)), float(pi), float(df),
-                                 float(R2), int(seed), _ptr(b), _ptr(d), _ptr(Vb), _ptr(hat), _ptr(scal)))
+        if bag != 1:  # R/wgr.R:21, :68, :87: a fresh row sample per iteration, swept by KMUP2
+            check(g.lib.bwgr_wgr_fit_bag(g.h, _ptr(y), int(it), int(bi), int(th), float(bag), int(bool(rp)), int(bool(iv)), int(bool(de)),
+                                         float(pi), float(df), float(R2), int(seed), _ptr(b), _ptr(d), _ptr(Vb), _ptr(hat), _ptr(scal)))
+        else:
+            check(g.lib.bwgr_wgr_fit(g.h, _ptr(y), int(it), int(bi), int(th), int(bool(iv)), int(bool(de)), float(pi), float(df),
+                                     float(R2), int(seed), _ptr(b), _ptr(d), _ptr(Vb), _ptr(hat), _ptr(scal)))
         return {"mu": float(scal[0]), "b": b, "Vb": Vb if (iv or de) else float(scal[2]), "d": d, "Ve": float(scal[1]),
                 "hat": hat, "cxx": float(scal[3])}
     finally:

@@ -932,7 +932,7 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
   if (dist) {
     if (!h->hx_connected) return fail(BWGR_ERR_STATE, "row-sharded handle: call bwgr_dist_connect before fitting");
     if (s.row_mask) return fail(BWGR_ERR_UNSUPPORTED, "row-sharded fits take unmasked systems");
-    if (s.model == M_MRR || s.model == M_KMUP) return fail(BWGR_ERR_UNSUPPORTED, "row sharding covers the univariate EM and Gibbs solvers");
+    if (s.model == M_MRR || s.model == M_KMUP || s.model == M_KMUP2) return fail(BWGR_ERR_UNSUPPORTED, "row sharding covers the univariate EM and Gibbs solvers");
   }
   const int saved_path_ = h->path;
   if (dist) h->path = BWGR_PATH_BLOCKED;
@@ -1116,6 +1116,7 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
         c.MSx = sum_vx; c.ve = 1; c.vb = 1; c.lmb = 1;
         break;
       }
+      case M_KMUP2:
       case M_KMUP: {  // state comes from the caller (KMUP :12-38) or from the wgr driver (R/wgr.R:46-59)
         c.MSx = sum_vx; c.ve = 1; c.vb = 1; c.lmb = 1;
         break;
@@ -1383,6 +1384,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
       memset(&a, 0, sizeof a);
       a.g = g; a.model = rule_model(f.model); a.nsys = f.nsys; a.perms = d_perm; a.y = f.y.p; a.e = f.e.p; a.b = f.b.p; a.d = f.d.p;
       a.vbv = f.vbv.p; a.xx = f.masked ? f.xx_sys.p : (f.xx_over.p ? f.xx_over.p : h->xx_f.p); a.xx_per_sys = f.masked ? 1 : 0; a.mask = f.mask.p;
+      a.xx2 = f.xx_over.p;
       a.sc = f.sc.p; a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0; a.err = h->err.p;
       cudaEvent_t pe = h->prof_begin(1);
       launch_small_n(a, h->smem_optin, h->stream);
@@ -1756,14 +1758,16 @@ int bwgr_gibbs_fit(bwgr_handle* h, const bwgr_gibbs_params* par, const double* y
 
 // Common start of KMUP / wgr: a one-system M_KMUP fit whose state (b, d, e, per-marker L, Ve, pi) is set by the caller.
 static int kmup_begin(bwgr_handle* h, const double* b, const double* d, const double* xx, const double* e, const double* L,
-                      double Ve, double pi, uint64_t seed) {
+                      double Ve, double pi, uint64_t seed, const uint8_t* row_mask = nullptr, double xx_scale = 1.0) {
   if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
   if (!b || !e || !L) return fail(BWGR_ERR_ARG, "null argument");
   if (!(Ve > 0)) return fail(BWGR_ERR_ARG, "Ve must be positive");
   const int64_t n = h->n, p = h->p, ld = h->ld;
   FitSpec s;
-  s.model = M_KMUP; s.nsys = 1; s.shuffled = false; s.row_mask = nullptr;
+  // row_mask = the bagged sweep KMUP2 (:41-77): the rows in use as a mask on the small-n family, xx_scale = bg = n0 / n (:47)
+  s.model = row_mask ? M_KMUP2 : M_KMUP; s.nsys = 1; s.shuffled = false; s.row_mask = row_mask;
   s.df = 5; s.R2 = 0.5f; s.Pi = 0; s.alpha = 0; s.pi = (float)pi; s.it = 1; s.bi = 0; s.seed = seed;
+  if (row_mask && !xx) return fail(BWGR_ERR_ARG, "KMUP2 needs xx");
   int rc = fit_begin(h, s, e);  // y := e (only its mean/variance feed unused defaults)
   if (rc) return rc;
   Fit& f = h->fit;
@@ -1789,7 +1793,7 @@ static int kmup_begin(bwgr_handle* h, const double* b, const double* d, const do
   CU(cudaMemcpyAsync(f.sc.p, &c, sizeof(SysScalars), cudaMemcpyHostToDevice, h->stream));
   if (xx) {
     std::vector<float> hx(p);
-    for (int64_t j = 0; j < p; j++) hx[j] = (float)xx[j];
+    for (int64_t j = 0; j < p; j++) hx[j] = (float)xx[j] * (float)xx_scale;
     if (f.xx_over.alloc(p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
     CU(cudaMemcpyAsync(f.xx_over.p, hx.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
   }
@@ -1894,6 +1898,164 @@ int bwgr_wgr_fit(bwgr_handle* h, const double* y, int it, int bi, int th, int iv
   f.reset();
   return 0;
 }
+
+// Rows of one bagged iteration as a 0/1 mask.  use: 0-based row indices as R passes them (doubles).  Duplicates (sampling with
+// replacement, rp = TRUE) would need row multiplicities in the dot products: not built.
+static int use_to_mask(const double* use, int64_t nuse, int64_t n, std::vector<uint8_t>& mask) {
+  mask.assign((size_t)n, 0);
+  for (int64_t q = 0; q < nuse; q++) {
+    const int64_t r = (int64_t)use[q];
+    if (r < 0 || r >= n) return fail(BWGR_ERR_ARG, "Use[%lld] = %lld is not a row of X", (long long)q, (long long)r);
+    if (mask[r]) return fail(BWGR_ERR_UNSUPPORTED, "KMUP2: repeated rows (sampling with replacement) are not on the B200 path");
+    mask[r] = 1;
+  }
+  return 0;
+}
+
+// KMUP2(X,Use,b,d,xx,E,L,Ve,pi) (:41-77): one Kuo-Mallick sweep over the rows Use.  b, d updated in place; e_out [nuse] = the
+// residuals of the rows in use, in the order of Use (the reference's third list element).  Runs on the small-n family (row mask).
+int bwgr_kmup2_sweep(bwgr_handle* h, const double* use, int64_t nuse, double* b, double* d, const double* xx, const double* E,
+                     double* e_out, const double* L, double Ve, double pi, uint64_t seed) {
+  if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
+  if (!use || !E || !e_out || nuse < 2) return fail(BWGR_ERR_ARG, "KMUP2: bad Use / E / e_out");
+  const int64_t n = h->n, p = h->p;
+  std::vector<uint8_t> mask;
+  int rc = use_to_mask(use, nuse, n, mask);
+  if (rc) return rc;
+  rc = kmup_begin(h, b, d, xx, E, L, Ve, pi, seed, mask.data(), (double)((float)n / (float)nuse));
+  if (rc) return rc;
+  Fit& f = h->fit;
+  f.skip_epilogue = true;
+  rc = fit_sweeps(h, 1);
+  if (rc) return rc;
+  rc = check_err_flag(h, "kmup2 sweep");
+  if (rc) { f.reset(); return rc; }
+  std::vector<float> he(n), hb(p), hd(p);
+  CU(cudaMemcpyAsync(he.data(), f.e.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(hb.data(), f.b.p, sizeof(float) * p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(hd.data(), f.d.p, sizeof(float) * p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int64_t q = 0; q < nuse; q++) e_out[q] = he[(int64_t)use[q]];
+  for (int64_t j = 0; j < p; j++) { b[j] = hb[j]; if (d) d[j] = hd[j]; }
+  f.reset();
+  return 0;
+}
+
+// wgr(y,X,it,bi,th,bag,rp=FALSE,iv,de,pi,df,R2) for bag != 1 (R/wgr.R:21, :49, :68, :87, :121): every iteration sweeps a fresh sorted sample
+// of floor(n * bag) rows with KMUP2, estimates Ve from their residuals, and rebuilds e = y - mu - X b over all rows.  The row samples
+// come from std::mt19937_64(seed), not from R's sample().  Same outputs as bwgr_wgr_fit.
+int bwgr_wgr_fit_bag(bwgr_handle* h, const double* y, int it, int bi, int th, double bag, int rp, int iv, int de, double pi, double df,
+                     double R2, uint64_t seed, double* b, double* d, double* Vb, double* hat, double* scal) {
+  if (bag == 1.0) return bwgr_wgr_fit(h, y, it, bi, th, iv, de, pi, df, R2, seed, b, d, Vb, hat, scal);
+  if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
+  if (!y) return fail(BWGR_ERR_ARG, "y is NULL");
+  if (it < 1 || bi < 1 || bi > it || th < 1) return fail(BWGR_ERR_ARG, "need 1 <= bi <= it and th >= 1");
+  if (rp) return fail(BWGR_ERR_UNSUPPORTED, "wgr(rp = TRUE): sampling rows with replacement is not on the B200 path");
+  const int64_t n = h->n, p = h->p, ld = h->ld;
+  const int64_t nuse = (int64_t)((double)n * bag);
+  if (!(bag > 0) || nuse < 2 || nuse > n) return fail(BWGR_ERR_ARG, "bag must give 2 <= n * bag <= n rows without replacement");
+  if (de) iv = 1;
+  df = df / (bag * bag);  // :21
+  double mu = 0;
+  for (int64_t i = 0; i < n; i++) { if (!(y[i] == y[i])) return fail(BWGR_ERR_ARG, "y contains NaN"); mu += y[i]; }
+  mu /= (double)n;
+  double vy = 0;
+  for (int64_t i = 0; i < n; i++) vy += (y[i] - mu) * (y[i] - mu);
+  vy /= (double)(n - 1);
+  double MSx = 0, sxx = 0;
+  for (int64_t j = 0; j < p; j++) { MSx += (h->h_xx[j] - h->h_sx[j] * h->h_sx[j] / (double)n) / ((double)n - 1.0); sxx += h->h_xx[j] * bag; }
+  if (!(MSx > 0)) return fail(BWGR_ERR_ARG, "genotypes have no variance");
+  std::vector<double> e0(n), b0(p, 0.0), d0(p, 1.0), L0(p, MSx), xxb(p);
+  for (int64_t i = 0; i < n; i++) e0[i] = y[i] - mu;
+  for (int64_t j = 0; j < p; j++) xxb[j] = h->h_xx[j] * bag;  // xx = crossprod * bag (:49)
+  std::mt19937_64 gen(seed ^ 0x9E3779B97F4A7C15ull);
+  std::vector<int64_t> rows(n);
+  std::vector<uint8_t> mask((size_t)ld, 0);
+  auto draw = [&]() {  // Use = sort(sample(n, n * bag)) (:68) as a mask
+    for (int64_t r = 0; r < n; r++) rows[r] = r;
+    std::fill(mask.begin(), mask.end(), 0);
+    for (int64_t r = 0; r < nuse; r++) { std::uniform_int_distribution<int64_t> pick(r, n - 1); std::swap(rows[r], rows[pick(gen)]); mask[rows[r]] = 1; }
+  };
+  draw();
+  int rc = kmup_begin(h, b0.data(), d0.data(), xxb.data(), e0.data(), L0.data(), 1.0, pi, seed, mask.data(), (double)((float)n / (float)nuse));
+  if (rc) return rc;
+  Fit& f = h->fit;
+  f.skip_epilogue = true;
+  {
+    SysScalars c = f.sc0[0];
+    c.mu = (float)mu;
+    CU(cudaMemcpyAsync(f.sc.p, &c, sizeof(SysScalars), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  DevBuf<float> yd, hatd;
+  DevBuf<long long> txx, tsx;
+  if (f.wst.alloc(1) != cudaSuccess || yd.alloc(ld) != cudaSuccess || hatd.alloc(ld) != cudaSuccess || txx.alloc(p) != cudaSuccess ||
+      tsx.alloc(p) != cudaSuccess)
+    return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  {
+    std::vector<float> yf(ld, 0.0f);
+    for (int64_t i = 0; i < n; i++) yf[i] = (float)y[i];
+    CU(cudaMemcpyAsync(yd.p, yf.data(), sizeof(float) * ld, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  CU(cudaMemsetAsync(f.wst.p, 0, sizeof(WgrState), h->stream));
+  WgrArgs& w = f.wgr_args;
+  memset(&w, 0, sizeof w);
+  w.n = (int)n; w.p = (int)p; w.ld = ld; w.e = f.e.p; w.b = f.b.p; w.d = f.d.p; w.L = f.vbv.p;
+  w.B = f.B.p; w.D = f.D.p; w.VB = f.VBv.p; w.sc = f.sc.p; w.st = f.wst.p; w.iv = iv; w.de = de;
+  w.Sb = (float)(R2 * df * vy / MSx); w.Se = (float)((1 - R2) * df * vy); w.df = (float)df; w.MSx = (float)MSx;
+  w.it = it; w.bi = bi; w.th = th; w.seed_lo = (uint32_t)seed; w.seed_hi = (uint32_t)(seed >> 32);
+  w.mask = f.mask.p; w.nsub = (float)nuse; w.y = yd.p; w.hat = hatd.p;
+  for (int i = 0; i < it; i++) {
+    if (i > 0) {  // this iteration's rows: mask, and H'H of every marker over them (the rule's likelihood-ratio scale)
+      draw();
+      CU(cudaMemcpyAsync(f.mask.p, mask.data(), (size_t)ld, cudaMemcpyHostToDevice, h->stream));
+      launch_col_stats_masked(h->view(), f.mask.p, txx.p, tsx.p, h->stream);
+      launch_ll_to_float(txx.p, f.xx_sys.p, (int)p, h->stream);
+      h->launches += 2;
+    }
+    rc = fit_sweeps(h, 1);  // KMUP2 over the rows in use
+    if (rc) return rc;
+    launch_wgr_bag_phase(w, 1, h->num_sms, h->stream);                       // Vb (with the old Ve), Va, Ve from the rows in use
+    rc = fit_hat(h, f.b.p, reinterpret_cast<const float*>(f.sc.p), hatd.p);  // mu + X b  (SysScalars starts with mu)
+    if (rc) return rc;
+    launch_wgr_bag_phase(w, 2, h->num_sms, h->stream);                       // e = y - hat, intercept draw, L, posterior sums
+    h->launches += 3;
+  }
+  rc = check_err_flag(h, "wgr (bagged) sweep");
+  if (rc) { f.reset(); return rc; }
+  WgrState st;
+  CU(cudaMemcpyAsync(&st, f.wst.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<float> B(p), D(p), V(p);
+  CU(cudaMemcpyAsync(B.data(), f.B.p, sizeof(float) * p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(D.data(), f.D.p, sizeof(float) * p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(V.data(), f.VBv.p, sizeof(float) * p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  const double mc = (double)((it - bi) / th + 1);
+  double mD = 0;
+  for (int64_t j = 0; j < p; j++) mD += D[j] / mc;
+  mD /= (double)p;
+  std::vector<float> Bm(p);
+  for (int64_t j = 0; j < p; j++) Bm[j] = (float)(B[j] / mc / mD);
+  const float B0 = (float)(st.B0 / mc);
+  DevBuf<float> bdev, mudev;
+  if (bdev.alloc(p) != cudaSuccess || mudev.alloc(1) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  CU(cudaMemcpyAsync(bdev.p, Bm.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(mudev.p, &B0, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  rc = fit_hat(h, bdev.p, mudev.p, hatd.p);
+  if (rc) return rc;
+  std::vector<float> hh(n);
+  CU(cudaMemcpyAsync(hh.data(), hatd.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (b) for (int64_t j = 0; j < p; j++) b[j] = Bm[j];
+  if (d) for (int64_t j = 0; j < p; j++) d[j] = D[j] / mc;
+  if (Vb && iv) for (int64_t j = 0; j < p; j++) Vb[j] = V[j] / mc;
+  if (hat) for (int64_t i = 0; i < n; i++) hat[i] = hh[i];
+  if (scal) { scal[0] = B0; scal[1] = st.VE / mc; scal[2] = iv ? 0.0 : st.VA / mc; scal[3] = sxx / (double)p; }
+  f.reset();
+  return 0;
+}
+
 }  // extern "C"
 
 namespace {
@@ -2116,18 +2278,18 @@ int mrr3_general(bwgr_handle* h, int f32_variant, const double* Y, int k, const 
   const size_t smem = mrr_gen_smem(k, rp, innergs);
   if (smem > h->smem_optin || grid > h->num_sms)
     return fail(BWGR_ERR_UNSUPPORTED, "MRR3 (general path): %lld rows x %d traits do not fit the shared memory of %d SMs", (long long)n, k, h->num_sms);
-  DevBuf<uint32_t> zbits; DevBuf<double> yd, ed, bd, bold, fixd, meand, tilded, sold, Wd, xsxd, dinvd, small, partd;
-  DevBuf<unsigned int> bar; DevBuf<int> permd;
-  const size_t nsmall = (size_t)2 * kk + 8 * 32;  // iG | vb | iVe | se | ey | cnv | trd | par(2 x 32) | shift
+  DevBuf<uint32_t> zbits; DevBuf<double> yd, ed, bd, bold, fixd, meand, tilded, sold, Wd, xsxd, dinvd, small;
+  DevBuf<unsigned long long> accd; DevBuf<int> permd;
+  const size_t nsmall = (size_t)2 * kk + 11 * 32;  // iG | vb | iVe | se | ey | cnv | trd | par(2 x 32) | shift | see | scale(2 x 32)
   if (zbits.alloc(ld) != cudaSuccess || yd.alloc((size_t)k * ld) != cudaSuccess || ed.alloc((size_t)k * ld) != cudaSuccess ||
       bd.alloc((size_t)p * k) != cudaSuccess || bold.alloc((size_t)p * k) != cudaSuccess || fixd.alloc((size_t)p * 2 * k) != cudaSuccess ||
       meand.alloc(p) != cudaSuccess || tilded.alloc((size_t)p * k) != cudaSuccess || sold.alloc((size_t)p * nmat * kk) != cudaSuccess ||
       (NonLinear && Wd.alloc((size_t)p * k) != cudaSuccess) || (F.TH && (xsxd.alloc((size_t)p * k) != cudaSuccess || dinvd.alloc((size_t)p * k) != cudaSuccess)) ||
-      small.alloc(nsmall + kk) != cudaSuccess || partd.alloc((size_t)2 * grid * 32) != cudaSuccess || bar.alloc(1) != cudaSuccess ||
+      small.alloc(nsmall + kk) != cudaSuccess || accd.alloc((size_t)p * 32 * kMrrGenCopies) != cudaSuccess || grid > 255 ||
       permd.alloc(p + 32) != cudaSuccess)
     return fail(BWGR_ERR_CUDA, "cudaMalloc(MRR3 general workspace) failed");
   double *d_iG = small.p, *d_vb = small.p + kk, *d_iVe = d_vb + kk, *d_se = d_iVe + 32, *d_ey = d_se + 32, *d_cnv = d_ey + 32,
-         *d_trd = d_cnv + 32, *d_par = d_trd + 32, *d_shift = d_par + 64, *d_th = small.p + nsmall;
+         *d_trd = d_cnv + 32, *d_par = d_trd + 32, *d_shift = d_par + 64, *d_see = d_shift + 32, *d_scale = d_see + 32, *d_th = small.p + nsmall;
   cudaStream_t st = h->stream;
   CU(cudaMemcpyAsync(zbits.p, zb.data(), sizeof(uint32_t) * ld, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(yd.p, yh.data(), sizeof(double) * k * ld, cudaMemcpyHostToDevice, st));
@@ -2145,7 +2307,10 @@ int mrr3_general(bwgr_handle* h, int f32_variant, const double* Y, int k, const 
     CU(cudaMemcpyAsync(tilde.data(), tilded.p, sizeof(double) * p * k, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
   }
-  std::vector<double> MSx(k, 0.0), TrXSX(k);
+  std::vector<double> MSx(k, 0.0), TrXSX(k), see(k);
+  double xxmax = 0;
+  for (int64_t j = 0; j < p; j++) xxmax = std::max(xxmax, h->h_xx[j]);
+  for (int t = 0; t < k; t++) see[t] = vy[t] * (nn[t] - 1.0);  // e = y at the start
   if (F.TH) xsx.resize((size_t)p * k);
   for (int64_t j = 0; j < p; j++) {
     const double m = h->h_sx[j] / (double)n;  // X.colwise().mean() over all n0 rows (:378)
@@ -2192,7 +2357,7 @@ int mrr3_general(bwgr_handle* h, int f32_variant, const double* Y, int k, const 
   int numit = 0, rc = 0;
   MrrGenArgs a;
   a.g = h->view(); a.k = k; a.rows_per_cta = rp; a.innergs = innergs ? 1 : 0; a.perm = permd.p; a.irgs = permd.p + p; a.zbits = zbits.p;
-  a.e = ed.p; a.b = bd.p; a.fixed = fixd.p; a.mean = meand.p; a.sol = sold.p; a.se0 = d_se; a.part = partd.p; a.bar = bar.p; a.err = h->err.p;
+  a.e = ed.p; a.b = bd.p; a.fixed = fixd.p; a.mean = meand.p; a.sol = sold.p; a.se0 = d_se; a.acc = accd.p; a.scale = d_scale; a.err = h->err.p;
   while (numit < maxit) {
     const Mat vb0(vb); const std::vector<double> h20(h2);
     CU(cudaMemcpyAsync(bold.p, bd.p, sizeof(double) * p * k, cudaMemcpyDeviceToDevice, st));  // beta0 (:475)
@@ -2207,14 +2372,24 @@ int mrr3_general(bwgr_handle* h, int f32_variant, const double* Y, int k, const 
     launch_mrr_gen_systems((int)p, k, fixd.p, (NonLinear && !f32_variant) ? Wd.p : nullptr, d_iG, d_vb, d_iVe, noinv_system ? 1 : 0,
                            innergs ? 1 : 0, sold.p, st);
     launch_mrr_gen_colred(ed.p, nullptr, ld, (int)n, k, d_se, st);
-    CU(cudaMemsetAsync(bar.p, 0, sizeof(unsigned int), st));
-    {
+    {  // fixed-point scale of the grid sums of this sweep: |x'e_t| <= sqrt(max_j x_j'x_j) |e_t| (Cauchy-Schwarz, also for the sum of
+       // the per-CTA magnitudes); 16 x headroom for the growth of |e_t| inside a sweep, 2^52 of range
+      std::vector<double> scl(64, 0.0);
+      for (int t = 0; t < k; t++) {
+        int ex = 0;
+        std::frexp(16.0 * std::sqrt(xxmax * see[t]) + 1e-300, &ex);
+        scl[t] = std::ldexp(1.0, 52 - ex); scl[32 + t] = std::ldexp(1.0, ex - 52);
+      }
+      CU(cudaMemcpyAsync(d_scale, scl.data(), sizeof(double) * 64, cudaMemcpyHostToDevice, st));
+      CU(cudaMemsetAsync(accd.p, 0, sizeof(unsigned long long) * p * 32 * kMrrGenCopies, st));
       const cudaError_t le = launch_mrr_gen_sweep(a, grid, st);
       if (le != cudaSuccess) return fail(BWGR_ERR_CUDA, "MRR3 general sweep launch failed: %s", cudaGetErrorString(le));
     }
     launch_mrr_gen_colred(ed.p, yd.p, ld, (int)n, k, d_ey, st);  // e.y (:536)
-    h->launches += 4;
+    launch_mrr_gen_colred(ed.p, ed.p, ld, (int)n, k, d_see, st);  // |e_t|^2: the next sweep's fixed-point range
+    h->launches += 5;
     CU(cudaMemcpyAsync(hsmall.data(), d_ey, sizeof(double) * k, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(see.data(), d_see, sizeof(double) * k, cudaMemcpyDeviceToHost, st));
     if (NonLinear) { bh.resize((size_t)p * k); CU(cudaMemcpyAsync(bh.data(), bd.p, sizeof(double) * p * k, cudaMemcpyDeviceToHost, st)); }
     CU(cudaStreamSynchronize(st));
     rc = check_err_flag(h, "MRR3 general sweep");

@@ -12,7 +12,8 @@ enum Model : int {
   M_BRR = 10, M_BA = 11, M_BB = 12, M_BC = 13, M_KMUP = 14, M_MRR = 15 /* rotated MRR3 trait: ridge, per-system lambda */,
   M_BL = 16, M_BCPI = 17, M_BDPI = 18,                 // the rest of mcmcCV's panel (R/cv.R:124-130)
   M_GSRR = 19, M_GSFLM = 20,                           // warm-start Gauss-Seidel solvers of mm() (Rcpp20260726ai.cpp:1564-1628)
-  M_EMMLD = 21                                         // emML with marker weights D: penalty Lmb / d_j (:495-496)
+  M_EMMLD = 21,                                        // emML with marker weights D: penalty Lmb / d_j (:495-496)
+  M_KMUP2 = 22                                         // the bagged Kuo-Mallick sweep of wgr(bag != 1) (:41-77): row subset, (H'e0 + b0) numerator
 };
 // Several solvers share one per-marker rule and differ only in the sweep epilogue: the sweep kernels are instantiated per
 // RULE, the epilogue and the host recipes see the full model.  emML :463 steps like emRR, emBCpi :1502 like emBC,
@@ -119,13 +120,13 @@ template <int MODEL>
 __device__ __forceinline__ float marker_lambda(float vbj, const SysScalars& s) {
   if constexpr (MODEL == M_EMBA || MODEL == M_EMBB || MODEL == M_BA || MODEL == M_BB || MODEL == M_BDPI) return s.ve * (1.0f / vbj);
   else if constexpr (MODEL == M_BL) return s.sweep == 0 ? s.ve * (1.0f / vbj) : sqrtf(s.Rho * s.ve / vbj);
-  else if constexpr (MODEL == M_EMDE || MODEL == M_KMUP) return vbj;
+  else if constexpr (MODEL == M_EMDE || MODEL == M_KMUP || MODEL == M_KMUP2) return vbj;
   else return s.lmb;
 }
 
 template <int MODEL>
 __device__ __forceinline__ RuleOut marker_rule(float g, float xx, float b0, float vbj, const SysScalars& s,
-                                               const MarkerDraws& dr) {
+                                               const MarkerDraws& dr, float xx2 = 0.0f) {
   RuleOut o;
   o.d = 1.0f; o.vbj = vbj;
   if constexpr (MODEL == M_EMRR || MODEL == M_MRR) {  // Rcpp20260726ai.cpp:335 ; MRR3 rotated system
@@ -211,6 +212,18 @@ __device__ __forceinline__ RuleOut marker_rule(float g, float xx, float b0, floa
       o.b = b1; o.d = 1.0f;
     }
     o.de = o.b - b0;
+  } else if constexpr (MODEL == M_KMUP2) {  // :60-74 ; g = H'e0 and xx = H'H over the rows in use, xx2 = the caller's xx(j) * bg, vbj = L[j]
+    const float den = xx2 + vbj, sd = sqrtf(s.ve / den);
+    const float b1 = (g + b0) / den + sd * dr.z1;  // sic: b0 enters without its xx (:60)
+    if (s.pi_mix > 0.0f) {
+      const float b2 = sd * dr.z2;
+      const float diff = (b2 - b1) * (-2.0f * g + xx * (b1 + b2 - 2.0f * b0));  // ||e2||^2-||e1||^2 of the rows in use
+      const float pj = 1.0f / (1.0f + (s.pi_mix / (1.0f - s.pi_mix)) * expf(s.C * diff));
+      if (dr.u < pj) { o.b = b1; o.d = 1.0f; } else { o.b = b2; o.d = 0.0f; }
+    } else {
+      o.b = b1; o.d = 1.0f;
+    }
+    o.de = o.b - b0;
   }
   return o;
 }
@@ -236,15 +249,15 @@ __device__ __forceinline__ LinCoef lin_coef(float xx, float b0, float vbj, const
   return o;
 }
 
-__host__ __device__ constexpr bool model_is_gibbs(int m) { return (m >= M_BRR && m <= M_KMUP) || (m >= M_BL && m <= M_BDPI); }
+__host__ __device__ constexpr bool model_is_gibbs(int m) { return (m >= M_BRR && m <= M_KMUP) || (m >= M_BL && m <= M_BDPI) || m == M_KMUP2; }
 __host__ __device__ constexpr bool model_has_vbj(int m) {
   return m == M_EMBA || m == M_EMBB || m == M_BA || m == M_BB || m == M_KMUP || m == M_EMDE || m == M_BL || m == M_BDPI || m == M_GSRR ||
-         m == M_GSFLM || m == M_EMMLD;
+         m == M_GSFLM || m == M_EMMLD || m == M_KMUP2;
 }
 // the rule itself rewrites the per-marker slot (KMUP's L and emDE's Lmb are inputs of the sweep: caller / epilogue own them)
-__host__ __device__ constexpr bool model_rule_writes_vbj(int m) { return model_has_vbj(m) && m != M_KMUP && m != M_EMDE && m != M_GSRR && m != M_GSFLM && m != M_EMMLD; }
+__host__ __device__ constexpr bool model_rule_writes_vbj(int m) { return model_has_vbj(m) && m != M_KMUP && m != M_KMUP2 && m != M_EMDE && m != M_GSRR && m != M_GSFLM && m != M_EMMLD; }
 __host__ __device__ constexpr bool model_has_d(int m) {
-  return m == M_EMBB || m == M_EMBC || m == M_BB || m == M_BC || m == M_KMUP || m == M_EMBCPI || m == M_LASSO || m == M_BCPI || m == M_BDPI;
+  return m == M_EMBB || m == M_EMBC || m == M_BB || m == M_BC || m == M_KMUP || m == M_EMBCPI || m == M_LASSO || m == M_BCPI || m == M_BDPI || m == M_KMUP2;
 }
 // solvers that stop on sum |b_old - b_new| < tol (emEN :449, emDE :297, emML :505, lasso :1492)
 __host__ __device__ constexpr bool model_has_cnv(int m) { return m == M_EMEN || m == M_EMDE || m == M_EMML || m == M_LASSO || m == M_GSRR || m == M_GSFLM || m == M_EMMLD; }

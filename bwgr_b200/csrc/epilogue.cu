@@ -302,10 +302,19 @@ __global__ void __launch_bounds__(1024) wgr_scalars_kernel(WgrArgs a) {
   __shared__ double sh[32];
   __shared__ float sh_max[32];
   const int tid = threadIdx.x, T = blockDim.x;
+  const int phase = a.phase;
   double se = 0, see = 0, sbb = 0;
   float emax = 0.0f;
-  for (int i = tid; i < a.n; i += T) { const double ev = a.e[i]; se += ev; see += ev * ev; emax = fmaxf(emax, fabsf(a.e[i])); }
-  for (int j = tid; j < a.p; j += T) { const double bj = a.b[j]; sbb += bj * bj; }
+  if (phase == 2) {  // bagged wgr: the residual is rebuilt from the fitted values every iteration (e = y - mu - X b, :124)
+    for (int i = tid; i < a.n; i += T) { const float ef = a.y[i] - a.hat[i]; a.e[i] = ef; se += (double)ef; emax = fmaxf(emax, fabsf(ef)); }
+  } else {
+    for (int i = tid; i < a.n; i += T) {
+      if (phase == 1 && !a.mask[i]) continue;  // KMUP2 returns the residuals of the rows in use only (:76): crossprod(e) is theirs
+      const double ev = a.e[i];
+      se += ev; see += ev * ev; emax = fmaxf(emax, fabsf(a.e[i]));
+    }
+    for (int j = tid; j < a.p; j += T) { const double bj = a.b[j]; sbb += bj * bj; }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
   if ((tid & 31) == 0) sh_max[tid >> 5] = emax;
@@ -318,32 +327,42 @@ __global__ void __launch_bounds__(1024) wgr_scalars_kernel(WgrArgs a) {
     const uint32_t sw = (uint32_t)s.sweep;
     const int i = s.sweep + 1;  // R's 1-based iteration
     const float n = (float)a.n, p = (float)a.p;
-    w.Ve_old = s.ve;
-    if (!a.iv) w.Va = ((float)sbb + a.Sb) / rchisq_philox(a.df + p, 0xFFFFFFFEu, sw, 0u, 2u, a.seed_lo, a.seed_hi);  // :113
-    w.Ve = ((float)see + a.Se) / rchisq_philox(n + a.df, 0xFFFFFFFEu, sw, 0u, 1u, a.seed_lo, a.seed_hi);               // :121
-    uint32_t c[4] = {0xFFFFFFFEu, sw, 0u, 0u};
-    philox4x32_10(c, a.seed_lo, a.seed_hi);
-    float z, z2;
-    box_muller(c[0], c[1], z, z2);
-    w.mu0 = (float)(se / (double)n) + (w.Ve / n) * z;  // sic: rnorm(1, mean(e), Ve/n), the sd argument is Ve/n (:125)
-    s.mu += w.mu0;
-    w.post = (i >= a.bi && i <= a.it && ((i - a.bi) % a.th) == 0) ? 1 : 0;
-    if (w.post) { w.B0 += (double)s.mu; w.VE += (double)w.Ve; if (!a.iv) w.VA += (double)w.Va; w.post_count += 1; }
-    s.ve = w.Ve;
-    s.C = -0.5f / sqrtf(s.ve);
-    s.sweep += 1;
-    s.its += 1;
-    {
-      int ex = 0;
-      const float bound = emax + fabsf(w.mu0);
-      if (bound > 0.0f && bound < 3.0e38f) frexpf(bound, &ex);
-      if (ex < -60) ex = -60;
-      s.e_q = ldexpf(1.0f, ex + 3 - 30);
-      s.e_qinv = ldexpf(1.0f, 30 - 3 - ex);
+    if (phase != 2) {
+      w.Ve_old = s.ve;
+      if (!a.iv) w.Va = ((float)sbb + a.Sb) / rchisq_philox(a.df + p, 0xFFFFFFFEu, sw, 0u, 2u, a.seed_lo, a.seed_hi);  // :113
+      const float nres = phase == 1 ? a.nsub : n;                                                                       // n * bag (:121)
+      w.Ve = ((float)see + a.Se) / rchisq_philox(nres + a.df, 0xFFFFFFFEu, sw, 0u, 1u, a.seed_lo, a.seed_hi);            // :121
     }
-    *a.sc = s;
+    if (phase != 1) {
+      uint32_t c[4] = {0xFFFFFFFEu, sw, 0u, 0u};
+      philox4x32_10(c, a.seed_lo, a.seed_hi);
+      float z, z2;
+      box_muller(c[0], c[1], z, z2);
+      w.mu0 = (float)(se / (double)n) + (w.Ve / n) * z;  // sic: rnorm(1, mean(e), Ve/n), the sd argument is Ve/n (:125)
+      s.mu += w.mu0;
+      w.post = (i >= a.bi && i <= a.it && ((i - a.bi) % a.th) == 0) ? 1 : 0;
+      if (w.post) { w.B0 += (double)s.mu; w.VE += (double)w.Ve; if (!a.iv) w.VA += (double)w.Va; w.post_count += 1; }
+      s.ve = w.Ve;
+      s.C = -0.5f / sqrtf(s.ve);
+      s.sweep += 1;
+      s.its += 1;
+      {
+        int ex = 0;
+        const float bound = emax + fabsf(w.mu0);
+        if (bound > 0.0f && bound < 3.0e38f) frexpf(bound, &ex);
+        if (ex < -60) ex = -60;
+        s.e_q = ldexpf(1.0f, ex + 3 - 30);
+        s.e_qinv = ldexpf(1.0f, 30 - 3 - ex);
+      }
+      *a.sc = s;
+    }
     *a.st = w;
   }
+}
+
+__global__ void __launch_bounds__(256) ll_to_float_kernel(const long long* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) dst[i] = (float)src[i];
 }
 
 __global__ void __launch_bounds__(256) wgr_markers_kernel(WgrArgs a) {
@@ -401,6 +420,18 @@ __global__ void __launch_bounds__(1024) epilogue_partial_kernel(EpilogueArgs a, 
 
 void launch_epilogue_partial(const EpilogueArgs& a, double* out, float* emax_out, cudaStream_t st) {
   epilogue_partial_kernel<<<a.nsys, 1024, 0, st>>>(a, out, emax_out);
+}
+
+// bagged wgr: phase 1 (variances) before the fitted values are rebuilt, phase 2 (intercept, posterior sums, per-marker part) after
+void launch_wgr_bag_phase(const WgrArgs& a, int phase, int num_sms, cudaStream_t st) {
+  WgrArgs b = a;
+  b.phase = phase;
+  wgr_scalars_kernel<<<1, 1024, 0, st>>>(b);
+  if (phase == 2) wgr_markers_kernel<<<num_sms, 256, 0, st>>>(b);
+}
+
+void launch_ll_to_float(const long long* src, float* dst, int n, cudaStream_t st) {
+  ll_to_float_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, n);
 }
 
 void launch_wgr_step(const WgrArgs& a, int num_sms, cudaStream_t st) {

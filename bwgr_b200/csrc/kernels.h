@@ -54,6 +54,7 @@ struct SmallNArgs {
   float* d;                // [nsys][p] or nullptr
   float* vbv;              // [nsys][p] per-marker variance (or KMUP lambda) or nullptr
   const float* xx;         // [nxx][p]  (nxx = 1 shared or nsys when masked)
+  const float* xx2;        // KMUP2: the caller's xx(j) * bg [p] (the rule's denominator; xx carries H'H of the rows in use)
   int xx_per_sys;
   const uint8_t* mask;     // [nsys][ld] or nullptr
   SysScalars* sc;          // [nsys]
@@ -203,8 +204,13 @@ struct WgrArgs {
   SysScalars* sc; WgrState* st;
   int iv, de; float Sb, Se, df, MSx; int it, bi, th;
   uint32_t seed_lo, seed_hi;
+  // wgr(bag != 1): phase 1 = variances from the rows in use (mask, nsub); phase 2 = e := y - hat (hat = mu + X b), intercept draw,
+  // posterior sums.  phase 0 = the unbagged step.
+  int phase; const uint8_t* mask; float nsub; const float* y; const float* hat;
 };
 void launch_wgr_step(const WgrArgs& a, int num_sms, cudaStream_t st);
+void launch_wgr_bag_phase(const WgrArgs& a, int phase, int num_sms, cudaStream_t st);
+void launch_ll_to_float(const long long* src, float* dst, int n, cudaStream_t st);
 
 // ---- multivariate ridge helpers (mrr.cu) ---------------------------------------------------------------------------
 // tilde[t][j] = x_j' Y[t]   (Y: [k][ld] float, out: [k][p])
@@ -217,6 +223,7 @@ void launch_pair_reduce(const float* A, const float* B, int64_t lda, int64_t ldb
                         cudaStream_t st);
 
 // ---- general multivariate ridge sweep (mrr_gen.cu): missing phenotypes, InnerGS, marker weights, NoInv, TH --------------
+constexpr int kMrrGenCopies = 8;  // accumulator copies per marker (power of two)
 struct MrrGenArgs {
   GenoView g;
   int k;
@@ -231,8 +238,8 @@ struct MrrGenArgs {
   const double* mean;     // [p] column means
   const double* sol;      // [p][nmat * k * k] from launch_mrr_gen_systems
   const double* se0;      // [k] column sums of e at launch
-  double* part;           // [2][grid][32] per-CTA partial dot products
-  unsigned int* bar;      // arrival counter, zeroed before launch
+  unsigned long long* acc;  // [p][kMrrGenCopies][32] the grid sums of marker position m: (fixed-point sum << 8) + arrivals; zeroed before launch
+  const double* scale;    // [64]: fixed-point scale of trait t (a power of two) | its inverse
   int* err;
 };
 size_t mrr_gen_smem(int k, int rows_per_cta, int innergs);

@@ -10,9 +10,10 @@
 //   * mrr_gen_sweep_kernel: one persistent cooperative grid; CTA c keeps its row slab of the k residual columns and of the
 //     observation mask in shared memory for the whole sweep (float64: this path is the reference's MRR3 arithmetic), streams
 //     its slab of the genotype columns in marker order through a cp.async ring together with the marker's matrix and
-//     vectors, and per marker: slab dot products -> one grid-wide sum through L2 (every CTA adds the partials in the same
-//     order, so all CTAs hold bit-identical effects and no broadcast is needed) -> mat-vec (or the inner Gauss-Seidel walk)
-//     -> masked rank-one update of the slab.  Column centring (:378-379) is analytic: x_c'e = x'e - mean_J * sum(e), with the
+//     vectors, and per marker: slab dot products -> one grid-wide sum through L2 (each warp adds its fixed-point partials to the
+//     marker's own 64-bit accumulator words with one atomic each; the low byte of a word counts the arrivals, so the data is its
+//     own flag: one L2 hop, no fence, no barrier; integer sums are order-free, so all CTAs read bit-identical totals and no
+//     broadcast is needed) -> mat-vec (or the inner Gauss-Seidel walk) -> masked rank-one update of the slab.  Column centring (:378-379) is analytic: x_c'e = x'e - mean_J * sum(e), with the
 //     running column sums of e carried in registers.
 // HBM traffic per sweep: n p bytes of genotypes + 8 k^2 p bytes of matrices; the bound is the grid sum's latency per marker.
 #include "kernels.h"
@@ -23,6 +24,7 @@ namespace {
 
 constexpr int kGT = 256;  // threads of a sweep CTA
 constexpr int kGD = 4;    // ring depth (markers in flight)
+constexpr int kGC = kMrrGenCopies;  // copies of a marker's accumulator words: CTA c adds to copy c % kGC (same-address atomics serialise in L2)
 
 __device__ __forceinline__ void cpa16(void* smem, const void* gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -35,9 +37,9 @@ __device__ __forceinline__ void cpa8(void* smem, const void* gmem) {
 __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -48,19 +50,21 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 // Per marker, one pass over the column: masked integer sums sxz[j][t] = sum_i x z_t, sxxz[j][t] = sum_i x^2 z_t (exact), and
-// xty[j][t] = sum_i x y_t (float64).  One CTA per marker.
+// xty[j][t] = sum_i x y_t (float64).  One warp per marker, eight markers per CTA: the eight warps walk the rows together, so the
+// k phenotype columns and the mask words they all read come from L1 (one CTA per marker re-read them from L2 for every marker:
+// 8 k n bytes each, 400 GB at 50k x 50k x 20).
 __global__ void __launch_bounds__(256) mrr_gen_colstats_kernel(GenoView g, const uint32_t* __restrict__ zbits,
                                                                const double* __restrict__ y, int k, double* __restrict__ sxz,
                                                                double* __restrict__ sxxz, double* __restrict__ xty) {
-  __shared__ long long r1[8][32], r2[8][32];
-  __shared__ double r3[8][32];
-  const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 8 + warp;
+  if (j >= g.p) return;
   const int8_t* col = g.x8 + (int64_t)j * g.ld;
   int s1[32], s2[32];
   double s3[32];
 #pragma unroll
   for (int t = 0; t < 32; t++) { s1[t] = 0; s2[t] = 0; s3[t] = 0.0; }
-  for (int i = tid; i < g.n; i += 256) {
+  for (int i = lane; i < g.n; i += 32) {
     const int x = col[i];
     const uint32_t zb = zbits[i];
     const double xd = (double)x;
@@ -81,17 +85,12 @@ __global__ void __launch_bounds__(256) mrr_gen_colstats_kernel(GenoView g, const
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
       const double d = warp_sum(s3[t]);
-      if (lane == 0) { r1[warp][t] = a; r2[warp][t] = c; r3[warp][t] = d; }
+      if (lane == 0) {
+        sxz[(size_t)j * k + t] = (double)a;
+        sxxz[(size_t)j * k + t] = (double)c;
+        xty[(size_t)j * k + t] = d;
+      }
     }
-  }
-  __syncthreads();
-  if (tid < k) {
-    long long a = 0, c = 0;
-    double d = 0;
-    for (int w = 0; w < 8; w++) { a += r1[w][tid]; c += r2[w][tid]; d += r3[w][tid]; }
-    sxz[(size_t)j * k + tid] = (double)a;
-    sxxz[(size_t)j * k + tid] = (double)c;
-    xty[(size_t)j * k + tid] = d;
   }
 }
 
@@ -164,7 +163,6 @@ __global__ void __launch_bounds__(32) mrr_gen_systems_kernel(int p, int k, int f
 struct GenSmem {
   double* E;        // [k][rp]
   uint32_t* zb;     // [rp]
-  double* red;      // [8][32]
   double* dl;       // [32]
   int* Js;          // [kGD]
   int* irgs;        // [32]
@@ -173,11 +171,10 @@ struct GenSmem {
   int8_t* xs[kGD];
 };
 
-__device__ __forceinline__ GenSmem carve(unsigned char* base, int k, int rp, int nmat) {
+__device__ __forceinline__ GenSmem carve(unsigned char* base, int ke, int rp, int nmat, int k) {
   GenSmem s;
   size_t o = 0;
-  s.E = reinterpret_cast<double*>(base + o); o += sizeof(double) * (size_t)k * rp;
-  s.red = reinterpret_cast<double*>(base + o); o += sizeof(double) * 8 * 32;
+  s.E = reinterpret_cast<double*>(base + o); o += sizeof(double) * (size_t)ke * rp;
   s.dl = reinterpret_cast<double*>(base + o); o += sizeof(double) * 32;
   for (int d = 0; d < kGD; d++) { s.mats[d] = reinterpret_cast<double*>(base + o); o += sizeof(double) * (size_t)nmat * k * k; }
   for (int d = 0; d < kGD; d++) { s.vec[d] = reinterpret_cast<double*>(base + o); o += sizeof(double) * (3 * k + 1); }
@@ -189,28 +186,58 @@ __device__ __forceinline__ GenSmem carve(unsigned char* base, int k, int rp, int
   return s;
 }
 
+// int8 genotype byte -> double on the integer and FP64 pipes (no I2F): u = x + 128 in the low mantissa bits of 2^52, minus 2^52 + 128
+__device__ __forceinline__ double byte_to_double(int8_t x) {
+  return __hiloint2double(0x43300000, (int)((uint32_t)(uint8_t)x ^ 0x80u)) - 4503599627370624.0;
+}
+
+// NJ > 0: a thread keeps its share of the residual slab in registers for the whole sweep -- the traits of its warp (w, w + 8, w + 16,
+// w + 24) x the rows lane + 32 j, j < NJ (rows_per_cta <= 32 NJ) -- together with the observation bits of those rows: the dot products
+// and the rank-one update of a marker touch no memory but the marker's genotype bytes.  NJ = 0: the slab lives in shared memory
+// (row slabs above 512 rows).
+template <int NJ>
 __global__ void __launch_bounds__(kGT, 1) mrr_gen_sweep_kernel(MrrGenArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_abort;
+  constexpr int NJR = NJ > 0 ? NJ : 1;
   const int k = a.k, rp = a.rows_per_cta, nmat = a.innergs ? 2 : 1, kk = k * k;
-  const GenSmem s = carve(smem_raw, k, rp, nmat);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = gridDim.x, cta = blockIdx.x;
+  const GenSmem s = carve(smem_raw, NJ > 0 ? 0 : k, rp, nmat, k);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = (int)gridDim.x, cta = blockIdx.x;
   const int64_t r0 = (int64_t)cta * rp;
   const int p = a.g.p;
   // slab of the residuals and of the observation mask
-  for (int q = tid; q < k * rp; q += kGT) {
-    const int t = q / rp, i = q - t * rp;
-    s.E[q] = (r0 + i < a.g.ld) ? a.e[(size_t)t * a.g.ld + r0 + i] : 0.0;
+  double er[4][NJR];
+  uint32_t zr[NJR];
+  if constexpr (NJ > 0) {
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      const int i = lane + 32 * j;
+      const bool in = i < rp && r0 + i < a.g.ld;
+      zr[j] = in ? a.zbits[r0 + i] : 0u;
+#pragma unroll
+      for (int q = 0; q < 4; q++) er[q][j] = (in && warp + 8 * q < k) ? a.e[(size_t)(warp + 8 * q) * a.g.ld + r0 + i] : 0.0;
+    }
+  } else {
+    for (int q = tid; q < k * rp; q += kGT) {
+      const int t = q / rp, i = q - t * rp;
+      s.E[q] = (r0 + i < a.g.ld) ? a.e[(size_t)t * a.g.ld + r0 + i] : 0.0;
+    }
+    for (int i = tid; i < rp; i += kGT) s.zb[i] = (r0 + i < a.g.ld) ? a.zbits[r0 + i] : 0u;
   }
-  for (int i = tid; i < rp; i += kGT) s.zb[i] = (r0 + i < a.g.ld) ? a.zbits[r0 + i] : 0u;
   if (tid < 32) s.irgs[tid] = (a.irgs && tid < k) ? a.irgs[tid] : tid;
   if (tid == 0) s_abort = 0;
   for (int q = tid; q < kGD * rp; q += kGT) s.xs[0][q] = 0;  // the four slots are contiguous
   double se = (warp == 0 && lane < k) ? a.se0[lane] : 0.0;  // running column sum of e_t over ALL rows (identical in every CTA)
+  double sc4[4];  // fixed-point scale of this warp's traits; inverse scale of lane t's trait
+#pragma unroll
+  for (int q = 0; q < 4; q++) sc4[q] = (warp + 8 * q < k) ? a.scale[warp + 8 * q] : 0.0;
+  const double inv_scale = lane < k ? a.scale[32 + lane] : 0.0;
   const int nch = rp / 16;
+  int Jnext = 0;  // marker of the NEXT prefetch, read one step early so that its L2 round trip is not in front of the address arithmetic
   auto prefetch = [&](int m) {
     if (m < p) {
-      const int J = a.perm[m], slot = m % kGD;
+      const int J = Jnext, slot = m % kGD;
+      if (m + 1 < p) Jnext = a.perm[m + 1];
       const int8_t* col = a.g.x8 + (int64_t)J * a.g.ld + r0;
       for (int c = tid; c < nch; c += kGT)
         if (r0 + 16 * c < a.g.ld) cpa16(s.xs[slot] + 16 * c, col + 16 * c);  // rows past the padded column stay as they are: e = z = 0 there
@@ -223,6 +250,7 @@ __global__ void __launch_bounds__(kGT, 1) mrr_gen_sweep_kernel(MrrGenArgs a) {
     }
     cpa_commit();
   };
+  Jnext = a.perm[0];
   for (int m = 0; m < kGD - 1; m++) prefetch(m);
   const unsigned long long t_start = globaltimer_ns();
   for (int m = 0; m < p; m++) {
@@ -234,57 +262,69 @@ __global__ void __launch_bounds__(kGT, 1) mrr_gen_sweep_kernel(MrrGenArgs a) {
     const double* vec = s.vec[slot];
     const double* mats = s.mats[slot];
     // ---- slab dot products x'e_t: warp w takes traits w, w + 8, w + 16, w + 24
+    double xr[NJR];
     {
       double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int i = lane; i < rp; i += 32) {
-        const double x = (double)xs[i];
+      if constexpr (NJ > 0) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int t = warp + 8 * q;
-          if (t < k) acc[q] = fma(x, s.E[t * rp + i], acc[q]);
+        for (int j = 0; j < NJ; j++) {
+          const int i = lane + 32 * j;
+          xr[j] = i < rp ? byte_to_double(xs[i]) : 0.0;
+#pragma unroll
+          for (int q = 0; q < 4; q++) acc[q] = fma(xr[j], er[q][j], acc[q]);
+        }
+      } else {
+        for (int i = lane; i < rp; i += 32) {
+          const double x = byte_to_double(xs[i]);
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int t = warp + 8 * q;
+            if (t < k) acc[q] = fma(x, s.E[t * rp + i], acc[q]);
+          }
         }
       }
-      double* out = a.part + ((size_t)(m & 1) * G + cta) * 32;
+      unsigned long long* accw = a.acc + ((size_t)m * kGC + (cta & (kGC - 1))) * 32;
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         const int t = warp + 8 * q;
         if (t < k) {
-          const double v = warp_sum(acc[q]);
-          if (lane == 0) __stcg(out + t, v);
+          const double v = warp_sum(acc[q]) * sc4[q];
+          if (lane == 0) {
+            if (!(fabs(v) < 4503599627370496.0)) atomicExch(a.err, 4);  // 2^52: the fixed-point range of this sweep is exceeded
+            atomicAdd(accw + t, ((unsigned long long)__double2ll_rn(v) << 8) + 1ull);
+          }
         }
       }
     }
-    __syncthreads();
-    if (tid == 0) {  // grid-wide arrival; the counter only grows within a launch
-      __threadfence();
-      atomicAdd(a.bar, 1u);
-      const unsigned int target = (unsigned int)(m + 1) * (unsigned int)G;
-      unsigned int spins = 0;
-      while (ld_acquire_u32(a.bar) < target) {
-        if ((++spins & 0x3fffu) == 0) {
-          if (*reinterpret_cast<volatile int*>(a.err) != 0) { s_abort = 1; break; }
-          if (globaltimer_ns() - t_start > 120000000000ull) { atomicExch(a.err, 3); s_abort = 1; break; }  // two minutes without the grid
-        }
-      }
-    }
-    __syncthreads();
-    if (s_abort) return;  // the host reports the error flag; the residuals of this launch are not written back
-    // ---- the grid sum, in CTA order, by every CTA alike
-    {
-      const int t = lane, grp = warp;
-      if (t < k) {
-        const double* src = a.part + (size_t)(m & 1) * G * 32 + t;
-        double sum = 0.0;
-        for (int c = grp; c < G; c += 8) sum += __ldcg(src + (size_t)c * 32);
-        s.red[grp * 32 + t] = sum;
-      }
-    }
-    __syncthreads();
     if (warp == 0) {
       const bool on = lane < k;
       double dot = 0.0;
-      if (on)
-        for (int grp = 0; grp < 8; grp++) dot += s.red[grp * 32 + lane];
+      {  // the marker's totals: word t is complete when its low byte counts all G CTAs
+        const unsigned long long* accw = a.acc + (size_t)m * kGC * 32 + (on ? lane : 0);
+        unsigned long long w[kGC];
+        unsigned int spins = 0;
+        for (;;) {
+          bool pending = false;
+#pragma unroll
+          for (int c = 0; c < kGC; c++) w[c] = ld_relaxed_u64(accw + c * 32);
+#pragma unroll
+          for (int c = 0; c < kGC; c++) pending |= (int)(w[c] & 0xffull) != (G + kGC - 1 - c) / kGC;  // CTAs with cta % kGC == c
+          if (!__any_sync(0xffffffffu, on && pending)) break;
+          if ((++spins & 0xfffu) == 0) {
+            int ab = 0;
+            if (lane == 0) {
+              if (*reinterpret_cast<volatile int*>(a.err) != 0) ab = 1;
+              else if (globaltimer_ns() - t_start > 120000000000ull) { atomicExch(a.err, 3); ab = 1; }  // two minutes without the grid
+              if (ab) s_abort = 1;
+            }
+            if (__shfl_sync(0xffffffffu, ab, 0)) break;
+          }
+        }
+        long long tot = 0;
+#pragma unroll
+        for (int c = 0; c < kGC; c++) tot += (long long)w[c] >> 8;
+        dot = (double)tot * inv_scale;
+      }
       const double XXt = on ? vec[lane] : 0.0, sxzc = on ? vec[k + lane] : 0.0, b0 = on ? vec[2 * k + lane] : 0.0;
       const double mean = vec[3 * k];
       const double r = on ? dot - mean * se + XXt * b0 : 0.0;  // x_c'e_t + XX(J,t) b0_t  (:506)
@@ -317,28 +357,53 @@ __global__ void __launch_bounds__(kGT, 1) mrr_gen_sweep_kernel(MrrGenArgs a) {
       }
     }
     __syncthreads();
+    if (s_abort) return;  // the host reports the error flag; the residuals of this launch are not written back
     // ---- e_t -= (x - mean) (b1_t - b0_t) on the observed rows (:518)
     {
       const double mean = vec[3 * k];
       double dl[4];
 #pragma unroll
       for (int q = 0; q < 4; q++) dl[q] = (warp + 8 * q < k) ? s.dl[warp + 8 * q] : 0.0;
-      for (int i = lane; i < rp; i += 32) {
-        const double x = (double)xs[i] - mean;
-        const uint32_t zb = s.zb[i];
+      if constexpr (NJ > 0) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int t = warp + 8 * q;
-          if (t < k && ((zb >> t) & 1u)) s.E[t * rp + i] = fma(-x, dl[q], s.E[t * rp + i]);
+        for (int j = 0; j < NJ; j++) {
+          const double x = xr[j] - mean;
+#pragma unroll
+          for (int q = 0; q < 4; q++) er[q][j] = fma(-x, ((zr[j] >> (warp + 8 * q)) & 1u) ? dl[q] : 0.0, er[q][j]);
+        }
+      } else {
+        for (int i = lane; i < rp; i += 32) {
+          const double x = byte_to_double(xs[i]) - mean;
+          const uint32_t zb = s.zb[i];
+          double ev[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) ev[q] = (warp + 8 * q < k) ? s.E[(warp + 8 * q) * rp + i] : 0.0;
+#pragma unroll
+          for (int q = 0; q < 4; q++) ev[q] = fma(-x, ((zb >> (warp + 8 * q)) & 1u) ? dl[q] : 0.0, ev[q]);
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            if (warp + 8 * q < k) s.E[(warp + 8 * q) * rp + i] = ev[q];
         }
       }
     }
   }
   cpa_wait<0>();
   __syncthreads();
-  for (int q = tid; q < k * rp; q += kGT) {
-    const int t = q / rp, i = q - t * rp;
-    if (r0 + i < a.g.ld) a.e[(size_t)t * a.g.ld + r0 + i] = s.E[q];
+  if constexpr (NJ > 0) {
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      const int i = lane + 32 * j;
+      if (i < rp && r0 + i < a.g.ld) {
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (warp + 8 * q < k) a.e[(size_t)(warp + 8 * q) * a.g.ld + r0 + i] = er[q][j];
+      }
+    }
+  } else {
+    for (int q = tid; q < k * rp; q += kGT) {
+      const int t = q / rp, i = q - t * rp;
+      if (r0 + i < a.g.ld) a.e[(size_t)t * a.g.ld + r0 + i] = s.E[q];
+    }
   }
 }
 
@@ -408,7 +473,7 @@ __global__ void __launch_bounds__(256) mrr_gen_shift_kernel(double* __restrict__
 
 size_t mrr_gen_smem(int k, int rows_per_cta, int innergs) {
   const int nmat = innergs ? 2 : 1;
-  size_t o = sizeof(double) * (size_t)k * rows_per_cta + sizeof(double) * (8 * 32 + 32);
+  size_t o = (rows_per_cta <= 512 ? 0 : sizeof(double) * (size_t)k * rows_per_cta) + sizeof(double) * 32;
   o += (size_t)kGD * sizeof(double) * ((size_t)nmat * k * k + 3 * k + 1);
   o = (o + 15) & ~(size_t)15;
   o += (size_t)kGD * rows_per_cta + sizeof(uint32_t) * (size_t)rows_per_cta + sizeof(int) * (kGD + 32);
@@ -417,7 +482,7 @@ size_t mrr_gen_smem(int k, int rows_per_cta, int innergs) {
 
 void launch_mrr_gen_colstats(const GenoView& g, const uint32_t* zbits, const double* y, int k, double* sxz, double* sxxz,
                              double* xty, cudaStream_t st) {
-  mrr_gen_colstats_kernel<<<g.p, 256, 0, st>>>(g, zbits, y, k, sxz, sxxz, xty);
+  mrr_gen_colstats_kernel<<<(g.p + 7) / 8, 256, 0, st>>>(g, zbits, y, k, sxz, sxxz, xty);
 }
 
 void launch_mrr_gen_systems(int p, int k, const double* fixed, const double* W, const double* iG, const double* vb,
@@ -427,11 +492,18 @@ void launch_mrr_gen_systems(int p, int k, const double* fixed, const double* W, 
 
 cudaError_t launch_mrr_gen_sweep(const MrrGenArgs& a, int grid, cudaStream_t st) {
   const size_t smem = mrr_gen_smem(a.k, a.rows_per_cta, a.innergs);
-  cudaError_t e = cudaFuncSetAttribute(mrr_gen_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int nj = (a.rows_per_cta + 31) / 32;
+  const void* fn = nj <= 2    ? reinterpret_cast<const void*>(mrr_gen_sweep_kernel<2>)
+                   : nj <= 4  ? reinterpret_cast<const void*>(mrr_gen_sweep_kernel<4>)
+                   : nj <= 8  ? reinterpret_cast<const void*>(mrr_gen_sweep_kernel<8>)
+                   : nj <= 12 ? reinterpret_cast<const void*>(mrr_gen_sweep_kernel<12>)
+                   : nj <= 16 ? reinterpret_cast<const void*>(mrr_gen_sweep_kernel<16>)
+                              : reinterpret_cast<const void*>(mrr_gen_sweep_kernel<0>);
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   MrrGenArgs args = a;
   void* params[] = {&args};
-  return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(mrr_gen_sweep_kernel), dim3(grid), dim3(kGT), params, smem, st);
+  return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kGT), params, smem, st);
 }
 
 void launch_mrr_gen_colred(const double* A, const double* B, int64_t ld, int n, int k, double* out, cudaStream_t st) {

@@ -114,12 +114,14 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
   int jA = marker_ahead(0, 0), jB = p > 1 ? marker_ahead(0, 1) : 0;
   float bA = b[jA], xA = xx[jA], vA = vbv ? vbv[jA] : 0.0f;
   float bB = b[jB], xB = xx[jB], vB = vbv ? vbv[jB] : 0.0f;
+  float hA = 0.0f, hB = 0.0f;  // KMUP2: the second per-marker scale
+  if constexpr (MODEL == M_KMUP2) { hA = a.xx2[jA]; hB = a.xx2[jB]; }
 
 #pragma unroll 1
   for (int pos = 0; pos < p; pos++) {
     const int j = jA;
-    const float b0 = bA, xxj = xA, vbj = vA;
-    jA = jB; bA = bB; xA = xB; vA = vB;
+    const float b0 = bA, xxj = xA, vbj = vA, xx2j = hA;
+    jA = jB; bA = bB; xA = xB; vA = vB; hA = hB;
     if (order && pos > 0 && pm == 0) {  // chunk pos / T + 1 of the order replaces chunk pos / T - 1 (nobody reads that any more)
       const int q = pos + T + tid;
       if (q < p) ord_s[(pb ^ 1) * T + tid] = order[q];
@@ -127,6 +129,7 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
     if (pos + 2 < p) {
       jB = marker_ahead(pos, 2);
       bB = b[jB]; xB = xx[jB]; vB = vbv ? vbv[jB] : 0.0f;
+      if constexpr (MODEL == M_KMUP2) hB = a.xx2[jB];
     }
     if (model_is_gibbs(MODEL) && pm == 0) {  // draws of the next T markers, one per thread
       const int q = pos + tid;
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
     MarkerDraws dr;
     if (model_is_gibbs(MODEL)) dr = draws[pb * T + pm];
     else { dr.z1 = dr.z2 = dr.u = 0.0f; dr.chi = 1.0f; }
-    const RuleOut r = marker_rule<MODEL>(g, xxj, b0, vbj, sc, dr);
+    const RuleOut r = marker_rule<MODEL>(g, xxj, b0, vbj, sc, dr, xx2j);
     if (tid == 0) {
       b[j] = r.b;
       if (model_has_d(MODEL) && dvec) dvec[j] = r.d;
@@ -295,6 +298,7 @@ void launch_small_n(const SmallNArgs& a, size_t smem_limit, cudaStream_t st) {
     case M_BB: launch_small_model<M_BB>(a, smem_limit, st); break;
     case M_BC: launch_small_model<M_BC>(a, smem_limit, st); break;
     case M_KMUP: launch_small_model<M_KMUP>(a, smem_limit, st); break;
+    case M_KMUP2: launch_small_model<M_KMUP2>(a, smem_limit, st); break;
     case M_MRR: launch_small_model<M_MRR>(a, smem_limit, st); break;
     default: break;
   }

@@ -168,6 +168,12 @@ BWGR_API int bwgr_gibbs_fit(bwgr_handle* h, const bwgr_gibbs_params* par, const 
 BWGR_API int bwgr_kmup_sweep(bwgr_handle* h, double* b, double* d, const double* xx, double* e, const double* L, double Ve,
                     double pi, uint64_t seed);
 
+/* KMUP2(X,Use,b,d,xx,E,L,Ve,pi) (:41-77), the bagged sweep of wgr(bag != 1): only the rows Use (0-based, as R passes them) enter.
+ * b, d updated in place; e_out [nuse] = the residuals of the rows in use, in the order of Use (the reference's third list element).
+ * Rows must be distinct (rp = FALSE); repeated rows -> BWGR_ERR_UNSUPPORTED.  Needs the residual of n rows to fit one SM. */
+BWGR_API int bwgr_kmup2_sweep(bwgr_handle* h, const double* use, int64_t nuse, double* b, double* d, const double* xx, const double* E,
+                     double* e_out, const double* L, double Ve, double pi, uint64_t seed);
+
 /* GSRR / GSFLM(y, e, gen, b, Lmb, xx, cxx, maxit = 50) (:1564-1628): the warm-start Gauss-Seidel solvers mm() calls inside its
  * back-fitting loop (R/mix.R:890-892).  which = 0 GSRR, 1 GSFLM.  In / out: e [n], b [p], Lmb [p] (the state the caller carries from
  * one outer iteration to the next); out: vb [p]; scal = {mu, h2, vna (the residual variance e.e0/n), sweeps done}. */
@@ -178,6 +184,11 @@ BWGR_API int bwgr_gs_fit(bwgr_handle* h, int which, const double* y, double* e, 
  * scal = {mu, Ve, Va, cxx}; Vb is [p] when iv/de, else scal[2]. */
 BWGR_API int bwgr_wgr_fit(bwgr_handle* h, const double* y, int it, int bi, int th, int iv, int de, double pi, double df,
                  double R2, uint64_t seed, double* b, double* d, double* Vb, double* hat, double* scal);
+
+/* wgr(..., bag, rp) for bag != 1 (R/wgr.R:21, :49, :68, :87, :121): a fresh sorted sample of floor(n * bag) rows per iteration (drawn
+ * with std::mt19937_64(seed), not R's sample()), swept by KMUP2; rp = TRUE -> BWGR_ERR_UNSUPPORTED.  bag = 1 forwards to bwgr_wgr_fit. */
+BWGR_API int bwgr_wgr_fit_bag(bwgr_handle* h, const double* y, int it, int bi, int th, double bag, int rp, int iv, int de, double pi,
+                     double df, double R2, uint64_t seed, double* b, double* d, double* Vb, double* hat, double* scal);
 
 /* ---- multivariate ridge -------------------------------------------------------------------- */
 /* MRR3 / MRR3F (src/RcppEigen20230423.cpp:318-701, :704-1079). par[30] = the arguments after

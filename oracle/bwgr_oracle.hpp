@@ -848,7 +848,8 @@ static inline void imp_columns(float* X, int n, int p) {
   }
 }
 
-// wgr(): R/wgr.R:2-169 with eigK=NULL, bag=1, no NA.  The driver arithmetic is R's (double);
+// wgr(): R/wgr.R:2-169 with eigK=NULL, no NA; bag != 1 resamples the rows of every iteration without replacement (rp = FALSE,
+// :68: Use = sort(sample(n, n*bag)) - 1) and sweeps them with KMUP2.  The driver arithmetic is R's (double);
 // every KMUP call crosses the Rcpp boundary, i.e. casts X,b,d,xx,e,L to float and back
 // (RcppExports.cpp:16-31).
 struct WgrOut {
@@ -856,9 +857,14 @@ struct WgrOut {
   std::vector<double> b, d, Vb, hat;
 };
 static inline void wgr(const double* y, const double* Xd, int n, int p, int it, int bi, int th, bool iv, bool de,
-                       double pi, double df, double R2, uint64_t seed, bool ratio_form, WgrOut& o) {
+                       double pi, double df, double R2, uint64_t seed, bool ratio_form, WgrOut& o, double bag = 1.0) {
   Rng rng(seed);
   if (de) iv = true;
+  const bool bagged = bag != 1.0;
+  if (bagged) df = df / (bag * bag);  // :21
+  const int nuse = bagged ? (int)(n * bag) : n;
+  std::vector<int> rows(n);
+  std::vector<float> usef(nuse), esub(nuse);
   std::vector<float> Xf((size_t)n * p);
   for (size_t i = 0; i < Xf.size(); i++) Xf[i] = (float)Xd[i];
   std::vector<int> post;
@@ -870,7 +876,7 @@ static inline void wgr(const double* y, const double* Xd, int n, int p, int it, 
     const double* x = Xd + (size_t)j * n;
     double s = 0, ss = 0;
     for (int i = 0; i < n; i++) { s += x[i]; ss += x[i] * x[i]; }
-    xx[j] = ss;
+    xx[j] = ss * bag;  // :49
     const double m = s / n;
     double v = 0;
     for (int i = 0; i < n; i++) v += (x[i] - m) * (x[i] - m);
@@ -892,7 +898,16 @@ static inline void wgr(const double* y, const double* Xd, int n, int p, int it, 
   for (int i = 1; i <= it; i++) {
     for (int j = 0; j < p; j++) { bf[j] = (float)b[j]; dfl[j] = (float)d[j]; xxf[j] = (float)xx[j]; Lf[j] = (float)L[j]; }
     for (int r = 0; r < n; r++) ef[r] = (float)e[r];
-    kmup(Xf.data(), n, p, bf.data(), dfl.data(), xxf.data(), ef.data(), Lf.data(), (float)Ve, (float)pi, rng, ratio_form);
+    if (bagged) {  // :68, :87: a fresh sorted row sample, swept by KMUP2; e becomes the residual of the rows in use
+      for (int r = 0; r < n; r++) rows[r] = r;
+      for (int r = 0; r < nuse; r++) { std::uniform_int_distribution<int> pick(r, n - 1); std::swap(rows[r], rows[pick(rng.g)]); }
+      std::sort(rows.begin(), rows.begin() + nuse);
+      for (int r = 0; r < nuse; r++) usef[r] = (float)rows[r];
+      kmup2(Xf.data(), n, p, usef.data(), nuse, bf.data(), dfl.data(), xxf.data(), ef.data(), esub.data(), Lf.data(), (float)Ve, (float)pi, rng,
+            ratio_form);
+    } else {
+      kmup(Xf.data(), n, p, bf.data(), dfl.data(), xxf.data(), ef.data(), Lf.data(), (float)Ve, (float)pi, rng, ratio_form);
+    }
     if (pi > 0) for (int j = 0; j < p; j++) d[j] = dfl[j];
     for (int j = 0; j < p; j++) b[j] = bf[j];
     for (int r = 0; r < n; r++) e[r] = ef[r];
@@ -906,8 +921,9 @@ static inline void wgr(const double* y, const double* Xd, int n, int p, int it, 
       for (int j = 0; j < p; j++) Vb[j] = Va;
     }
     double ee = 0;
-    for (int r = 0; r < n; r++) ee += e[r] * e[r];
-    Ve = (ee + Se) / rng.rchisq(n + df);
+    if (bagged) for (int r = 0; r < nuse; r++) ee += (double)esub[r] * (double)esub[r];
+    else for (int r = 0; r < n; r++) ee += e[r] * e[r];
+    Ve = (ee + Se) / rng.rchisq(n * bag + df);  // :121
     for (int j = 0; j < p; j++) L[j] = Ve / Vb[j];
     for (int r = 0; r < n; r++) e[r] = y[r] - mu;  // e = y-mu-X%*%b
     for (int j = 0; j < p; j++) {
