@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import EmOut, EmParams, GibbsOut, GibbsParams, check
 
 STORE_I8, STORE_2BIT = 0, 1
-PATH_AUTO, PATH_SMALL_N, PATH_BLOCKED = 0, 1, 2
+PATH_AUTO, PATH_SMALL_N, PATH_BLOCKED, PATH_GRID = 0, 1, 2, 3
 _EM = {"emRR": 0, "emBA": 1, "emBB": 2, "emBC": 3, "emBL": 4, "emEN": 5, "emDE": 6, "emML": 7, "emBCpi": 8, "lasso": 9}
 _GIBBS = {"BayesRR": 0, "BayesA": 1, "BayesB": 2, "BayesC": 3, "BayesL": 4, "BayesCpi": 5, "BayesDpi": 6}
 NSCAL = 6  # BWGR_NSCAL of include/bwgr_b200.h

@@ -153,6 +153,8 @@ struct Fit {
   int sweeps_issued = 0;
   bool shuffled = true; // EM: shuffled order; Gibbs: natural
   bool blocked = false;
+  bool gridfam = false;                 // grid family (grid_sweep.cu)
+  DevBuf<unsigned long long> gridacc;   // its per-marker accumulator words
   bool masked = false;
   int rows_per_cta = 0, grid = 0, nblocks = 0;
   bool gram_cached = false;
@@ -551,7 +553,7 @@ int bwgr_set_tuning(bwgr_handle* h, int block, int path, int grid) {
   if (!h) return fail(BWGR_ERR_ARG, "null handle");
   if (block >= 0 && block != kBlk) return fail(BWGR_ERR_UNSUPPORTED, "only block=%d is built", kBlk);
   if (path >= 0) {
-    if (path > BWGR_PATH_BLOCKED) return fail(BWGR_ERR_ARG, "bad path %d", path);
+    if (path > BWGR_PATH_GRID) return fail(BWGR_ERR_ARG, "bad path %d", path);
     h->path = path;
   }
   if (grid >= 0) h->grid = grid;
@@ -893,7 +895,16 @@ bool plan_pipe(const bwgr_handle* h, int model, int ns, PipePlan* pl) {
   return false;
 }
 
-int choose_path(bwgr_handle* h, const FitSpec& s, bool* blocked) {
+// rows per CTA and CTAs of the grid family for this store
+void grid_geometry(bwgr_handle* h, int* rp, int* grid) {
+  int r = (int)((h->ld + h->num_sms - 1) / h->num_sms);
+  r = std::max(64, (r + 15) / 16 * 16);
+  *rp = r;
+  *grid = (int)((h->ld + r - 1) / r);
+}
+
+// family: 0 = small-n, 1 = blocked, 2 = grid
+int choose_path(bwgr_handle* h, const FitSpec& s, int* family) {
   const GenoView g = h->view();
   const bool small_ok = small_n_fits(g, s.row_mask != nullptr, h->smem_optin);
   const int grid = h->grid > 0 ? std::min(h->grid, h->num_sms) : h->num_sms;
@@ -901,17 +912,25 @@ int choose_path(bwgr_handle* h, const FitSpec& s, bool* blocked) {
   PipePlan pl;
   const bool blocked_ok = h->storage == BWGR_STORE_I8 && !s.row_mask && s.nsys <= 32 &&
                           (plan_pipe(h, s.model, s.nsys, &pl) || (rows <= 512 && sweep_blocked_smem((int)rows, s.nsys) <= h->smem_optin));
+  int grp = 0, ggrid = 0;
+  grid_geometry(h, &grp, &ggrid);
+  const bool grid_ok = h->storage == BWGR_STORE_I8 && h->world <= 1 && s.nsys <= 32 && s.model != M_MRR && ggrid <= 255 &&
+                       grid_sweep_smem(s.nsys, grp, s.row_mask != nullptr) <= h->smem_optin;
   if (h->path == BWGR_PATH_SMALL_N) {
     if (!small_ok) return fail(BWGR_ERR_UNSUPPORTED, "small-n path: residual of n=%lld does not fit one SM", (long long)h->n);
-    *blocked = false;
+    *family = 0;
   } else if (h->path == BWGR_PATH_BLOCKED) {
     if (!blocked_ok) return fail(BWGR_ERR_UNSUPPORTED, "blocked path needs the int8 store, no row mask, nsys<=32 and n <= 512 rows x grid");
-    *blocked = true;
+    *family = 1;
+  } else if (h->path == BWGR_PATH_GRID) {
+    if (!grid_ok) return fail(BWGR_ERR_UNSUPPORTED, "grid path needs the int8 store, one GPU, nsys<=32 and the row slabs of all systems in shared memory");
+    *family = 2;
   } else {
     const bool prefer_small = small_ok && (s.row_mask || s.nsys >= 8 || h->n <= 1024);
-    if (prefer_small) *blocked = false;
-    else if (blocked_ok) *blocked = true;
-    else if (small_ok) *blocked = false;
+    if (prefer_small) *family = 0;
+    else if (blocked_ok) *family = 1;
+    else if (small_ok) *family = 0;
+    else if (grid_ok) *family = 2;
     else return fail(BWGR_ERR_UNSUPPORTED, "no kernel family fits n=%lld nsys=%d storage=%d", (long long)h->n, s.nsys, h->storage);
   }
   return 0;
@@ -927,7 +946,7 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
   CU(cudaSetDevice(h->device));
   Fit& f = h->fit;
   f.reset();
-  bool blocked = false;
+  int family = 0;
   const bool dist = h->world > 1;
   if (dist) {
     if (!h->hx_connected) return fail(BWGR_ERR_STATE, "row-sharded handle: call bwgr_dist_connect before fitting");
@@ -936,12 +955,13 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
   }
   const int saved_path_ = h->path;
   if (dist) h->path = BWGR_PATH_BLOCKED;
-  int rc = choose_path(h, s, &blocked);
+  int rc = choose_path(h, s, &family);
   h->path = saved_path_;
   if (rc) return rc;
+  const bool blocked = family == 1;
   const int64_t n = h->n, p = h->p, ld = h->ld;
   const int ns = s.nsys;
-  f.model = s.model; f.nsys = ns; f.shuffled = s.shuffled; f.blocked = blocked; f.masked = s.row_mask != nullptr;
+  f.model = s.model; f.nsys = ns; f.shuffled = s.shuffled; f.blocked = blocked; f.gridfam = family == 2; f.masked = s.row_mask != nullptr;
   f.sweeps_issued = 0; f.seed = s.seed; f.gram_cached = false; f.skip_epilogue = false; f.wgr_mode = false; f.gram_p = nullptr;
   f.overlap = false; f.gram_ahead = -1;
   if (h->side) CU(cudaStreamSynchronize(h->side));  // a band computed ahead for a sweep the previous fit never ran
@@ -1243,6 +1263,10 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
       f.gram_p = f.gram.p;
     }
   }
+  if (f.gridfam) {
+    grid_geometry(h, &f.rows_per_cta, &f.grid);
+    if (f.gridacc.alloc((size_t)p * kGridCopies * 32) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(grid accumulators) failed");
+  }
   f.active = true;
   return 0;
 }
@@ -1267,7 +1291,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
   const int64_t p = h->p, ld = h->ld;
   const GenoView g = h->view();
   float quantum = 1, limit = 1;
-  if (f.blocked) g_fixed_point(h, f, &quantum, &limit);
+  if (f.blocked || f.gridfam) g_fixed_point(h, f, &quantum, &limit);
   for (int k = 0; k < nsweeps; k++) {
     const int sweep = f.sweeps_issued;
     const int slot = sweep % kPermRing;
@@ -1379,6 +1403,20 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
         h->prof_end(pe);
         h->launches++;
       }
+    } else if (f.gridfam) {
+      GridArgs a;
+      memset(&a, 0, sizeof a);
+      a.g = g; a.model = f.model; a.nsys = f.nsys; a.perm = d_perm; a.e = f.e.p; a.b = f.b.p; a.d = f.d.p; a.vbv = f.vbv.p;
+      a.xx = f.masked ? f.xx_sys.p : (f.xx_over.p ? f.xx_over.p : h->xx_f.p); a.xx_per_sys = f.masked ? 1 : 0; a.mask = f.mask.p;
+      a.xx2 = f.model == M_KMUP2 ? f.xx_over.p : nullptr;
+      a.sc = f.sc.p; a.acc = f.gridacc.p; a.g_quantum = quantum; a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32);
+      a.chain0 = 0; a.rows_per_cta = f.rows_per_cta; a.err = h->err.p;
+      CU(cudaMemsetAsync(f.gridacc.p, 0, sizeof(unsigned long long) * f.gridacc.n, h->stream));
+      cudaEvent_t pe = h->prof_begin(1);
+      const cudaError_t le = launch_grid_sweep(a, f.grid, h->stream);
+      h->prof_end(pe);
+      if (le != cudaSuccess) return fail(BWGR_ERR_CUDA, "grid sweep launch failed: %s", cudaGetErrorString(le));
+      h->launches++;
     } else {
       SmallNArgs a;
       memset(&a, 0, sizeof a);
@@ -2552,9 +2590,12 @@ int bwgr_mrr3_fit(bwgr_handle* h, int f32_variant, const double* Y, int k, const
   h->path = BWGR_PATH_BLOCKED;
   int rc = fit_begin(h, s, Y);
   h->path = saved_path;
-  if (rc) return rc;
   Fit& f = h->fit;
-  if (!f.pipe) { f.reset(); return fail(BWGR_ERR_UNSUPPORTED, "MRR3 needs the pipelined blocked sweep (shape does not fit)"); }
+  if (rc == BWGR_ERR_UNSUPPORTED || (!rc && !f.pipe)) {  // the shape does not fit the pipelined blocked sweep (row slabs above 512 rows): general path
+    f.reset();
+    return mrr3_general(h, f32_variant, Y, k, F, mu_out, b_out, hat_out, h2_out, GC_out, vb_out, ve_out, MSx_out, cnv_out, W_out, its_out);
+  }
+  if (rc) return rc;
   f.skip_epilogue = true;
   DevBuf<float> tilde, e_alt, b_alt, b_old, Tdev, amax;
   DevBuf<double> red, red2;

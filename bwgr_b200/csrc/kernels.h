@@ -222,6 +222,30 @@ void launch_rotate(const float* in, float* out, int64_t ld, int len, int k, cons
 void launch_pair_reduce(const float* A, const float* B, int64_t lda, int64_t ldb, int len, int k, int mode, double* out,
                         cudaStream_t st);
 
+// ---- grid family (grid_sweep.cu): the per-marker step with the individuals spread over the whole GPU; any n, row masks, every rule ----
+constexpr int kGridCopies = 8;  // accumulator copies per marker (power of two)
+struct GridArgs {
+  GenoView g;
+  int model;
+  int nsys;               // <= 32
+  const int* perm;        // marker order of this sweep [p], or nullptr = natural order
+  float* e;               // [nsys][ld]
+  float* b; float* d; float* vbv;  // [nsys][p]
+  const float* xx;        // [nxx][p]
+  int xx_per_sys;
+  const float* xx2;       // KMUP2 only
+  const uint8_t* mask;    // [nsys][ld] or nullptr
+  SysScalars* sc;         // [nsys]
+  unsigned long long* acc;  // [p][kGridCopies][32]: (fixed-point sum << 8) + arrivals; zeroed before launch
+  float g_quantum;        // value of one fixed-point unit of g
+  uint32_t seed_lo, seed_hi;
+  int chain0;
+  int rows_per_cta;       // multiple of 16; grid * rows_per_cta >= ld
+  int* err;
+};
+size_t grid_sweep_smem(int nsys, int rows_per_cta, bool masked);
+cudaError_t launch_grid_sweep(const GridArgs& a, int grid, cudaStream_t st);
+
 // ---- general multivariate ridge sweep (mrr_gen.cu): missing phenotypes, InnerGS, marker weights, NoInv, TH --------------
 constexpr int kMrrGenCopies = 8;  // accumulator copies per marker (power of two)
 struct MrrGenArgs {

@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(kGT, 1) mrr_gen_sweep_kernel(MrrGenArgs a) {
     cpa_commit();
   };
   Jnext = a.perm[0];
+  __syncthreads();  // the zeroed ring slots are in place before any cp.async lands in them
   for (int m = 0; m < kGD - 1; m++) prefetch(m);
   const unsigned long long t_start = globaltimer_ns();
   for (int m = 0; m < p; m++) {

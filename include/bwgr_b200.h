@@ -72,8 +72,10 @@ enum bwgr_gibbs_model {
 #define BWGR_NSCAL 6 /* scalars per system in bwgr_em_out.scal / bwgr_gibbs_out.scal */
 
 /* Which kernel family runs the sweep. AUTO picks SMALL_N when several systems share X and the
- * residual of one system fits one SM's shared memory, BLOCKED otherwise. */
-enum bwgr_path { BWGR_PATH_AUTO = 0, BWGR_PATH_SMALL_N = 1, BWGR_PATH_BLOCKED = 2 };
+ * residual of one system fits one SM's shared memory, BLOCKED otherwise, and GRID (the per-marker step with the individuals spread
+ * over the whole GPU: any n, row masks, every rule, <= 32 systems; latency-bound) when neither takes the shape -- n above ~75k on one
+ * GPU, or row-masked systems whose residual does not fit one SM. */
+enum bwgr_path { BWGR_PATH_AUTO = 0, BWGR_PATH_SMALL_N = 1, BWGR_PATH_BLOCKED = 2, BWGR_PATH_GRID = 3 };
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
 BWGR_API int bwgr_create(int device, bwgr_handle** out);
@@ -194,10 +196,13 @@ BWGR_API int bwgr_wgr_fit_bag(bwgr_handle* h, const double* y, int it, int bi, i
 /* MRR3 / MRR3F (src/RcppEigen20230423.cpp:318-701, :704-1079). par[30] = the arguments after
  * (Y,X) in the order of R/RcppExports.R:180. Y: n x k column-major.
  * cnv: 3*maxit doubles (cnvB | cnvH2 | cnvV).
- * On the device: complete phenotypes and the direct k x k solve, with HCS / XFA / ACS / updateMu / OneVarB / OneVarE / the GC and h2
- * shaping arguments (PenCor, MinCor, uncorH2below, roundGC*, bucketGC*, Deflate*, weight_prior_*).
- * NOT built -- BWGR_ERR_UNSUPPORTED, never a CPU fallback: NaN in Y (missing phenotypes), InnerGS = TRUE, TH = TRUE, NLfactor != 0,
- * MRR3F with NoInv = TRUE, row-sharded stores. */
+ * Two device paths, chosen by the arguments (never a CPU fallback):
+ *  - complete Y, direct k x k solve (the default flags, HCS / XFA / ACS / updateMu / OneVarB / OneVarE / NoInv for MRR3 and all the GC
+ *    and h2 shaping arguments): k rotated ridge systems on the pipelined blocked sweep, float32 device state (csrc/mrr.cu);
+ *  - everything else -- NaN in Y (missing phenotypes, :359-365), InnerGS = TRUE (:510-514), TH = TRUE (:423, :549-571), NLfactor != 0
+ *    (:524-533), MRR3F with NoInv = TRUE (:878-882): one k x k system per marker with per-trait observation masks, float64 device
+ *    state (csrc/mrr_gen.cu); needs the int8 store.
+ * BWGR_ERR_UNSUPPORTED: k > 32, row-sharded stores, a trait with fewer than two observations is BWGR_ERR_ARG. */
 BWGR_API int bwgr_mrr3_fit(bwgr_handle* h, int f32_variant, const double* Y, int k, const double* par, double* mu, double* b,
                   double* hat, double* h2, double* GC, double* vb, double* ve, double* MSx, double* cnv, double* W,
                   int* its);

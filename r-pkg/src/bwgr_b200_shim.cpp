@@ -224,6 +224,22 @@ BEGIN_RCPP
 END_RCPP
 }
 
+// ---- KMUP2: the bagged sweep of wgr(bag != 1) (glue :34-50; Rcpp20260726ai.cpp:41-77).  Use = 0-based rows (R/wgr.R:68); the third list
+// element is the residual of the rows in use.  The whole bagged loop native: bwgr_wgr_fit_bag ----
+RcppExport SEXP _bWGR_KMUP2(SEXP XSEXP, SEXP UseSEXP, SEXP bSEXP, SEXP dSEXP, SEXP xxSEXP, SEXP ESEXP, SEXP LSEXP, SEXP VeSEXP, SEXP piSEXP) {
+BEGIN_RCPP
+  int64_t n, p;
+  bwgr_handle* h = load(XSEXP, &n, &p);
+  NumericVector b = Rcpp::clone(NumericVector(bSEXP)), d = Rcpp::clone(NumericVector(dSEXP));
+  NumericVector Use(UseSEXP), xx(xxSEXP), E(ESEXP), L(LSEXP);
+  if (b.size() != p || d.size() != p || xx.size() != p || L.size() != p || E.size() != n) Rcpp::stop("KMUP2: argument lengths disagree with X");
+  NumericVector e(Use.size());
+  check(bwgr_kmup2_sweep(h, Use.begin(), Use.size(), b.begin(), d.begin(), xx.begin(), E.begin(), e.begin(), L.begin(), Rcpp::as<double>(VeSEXP),
+                         Rcpp::as<double>(piSEXP), seed_from_R()));
+  return List::create(Named("b") = b, Named("d") = d, Named("e") = e);
+END_RCPP
+}
+
 // ---- GSRR / GSFLM: the warm-start solvers of mm() (glue :493-527; lists Rcpp20260726ai.cpp:1591-1593, :1625-1627) ----
 static SEXP gs_call(int which, SEXP ySEXP, SEXP eSEXP, SEXP genSEXP, SEXP bSEXP, SEXP LmbSEXP, SEXP xxSEXP, SEXP cxxSEXP, SEXP maxitSEXP) {
   int64_t n, p;

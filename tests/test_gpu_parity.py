@@ -210,6 +210,69 @@ def test_em_synthetic_mid_size(path):
             _close_em(out, ref, model, ref64)
 
 
+# ---- the grid family (csrc/grid_sweep.cu): any n on one GPU, row masks at any n ------------------------------------------------
+@pytest.mark.parametrize("model", list(O.EM_MODELS))
+def test_grid_family_em_tpod_golden(tpod, model):
+    """The ten EM solvers on tpod forced onto the grid family (path = 3) against the oracle goldens and the reference-executed ones."""
+    y, gen = tpod
+    gold = np.load(os.path.join(GOLDEN, "tpod_em.npz"))
+    ref = {k.split("__")[1]: gold[k] for k in gold.files if k.startswith(model + "_f32__")}
+    ref = {k: (v.item() if v.ndim == 0 else v) for k, v in ref.items()}
+    ref64 = {k.split("__")[1]: gold[k] for k in gold.files if k.startswith(model + "_f64__")}
+    ref64 = {k: (v.item() if v.ndim == 0 else v) for k, v in ref64.items()}
+    with bw.Genotypes(gen, path=bw.PATH_GRID) as g:
+        out = bw.em_fit(model, y, g)
+        again = bw.em_fit(model, y, g)
+    _close_em(out, ref, model, ref64, check_its=model != "emML")
+    refx = {k.split("__")[1]: gold[k] for k in gold.files if k.startswith(model + "_ref__")}
+    refx = {k: (v.item() if v.ndim == 0 else v) for k, v in refx.items()}
+    _close_em(out, refx, model, ref64, check_its=False)
+    assert np.array_equal(out["b"], again["b"])  # integer grid sums: a fit is bit-reproducible
+
+
+def test_grid_family_large_n_masks_and_chains(tpod):
+    """What only the grid family takes: (i) n = 80,000 rows on one GPU (above the blocked family's 512 rows per worker), picked by
+    PATH_AUTO, emRR and emBC vs the oracle; (ii) row-masked systems (CV folds) at n = 40,000, where a residual no longer fits one SM,
+    vs per-subset oracle fits; (iii) a Gibbs sampler and a Kuo-Mallick sweep on it (same Philox draws as the other families)."""
+    X, y = synth(80000, 256, seed=21)
+    with bw.Genotypes(X) as g:  # AUTO
+        for model in ("emRR", "emBC"):
+            ref = O.em(model, y, X.astype(np.float32), it=6)
+            ref64 = O.em(model, y, X.astype(np.float32), it=6, use_double=True)
+            out = bw.em_fit(model, y, g, it=6)
+            _close_em(out, ref, model, ref64)
+    n = 40000
+    X, Y = synth(n, 200, k=3, seed=22)
+    fold = np.random.default_rng(1).integers(0, 2, size=n)
+    masks = np.stack([fold != 0, fold != 1, np.ones(n, bool)], axis=1)
+    with bw.Genotypes(X) as g:  # AUTO: masked, the residual of a system does not fit one SM
+        out = bw.em_fit("emBC", Y, g, it=8, row_mask=masks)
+    for t in range(3):
+        keep = masks[:, t]
+        ref = O.em("emBC", Y[keep, t], X[keep].astype(np.float32), it=8)
+        ref64 = O.em("emBC", Y[keep, t], X[keep].astype(np.float32), it=8, use_double=True)
+        # the float reference's own noise floor at 20,000 rows (its distance to its double recipe) widens the bar, as in _close_em
+        nb = np.abs(ref["b"] - ref64["b"]).max()
+        assert np.abs(out["b"][:, t] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max() + nb, (t, nb)
+        assert abs(out["h2"][t] - ref["h2"]) <= RTOL + abs(ref["h2"] - ref64["h2"]), t
+        assert np.abs(out["b"][:, t] - ref64["b"]).max() <= 5e-3 * np.abs(ref64["b"]).max(), t
+    y, gen = tpod
+    Xd = gen.astype(np.float64)
+    p = Xd.shape[1]
+    with bw.Genotypes(gen, path=bw.PATH_GRID) as g, bw.Genotypes(gen, path=bw.PATH_SMALL_N) as gs:
+        a = bw.gibbs_fit("BayesB", y, g, it=300, bi=100, seed=11)
+        b = bw.gibbs_fit("BayesB", y, gs, it=300, bi=100, seed=11)
+        # same draws, same rule; only the summation order of g differs (float vs integer sums): the chains agree to rounding early on,
+        # and the posterior summaries stay close
+        assert np.corrcoef(a["hat"], b["hat"])[0, 1] > 0.99 and abs(a["ve"] - b["ve"]) < 0.1 * b["ve"]
+        xx = (Xd ** 2).sum(0)
+        e = y - y.mean()
+        ref = O.kmup(Xd, np.zeros(p), np.ones(p), xx, e, np.full(p, 37.0), 1e-30, 0.0, seed=3)
+        out = bw.KMUP(g, np.zeros(p), np.ones(p), xx, e, np.full(p, 37.0), 1e-30, 0.0, seed=9)
+        assert np.abs(out["b"] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max()
+        assert np.abs(out["e"] - ref["e"]).max() <= RTOL * np.abs(ref["e"]).max()
+
+
 def test_em_multi_system_and_folds():
     """Batched fits (config 4 pattern): k traits x folds as independent systems with row masks equal the
     same fits done one by one on the row subset (what emCV does with gen[-w,], R/cv.R:13-22)."""
