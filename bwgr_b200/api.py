@@ -12,7 +12,7 @@ import numpy as np
 from . import _lib
 from ._lib import EmOut, EmParams, GibbsOut, GibbsParams, check
 
-STORE_I8, STORE_2BIT = 0, 1
+STORE_I8, STORE_2BIT, STORE_F32 = 0, 1, 2
 PATH_AUTO, PATH_SMALL_N, PATH_BLOCKED, PATH_GRID = 0, 1, 2, 3
 _EM = {"emRR": 0, "emBA": 1, "emBB": 2, "emBC": 3, "emBL": 4, "emEN": 5, "emDE": 6, "emML": 7, "emBCpi": 8, "lasso": 9}
 _GIBBS = {"BayesRR": 0, "BayesA": 1, "BayesB": 2, "BayesC": 3, "BayesL": 4, "BayesCpi": 5, "BayesDpi": 6}
@@ -63,7 +63,14 @@ class Genotypes:
             else:
                 Xf = np.asfortranarray(X, dtype=np.float64)
                 fn = self.lib.bwgr_geno_load_f64_centred if centred_ok else self.lib.bwgr_geno_load_f64
-                check(fn(self.h, _ptr(Xf), n, p, n, storage))
+                try:
+                    check(fn(self.h, _ptr(Xf), n, p, n, storage))
+                except _lib.BwgrError as err:
+                    # real-valued genotypes (NA cells imputed with column means, R/wgr.R:13-19; IMP() / CNT() output): the float32
+                    # store, the type the reference itself computes in -- served by the grid family
+                    if err.code != -1 or storage != STORE_I8 or "non-integer" not in str(err):
+                        raise
+                    check(self.lib.bwgr_geno_load_f64(self.h, _ptr(Xf), n, p, n, STORE_F32))
         self.n, self.p = int(n), int(p)
         return self
 

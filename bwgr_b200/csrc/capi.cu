@@ -247,6 +247,7 @@ struct bwgr_handle {
   // genotype store
   DevBuf<int8_t> x8_own;
   const int8_t* x8 = nullptr;
+  DevBuf<float> xf_own;  // float32 store (BWGR_STORE_F32): real-valued genotypes, grid family only
   DevBuf<uint8_t> x2;
   DevBuf<uint8_t> x2f;  // packed 2-bit shadow in the layout gram_fp4.cu expands to E2M1 nibbles (codes 0..2 only)
   DevBuf<uint8_t> x2g;  // packed 2-bit shadow of an int8 store with codes 0..2: what the Gram kernel gathers (4x fewer bytes)
@@ -324,7 +325,7 @@ struct bwgr_handle {
 
   GenoView view() const {
     GenoView g;
-    g.x8 = x8; g.x2 = x2.p; g.ld = ld; g.ldb = ldb; g.n = (int)n; g.p = (int)p;
+    g.x8 = x8; g.x2 = x2.p; g.xf = xf_own.p; g.ld = ld; g.ldb = ldb; g.n = (int)n; g.p = (int)p;
     g.storage = storage;
     return g;
   }
@@ -456,7 +457,7 @@ int finish_store(bwgr_handle* h, int storage) {
 int prepare_store(bwgr_handle* h, int64_t n, int64_t p, int storage) {
   if (!h) return fail(BWGR_ERR_ARG, "null handle");
   if (n < 2 || p < 1 || n > (int64_t)1 << 30 || p > (int64_t)1 << 30) return fail(BWGR_ERR_ARG, "bad shape n=%lld p=%lld", (long long)n, (long long)p);
-  if (storage != BWGR_STORE_I8 && storage != BWGR_STORE_2BIT) return fail(BWGR_ERR_ARG, "bad storage %d", storage);
+  if (storage != BWGR_STORE_I8 && storage != BWGR_STORE_2BIT && storage != BWGR_STORE_F32) return fail(BWGR_ERR_ARG, "bad storage %d", storage);
   CU(cudaSetDevice(h->device));
   h->fit.reset();
   h->x2.release();
@@ -465,6 +466,13 @@ int prepare_store(bwgr_handle* h, int64_t n, int64_t p, int storage) {
   h->n = n; h->p = p;
   h->ld = (n + 127) / 128 * 128;
   h->ldb = 0;
+  h->xf_own.release();
+  if (storage == BWGR_STORE_F32) {
+    if (h->world > 1) return fail(BWGR_ERR_UNSUPPORTED, "row-sharded fits take the int8 store");
+    h->x8_own.release(); h->x8 = nullptr;
+    if (h->xf_own.alloc((size_t)h->ld * p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(%lld bytes) for genotypes failed", (long long)(h->ld * p * 4));
+    return 0;
+  }
   if (h->x8_own.alloc((size_t)h->ld * p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(%lld bytes) for genotypes failed", (long long)(h->ld * p));
   h->x8 = h->x8_own.p;
   return 0;
@@ -603,8 +611,64 @@ static int loader_threads() {
   return std::max(1, std::min(nt, 64));
 }
 
+// BWGR_STORE_F32: R's double matrix narrowed to float32, the type the reference itself computes in (Eigen::MatrixXf arguments,
+// RcppExports.cpp:115-116) -- any real-valued genotypes: NA cells imputed with column means (R/wgr.R:13-19), IMP() / CNT() output.
+static int load_f64_real(bwgr_handle* h, const double* X, int64_t n, int64_t p, int64_t ld) {
+  int rc = prepare_store(h, n, p, BWGR_STORE_F32);
+  if (rc) return rc;
+  h->col_offset.clear(); h->has_offset = false;
+  const int64_t ldd = h->ld;
+  const int64_t chunk_cols = std::max<int64_t>(1, std::min<int64_t>(p, ((int64_t)64 << 20) / (ldd * 4)));
+  float* stage[2] = {nullptr, nullptr};
+  const size_t bytes = (size_t)chunk_cols * ldd * sizeof(float);
+  if (pinned_alloc(reinterpret_cast<void**>(&stage[0]), bytes) != cudaSuccess || pinned_alloc(reinterpret_cast<void**>(&stage[1]), bytes) != cudaSuccess) {
+    pinned_free(stage[0], bytes); pinned_free(stage[1], bytes);
+    return fail(BWGR_ERR_CUDA, "cudaMallocHost(staging) failed");
+  }
+  cudaEvent_t done[2];
+  cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming);
+  bool used[2] = {false, false}, bad = false;
+  cudaError_t ce = cudaSuccess;
+  for (int64_t j0 = 0, c = 0; j0 < p && ce == cudaSuccess; j0 += chunk_cols, c++) {
+    const int sl = (int)(c & 1);
+    const int64_t pc = std::min(chunk_cols, p - j0);
+    if (used[sl]) ce = cudaEventSynchronize(done[sl]);
+    float* dst = stage[sl];
+    for (int64_t j = 0; j < pc; j++) {
+      const double* src = X + (size_t)(j0 + j) * ld;
+      float* col = dst + (size_t)j * ldd;
+      for (int64_t i = 0; i < n; i++) { const double v = src[i]; if (!(v - v == 0.0)) bad = true; col[i] = (float)v; }
+      for (int64_t i = n; i < ldd; i++) col[i] = 0.0f;
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->xf_own.p + j0 * ldd, dst, (size_t)pc * ldd * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+    if (ce == cudaSuccess) ce = cudaEventRecord(done[sl], h->stream);
+    used[sl] = true;
+  }
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+  cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+  pinned_free(stage[0], bytes); pinned_free(stage[1], bytes);
+  if (ce != cudaSuccess) return fail(BWGR_ERR_CUDA, "bwgr_geno_load_f64: %s", cudaGetErrorString(ce));
+  if (bad) return fail(BWGR_ERR_ARG, "bwgr_geno_load_f64: NaN or infinite genotype (impute first: R/wgr.R:13-19)");
+  // column statistics in double
+  DevBuf<double> dxx, dsx;
+  if (dxx.alloc(p) != cudaSuccess || dsx.alloc(p) != cudaSuccess || h->xx_f.alloc(p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(stats) failed");
+  launch_col_stats_f32(h->view(), nullptr, dxx.p, dsx.p, h->stream);
+  launch_d_to_float(dxx.p, h->xx_f.p, (int)p, h->stream);
+  h->launches += 2;
+  h->h_xx.resize(p); h->h_sx.resize(p);
+  CU(cudaMemcpyAsync(h->h_xx.data(), dxx.p, sizeof(double) * p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(h->h_sx.data(), dsx.p, sizeof(double) * p, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->n_global = h->n;
+  h->storage = BWGR_STORE_F32;
+  h->fp8_codes = 0; h->tmap_ok = false;
+  h->x2f.release(); h->x2g.release();
+  return 0;
+}
+
 static int load_f64_common(bwgr_handle* h, const double* X, int64_t n, int64_t p, int64_t ld, int storage, bool allow_offset) {
   if (!X || ld < n) return fail(BWGR_ERR_ARG, "bad X / ld");
+  if (storage == BWGR_STORE_F32) return load_f64_real(h, X, n, p, ld);
   int rc = prepare_store(h, n, p, storage);
   if (rc) return rc;
   h->col_offset.clear(); h->has_offset = false;
@@ -757,7 +821,7 @@ int bwgr_geno_load_i8_device(bwgr_handle* h, const int8_t* dX, int64_t n, int64_
 
 int bwgr_geno_info(bwgr_handle* h, int64_t* n, int64_t* p, int64_t* ld_bytes, int* storage, int64_t* total_bytes) {
   if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
-  const int64_t ldb = h->storage == BWGR_STORE_2BIT ? h->ldb : h->ld;
+  const int64_t ldb = h->storage == BWGR_STORE_2BIT ? h->ldb : h->storage == BWGR_STORE_F32 ? h->ld * 4 : h->ld;
   if (n) *n = h->n;
   if (p) *p = h->p;
   if (ld_bytes) *ld_bytes = ldb;
@@ -768,8 +832,8 @@ int bwgr_geno_info(bwgr_handle* h, int64_t* n, int64_t* p, int64_t* ld_bytes, in
 
 int bwgr_geno_raw(bwgr_handle* h, uint8_t* out) {
   if (!h || !h->p || !out) return fail(BWGR_ERR_STATE, "no genotypes loaded");
-  const void* src = h->storage == BWGR_STORE_2BIT ? (const void*)h->x2.p : (const void*)h->x8;
-  const int64_t ldb = h->storage == BWGR_STORE_2BIT ? h->ldb : h->ld;
+  const void* src = h->storage == BWGR_STORE_2BIT ? (const void*)h->x2.p : h->storage == BWGR_STORE_F32 ? (const void*)h->xf_own.p : (const void*)h->x8;
+  const int64_t ldb = h->storage == BWGR_STORE_2BIT ? h->ldb : h->storage == BWGR_STORE_F32 ? h->ld * 4 : h->ld;
   CU(cudaMemcpyAsync(out, src, (size_t)ldb * h->p, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return 0;
@@ -777,6 +841,7 @@ int bwgr_geno_raw(bwgr_handle* h, uint8_t* out) {
 
 int bwgr_geno_unpack_i8(bwgr_handle* h, int8_t* out) {
   if (!h || !h->p || !out) return fail(BWGR_ERR_STATE, "no genotypes loaded");
+  if (h->storage == BWGR_STORE_F32) return fail(BWGR_ERR_UNSUPPORTED, "the float32 store holds real-valued genotypes: read it with bwgr_geno_raw");
   if (h->storage == BWGR_STORE_I8) {
     CU(cudaMemcpy2DAsync(out, h->n, h->x8, h->ld, h->n, h->p, cudaMemcpyDeviceToHost, h->stream));
   } else {
@@ -906,7 +971,7 @@ void grid_geometry(bwgr_handle* h, int* rp, int* grid) {
 // family: 0 = small-n, 1 = blocked, 2 = grid
 int choose_path(bwgr_handle* h, const FitSpec& s, int* family) {
   const GenoView g = h->view();
-  const bool small_ok = small_n_fits(g, s.row_mask != nullptr, h->smem_optin);
+  const bool small_ok = h->storage != BWGR_STORE_F32 && small_n_fits(g, s.row_mask != nullptr, h->smem_optin);
   const int grid = h->grid > 0 ? std::min(h->grid, h->num_sms) : h->num_sms;
   const int64_t rows = ((h->ld + grid - 1) / grid + 15) / 16 * 16;
   PipePlan pl;
@@ -914,8 +979,8 @@ int choose_path(bwgr_handle* h, const FitSpec& s, int* family) {
                           (plan_pipe(h, s.model, s.nsys, &pl) || (rows <= 512 && sweep_blocked_smem((int)rows, s.nsys) <= h->smem_optin));
   int grp = 0, ggrid = 0;
   grid_geometry(h, &grp, &ggrid);
-  const bool grid_ok = h->storage == BWGR_STORE_I8 && h->world <= 1 && s.nsys <= 32 && s.model != M_MRR && ggrid <= 255 &&
-                       grid_sweep_smem(s.nsys, grp, s.row_mask != nullptr) <= h->smem_optin;
+  const bool grid_ok = (h->storage == BWGR_STORE_I8 || h->storage == BWGR_STORE_F32) && h->world <= 1 && s.nsys <= 32 && s.model != M_MRR &&
+                       ggrid <= 255 && grid_sweep_smem(s.nsys, grp, s.row_mask != nullptr, h->storage == BWGR_STORE_F32) <= h->smem_optin;
   if (h->path == BWGR_PATH_SMALL_N) {
     if (!small_ok) return fail(BWGR_ERR_UNSUPPORTED, "small-n path: residual of n=%lld does not fit one SM", (long long)h->n);
     *family = 0;
@@ -923,7 +988,7 @@ int choose_path(bwgr_handle* h, const FitSpec& s, int* family) {
     if (!blocked_ok) return fail(BWGR_ERR_UNSUPPORTED, "blocked path needs the int8 store, no row mask, nsys<=32 and n <= 512 rows x grid");
     *family = 1;
   } else if (h->path == BWGR_PATH_GRID) {
-    if (!grid_ok) return fail(BWGR_ERR_UNSUPPORTED, "grid path needs the int8 store, one GPU, nsys<=32 and the row slabs of all systems in shared memory");
+    if (!grid_ok) return fail(BWGR_ERR_UNSUPPORTED, "grid path needs the int8 or float32 store, one GPU, nsys<=32 and the row slabs of all systems in shared memory");
     *family = 2;
   } else {
     const bool prefer_small = small_ok && (s.row_mask || s.nsys >= 8 || h->n <= 1024);
@@ -987,6 +1052,19 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
     std::vector<long long> hx(p), hs(p);
     std::vector<float> xf(p);
     for (int t = 0; t < ns; t++) {
+      if (h->storage == BWGR_STORE_F32) {  // real-valued store: the same sums in double (two long long = two double buffers)
+        double* dxx = reinterpret_cast<double*>(txx.p); double* dsx = reinterpret_cast<double*>(tsx.p);
+        launch_col_stats_f32(h->view(), f.mask.p + (size_t)t * ld, dxx, dsx, h->stream);
+        h->launches++;
+        xx_s[t].resize(p); sx_s[t].resize(p);
+        CU(cudaMemcpyAsync(xx_s[t].data(), dxx, sizeof(double) * p, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(sx_s[t].data(), dsx, sizeof(double) * p, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (int64_t j = 0; j < p; j++) xf[j] = (float)xx_s[t][j];
+        CU(cudaMemcpyAsync(f.xx_sys.p + (size_t)t * p, xf.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        continue;
+      }
       launch_col_stats_masked(h->view(), f.mask.p + (size_t)t * ld, txx.p, tsx.p, h->stream);
       h->launches++;
       CU(cudaMemcpyAsync(hx.data(), txx.p, sizeof(long long) * p, cudaMemcpyDeviceToHost, h->stream));
@@ -2048,8 +2126,13 @@ int bwgr_wgr_fit_bag(bwgr_handle* h, const double* y, int it, int bi, int th, do
     if (i > 0) {  // this iteration's rows: mask, and H'H of every marker over them (the rule's likelihood-ratio scale)
       draw();
       CU(cudaMemcpyAsync(f.mask.p, mask.data(), (size_t)ld, cudaMemcpyHostToDevice, h->stream));
-      launch_col_stats_masked(h->view(), f.mask.p, txx.p, tsx.p, h->stream);
-      launch_ll_to_float(txx.p, f.xx_sys.p, (int)p, h->stream);
+      if (h->storage == BWGR_STORE_F32) {
+        launch_col_stats_f32(h->view(), f.mask.p, reinterpret_cast<double*>(txx.p), reinterpret_cast<double*>(tsx.p), h->stream);
+        launch_d_to_float(reinterpret_cast<double*>(txx.p), f.xx_sys.p, (int)p, h->stream);
+      } else {
+        launch_col_stats_masked(h->view(), f.mask.p, txx.p, tsx.p, h->stream);
+        launch_ll_to_float(txx.p, f.xx_sys.p, (int)p, h->stream);
+      }
       h->launches += 2;
     }
     rc = fit_sweeps(h, 1);  // KMUP2 over the rows in use
@@ -2797,6 +2880,7 @@ int bwgr_profile_read(bwgr_handle* h, double* ms, int64_t* counts) {
 // The band the pipelined sweep consumes, produced by the SAME dispatch as in a fit (FP4 shadow when the store has one):
 // out [nblocks][128][256] floats, row r of block b = [x_{b,r}'X_b | x_{b-1,r}'X_b].  *kind_out: 4 = FP4 path, 8 = E4M3 / int8 path.
 int bwgr_debug_gram_band(bwgr_handle* h, const int32_t* perm, float* gram_out, int* kind_out) {
+  if (h && h->storage == BWGR_STORE_F32) return fail(BWGR_ERR_UNSUPPORTED, "the Gram kernels read the integer stores");
   if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
   if (h->storage != BWGR_STORE_I8) return fail(BWGR_ERR_UNSUPPORTED, "Gram kernel needs the int8 store");
   CU(cudaSetDevice(h->device));
@@ -2820,6 +2904,7 @@ int bwgr_debug_gram_band(bwgr_handle* h, const int32_t* perm, float* gram_out, i
 }
 
 int bwgr_debug_gram(bwgr_handle* h, const int32_t* perm, int block, int32_t* gram_out) {
+  if (h && h->storage == BWGR_STORE_F32) return fail(BWGR_ERR_UNSUPPORTED, "the Gram kernels read the integer stores");
   if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
   if (block != kBlk) return fail(BWGR_ERR_UNSUPPORTED, "only block=%d is built", kBlk);
   if (h->storage != BWGR_STORE_I8) return fail(BWGR_ERR_UNSUPPORTED, "Gram kernel needs the int8 store");

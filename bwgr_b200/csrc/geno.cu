@@ -208,6 +208,36 @@ void launch_col_stats_masked(const GenoView& g, const uint8_t* mask, long long* 
   col_stats_kernel<true><<<g.p, 256, 0, st>>>(g, mask, xx, sx);
 }
 
+// float32 store: xx_j = sum x^2, sx_j = sum x in double, fixed order (one CTA per marker)
+__global__ void __launch_bounds__(256) col_stats_f32_kernel(GenoView g, const uint8_t* __restrict__ mask, double* __restrict__ xx,
+                                                            double* __restrict__ sx) {
+  __shared__ double sh1[8], sh2[8];
+  const int j = blockIdx.x, tid = threadIdx.x;
+  const float* col = g.xf + (int64_t)j * g.ld;
+  double s1 = 0, s2 = 0;
+  for (int i = tid; i < g.n; i += 256) {
+    if (mask && !mask[i]) continue;
+    const double v = (double)col[i];
+    s1 += v; s2 += v * v;
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if ((tid & 31) == 0) { sh1[tid >> 5] = s1; sh2[tid >> 5] = s2; }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0, c = 0;
+    for (int w = 0; w < 8; w++) { a += sh1[w]; c += sh2[w]; }
+    sx[j] = a; xx[j] = c;
+  }
+}
+void launch_col_stats_f32(const GenoView& g, const uint8_t* mask, double* xx, double* sx, cudaStream_t st) {
+  col_stats_f32_kernel<<<g.p, 256, 0, st>>>(g, mask, xx, sx);
+}
+__global__ void __launch_bounds__(256) d_to_float_kernel(const double* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) dst[i] = (float)src[i];
+}
+void launch_d_to_float(const double* src, float* dst, int n, cudaStream_t st) { d_to_float_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, n); }
+
 // hat = mu + X b.  CTA (x = row tile of 256*16 rows, y = column split): partial[y][row] = sum over its
 // columns; then a second kernel adds the splits in a fixed order (deterministic).
 __global__ void __launch_bounds__(256) gemv_partial_kernel(GenoView g, const float* __restrict__ b, float* __restrict__ work,
@@ -220,6 +250,16 @@ __global__ void __launch_bounds__(256) gemv_partial_kernel(GenoView g, const flo
   for (int j = blockIdx.y; j < g.p; j += splits) {
     const float bj = __ldg(b + j);
     if (bj == 0.0f) continue;
+    if (g.storage == 2) {  // float32 store
+      const float4* v = reinterpret_cast<const float4*>(g.xf + (int64_t)j * g.ld + row0);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const float4 x = __ldg(v + q);
+        acc[4 * q + 0] = fmaf(x.x, bj, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(x.y, bj, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(x.z, bj, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(x.w, bj, acc[4 * q + 3]);
+      }
+      continue;
+    }
     uint32_t w[4];
     if (g.storage == 0) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(g.x8 + (int64_t)j * g.ld + row0));

@@ -46,19 +46,19 @@ __device__ __forceinline__ unsigned long long gtimer() {
 struct GridSmem {
   float* E;          // [ns][rp]
   uint8_t* M;        // [ns][rp] (masked fits)
-  int8_t* xs[kD];    // [rp]
+  unsigned char* xs[kD];  // [rp] int8 or [rp] float
   float* vin[kD];    // b0[32] | vbj[32] | xx[32] | xx2
   SysScalars* sc;    // [ns]
   MarkerDraws* dr;   // [2][32]
   int* Js;           // [kD]
 };
 
-__host__ __device__ inline size_t grid_carve(unsigned char* base, int ns, int rp, bool masked, GridSmem* s) {
+__host__ __device__ inline size_t grid_carve(unsigned char* base, int ns, int rp, bool masked, int xbytes, GridSmem* s) {
   size_t o = 0;
   auto take = [&](size_t bytes) { unsigned char* q = base ? base + o : nullptr; o = (o + bytes + 15) & ~(size_t)15; return q; };
   float* E = reinterpret_cast<float*>(take(sizeof(float) * (size_t)ns * rp));
-  int8_t* xs[kD];
-  for (int d = 0; d < kD; d++) xs[d] = reinterpret_cast<int8_t*>(take((size_t)rp));
+  unsigned char* xs[kD];
+  for (int d = 0; d < kD; d++) xs[d] = take((size_t)rp * xbytes);
   uint8_t* M = reinterpret_cast<uint8_t*>(take(masked ? (size_t)ns * rp : 0));
   float* vin[kD];
   for (int d = 0; d < kD; d++) vin[d] = reinterpret_cast<float*>(take(sizeof(float) * 100));
@@ -72,7 +72,8 @@ __host__ __device__ inline size_t grid_carve(unsigned char* base, int ns, int rp
   return o;
 }
 
-template <int MODEL>
+// XT = int8_t (integer store) or float (real-valued store: NA-imputed / centred genotypes, what the reference holds as MatrixXf)
+template <int MODEL, class XT>
 __global__ void __launch_bounds__(kT, 1) grid_sweep_kernel(GridArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_abort;
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(kT, 1) grid_sweep_kernel(GridArgs a) {
   GridSmem s;
   const int ns = a.nsys, rp = a.rows_per_cta, p = a.g.p;
   const bool masked = a.mask != nullptr;
-  grid_carve(smem_raw, ns, rp, masked, &s);
+  grid_carve(smem_raw, ns, rp, masked, (int)sizeof(XT), &s);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = (int)gridDim.x, cta = blockIdx.x;
   const int64_t ld = a.g.ld, r0 = (int64_t)cta * rp;
   for (int q = tid; q < ns * rp; q += kT) {
@@ -90,19 +91,21 @@ __global__ void __launch_bounds__(kT, 1) grid_sweep_kernel(GridArgs a) {
     s.E[q] = in ? a.e[(size_t)t * ld + r0 + i] : 0.0f;
     if (masked) s.M[q] = in ? a.mask[(size_t)t * ld + r0 + i] : (uint8_t)0;
   }
-  for (int q = tid; q < kD * rp; q += kT) s.xs[0][q] = 0;  // the ring slots are contiguous (rp is a multiple of 16)
+  for (int q = tid; q < kD * rp * (int)sizeof(XT); q += kT) s.xs[0][q] = 0;  // the ring slots are contiguous (rp is a multiple of 16)
   if (tid < ns) s.sc[tid] = a.sc[tid];
   if (tid == 0) s_abort = 0;
-  const int nch = rp / 16;
+  const int nch = rp * (int)sizeof(XT) / 16;  // 16-byte chunks of a slab
+  constexpr int kRowsPerChunk = 16 / (int)sizeof(XT);
   const float* xxbase = a.xx;
   int Jnext = a.perm ? a.perm[0] : 0;
   auto prefetch = [&](int m) {
     if (m < p) {
       const int J = Jnext, slot = m % kD;
       if (m + 1 < p) Jnext = a.perm ? a.perm[m + 1] : m + 1;
-      const int8_t* col = a.g.x8 + (int64_t)J * ld + r0;
+      const unsigned char* col = sizeof(XT) == 1 ? reinterpret_cast<const unsigned char*>(a.g.x8 + (int64_t)J * ld + r0)
+                                                 : reinterpret_cast<const unsigned char*>(a.g.xf + (int64_t)J * ld + r0);
       for (int c = tid; c < nch; c += kT)
-        if (r0 + 16 * c < ld) gcp16(s.xs[slot] + 16 * c, col + 16 * c);
+        if (r0 + (int64_t)kRowsPerChunk * c < ld) gcp16(s.xs[slot] + 16 * c, col + 16 * c);
       float* v = s.vin[slot];
       if (tid < 32) { if (tid < ns) gcp4(v + tid, a.b + (size_t)tid * p + J); }
       else if (tid < 64) { const int t = tid - 32; if (t < ns && a.vbv) gcp4(v + 32 + t, a.vbv + (size_t)t * p + J); }
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(kT, 1) grid_sweep_kernel(GridArgs a) {
     __syncthreads();  // marker m's slot has landed; step m - 1 is finished by every thread
     prefetch(m + kD - 1);
     const int slot = m % kD;
-    const int8_t* xs = s.xs[slot];
+    const XT* xs = reinterpret_cast<const XT*>(s.xs[slot]);
     const float* vin = s.vin[slot];
     // ---- slab dot products g_s = x'e_s
     if (ns == 1) {
@@ -238,8 +241,9 @@ __global__ void __launch_bounds__(kT, 1) grid_sweep_kernel(GridArgs a) {
 
 template <int MODEL>
 cudaError_t launch_grid_model(const GridArgs& a, int grid, cudaStream_t st) {
-  const size_t smem = grid_sweep_smem(a.nsys, a.rows_per_cta, a.mask != nullptr);
-  const void* fn = reinterpret_cast<const void*>(grid_sweep_kernel<MODEL>);
+  const bool real = a.g.storage == 2;
+  const size_t smem = grid_sweep_smem(a.nsys, a.rows_per_cta, a.mask != nullptr, real);
+  const void* fn = real ? reinterpret_cast<const void*>(grid_sweep_kernel<MODEL, float>) : reinterpret_cast<const void*>(grid_sweep_kernel<MODEL, int8_t>);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   GridArgs args = a;
@@ -249,7 +253,9 @@ cudaError_t launch_grid_model(const GridArgs& a, int grid, cudaStream_t st) {
 
 }  // namespace
 
-size_t grid_sweep_smem(int nsys, int rows_per_cta, bool masked) { return grid_carve(nullptr, nsys, rows_per_cta, masked, nullptr) + 16; }
+size_t grid_sweep_smem(int nsys, int rows_per_cta, bool masked, bool real_store) {
+  return grid_carve(nullptr, nsys, rows_per_cta, masked, real_store ? 4 : 1, nullptr) + 16;
+}
 
 cudaError_t launch_grid_sweep(const GridArgs& a, int grid, cudaStream_t st) {
   switch (rule_model(a.model)) {

@@ -11,6 +11,7 @@ namespace bwgr {
 struct GenoView {
   const int8_t* x8 = nullptr;   // int8 store: column j at x8 + j*ld
   const uint8_t* x2 = nullptr;  // 2-bit store: column j at x2 + j*ldb, row r in byte r/4, bits 2*(r%4)
+  const float* xf = nullptr;    // float32 store (storage 2, real-valued genotypes): column j at xf + j*ld; grid family only
   int64_t ld = 0, ldb = 0;
   int n = 0, p = 0;
   int storage = 0;
@@ -35,6 +36,9 @@ void launch_zero_pad(int8_t* x, int64_t ld, int n, int p, cudaStream_t st);
 void launch_col_stats(const GenoView& g, long long* xx, long long* sx, cudaStream_t st);
 // masked variant for a system with a row mask (uint8 n): xx, sx over used rows
 void launch_col_stats_masked(const GenoView& g, const uint8_t* mask, long long* xx, long long* sx, cudaStream_t st);
+// float32 store: column statistics in double (mask: optional uint8 [n], rows used)
+void launch_col_stats_f32(const GenoView& g, const uint8_t* mask, double* xx, double* sx, cudaStream_t st);
+void launch_d_to_float(const double* src, float* dst, int n, cudaStream_t st);
 // hat = mu + X b (deterministic two-stage reduction). work: [splits][ld] floats.
 void launch_gemv_hat(const GenoView& g, const float* b, const float* mu_dev, float* hat, float* work, int splits,
                      cudaStream_t st);
@@ -243,7 +247,7 @@ struct GridArgs {
   int rows_per_cta;       // multiple of 16; grid * rows_per_cta >= ld
   int* err;
 };
-size_t grid_sweep_smem(int nsys, int rows_per_cta, bool masked);
+size_t grid_sweep_smem(int nsys, int rows_per_cta, bool masked, bool real_store);
 cudaError_t launch_grid_sweep(const GridArgs& a, int grid, cudaStream_t st);
 
 // ---- general multivariate ridge sweep (mrr_gen.cu): missing phenotypes, InnerGS, marker weights, NoInv, TH --------------

@@ -39,7 +39,9 @@ enum bwgr_status {
 /* Genotype storage in HBM: column-major, one marker per column. */
 enum bwgr_storage {
   BWGR_STORE_I8 = 0,  /* int8, leading dimension padded to 128 rows */
-  BWGR_STORE_2BIT = 1 /* codes {0,1,2} packed 4 per byte (little end first), unpacked on the fly */
+  BWGR_STORE_2BIT = 1, /* codes {0,1,2} packed 4 per byte (little end first), unpacked on the fly */
+  BWGR_STORE_F32 = 2   /* float32, the type the reference computes in (Eigen::MatrixXf): ANY real-valued genotypes -- NA cells imputed
+                          with column means (R/wgr.R:13-19), IMP() / CNT() output.  Served by the grid family only (bwgr_geno_load_f64). */
 };
 
 /* Univariate EM solvers of src/Rcpp20260726ai.cpp. */

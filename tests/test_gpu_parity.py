@@ -273,6 +273,40 @@ def test_grid_family_large_n_masks_and_chains(tpod):
         assert np.abs(out["e"] - ref["e"]).max() <= RTOL * np.abs(ref["e"]).max()
 
 
+def test_real_valued_genotypes_float32_store(tpod):
+    """Genotypes with NA cells imputed by the column mean (what wgr does itself, R/wgr.R:13-19, and what IMP() returns) are not integer
+    codes: they go to the float32 store -- the reference's own MatrixXf -- and run on the grid family.  emRR / emBC / emBL against the
+    oracle on the same imputed matrix, wgr within Monte-Carlo error, CNT(gen) through emRR; an integer matrix in the float32 store gives
+    the same bits as in the int8 store."""
+    y, gen = tpod
+    rng = np.random.default_rng(5)
+    X = gen.astype(np.float64)
+    miss = rng.random(X.shape) < 0.03
+    Xn = X.copy(); Xn[miss] = np.nan
+    Xi = np.where(miss, np.nanmean(Xn, axis=0)[None, :], X)  # imp(): x[is.na(x)] = mean(x, na.rm = TRUE)
+    with bw.Genotypes(Xi) as g:
+        assert g.info()["storage"] == bw.STORE_F32
+        for model in ("emRR", "emBC", "emBL"):
+            ref = O.em(model, y, Xi.astype(np.float32), it=40)
+            ref64 = O.em(model, y, Xi.astype(np.float32), it=40, use_double=True)
+            out = bw.em_fit(model, y, g, it=40)
+            _close_em(out, ref, model, ref64)
+        kw = dict(pi=0.9, iv=True)
+        ora = [O.wgr(y, Xi, it=600, bi=150, seed=50 + s, ratio_form=True, **kw) for s in range(6)]
+        gpu = [bw.wgr(y, g, it=600, bi=150, seed=70 + s, **kw) for s in range(6)]
+        A = np.mean([r["hat"] for r in ora], 0); B = np.mean([r["hat"] for r in gpu], 0)
+        A1 = np.mean([r["hat"] for r in ora[:3]], 0); A2 = np.mean([r["hat"] for r in ora[3:]], 0)
+        assert np.corrcoef(A, B)[0, 1] > min(0.99, np.corrcoef(A1, A2)[0, 1] - 0.005)
+        assert np.isclose(gpu[0]["cxx"], ora[0]["cxx"])
+    Xc = X - X.mean(0)  # CNT(gen), Rcpp20260726ai.cpp:1308
+    ref = O.em("emRR", y, Xc.astype(np.float32), it=30)
+    ref64 = O.em("emRR", y, Xc.astype(np.float32), it=30, use_double=True)
+    _close_em(bw.em_fit("emRR", y, Xc, it=30), ref, "emRR", ref64)
+    with bw.Genotypes(gen, path=bw.PATH_GRID) as g8, bw.Genotypes(X, storage=bw.STORE_F32) as gf:
+        a, b = bw.em_fit("emBB", y, g8, it=25), bw.em_fit("emBB", y, gf, it=25)
+        assert np.array_equal(a["b"], b["b"]) and np.array_equal(a["hat"], b["hat"])
+
+
 def test_em_multi_system_and_folds():
     """Batched fits (config 4 pattern): k traits x folds as independent systems with row masks equal the
     same fits done one by one on the row subset (what emCV does with gen[-w,], R/cv.R:13-22)."""
