@@ -32,8 +32,12 @@ bwgr_handle* load(SEXP genSEXP, int64_t* n, int64_t* p, bool centred_ok = false)
   *n = gen.nrow(); *p = gen.ncol();
   bwgr_handle* h = handle();
   if (gen.begin() != last || *n != ln || *p != lp || lc != centred_ok) {
-    // exact integer codes only (plus one constant per column for the solvers that centre the columns); anything else is an R error
-    check(centred_ok ? bwgr_geno_load_f64_centred(h, gen.begin(), *n, *p, *n, BWGR_STORE_I8) : bwgr_geno_load_f64(h, gen.begin(), *n, *p, *n, BWGR_STORE_I8));
+    // exact integer codes (plus one constant per column for the solvers that centre the columns) go to the int8 store; any other
+    // real-valued matrix -- NA cells imputed with column means (R/wgr.R:13-19), IMP() / CNT() output -- to the float32 store, the type the
+    // reference's own glue narrows to (RcppExports.cpp:115-116), which the grid kernel family serves
+    int rc = centred_ok ? bwgr_geno_load_f64_centred(h, gen.begin(), *n, *p, *n, BWGR_STORE_I8) : bwgr_geno_load_f64(h, gen.begin(), *n, *p, *n, BWGR_STORE_I8);
+    if (rc == BWGR_ERR_ARG) rc = bwgr_geno_load_f64(h, gen.begin(), *n, *p, *n, BWGR_STORE_F32);
+    check(rc);
     last = gen.begin(); ln = *n; lp = *p; lc = centred_ok;
   }
   return h;
