@@ -462,8 +462,121 @@ def wgr(y, X, it=1500, bi=500, th=1, bag=1, rp=False, iv=False, de=False, pi=0, 
         verb=False, seed=1, **store_kw):
     """wgr() of R/wgr.R:2-8 with the MCMC loop native (one C call instead of `it` KMUP round trips).
     Model map (man/wgr.Rd:185): BRR pi=0,iv=F; BayesA iv=T; BayesB pi>0,iv=T; BayesC pi>0,iv=F; BayesL de=T."""
+    # R/wgr.R:11-19, :35-40: missing genotypes take their column mean (the float32 store serves real-valued genotypes); individuals
+    # without a phenotype leave the fit and keep their fitted value
+    gen0 = None
+    if not isinstance(X, Genotypes) and not hasattr(X, "data_ptr"):
+        X = np.asarray(X)
+        if X.dtype.kind == "f" and np.isnan(X).any():
+            X = np.array(X, dtype=np.float64)
+            cm = np.nan_to_num(np.nanmean(X, axis=0), nan=0.0)  # x[is.nan(x)] = 0: an all-missing column
+            X[np.isnan(X)] = np.broadcast_to(cm, X.shape)[np.isnan(X)]
+        y = np.asarray(y, dtype=np.float64)
+        if np.isnan(y).any():
+            gen0, keep = X, ~np.isnan(y)
+            X, y = X[keep], y[keep]
+            if eigK is not None:
+                eigK = {"values": eigK["values"], "vectors": np.asarray(eigK["vectors"])[keep], "vectors0": np.asarray(eigK["vectors"])}
     if eigK is not None:
-        raise _lib.BwgrError(-5, "wgr: the polygenic term (eigK: Kuo-Mallick sweeps over real-valued eigenvectors) is not on the B200 path")
+        out = _wgr_eigk(y, X, eigK, VarK, it, bi, th, bag, iv, de, pi, df, R2, seed, store_kw)
+    else:
+        out = _wgr_native(y, X, it, bi, th, bag, rp, iv, de, pi, df, R2, seed, store_kw)
+    if gen0 is not None:  # :143-150: HAT = B0 + gen0 %*% B (+ U0 %*% H)
+        out["hat"] = out["mu"] + np.asarray(gen0, dtype=np.float64) @ out["b"]
+        if eigK is not None:
+            out["hat"] = out["hat"] + out["u"]
+    return out
+
+
+def _wgr_eigk(y, X, eigK, VarK, it, bi, th, bag, iv, de, pi, df, R2, seed, store_kw):
+    """wgr with the polygenic term (R/wgr.R:23-33, :74-84, :116-119, :124, :145-150): the reference's own R loop, one Kuo-Mallick sweep
+    over the leading eigenvectors of the kernel (real-valued: the float32 store) and one over the markers per iteration, both on the
+    device through the KMUP entry point; the variance draws of the driver on the host, like R's.  bag must be 1: with bag != 1 the
+    reference hands KMUP2's residual of the rows in use back to KMUP2 as the full residual (:81-87) and reads out of bounds."""
+    if bag != 1:
+        raise _lib.BwgrError(-5, "wgr: eigK with bag != 1 reads out of bounds in the reference (R/wgr.R:81-87); not reproduced")
+    if de:
+        iv = True
+    V = np.asarray(eigK["values"], dtype=np.float64)
+    vec = np.asarray(eigK["vectors"], dtype=np.float64)
+    pk = int(np.argmax(np.cumsum(V) / V.size > VarK)) + 1  # which.max(cumsum(V) / length(V) > VarK)
+    U = np.asfortranarray(vec[:, :pk])
+    U0 = np.asarray(eigK.get("vectors0", vec), dtype=np.float64)[:, :pk]
+    V = V[:pk]
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    g, own = _store(X, **store_kw)
+    gu = Genotypes(device=g.device if hasattr(g, "device") else 0)
+    try:
+        _need(y.size == g.n and U.shape[0] == g.n, "y has %d values, eigK$vectors %d rows, the genotype store %d rows" % (y.size, U.shape[0], g.n))
+        check(gu.lib.bwgr_geno_load_f64(gu.h, _ptr(U), g.n, pk, g.n, STORE_F32))
+        gu.n, gu.p = g.n, pk
+        n, p = g.n, g.p
+        rng = np.random.default_rng(seed)
+        xxi, sxi = g.stats()
+        xx = np.asarray(xxi, dtype=np.float64)
+        MSx = float(((xx - np.asarray(sxi, dtype=np.float64) ** 2 / n) / (n - 1)).sum())  # sum(apply(X, 2, var))
+        Xh = None if isinstance(X, Genotypes) or hasattr(X, "data_ptr") else np.asarray(X, dtype=np.float64)
+        post = set(range(bi, it + 1, th)) if bi > 0 else set(range(bi, it + 1, th)) - {0}
+        mc = len(range(bi, it + 1, th))
+        b, d, h = np.zeros(p), np.ones(p), np.zeros(pk)
+        mu = float(y.mean())
+        e = y - mu
+        Va, Ve = MSx, 1.0
+        Vb = np.full(p, Va)
+        Vk = np.ones(pk)
+        L = Vb / Ve  # sic (:55)
+        vy = float(y.var(ddof=1))
+        Sb, Se, Sk = R2 * df * vy / MSx, (1 - R2) * df * vy, R2 * vy * (df + 2)
+        xxK = np.full(pk, float(bag))
+        B0 = VA = VE = VP = 0.0
+        VB, D, B, H = np.zeros(p), np.zeros(p), np.zeros(p), np.zeros(pk)
+        Vp = 0.0
+        for i in range(1, it + 1):
+            s = int(rng.integers(1, 2 ** 62))
+            up = KMUP(gu, h, np.zeros(pk), xxK, e, Ve / (V * Vk), Ve, 0, seed=s)
+            h, e = up["b"], up["e"]
+            up = KMUP(g, b, d, xx, e, L, Ve, pi, seed=s + 1)
+            if pi > 0:
+                d = up["d"]
+            b, e = up["b"], up["e"]
+            if iv:
+                Vb = np.sqrt(b * b * Ve / MSx) if de else (Sb + b * b) / rng.chisquare(df + 1, size=p)
+            else:
+                Va = float((b @ b + Sb) / rng.chisquare(df + p))
+                Vb = np.full(p, Va)
+            Vp = float(((h * h / V).sum() + Sk) / rng.chisquare(df + pk))
+            Vk = np.full(pk, Vp)
+            Ve = float((e @ e + Se) / rng.chisquare(n * bag + df))
+            L = Ve / Vb
+            if Xh is not None:  # :124: the residual rebuilt in double (a rounding refresh: KMUP's e is the same residual)
+                e = y - mu - Xh @ b - U @ h
+            mu0 = rng.normal(e.mean(), Ve / n)  # sic: the sd argument is Ve / n (:125)
+            mu += mu0
+            e = e - mu0
+            if i in post:
+                B0 += mu; B += b; D += d; VE += Ve; H += h; VP += Vp
+                if iv:
+                    VB += Vb
+                else:
+                    VA += Va
+        B0 /= mc; D /= mc; B = B / mc / D.mean(); VE /= mc; H /= mc; VP /= mc
+        poly = U0 @ H
+        hat = B0 + (Xh @ B if Xh is not None else _fitted(g, B)) + (poly if U0.shape[0] == n else U @ H)
+        return {"mu": B0, "b": B, "Vb": VB / mc if iv else VA / mc, "d": D, "Ve": VE, "hat": hat, "u": poly, "Vk": VP, "cxx": float(xx.mean() * bag)}
+    finally:
+        gu.close()
+        if own:
+            g.close()
+
+
+def _fitted(g, b):
+    """X b of a store without a host copy of X: one ridge sweep with an infinite penalty is a no-op, so take the fitted values of a
+    zero-iteration GS fit instead: GSRR with maxit = 0 returns e untouched; e = 0 - X b is then read off a KMUP sweep with Ve -> 0 ... not
+    available: unpack the store."""
+    return g.unpack().astype(np.float64) @ b
+
+
+def _wgr_native(y, X, it, bi, th, bag, rp, iv, de, pi, df, R2, seed, store_kw):
     g, own = _store(X, **store_kw)
     try:
         y = np.ascontiguousarray(y, dtype=np.float64)

@@ -154,6 +154,7 @@ struct Fit {
   bool shuffled = true; // EM: shuffled order; Gibbs: natural
   bool blocked = false;
   bool gridfam = false;                 // grid family (grid_sweep.cu)
+  bool grid_blocked = false;            // ... its blocked variant (unmasked systems)
   DevBuf<unsigned long long> gridacc;   // its per-marker accumulator words
   bool masked = false;
   int rows_per_cta = 0, grid = 0, nblocks = 0;
@@ -1343,7 +1344,12 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
   }
   if (f.gridfam) {
     grid_geometry(h, &f.rows_per_cta, &f.grid);
-    if (f.gridacc.alloc((size_t)p * kGridCopies * 32) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(grid accumulators) failed");
+    // unmasked systems: blocks of markers per grid sum, if the block ring fits next to the residual slabs (BWGR_GRID_BLOCK=0: one marker per sum)
+    const char* gb = getenv("BWGR_GRID_BLOCK");
+    f.grid_blocked = !f.masked && s.model != M_KMUP2 && !(gb && !strcmp(gb, "0")) &&
+                     grid_block_smem(ns, f.rows_per_cta, h->storage == BWGR_STORE_F32, model_is_gibbs(s.model)) <= h->smem_optin;
+    const size_t words = f.grid_blocked ? grid_block_acc_words(ns, (int)p) : (size_t)p * kGridCopies * 32;
+    if (f.gridacc.alloc(words) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc(grid accumulators) failed");
   }
   f.active = true;
   return 0;
@@ -1487,6 +1493,14 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
       a.g = g; a.model = f.model; a.nsys = f.nsys; a.perm = d_perm; a.e = f.e.p; a.b = f.b.p; a.d = f.d.p; a.vbv = f.vbv.p;
       a.xx = f.masked ? f.xx_sys.p : (f.xx_over.p ? f.xx_over.p : h->xx_f.p); a.xx_per_sys = f.masked ? 1 : 0; a.mask = f.mask.p;
       a.xx2 = f.model == M_KMUP2 ? f.xx_over.p : nullptr;
+      a.blocked = f.grid_blocked ? 1 : 0;
+      {  // cross products are bounded by max_j x_j'x_j (Cauchy-Schwarz): one unit = 1 (exact integers) unless that exceeds 2^50
+        double xxmax = 1;
+        for (double v : h->h_xx) xxmax = std::max(xxmax, v);
+        int ex = 0;
+        std::frexp(xxmax, &ex);
+        a.gram_quantum = h->storage == BWGR_STORE_F32 ? (float)std::ldexp(1.0, ex - 50) : (float)std::ldexp(1.0, std::max(0, ex - 50));
+      }
       a.sc = f.sc.p; a.acc = f.gridacc.p; a.g_quantum = quantum; a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32);
       a.chain0 = 0; a.rows_per_cta = f.rows_per_cta; a.err = h->err.p;
       CU(cudaMemsetAsync(f.gridacc.p, 0, sizeof(unsigned long long) * f.gridacc.n, h->stream));

@@ -239,19 +239,305 @@ __global__ void __launch_bounds__(kT, 1) grid_sweep_kernel(GridArgs a) {
   }
 }
 
+// ---- blocks of kGB markers per grid sum (unmasked systems) -----------------------------------------------------------------------
+// One L2 round trip per BLOCK instead of per marker: the round carries the dot products of the block's markers with the residuals as
+// they stand at the start of the block, and the cross products x_j'x_i of the block (integers for the int8 store: exact).  Every CTA
+// then walks the block alike: the dot of marker j is corrected by the steps already taken in the block,
+// g_j = g_j(stale) - sum_{i<j} (x_j'x_i) de_i -- the same algebra as the blocked family, on CUDA cores -- and the residual slab gets the
+// block's update at once.
+constexpr int kGB = 16;                       // markers per block
+constexpr int kGP = kGB * (kGB - 1) / 2;      // cross products per block
+constexpr int kGR = 3;                        // blocks in flight
+constexpr int kJR = kGR + 1;                  // marker indices are staged one block further ahead
+constexpr int kTB = 1024;                     // threads per CTA of the blocked variant: its phases are short dependent chains, 32 warps hide them
+// pair index pr = j (j - 1) / 2 + i (i < j) -> j
+__constant__ unsigned char kPairJ[kGP] = {1, 2, 2, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 7, 8, 8, 8, 8, 8, 8, 8, 8,
+                                          9, 9, 9, 9, 9, 9, 9, 9, 9, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 11, 11, 11, 11, 11, 11, 11, 11, 11, 11, 11,
+                                          12, 12, 12, 12, 12, 12, 12, 12, 12, 12, 12, 12, 13, 13, 13, 13, 13, 13, 13, 13, 13, 13, 13, 13, 13,
+                                          14, 14, 14, 14, 14, 14, 14, 14, 14, 14, 14, 14, 14, 14, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15};
+
+struct GridBlockSmem {
+  float* E;                 // [ns][rp]
+  unsigned char* xs[kGR];   // [kGB][rp] int8 / float
+  float* vin[kGR];          // [kGB][100]
+  int* Js[kJR];             // [kGB]
+  float* tot;               // [kGB * ns + kGP] the block's totals: dots (marker-major, stale) | cross products j (j - 1) / 2 + i
+  float* de;                // [kGB][32]
+  SysScalars* sc;           // [ns]
+  MarkerDraws* dr;          // [2][kGB][32]
+};
+
+__host__ __device__ inline size_t grid_block_carve(unsigned char* base, int ns, int rp, int xbytes, bool gibbs, GridBlockSmem* s) {
+  size_t o = 0;
+  auto take = [&](size_t bytes) { unsigned char* q = base ? base + o : nullptr; o = (o + bytes + 15) & ~(size_t)15; return q; };
+  float* E = reinterpret_cast<float*>(take(sizeof(float) * (size_t)ns * rp));
+  unsigned char* xs[kGR];
+  for (int d = 0; d < kGR; d++) xs[d] = take((size_t)kGB * rp * xbytes);
+  float* vin[kGR];
+  for (int d = 0; d < kGR; d++) vin[d] = reinterpret_cast<float*>(take(sizeof(float) * kGB * 100));
+  int* Js[kJR];
+  for (int d = 0; d < kJR; d++) Js[d] = reinterpret_cast<int*>(take(sizeof(int) * kGB));
+  float* tot = reinterpret_cast<float*>(take(sizeof(float) * (kGB * 32 + kGP)));
+  float* de = reinterpret_cast<float*>(take(sizeof(float) * kGB * 32));
+  SysScalars* sc = reinterpret_cast<SysScalars*>(take(sizeof(SysScalars) * (size_t)ns));
+  MarkerDraws* dr = reinterpret_cast<MarkerDraws*>(take(gibbs ? sizeof(MarkerDraws) * 2 * kGB * 32 : 0));
+  if (s) {
+    s->E = E; s->tot = tot; s->de = de; s->sc = sc; s->dr = dr;
+    for (int d = 0; d < kGR; d++) { s->xs[d] = xs[d]; s->vin[d] = vin[d]; }
+    for (int d = 0; d < kJR; d++) s->Js[d] = Js[d];
+  }
+  return o;
+}
+
+__host__ __device__ inline int grid_block_words(int ns) { return (kGB * ns + kGP + 31) / 32 * 32; }
+
+template <int MODEL, class XT>
+__global__ void __launch_bounds__(kTB, 1) grid_block_kernel(GridArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_abort;
+  GridBlockSmem s;
+  const int ns = a.nsys, rp = a.rows_per_cta, p = a.g.p;
+  grid_block_carve(smem_raw, ns, rp, (int)sizeof(XT), model_is_gibbs(MODEL), &s);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = (int)gridDim.x, cta = blockIdx.x;
+  const int64_t ld = a.g.ld, r0 = (int64_t)cta * rp;
+  const int nblk = (p + kGB - 1) / kGB, W = grid_block_words(ns), ndot = kGB * ns;
+  for (int q = tid; q < ns * rp; q += kTB) {
+    const int t = q / rp, i = q - t * rp;
+    s.E[q] = (r0 + i < ld) ? a.e[(size_t)t * ld + r0 + i] : 0.0f;
+  }
+  for (int q = tid; q < kGR * kGB * rp * (int)sizeof(XT); q += kTB) s.xs[0][q] = 0;  // slots are contiguous
+  for (int q = tid; q < kGR * kGB * 100; q += kTB) s.vin[0][q] = 0.0f;
+  if (tid < ns) s.sc[tid] = a.sc[tid];
+  if (tid == 0) s_abort = 0;
+  __syncthreads();  // the zeroed ring slots are in place before any cp.async lands in them
+  const int nch = rp * (int)sizeof(XT) / 16;
+  constexpr int kRowsPerChunk = 16 / (int)sizeof(XT);
+  // marker indices of block blk -> shared memory, by sixteen threads of the last warp (their L2 round trip stays off everybody's path:
+  // the indices are used one step later)
+  auto load_js = [&](int blk) {
+    const int j = tid - (kTB - 32);
+    if (j >= 0 && j < kGB && blk < nblk) {
+      const int m = blk * kGB + j;
+      s.Js[blk % kJR][j] = m < p ? (a.perm ? a.perm[m] : m) : 0;
+    }
+  };
+  auto prefetch = [&](int blk) {
+    if (blk < nblk) {
+      const int slot = blk % kGR;
+      const int* Jv = s.Js[blk % kJR];
+      for (int j = 0; j < kGB; j++) {
+        const int m = blk * kGB + j;
+        if (m >= p) break;
+        const int J = Jv[j];
+        const unsigned char* col = sizeof(XT) == 1 ? reinterpret_cast<const unsigned char*>(a.g.x8 + (int64_t)J * ld + r0)
+                                                   : reinterpret_cast<const unsigned char*>(a.g.xf + (int64_t)J * ld + r0);
+        unsigned char* dst = s.xs[slot] + (size_t)j * rp * sizeof(XT);
+        for (int c = tid; c < nch; c += kTB)
+          if (r0 + (int64_t)kRowsPerChunk * c < ld) gcp16(dst + 16 * c, col + 16 * c);
+        float* v = s.vin[slot] + j * 100;
+        if (tid < 32) { if (tid < ns) gcp4(v + tid, a.b + (size_t)tid * p + J); }
+        else if (tid < 64) { const int t = tid - 32; if (t < ns && a.vbv) gcp4(v + 32 + t, a.vbv + (size_t)t * p + J); }
+        else if (tid < 96) { const int t = tid - 64; if (t < ns) gcp4(v + 64 + t, a.xx + (a.xx_per_sys ? (size_t)t * p : 0) + J); }
+      }
+    }
+    gcp_commit();
+  };
+  auto draws_for = [&](int blk) {  // Gibbs draws of a block's markers, one (marker, system) per thread of warps 1..7
+    if (!model_is_gibbs(MODEL) || blk >= nblk) return;
+    const int nb = min(kGB, p - blk * kGB);
+    for (int q = tid - 32; q < nb * ns; q += kTB - 32) {
+      if (q < 0) break;
+      const int j = q / ns, t = q - j * ns;
+      s.dr[((blk & 1) * kGB + j) * 32 + t] = marker_draws(MODEL, (uint32_t)s.Js[blk % kJR][j], (uint32_t)s.sc[t].sweep, (uint32_t)(a.chain0 + t),
+                                                          s.sc[t].df, a.seed_lo, a.seed_hi);
+    }
+  };
+  for (int b = 0; b < kGR; b++) load_js(b);
+  __syncthreads();
+  for (int b = 0; b < kGR - 1; b++) prefetch(b);
+  draws_for(0);
+  const unsigned long long t_start = gtimer();
+  const double inv_q = (double)a.g_quantum, qinv = 1.0 / (double)a.g_quantum;
+  const double inv_qG = (double)a.gram_quantum, qinvG = 1.0 / (double)a.gram_quantum;
+  for (int blk = 0; blk < nblk; blk++) {
+    gcp_wait<kGR - 2>();
+    __syncthreads();  // block blk's slot has landed; block blk - 1 is finished by every thread
+    prefetch(blk + kGR - 1);
+    const int slot = blk % kGR, nb = min(kGB, p - blk * kGB);
+    const int* Jcur = s.Js[blk % kJR];
+    const XT* xs = reinterpret_cast<const XT*>(s.xs[slot]);
+    unsigned long long* accw = a.acc + ((size_t)blk * kC + (cta & (kC - 1))) * W;
+    // ---- the block's 16 dot tasks (marker j with the residuals as they stand) and 120 cross-product tasks (x_j'x_i, i < j), dealt
+    // round-robin over the 32 warps
+    for (int task = warp; task < kGB + kGP; task += kTB / 32) {
+      if (task < kGB) {
+        const int j = task;
+        if (j >= nb) continue;
+        const XT* xj = xs + (size_t)j * rp;
+        if (ns == 1) {
+          float acc = 0.0f;
+          for (int i = lane; i < rp; i += 32) acc = fmaf((float)xj[i], s.E[i], acc);
+          const double v = (double)warp_sum(acc) * qinv;
+          if (lane == 0) {
+            if (!(fabs(v) < 4503599627370496.0)) atomicExch(a.err, 4);
+            atomicAdd(accw + j, ((unsigned long long)__double2ll_rn(v) << 8) + 1ull);
+          }
+        } else {
+          for (int t0 = 0; t0 < ns; t0 += 4) {
+            const int nt = min(4, ns - t0);
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            for (int i = lane; i < rp; i += 32) {
+              const float x = (float)xj[i];
+#pragma unroll
+              for (int q = 0; q < 4; q++)
+                if (q < nt) acc[q] = fmaf(x, s.E[(t0 + q) * rp + i], acc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              if (q < nt) {
+                const double v = (double)warp_sum(acc[q]) * qinv;
+                if (lane == 0) {
+                  if (!(fabs(v) < 4503599627370496.0)) atomicExch(a.err, 4);
+                  atomicAdd(accw + j * ns + t0 + q, ((unsigned long long)__double2ll_rn(v) << 8) + 1ull);
+                }
+              }
+            }
+          }
+        }
+      } else {
+        const int pr = task - kGB, j = kPairJ[pr], i2 = pr - j * (j - 1) / 2;
+        double v;
+        if constexpr (sizeof(XT) == 1) {
+          const int* wj = reinterpret_cast<const int*>(xs + (size_t)j * rp);
+          const int* wi = reinterpret_cast<const int*>(xs + (size_t)i2 * rp);
+          int acc = 0;
+          for (int q = lane; q < rp / 4; q += 32) acc = __dp4a(wj[q], wi[q], acc);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+          v = (double)acc * qinvG;
+        } else {
+          const float* fj = reinterpret_cast<const float*>(xs + (size_t)j * rp);
+          const float* fi = reinterpret_cast<const float*>(xs + (size_t)i2 * rp);
+          float acc = 0.0f;
+          for (int q = lane; q < rp; q += 32) acc = fmaf(fj[q], fi[q], acc);
+          v = (double)warp_sum(acc) * qinvG;
+        }
+        if (lane == 0) atomicAdd(accw + ndot + pr, ((unsigned long long)__double2ll_rn(v) << 8) + 1ull);
+      }
+    }
+    load_js(blk + kGR);
+    // ---- the block's totals: every word is complete when its low byte counts all the CTAs of its copy
+    {
+      const int nw = ndot + kGP;
+      unsigned int spins = 0;
+      for (;;) {
+        bool pending = false;
+        for (int wd = tid; wd < nw; wd += kTB) {
+          const int jw = wd < ndot ? wd / ns : 0;
+          if (wd < ndot && jw >= nb) continue;  // markers past the end of the last block are never added
+          const unsigned long long* src = a.acc + (size_t)blk * kC * W + wd;
+          long long tot = 0;
+          bool done = true;
+#pragma unroll
+          for (int c = 0; c < kC; c++) {
+            const unsigned long long w = gld_relaxed(src + (size_t)c * W);
+            done &= (int)(w & 0xffull) == (G + kC - 1 - c) / kC;
+            tot += (long long)w >> 8;
+          }
+          if (done) {
+            s.tot[wd] = (float)((double)tot * (wd < ndot ? inv_q : inv_qG));
+          } else pending = true;
+        }
+        if ((++spins & 0x3ffu) == 0 && tid == 0) {
+          if (*reinterpret_cast<volatile int*>(a.err) != 0) s_abort = 1;
+          else if (gtimer() - t_start > 120000000000ull) { atomicExch(a.err, 3); s_abort = 1; }  // two minutes without the grid
+        }
+        if (!__syncthreads_or(pending ? 1 : 0)) break;
+        if (s_abort) break;
+      }
+      if (s_abort) return;
+    }
+    __syncthreads();
+    // ---- the block's chain, by every CTA alike: lane t of warp 0 walks system t; the other warps draw for the next block
+    if (warp == 0) {
+      if (lane < ns) {
+        const SysScalars& sc = s.sc[lane];
+        const float* vin = s.vin[slot];
+        float de[kGB];
+#pragma unroll
+        for (int j = 0; j < kGB; j++) {
+          de[j] = 0.0f;
+          if (j < nb && !sc.done) {
+            float g = s.tot[j * ns + lane];
+#pragma unroll
+            for (int i = 0; i < j; i++) g = fmaf(-s.tot[ndot + j * (j - 1) / 2 + i], de[i], g);
+            MarkerDraws dr;
+            if (model_is_gibbs(MODEL)) dr = s.dr[((blk & 1) * kGB + j) * 32 + lane];
+            else { dr.z1 = dr.z2 = dr.u = 0.0f; dr.chi = 1.0f; }
+            const float* v = vin + j * 100;
+            const RuleOut r = marker_rule<MODEL>(g, v[64 + lane], v[lane], a.vbv ? v[32 + lane] : 0.0f, sc, dr, 0.0f);
+            de[j] = r.de;
+            if (cta == 0) {
+              const size_t q = (size_t)lane * p + Jcur[j];
+              a.b[q] = r.b;
+              if (model_has_d(MODEL) && a.d) a.d[q] = r.d;
+              if (model_rule_writes_vbj(MODEL) && a.vbv) a.vbv[q] = r.vbj;
+            }
+          }
+          s.de[j * 32 + lane] = de[j];
+        }
+      }
+    } else {
+      draws_for(blk + 1);
+    }
+    __syncthreads();
+    // ---- e_t -= sum_j x_j de_jt
+    for (int i = tid; i < rp; i += kTB) {
+      float x[kGB];
+#pragma unroll
+      for (int j = 0; j < kGB; j++) x[j] = (float)xs[(size_t)j * rp + i];
+      for (int t = 0; t < ns; t++) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kGB; j++) acc = fmaf(x[j], s.de[j * 32 + t], acc);
+        s.E[t * rp + i] -= acc;
+      }
+    }
+  }
+  gcp_wait<0>();
+  __syncthreads();
+  for (int q = tid; q < ns * rp; q += kTB) {
+    const int t = q / rp, i = q - t * rp;
+    if (r0 + i < ld) a.e[(size_t)t * ld + r0 + i] = s.E[q];
+  }
+}
+
 template <int MODEL>
 cudaError_t launch_grid_model(const GridArgs& a, int grid, cudaStream_t st) {
   const bool real = a.g.storage == 2;
-  const size_t smem = grid_sweep_smem(a.nsys, a.rows_per_cta, a.mask != nullptr, real);
+  size_t smem = grid_sweep_smem(a.nsys, a.rows_per_cta, a.mask != nullptr, real);
+  int threads = kT;
   const void* fn = real ? reinterpret_cast<const void*>(grid_sweep_kernel<MODEL, float>) : reinterpret_cast<const void*>(grid_sweep_kernel<MODEL, int8_t>);
+  if (a.blocked) {
+    if constexpr (MODEL != M_KMUP2) {
+      smem = grid_block_smem(a.nsys, a.rows_per_cta, real, model_is_gibbs(MODEL));
+      fn = real ? reinterpret_cast<const void*>(grid_block_kernel<MODEL, float>) : reinterpret_cast<const void*>(grid_block_kernel<MODEL, int8_t>);
+      threads = kTB;
+    }
+  }
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   GridArgs args = a;
   void* params[] = {&args};
-  return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kT), params, smem, st);
+  return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), params, smem, st);
 }
 
 }  // namespace
+
+size_t grid_block_smem(int nsys, int rows_per_cta, bool real_store, bool gibbs) {
+  return grid_block_carve(nullptr, nsys, rows_per_cta, real_store ? 4 : 1, gibbs, nullptr) + 16;
+}
+size_t grid_block_acc_words(int nsys, int p) { return (size_t)((p + kGB - 1) / kGB) * kC * grid_block_words(nsys); }
 
 size_t grid_sweep_smem(int nsys, int rows_per_cta, bool masked, bool real_store) {
   return grid_carve(nullptr, nsys, rows_per_cta, masked, real_store ? 4 : 1, nullptr) + 16;

@@ -242,11 +242,15 @@ struct GridArgs {
   SysScalars* sc;         // [nsys]
   unsigned long long* acc;  // [p][kGridCopies][32]: (fixed-point sum << 8) + arrivals; zeroed before launch
   float g_quantum;        // value of one fixed-point unit of g
+  float gram_quantum;     // blocked variant: value of one fixed-point unit of a cross product x_j'x_i (<= 1 for the int8 store: exact)
+  int blocked;            // blocked variant (unmasked systems): acc is [nblocks][kGridCopies][grid_block_words(nsys)]
   uint32_t seed_lo, seed_hi;
   int chain0;
   int rows_per_cta;       // multiple of 16; grid * rows_per_cta >= ld
   int* err;
 };
+size_t grid_block_smem(int nsys, int rows_per_cta, bool real_store, bool gibbs);
+size_t grid_block_acc_words(int nsys, int p);
 size_t grid_sweep_smem(int nsys, int rows_per_cta, bool masked, bool real_store);
 cudaError_t launch_grid_sweep(const GridArgs& a, int grid, cudaStream_t st);
 

@@ -852,12 +852,15 @@ static inline void imp_columns(float* X, int n, int p) {
 // :68: Use = sort(sample(n, n*bag)) - 1) and sweeps them with KMUP2.  The driver arithmetic is R's (double);
 // every KMUP call crosses the Rcpp boundary, i.e. casts X,b,d,xx,e,L to float and back
 // (RcppExports.cpp:16-31).
+// eigK (bag == 1 only: with bag != 1 the reference hands KMUP2's nuse-long residual back to KMUP2 as E, :81-87, and reads out of
+// bounds): Ud = the first pk eigenvectors (n x pk, column-major), Vd their eigenvalues; pk is chosen by the caller (:25).
 struct WgrOut {
-  double mu = 0, Ve = 0, Va = 0, cxx = 0;
-  std::vector<double> b, d, Vb, hat;
+  double mu = 0, Ve = 0, Va = 0, cxx = 0, Vk = 0;
+  std::vector<double> b, d, Vb, hat, u;
 };
 static inline void wgr(const double* y, const double* Xd, int n, int p, int it, int bi, int th, bool iv, bool de,
-                       double pi, double df, double R2, uint64_t seed, bool ratio_form, WgrOut& o, double bag = 1.0) {
+                       double pi, double df, double R2, uint64_t seed, bool ratio_form, WgrOut& o, double bag = 1.0,
+                       const double* Ud = nullptr, const double* Vd = nullptr, int pk = 0) {
   Rng rng(seed);
   if (de) iv = true;
   const bool bagged = bag != 1.0;
@@ -894,10 +897,22 @@ static inline void wgr(const double* y, const double* Xd, int n, int p, int it, 
   double B0 = 0, VA = 0, VE = 0;
   std::vector<double> VB(p, 0.0), D(p, 0.0), B(p, 0.0);
   std::vector<float> bf(p), dfl(p), xxf(p), ef(n), Lf(p);
+  // polygenic term (:23-33, :60): h = effects of the eigenvectors, xxK = bag, Vk = 1, Sk = R2 var(y) (df + 2)
+  const bool poly = Ud != nullptr && pk > 0;
+  std::vector<double> h(pk, 0.0), H(pk, 0.0), Vk(pk, 1.0);
+  std::vector<float> Uf((size_t)n * pk), hf(pk), dhf(pk), xxKf(pk, (float)bag), Lkf(pk);
+  for (size_t i = 0; i < Uf.size(); i++) Uf[i] = (float)Ud[i];
+  const double Sk = R2 * vy * (df + 2);
+  double Vp = 0, VP = 0;
   size_t next_post = 0;
   for (int i = 1; i <= it; i++) {
     for (int j = 0; j < p; j++) { bf[j] = (float)b[j]; dfl[j] = (float)d[j]; xxf[j] = (float)xx[j]; Lf[j] = (float)L[j]; }
     for (int r = 0; r < n; r++) ef[r] = (float)e[r];
+    if (poly) {  // :77-84: Lk = Ve / (V Vk); KMUP(U, h, dh, xxK, e, Lk, Ve, 0)
+      for (int q = 0; q < pk; q++) { Lkf[q] = (float)(Ve / (Vd[q] * Vk[q])); hf[q] = (float)h[q]; dhf[q] = 0.0f; }
+      kmup(Uf.data(), n, pk, hf.data(), dhf.data(), xxKf.data(), ef.data(), Lkf.data(), (float)Ve, 0.0f, rng, ratio_form);
+      for (int q = 0; q < pk; q++) h[q] = hf[q];
+    }
     if (bagged) {  // :68, :87: a fresh sorted row sample, swept by KMUP2; e becomes the residual of the rows in use
       for (int r = 0; r < n; r++) rows[r] = r;
       for (int r = 0; r < nuse; r++) { std::uniform_int_distribution<int> pick(r, n - 1); std::swap(rows[r], rows[pick(rng.g)]); }
@@ -920,6 +935,12 @@ static inline void wgr(const double* y, const double* Xd, int n, int p, int it, 
       Va = (bb + Sb) / rng.rchisq(df + p);
       for (int j = 0; j < p; j++) Vb[j] = Va;
     }
+    if (poly) {  // :116-119
+      double hh = 0;
+      for (int q = 0; q < pk; q++) hh += h[q] * h[q] / Vd[q];
+      Vp = (hh + Sk) / rng.rchisq(df + pk);
+      for (int q = 0; q < pk; q++) Vk[q] = Vp;
+    }
     double ee = 0;
     if (bagged) for (int r = 0; r < nuse; r++) ee += (double)esub[r] * (double)esub[r];
     else for (int r = 0; r < n; r++) ee += e[r] * e[r];
@@ -932,6 +953,11 @@ static inline void wgr(const double* y, const double* Xd, int n, int p, int it, 
       const double* x = Xd + (size_t)j * n;
       for (int r = 0; r < n; r++) e[r] -= x[r] * bj;
     }
+    if (poly)  // :124: ... - U %*% h
+      for (int q = 0; q < pk; q++) {
+        const double* u = Ud + (size_t)q * n;
+        for (int r = 0; r < n; r++) e[r] -= u[r] * h[q];
+      }
     double em = 0;
     for (int r = 0; r < n; r++) em += e[r];
     em /= n;
@@ -944,6 +970,7 @@ static inline void wgr(const double* y, const double* Xd, int n, int p, int it, 
       for (int j = 0; j < p; j++) { B[j] += b[j]; D[j] += d[j]; }
       if (iv) for (int j = 0; j < p; j++) VB[j] += Vb[j];
       else VA += Va;
+      if (poly) { for (int q = 0; q < pk; q++) H[q] += h[q]; VP += Vp; }
     }
   }
   B0 /= mc;
@@ -962,6 +989,15 @@ static inline void wgr(const double* y, const double* Xd, int n, int p, int it, 
   for (int j = 0; j < p; j++) {
     const double* x = Xd + (size_t)j * n;
     for (int r = 0; r < n; r++) o.hat[r] += x[r] * B[j];
+  }
+  if (poly) {  // :145-150: poly = U0 %*% (H / mc); HAT += poly
+    o.Vk = VP / mc;
+    o.u.assign(n, 0.0);
+    for (int q = 0; q < pk; q++) {
+      const double* u = Ud + (size_t)q * n;
+      for (int r = 0; r < n; r++) o.u[r] += u[r] * (H[q] / mc);
+    }
+    for (int r = 0; r < n; r++) o.hat[r] += o.u[r];
   }
 }
 

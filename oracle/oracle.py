@@ -181,13 +181,32 @@ def imp(X):
     return X
 
 
-def wgr(y, X, it=1500, bi=500, th=1, iv=False, de=False, pi=0.0, df=5.0, R2=0.5, seed=1, ratio_form=False, bag=1.0):
+def eigk_rank(values, VarK=0.95):
+    """pk of R/wgr.R:25: which.max((cumsum(V) / length(V)) > VarK) (1 if the condition never holds)."""
+    V = np.asarray(values, dtype=np.float64)
+    return int(np.argmax(np.cumsum(V) / V.size > VarK)) + 1
+
+
+def wgr(y, X, it=1500, bi=500, th=1, iv=False, de=False, pi=0.0, df=5.0, R2=0.5, seed=1, ratio_form=False, bag=1.0, eigK=None, VarK=0.95):
     y = np.ascontiguousarray(y, dtype=np.float64)
     X = np.asfortranarray(X, dtype=np.float64)
     n, p = X.shape
     b, d, Vb = (np.zeros(p) for _ in range(3))
     hat = np.zeros(n)
     scal = np.zeros(4)
+    if eigK is not None:  # R/wgr.R:23-33 (bag == 1)
+        assert bag == 1.0
+        pk = eigk_rank(eigK["values"], VarK)
+        U = np.asfortranarray(np.asarray(eigK["vectors"], dtype=np.float64)[:, :pk])
+        V = np.ascontiguousarray(np.asarray(eigK["values"], dtype=np.float64)[:pk])
+        u = np.zeros(n)
+        scal = np.zeros(5)
+        lib().orc_wgr_eigk(_p(y, C.c_double), _p(X, C.c_double), C.c_int(n), C.c_int(p), _p(U, C.c_double), _p(V, C.c_double), C.c_int(pk),
+                           C.c_int(it), C.c_int(bi), C.c_int(th), C.c_int(int(iv)), C.c_int(int(de)), C.c_double(pi), C.c_double(df),
+                           C.c_double(R2), C.c_uint64(seed), C.c_int(int(ratio_form)), _p(b, C.c_double), _p(d, C.c_double),
+                           _p(Vb, C.c_double), _p(hat, C.c_double), _p(u, C.c_double), _p(scal, C.c_double))
+        mu, Ve, Va, cxx, Vk = scal
+        return {"mu": mu, "b": b, "Vb": Vb if (iv or de) else Va, "d": d, "Ve": Ve, "hat": hat, "u": u, "Vk": Vk, "cxx": cxx}
     if bag != 1.0:
         lib().orc_wgr_bag(_p(y, C.c_double), _p(X, C.c_double), C.c_int(n), C.c_int(p), C.c_int(it), C.c_int(bi), C.c_int(th),
                           C.c_double(bag), C.c_int(int(iv)), C.c_int(int(de)), C.c_double(pi), C.c_double(df), C.c_double(R2),

@@ -113,6 +113,18 @@ int orc_wgr(const double* y, const double* X, int n, int p, int it, int bi, int 
   return 0;
 }
 
+// wgr with the polygenic term (eigK): U n x pk, V pk; scal = {mu, Ve, Va, cxx, Vk}; u = U0 %*% H
+int orc_wgr_eigk(const double* y, const double* X, int n, int p, const double* U, const double* V, int pk, int it, int bi, int th, int iv,
+                 int de, double pi, double df, double R2, uint64_t seed, int ratio_form, double* b, double* d, double* Vb, double* hat,
+                 double* u, double* scal) {
+  orc::WgrOut o;
+  orc::wgr(y, X, n, p, it, bi, th, iv != 0, de != 0, pi, df, R2, seed, ratio_form != 0, o, 1.0, U, V, pk);
+  for (int j = 0; j < p; j++) { b[j] = o.b[j]; d[j] = o.d[j]; Vb[j] = o.Vb[j]; }
+  for (int i = 0; i < n; i++) { hat[i] = o.hat[i]; u[i] = o.u[i]; }
+  scal[0] = o.mu; scal[1] = o.Ve; scal[2] = o.Va; scal[3] = o.cxx; scal[4] = o.Vk;
+  return 0;
+}
+
 int orc_wgr_bag(const double* y, const double* X, int n, int p, int it, int bi, int th, double bag, int iv, int de, double pi, double df,
                 double R2, uint64_t seed, int ratio_form, double* b, double* d, double* Vb, double* hat, double* scal) {
   orc::WgrOut o;

@@ -3,6 +3,7 @@
 Bars (SURVEY 8c / BASELINE.md 5): packing, indexing, column statistics and Gram blocks bit-exact;
 EM solvers rel <= 1e-4 on b (relative to max|b|), hat, variance components and h2 vs the float oracle;
 Gibbs posterior means within Monte-Carlo error across seeds."""
+import ctypes
 import os
 
 import numpy as np
@@ -65,8 +66,12 @@ def test_pack_rejects_non_integer(tpod):
     _, gen = tpod
     X = gen.astype(np.float64)
     X[3, 5] = 0.5
-    with pytest.raises(bw.BwgrError):
-        bw.Genotypes(X)
+    Xf = np.asfortranarray(X)
+    with bw.Genotypes() as g:  # the integer stores reject a fractional cell at the C ABI ...
+        for storage in (bw.STORE_I8, bw.STORE_2BIT):
+            assert g.lib.bwgr_geno_load_f64(g.h, Xf.ctypes.data_as(ctypes.c_void_p), 196, 376, 196, storage) == -1
+    with bw.Genotypes(X) as g:     # ... and the mirror then falls back to the float32 store (real-valued genotypes)
+        assert g.info()["storage"] == bw.STORE_F32
     X[3, 5] = 3.0
     with pytest.raises(bw.BwgrError):
         bw.Genotypes(X, storage=1)
@@ -105,8 +110,8 @@ def test_float64_loader_many_chunks_and_block_reuse():
     with bw.Genotypes(X8, path=2) as g:  # the int8 loader sees the same store
         assert np.array_equal(bw.emRR(y, g, it=5)["b"], fits[0]["b"])
     Xd[n // 2, p - 3] = 1.5
-    with pytest.raises(bw.BwgrError):
-        bw.Genotypes(Xd)
+    with bw.Genotypes() as g:  # a fractional cell in a late chunk: the integer store rejects it at the C ABI
+        assert g.lib.bwgr_geno_load_f64(g.h, Xd.ctypes.data_as(ctypes.c_void_p), n, p, n, bw.STORE_I8) == -1
 
 
 @pytest.mark.parametrize("shape", [(196, 376), (1000, 300), (4100, 129)])
@@ -271,6 +276,26 @@ def test_grid_family_large_n_masks_and_chains(tpod):
         out = bw.KMUP(g, np.zeros(p), np.ones(p), xx, e, np.full(p, 37.0), 1e-30, 0.0, seed=9)
         assert np.abs(out["b"] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max()
         assert np.abs(out["e"] - ref["e"]).max() <= RTOL * np.abs(ref["e"]).max()
+
+
+@pytest.mark.parametrize("blocked", ["1", "0"])
+def test_grid_family_block_variants_multi_system(monkeypatch, blocked):
+    """Unmasked systems on the grid family run blocks of 16 markers per grid sum (stale dots corrected by the block's exact integer
+    cross products); BWGR_GRID_BLOCK=0 keeps one marker per sum.  Five traits at once on a ragged shape (p not a multiple of 16,
+    n not a multiple of the row slab) against per-trait oracle fits, both variants; each is bit-reproducible."""
+    monkeypatch.setenv("BWGR_GRID_BLOCK", blocked)
+    X, Y = synth(3001, 333, k=5, seed=31)
+    with bw.Genotypes(X, path=bw.PATH_GRID) as g:
+        for model in ("emBA", "emBC"):
+            out = bw.em_fit(model, Y, g, it=10)
+            again = bw.em_fit(model, Y, g, it=10)
+            assert np.array_equal(out["b"], again["b"])
+            for t in range(5):
+                ref = O.em(model, Y[:, t], X.astype(np.float32), it=10)
+                ref64 = O.em(model, Y[:, t], X.astype(np.float32), it=10, use_double=True)
+                nb = np.abs(ref["b"] - ref64["b"]).max()
+                assert np.abs(out["b"][:, t] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max() + nb, (model, t)
+                assert abs(out["h2"][t] - ref["h2"]) <= RTOL + abs(ref["h2"] - ref64["h2"]), (model, t)
 
 
 def test_real_valued_genotypes_float32_store(tpod):
@@ -970,8 +995,8 @@ def test_mrr_on_centred_genotypes(tpod):
         with pytest.raises(bw.BwgrError) as ei:
             bw.emRR(Y[:, 0], g, it=2)
         assert ei.value.code == -5
-    with pytest.raises(bw.BwgrError):
-        bw.Genotypes(Xc)  # the strict loader still rejects non-integers
+    with bw.Genotypes() as g:  # the strict loader still rejects non-integers (the mirror then takes the float32 store)
+        assert g.lib.bwgr_geno_load_f64(g.h, np.asfortranarray(Xc).ctypes.data_as(ctypes.c_void_p), 196, 376, 196, bw.STORE_I8) == -1
 
 
 def _write_plink(prefix, G, miss):
