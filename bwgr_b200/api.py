@@ -505,7 +505,7 @@ def _wgr_eigk(y, X, eigK, VarK, it, bi, th, bag, iv, de, pi, df, R2, seed, store
     V = V[:pk]
     y = np.ascontiguousarray(y, dtype=np.float64)
     g, own = _store(X, **store_kw)
-    gu = Genotypes(device=g.device if hasattr(g, "device") else 0)
+    gu = Genotypes(device=store_kw.get("device", 0))
     try:
         _need(y.size == g.n and U.shape[0] == g.n, "y has %d values, eigK$vectors %d rows, the genotype store %d rows" % (y.size, U.shape[0], g.n))
         check(gu.lib.bwgr_geno_load_f64(gu.h, _ptr(U), g.n, pk, g.n, STORE_F32))
@@ -516,8 +516,8 @@ def _wgr_eigk(y, X, eigK, VarK, it, bi, th, bag, iv, de, pi, df, R2, seed, store
         xx = np.asarray(xxi, dtype=np.float64)
         MSx = float(((xx - np.asarray(sxi, dtype=np.float64) ** 2 / n) / (n - 1)).sum())  # sum(apply(X, 2, var))
         Xh = None if isinstance(X, Genotypes) or hasattr(X, "data_ptr") else np.asarray(X, dtype=np.float64)
-        post = set(range(bi, it + 1, th)) if bi > 0 else set(range(bi, it + 1, th)) - {0}
-        mc = len(range(bi, it + 1, th))
+        post = set(range(bi, it + 1, th))  # seq(bi, it, th)
+        mc = len(post)
         b, d, h = np.zeros(p), np.ones(p), np.zeros(pk)
         mu = float(y.mean())
         e = y - mu
@@ -570,9 +570,9 @@ def _wgr_eigk(y, X, eigK, VarK, it, bi, th, bag, iv, de, pi, df, R2, seed, store
 
 
 def _fitted(g, b):
-    """X b of a store without a host copy of X: one ridge sweep with an infinite penalty is a no-op, so take the fitted values of a
-    zero-iteration GS fit instead: GSRR with maxit = 0 returns e untouched; e = 0 - X b is then read off a KMUP sweep with Ve -> 0 ... not
-    available: unpack the store."""
+    """X b for a store handed over without a host copy of X (integer stores only)."""
+    if g.info()["storage"] == STORE_F32:
+        raise _lib.BwgrError(-5, "wgr(eigK): pass the genotype matrix, not a float32 store, to get fitted values")
     return g.unpack().astype(np.float64) @ b
 
 

@@ -914,6 +914,50 @@ def test_wgr_bagged(tpod, mode):
     assert np.isclose(gpu[0]["cxx"], ora[0]["cxx"])
 
 
+def test_wgr_polygenic_term_and_missing_values(tpod):
+    """wgr(eigK = eigen(K)) (R/wgr.R:23-33, :74-84, :116-119, :124, :145-150): one Kuo-Mallick sweep over the leading eigenvectors of a
+    kernel (real-valued: the float32 store) and one over the markers per iteration, both through the device KMUP entry point, the
+    driver's variance draws on the host like R's -- posterior means vs the oracle's restatement within Monte-Carlo error.  Then wgr's own
+    handling of missing values (:11-19, :35-40): NA genotypes take the column mean, individuals without a phenotype leave the fit and
+    keep a fitted value."""
+    y, gen = tpod
+    X = gen.astype(np.float64)
+    Z = X - X.mean(0)
+    K = Z @ Z.T
+    K /= np.diag(K).mean()
+    val, vec = np.linalg.eigh(K)
+    eigK = {"values": val[::-1].copy(), "vectors": vec[:, ::-1].copy()}
+    pk = O.eigk_rank(eigK["values"], 0.5)
+    assert 1 < pk < 196
+    kw = dict(pi=0.9, iv=True, eigK=eigK, VarK=0.5)
+    seeds = range(6)
+    ora = [O.wgr(y, X, it=500, bi=150, seed=50 + s, ratio_form=True, **kw) for s in seeds]
+    gpu = [bw.wgr(y, X, it=500, bi=150, seed=70 + s, **kw) for s in seeds]
+    for key in ("mu", "Ve", "Vk"):
+        a = np.array([r[key] for r in ora]); b = np.array([r[key] for r in gpu])
+        se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+        assert abs(a.mean() - b.mean()) <= 4 * se + 2e-2 * abs(a.mean()), (key, a.mean(), b.mean(), se)
+    for key in ("hat", "u"):
+        A = np.mean([r[key] for r in ora], 0); B = np.mean([r[key] for r in gpu], 0)
+        A1 = np.mean([r[key] for r in ora[:3]], 0); A2 = np.mean([r[key] for r in ora[3:]], 0)
+        assert np.corrcoef(A, B)[0, 1] > min(0.99, np.corrcoef(A1, A2)[0, 1] - 0.01), key
+    da = np.mean([r["d"].mean() for r in ora]); db = np.mean([r["d"].mean() for r in gpu])
+    assert abs(da - db) < 0.03
+    assert np.isclose(gpu[0]["cxx"], ora[0]["cxx"])
+    with pytest.raises(bw.BwgrError):
+        bw.wgr(y, X, it=10, bi=2, bag=0.5, eigK=eigK)
+    # missing values: the fit on (imputed X, observed rows) is the fit wgr makes itself
+    rng = np.random.default_rng(9)
+    Xn = X.copy(); Xn[rng.random(X.shape) < 0.02] = np.nan
+    yn = y.copy(); yn[[3, 50, 120]] = np.nan
+    Xi = np.where(np.isnan(Xn), np.nanmean(Xn, axis=0)[None, :], Xn)
+    keep = ~np.isnan(yn)
+    a = bw.wgr(yn, Xn, it=300, bi=100, seed=5)
+    b = bw.wgr(yn[keep], Xi[keep], it=300, bi=100, seed=5)
+    assert np.array_equal(a["b"], b["b"]) and a["hat"].shape == (196,) and np.allclose(a["hat"][keep], b["hat"], rtol=0, atol=1e-4)
+    assert np.allclose(a["hat"], a["mu"] + Xi @ a["b"])
+
+
 @pytest.mark.parametrize("path", [1, 2])
 @pytest.mark.parametrize("which", ["GSRR", "GSFLM"])
 def test_gs_warm_start_solvers(tpod, which, path):
