@@ -515,12 +515,12 @@ def _wgr_eigk(y, X, eigK, VarK, it, bi, th, bag, iv, de, pi, df, R2, seed, store
         xxi, sxi = g.stats()
         xx = np.asarray(xxi, dtype=np.float64)
         MSx = float(((xx - np.asarray(sxi, dtype=np.float64) ** 2 / n) / (n - 1)).sum())  # sum(apply(X, 2, var))
-        Xh = None if isinstance(X, Genotypes) or hasattr(X, "data_ptr") else np.asarray(X, dtype=np.float64)
         post = set(range(bi, it + 1, th))  # seq(bi, it, th)
         mc = len(post)
         b, d, h = np.zeros(p), np.ones(p), np.zeros(pk)
         mu = float(y.mean())
         e = y - mu
+        xb, uh = np.zeros(n), np.zeros(n)  # X b and U h, followed through the residual: a sweep changes e by -(change of its fitted values)
         Va, Ve = MSx, 1.0
         Vb = np.full(p, Va)
         Vk = np.ones(pk)
@@ -529,13 +529,15 @@ def _wgr_eigk(y, X, eigK, VarK, it, bi, th, bag, iv, de, pi, df, R2, seed, store
         Sb, Se, Sk = R2 * df * vy / MSx, (1 - R2) * df * vy, R2 * vy * (df + 2)
         xxK = np.full(pk, float(bag))
         B0 = VA = VE = VP = 0.0
-        VB, D, B, H = np.zeros(p), np.zeros(p), np.zeros(p), np.zeros(pk)
+        VB, D, B, H, XB = np.zeros(p), np.zeros(p), np.zeros(p), np.zeros(pk), np.zeros(n)
         Vp = 0.0
         for i in range(1, it + 1):
             s = int(rng.integers(1, 2 ** 62))
             up = KMUP(gu, h, np.zeros(pk), xxK, e, Ve / (V * Vk), Ve, 0, seed=s)
+            uh += e.astype(np.float32) - up["e"]  # the device works on the float32 residual
             h, e = up["b"], up["e"]
             up = KMUP(g, b, d, xx, e, L, Ve, pi, seed=s + 1)
+            xb += e.astype(np.float32) - up["e"]
             if pi > 0:
                 d = up["d"]
             b, e = up["b"], up["e"]
@@ -548,32 +550,24 @@ def _wgr_eigk(y, X, eigK, VarK, it, bi, th, bag, iv, de, pi, df, R2, seed, store
             Vk = np.full(pk, Vp)
             Ve = float((e @ e + Se) / rng.chisquare(n * bag + df))
             L = Ve / Vb
-            if Xh is not None:  # :124: the residual rebuilt in double (a rounding refresh: KMUP's e is the same residual)
-                e = y - mu - Xh @ b - U @ h
+            e = y - mu - xb - uh  # :124 (e = y - mu - X b - U h)
             mu0 = rng.normal(e.mean(), Ve / n)  # sic: the sd argument is Ve / n (:125)
             mu += mu0
             e = e - mu0
             if i in post:
-                B0 += mu; B += b; D += d; VE += Ve; H += h; VP += Vp
+                B0 += mu; B += b; D += d; VE += Ve; H += h; VP += Vp; XB += xb
                 if iv:
                     VB += Vb
                 else:
                     VA += Va
-        B0 /= mc; D /= mc; B = B / mc / D.mean(); VE /= mc; H /= mc; VP /= mc
+        B0 /= mc; D /= mc; mD = D.mean(); B = B / mc / mD; VE /= mc; H /= mc; VP /= mc
         poly = U0 @ H
-        hat = B0 + (Xh @ B if Xh is not None else _fitted(g, B)) + (poly if U0.shape[0] == n else U @ H)
+        hat = B0 + XB / mc / mD + U @ H  # B0 + gen0 %*% B + U0 %*% H on the rows of the fit
         return {"mu": B0, "b": B, "Vb": VB / mc if iv else VA / mc, "d": D, "Ve": VE, "hat": hat, "u": poly, "Vk": VP, "cxx": float(xx.mean() * bag)}
     finally:
         gu.close()
         if own:
             g.close()
-
-
-def _fitted(g, b):
-    """X b for a store handed over without a host copy of X (integer stores only)."""
-    if g.info()["storage"] == STORE_F32:
-        raise _lib.BwgrError(-5, "wgr(eigK): pass the genotype matrix, not a float32 store, to get fitted values")
-    return g.unpack().astype(np.float64) @ b
 
 
 def _wgr_native(y, X, it, bi, th, bag, rp, iv, de, pi, df, R2, seed, store_kw):
@@ -595,6 +589,153 @@ def _wgr_native(y, X, it, bi, th, bag, rp, iv, de, pi, df, R2, seed, store_kw):
     finally:
         if own:
             g.close()
+
+
+class _TwoDesigns:
+    """The two marker matrices of a two-design solver as two stores, and the reference's set-up of both (xx, MSx = sum of column variances)."""
+
+    def __init__(self, y, X1, X2, store_kw):
+        self.y = np.ascontiguousarray(y, dtype=np.float64)
+        self.g, self.own = [], []
+        try:
+            for X in (X1, X2):
+                g, own = _store(X, **store_kw)
+                self.g.append(g); self.own.append(own)
+            _need(self.g[0].n == self.g[1].n == self.y.size, "y, X1 and X2 must have the same number of rows")
+            self.n, self.p = self.g[0].n, [self.g[0].p, self.g[1].p]
+            self.xx, self.MSx = [], []
+            for g in self.g:
+                xx, sx = (np.asarray(v, dtype=np.float64) for v in g.stats())
+                self.xx.append(xx)
+                self.MSx.append(float(((xx - sx * sx / self.n) / (self.n - 1)).sum()))
+        except Exception:
+            self.close()
+            raise
+
+    def sweep(self, q, b, d, e, L, Ve, pi, seed):
+        """One Kuo-Mallick sweep over design q on the device (natural marker order, shared residual)."""
+        return KMUP(self.g[q], b, d, self.xx[q], e, L, Ve, pi, seed=seed)
+
+    def close(self):
+        for g, own in zip(self.g, self.own):
+            if own:
+                g.close()
+
+
+def emML2(y, X1, X2, D1=None, D2=None, **store_kw):
+    """emML2(y, X1, X2, D1 = NULL, D2 = NULL) (Rcpp20260726ai.cpp:1221-1305): y = mu + X1 b1 + X2 b2 + e, ridge sweeps over both designs
+    with one residual (the device's Kuo-Mallick sweep in its deterministic limit Ve -> 0, pi = 0: b1 = (x'e + xx b0) / (xx + Lmb)),
+    variance components from u'cY / n; same list.  u1 = X1 b1 and u2 = X2 b2 are followed through the residual."""
+    T = _TwoDesigns(y, X1, X2, store_kw)
+    try:
+        n, y = T.n, T.y
+        Dw = [None if D is None else np.asarray(D, dtype=np.float64) for D in (D1, D2)]
+        for q in range(2):
+            _need(Dw[q] is None or Dw[q].size == T.p[q], "emML2: D%d must have one weight per marker" % (q + 1))
+        b = [np.zeros(T.p[0]), np.zeros(T.p[1])]
+        u = [np.zeros(n), np.zeros(n)]
+        Lmb = list(T.MSx)
+        vb = [0.0, 0.0]
+        mu = float(np.float32(y.mean()))
+        e = y - mu
+        ve = 0.0
+        for numit in range(350):
+            bc = [b[0].copy(), b[1].copy()]
+            for q in range(2):
+                L = np.full(T.p[q], Lmb[q]) if Dw[q] is None else Lmb[q] / Dw[q]
+                up = T.sweep(q, b[q], np.ones(T.p[q]), e, L, 1e-30, 0.0, 1)
+                u[q] += e.astype(np.float32) - up["e"]  # the device works on the float32 residual
+                b[q], e = up["b"], up["e"]
+            eM = e.mean()
+            mu += eM
+            e = e - eM
+            cY = u[0] + u[1] + e
+            ve = float(e @ cY / n)
+            for q in range(2):
+                vb[q] = float(u[q] @ cY / n) / T.MSx[q]
+                Lmb[q] = ve / vb[q]
+            if np.abs(bc[0] - b[0]).sum() + np.abs(bc[1] - b[1]).sum() < 10e-8:
+                break
+        return {"mu": mu, "b1": b[0], "b2": b[1], "Vb1": vb[0], "Vb2": vb[1], "Ve": ve, "u1": u[0], "u2": u[1], "MSx1": T.MSx[0],
+                "MSx2": T.MSx[1], "h2": 1 - ve / float(y.var(ddof=1)), "hat": mu + u[0] + u[1], "its": numit + 1}
+    finally:
+        T.close()
+
+
+def _gibbs2(model, y, X1, X2, it, bi, pi, df, R2, seed, store_kw):
+    """BayesA2 :990-1069, BayesB2 :1072-1154, BayesRR2 :1157-1218: per iteration one Kuo-Mallick sweep per design on the device (BayesB2's
+    marker step IS KMUP's, :1106-1118; the others are its pi = 0 case), the variance draws on the host.  A marker's variance draw depends
+    on its own effect only and is not read again before the sweep ends, so drawing all of them after the sweep is the same sampler."""
+    T = _TwoDesigns(y, X1, X2, store_kw)
+    try:
+        n, y, P = T.n, T.y, T.p
+        it, bi = int(it), int(bi)
+        rng = np.random.default_rng(seed)
+        vy = float(y.var(ddof=1))
+        Sb = [R2 * df * vy / T.MSx[q] for q in range(2)]
+        Se = (1 - R2) * df * vy
+        mu, ve = float(y.mean()), vy
+        e = y - mu
+        b = [np.zeros(P[q]) for q in range(2)]
+        d = [np.zeros(P[q]) for q in range(2)]
+        vb = [np.full(P[q], Sb[q]) for q in range(2)]
+        vbs = [0.0, 0.0]
+        L = [np.full(P[q], T.MSx[q]) if model == "BayesRR2" else ve / vb[q] for q in range(2)]
+        MU = VE = 0.0
+        B = [np.zeros(P[q]) for q in range(2)]
+        D = [np.zeros(P[q]) for q in range(2)]
+        VB = [np.zeros(P[q]) for q in range(2)]
+        VBs = [0.0, 0.0]
+        E = np.zeros(n)
+        for i in range(it):
+            for q in range(2):
+                up = T.sweep(q, b[q], d[q], e, L[q], ve, pi if model == "BayesB2" else 0.0, int(rng.integers(1, 2 ** 62)))
+                b[q], e = up["b"], up["e"]
+                if model == "BayesB2":
+                    d[q] = up["d"]
+                if model != "BayesRR2":
+                    vb[q] = (Sb[q] + b[q] * b[q]) / rng.chisquare(df + 1, size=P[q])
+            eM = rng.normal(e.mean(), np.sqrt(ve / n))
+            mu += eM
+            e = e - eM
+            ve = float((e @ e + Se) / rng.chisquare(n + df))
+            for q in range(2):
+                if model == "BayesRR2":
+                    vbs[q] = float((Sb[q] + b[q] @ b[q]) / rng.chisquare(df + P[q]))
+                    L[q] = np.full(P[q], ve / vbs[q])
+                else:
+                    L[q] = ve / vb[q]
+            if i > bi:
+                MU += mu; VE += ve; E += e
+                for q in range(2):
+                    B[q] += b[q]; D[q] += d[q]; VB[q] += vb[q]; VBs[q] += vbs[q]
+        mc = float(it - bi)
+        MU /= mc; VE /= mc
+        B = [v / mc for v in B]; D = [v / mc for v in D]; VB = [v / mc for v in VB]; VBs = [v / mc for v in VBs]
+        vg = VBs[0] * T.MSx[0] + VBs[1] * T.MSx[1] if model == "BayesRR2" else float(VB[0].sum() + VB[1].sum())
+        # fit = X1 B1 + X2 B2 + MU: the chain's fitted values are y - e, and the posterior mean is linear in them
+        out = {"hat": y - E / mc, "mu": MU, "b1": B[0], "b2": B[1], "vb1": VBs[0] if model == "BayesRR2" else VB[0],
+               "vb2": VBs[1] if model == "BayesRR2" else VB[1], "ve": VE, "h2": vg / (vg + VE)}
+        if model == "BayesB2":
+            out["d1"], out["d2"] = D[0], D[1]
+        return out
+    finally:
+        T.close()
+
+
+def BayesA2(y, X1, X2, it=1500, bi=500, df=5, R2=0.5, seed=1, **kw):
+    """BayesA2(y, X1, X2, it = 1500, bi = 500, df = 5, R2 = 0.5) (Rcpp20260726ai.cpp:990-1069)."""
+    return _gibbs2("BayesA2", y, X1, X2, it, bi, 0.0, df, R2, seed, kw)
+
+
+def BayesB2(y, X1, X2, it=1500, bi=500, pi=0.95, df=5, R2=0.5, seed=1, **kw):
+    """BayesB2(y, X1, X2, it = 1500, bi = 500, pi = 0.95, df = 5, R2 = 0.5) (Rcpp20260726ai.cpp:1072-1154)."""
+    return _gibbs2("BayesB2", y, X1, X2, it, bi, pi, df, R2, seed, kw)
+
+
+def BayesRR2(y, X1, X2, it=1500, bi=500, df=5, R2=0.5, seed=1, **kw):
+    """BayesRR2(y, X1, X2, it = 1500, bi = 500, df = 5, R2 = 0.5) (Rcpp20260726ai.cpp:1157-1218)."""
+    return _gibbs2("BayesRR2", y, X1, X2, it, bi, 0.0, df, R2, seed, kw)
 
 
 _MRR3_DEFAULTS = dict(

@@ -755,6 +755,158 @@ static inline void kmup(const float* X, int n, int p, float* b, float* d, const 
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// Two-design solvers: y = mu + X1 b1 + X2 b2 + e, the per-marker step of the univariate solvers looped over two
+// marker matrices with one shared residual.  BayesA2 :990-1069, BayesB2 :1072-1154, BayesRR2 :1157-1218, emML2 :1221-1305 of
+// Rcpp20260726ai.cpp.  Draws are made in the reference's order (the marker's variance right after its effect).
+// ------------------------------------------------------------------------------------------------
+enum TwoDesignModel { TD_A2 = 0, TD_B2 = 1, TD_RR2 = 2 };
+struct TwoDesignOut {
+  float mu = 0, ve = 0, h2 = 0, vb1s = 0, vb2s = 0, MSx1 = 0, MSx2 = 0;
+  int its = 0;
+  std::vector<float> b1, b2, d1, d2, vb1, vb2, hat, u1, u2;
+};
+static inline void gibbs2_fit(int model, const float* y, const float* X1, const float* X2, int n, int p1, int p2, float it_f, float bi_f,
+                              float pi, float df, float R2, uint64_t seed, TwoDesignOut& o) {
+  Rng rng(seed);
+  const int iit = (int)it_f, ibi = (int)bi_f;
+  const int P[2] = {p1, p2};
+  const float* X[2] = {X1, X2};
+  std::vector<float> xx[2], vx[2], b[2], d[2], vbv[2], Lv[2], B[2], D[2], VBv[2];
+  float MSx[2], Sb[2], Lmb[2], vbs[2] = {0, 0}, VBs[2] = {0, 0};
+  const float vy = fvar(y, n);
+  for (int q = 0; q < 2; q++) {
+    xx_vx(X[q], n, P[q], xx[q], &vx[q]);
+    MSx[q] = vsum(vx[q].data(), P[q]);
+    Sb[q] = R2 * df * vy / MSx[q];
+    Lmb[q] = MSx[q];  // BayesRR2 :1181
+    b[q].assign(P[q], 0.0f); d[q].assign(P[q], 0.0f); B[q].assign(P[q], 0.0f); D[q].assign(P[q], 0.0f); VBv[q].assign(P[q], 0.0f);
+    vbv[q].assign(P[q], Sb[q]);
+  }
+  const float Se = (1 - R2) * df * vy;
+  float mu = vmean(y, n), ve = vy, MU = 0, VE = 0;
+  for (int q = 0; q < 2; q++) { Lv[q].resize(P[q]); for (int j = 0; j < P[q]; j++) Lv[q][j] = ve * (1.0f / vbv[q][j]); }
+  std::vector<float> e(n), e1(n), e2(n);
+  for (int i = 0; i < n; i++) e[i] = y[i] - mu;
+  for (int i = 0; i < iit; i++) {
+    const float C = -0.5f / std::sqrt(ve);
+    for (int q = 0; q < 2; q++) {
+      for (int j = 0; j < P[q]; j++) {
+        const float* x = X[q] + (size_t)j * n;
+        const float b0 = b[q][j];
+        const float L = model == TD_RR2 ? Lmb[q] : Lv[q][j];
+        const float sd = std::sqrt(ve / (xx[q][j] + L));
+        const float bt1 = (float)rng.rnorm((vdot(x, e.data(), n) + xx[q][j] * b0) / (xx[q][j] + L), sd);
+        float bn = bt1;
+        if (model == TD_B2) {  // :1106-1118
+          const float bt2 = (float)rng.rnorm(0, sd);
+          for (int r = 0; r < n; r++) { e1[r] = e[r] - x[r] * (bt1 - b0); e2[r] = e[r] - x[r] * (bt2 - b0); }
+          const float cj = (1 - pi) * std::exp(C * vsq(e1.data(), n));
+          const float dj = (pi)*std::exp(C * vsq(e2.data(), n));
+          const float pj = cj / (cj + dj);
+          if (rng.rbinom1(pj) == 1) { bn = bt1; d[q][j] = 1; } else { bn = bt2; d[q][j] = 0; }
+        }
+        b[q][j] = bn;
+        if (model != TD_RR2) vbv[q][j] = (Sb[q] + bn * bn) / (float)rng.rchisq(df + 1);
+        for (int r = 0; r < n; r++) e[r] -= x[r] * (bn - b0);
+      }
+    }
+    const float eM = (float)rng.rnorm(vmean(e.data(), n), std::sqrt(ve / n));
+    mu += eM;
+    for (int r = 0; r < n; r++) e[r] -= eM;
+    ve = (vsq(e.data(), n) + Se) / (float)rng.rchisq(n + df);
+    for (int q = 0; q < 2; q++) {
+      if (model == TD_RR2) { vbs[q] = (Sb[q] + vsq(b[q].data(), P[q])) / (float)rng.rchisq(df + P[q]); Lmb[q] = ve / vbs[q]; }
+      else for (int j = 0; j < P[q]; j++) Lv[q][j] = ve * (1.0f / vbv[q][j]);
+    }
+    if (i > ibi) {
+      MU += mu; VE += ve;
+      for (int q = 0; q < 2; q++) {
+        for (int j = 0; j < P[q]; j++) { B[q][j] += b[q][j]; D[q][j] += d[q][j]; VBv[q][j] += vbv[q][j]; }
+        VBs[q] += vbs[q];
+      }
+    }
+  }
+  const float MCMC = it_f - bi_f;
+  MU /= MCMC; VE /= MCMC;
+  for (int q = 0; q < 2; q++) {
+    for (int j = 0; j < P[q]; j++) { B[q][j] /= MCMC; D[q][j] /= MCMC; VBv[q][j] /= MCMC; }
+    VBs[q] /= MCMC;
+  }
+  const float vg = model == TD_RR2 ? VBs[0] * MSx[0] + VBs[1] * MSx[1] : vsum(VBv[0].data(), p1) + vsum(VBv[1].data(), p2);
+  o.h2 = vg / (vg + VE);
+  o.mu = MU; o.ve = VE; o.vb1s = VBs[0]; o.vb2s = VBs[1]; o.MSx1 = MSx[0]; o.MSx2 = MSx[1];
+  o.b1 = B[0]; o.b2 = B[1]; o.d1 = D[0]; o.d2 = D[1]; o.vb1 = VBv[0]; o.vb2 = VBv[1];
+  o.hat.assign(n, 0.0f);
+  for (int q = 0; q < 2; q++)
+    for (int j = 0; j < P[q]; j++) {
+      const float* x = X[q] + (size_t)j * n;
+      for (int r = 0; r < n; r++) o.hat[r] += x[r] * B[q][j];
+    }
+  for (int r = 0; r < n; r++) o.hat[r] += MU;
+}
+
+// emML2 :1221-1305: natural marker order, at most 350 sweeps, stop when sum |db| < 1e-7; D1 / D2 = optional marker weights
+// (penalty Lmb / D[j]).
+static inline void emml2_fit(const float* y, const float* X1, const float* X2, int n, int p1, int p2, const double* D1, const double* D2,
+                             TwoDesignOut& o) {
+  const int maxit = 350;
+  const float tol = 10e-8f;
+  const int P[2] = {p1, p2};
+  const float* X[2] = {X1, X2};
+  const double* Dw[2] = {D1, D2};
+  std::vector<float> xx[2], vx[2], b[2], bc[2], dw[2], u[2];
+  float MSx[2], Lmb[2], vb[2] = {0, 0};
+  for (int q = 0; q < 2; q++) {
+    xx_vx(X[q], n, P[q], xx[q], &vx[q]);
+    MSx[q] = vsum(vx[q].data(), P[q]);
+    Lmb[q] = MSx[q];
+    b[q].assign(P[q], 0.0f);
+    dw[q].assign(P[q], 1.0f);
+    if (Dw[q]) for (int j = 0; j < P[q]; j++) dw[q][j] = (float)Dw[q][j];
+    u[q].assign(n, 0.0f);
+  }
+  float mu = vmean(y, n), ve = 0;
+  std::vector<float> e(n), cY(n);
+  for (int i = 0; i < n; i++) e[i] = y[i] - mu;
+  int numit = 0;
+  while (numit < maxit) {
+    float cnv = 0;
+    for (int q = 0; q < 2; q++) {
+      bc[q] = b[q];
+      for (int j = 0; j < P[q]; j++) {
+        const float* x = X[q] + (size_t)j * n;
+        const float b0 = b[q][j];
+        const float bn = Dw[q] ? (vdot(x, e.data(), n) + xx[q][j] * b0) / (xx[q][j] + Lmb[q] / dw[q][j])
+                               : (vdot(x, e.data(), n) + xx[q][j] * b0) / (xx[q][j] + Lmb[q]);
+        b[q][j] = bn;
+        for (int r = 0; r < n; r++) e[r] -= x[r] * (bn - b0);
+      }
+    }
+    for (int q = 0; q < 2; q++) {  // u = X b, column by column like Eigen's gemv
+      std::fill(u[q].begin(), u[q].end(), 0.0f);
+      for (int j = 0; j < P[q]; j++) {
+        const float* x = X[q] + (size_t)j * n;
+        const float bj = b[q][j];
+        for (int r = 0; r < n; r++) u[q][r] += x[r] * bj;
+      }
+    }
+    const float eM = vmean(e.data(), n);
+    mu += eM;
+    for (int r = 0; r < n; r++) { e[r] -= eM; cY[r] = u[0][r] + u[1][r] + e[r]; }
+    ve = vdot(e.data(), cY.data(), n) / (float)n;
+    for (int q = 0; q < 2; q++) { vb[q] = (vdot(u[q].data(), cY.data(), n) / (float)n) / MSx[q]; Lmb[q] = ve / vb[q]; }
+    ++numit;
+    for (int q = 0; q < 2; q++) cnv += reduce_sum<float>(P[q], [&](int j) { return std::fabs(bc[q][j] - b[q][j]); });
+    if (cnv < tol) break;
+  }
+  o.its = numit; o.mu = mu; o.ve = ve; o.vb1s = vb[0]; o.vb2s = vb[1]; o.MSx1 = MSx[0]; o.MSx2 = MSx[1];
+  o.h2 = 1 - ve / fvar(y, n);
+  o.b1 = b[0]; o.b2 = b[1]; o.u1 = u[0]; o.u2 = u[1];
+  o.hat.resize(n);
+  for (int r = 0; r < n; r++) o.hat[r] = mu + u[0][r] + u[1][r];
+}
+
 // KMUP2: Rcpp20260726ai.cpp:41-77.  The bagged sweep of wgr(bag != 1): only the rows `use` enter; note (H.e0 + b0) without the xx
 // factor (:59, sic) and xx scaled by bg = n0 / n.  e_out has length nuse.
 static inline void kmup2(const float* X, int n0, int p, const float* use, int nuse, float* b, float* d, const float* xx, const float* E,

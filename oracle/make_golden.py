@@ -61,8 +61,26 @@ def main():
     Y = synth_traits(genf)
     r = R.mrr3(Y, genf)
     np.savez_compressed(os.path.join(OUT, "tpod_mrr3.npz"), Y=Y, **{k: np.asarray(v) for k, v in r.items()})
+    two_design_golden(y, genf)
     print("wrote", sorted(os.listdir(OUT)))
 
 
+def two_design_golden(y, genf):
+    """emML2 (Rcpp20260726ai.cpp:1221-1305) executed by the reference's own source on tpod split into two designs (markers 1-200 and
+    201-376), without and with marker weights.  `python oracle/make_golden.py two_design` writes this file alone."""
+    X1, X2 = genf[:, :200], genf[:, 200:]
+    rng = np.random.default_rng(20261018)
+    D1, D2 = rng.uniform(0.5, 2.0, 200), rng.uniform(0.5, 2.0, 176)
+    out = {"provenance": np.array("reference-executed"), "split": np.array(200), "D1": D1, "D2": D2}
+    for tag, kw in (("plain", {}), ("weighted", dict(D1=D1, D2=D2))):
+        for key, v in R.two_design("emML2", y, X1, X2, **kw).items():
+            out[tag + "__" + key] = np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, "tpod_two_design.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["two_design"]:
+        t = np.load(os.path.join(OUT, "tpod.npz"))
+        two_design_golden(t["y"], t["gen"].astype(np.float64))
+    else:
+        main()

@@ -251,3 +251,34 @@ def mrr3(Y, X, f32_variant=False, **kw):
     q = its.value
     return {"mu": mu, "b": b, "hat": hat, "h2": h2, "GC": GC, "vb": vb, "ve": ve, "MSx": MSx, "cnvB": cnv[:q],
             "cnvH2": cnv[maxit:maxit + q], "cnvV": cnv[2 * maxit:2 * maxit + q], "b_Weights": W, "Its": q}
+
+TWO_DESIGN = {"BayesA2": 0, "BayesB2": 1, "BayesRR2": 2, "emML2": 3}
+
+
+def two_design(model, y, X1, X2, it=1500, bi=500, pi=0.95, df=5.0, R2=0.5, seed=1, D1=None, D2=None):
+    """BayesA2 / BayesB2 / BayesRR2 / emML2 (Rcpp20260726ai.cpp:990-1305): y = mu + X1 b1 + X2 b2 + e.  Keys as the reference's lists."""
+    y = _f32(y)
+    X1, X2 = _f32(X1), _f32(X2)
+    n, p1 = X1.shape
+    p2 = X2.shape[1]
+    b1, d1, vb1 = (np.zeros(p1) for _ in range(3))
+    b2, d2, vb2 = (np.zeros(p2) for _ in range(3))
+    hat, u1, u2 = (np.zeros(n) for _ in range(3))
+    scal = np.zeros(8)
+    D1 = None if D1 is None else np.ascontiguousarray(D1, dtype=np.float64)
+    D2 = None if D2 is None else np.ascontiguousarray(D2, dtype=np.float64)
+    rc = lib().orc_two_design(C.c_int(TWO_DESIGN[model]), _p(y, C.c_float), _p(X1, C.c_float), _p(X2, C.c_float), C.c_int(n), C.c_int(p1),
+                  C.c_int(p2), C.c_float(it), C.c_float(bi), C.c_float(pi), C.c_float(df), C.c_float(R2), C.c_uint64(seed),
+                  _p(D1, C.c_double) if D1 is not None else None, _p(D2, C.c_double) if D2 is not None else None,
+                  _p(b1, C.c_double), _p(b2, C.c_double), _p(d1, C.c_double), _p(d2, C.c_double), _p(vb1, C.c_double),
+                  _p(vb2, C.c_double), _p(hat, C.c_double), _p(u1, C.c_double), _p(u2, C.c_double), _p(scal, C.c_double))
+    assert rc == 0
+    mu, ve, h2, s1, s2, MSx1, MSx2, its = scal
+    if model == "emML2":
+        return {"mu": mu, "b1": b1, "b2": b2, "Vb1": s1, "Vb2": s2, "Ve": ve, "u1": u1, "u2": u2, "MSx1": MSx1, "MSx2": MSx2, "h2": h2,
+                "hat": hat}
+    out = {"hat": hat, "mu": mu, "b1": b1, "b2": b2, "vb1": s1 if model == "BayesRR2" else vb1, "vb2": s2 if model == "BayesRR2" else vb2,
+           "ve": ve, "h2": h2}
+    if model == "BayesB2":
+        out["d1"], out["d2"] = d1, d2
+    return out

@@ -102,6 +102,19 @@ int orc_cnt_imp(int which, float* X, int n, int p) {
   return 0;
 }
 
+// two-design solvers.  model: 0 BayesA2, 1 BayesB2, 2 BayesRR2, 3 emML2.  scal = {mu, ve, h2, vb1 (scalar), vb2 (scalar), MSx1, MSx2, its}
+int orc_two_design(int model, const float* y, const float* X1, const float* X2, int n, int p1, int p2, float it, float bi, float pi, float df,
+                   float R2, uint64_t seed, const double* D1, const double* D2, double* b1, double* b2, double* d1, double* d2, double* vb1,
+                   double* vb2, double* hat, double* u1, double* u2, double* scal) {
+  orc::TwoDesignOut o;
+  if (model == 3) orc::emml2_fit(y, X1, X2, n, p1, p2, D1, D2, o);
+  else orc::gibbs2_fit(model, y, X1, X2, n, p1, p2, it, bi, pi, df, R2, seed, o);
+  auto cp = [](const std::vector<float>& v, double* out) { if (out) for (size_t i = 0; i < v.size(); i++) out[i] = v[i]; };
+  cp(o.b1, b1); cp(o.b2, b2); cp(o.d1, d1); cp(o.d2, d2); cp(o.vb1, vb1); cp(o.vb2, vb2); cp(o.hat, hat); cp(o.u1, u1); cp(o.u2, u2);
+  scal[0] = o.mu; scal[1] = o.ve; scal[2] = o.h2; scal[3] = o.vb1s; scal[4] = o.vb2s; scal[5] = o.MSx1; scal[6] = o.MSx2; scal[7] = o.its;
+  return 0;
+}
+
 // scal = {mu, Ve, Va, cxx}
 int orc_wgr(const double* y, const double* X, int n, int p, int it, int bi, int th, int iv, int de, double pi, double df,
             double R2, uint64_t seed, int ratio_form, double* b, double* d, double* Vb, double* hat, double* scal) {

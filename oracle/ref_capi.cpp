@@ -138,6 +138,34 @@ int ref_gs(int which, const float* y, float* e, const float* X, int n, int p, fl
   return 0;
 }
 
+// two-design solvers (:990-1305).  model: 0 BayesA2, 1 BayesB2, 2 BayesRR2, 3 emML2.  Same outputs as orc_two_design.
+int ref_two_design(int model, const float* y, const float* X1, const float* X2, int n, int p1, int p2, float it, float bi, float pi, float df,
+                   float R2, uint64_t seed, const double* D1, const double* D2, double* b1, double* b2, double* d1, double* d2, double* vb1,
+                   double* vb2, double* hat, double* u1, double* u2, double* scal_out) {
+  Eigen::VectorXf yy = vec_f(y, n);
+  Eigen::MatrixXf A = mat_f(X1, n, p1), B = mat_f(X2, n, p2);
+  R::set_seed(seed);
+  SEXP r = nullptr;
+  if (model == 0) r = BayesA2(yy, A, B, it, bi, df, R2);
+  else if (model == 1) r = BayesB2(yy, A, B, it, bi, pi, df, R2);
+  else if (model == 2) r = BayesRR2(yy, A, B, it, bi, df, R2);
+  else if (model == 3) {
+    Rcpp::Nullable<Rcpp::NumericVector> n1, n2;
+    if (D1) n1 = Rcpp::Nullable<Rcpp::NumericVector>(Rcpp::NumericVector(D1, (size_t)p1));
+    if (D2) n2 = Rcpp::Nullable<Rcpp::NumericVector>(Rcpp::NumericVector(D2, (size_t)p2));
+    r = emML2(yy, A, B, n1, n2);
+  } else return -1;
+  List* l = (List*)r;
+  put(l, "b1", b1); put(l, "b2", b2); put(l, "d1", d1); put(l, "d2", d2); put(l, "hat", hat); put(l, "u1", u1); put(l, "u2", u2);
+  for (int i = 0; i < 8; i++) scal_out[i] = 0;
+  scal_out[0] = scal(l, "mu"); scal_out[1] = model == 3 ? scal(l, "Ve") : scal(l, "ve"); scal_out[2] = scal(l, "h2");
+  if (model == 3) { scal_out[3] = scal(l, "Vb1"); scal_out[4] = scal(l, "Vb2"); scal_out[5] = scal(l, "MSx1"); scal_out[6] = scal(l, "MSx2"); }
+  else if (model == 2) { scal_out[3] = scal(l, "vb1"); scal_out[4] = scal(l, "vb2"); }
+  else { put(l, "vb1", vb1); put(l, "vb2", vb2); }
+  delete l;
+  return 0;
+}
+
 // CNT (:1308) and IMP (:1316): column centring / mean imputation of the genotype matrix (in place, column-major)
 int ref_cnt_imp(int which, float* X, int n, int p) {
   Eigen::MatrixXf o = which == 0 ? CNT(mat_f(X, n, p)) : IMP(mat_f(X, n, p));

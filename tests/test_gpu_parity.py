@@ -958,6 +958,55 @@ def test_wgr_polygenic_term_and_missing_values(tpod):
     assert np.allclose(a["hat"], a["mu"] + Xi @ a["b"])
 
 
+def test_two_design_emml2(tpod):
+    """emML2(y, X1, X2, D1, D2) (Rcpp20260726ai.cpp:1221-1305) on tpod split into two designs: ridge sweeps over both stores with one
+    residual on the device, against the oracle and the reference-executed golden.  The bar is 1e-4 widened by the float recipe's own
+    noise floor (the distance between the oracle and the reference's run of the same 350 float sweeps)."""
+    y, gen = tpod
+    g = np.load(os.path.join(GOLDEN, "tpod_two_design.npz"))
+    X1, X2 = gen[:, :200], gen[:, 200:]
+    with bw.Genotypes(X1) as g1, bw.Genotypes(X2) as g2:
+        for tag, kw in (("plain", {}), ("weighted", dict(D1=g["D1"], D2=g["D2"]))):
+            ora = O.two_design("emML2", y, X1.astype(np.float64), X2.astype(np.float64), **kw)
+            out = bw.emML2(y, g1, g2, **kw)
+            for key in ("mu", "b1", "b2", "Vb1", "Vb2", "Ve", "u1", "u2", "h2", "hat"):
+                ref = np.asarray(g[tag + "__" + key], dtype=np.float64)
+                scale = max(np.abs(ref).max(), 1e-30)
+                floor = np.abs(np.asarray(ora[key]) - ref).max()
+                assert np.abs(np.asarray(out[key]) - ref).max() <= RTOL * scale + 2 * floor, (tag, key, np.abs(np.asarray(out[key]) - ref).max() / scale, floor / scale)
+                assert np.abs(np.asarray(out[key]) - np.asarray(ora[key])).max() <= RTOL * scale + 2 * floor, (tag, key)
+            assert np.isclose(out["MSx1"], ora["MSx1"], rtol=1e-5) and np.isclose(out["MSx2"], ora["MSx2"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("model", ["BayesRR2", "BayesA2", "BayesB2"])
+def test_two_design_gibbs(tpod, model):
+    """BayesRR2 / BayesA2 / BayesB2 (Rcpp20260726ai.cpp:990-1218): one Kuo-Mallick sweep per design and iteration on the device, variance
+    draws on the host -- posterior means vs the oracle (pinned draw for draw against the reference's source) within Monte-Carlo error."""
+    y, gen = tpod
+    X1, X2 = gen[:, :200], gen[:, 200:]
+    fn = getattr(bw, model)
+    kw = dict(pi=0.8) if model == "BayesB2" else {}
+    seeds = range(6)
+    ora = [O.two_design(model, y, X1.astype(np.float64), X2.astype(np.float64), it=500, bi=150, seed=50 + s, **kw) for s in seeds]
+    with bw.Genotypes(X1) as g1, bw.Genotypes(X2) as g2:
+        gpu = [fn(y, g1, g2, it=500, bi=150, seed=70 + s, **kw) for s in seeds]
+    for key in ("mu", "ve", "h2"):
+        a = np.array([r[key] for r in ora]); b = np.array([r[key] for r in gpu])
+        se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+        assert abs(a.mean() - b.mean()) <= 4 * se + 2e-2 * abs(a.mean()), (key, a.mean(), b.mean(), se)
+    A = np.mean([r["hat"] for r in ora], 0); B = np.mean([r["hat"] for r in gpu], 0)
+    A1 = np.mean([r["hat"] for r in ora[:3]], 0); A2 = np.mean([r["hat"] for r in ora[3:]], 0)
+    assert np.corrcoef(A, B)[0, 1] > min(0.99, np.corrcoef(A1, A2)[0, 1] - 0.005)
+    for q in ("1", "2"):  # fitted values of each design from the posterior means
+        a = np.mean([np.mean(r["vb" + q]) for r in ora]); b = np.mean([np.mean(r["vb" + q]) for r in gpu])
+        assert abs(a - b) <= 0.1 * a, ("vb" + q, a, b)
+    if model == "BayesB2":
+        da = np.mean([r["d1"].mean() for r in ora]); db = np.mean([r["d1"].mean() for r in gpu])
+        assert abs(da - db) < 0.03
+    hat = gpu[0]["mu"] + X1.astype(np.float64) @ gpu[0]["b1"] + X2.astype(np.float64) @ gpu[0]["b2"]
+    assert np.abs(hat - gpu[0]["hat"]).max() <= 1e-4 * np.abs(hat).max() + 1e-5  # hat = y - mean residual IS MU + X1 B1 + X2 B2
+
+
 @pytest.mark.parametrize("path", [1, 2])
 @pytest.mark.parametrize("which", ["GSRR", "GSFLM"])
 def test_gs_warm_start_solvers(tpod, which, path):

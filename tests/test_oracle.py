@@ -329,3 +329,16 @@ def test_first_panel_vs_numpy(tpod, model):
     r = O.em(model, y, X, it=10, use_double=True)
     for key, v in ref.items():
         np.testing.assert_allclose(r[key], v, rtol=2e-5, atol=1e-9, err_msg=key)
+
+
+def test_two_design_oracle_matches_reference_executed_golden(tpod):
+    """The oracle's emML2 against tests/golden/tpod_two_design.npz (emML2 run by the reference's own source, oracle/make_golden.py)."""
+    y, X = tpod
+    g = np.load(os.path.join(GOLDEN, "tpod_two_design.npz"))
+    X1, X2 = X[:, :200].astype(np.float64), X[:, 200:].astype(np.float64)
+    for tag, kw in (("plain", {}), ("weighted", dict(D1=g["D1"], D2=g["D2"]))):
+        r = O.two_design("emML2", y, X1, X2, **kw)
+        for key in ("mu", "b1", "b2", "Vb1", "Vb2", "Ve", "u1", "u2", "h2", "hat"):
+            ref = g[tag + "__" + key]
+            assert np.abs(np.asarray(r[key]) - ref).max() <= 1e-3 * max(np.abs(ref).max(), 1e-30), (tag, key)
+

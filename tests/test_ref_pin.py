@@ -68,6 +68,22 @@ def test_gibbs_chains_match_reference_text(tpod, model):
         assert rel(a[key], r[key]) < 2e-4, (model, key, rel(a[key], r[key]))
 
 
+@pytest.mark.parametrize("model", list(O.TWO_DESIGN))
+def test_two_design_solvers_match_reference_text(tpod, model):
+    """BayesA2 / BayesB2 / BayesRR2 / emML2 (Rcpp20260726ai.cpp:990-1305) on tpod split into two designs: the chains draw for draw,
+    emML2 to float reassociation over its 350 sweeps (with and without marker weights)."""
+    y, X = tpod
+    X1, X2 = X[:, :200], X[:, 200:]
+    cases = [dict(it=80, bi=30, seed=11)]
+    if model == "emML2":
+        rng = np.random.default_rng(1)
+        cases = [dict(), dict(D1=rng.uniform(0.5, 2, 200), D2=rng.uniform(0.5, 2, 176))]
+    for kw in cases:
+        a, r = O.two_design(model, y, X1, X2, **kw), R.two_design(model, y, X1, X2, **kw)
+        for key in r:
+            assert rel(a[key], r[key]) < (1e-3 if model == "emML2" else 2e-4), (model, key, rel(a[key], r[key]))
+
+
 def test_kmup_sweep_matches_reference_text(tpod):
     y, X = tpod
     n, p = X.shape
