@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libbwgr_b200.so")
 # every symbol include/bwgr_b200.h declares (tests check the shared object exports all of them)
 SYMBOLS = [
     "bwgr_create", "bwgr_destroy", "bwgr_last_error", "bwgr_version", "bwgr_set_stream", "bwgr_set_tuning",
-    "bwgr_geno_load_f64", "bwgr_geno_load_f64_centred", "bwgr_geno_load_bed", "bwgr_geno_load_i8", "bwgr_geno_load_i8_device", "bwgr_geno_unpack_i8", "bwgr_geno_raw",
+    "bwgr_fitted", "bwgr_geno_load_f64", "bwgr_geno_load_f64_centred", "bwgr_geno_load_bed", "bwgr_geno_load_i8", "bwgr_geno_load_i8_device", "bwgr_geno_unpack_i8", "bwgr_geno_raw",
     "bwgr_geno_info", "bwgr_geno_stats", "bwgr_em_fit", "bwgr_em_begin", "bwgr_em_sweeps", "bwgr_em_end",
     "bwgr_gibbs_fit", "bwgr_kmup_sweep", "bwgr_kmup2_sweep", "bwgr_wgr_fit_bag", "bwgr_gs_fit", "bwgr_wgr_fit", "bwgr_mrr3_fit", "bwgr_dist_unique_id", "bwgr_dist_init", "bwgr_dist_connect", "bwgr_launch_count", "bwgr_debug_gram", "bwgr_debug_gram_band", "bwgr_debug_narrow", "bwgr_trim", "bwgr_profile", "bwgr_profile_read",
 ]
@@ -75,6 +75,7 @@ def load():
         lib.bwgr_em_sweeps.argtypes = [C.c_void_p, C.c_int]
         lib.bwgr_em_end.argtypes = [C.c_void_p, C.POINTER(EmOut)]
         lib.bwgr_gibbs_fit.argtypes = [C.c_void_p, C.POINTER(GibbsParams), C.c_void_p, C.POINTER(GibbsOut)]
+        lib.bwgr_fitted.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         lib.bwgr_kmup_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_double, C.c_double, C.c_uint64]
         lib.bwgr_kmup2_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

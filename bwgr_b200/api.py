@@ -135,6 +135,14 @@ class Genotypes:
         check(self.lib.bwgr_geno_stats(self.h, _ptr(xx), _ptr(sx)))
         return xx, sx
 
+    def fitted(self, b, mu=0.0):
+        """mu + X b on the store (bwgr_fitted)."""
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        _need(b.size == self.p, "b must have p = %d values" % self.p)
+        hat = np.empty(self.n)
+        check(self.lib.bwgr_fitted(self.h, _ptr(b), float(mu), _ptr(hat)))
+        return hat
+
     def gram_blocks(self, perm, block=128):
         perm = np.ascontiguousarray(perm, dtype=np.int32)
         nb = (self.p + block - 1) // block
@@ -520,7 +528,6 @@ def _wgr_eigk(y, X, eigK, VarK, it, bi, th, bag, iv, de, pi, df, R2, seed, store
         b, d, h = np.zeros(p), np.ones(p), np.zeros(pk)
         mu = float(y.mean())
         e = y - mu
-        xb, uh = np.zeros(n), np.zeros(n)  # X b and U h, followed through the residual: a sweep changes e by -(change of its fitted values)
         Va, Ve = MSx, 1.0
         Vb = np.full(p, Va)
         Vk = np.ones(pk)
@@ -529,15 +536,13 @@ def _wgr_eigk(y, X, eigK, VarK, it, bi, th, bag, iv, de, pi, df, R2, seed, store
         Sb, Se, Sk = R2 * df * vy / MSx, (1 - R2) * df * vy, R2 * vy * (df + 2)
         xxK = np.full(pk, float(bag))
         B0 = VA = VE = VP = 0.0
-        VB, D, B, H, XB = np.zeros(p), np.zeros(p), np.zeros(p), np.zeros(pk), np.zeros(n)
+        VB, D, B, H = np.zeros(p), np.zeros(p), np.zeros(p), np.zeros(pk)
         Vp = 0.0
         for i in range(1, it + 1):
             s = int(rng.integers(1, 2 ** 62))
             up = KMUP(gu, h, np.zeros(pk), xxK, e, Ve / (V * Vk), Ve, 0, seed=s)
-            uh += e.astype(np.float32) - up["e"]  # the device works on the float32 residual
             h, e = up["b"], up["e"]
             up = KMUP(g, b, d, xx, e, L, Ve, pi, seed=s + 1)
-            xb += e.astype(np.float32) - up["e"]
             if pi > 0:
                 d = up["d"]
             b, e = up["b"], up["e"]
@@ -550,19 +555,19 @@ def _wgr_eigk(y, X, eigK, VarK, it, bi, th, bag, iv, de, pi, df, R2, seed, store
             Vk = np.full(pk, Vp)
             Ve = float((e @ e + Se) / rng.chisquare(n * bag + df))
             L = Ve / Vb
-            e = y - mu - xb - uh  # :124 (e = y - mu - X b - U h)
+            e = y - g.fitted(b, mu) - U @ h  # :124 (e = y - mu - X b - U h)
             mu0 = rng.normal(e.mean(), Ve / n)  # sic: the sd argument is Ve / n (:125)
             mu += mu0
             e = e - mu0
             if i in post:
-                B0 += mu; B += b; D += d; VE += Ve; H += h; VP += Vp; XB += xb
+                B0 += mu; B += b; D += d; VE += Ve; H += h; VP += Vp
                 if iv:
                     VB += Vb
                 else:
                     VA += Va
-        B0 /= mc; D /= mc; mD = D.mean(); B = B / mc / mD; VE /= mc; H /= mc; VP /= mc
+        B0 /= mc; D /= mc; B = B / mc / D.mean(); VE /= mc; H /= mc; VP /= mc
         poly = U0 @ H
-        hat = B0 + XB / mc / mD + U @ H  # B0 + gen0 %*% B + U0 %*% H on the rows of the fit
+        hat = g.fitted(B, B0) + U @ H  # B0 + gen0 %*% B + U0 %*% H on the rows of the fit
         return {"mu": B0, "b": B, "Vb": VB / mc if iv else VA / mc, "d": D, "Ve": VE, "hat": hat, "u": poly, "Vk": VP, "cxx": float(xx.mean() * bag)}
     finally:
         gu.close()
@@ -625,7 +630,7 @@ class _TwoDesigns:
 def emML2(y, X1, X2, D1=None, D2=None, **store_kw):
     """emML2(y, X1, X2, D1 = NULL, D2 = NULL) (Rcpp20260726ai.cpp:1221-1305): y = mu + X1 b1 + X2 b2 + e, ridge sweeps over both designs
     with one residual (the device's Kuo-Mallick sweep in its deterministic limit Ve -> 0, pi = 0: b1 = (x'e + xx b0) / (xx + Lmb)),
-    variance components from u'cY / n; same list.  u1 = X1 b1 and u2 = X2 b2 are followed through the residual."""
+    variance components from u'cY / n with u1 = X1 b1, u2 = X2 b2 formed on the device every sweep; same list."""
     T = _TwoDesigns(y, X1, X2, store_kw)
     try:
         n, y = T.n, T.y
@@ -644,8 +649,9 @@ def emML2(y, X1, X2, D1=None, D2=None, **store_kw):
             for q in range(2):
                 L = np.full(T.p[q], Lmb[q]) if Dw[q] is None else Lmb[q] / Dw[q]
                 up = T.sweep(q, b[q], np.ones(T.p[q]), e, L, 1e-30, 0.0, 1)
-                u[q] += e.astype(np.float32) - up["e"]  # the device works on the float32 residual
                 b[q], e = up["b"], up["e"]
+            for q in range(2):  # :1275-1276 (formed afresh like the reference: the variance components feed back on them)
+                u[q] = T.g[q].fitted(b[q])
             eM = e.mean()
             mu += eM
             e = e - eM
@@ -686,7 +692,6 @@ def _gibbs2(model, y, X1, X2, it, bi, pi, df, R2, seed, store_kw):
         D = [np.zeros(P[q]) for q in range(2)]
         VB = [np.zeros(P[q]) for q in range(2)]
         VBs = [0.0, 0.0]
-        E = np.zeros(n)
         for i in range(it):
             for q in range(2):
                 up = T.sweep(q, b[q], d[q], e, L[q], ve, pi if model == "BayesB2" else 0.0, int(rng.integers(1, 2 ** 62)))
@@ -705,16 +710,16 @@ def _gibbs2(model, y, X1, X2, it, bi, pi, df, R2, seed, store_kw):
                     L[q] = np.full(P[q], ve / vbs[q])
                 else:
                     L[q] = ve / vb[q]
-            if i > bi:
-                MU += mu; VE += ve; E += e
+            if i > bi:  # sic: it - bi - 1 draws are summed and divided by it - bi (:1062-1065)
+                MU += mu; VE += ve
                 for q in range(2):
                     B[q] += b[q]; D[q] += d[q]; VB[q] += vb[q]; VBs[q] += vbs[q]
         mc = float(it - bi)
         MU /= mc; VE /= mc
         B = [v / mc for v in B]; D = [v / mc for v in D]; VB = [v / mc for v in VB]; VBs = [v / mc for v in VBs]
         vg = VBs[0] * T.MSx[0] + VBs[1] * T.MSx[1] if model == "BayesRR2" else float(VB[0].sum() + VB[1].sum())
-        # fit = X1 B1 + X2 B2 + MU: the chain's fitted values are y - e, and the posterior mean is linear in them
-        out = {"hat": y - E / mc, "mu": MU, "b1": B[0], "b2": B[1], "vb1": VBs[0] if model == "BayesRR2" else VB[0],
+        hat = T.g[0].fitted(B[0], MU) + T.g[1].fitted(B[1])  # fit = X1 B1 + X2 B2 + MU (:1063-1064)
+        out = {"hat": hat, "mu": MU, "b1": B[0], "b2": B[1], "vb1": VBs[0] if model == "BayesRR2" else VB[0],
                "vb2": VBs[1] if model == "BayesRR2" else VB[1], "ve": VE, "h2": vg / (vg + VE)}
         if model == "BayesB2":
             out["d1"], out["d2"] = D[0], D[1]

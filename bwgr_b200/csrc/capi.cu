@@ -1954,6 +1954,30 @@ int bwgr_kmup_sweep(bwgr_handle* h, double* b, double* d, const double* xx, doub
   return 0;
 }
 
+// Fitted values of the handle's store: hat = mu + X b.  What the reference's drivers form as X * b (emML2's u1 = X1 * b1,
+// Rcpp20260726ai.cpp:1275-1276; the fit of the two-design samplers :1063, :1151, :1212; wgr's gen0 %*% B, R/wgr.R:147).
+int bwgr_fitted(bwgr_handle* h, const double* b, double mu, double* hat) {
+  if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
+  if (!b || !hat) return fail(BWGR_ERR_ARG, "null argument");
+  if (h->world > 1) return fail(BWGR_ERR_UNSUPPORTED, "bwgr_fitted on a row-sharded store");
+  if (h->col_offset.size()) return fail(BWGR_ERR_UNSUPPORTED, "this store holds integer codes + a constant per column: use the solvers that centre the columns themselves");
+  CU(cudaSetDevice(h->device));
+  const int64_t n = h->n, p = h->p;
+  std::vector<float> bf(p), hh(n);
+  for (int64_t j = 0; j < p; j++) bf[j] = (float)b[j];
+  const float m0 = (float)mu;
+  DevBuf<float> bdev, mudev, hatd;
+  if (bdev.alloc(p) != cudaSuccess || mudev.alloc(1) != cudaSuccess || hatd.alloc(h->ld) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  CU(cudaMemcpyAsync(bdev.p, bf.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(mudev.p, &m0, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  int rc = fit_hat(h, bdev.p, mudev.p, hatd.p);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(hh.data(), hatd.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int64_t i = 0; i < n; i++) hat[i] = hh[i];
+  return 0;
+}
+
 // wgr(y, X, it, bi, th, bag = 1, rp = FALSE, iv, de, pi, df, R2, eigK = NULL) (R/wgr.R:2-169) with the MCMC loop on the device.
 int bwgr_wgr_fit(bwgr_handle* h, const double* y, int it, int bi, int th, int iv, int de, double pi, double df, double R2,
                  uint64_t seed, double* b, double* d, double* Vb, double* hat, double* scal) {

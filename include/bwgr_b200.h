@@ -149,7 +149,7 @@ BWGR_API int bwgr_em_end(bwgr_handle* h, bwgr_em_out* out);
 /* ---- univariate Gibbs family --------------------------------------------------------------- */
 typedef struct {
   int model;    /* bwgr_gibbs_model */
-  int nchains;  /* independent chains of the same model on the same y (seeds seed, seed+1, ...) */
+  int nchains;  /* independent chains of the same model on the same y (one seed; the chain index enters the Philox counter, so the chains draw from disjoint streams) */
   int it, bi;   /* reference defaults 1500, 500 */
   double pi, df, R2; /* 0.95, 5, 0.5 */
   uint64_t seed;
@@ -171,6 +171,10 @@ BWGR_API int bwgr_gibbs_fit(bwgr_handle* h, const bwgr_gibbs_params* par, const 
  * :25-27 but free of the exp underflow. */
 BWGR_API int bwgr_kmup_sweep(bwgr_handle* h, double* b, double* d, const double* xx, double* e, const double* L, double Ve,
                     double pi, uint64_t seed);
+
+/* hat[n] = mu + X b on the handle's store: the X * b the reference's drivers form around the marker loop (emML2's u1 = X1 * b1,
+ * Rcpp20260726ai.cpp:1275-1276; the fitted values of the two-design samplers :1063, :1151, :1212; wgr's gen0 %*% B, R/wgr.R:147). */
+BWGR_API int bwgr_fitted(bwgr_handle* h, const double* b, double mu, double* hat);
 
 /* KMUP2(X,Use,b,d,xx,E,L,Ve,pi) (:41-77), the bagged sweep of wgr(bag != 1): only the rows Use (0-based, as R passes them) enter.
  * b, d updated in place; e_out [nuse] = the residuals of the rows in use, in the order of Use (the reference's third list element).

@@ -997,14 +997,15 @@ def test_two_design_gibbs(tpod, model):
     A = np.mean([r["hat"] for r in ora], 0); B = np.mean([r["hat"] for r in gpu], 0)
     A1 = np.mean([r["hat"] for r in ora[:3]], 0); A2 = np.mean([r["hat"] for r in ora[3:]], 0)
     assert np.corrcoef(A, B)[0, 1] > min(0.99, np.corrcoef(A1, A2)[0, 1] - 0.005)
-    for q in ("1", "2"):  # fitted values of each design from the posterior means
-        a = np.mean([np.mean(r["vb" + q]) for r in ora]); b = np.mean([np.mean(r["vb" + q]) for r in gpu])
-        assert abs(a - b) <= 0.1 * a, ("vb" + q, a, b)
+    for q in ("1", "2"):  # marker variances of each design (one scalar per chain for BayesRR2: the noisiest summary)
+        a = np.array([np.mean(r["vb" + q]) for r in ora]); b = np.array([np.mean(r["vb" + q]) for r in gpu])
+        se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+        assert abs(a.mean() - b.mean()) <= 4 * se + 0.05 * a.mean(), ("vb" + q, a.mean(), b.mean(), se)
     if model == "BayesB2":
         da = np.mean([r["d1"].mean() for r in ora]); db = np.mean([r["d1"].mean() for r in gpu])
         assert abs(da - db) < 0.03
     hat = gpu[0]["mu"] + X1.astype(np.float64) @ gpu[0]["b1"] + X2.astype(np.float64) @ gpu[0]["b2"]
-    assert np.abs(hat - gpu[0]["hat"]).max() <= 1e-4 * np.abs(hat).max() + 1e-5  # hat = y - mean residual IS MU + X1 B1 + X2 B2
+    assert np.abs(hat - gpu[0]["hat"]).max() <= 1e-4 * np.abs(hat).max() + 1e-5  # fit = X1 B1 + X2 B2 + MU on the device
 
 
 @pytest.mark.parametrize("path", [1, 2])
