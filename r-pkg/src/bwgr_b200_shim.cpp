@@ -244,6 +244,139 @@ BEGIN_RCPP
 END_RCPP
 }
 
+// ---- two-design solvers (glue :291-355; Rcpp20260726ai.cpp:990-1305): y = mu + X1 b1 + X2 b2 + e.  Two handles, one store each; the
+// marker loops of the reference are bwgr_kmup_sweep on each store with the shared residual (BayesB2's step IS KMUP's, :1106-1118; the
+// others are its pi = 0 case; emML2 its Ve -> 0 limit), everything around them is the reference's own driver arithmetic.  Same loops
+// as bwgr_b200/api.py: _gibbs2 / emML2, which is what tests/ runs ----
+namespace {
+struct Design {
+  bwgr_handle* h = nullptr;
+  int64_t n = 0, p = 0;
+  NumericVector xx;
+  double MSx = 0;
+};
+Design design(int slot, SEXP XSEXP) {  // slot 0 / 1: one handle per design, stores cached by matrix pointer like load()
+  static bwgr_handle* hs[2] = {nullptr, nullptr};
+  static const double* last[2] = {nullptr, nullptr};
+  static int64_t ln[2] = {0, 0}, lp[2] = {0, 0};
+  NumericMatrix X(XSEXP);
+  Design d;
+  d.n = X.nrow(); d.p = X.ncol();
+  if (!hs[slot] && bwgr_create(0, &hs[slot]) != BWGR_OK) Rcpp::stop(bwgr_last_error());
+  d.h = hs[slot];
+  if (X.begin() != last[slot] || d.n != ln[slot] || d.p != lp[slot]) {
+    int rc = bwgr_geno_load_f64(d.h, X.begin(), d.n, d.p, d.n, BWGR_STORE_I8);
+    if (rc == BWGR_ERR_ARG) rc = bwgr_geno_load_f64(d.h, X.begin(), d.n, d.p, d.n, BWGR_STORE_F32);
+    check(rc);
+    last[slot] = X.begin(); ln[slot] = d.n; lp[slot] = d.p;
+  }
+  d.xx = NumericVector(d.p);
+  NumericVector sx(d.p);
+  check(bwgr_geno_stats(d.h, d.xx.begin(), sx.begin()));
+  for (int64_t j = 0; j < d.p; j++) d.MSx += (d.xx[j] - sx[j] * sx[j] / (double)d.n) / ((double)d.n - 1.0);  // sum of fvar(x_j)
+  return d;
+}
+double var1(const NumericVector& y) { double m = Rcpp::mean(y), s = 0; for (double v : y) s += (v - m) * (v - m); return s / (y.size() - 1.0); }
+
+SEXP gibbs2(int model /* 0 A2, 1 B2, 2 RR2 */, SEXP ySEXP, SEXP X1SEXP, SEXP X2SEXP, double it, double bi, double pi, double df, double R2) {
+  Rcpp::RNGScope scope;
+  NumericVector y(ySEXP);
+  Design T[2] = {design(0, X1SEXP), design(1, X2SEXP)};
+  const int64_t n = T[0].n;
+  if (T[1].n != n || y.size() != n) Rcpp::stop("y, X1 and X2 disagree on the number of individuals");
+  const int iit = (int)it, ibi = (int)bi;
+  const double vy = var1(y), Se = (1 - R2) * df * vy;
+  double Sb[2], vbs[2] = {0, 0}, VBs[2] = {0, 0}, mu = Rcpp::mean(y), ve = vy, MU = 0, VE = 0;
+  NumericVector b[2], d[2], vb[2], L[2], B[2], D[2], VB[2], e = y - mu;
+  for (int q = 0; q < 2; q++) {
+    const int64_t p = T[q].p;
+    Sb[q] = R2 * df * vy / T[q].MSx;
+    b[q] = NumericVector(p); d[q] = NumericVector(p); B[q] = NumericVector(p); D[q] = NumericVector(p); VB[q] = NumericVector(p);
+    vb[q] = NumericVector(p, Sb[q]);
+    L[q] = model == 2 ? NumericVector(p, T[q].MSx) : NumericVector(ve / vb[q]);
+  }
+  for (int i = 0; i < iit; i++) {
+    for (int q = 0; q < 2; q++) {
+      check(bwgr_kmup_sweep(T[q].h, b[q].begin(), d[q].begin(), T[q].xx.begin(), e.begin(), L[q].begin(), ve, model == 1 ? pi : 0.0, seed_from_R()));
+      if (model != 2) for (int64_t j = 0; j < T[q].p; j++) vb[q][j] = (Sb[q] + b[q][j] * b[q][j]) / R::rchisq(df + 1);
+    }
+    const double eM = R::rnorm(Rcpp::mean(e), std::sqrt(ve / n));
+    mu += eM; e = e - eM;
+    ve = (Rcpp::sum(e * e) + Se) / R::rchisq(n + df);
+    for (int q = 0; q < 2; q++) {
+      if (model == 2) { vbs[q] = (Sb[q] + Rcpp::sum(b[q] * b[q])) / R::rchisq(df + T[q].p); L[q] = NumericVector(T[q].p, ve / vbs[q]); }
+      else L[q] = ve / vb[q];
+    }
+    if (i > ibi) { MU += mu; VE += ve; for (int q = 0; q < 2; q++) { B[q] += b[q]; D[q] += d[q]; VB[q] += vb[q]; VBs[q] += vbs[q]; } }
+  }
+  const double MCMC = it - bi;
+  MU /= MCMC; VE /= MCMC;
+  for (int q = 0; q < 2; q++) { B[q] = B[q] / MCMC; D[q] = D[q] / MCMC; VB[q] = VB[q] / MCMC; VBs[q] /= MCMC; }
+  const double vg = model == 2 ? VBs[0] * T[0].MSx + VBs[1] * T[1].MSx : Rcpp::sum(VB[0]) + Rcpp::sum(VB[1]);
+  NumericVector fit(n), u2(n);
+  check(bwgr_fitted(T[0].h, B[0].begin(), MU, fit.begin()));
+  check(bwgr_fitted(T[1].h, B[1].begin(), 0.0, u2.begin()));
+  fit = fit + u2;
+  if (model == 1)
+    return List::create(Named("mu") = MU, Named("b1") = B[0], Named("b2") = B[1], Named("d1") = D[0], Named("d2") = D[1], Named("hat") = fit,
+                        Named("vb1") = VB[0], Named("vb2") = VB[1], Named("ve") = VE, Named("h2") = vg / (vg + VE));
+  if (model == 2)
+    return List::create(Named("hat") = fit, Named("mu") = MU, Named("b1") = B[0], Named("b2") = B[1], Named("vb1") = VBs[0], Named("vb2") = VBs[1],
+                        Named("ve") = VE, Named("h2") = vg / (vg + VE));
+  return List::create(Named("hat") = fit, Named("mu") = MU, Named("b1") = B[0], Named("b2") = B[1], Named("vb1") = VB[0], Named("vb2") = VB[1],
+                      Named("ve") = VE, Named("h2") = vg / (vg + VE));
+}
+}  // namespace
+RcppExport SEXP _bWGR_BayesA2(SEXP ySEXP, SEXP X1SEXP, SEXP X2SEXP, SEXP itSEXP, SEXP biSEXP, SEXP dfSEXP, SEXP R2SEXP) {
+BEGIN_RCPP
+  return gibbs2(0, ySEXP, X1SEXP, X2SEXP, Rcpp::as<double>(itSEXP), Rcpp::as<double>(biSEXP), 0, Rcpp::as<double>(dfSEXP), Rcpp::as<double>(R2SEXP));
+END_RCPP
+}
+RcppExport SEXP _bWGR_BayesB2(SEXP ySEXP, SEXP X1SEXP, SEXP X2SEXP, SEXP itSEXP, SEXP biSEXP, SEXP piSEXP, SEXP dfSEXP, SEXP R2SEXP) {
+BEGIN_RCPP
+  return gibbs2(1, ySEXP, X1SEXP, X2SEXP, Rcpp::as<double>(itSEXP), Rcpp::as<double>(biSEXP), Rcpp::as<double>(piSEXP), Rcpp::as<double>(dfSEXP),
+                Rcpp::as<double>(R2SEXP));
+END_RCPP
+}
+RcppExport SEXP _bWGR_BayesRR2(SEXP ySEXP, SEXP X1SEXP, SEXP X2SEXP, SEXP itSEXP, SEXP biSEXP, SEXP dfSEXP, SEXP R2SEXP) {
+BEGIN_RCPP
+  return gibbs2(2, ySEXP, X1SEXP, X2SEXP, Rcpp::as<double>(itSEXP), Rcpp::as<double>(biSEXP), 0, Rcpp::as<double>(dfSEXP), Rcpp::as<double>(R2SEXP));
+END_RCPP
+}
+RcppExport SEXP _bWGR_emML2(SEXP ySEXP, SEXP X1SEXP, SEXP X2SEXP, SEXP D1SEXP, SEXP D2SEXP) {
+BEGIN_RCPP
+  NumericVector y(ySEXP);
+  Design T[2] = {design(0, X1SEXP), design(1, X2SEXP)};
+  const int64_t n = T[0].n;
+  if (T[1].n != n || y.size() != n) Rcpp::stop("y, X1 and X2 disagree on the number of individuals");
+  SEXP Ds[2] = {D1SEXP, D2SEXP};
+  NumericVector b[2], bc[2], u[2], ones[2], L[2], e = y - Rcpp::mean(y), cY(n);
+  double Lmb[2], vb[2] = {0, 0}, mu = Rcpp::mean(y), ve = 0;
+  for (int q = 0; q < 2; q++) {
+    b[q] = NumericVector(T[q].p); u[q] = NumericVector(n); ones[q] = NumericVector(T[q].p, 1.0); Lmb[q] = T[q].MSx;
+    if (!Rf_isNull(Ds[q]) && NumericVector(Ds[q]).size() != T[q].p) Rcpp::stop("emML2: one weight per marker");
+  }
+  for (int numit = 0; numit < 350; numit++) {  // :1224, :1259-1296
+    for (int q = 0; q < 2; q++) {
+      bc[q] = Rcpp::clone(b[q]);
+      L[q] = Rf_isNull(Ds[q]) ? NumericVector(T[q].p, Lmb[q]) : NumericVector(Lmb[q] / NumericVector(Ds[q]));
+      check(bwgr_kmup_sweep(T[q].h, b[q].begin(), ones[q].begin(), T[q].xx.begin(), e.begin(), L[q].begin(), 1e-30, 0.0, 1));  // ridge step
+    }
+    for (int q = 0; q < 2; q++) check(bwgr_fitted(T[q].h, b[q].begin(), 0.0, u[q].begin()));  // u = X b (:1275-1276)
+    const double eM = Rcpp::mean(e);
+    mu += eM; e = e - eM;
+    cY = u[0] + u[1] + e;
+    ve = Rcpp::sum(e * cY) / n;
+    for (int q = 0; q < 2; q++) { vb[q] = Rcpp::sum(u[q] * cY) / n / T[q].MSx; Lmb[q] = ve / vb[q]; }
+    if (Rcpp::sum(Rcpp::abs(bc[0] - b[0])) + Rcpp::sum(Rcpp::abs(bc[1] - b[1])) < 10e-8) break;
+  }
+  NumericVector fit = u[0] + u[1] + mu;
+  return List::create(Named("mu") = mu, Named("b1") = b[0], Named("b2") = b[1], Named("Vb1") = vb[0], Named("Vb2") = vb[1], Named("Ve") = ve,
+                      Named("u1") = u[0], Named("u2") = u[1], Named("MSx1") = T[0].MSx, Named("MSx2") = T[1].MSx,
+                      Named("h2") = 1 - ve / var1(y), Named("hat") = fit);
+END_RCPP
+}
+
 // ---- GSRR / GSFLM: the warm-start solvers of mm() (glue :493-527; lists Rcpp20260726ai.cpp:1591-1593, :1625-1627) ----
 static SEXP gs_call(int which, SEXP ySEXP, SEXP eSEXP, SEXP genSEXP, SEXP bSEXP, SEXP LmbSEXP, SEXP xxSEXP, SEXP cxxSEXP, SEXP maxitSEXP) {
   int64_t n, p;
