@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbwgr_b200.so")
+LIB_PATH = os.environ.get("BWGR_LIB") or os.path.join(_HERE, "lib", "libbwgr_b200.so")  # BWGR_LIB: another build of the same library (A/B runs)
 
 # every symbol include/bwgr_b200.h declares (tests check the shared object exports all of them)
 SYMBOLS = [
