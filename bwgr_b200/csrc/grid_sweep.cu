@@ -244,17 +244,16 @@ __global__ void __launch_bounds__(kT, 1) grid_sweep_kernel(GridArgs a) {
 // they stand at the start of the block, and the cross products x_j'x_i of the block (integers for the int8 store: exact).  Every CTA
 // then walks the block alike: the dot of marker j is corrected by the steps already taken in the block,
 // g_j = g_j(stale) - sum_{i<j} (x_j'x_i) de_i -- the same algebra as the blocked family, on CUDA cores -- and the residual slab gets the
-// block's update at once.
-constexpr int kGB = 16;                       // markers per block
+// block's update at once.  The cross products do not depend on the residuals: they are summed one block AHEAD, by the warps that do
+// not poll, while the polling warps (one thread per word) wait for the current block's totals; before the wait a CTA only has its 16
+// dot products to add.  Measured at n = 100,000 (profiles/r2_grid_block_probe.txt): 0.51 us per marker (1.88 one marker per sum).
+constexpr int kGB = 16;                       // markers per block (measured: 32 is 10 % slower per marker, the chain and the payload grow)
 constexpr int kGP = kGB * (kGB - 1) / 2;      // cross products per block
 constexpr int kGR = 3;                        // blocks in flight
 constexpr int kJR = kGR + 1;                  // marker indices are staged one block further ahead
 constexpr int kTB = 1024;                     // threads per CTA of the blocked variant: its phases are short dependent chains, 32 warps hide them
-// pair index pr = j (j - 1) / 2 + i (i < j) -> j
-__constant__ unsigned char kPairJ[kGP] = {1, 2, 2, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 7, 8, 8, 8, 8, 8, 8, 8, 8,
-                                          9, 9, 9, 9, 9, 9, 9, 9, 9, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 11, 11, 11, 11, 11, 11, 11, 11, 11, 11, 11,
-                                          12, 12, 12, 12, 12, 12, 12, 12, 12, 12, 12, 12, 13, 13, 13, 13, 13, 13, 13, 13, 13, 13, 13, 13, 13,
-                                          14, 14, 14, 14, 14, 14, 14, 14, 14, 14, 14, 14, 14, 14, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15};
+constexpr int kCB = kGridCopies;              // accumulator copies (power of two; 4, 8, 16 measured alike)
+static_assert(kGB <= 32 && kGB * 32 + kGP <= kTB, "one dot warp per marker, one polling thread per word");
 
 struct GridBlockSmem {
   float* E;                 // [ns][rp]
@@ -265,6 +264,7 @@ struct GridBlockSmem {
   float* de;                // [kGB][32]
   SysScalars* sc;           // [ns]
   MarkerDraws* dr;          // [2][kGB][32]
+  unsigned char* pj;        // [kGP] pair index pr = j (j - 1) / 2 + i (i < j) -> j
 };
 
 __host__ __device__ inline size_t grid_block_carve(unsigned char* base, int ns, int rp, int xbytes, bool gibbs, GridBlockSmem* s) {
@@ -281,8 +281,9 @@ __host__ __device__ inline size_t grid_block_carve(unsigned char* base, int ns, 
   float* de = reinterpret_cast<float*>(take(sizeof(float) * kGB * 32));
   SysScalars* sc = reinterpret_cast<SysScalars*>(take(sizeof(SysScalars) * (size_t)ns));
   MarkerDraws* dr = reinterpret_cast<MarkerDraws*>(take(gibbs ? sizeof(MarkerDraws) * 2 * kGB * 32 : 0));
+  unsigned char* pj = take(kGP);
   if (s) {
-    s->E = E; s->tot = tot; s->de = de; s->sc = sc; s->dr = dr;
+    s->E = E; s->tot = tot; s->de = de; s->sc = sc; s->dr = dr; s->pj = pj;
     for (int d = 0; d < kGR; d++) { s->xs[d] = xs[d]; s->vin[d] = vin[d]; }
     for (int d = 0; d < kJR; d++) s->Js[d] = Js[d];
   }
@@ -309,6 +310,8 @@ __global__ void __launch_bounds__(kTB, 1) grid_block_kernel(GridArgs a) {
   for (int q = tid; q < kGR * kGB * 100; q += kTB) s.vin[0][q] = 0.0f;
   if (tid < ns) s.sc[tid] = a.sc[tid];
   if (tid == 0) s_abort = 0;
+  for (int j = 1 + warp; j < kGB; j += kTB / 32)
+    for (int i = lane; i < j; i += 32) s.pj[j * (j - 1) / 2 + i] = (unsigned char)j;
   __syncthreads();  // the zeroed ring slots are in place before any cp.async lands in them
   const int nch = rp * (int)sizeof(XT) / 16;
   constexpr int kRowsPerChunk = 16 / (int)sizeof(XT);
@@ -323,21 +326,27 @@ __global__ void __launch_bounds__(kTB, 1) grid_block_kernel(GridArgs a) {
   };
   auto prefetch = [&](int blk) {
     if (blk < nblk) {
-      const int slot = blk % kGR;
+      const int slot = blk % kGR, nb = min(kGB, p - blk * kGB);
       const int* Jv = s.Js[blk % kJR];
-      for (int j = 0; j < kGB; j++) {
-        const int m = blk * kGB + j;
-        if (m >= p) break;
-        const int J = Jv[j];
-        const unsigned char* col = sizeof(XT) == 1 ? reinterpret_cast<const unsigned char*>(a.g.x8 + (int64_t)J * ld + r0)
-                                                   : reinterpret_cast<const unsigned char*>(a.g.xf + (int64_t)J * ld + r0);
-        unsigned char* dst = s.xs[slot] + (size_t)j * rp * sizeof(XT);
-        for (int c = tid; c < nch; c += kTB)
-          if (r0 + (int64_t)kRowsPerChunk * c < ld) gcp16(dst + 16 * c, col + 16 * c);
-        float* v = s.vin[slot] + j * 100;
-        if (tid < 32) { if (tid < ns) gcp4(v + tid, a.b + (size_t)tid * p + J); }
-        else if (tid < 64) { const int t = tid - 32; if (t < ns && a.vbv) gcp4(v + 32 + t, a.vbv + (size_t)t * p + J); }
-        else if (tid < 96) { const int t = tid - 64; if (t < ns) gcp4(v + 64 + t, a.xx + (a.xx_per_sys ? (size_t)t * p : 0) + J); }
+      // the block's column slabs as (marker, 16-byte chunk) pairs dealt over the CTA: one pass, no per-marker loop on every thread
+      for (int q = tid; q < nb * nch; q += kTB) {
+        const int j = q / nch, c = q - j * nch;
+        if (r0 + (int64_t)kRowsPerChunk * c < ld) {
+          const int64_t off = (int64_t)Jv[j] * ld + r0;
+          const unsigned char* col = sizeof(XT) == 1 ? reinterpret_cast<const unsigned char*>(a.g.x8 + off) : reinterpret_cast<const unsigned char*>(a.g.xf + off);
+          gcp16(s.xs[slot] + (size_t)j * rp * sizeof(XT) + 16 * c, col + 16 * c);
+        }
+      }
+      // the markers' inputs (b0 | vb_j | xx per system), dealt from the other end of the CTA
+      for (int q = kTB - 1 - tid; q < nb * 96; q += kTB) {
+        const int j = q / 96, w = (q - j * 96) >> 5, t = q & 31;
+        if (t < ns) {
+          const int J = Jv[j];
+          float* v = s.vin[slot] + j * 100 + 32 * w + t;
+          if (w == 0) gcp4(v, a.b + (size_t)t * p + J);
+          else if (w == 1) { if (a.vbv) gcp4(v, a.vbv + (size_t)t * p + J); }
+          else gcp4(v, a.xx + (a.xx_per_sys ? (size_t)t * p : 0) + J);
+        }
       }
     }
     gcp_commit();
@@ -352,112 +361,113 @@ __global__ void __launch_bounds__(kTB, 1) grid_block_kernel(GridArgs a) {
                                                           s.sc[t].df, a.seed_lo, a.seed_hi);
     }
   };
+  const unsigned long long t_start = gtimer();
+  const double inv_q = (double)a.g_quantum, qinv = 1.0 / (double)a.g_quantum;
+  const double inv_qG = (double)a.gram_quantum, qinvG = 1.0 / (double)a.gram_quantum;
+  // cross products x_j'x_i (i < j) of a block: E-independent, so they are summed over the grid one block AHEAD of their use -- while the
+  // polling warps wait for the current block's totals -- by the warps w0, w0 + 1, ... of the CTA
+  auto cross_tasks = [&](int blk, int w0) {
+    if (blk >= nblk) return;
+    const XT* xs = reinterpret_cast<const XT*>(s.xs[blk % kGR]);
+    unsigned long long* accw = a.acc + ((size_t)blk * kCB + (cta & (kCB - 1))) * W + ndot;
+    for (int pr = warp - w0; pr < kGP; pr += kTB / 32 - w0) {
+      const int j = s.pj[pr], i2 = pr - j * (j - 1) / 2;
+      double v;
+      if constexpr (sizeof(XT) == 1) {
+        const int* wj = reinterpret_cast<const int*>(xs + (size_t)j * rp);
+        const int* wi = reinterpret_cast<const int*>(xs + (size_t)i2 * rp);
+        int acc = 0;
+        for (int q = lane; q < rp / 4; q += 32) acc = __dp4a(wj[q], wi[q], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        v = (double)acc * qinvG;
+      } else {
+        const float* fj = reinterpret_cast<const float*>(xs + (size_t)j * rp);
+        const float* fi = reinterpret_cast<const float*>(xs + (size_t)i2 * rp);
+        float acc = 0.0f;
+        for (int q = lane; q < rp; q += 32) acc = fmaf(fj[q], fi[q], acc);
+        v = (double)warp_sum(acc) * qinvG;
+      }
+      if (lane == 0) atomicAdd(accw + pr, ((unsigned long long)__double2ll_rn(v) << 8) + 1ull);
+    }
+  };
+  const int nw = ndot + kGP;            // words of a block: one polling thread each (nw <= 16 * 32 + 120 < kTB)
+  const int npollw = (nw + 31) / 32;    // the polling warps; the others work ahead while these wait
   for (int b = 0; b < kGR; b++) load_js(b);
   __syncthreads();
   for (int b = 0; b < kGR - 1; b++) prefetch(b);
   draws_for(0);
-  const unsigned long long t_start = gtimer();
-  const double inv_q = (double)a.g_quantum, qinv = 1.0 / (double)a.g_quantum;
-  const double inv_qG = (double)a.gram_quantum, qinvG = 1.0 / (double)a.gram_quantum;
+  gcp_wait<0>();
+  __syncthreads();
+  cross_tasks(0, 0);
   for (int blk = 0; blk < nblk; blk++) {
-    gcp_wait<kGR - 2>();
-    __syncthreads();  // block blk's slot has landed; block blk - 1 is finished by every thread
+    gcp_wait<0>();    // block blk + 1's slab (issued one whole block ago) has landed, block blk's long since
+    __syncthreads();  // ... for every thread; block blk - 1 is finished by every thread
     prefetch(blk + kGR - 1);
     const int slot = blk % kGR, nb = min(kGB, p - blk * kGB);
     const int* Jcur = s.Js[blk % kJR];
     const XT* xs = reinterpret_cast<const XT*>(s.xs[slot]);
-    unsigned long long* accw = a.acc + ((size_t)blk * kC + (cta & (kC - 1))) * W;
-    // ---- the block's 16 dot tasks (marker j with the residuals as they stand) and 120 cross-product tasks (x_j'x_i, i < j), dealt
-    // round-robin over the 32 warps
-    for (int task = warp; task < kGB + kGP; task += kTB / 32) {
-      if (task < kGB) {
-        const int j = task;
-        if (j >= nb) continue;
-        const XT* xj = xs + (size_t)j * rp;
-        if (ns == 1) {
-          float acc = 0.0f;
-          for (int i = lane; i < rp; i += 32) acc = fmaf((float)xj[i], s.E[i], acc);
-          const double v = (double)warp_sum(acc) * qinv;
-          if (lane == 0) {
-            if (!(fabs(v) < 4503599627370496.0)) atomicExch(a.err, 4);
-            atomicAdd(accw + j, ((unsigned long long)__double2ll_rn(v) << 8) + 1ull);
+    unsigned long long* accw = a.acc + ((size_t)blk * kCB + (cta & (kCB - 1))) * W;
+    // ---- the block's dot tasks (marker j with the residuals as they stand), one warp each
+    if (warp < nb) {
+      const int j = warp;
+      const XT* xj = xs + (size_t)j * rp;
+      if (ns == 1) {
+        float acc = 0.0f;
+        for (int i = lane; i < rp; i += 32) acc = fmaf((float)xj[i], s.E[i], acc);
+        const double v = (double)warp_sum(acc) * qinv;
+        if (lane == 0) {
+          if (!(fabs(v) < 4503599627370496.0)) atomicExch(a.err, 4);
+          atomicAdd(accw + j, ((unsigned long long)__double2ll_rn(v) << 8) + 1ull);
+        }
+      } else {
+        for (int t0 = 0; t0 < ns; t0 += 4) {
+          const int nt = min(4, ns - t0);
+          float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          for (int i = lane; i < rp; i += 32) {
+            const float x = (float)xj[i];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+              if (q < nt) acc[q] = fmaf(x, s.E[(t0 + q) * rp + i], acc[q]);
           }
-        } else {
-          for (int t0 = 0; t0 < ns; t0 += 4) {
-            const int nt = min(4, ns - t0);
-            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            for (int i = lane; i < rp; i += 32) {
-              const float x = (float)xj[i];
 #pragma unroll
-              for (int q = 0; q < 4; q++)
-                if (q < nt) acc[q] = fmaf(x, s.E[(t0 + q) * rp + i], acc[q]);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              if (q < nt) {
-                const double v = (double)warp_sum(acc[q]) * qinv;
-                if (lane == 0) {
-                  if (!(fabs(v) < 4503599627370496.0)) atomicExch(a.err, 4);
-                  atomicAdd(accw + j * ns + t0 + q, ((unsigned long long)__double2ll_rn(v) << 8) + 1ull);
-                }
+          for (int q = 0; q < 4; q++) {
+            if (q < nt) {
+              const double v = (double)warp_sum(acc[q]) * qinv;
+              if (lane == 0) {
+                if (!(fabs(v) < 4503599627370496.0)) atomicExch(a.err, 4);
+                atomicAdd(accw + j * ns + t0 + q, ((unsigned long long)__double2ll_rn(v) << 8) + 1ull);
               }
             }
           }
         }
-      } else {
-        const int pr = task - kGB, j = kPairJ[pr], i2 = pr - j * (j - 1) / 2;
-        double v;
-        if constexpr (sizeof(XT) == 1) {
-          const int* wj = reinterpret_cast<const int*>(xs + (size_t)j * rp);
-          const int* wi = reinterpret_cast<const int*>(xs + (size_t)i2 * rp);
-          int acc = 0;
-          for (int q = lane; q < rp / 4; q += 32) acc = __dp4a(wj[q], wi[q], acc);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-          v = (double)acc * qinvG;
-        } else {
-          const float* fj = reinterpret_cast<const float*>(xs + (size_t)j * rp);
-          const float* fi = reinterpret_cast<const float*>(xs + (size_t)i2 * rp);
-          float acc = 0.0f;
-          for (int q = lane; q < rp; q += 32) acc = fmaf(fj[q], fi[q], acc);
-          v = (double)warp_sum(acc) * qinvG;
-        }
-        if (lane == 0) atomicAdd(accw + ndot + pr, ((unsigned long long)__double2ll_rn(v) << 8) + 1ull);
       }
     }
     load_js(blk + kGR);
-    // ---- the block's totals: every word is complete when its low byte counts all the CTAs of its copy
-    {
-      const int nw = ndot + kGP;
+    if (warp >= npollw) {
+      cross_tasks(blk + 1, npollw);  // next block's cross products, under this block's wait
+    } else if (tid < nw && !(tid < ndot && tid / ns >= nb)) {  // markers past the end of the last block are never added
+      // ---- the block's totals, one word per polling thread: a word is complete when its low byte counts all the CTAs of its copy
+      const unsigned long long* src = a.acc + (size_t)blk * kCB * W + tid;
       unsigned int spins = 0;
       for (;;) {
-        bool pending = false;
-        for (int wd = tid; wd < nw; wd += kTB) {
-          const int jw = wd < ndot ? wd / ns : 0;
-          if (wd < ndot && jw >= nb) continue;  // markers past the end of the last block are never added
-          const unsigned long long* src = a.acc + (size_t)blk * kC * W + wd;
-          long long tot = 0;
-          bool done = true;
+        long long tot = 0;
+        bool done = true;
 #pragma unroll
-          for (int c = 0; c < kC; c++) {
-            const unsigned long long w = gld_relaxed(src + (size_t)c * W);
-            done &= (int)(w & 0xffull) == (G + kC - 1 - c) / kC;
-            tot += (long long)w >> 8;
-          }
-          if (done) {
-            s.tot[wd] = (float)((double)tot * (wd < ndot ? inv_q : inv_qG));
-          } else pending = true;
+        for (int c = 0; c < kCB; c++) {
+          const unsigned long long w = gld_relaxed(src + (size_t)c * W);
+          done &= (int)(w & 0xffull) == (G + kCB - 1 - c) / kCB;
+          tot += (long long)w >> 8;
         }
-        if ((++spins & 0x3ffu) == 0 && tid == 0) {
-          if (*reinterpret_cast<volatile int*>(a.err) != 0) s_abort = 1;
-          else if (gtimer() - t_start > 120000000000ull) { atomicExch(a.err, 3); s_abort = 1; }  // two minutes without the grid
+        if (done) { s.tot[tid] = (float)((double)tot * (tid < ndot ? inv_q : inv_qG)); break; }
+        if ((++spins & 0x3ffu) == 0) {
+          if (*reinterpret_cast<volatile int*>(a.err) != 0) { s_abort = 1; break; }
+          if (gtimer() - t_start > 120000000000ull) { atomicExch(a.err, 3); s_abort = 1; break; }  // two minutes without the grid
         }
-        if (!__syncthreads_or(pending ? 1 : 0)) break;
-        if (s_abort) break;
       }
-      if (s_abort) return;
     }
     __syncthreads();
+    if (s_abort) return;
     // ---- the block's chain, by every CTA alike: lane t of warp 0 walks system t; the other warps draw for the next block
     if (warp == 0) {
       if (lane < ns) {
@@ -537,7 +547,7 @@ cudaError_t launch_grid_model(const GridArgs& a, int grid, cudaStream_t st) {
 size_t grid_block_smem(int nsys, int rows_per_cta, bool real_store, bool gibbs) {
   return grid_block_carve(nullptr, nsys, rows_per_cta, real_store ? 4 : 1, gibbs, nullptr) + 16;
 }
-size_t grid_block_acc_words(int nsys, int p) { return (size_t)((p + kGB - 1) / kGB) * kC * grid_block_words(nsys); }
+size_t grid_block_acc_words(int nsys, int p) { return (size_t)((p + kGB - 1) / kGB) * kCB * grid_block_words(nsys); }
 
 size_t grid_sweep_smem(int nsys, int rows_per_cta, bool masked, bool real_store) {
   return grid_carve(nullptr, nsys, rows_per_cta, masked, real_store ? 4 : 1, nullptr) + 16;
