@@ -423,15 +423,16 @@ def KMUP(X, b, d, xx, e, L, Ve, pi, seed=1, **store_kw):
 
 
 def KMUP2(X, Use, b, d, xx, E, L, Ve, pi, seed=1, **store_kw):
-    """The bagged Kuo-Mallick sweep, drop-in for KMUP2(X,Use,b,d,xx,E,L,Ve,pi) (Rcpp20260726ai.cpp:41-77): Use = 0-based rows (distinct);
-    returns (b, d, e) with e the residuals of the rows in use, like the reference's list."""
+    """The bagged Kuo-Mallick sweep, drop-in for KMUP2(X,Use,b,d,xx,E,L,Ve,pi) (Rcpp20260726ai.cpp:41-77): Use = 0-based rows; a row
+    named more than once (sampling with replacement) counts once per occurrence in the dot products, as in the reference's H / e0.
+    Returns (b, d, e) with e the residuals of the rows in use in the order of Use, like the reference's list."""
     g, own = _store(X, **store_kw)
     try:
         Use = np.array(Use, dtype=np.float64).ravel()
         b, d, xx, E, L = (np.array(v, dtype=np.float64) for v in (b, d, xx, E, L))
         _need(b.size == g.p and d.size == g.p and xx.size == g.p and L.size == g.p, "KMUP2: b, d, xx, L must have p = %d values" % g.p)
         _need(E.size == g.n, "KMUP2: E must have n = %d values" % g.n)
-        _need(2 <= Use.size <= g.n, "KMUP2: Use must name between 2 and n rows")
+        _need(Use.size >= 2, "KMUP2: Use must name at least 2 rows")
         e = np.zeros(Use.size)
         check(g.lib.bwgr_kmup2_sweep(g.h, _ptr(Use), int(Use.size), _ptr(b), _ptr(d), _ptr(xx), _ptr(E), _ptr(e), _ptr(L), float(Ve),
                                      float(pi), int(seed)))

@@ -164,7 +164,9 @@ struct Fit {
   std::vector<float> vy, MSx, cxx;      // per system constants needed for outputs
   std::vector<int> order;               // host marker order (cumulative shuffles)
   DevBuf<float> y, e, b, d, vbv, b_prev, B, D, VBv, xx_sys, gram, work;
-  DevBuf<uint8_t> mask;
+  DevBuf<uint8_t> mask, cnt;            // cnt / row_w: row multiplicities of a bagged sweep with replacement (uint8 and float)
+  DevBuf<float> row_w;
+  bool weighted = false;
   DevBuf<SysScalars> sc;
   DevBuf<int> perm;                     // [kPermRing][p]
   DevBuf<long long> gacc, trace;
@@ -876,6 +878,7 @@ struct FitSpec {
   int nsys;
   bool shuffled;
   const uint8_t* row_mask;  // host, n x nsys or null
+  const uint8_t* row_cnt = nullptr;  // KMUP2 on rows drawn with replacement: multiplicity of every row (host, n; nsys = 1), row_mask = cnt != 0
   float df, R2, Pi, alpha, pi;
   int it, bi;
   uint64_t seed;
@@ -972,7 +975,7 @@ void grid_geometry(bwgr_handle* h, int* rp, int* grid) {
 // family: 0 = small-n, 1 = blocked, 2 = grid
 int choose_path(bwgr_handle* h, const FitSpec& s, int* family) {
   const GenoView g = h->view();
-  const bool small_ok = h->storage != BWGR_STORE_F32 && small_n_fits(g, s.row_mask != nullptr, h->smem_optin);
+  const bool small_ok = h->storage != BWGR_STORE_F32 && small_n_fits(g, s.row_mask != nullptr, h->smem_optin, s.row_cnt != nullptr);
   const int grid = h->grid > 0 ? std::min(h->grid, h->num_sms) : h->num_sms;
   const int64_t rows = ((h->ld + grid - 1) / grid + 15) / 16 * 16;
   PipePlan pl;
@@ -1024,10 +1027,13 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
   int rc = choose_path(h, s, &family);
   h->path = saved_path_;
   if (rc) return rc;
+  if (s.row_cnt && family != 0)
+    return fail(BWGR_ERR_UNSUPPORTED, "KMUP2 on repeated rows (sampling with replacement) runs on the small-n family: needs the int8 / 2-bit store "
+                                      "and residual + multiplicities of n=%lld rows in one SM's shared memory", (long long)h->n);
   const bool blocked = family == 1;
   const int64_t n = h->n, p = h->p, ld = h->ld;
   const int ns = s.nsys;
-  f.model = s.model; f.nsys = ns; f.shuffled = s.shuffled; f.blocked = blocked; f.gridfam = family == 2; f.masked = s.row_mask != nullptr;
+  f.model = s.model; f.nsys = ns; f.shuffled = s.shuffled; f.blocked = blocked; f.gridfam = family == 2; f.masked = s.row_mask != nullptr; f.weighted = false;
   f.sweeps_issued = 0; f.seed = s.seed; f.gram_cached = false; f.skip_epilogue = false; f.wgr_mode = false; f.gram_p = nullptr;
   f.overlap = false; f.gram_ahead = -1;
   if (h->side) CU(cudaStreamSynchronize(h->side));  // a band computed ahead for a sweep the previous fit never ran
@@ -1514,7 +1520,7 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
       memset(&a, 0, sizeof a);
       a.g = g; a.model = rule_model(f.model); a.nsys = f.nsys; a.perms = d_perm; a.y = f.y.p; a.e = f.e.p; a.b = f.b.p; a.d = f.d.p;
       a.vbv = f.vbv.p; a.xx = f.masked ? f.xx_sys.p : (f.xx_over.p ? f.xx_over.p : h->xx_f.p); a.xx_per_sys = f.masked ? 1 : 0; a.mask = f.mask.p;
-      a.xx2 = f.xx_over.p;
+      a.xx2 = f.xx_over.p; a.row_w = f.weighted ? f.row_w.p : nullptr;
       a.sc = f.sc.p; a.seed_lo = (uint32_t)f.seed; a.seed_hi = (uint32_t)(f.seed >> 32); a.chain0 = 0; a.err = h->err.p;
       cudaEvent_t pe = h->prof_begin(1);
       launch_small_n(a, h->smem_optin, h->stream);
@@ -1887,15 +1893,38 @@ int bwgr_gibbs_fit(bwgr_handle* h, const bwgr_gibbs_params* par, const double* y
 }
 
 // Common start of KMUP / wgr: a one-system M_KMUP fit whose state (b, d, e, per-marker L, Ve, pi) is set by the caller.
+// Row multiplicities of a sweep over rows drawn with replacement (Use with repeats, :41-77): cnt [n] on the host -> the uint8 and
+// float copies on the device, and xx_sys = H'H over the rows in use with their multiplicities (the scale of the rule's
+// likelihood ratio).  The 0/1 mask (cnt != 0) is the caller's.
+static int set_row_multiplicities(bwgr_handle* h, const uint8_t* cnt) {
+  Fit& f = h->fit;
+  const int64_t n = h->n, p = h->p, ld = h->ld;
+  std::vector<uint8_t> c8((size_t)ld, 0);
+  std::vector<float> cf((size_t)ld, 0.0f);
+  for (int64_t i = 0; i < n; i++) { c8[i] = cnt[i]; cf[i] = (float)cnt[i]; }
+  DevBuf<double> txx, tsx;
+  if (f.cnt.alloc(ld) != cudaSuccess || f.row_w.alloc(ld) != cudaSuccess || txx.alloc(p) != cudaSuccess || tsx.alloc(p) != cudaSuccess)
+    return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
+  CU(cudaMemcpyAsync(f.cnt.p, c8.data(), (size_t)ld, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(f.row_w.p, cf.data(), sizeof(float) * ld, cudaMemcpyHostToDevice, h->stream));
+  launch_col_stats_cnt(h->view(), f.cnt.p, txx.p, tsx.p, h->stream);
+  launch_d_to_float(txx.p, f.xx_sys.p, (int)p, h->stream);
+  h->launches += 2;
+  CU(cudaStreamSynchronize(h->stream));  // c8 / cf / txx go out of scope
+  f.weighted = true;
+  return 0;
+}
+
 static int kmup_begin(bwgr_handle* h, const double* b, const double* d, const double* xx, const double* e, const double* L,
-                      double Ve, double pi, uint64_t seed, const uint8_t* row_mask = nullptr, double xx_scale = 1.0) {
+                      double Ve, double pi, uint64_t seed, const uint8_t* row_mask = nullptr, double xx_scale = 1.0,
+                      const uint8_t* row_cnt = nullptr) {
   if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
   if (!b || !e || !L) return fail(BWGR_ERR_ARG, "null argument");
   if (!(Ve > 0)) return fail(BWGR_ERR_ARG, "Ve must be positive");
   const int64_t n = h->n, p = h->p, ld = h->ld;
   FitSpec s;
   // row_mask = the bagged sweep KMUP2 (:41-77): the rows in use as a mask on the small-n family, xx_scale = bg = n0 / n (:47)
-  s.model = row_mask ? M_KMUP2 : M_KMUP; s.nsys = 1; s.shuffled = false; s.row_mask = row_mask;
+  s.model = row_mask ? M_KMUP2 : M_KMUP; s.nsys = 1; s.shuffled = false; s.row_mask = row_mask; s.row_cnt = row_mask ? row_cnt : nullptr;
   s.df = 5; s.R2 = 0.5f; s.Pi = 0; s.alpha = 0; s.pi = (float)pi; s.it = 1; s.bi = 0; s.seed = seed;
   if (row_mask && !xx) return fail(BWGR_ERR_ARG, "KMUP2 needs xx");
   int rc = fit_begin(h, s, e);  // y := e (only its mean/variance feed unused defaults)
@@ -1926,6 +1955,10 @@ static int kmup_begin(bwgr_handle* h, const double* b, const double* d, const do
     for (int64_t j = 0; j < p; j++) hx[j] = (float)xx[j] * (float)xx_scale;
     if (f.xx_over.alloc(p) != cudaSuccess) return fail(BWGR_ERR_CUDA, "cudaMalloc failed");
     CU(cudaMemcpyAsync(f.xx_over.p, hx.data(), sizeof(float) * p, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (s.row_cnt) {  // repeated rows: multiplicities for the dot products, and H'H with a row counted as often as it was drawn
+    rc = set_row_multiplicities(h, s.row_cnt);
+    if (rc) return rc;
   }
   CU(cudaStreamSynchronize(h->stream));
   return 0;
@@ -2053,15 +2086,19 @@ int bwgr_wgr_fit(bwgr_handle* h, const double* y, int it, int bi, int th, int iv
   return 0;
 }
 
-// Rows of one bagged iteration as a 0/1 mask.  use: 0-based row indices as R passes them (doubles).  Duplicates (sampling with
-// replacement, rp = TRUE) would need row multiplicities in the dot products: not built.
-static int use_to_mask(const double* use, int64_t nuse, int64_t n, std::vector<uint8_t>& mask) {
+// Rows of one bagged iteration as a 0/1 mask plus the multiplicity of every row.  use: 0-based row indices as R passes them
+// (doubles).  *repeats = some row occurs more than once (sampling with replacement, rp = TRUE).
+static int use_to_mask(const double* use, int64_t nuse, int64_t n, std::vector<uint8_t>& mask, std::vector<uint8_t>& cnt, bool* repeats) {
   mask.assign((size_t)n, 0);
+  cnt.assign((size_t)n, 0);
+  *repeats = false;
   for (int64_t q = 0; q < nuse; q++) {
     const int64_t r = (int64_t)use[q];
     if (r < 0 || r >= n) return fail(BWGR_ERR_ARG, "Use[%lld] = %lld is not a row of X", (long long)q, (long long)r);
-    if (mask[r]) return fail(BWGR_ERR_UNSUPPORTED, "KMUP2: repeated rows (sampling with replacement) are not on the B200 path");
+    if (cnt[r] == 255) return fail(BWGR_ERR_UNSUPPORTED, "KMUP2: row %lld occurs more than 255 times in Use", (long long)r);
+    if (mask[r]) *repeats = true;
     mask[r] = 1;
+    cnt[r]++;
   }
   return 0;
 }
@@ -2073,10 +2110,11 @@ int bwgr_kmup2_sweep(bwgr_handle* h, const double* use, int64_t nuse, double* b,
   if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
   if (!use || !E || !e_out || nuse < 2) return fail(BWGR_ERR_ARG, "KMUP2: bad Use / E / e_out");
   const int64_t n = h->n, p = h->p;
-  std::vector<uint8_t> mask;
-  int rc = use_to_mask(use, nuse, n, mask);
+  std::vector<uint8_t> mask, cnt;
+  bool repeats = false;
+  int rc = use_to_mask(use, nuse, n, mask, cnt, &repeats);
   if (rc) return rc;
-  rc = kmup_begin(h, b, d, xx, E, L, Ve, pi, seed, mask.data(), (double)((float)n / (float)nuse));
+  rc = kmup_begin(h, b, d, xx, E, L, Ve, pi, seed, mask.data(), (double)((float)n / (float)nuse), repeats ? cnt.data() : nullptr);
   if (rc) return rc;
   Fit& f = h->fit;
   f.skip_epilogue = true;
@@ -2104,10 +2142,9 @@ int bwgr_wgr_fit_bag(bwgr_handle* h, const double* y, int it, int bi, int th, do
   if (!h || !h->p) return fail(BWGR_ERR_STATE, "no genotypes loaded");
   if (!y) return fail(BWGR_ERR_ARG, "y is NULL");
   if (it < 1 || bi < 1 || bi > it || th < 1) return fail(BWGR_ERR_ARG, "need 1 <= bi <= it and th >= 1");
-  if (rp) return fail(BWGR_ERR_UNSUPPORTED, "wgr(rp = TRUE): sampling rows with replacement is not on the B200 path");
   const int64_t n = h->n, p = h->p, ld = h->ld;
   const int64_t nuse = (int64_t)((double)n * bag);
-  if (!(bag > 0) || nuse < 2 || nuse > n) return fail(BWGR_ERR_ARG, "bag must give 2 <= n * bag <= n rows without replacement");
+  if (!(bag > 0) || nuse < 2 || (!rp && nuse > n)) return fail(BWGR_ERR_ARG, "bag must give 2 <= n * bag (<= n rows without replacement)");
   if (de) iv = 1;
   df = df / (bag * bag);  // :21
   double mu = 0;
@@ -2124,14 +2161,24 @@ int bwgr_wgr_fit_bag(bwgr_handle* h, const double* y, int it, int bi, int th, do
   for (int64_t j = 0; j < p; j++) xxb[j] = h->h_xx[j] * bag;  // xx = crossprod * bag (:49)
   std::mt19937_64 gen(seed ^ 0x9E3779B97F4A7C15ull);
   std::vector<int64_t> rows(n);
-  std::vector<uint8_t> mask((size_t)ld, 0);
-  auto draw = [&]() {  // Use = sort(sample(n, n * bag)) (:68) as a mask
-    for (int64_t r = 0; r < n; r++) rows[r] = r;
+  std::vector<uint8_t> mask((size_t)ld, 0), cnt((size_t)ld, 0);
+  std::vector<float> cntf((size_t)ld, 0.0f);
+  bool overflow = false;
+  auto draw = [&]() {  // Use = sort(sample(n, n * bag, rp)) (:68) as a mask (+ the multiplicity of every row when rp = TRUE)
     std::fill(mask.begin(), mask.end(), 0);
+    if (rp) {
+      std::fill(cnt.begin(), cnt.end(), 0);
+      std::uniform_int_distribution<int64_t> pick(0, n - 1);
+      for (int64_t r = 0; r < nuse; r++) { const int64_t q = pick(gen); mask[q] = 1; if (cnt[q] == 255) overflow = true; else cnt[q]++; }
+      for (int64_t r = 0; r < n; r++) cntf[r] = (float)cnt[r];
+      return;
+    }
+    for (int64_t r = 0; r < n; r++) rows[r] = r;
     for (int64_t r = 0; r < nuse; r++) { std::uniform_int_distribution<int64_t> pick(r, n - 1); std::swap(rows[r], rows[pick(gen)]); mask[rows[r]] = 1; }
   };
   draw();
-  int rc = kmup_begin(h, b0.data(), d0.data(), xxb.data(), e0.data(), L0.data(), 1.0, pi, seed, mask.data(), (double)((float)n / (float)nuse));
+  int rc = kmup_begin(h, b0.data(), d0.data(), xxb.data(), e0.data(), L0.data(), 1.0, pi, seed, mask.data(), (double)((float)n / (float)nuse),
+                      rp ? cnt.data() : nullptr);
   if (rc) return rc;
   Fit& f = h->fit;
   f.skip_epilogue = true;
@@ -2159,12 +2206,18 @@ int bwgr_wgr_fit_bag(bwgr_handle* h, const double* y, int it, int bi, int th, do
   w.B = f.B.p; w.D = f.D.p; w.VB = f.VBv.p; w.sc = f.sc.p; w.st = f.wst.p; w.iv = iv; w.de = de;
   w.Sb = (float)(R2 * df * vy / MSx); w.Se = (float)((1 - R2) * df * vy); w.df = (float)df; w.MSx = (float)MSx;
   w.it = it; w.bi = bi; w.th = th; w.seed_lo = (uint32_t)seed; w.seed_hi = (uint32_t)(seed >> 32);
-  w.mask = f.mask.p; w.nsub = (float)nuse; w.y = yd.p; w.hat = hatd.p;
+  w.mask = rp ? f.cnt.p : f.mask.p; w.nsub = (float)nuse; w.y = yd.p; w.hat = hatd.p;  // phase 1 weighs e^2 by the byte (0/1 or the multiplicity)
   for (int i = 0; i < it; i++) {
     if (i > 0) {  // this iteration's rows: mask, and H'H of every marker over them (the rule's likelihood-ratio scale)
       draw();
       CU(cudaMemcpyAsync(f.mask.p, mask.data(), (size_t)ld, cudaMemcpyHostToDevice, h->stream));
-      if (h->storage == BWGR_STORE_F32) {
+      if (rp) {
+        if (overflow) { f.reset(); return fail(BWGR_ERR_UNSUPPORTED, "wgr(rp = TRUE): a row was drawn more than 255 times in one iteration"); }
+        CU(cudaMemcpyAsync(f.cnt.p, cnt.data(), (size_t)ld, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(f.row_w.p, cntf.data(), sizeof(float) * ld, cudaMemcpyHostToDevice, h->stream));
+        launch_col_stats_cnt(h->view(), f.cnt.p, reinterpret_cast<double*>(txx.p), reinterpret_cast<double*>(tsx.p), h->stream);
+        launch_d_to_float(reinterpret_cast<double*>(txx.p), f.xx_sys.p, (int)p, h->stream);
+      } else if (h->storage == BWGR_STORE_F32) {
         launch_col_stats_f32(h->view(), f.mask.p, reinterpret_cast<double*>(txx.p), reinterpret_cast<double*>(tsx.p), h->stream);
         launch_d_to_float(reinterpret_cast<double*>(txx.p), f.xx_sys.p, (int)p, h->stream);
       } else {

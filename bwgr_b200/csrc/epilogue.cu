@@ -309,9 +309,12 @@ __global__ void __launch_bounds__(1024) wgr_scalars_kernel(WgrArgs a) {
     for (int i = tid; i < a.n; i += T) { const float ef = a.y[i] - a.hat[i]; a.e[i] = ef; se += (double)ef; emax = fmaxf(emax, fabsf(ef)); }
   } else {
     for (int i = tid; i < a.n; i += T) {
-      if (phase == 1 && !a.mask[i]) continue;  // KMUP2 returns the residuals of the rows in use only (:76): crossprod(e) is theirs
+      // KMUP2 returns the residuals of the rows in use only (:76): crossprod(e) is theirs, a row drawn c times (rp = TRUE) enters c
+      // times (the mask byte is 0/1, or the multiplicity)
+      const double wv = phase == 1 ? (double)a.mask[i] : 1.0;
+      if (wv == 0.0) continue;
       const double ev = a.e[i];
-      se += ev; see += ev * ev; emax = fmaxf(emax, fabsf(a.e[i]));
+      se += wv * ev; see += wv * ev * ev; emax = fmaxf(emax, fabsf(a.e[i]));
     }
     for (int j = tid; j < a.p; j += T) { const double bj = a.b[j]; sbb += bj * bj; }
   }

@@ -232,6 +232,34 @@ __global__ void __launch_bounds__(256) col_stats_f32_kernel(GenoView g, const ui
 void launch_col_stats_f32(const GenoView& g, const uint8_t* mask, double* xx, double* sx, cudaStream_t st) {
   col_stats_f32_kernel<<<g.p, 256, 0, st>>>(g, mask, xx, sx);
 }
+// Row multiplicities (KMUP2 on rows sampled with replacement, R/wgr.R:68 with rp = TRUE): xx_j = sum_i c_i x_ij^2, sx_j = sum_i c_i x_ij
+// for any store, in double (exact for the integer stores: every partial sum is an integer below 2^53).  One CTA per marker.
+__global__ void __launch_bounds__(256) col_stats_cnt_kernel(GenoView g, const uint8_t* __restrict__ cnt, double* __restrict__ xx,
+                                                            double* __restrict__ sx) {
+  __shared__ double sh1[8], sh2[8];
+  const int j = blockIdx.x, tid = threadIdx.x;
+  double s1 = 0, s2 = 0;
+  for (int i = tid; i < g.n; i += 256) {
+    const double c = (double)cnt[i];
+    if (c == 0.0) continue;
+    double v;
+    if (g.storage == 0) v = (double)g.x8[(int64_t)j * g.ld + i];
+    else if (g.storage == 1) v = (double)((g.x2[(int64_t)j * g.ldb + (i >> 2)] >> (2 * (i & 3))) & 3);
+    else v = (double)g.xf[(int64_t)j * g.ld + i];
+    s1 += c * v; s2 += c * v * v;
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if ((tid & 31) == 0) { sh1[tid >> 5] = s1; sh2[tid >> 5] = s2; }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0, c = 0;
+    for (int w = 0; w < 8; w++) { a += sh1[w]; c += sh2[w]; }
+    sx[j] = a; xx[j] = c;
+  }
+}
+void launch_col_stats_cnt(const GenoView& g, const uint8_t* cnt, double* xx, double* sx, cudaStream_t st) {
+  col_stats_cnt_kernel<<<g.p, 256, 0, st>>>(g, cnt, xx, sx);
+}
 __global__ void __launch_bounds__(256) d_to_float_kernel(const double* __restrict__ src, float* __restrict__ dst, int n) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i < n) dst[i] = (float)src[i];

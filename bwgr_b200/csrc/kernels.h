@@ -38,6 +38,8 @@ void launch_col_stats(const GenoView& g, long long* xx, long long* sx, cudaStrea
 void launch_col_stats_masked(const GenoView& g, const uint8_t* mask, long long* xx, long long* sx, cudaStream_t st);
 // float32 store: column statistics in double (mask: optional uint8 [n], rows used)
 void launch_col_stats_f32(const GenoView& g, const uint8_t* mask, double* xx, double* sx, cudaStream_t st);
+// row multiplicities cnt[i] (uint8) instead of a 0/1 mask; any store
+void launch_col_stats_cnt(const GenoView& g, const uint8_t* cnt, double* xx, double* sx, cudaStream_t st);
 void launch_d_to_float(const double* src, float* dst, int n, cudaStream_t st);
 // hat = mu + X b (deterministic two-stage reduction). work: [splits][ld] floats.
 void launch_gemv_hat(const GenoView& g, const float* b, const float* mu_dev, float* hat, float* work, int splits,
@@ -61,6 +63,7 @@ struct SmallNArgs {
   const float* xx2;        // KMUP2: the caller's xx(j) * bg [p] (the rule's denominator; xx carries H'H of the rows in use)
   int xx_per_sys;
   const uint8_t* mask;     // [nsys][ld] or nullptr
+  const float* row_w;      // KMUP2 on rows sampled with replacement: [ld] row multiplicities as floats (nsys = 1), or nullptr
   SysScalars* sc;          // [nsys]
   // Gibbs posterior sums
   float* B; float* D; float* VBv;  // [nsys][p] or nullptr
@@ -69,7 +72,7 @@ struct SmallNArgs {
   int* err;                // device error flag
 };
 void launch_small_n(const SmallNArgs& a, size_t smem_limit, cudaStream_t st);
-bool small_n_fits(const GenoView& g, bool masked, size_t smem_limit);
+bool small_n_fits(const GenoView& g, bool masked, size_t smem_limit, bool weighted = false);
 
 // ---- blocked path ---------------------------------------------------------------------------------
 constexpr int kBlk = 128;  // markers per block

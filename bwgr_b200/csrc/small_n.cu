@@ -59,6 +59,11 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
   float* red = reinterpret_cast<float*>(mask_s + (a.mask ? ld : 0));        // [2][32]
   MarkerDraws* draws = reinterpret_cast<MarkerDraws*>(red + 64);            // [2][T] (Gibbs)
   int* ord_s = reinterpret_cast<int*>(draws + (model_is_gibbs(MODEL) ? 2 * T : 0));  // [2][T]: the marker order, two chunks of T positions
+  // KMUP2 on rows drawn with replacement (R/wgr.R:68, rp = TRUE): H'e0 counts a row as often as it was drawn (:57-60), the residual
+  // of a repeated row is one value.  Multiplicities as floats in e's layout, multiplied into the dot product only.
+  const float* w_s = nullptr;
+  if constexpr (MODEL == M_KMUP2)
+    if (a.row_w) w_s = reinterpret_cast<const float*>((reinterpret_cast<uintptr_t>(ord_s + 2 * T) + 15) & ~(uintptr_t)15);
   __shared__ SysScalars sc;
 
   if (tid == 0) sc = a.sc[sys];
@@ -69,6 +74,8 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
   for (int i = tid; i < ld; i += T) e_s[e_idx(i)] = e_g[i];
   if (a.mask)
     for (int i = tid; i < ld; i += T) mask_s[i] = a.mask[(size_t)sys * ld + i];
+  if (w_s)
+    for (int i = tid; i < ld; i += T) const_cast<float*>(w_s)[e_idx(i)] = a.row_w[i];
 
   float* b = a.b + (size_t)sys * p;
   float* dvec = a.d ? a.d + (size_t)sys * p : nullptr;
@@ -159,7 +166,8 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
         float a4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-          const float4 e4 = ev[(size_t)q * nchunks];
+          float4 e4 = ev[(size_t)q * nchunks];
+          if (w_s) { const float4 w4 = reinterpret_cast<const float4*>(w_s)[(size_t)q * nchunks + c]; e4.x *= w4.x; e4.y *= w4.y; e4.z *= w4.z; e4.w *= w4.w; }
 #pragma unroll
           for (int k = 0; k < 4; k++) xf[4 * q + k] = byte_to_float(ww[q], k);
           a4[q] = fmaf(xf[4 * q + 0], e4.x, a4[q]); a4[q] = fmaf(xf[4 * q + 1], e4.y, a4[q]);
@@ -179,7 +187,8 @@ __global__ void __launch_bounds__(1024, 1) small_n_sweep_kernel(SmallNArgs a) {
       const float4* ev = reinterpret_cast<const float4*>(e_s) + c;
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        const float4 e4 = ev[(size_t)q * nchunks];
+        float4 e4 = ev[(size_t)q * nchunks];
+        if (w_s) { const float4 w4 = reinterpret_cast<const float4*>(w_s)[(size_t)q * nchunks + c]; e4.x *= w4.x; e4.y *= w4.y; e4.z *= w4.z; e4.w *= w4.w; }
         acc = fmaf(byte_to_float(ww[q], 0), e4.x, acc);
         acc = fmaf(byte_to_float(ww[q], 1), e4.y, acc);
         acc = fmaf(byte_to_float(ww[q], 2), e4.z, acc);
@@ -250,13 +259,14 @@ static size_t small_n_smem(const SmallNArgs& a, int ring, int T) {
   const size_t ld = (size_t)a.g.ld;
   const size_t col_bytes = a.g.storage ? (ld >> 2) : ld;
   return ld * 4 + (size_t)ring * col_bytes + (a.mask ? ld : 0) + 64 * 4 +
-         (model_is_gibbs(a.model) ? 2 * (size_t)T * sizeof(MarkerDraws) : 0) + 2 * (size_t)T * sizeof(int) + 16;
+         (model_is_gibbs(a.model) ? 2 * (size_t)T * sizeof(MarkerDraws) : 0) + 2 * (size_t)T * sizeof(int) + 16 + (a.row_w ? ld * 4 + 16 : 0);
 }
 
 // Largest n this path takes: e (4 B/row) + two ring slots must fit the 227 KB of one SM.
-bool small_n_fits(const GenoView& g, bool masked, size_t smem_limit) {
+bool small_n_fits(const GenoView& g, bool masked, size_t smem_limit, bool weighted) {
   SmallNArgs a;
   a.g = g; a.mask = masked ? reinterpret_cast<const uint8_t*>(1) : nullptr; a.model = M_BB;
+  a.row_w = weighted ? reinterpret_cast<const float*>(1) : nullptr;
   return small_n_smem(a, 2, 1024) <= smem_limit;
 }
 

@@ -178,7 +178,9 @@ BWGR_API int bwgr_fitted(bwgr_handle* h, const double* b, double mu, double* hat
 
 /* KMUP2(X,Use,b,d,xx,E,L,Ve,pi) (:41-77), the bagged sweep of wgr(bag != 1): only the rows Use (0-based, as R passes them) enter.
  * b, d updated in place; e_out [nuse] = the residuals of the rows in use, in the order of Use (the reference's third list element).
- * Rows must be distinct (rp = FALSE); repeated rows -> BWGR_ERR_UNSUPPORTED.  Needs the residual of n rows to fit one SM. */
+ * A row named more than once (sampling with replacement, rp = TRUE) counts once per occurrence in H'e0, H'H and ||e||^2, as in the
+ * reference's H / e0 (:51-60): row multiplicities (<= 255) in the dot products of the small-n family, which this case needs (int8 or
+ * 2-bit store, residual + multiplicities of n rows in one SM's shared memory); without repeats larger n run on the grid family. */
 BWGR_API int bwgr_kmup2_sweep(bwgr_handle* h, const double* use, int64_t nuse, double* b, double* d, const double* xx, const double* E,
                      double* e_out, const double* L, double Ve, double pi, uint64_t seed);
 
@@ -194,7 +196,8 @@ BWGR_API int bwgr_wgr_fit(bwgr_handle* h, const double* y, int it, int bi, int t
                  double R2, uint64_t seed, double* b, double* d, double* Vb, double* hat, double* scal);
 
 /* wgr(..., bag, rp) for bag != 1 (R/wgr.R:21, :49, :68, :87, :121): a fresh sorted sample of floor(n * bag) rows per iteration (drawn
- * with std::mt19937_64(seed), not R's sample()), swept by KMUP2; rp = TRUE -> BWGR_ERR_UNSUPPORTED.  bag = 1 forwards to bwgr_wgr_fit. */
+ * with std::mt19937_64(seed), not R's sample()), swept by KMUP2; rp = TRUE draws them with replacement (bag > 1 allowed) and sweeps with row multiplicities (see
+ * bwgr_kmup2_sweep).  bag = 1 forwards to bwgr_wgr_fit. */
 BWGR_API int bwgr_wgr_fit_bag(bwgr_handle* h, const double* y, int it, int bi, int th, double bag, int rp, int iv, int de, double pi,
                      double df, double R2, uint64_t seed, double* b, double* d, double* Vb, double* hat, double* scal);
 

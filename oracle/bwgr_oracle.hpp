@@ -1000,8 +1000,8 @@ static inline void imp_columns(float* X, int n, int p) {
   }
 }
 
-// wgr(): R/wgr.R:2-169 with eigK=NULL, no NA; bag != 1 resamples the rows of every iteration without replacement (rp = FALSE,
-// :68: Use = sort(sample(n, n*bag)) - 1) and sweeps them with KMUP2.  The driver arithmetic is R's (double);
+// wgr(): R/wgr.R:2-169 with eigK=NULL, no NA; bag != 1 resamples the rows of every iteration (:68: Use = sort(sample(n, n*bag, rp)) - 1,
+// without replacement unless rp) and sweeps them with KMUP2.  The driver arithmetic is R's (double);
 // every KMUP call crosses the Rcpp boundary, i.e. casts X,b,d,xx,e,L to float and back
 // (RcppExports.cpp:16-31).
 // eigK (bag == 1 only: with bag != 1 the reference hands KMUP2's nuse-long residual back to KMUP2 as E, :81-87, and reads out of
@@ -1012,7 +1012,7 @@ struct WgrOut {
 };
 static inline void wgr(const double* y, const double* Xd, int n, int p, int it, int bi, int th, bool iv, bool de,
                        double pi, double df, double R2, uint64_t seed, bool ratio_form, WgrOut& o, double bag = 1.0,
-                       const double* Ud = nullptr, const double* Vd = nullptr, int pk = 0) {
+                       const double* Ud = nullptr, const double* Vd = nullptr, int pk = 0, bool rp = false) {
   Rng rng(seed);
   if (de) iv = true;
   const bool bagged = bag != 1.0;
@@ -1066,8 +1066,14 @@ static inline void wgr(const double* y, const double* Xd, int n, int p, int it, 
       for (int q = 0; q < pk; q++) h[q] = hf[q];
     }
     if (bagged) {  // :68, :87: a fresh sorted row sample, swept by KMUP2; e becomes the residual of the rows in use
-      for (int r = 0; r < n; r++) rows[r] = r;
-      for (int r = 0; r < nuse; r++) { std::uniform_int_distribution<int> pick(r, n - 1); std::swap(rows[r], rows[pick(rng.g)]); }
+      if (rp) {  // sample(n, n*bag, TRUE): rows may repeat; KMUP2 then counts a repeated row once per draw (:51-60)
+        rows.resize(std::max(n, nuse));
+        std::uniform_int_distribution<int> pick(0, n - 1);
+        for (int r = 0; r < nuse; r++) rows[r] = pick(rng.g);
+      } else {
+        for (int r = 0; r < n; r++) rows[r] = r;
+        for (int r = 0; r < nuse; r++) { std::uniform_int_distribution<int> pick(r, n - 1); std::swap(rows[r], rows[pick(rng.g)]); }
+      }
       std::sort(rows.begin(), rows.begin() + nuse);
       for (int r = 0; r < nuse; r++) usef[r] = (float)rows[r];
       kmup2(Xf.data(), n, p, usef.data(), nuse, bf.data(), dfl.data(), xxf.data(), ef.data(), esub.data(), Lf.data(), (float)Ve, (float)pi, rng,

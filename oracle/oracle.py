@@ -187,7 +187,7 @@ def eigk_rank(values, VarK=0.95):
     return int(np.argmax(np.cumsum(V) / V.size > VarK)) + 1
 
 
-def wgr(y, X, it=1500, bi=500, th=1, iv=False, de=False, pi=0.0, df=5.0, R2=0.5, seed=1, ratio_form=False, bag=1.0, eigK=None, VarK=0.95):
+def wgr(y, X, it=1500, bi=500, th=1, iv=False, de=False, pi=0.0, df=5.0, R2=0.5, seed=1, ratio_form=False, bag=1.0, eigK=None, VarK=0.95, rp=False):
     y = np.ascontiguousarray(y, dtype=np.float64)
     X = np.asfortranarray(X, dtype=np.float64)
     n, p = X.shape
@@ -207,6 +207,13 @@ def wgr(y, X, it=1500, bi=500, th=1, iv=False, de=False, pi=0.0, df=5.0, R2=0.5,
                            _p(Vb, C.c_double), _p(hat, C.c_double), _p(u, C.c_double), _p(scal, C.c_double))
         mu, Ve, Va, cxx, Vk = scal
         return {"mu": mu, "b": b, "Vb": Vb if (iv or de) else Va, "d": d, "Ve": Ve, "hat": hat, "u": u, "Vk": Vk, "cxx": cxx}
+    if bag != 1.0 and rp:  # R/wgr.R:68, rows drawn with replacement
+        lib().orc_wgr_bag_rp(_p(y, C.c_double), _p(X, C.c_double), C.c_int(n), C.c_int(p), C.c_int(it), C.c_int(bi), C.c_int(th),
+                             C.c_double(bag), C.c_int(1), C.c_int(int(iv)), C.c_int(int(de)), C.c_double(pi), C.c_double(df), C.c_double(R2),
+                             C.c_uint64(seed), C.c_int(int(ratio_form)), _p(b, C.c_double), _p(d, C.c_double), _p(Vb, C.c_double),
+                             _p(hat, C.c_double), _p(scal, C.c_double))
+        mu, Ve, Va, cxx = scal
+        return {"mu": mu, "b": b, "Vb": Vb if (iv or de) else Va, "d": d, "Ve": Ve, "hat": hat, "cxx": cxx}
     if bag != 1.0:
         lib().orc_wgr_bag(_p(y, C.c_double), _p(X, C.c_double), C.c_int(n), C.c_int(p), C.c_int(it), C.c_int(bi), C.c_int(th),
                           C.c_double(bag), C.c_int(int(iv)), C.c_int(int(de)), C.c_double(pi), C.c_double(df), C.c_double(R2),

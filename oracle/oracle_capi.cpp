@@ -148,6 +148,17 @@ int orc_wgr_bag(const double* y, const double* X, int n, int p, int it, int bi, 
   return 0;
 }
 
+// wgr(bag, rp): rp != 0 draws the rows of every iteration with replacement (R/wgr.R:68)
+int orc_wgr_bag_rp(const double* y, const double* X, int n, int p, int it, int bi, int th, double bag, int rp, int iv, int de, double pi,
+                   double df, double R2, uint64_t seed, int ratio_form, double* b, double* d, double* Vb, double* hat, double* scal) {
+  orc::WgrOut o;
+  orc::wgr(y, X, n, p, it, bi, th, iv != 0, de != 0, pi, df, R2, seed, ratio_form != 0, o, bag, nullptr, nullptr, 0, rp != 0);
+  for (int j = 0; j < p; j++) { b[j] = o.b[j]; d[j] = o.d[j]; Vb[j] = o.Vb[j]; }
+  for (int i = 0; i < n; i++) hat[i] = o.hat[i];
+  scal[0] = o.mu; scal[1] = o.Ve; scal[2] = o.Va; scal[3] = o.cxx;
+  return 0;
+}
+
 // MRR3 (f32_variant=0, float64) / MRR3F (f32_variant=1, float32).  par[] in the order of the R
 // signature after (Y,X): maxit,tol,cores,TH,NLfactor,InnerGS,NoInv,HCS,XFA,ACS,NumXFA,R2,gc0,df0,
 // updateMu,weight_prior_h2,weight_prior_gc,PenCor,MinCor,uncorH2below,roundGCupFrom,roundGCupTo,

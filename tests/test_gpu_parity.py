@@ -853,7 +853,8 @@ def test_kmup_stochastic_branch(tpod, path):
 def test_kmup2_bagged_sweep(tpod):
     """KMUP2(X,Use,b,d,xx,E,L,Ve,pi) (Rcpp20260726ai.cpp:41-77), the sweep of wgr(bag != 1) over a row subset: (i) the deterministic
     limit (pi = 0, Ve -> 0) equals the oracle to float rounding, including the returned subset residual and the reference's
-    (H'e0 + b0) numerator; (ii) the indicator branch over 300 seeds agrees within Monte-Carlo error; (iii) repeated rows are refused."""
+    (H'e0 + b0) numerator; (ii) the indicator branch over 300 seeds agrees within Monte-Carlo error.  Repeated rows (sampling with
+    replacement): test_kmup2_repeated_rows."""
     y, gen = tpod
     X = gen.astype(np.float64)
     n, p = X.shape
@@ -884,24 +885,63 @@ def test_kmup2_bagged_sweep(tpod):
         assert z.max() < 5.5 and (z > 3).mean() < 0.02, (z.max(), (z > 3).mean())
         ea, eb = np.mean([r["e"] for r in A], 0), np.mean([r["e"] for r in B], 0)
         assert np.corrcoef(ea, eb)[0, 1] > 0.995  # means of 300 draws on either side
+
+
+@pytest.mark.parametrize("storage", ["i8", "2bit"])
+def test_kmup2_repeated_rows(tpod, storage):
+    """KMUP2 with repeats in Use -- wgr(bag, rp = TRUE) draws sort(sample(n, n*bag, TRUE)) (R/wgr.R:68): the reference's e0 / H hold
+    a repeated row once per draw (Rcpp20260726ai.cpp:51-60), so H'e0, H'H and ||e||^2 count it that often while its residual stays
+    one value.  On the device: row multiplicities in the dot products of the small-n family.  (i) deterministic limit vs the oracle to
+    float rounding, the returned residual in the order of Use (repeats repeated); (ii) the indicator branch over 300 seeds; (iii) a
+    row index outside X is an argument error."""
+    y, gen = tpod
+    X = gen.astype(np.float64)
+    n, p = X.shape
+    rng = np.random.default_rng(11)
+    use = np.sort(rng.integers(0, n, int(n * 0.8))).astype(np.float64)
+    assert np.unique(use).size < use.size and np.bincount(use.astype(int)).max() >= 3
+    bag = use.size / n
+    xx = (X ** 2).sum(0) * bag
+    b0 = np.linspace(-0.01, 0.01, p)
+    e = y - y.mean() - X @ b0
+    L = np.full(p, 37.0)
+    kw = dict(storage=bw.STORE_2BIT) if storage == "2bit" else {}
+    with bw.Genotypes(gen, **kw) as g:
+        ref = O.kmup2(X, use, b0, np.ones(p), xx, e, L, 1e-30, 0.0, seed=3)
+        out = bw.KMUP2(g, use, b0, np.ones(p), xx, e, L, 1e-30, 0.0, seed=9)
+        assert out["e"].shape == ref["e"].shape == (use.size,)
+        assert np.abs(out["b"] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max()
+        assert np.abs(out["e"] - ref["e"]).max() <= RTOL * np.abs(ref["e"]).max()
+        Ve, pi, reps = 0.03, 0.4, 300
+        L = np.full(p, 80.0)
+        A = [O.kmup2(X, use, b0, np.ones(p), xx, e, L, Ve, pi, seed=1000 + s, ratio_form=True) for s in range(reps)]
+        B = [bw.KMUP2(g, use, b0, np.ones(p), xx, e, L, Ve, pi, seed=5000 + s) for s in range(reps)]
+        da, db = np.mean([r["d"] for r in A], 0), np.mean([r["d"] for r in B], 0)
+        se_d = np.sqrt(da * (1 - da) / reps + db * (1 - db) / reps) + 1e-3
+        assert np.abs(da - db).max() <= 5 * se_d.max(), (np.abs(da - db).max(), se_d.max())
+        ba, bb = np.array([r["b"] for r in A]), np.array([r["b"] for r in B])
+        se_b = np.sqrt(ba.var(0, ddof=1) / reps + bb.var(0, ddof=1) / reps)
+        z = np.abs(ba.mean(0) - bb.mean(0)) / se_b
+        assert z.max() < 5.5 and (z > 3).mean() < 0.02, (z.max(), (z > 3).mean())
         with pytest.raises(bw.BwgrError) as ei:
-            bw.KMUP2(g, np.array([0.0, 1.0, 1.0, 5.0]), b0, np.ones(p), xx, e, L, Ve, pi)
-        assert ei.value.code == -5
+            bw.KMUP2(g, np.array([0.0, 1.0, 1.0, float(n)]), b0, np.ones(p), xx, e, L, Ve, pi)
+        assert ei.value.code == -1
 
 
+@pytest.mark.parametrize("rp", [False, True])
 @pytest.mark.parametrize("mode", ["BRR", "BayesB"])
-def test_wgr_bagged(tpod, mode):
-    """wgr(bag = 0.5) (R/wgr.R:21, :49, :68, :87, :121): a fresh row sample per iteration swept by KMUP2, Ve from the rows in use, the
+def test_wgr_bagged(tpod, mode, rp):
+    """rp = TRUE: the rows of an iteration are drawn with replacement (R/wgr.R:68), KMUP2 counts a repeated row once per draw.
+    wgr(bag = 0.5) (R/wgr.R:21, :49, :68, :87, :121): a fresh row sample per iteration swept by KMUP2, Ve from the rows in use, the
     residual rebuilt from the fitted values -- posterior means vs the oracle's restatement within Monte-Carlo error."""
     y, gen = tpod
     X = gen.astype(np.float64)
     kw = {"BRR": dict(pi=0.0, iv=False), "BayesB": dict(pi=0.9, iv=True)}[mode]
     seeds = range(6)
+    kw["rp"] = rp
     ora = [O.wgr(y, X, it=800, bi=200, seed=50 + s, ratio_form=True, bag=0.5, **kw) for s in seeds]
     with bw.Genotypes(gen) as g:
         gpu = [bw.wgr(y, g, it=800, bi=200, seed=70 + s, bag=0.5, **kw) for s in seeds]
-        with pytest.raises(bw.BwgrError):
-            bw.wgr(y, g, it=10, bi=2, bag=0.5, rp=True)
     for key in ("mu", "Ve"):
         a = np.array([r[key] for r in ora]); b = np.array([r[key] for r in gpu])
         se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))

@@ -178,6 +178,13 @@ def test_kmup2_and_preprocessing_match_reference_text(tpod):
         a = O.kmup2(X, use, b0, np.ones(p), xx, E, L, 0.03, pi, seed=8)
         r = R.kmup2(X, use, b0, np.ones(p), xx, E, L, 0.03, pi, seed=8)
         assert np.array_equal(a["d"], r["d"]) and rel(a["b"], r["b"]) < 1e-4 and rel(a["e"], r["e"]) < 1e-4
+    # Use with repeats: what wgr(bag, rp = TRUE) passes (R/wgr.R:68, sort(sample(n, n*bag, TRUE)) - 1)
+    use_r = np.sort(rng.integers(0, n, size=n // 2)).astype(np.float64)
+    assert np.unique(use_r).size < use_r.size
+    for pi in (0.0, 0.3):
+        a = O.kmup2(X, use_r, b0, np.ones(p), xx, E, L, 0.03, pi, seed=8)
+        r = R.kmup2(X, use_r, b0, np.ones(p), xx, E, L, 0.03, pi, seed=8)
+        assert np.array_equal(a["d"], r["d"]) and rel(a["b"], r["b"]) < 1e-4 and rel(a["e"], r["e"]) < 1e-4
     Xn = X.copy()
     Xn[rng.random(X.shape) < 0.03] = np.nan
     assert np.allclose(O.imp(Xn), R.imp(Xn), rtol=0, atol=1e-6) and not np.isnan(O.imp(Xn)).any()
