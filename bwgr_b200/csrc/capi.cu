@@ -1027,9 +1027,6 @@ int fit_begin(bwgr_handle* h, const FitSpec& s, const double* y) {
   int rc = choose_path(h, s, &family);
   h->path = saved_path_;
   if (rc) return rc;
-  if (s.row_cnt && family != 0)
-    return fail(BWGR_ERR_UNSUPPORTED, "KMUP2 on repeated rows (sampling with replacement) runs on the small-n family: needs the int8 / 2-bit store "
-                                      "and residual + multiplicities of n=%lld rows in one SM's shared memory", (long long)h->n);
   const bool blocked = family == 1;
   const int64_t n = h->n, p = h->p, ld = h->ld;
   const int ns = s.nsys;
@@ -1367,7 +1364,7 @@ void g_fixed_point(bwgr_handle* h, const Fit& f, float* quantum, float* limit) {
   for (double v : h->h_xx) xxmax = std::max(xxmax, v);
   double yy = 0;
   for (size_t t = 0; t < f.vy.size(); t++) yy = std::max(yy, (double)f.vy[t] * (double)(h->n - 1));
-  const double bound = 64.0 * std::sqrt(xxmax * std::max(yy, 1e-30));
+  const double bound = 64.0 * (f.weighted ? 256.0 : 1.0) * std::sqrt(xxmax * std::max(yy, 1e-30));  // row multiplicities <= 255
   int ex;
   std::frexp(bound, &ex);
   *quantum = (float)std::ldexp(1.0, ex - 50);
@@ -1497,7 +1494,8 @@ int fit_sweeps(bwgr_handle* h, int nsweeps) {
       GridArgs a;
       memset(&a, 0, sizeof a);
       a.g = g; a.model = f.model; a.nsys = f.nsys; a.perm = d_perm; a.e = f.e.p; a.b = f.b.p; a.d = f.d.p; a.vbv = f.vbv.p;
-      a.xx = f.masked ? f.xx_sys.p : (f.xx_over.p ? f.xx_over.p : h->xx_f.p); a.xx_per_sys = f.masked ? 1 : 0; a.mask = f.mask.p;
+      a.xx = f.masked ? f.xx_sys.p : (f.xx_over.p ? f.xx_over.p : h->xx_f.p); a.xx_per_sys = f.masked ? 1 : 0;
+      a.mask = f.weighted ? f.cnt.p : f.mask.p;  // row multiplicities ride in the mask bytes (they weigh the dot products only)
       a.xx2 = f.model == M_KMUP2 ? f.xx_over.p : nullptr;
       a.blocked = f.grid_blocked ? 1 : 0;
       {  // cross products are bounded by max_j x_j'x_j (Cauchy-Schwarz): one unit = 1 (exact integers) unless that exceeds 2^50

@@ -45,7 +45,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 
 struct GridSmem {
   float* E;          // [ns][rp]
-  uint8_t* M;        // [ns][rp] (masked fits)
+  uint8_t* M;        // [ns][rp] (masked fits): 0/1, or the multiplicity of a row drawn with replacement (KMUP2, rp = TRUE)
   unsigned char* xs[kD];  // [rp] int8 or [rp] float
   float* vin[kD];    // b0[32] | vbj[32] | xx[32] | xx2
   SysScalars* sc;    // [ns]
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kT, 1) grid_sweep_kernel(GridArgs a) {
       float* Et = s.E + (size_t)t * rp;
       if (masked) {
         const uint8_t* Mt = s.M + (size_t)t * rp;
-        for (int i = tid; i < rp; i += kT) Et[i] = fmaf(-(float)xs[i] * (float)Mt[i], de, Et[i]);
+        for (int i = tid; i < rp; i += kT) Et[i] = fmaf(Mt[i] ? -(float)xs[i] : 0.0f, de, Et[i]);  // the byte may be a row multiplicity: it weighs the dot products only
       } else {
         for (int i = tid; i < rp; i += kT) Et[i] = fmaf(-(float)xs[i], de, Et[i]);
       }

@@ -179,8 +179,8 @@ BWGR_API int bwgr_fitted(bwgr_handle* h, const double* b, double mu, double* hat
 /* KMUP2(X,Use,b,d,xx,E,L,Ve,pi) (:41-77), the bagged sweep of wgr(bag != 1): only the rows Use (0-based, as R passes them) enter.
  * b, d updated in place; e_out [nuse] = the residuals of the rows in use, in the order of Use (the reference's third list element).
  * A row named more than once (sampling with replacement, rp = TRUE) counts once per occurrence in H'e0, H'H and ||e||^2, as in the
- * reference's H / e0 (:51-60): row multiplicities (<= 255) in the dot products of the small-n family, which this case needs (int8 or
- * 2-bit store, residual + multiplicities of n rows in one SM's shared memory); without repeats larger n run on the grid family. */
+ * reference's H / e0 (:51-60): row multiplicities (<= 255) in the dot products, on the small-n family when the residual and the
+ * multiplicities of n rows fit one SM's shared memory, else on the grid family (any n, int8 or float32 store). */
 BWGR_API int bwgr_kmup2_sweep(bwgr_handle* h, const double* use, int64_t nuse, double* b, double* d, const double* xx, const double* E,
                      double* e_out, const double* L, double Ve, double pi, uint64_t seed);
 

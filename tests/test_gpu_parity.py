@@ -887,11 +887,12 @@ def test_kmup2_bagged_sweep(tpod):
         assert np.corrcoef(ea, eb)[0, 1] > 0.995  # means of 300 draws on either side
 
 
-@pytest.mark.parametrize("storage", ["i8", "2bit"])
+@pytest.mark.parametrize("storage", ["i8", "2bit", "grid", "f32"])
 def test_kmup2_repeated_rows(tpod, storage):
     """KMUP2 with repeats in Use -- wgr(bag, rp = TRUE) draws sort(sample(n, n*bag, TRUE)) (R/wgr.R:68): the reference's e0 / H hold
     a repeated row once per draw (Rcpp20260726ai.cpp:51-60), so H'e0, H'H and ||e||^2 count it that often while its residual stays
-    one value.  On the device: row multiplicities in the dot products of the small-n family.  (i) deterministic limit vs the oracle to
+    one value.  On the device: row multiplicities in the dot products of the small-n family (int8 / 2-bit store) and of the grid family
+    (any n; int8 or float32 store), where they ride in the mask bytes.  (i) deterministic limit vs the oracle to
     float rounding, the returned residual in the order of Use (repeats repeated); (ii) the indicator branch over 300 seeds; (iii) a
     row index outside X is an argument error."""
     y, gen = tpod
@@ -905,8 +906,8 @@ def test_kmup2_repeated_rows(tpod, storage):
     b0 = np.linspace(-0.01, 0.01, p)
     e = y - y.mean() - X @ b0
     L = np.full(p, 37.0)
-    kw = dict(storage=bw.STORE_2BIT) if storage == "2bit" else {}
-    with bw.Genotypes(gen, **kw) as g:
+    kw = {"2bit": dict(storage=bw.STORE_2BIT), "grid": dict(path=bw.PATH_GRID), "f32": dict(storage=bw.STORE_F32)}.get(storage, {})
+    with bw.Genotypes(X if storage == "f32" else gen, **kw) as g:
         ref = O.kmup2(X, use, b0, np.ones(p), xx, e, L, 1e-30, 0.0, seed=3)
         out = bw.KMUP2(g, use, b0, np.ones(p), xx, e, L, 1e-30, 0.0, seed=9)
         assert out["e"].shape == ref["e"].shape == (use.size,)
