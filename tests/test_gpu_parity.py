@@ -955,6 +955,27 @@ def test_wgr_bagged(tpod, mode, rp):
     assert np.isclose(gpu[0]["cxx"], ora[0]["cxx"])
 
 
+def test_wgr_bagged_rp_grid_family(tpod):
+    """wgr(bag = 0.5, rp = TRUE) on the grid family (what any n beyond one SM's shared memory runs on) and on the float32 store: the row
+    multiplicities of every iteration ride in the mask bytes -- posterior means vs the oracle within Monte-Carlo error."""
+    y, gen = tpod
+    X = gen.astype(np.float64)
+    kw = dict(pi=0.0, iv=False, rp=True)
+    seeds = range(6)
+    ora = [O.wgr(y, X, it=600, bi=200, seed=50 + s, ratio_form=True, bag=0.5, **kw) for s in seeds]
+    A = np.mean([r["hat"] for r in ora], 0)
+    A1 = np.mean([r["hat"] for r in ora[:3]], 0); A2 = np.mean([r["hat"] for r in ora[3:]], 0)
+    for store in (dict(path=bw.PATH_GRID), dict(storage=bw.STORE_F32)):
+        with bw.Genotypes(X if "storage" in store else gen, **store) as g:
+            gpu = [bw.wgr(y, g, it=600, bi=200, seed=70 + s, bag=0.5, **kw) for s in seeds]
+        for key in ("mu", "Ve"):
+            a = np.array([r[key] for r in ora]); b = np.array([r[key] for r in gpu])
+            se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+            assert abs(a.mean() - b.mean()) <= 4 * se + 2e-2 * abs(a.mean()), (store, key, a.mean(), b.mean(), se)
+        B = np.mean([r["hat"] for r in gpu], 0)
+        assert np.corrcoef(A, B)[0, 1] > min(0.99, np.corrcoef(A1, A2)[0, 1] - 0.005), store
+
+
 def test_wgr_polygenic_term_and_missing_values(tpod):
     """wgr(eigK = eigen(K)) (R/wgr.R:23-33, :74-84, :116-119, :124, :145-150): one Kuo-Mallick sweep over the leading eigenvectors of a
     kernel (real-valued: the float32 store) and one over the markers per iteration, both through the device KMUP entry point, the
