@@ -217,8 +217,12 @@ def run_reference(args, rank, world):
             "value": val, "unit": "marker-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s Gauss-Seidel sweep, synthetic n=%d x p=%d genotypes, k=1" % (args.model, args.n, args.p),
-                       "note": "per-marker cost is independent of p; CPU times a bounded marker sample at full n"},
+            # the same workload string and seed as the B200 arm's line (the driver compares the two configs)
+            "config": {"workload": "%s Gauss-Seidel sweep, synthetic n=%d x p=%d int8 genotypes, k=1" % (args.model, args.n, args.p),
+                       "step": "one full sweep = p marker updates (the reference's per-marker loop, src/Rcpp20260726ai.cpp:308-354)",
+                       "parallelism": "1 host thread", "seed": SEED,
+                       "note": "reference arm: the CPU loop (1 host thread; the reference's Gauss-Seidel loop is sequential and single-threaded) "
+                               "on a bounded marker sample at full n -- per-marker cost is independent of p"},
             "cpu_baseline": {"value": val, "unit": "marker-updates/s", "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "marker-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
