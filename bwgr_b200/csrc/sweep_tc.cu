@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(SweepArgs a) {
         const int jj = 32 * t + lane;
         const bool valid = jj < nvalid && !Sy.done;
         const int q = valid ? __float2int_rn(de[t] * dqinv) : 0;
-        const float deq = (float)q * dq;  // the step actually applied to E (exactly representable)
+        const float deq = (float)q * dq;  // the step actually applied to E, rounded to float (a 31-bit q keeps its leading 24 bits; the residual update uses the same q, so b and E stay consistent to that rounding)
         int l0, l1, l2, l3;
         split_limbs(q, l0, l1, l2, l3);
         DL[sw128_off(4 * s + 0, jj)] = (unsigned char)l0; DL[sw128_off(4 * s + 1, jj)] = (unsigned char)l1;

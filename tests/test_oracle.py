@@ -342,3 +342,25 @@ def test_two_design_oracle_matches_reference_executed_golden(tpod):
             ref = g[tag + "__" + key]
             assert np.abs(np.asarray(r[key]) - ref).max() <= 1e-3 * max(np.abs(ref).max(), 1e-30), (tag, key)
 
+
+
+def test_kmup2_repeated_rows_equal_replicated_rows(tpod):
+    """KMUP2 on a Use with repeats (what wgr(bag, rp = TRUE) passes, R/wgr.R:68) is the sweep over a matrix that physically holds every
+    repeated row once per draw (Rcpp20260726ai.cpp:51-60 builds exactly that H / e0): the same arithmetic in the same order, equal up to the
+    float rounding of xx(j) * bg (bg differs between the two calls and is folded into xx)."""
+    y, X = tpod
+    n, p = X.shape
+    rng = np.random.default_rng(21)
+    use = np.sort(rng.integers(0, n, size=int(0.7 * n)))
+    assert np.unique(use).size < use.size
+    Xr = np.asfortranarray(X[use])
+    b0 = rng.normal(size=p) * 0.01
+    E = y - y.mean() - X @ b0
+    xx = (X * X).sum(0) * (use.size / n)
+    L = np.full(p, 40.0)
+    for pi in (0.0, 0.3):
+        a = O.kmup2(X, use.astype(np.float64), b0, np.ones(p), xx, E, L, 0.03, pi, seed=5)
+        # the replicated matrix has n0 = nuse rows, so bg = 1 there: hand it xx * (n / nuse) to keep the same denominators
+        r = O.kmup2(Xr, np.arange(use.size, dtype=np.float64), b0, np.ones(p), xx * np.float32(n / use.size), E[use], L, 0.03, pi, seed=5)
+        assert np.array_equal(a["d"], r["d"])
+        assert np.abs(a["b"] - r["b"]).max() <= 2e-6 * np.abs(a["b"]).max() and np.abs(a["e"] - r["e"]).max() <= 2e-6 * np.abs(a["e"]).max()
