@@ -913,6 +913,12 @@ def test_kmup2_repeated_rows(tpod, storage):
         assert out["e"].shape == ref["e"].shape == (use.size,)
         assert np.abs(out["b"] - ref["b"]).max() <= RTOL * np.abs(ref["b"]).max()
         assert np.abs(out["e"] - ref["e"]).max() <= RTOL * np.abs(ref["e"]).max()
+        if storage == "i8":  # the same sweep over a store that physically holds a repeated row once per draw (distinct rows, bg folded into xx)
+            ui = use.astype(int)
+            with bw.Genotypes(np.ascontiguousarray(gen[ui])) as gr:
+                rep = bw.KMUP2(gr, np.arange(use.size, dtype=np.float64), b0, np.ones(p), xx * np.float32(n / use.size), e[ui], L, 1e-30, 0.0, seed=9)
+            assert np.abs(out["b"] - rep["b"]).max() <= RTOL * np.abs(rep["b"]).max()
+            assert np.abs(out["e"] - rep["e"]).max() <= RTOL * np.abs(rep["e"]).max()
         Ve, pi, reps = 0.03, 0.4, 300
         L = np.full(p, 80.0)
         A = [O.kmup2(X, use, b0, np.ones(p), xx, e, L, Ve, pi, seed=1000 + s, ratio_form=True) for s in range(reps)]
