@@ -1136,25 +1136,20 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
                 const float gnext = i < 31 ? __shfl_sync(0xffffffffu, g[t], i + 1) : __shfl_sync(0xffffffffu, g[t < 3 ? t + 1 : 3], 0);
                 const float Gnext = i < 31 ? Gb[(size_t)tri(t, t) * kTileF + i * kTS + i + 1] : Gb[(size_t)tri(t < 3 ? t + 1 : 3, t) * kTileF + i * kTS];
                 RuleOut ro;
-                if (kSlabDraw && MODEL == M_KMUP) {
-                  // q = (b2 - b1) (xx (b1 + b2 - 2 b0) - 2 g), b1 = a g + c: both factors are affine in g.  C times the second one's
-                  // coefficients were formed with the marker's other inputs one block ahead (dr.z1 = P, dr.chi = Q; KMUP draws no
-                  // chi-square), so the chain per marker is g -> two FMAs side by side -> multiply -> compare -> select -> FMA.
-                  const float b2 = dr.z2;
-                  const bool take = fmaf(gc, -in.a, b2 - in.c) * fmaf(gc, dr.z1, dr.chi) < dr.u;  // C q < threshold
+                if (kSlabDraw) {
+                  // ||e2||^2 - ||e1||^2 in closed form: KMUP and BayesDpi (:953-955) compare the two draws, BayesB/C the draw against
+                  // b = 0 (:673):   q = (b2 - b1) (xx (b1 + b2 - 2 b0) - 2 g)   resp.   q = b1 (xx (2 b0 - b1) + 2 g),   b1 = a g + c.
+                  // Both factors are affine in g.  C times the second one's coefficients were formed with the marker's other inputs one
+                  // block ahead (P in dr.z1; Q in dr.chi, or in in.vbj for the rules that draw a chi-square and recompute vbj), so the
+                  // chain per marker is g -> two FMAs side by side -> multiply -> compare -> select the step -> FMA into the next g.
+                  // (Forming P and Q inside this loop instead was measured slower: the chain's warp is issue-bound too.)
+                  constexpr bool kTwoDraws = MODEL == M_KMUP || MODEL == M_BDPI, kChi = MODEL == M_BB || MODEL == M_BDPI;
+                  const float b2 = dr.z2, b1 = fmaf(gc, in.a, in.c);
+                  const float f1 = kTwoDraws ? fmaf(gc, -in.a, b2 - in.c) : b1;
+                  const bool take = f1 * fmaf(gc, dr.z1, kChi ? in.vbj : dr.chi) < dr.u;  // C q < threshold
                   ro.de = take ? fmaf(gc, in.a, in.c - in.b0) : b2 - in.b0;
-                  ro.b = take ? fmaf(gc, in.a, in.c) : b2; ro.d = take ? 1.0f : 0.0f;
-                  ro.vbj = in.vbj;
-                } else if (kSlabDraw) {
-                  const float xxj = xxj_, b1 = fmaf(gc, in.a, in.c), b2 = dr.z2;
-                  // ||e2||^2 - ||e1||^2 in closed form: BayesB/C compare the draw against b = 0 (:673), BayesDpi (:953-955) the two
-                  // draws, with its own acceptance threshold folded into dr.u
-                  const float q = MODEL == M_BDPI ? (b2 - b1) * fmaf(xxj, (b1 + b2) - 2.0f * in.b0, -2.0f * gc)
-                                                  : b1 * fmaf(xxj, 2.0f * in.b0 - b1, 2.0f * gc);
-                  const bool take = Sy.C * q < dr.u;
                   ro.b = take ? b1 : b2; ro.d = take ? 1.0f : 0.0f;
-                  ro.de = ro.b - in.b0;
-                  ro.vbj = (MODEL == M_BB || MODEL == M_BDPI) ? (Sy.Sb + ro.b * ro.b) / dr.chi : in.vbj;
+                  ro.vbj = kChi ? (Sy.Sb + ro.b * ro.b) / dr.chi : in.vbj;
                 } else if (kSlabEM) {
                   const float xxj = xxj_, b1 = fmaf(gc, in.a, in.c);
                   const float LR = Sy.Pi0 * expf(Sy.C * (b1 * fmaf(xxj, 2.0f * in.b0 - b1, 2.0f * gc)));
@@ -1403,9 +1398,13 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
               // accept b1 iff C*q < this.  BayesDpi: u < min(1, (1-pi) exp(-C q))  <=>  C q < log((1-pi)/u)
               if (MODEL == M_BDPI) dr.u = logf((1.0f - sc[s].Pi) / dr.u);
               else dr.u = (MODEL == M_KMUP && !(sc[s].pi_mix > 0.0f)) ? 3.0e38f : logf((1.0f / dr.u - 1.0f) / ratio);
-              if (MODEL == M_KMUP) {  // C (xx (b1 + b2 - 2 b0) - 2 g) = P g + Q  (the chain's second factor)
-                dr.z1 = sc[s].C * fmaf(mcv.xx, ia, -2.0f);
-                dr.chi = sc[s].C * (mcv.xx * ((in.c + dr.z2) - 2.0f * in.b0));
+              {  // the chain's second factor times C as P g + Q (see the chain): C (xx (b1 + b2 - 2 b0) - 2 g) resp. C (xx (2 b0 - b1) + 2 g)
+                const bool two = MODEL == M_KMUP || MODEL == M_BDPI;
+                const float P = sc[s].C * (two ? fmaf(mcv.xx, ia, -2.0f) : fmaf(-mcv.xx, ia, 2.0f));
+                const float Q = sc[s].C * (mcv.xx * (two ? (in.c + dr.z2) - 2.0f * in.b0 : 2.0f * in.b0 - in.c));
+                dr.z1 = P;
+                if (MODEL == M_BB || MODEL == M_BDPI) in.vbj = Q;  // these rules recompute vbj from their chi-square draw
+                else dr.chi = Q;                                   // KMUP, BayesC: no chi-square draw per marker
               }
               drw[((size_t)slot * ns + s) * 128 + ht] = dr;
             }
