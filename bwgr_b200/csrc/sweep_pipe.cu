@@ -1119,7 +1119,8 @@ __global__ void __launch_bounds__(kT, 1) sweep_pipe_kernel(PipeArgs a) {
             float xx_n = mc[0].xx;
 #pragma unroll
             for (int t = 0; t < 4; t++) {
-#pragma unroll 8
+              // unroll measured on wgr BayesB at 10k x 50k (profiles/r2_wgr_bayesb_fold_variants.txt): 4 -> 2.93, 8 -> 2.54, 16 -> 2.47, 32 -> 3.8 ms
+#pragma unroll (MODEL == M_KMUP ? 16 : 8)
               for (int i = 0; i < 32; i++) {
                 const int jj = 32 * t + i;
                 const bool valid = jj < nvalid;
